@@ -1,0 +1,169 @@
+/*
+ * vis_b200.h — C ABI of the B200 inspection-frame preprocessing engine (libvis_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of Aditya-Somasi/Vision-Inspection-System:
+ *   inspection frame -> Qwen2-VL pixel_values / image_grid_thw, thumbnail/resize, defect overlay.
+ * Every entry point names the reference interface it replaces (file:line under the reference
+ * tree; `tf:` = transformers 5.5.0, `PIL:` = Pillow 12.2.0, `cv:` = OpenCV 4.13 drawing.cpp).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - return 0 on success, negative VIS_E_* on failure; vis_last_error() gives a thread-local text.
+ *   - functions marked [host] never touch the GPU; functions marked [device] enqueue work on the
+ *     given CUDA stream (a cudaStream_t passed as void*), never synchronise, never allocate:
+ *     every device buffer (inputs, outputs, tables, scratch) is owned by the caller.
+ *   - thread-safe: no global mutable state except the thread-local error string.
+ */
+#ifndef VIS_B200_H
+#define VIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIS_B200_ABI_VERSION 1
+
+/* status codes */
+#define VIS_OK            0
+#define VIS_E_INVALID    -1   /* bad argument */
+#define VIS_E_CUDA       -2   /* CUDA runtime error (text in vis_last_error) */
+#define VIS_E_UNSUPPORTED -3  /* geometry outside what the fast path handles; caller must use the generic path */
+#define VIS_E_CAPACITY   -4   /* caller-provided buffer too small */
+
+/* resampling filters (PIL:Image.py Resampling enum values are kept) */
+#define VIS_FILTER_LANCZOS 1  /* Image.Resampling.LANCZOS, support 3.0 — utils/image_utils.py:75, src/agents/vlm_inspector.py:64, src/agents/vlm_auditor.py:91 */
+#define VIS_FILTER_BICUBIC 3  /* Image.Resampling.BICUBIC, a=-0.5, support 2.0 — tf:image_transforms.py:367 */
+
+int         vis_abi_version(void);      /* [host] */
+const char* vis_last_error(void);       /* [host] thread-local, never NULL */
+
+/* ------------------------------------------------------------------------------------------
+ * Coefficient tables                                                              [host]
+ * Replaces Pillow's precompute_coeffs + normalize_coeffs_8bpc (libImaging/Resample.c), reached
+ * from Image.resize at utils/image_utils.py:75 and tf:image_transforms.py:367.
+ * IEEE double arithmetic, no FMA contraction, coefficients truncated to 22-bit fixed point.
+ * ------------------------------------------------------------------------------------------ */
+/* number of coefficient slots per output sample for (in_size -> out_size) */
+int vis_coeff_ksize(int in_size, int out_size, int filter);
+/* k[out_size*ksize] (zero padded), bounds[out_size*2] = (first input index, tap count) */
+int vis_build_coeffs(int in_size, int out_size, int filter, int32_t* k, int32_t* bounds, int* ksize_out);
+
+/* 768-entry normalisation table: lut[v*3+c] = (f32(f64(v)*rescale) - f32(mean[c])) / f32(std[c])
+ * Replaces tf:image_transforms.py:118-122 (rescale) + :427-439 (normalize) — exact because a
+ * uint8 input admits only 256x3 distinct results.                                  [host] */
+int vis_build_lut(const float mean[3], const float stdv[3], double rescale, float* lut768);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic (any geometry) device passes — one image per call.                      [device]
+ * Pillow ImagingResampleHorizontal_8bpc / ImagingResampleVertical_8bpc; the caller chooses the
+ * pass order exactly as PIL:Image.py:2431-2435 does (horizontal first unless the tall-image branch).
+ * src/dst: interleaved uint8, `channels` bytes per pixel, row pitches in bytes.
+ * k/bounds: device copies of the vis_build_coeffs tables.
+ * ------------------------------------------------------------------------------------------ */
+int vis_resample_h_u8(const uint8_t* src, int64_t src_pitch, int rows, int in_w, int channels,
+                      uint8_t* dst, int64_t dst_pitch, int out_w,
+                      const int32_t* k, const int32_t* bounds, int ksize, void* stream);
+int vis_resample_v_u8(const uint8_t* src, int64_t src_pitch, int in_h, int row_bytes,
+                      uint8_t* dst, int64_t dst_pitch, int out_h,
+                      const int32_t* k, const int32_t* bounds, int ksize, void* stream);
+
+/* resized RGB uint8 HWC [h,w,3] (h,w multiples of 28) -> rows [row0, row0 + (h/14)*(w/14)) of
+ * pixel_values [*,1176] f32 in Qwen2-VL patch order (tf:models/qwen2_vl/image_processing_pil_qwen2_vl.py:182-214):
+ * rescale+normalize through lut768, temporal duplicate (T=2), 14x14 patches, 2x2 merge order.  [device] */
+int vis_normalize_patchify(const uint8_t* src, int64_t src_pitch, int h, int w,
+                           const float* lut768, float* pixel_values, int64_t row0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused hot path: frame -> pixel_values in ONE launch for a whole batch.           [device]
+ * Replaces, per frame, tf:...image_processing_pil_qwen2_vl.py:164-214 (smart-resized bicubic resample,
+ * rescale, normalize, patchify).  Horizontal-then-vertical order only (VIS_E_UNSUPPORTED otherwise).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VisFrame {
+    const uint8_t* src;        /* device, RGB uint8 HWC, 16-byte aligned                          */
+    int64_t        src_pitch;  /* bytes per row, multiple of 16                                  */
+    int32_t        src_h, src_w;
+    int32_t        dst_h, dst_w;   /* smart_resize result, multiples of 28                       */
+    const int32_t* hrec;       /* device, packed horizontal records (vis_pack_records, dst_w+1)  */
+    const int32_t* vrec;       /* device, packed vertical records   (vis_pack_records, dst_h+1)  */
+    int64_t        row0;       /* first row of this frame in pixel_values                        */
+} VisFrame;
+
+typedef struct VisStrip {      /* one unit of work (one CTA): a column strip of one frame        */
+    int32_t frame;             /* index into frames[]                                            */
+    int32_t x0, x1;            /* output columns [x0,x1), multiples of 28                        */
+    int32_t y0, y1;            /* output rows    [y0,y1), multiples of 14                        */
+} VisStrip;
+
+/* largest tap count of a bounds table                                                 [host] */
+int vis_max_taps(const int32_t* bounds, int out_size);
+/* tap class the fused kernel is instantiated for (6, 8, 12, 16) or 0 if kt > 16        [host] */
+int vis_fused_kt_class(int kt);
+/* int32 slots per record for tap class kt                                              [host] */
+int vis_record_stride(int kt);
+/* pack a vis_build_coeffs table into push-order records: out_size+1 records (last = sentinel),
+ * each vis_record_stride(kt) int32: [0..kt) coefficients newest tap first (zero padded),
+ * [stride-2] = first, [stride-1] = last input index of the window.  Both tables of a frame must be
+ * packed with the same kt = vis_fused_kt_class(max taps of both).                      [host] */
+int vis_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt,
+                     int32_t* rec, int64_t rec_capacity);
+/* VIS_OK if the fused kernel can take this geometry (alignment, <= 16 taps, horizontal-first order),
+ * else VIS_E_UNSUPPORTED: use the generic passes                                        [host] */
+int vis_fused_supported(int64_t src_addr, int64_t src_pitch, int src_h, int src_w,
+                        int dst_h, int dst_w, int hkt, int vkt);
+/* upper bound of strips vis_plan_strips emits for one frame                            [host] */
+int vis_plan_strips_max(int dst_h, int dst_w);
+/* split one frame into column strips x `vsplit` row segments; hbounds = HOST horizontal bounds table,
+ * kt = max taps of both axes.  Returns the strip count; *span_bytes_out / *strip_w_out receive the widest
+ * staged input span and strip width (they size the launch's shared memory).            [host] */
+int vis_plan_strips(int frame_index, int dst_h, int dst_w, const int32_t* hbounds, int kt, int vsplit,
+                    VisStrip* strips, int capacity, int* span_bytes_out, int* strip_w_out);
+/* frames/strips: DEVICE arrays; every frame of one call shares the tap class of max_kt.
+ * max_span_bytes / max_strip_w: maxima of vis_plan_strips over the batch.              [device] */
+int vis_preprocess_fused(const VisFrame* frames, int n_frames, const VisStrip* strips, int n_strips,
+                         int max_kt, int max_span_bytes, int max_strip_w,
+                         const float* lut768, float* pixel_values, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Defect overlay rasteriser.
+ * Replaces the cv2 drawing calls of draw_bounding_boxes (utils/image_utils.py:259-313):
+ * cv2.rectangle/line (LINE_AA, thickness 2), cv2.circle (filled, and thickness 3), cv2.putText
+ * (FONT_HERSHEY_SIMPLEX).  The host expands validated pixel boxes into an ORDERED list of leaf
+ * primitives (cv: ThickLine/PolyLine/EllipseEx/FillConvexPoly/LineAA/Line2/Circle/putText) and
+ * the device applies them per pixel in list order, which reproduces OpenCV's sequential result.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VisBox {        /* a box AFTER the reference's validation + percent->pixel conversion (utils/image_utils.py:200-237) */
+    int32_t x, y, w, h;        /* pixels                                                         */
+    uint8_t b, g, r;           /* BGR colour (utils/image_utils.py:250-252)                       */
+    uint8_t dashed;            /* 1 iff confidence == "low" (utils/image_utils.py:257)            */
+    char    label[12];         /* NUL-terminated text drawn in the marker ('#' already removed)   */
+} VisBox;
+
+#define VIS_LEAF_WORDS 12
+typedef struct VisLeaf { int32_t w[VIS_LEAF_WORDS]; } VisLeaf;   /* opaque 48-byte leaf primitive */
+
+/* expand the boxes of ONE frame into its leaf array: n_boxes group headers (one per box: leaf range +
+ * bounding box, indices relative to the start of this array) followed by the ordered leaves.
+ * Returns the leaf count, or VIS_E_CAPACITY with *needed = required count (call again with a larger buffer),
+ * or VIS_E_UNSUPPORTED for a label character outside the built-in Hershey digits.     [host] */
+int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int n_boxes,
+                       VisLeaf* leaves, int capacity, int* needed);
+
+typedef struct VisOverlayFrame {
+    const uint8_t* src;        /* device BGR uint8 HWC                                           */
+    uint8_t*       dst;        /* device BGR uint8 HWC; may equal src (in place)                 */
+    int64_t        src_pitch, dst_pitch;
+    int32_t        h, w;
+    int32_t        group_begin, group_end;   /* this frame's group headers in leaves[]; its leaf array starts at group_begin */
+} VisOverlayFrame;
+
+/* frames / leaves: DEVICE arrays. One launch draws every frame of the batch (<= 65535 frames).
+ * Out of place (dst != src) every pixel is written; in place only tiles a box touches.  [device] */
+int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int max_h, int max_w,
+                     const VisLeaf* leaves, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIS_B200_H */

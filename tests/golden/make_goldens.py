@@ -1,0 +1,206 @@
+"""Generates tests/golden/goldens.json + arrays.npz from the REAL reference and its dependencies.
+
+Run in the build container only (needs /root/reference, Pillow, opencv, transformers):
+
+    python tests/golden/make_goldens.py
+
+What is recorded (versions of every binary are stored next to the vectors):
+  * ``qwen``       Qwen2VLImageProcessorPil (transformers, PIL backend) outputs — grid_thw, sha256 of pixel_values,
+                   three sample rows — for seeded frames, pattern frames, Mouri.jpg and edge geometries.
+  * ``thumbnail``  PIL ``Image.thumbnail(LANCZOS)`` as called by ``_encode_image_optimized`` (src/agents/*.py) and the
+                   reference's own ``utils.image_utils.resize_image`` — sha256 of the resized bytes.
+  * ``overlay``    the reference's own ``utils.image_utils.draw_bounding_boxes`` executed unmodified, with
+                   ``cv2.imread`` / ``cv2.imwrite`` intercepted so the BGR array it holds right before the
+                   JPEG encode is captured — sha256 + changed-pixel count.
+The reference has no tests or vectors of its own for this path; these fixtures are the pin.
+"""
+from __future__ import annotations
+
+import hashlib
+import importlib
+import json
+import os
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+REFERENCE = Path("/root/reference")
+sys.path.insert(0, str(REPO))
+
+from vision_inspection_system_b200 import synth  # noqa: E402  (seeded workload definitions, numpy only)
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def import_reference_image_utils():
+    """Import /root/reference/utils/image_utils.py unmodified (colorlog shim, dummy key, temp cwd)."""
+    shim = types.ModuleType("colorlog")
+    import logging
+
+    class ColoredFormatter(logging.Formatter):
+        def __init__(self, fmt=None, datefmt=None, *a, **k):
+            super().__init__("%(message)s", datefmt)
+
+    shim.ColoredFormatter = ColoredFormatter
+    shim.StreamHandler = logging.StreamHandler
+    sys.modules.setdefault("colorlog", shim)
+    os.environ.setdefault("HUGGINGFACE_API_KEY", "hf_dummy_key_for_goldens_0000000000")
+    tmp = tempfile.mkdtemp(prefix="ref_cwd_")
+    os.chdir(tmp)                       # utils/config.py creates uploads/ reports/ logs/ at import
+    sys.path.insert(0, str(REFERENCE))
+    return importlib.import_module("utils.image_utils")
+
+
+def qwen_cases():
+    pats = synth.pattern_frames(1080, 1920)
+    small = synth.pattern_frames(140, 252)
+    cases = [
+        ("noise_1080p_seed1234", synth.noise_frame(1234, 1080, 1920), None),
+        ("noise_1080p_seed1235", synth.noise_frame(1235, 1080, 1920), None),
+        ("noise_1080p_seed1234_hub", synth.noise_frame(1234, 1080, 1920), 12845056),
+        ("noise_4k_seed4000", synth.noise_frame(4000, 2160, 3840), None),
+        ("noise_720p_seed1", synth.noise_frame(1, 720, 1280), None),
+        ("noise_480p_seed2", synth.noise_frame(2, 480, 640), None),
+        ("noise_2048x1536_seed3", synth.noise_frame(3, 1536, 2048), None),
+        ("noise_thumb2048_seed4", synth.noise_frame(4, 1152, 2048), None),
+        ("noise_thumb1024_seed5", synth.noise_frame(5, 576, 1024), None),
+        ("noise_odd_333x517_seed6", synth.noise_frame(6, 333, 517), None),
+        ("noise_tall_3000x20_seed7", synth.noise_frame(7, 3000, 20), None),
+        ("noise_wide_20x3000_seed8", synth.noise_frame(8, 20, 3000), None),
+        ("noise_tiny_10x10_seed9", synth.noise_frame(9, 10, 10), None),
+        ("noise_1x1_seed10", synth.noise_frame(10, 1, 1), None),
+        ("noise_56x56_seed11", synth.noise_frame(11, 56, 56), None),
+        ("noise_small_64x96_seed12", synth.noise_frame(12, 64, 96), None),
+    ]
+    cases += [(f"pattern_{k}_1080p", v, None) for k, v in pats.items()]
+    cases += [(f"pattern_{k}_140x252", v, None) for k, v in small.items()]
+    return cases
+
+
+def main():
+    import cv2
+    import PIL
+    import transformers
+    from PIL import Image
+    from transformers.models.qwen2_vl.image_processing_pil_qwen2_vl import Qwen2VLImageProcessorPil
+
+    out = {"versions": {"pillow": PIL.__version__, "opencv": cv2.__version__, "transformers": transformers.__version__,
+                        "numpy": np.__version__}, "qwen": [], "thumbnail": [], "overlay": []}
+    arrays = {}
+
+    # ---------------- Mouri.jpg (BASELINE config 1) ----------------
+    mouri = np.asarray(Image.open(REFERENCE / "Mouri.jpg").convert("RGB"))
+    arrays["mouri_rgb"] = mouri
+
+    # ---------------- qwen ----------------
+    def run_proc(frame, max_pixels):
+        proc = Qwen2VLImageProcessorPil() if max_pixels is None else Qwen2VLImageProcessorPil(
+            size={"shortest_edge": 56 * 56, "longest_edge": max_pixels})
+        r = proc(images=[Image.fromarray(frame)], return_tensors="np")
+        return r["pixel_values"], r["image_grid_thw"]
+
+    for name, frame, max_pixels in [("mouri", mouri, None)] + qwen_cases():
+        pv, grid = run_proc(frame, max_pixels)
+        n = pv.shape[0]
+        rows = sorted({0, n // 2, n - 1})
+        out["qwen"].append({
+            "name": name, "shape": list(frame.shape[:2]), "input_sha256": sha(frame),
+            "max_pixels": max_pixels, "grid_thw": grid[0].tolist(), "rows": n, "sha256": sha(pv),
+            "min": float(pv.min()), "max": float(pv.max()), "sample_rows": rows})
+        arrays[f"qwen_{name}_samples"] = pv[rows]
+        if pv.nbytes <= 200_000:
+            arrays[f"qwen_{name}_full"] = pv
+        print("qwen", name, grid[0].tolist(), sha(pv)[:16])
+
+    # ---------------- thumbnails / resize_image ----------------
+    ref = import_reference_image_utils()
+    for name, frame, limit in [
+        ("thumb_4k_to_2048", synth.noise_frame(20, 2160, 3840), 2048),
+        ("thumb_4k_to_1024", synth.noise_frame(21, 2160, 3840), 1024),
+        ("thumb_1080p_to_1024", synth.noise_frame(22, 1080, 1920), 1024),
+        ("thumb_portrait_1600x1200_to_1024", synth.noise_frame(23, 1600, 1200), 1024),
+        ("thumb_2048x1536_to_1024", synth.noise_frame(24, 1536, 2048), 1024),
+        ("thumb_small_300x500_to_256", synth.noise_frame(25, 300, 500), 256),
+    ]:
+        im = Image.fromarray(frame)
+        im.thumbnail((limit, limit), Image.Resampling.LANCZOS)      # exactly the agents' call
+        t = np.asarray(im)
+        rz = np.asarray(ref.resize_image(Image.fromarray(frame), limit))   # the reference's own function
+        out["thumbnail"].append({"name": name, "shape": list(frame.shape[:2]), "seed": int(name and 0),
+                                 "limit": limit, "thumb_size": [im.size[0], im.size[1]], "thumb_sha256": sha(t),
+                                 "resize_image_size": [rz.shape[1], rz.shape[0]], "resize_image_sha256": sha(rz)})
+        if t.nbytes <= 200_000:
+            arrays[f"thumb_{name}_full"] = t
+        print("thumb", name, im.size, sha(t)[:16], rz.shape, sha(rz)[:16])
+    seeds = {"thumb_4k_to_2048": 20, "thumb_4k_to_1024": 21, "thumb_1080p_to_1024": 22,
+             "thumb_portrait_1600x1200_to_1024": 23, "thumb_2048x1536_to_1024": 24, "thumb_small_300x500_to_256": 25}
+    for rec in out["thumbnail"]:
+        rec["seed"] = seeds[rec["name"]]
+
+    # ---------------- overlay: the reference function itself ----------------
+    captured = {}
+    real_imread, real_imwrite = ref.cv2.imread, ref.cv2.imwrite
+
+    def fake_imread(path, *a):
+        return captured["input"].copy()
+
+    def fake_imwrite(path, img, *a):
+        captured["output"] = img.copy()
+        return True
+
+    def run_ref(frame, boxes, thr="low", crit="medium"):
+        captured["input"] = frame
+        ref.cv2.imread, ref.cv2.imwrite = fake_imread, fake_imwrite
+        try:
+            ref.draw_bounding_boxes(Path("in.png"), boxes, Path("out.jpg"), thr, crit)
+        finally:
+            ref.cv2.imread, ref.cv2.imwrite = real_imread, real_imwrite
+        return captured["output"]
+
+    overlay_cases = []
+    for i in range(6):
+        frame, boxes = synth.annotated_frame(7000 + i)
+        overlay_cases.append((f"cfg4_seed{7000 + i}", 7000 + i, (1080, 1920), boxes, "low", "medium"))
+    for i in range(6):
+        frame, boxes = synth.annotated_frame(7100 + i, 480, 640)
+        overlay_cases.append((f"vga_seed{7100 + i}", 7100 + i, (480, 640), boxes, "low", "medium"))
+    frame, boxes = synth.annotated_frame(7200, 2160, 3840)
+    overlay_cases.append(("uhd_seed7200", 7200, (2160, 3840), boxes, "low", "medium"))
+    edge = [
+        {"x": 0, "y": 0, "width": 30, "height": 30, "label": "#10", "confidence": "low"},
+        {"x": 70, "y": 60, "width": 30, "height": 40, "label": "#12", "severity": "COSMETIC", "confidence": "low"},
+        {"x": 60.0, "y": 70.0, "width": 40.0, "height": 30.0, "label": "#3"},
+        {"x": 99.5, "y": 99.5, "width": 0.5, "height": 0.5, "label": "#4"},          # too small -> skipped
+        {"x": 10, "y": 10, "width": 95, "height": 20, "label": "#5"},                 # exceeds bounds -> skipped
+        {"x": 5, "y": 50, "width": 90, "height": 60, "label": "#6"},                  # exceeds / too large -> skipped
+        {"x": -1, "y": 5, "width": 10, "height": 10, "label": "#7"},                  # invalid -> skipped
+        {"x": 45.5, "y": 2.2, "width": 3.3, "height": 3.1, "label": "#8", "severity": "CRITICAL", "confidence": "high"},
+        {"x": 2, "y": 80, "width": 20, "height": 20, "confidence": "medium"},         # default label from index
+    ]
+    for shape, tag in (((1080, 1920), "1080p"), ((480, 640), "vga"), ((2160, 3840), "uhd"), ((333, 517), "odd")):
+        overlay_cases.append((f"edge_{tag}", 7300, shape, edge, "low", "medium"))
+    overlay_cases.append(("edge_1080p_thr_medium", 7300, (1080, 1920), edge, "medium", "medium"))
+    overlay_cases.append(("edge_1080p_thr_high_crit_high", 7300, (1080, 1920), edge, "high", "high"))
+    overlay_cases.append(("edge_1080p_thr_high", 7300, (1080, 1920), edge, "high", "low"))
+    for name, seed, shape, boxes, thr, crit in overlay_cases:
+        frame = np.random.default_rng(seed).integers(0, 256, (*shape, 3), dtype=np.uint8)
+        res = run_ref(frame, boxes, thr, crit)
+        out["overlay"].append({"name": name, "seed": seed, "shape": list(shape), "boxes": boxes,
+                               "confidence_threshold": thr, "criticality": crit, "sha256": sha(res),
+                               "changed_pixels": int((res != frame).any(2).sum())})
+        print("overlay", name, sha(res)[:16], out["overlay"][-1]["changed_pixels"])
+
+    (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
+    np.savez_compressed(HERE / "arrays.npz", **arrays)
+    print("wrote", HERE / "goldens.json", HERE / "arrays.npz")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,120 @@
+"""ctypes binding of libvis_b200.so — the C ABI declared in include/vis_b200.h.
+
+There is no CPU fallback: if the library is missing the import of anything that needs it raises, and every
+device entry point requires CUDA pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libvis_b200.so"
+
+VIS_OK = 0
+VIS_E_INVALID = -1
+VIS_E_CUDA = -2
+VIS_E_UNSUPPORTED = -3
+VIS_E_CAPACITY = -4
+
+FILTER_LANCZOS = 1
+FILTER_BICUBIC = 3
+
+LEAF_WORDS = 12
+
+# struct layouts of include/vis_b200.h as numpy dtypes (C alignment)
+FRAME_DTYPE = np.dtype([
+    ("src", np.uint64), ("src_pitch", np.int64),
+    ("src_h", np.int32), ("src_w", np.int32), ("dst_h", np.int32), ("dst_w", np.int32),
+    ("hrec", np.uint64), ("vrec", np.uint64), ("row0", np.int64)], align=True)
+STRIP_DTYPE = np.dtype([("frame", np.int32), ("x0", np.int32), ("x1", np.int32), ("y0", np.int32), ("y1", np.int32)],
+                       align=True)
+BOX_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("w", np.int32), ("h", np.int32),
+                      ("b", np.uint8), ("g", np.uint8), ("r", np.uint8), ("dashed", np.uint8),
+                      ("label", "S12")], align=True)
+LEAF_DTYPE = np.dtype([("w", np.int32, (LEAF_WORDS,))], align=True)
+OVERLAY_FRAME_DTYPE = np.dtype([
+    ("src", np.uint64), ("dst", np.uint64), ("src_pitch", np.int64), ("dst_pitch", np.int64),
+    ("h", np.int32), ("w", np.int32), ("group_begin", np.int32), ("group_end", np.int32)], align=True)
+
+assert FRAME_DTYPE.itemsize == 56 and STRIP_DTYPE.itemsize == 20 and BOX_DTYPE.itemsize == 32
+assert LEAF_DTYPE.itemsize == 48 and OVERLAY_FRAME_DTYPE.itemsize == 48
+
+EXPORTS = [
+    "vis_abi_version", "vis_last_error", "vis_coeff_ksize", "vis_build_coeffs", "vis_build_lut",
+    "vis_resample_h_u8", "vis_resample_v_u8", "vis_normalize_patchify",
+    "vis_max_taps", "vis_fused_kt_class", "vis_record_stride", "vis_pack_records", "vis_fused_supported",
+    "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
+    "vis_overlay_expand", "vis_overlay_draw",
+]
+
+
+class VisError(RuntimeError):
+    def __init__(self, code: int, where: str, text: str):
+        super().__init__(f"{where} failed ({code}): {text}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python {PKG_DIR / 'build.py'}` (nvcc, sm_100a). "
+                "This engine has no CPU fallback.")
+        L = C.CDLL(os.fspath(LIB_PATH))
+        _declare(L)
+        if L.vis_abi_version() != 1:
+            raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
+        _lib = L
+    return _lib
+
+
+def _declare(L: C.CDLL) -> None:
+    i32p, f32p, vp = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p
+    ip = C.POINTER(C.c_int)
+    L.vis_abi_version.restype = C.c_int
+    L.vis_last_error.restype = C.c_char_p
+    L.vis_coeff_ksize.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.vis_build_coeffs.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, ip]
+    L.vis_build_lut.argtypes = [f32p, f32p, C.c_double, f32p]
+    L.vis_resample_h_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int,
+                                    vp, vp, C.c_int, vp]
+    L.vis_resample_v_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int64, C.c_int, vp, vp, C.c_int, vp]
+    L.vis_normalize_patchify.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, vp, C.c_int64, vp]
+    L.vis_max_taps.argtypes = [i32p, C.c_int]
+    L.vis_fused_kt_class.argtypes = [C.c_int]
+    L.vis_record_stride.argtypes = [C.c_int]
+    L.vis_pack_records.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, C.c_int64]
+    L.vis_fused_supported.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.vis_plan_strips_max.argtypes = [C.c_int, C.c_int]
+    L.vis_plan_strips.argtypes = [C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.c_int, vp, C.c_int, ip, ip]
+    L.vis_preprocess_fused.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
+    L.vis_overlay_draw.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    for name in EXPORTS:
+        if name != "vis_last_error":
+            getattr(L, name).restype = C.c_int
+
+
+def check(code: int, where: str) -> int:
+    if code < 0:
+        raise VisError(code, where, lib().vis_last_error().decode("utf-8", "replace"))
+    return code
+
+
+def i32ptr(a: np.ndarray):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def f32ptr(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_float))

@@ -1,0 +1,160 @@
+// vis_generic.cu — generic (any geometry, any filter) device passes of libvis_b200.so.
+//
+// These are the always-correct building blocks: one horizontal pass, one vertical pass, one
+// normalize+patchify pass, each a separate launch on one image.  They serve
+//   * resize_image / agent thumbnails (LANCZOS, uint8 out) — utils/image_utils.py:75,
+//     src/agents/vlm_inspector.py:64, src/agents/vlm_auditor.py:91;
+//   * geometries the fused kernel (vis_fused.cu) declines: > 16 taps, the tall-image vertical-first
+//     branch (PIL:Image.py:2431-2435), unaligned row pitches.
+// Arithmetic: Pillow ImagingResampleHorizontal_8bpc / ImagingResampleVertical_8bpc — int32 accumulate of
+// uint8 x 22-bit coefficients, +2^21, arithmetic >>22, clamp to 0..255, uint8 between the passes.
+#include "vis_internal.h"
+
+namespace {
+
+__device__ __forceinline__ uint8_t clip8(int acc) {
+    return (uint8_t)min(max(acc >> VIS_PRECISION_BITS, 0), 255);
+}
+
+// one thread = one output pixel (all channels); taps are contiguous pixels of the same row
+template <int CH>
+__global__ void __launch_bounds__(256)
+k_resample_h(const uint8_t* __restrict__ src, int64_t src_pitch, int rows,
+             uint8_t* __restrict__ dst, int64_t dst_pitch, int out_w,
+             const int32_t* __restrict__ k, const int32_t* __restrict__ bounds, int ksize) {
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xo >= out_w || y >= rows) return;
+    const int first = __ldg(bounds + 2 * xo), taps = __ldg(bounds + 2 * xo + 1);
+    const int32_t* kk = k + (size_t)xo * ksize;
+    const uint8_t* p = src + (size_t)y * src_pitch + (size_t)first * CH;
+    int acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 1 << (VIS_PRECISION_BITS - 1);
+    for (int t = 0; t < taps; ++t) {
+        const int w = __ldg(kk + t);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] += (int)p[t * CH + c] * w;
+    }
+    uint8_t* d = dst + (size_t)y * dst_pitch + (size_t)xo * CH;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) d[c] = clip8(acc[c]);
+}
+
+// one thread = VEC consecutive bytes of one output row; taps are the same bytes of consecutive source rows
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_resample_v(const uint8_t* __restrict__ src, int64_t src_pitch, int row_bytes,
+             uint8_t* __restrict__ dst, int64_t dst_pitch, int out_h,
+             const int32_t* __restrict__ k, const int32_t* __restrict__ bounds, int ksize) {
+    const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const int yo = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xb >= row_bytes || yo >= out_h) return;
+    const int first = __ldg(bounds + 2 * yo), taps = __ldg(bounds + 2 * yo + 1);
+    const int32_t* kk = k + (size_t)yo * ksize;
+    int acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 1 << (VIS_PRECISION_BITS - 1);
+    const uint8_t* p = src + (size_t)first * src_pitch + xb;
+    if (VEC == 4) {
+        for (int t = 0; t < taps; ++t) {
+            const int w = __ldg(kk + t);
+            const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)t * src_pitch));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += (int)((q >> (8 * i)) & 0xff) * w;
+        }
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o |= (uint32_t)clip8(acc[i]) << (8 * i);
+        *reinterpret_cast<uint32_t*>(dst + (size_t)yo * dst_pitch + xb) = o;
+    } else {
+        for (int t = 0; t < taps; ++t) acc[0] += (int)p[(size_t)t * src_pitch] * __ldg(kk + t);
+        dst[(size_t)yo * dst_pitch + xb] = clip8(acc[0]);
+    }
+}
+
+// one thread = 4 consecutive floats (16 B) of one pixel_values row
+__global__ void __launch_bounds__(128)
+k_normalize_patchify(const uint8_t* __restrict__ src, int64_t src_pitch, int gw,
+                     const float* __restrict__ lut, float* __restrict__ out, int64_t row0, int n_rows) {
+    const int q = blockIdx.y * blockDim.x + threadIdx.x;      // 16-byte chunk inside the row
+    const int r = blockIdx.x;                                 // patch row of this frame
+    if (q >= VIS_ROW_FLOATS / 4 || r >= n_rows) return;
+    // invert row = ((bh*(gw/2) + bw)*2 + mh)*2 + mw   (tf:...pil_qwen2_vl.py:198-214)
+    const int mw = r & 1, mh = (r >> 1) & 1, blk = r >> 2;
+    const int bw = blk % (gw / 2), bh = blk / (gw / 2);
+    const int gy = bh * 2 + mh, gx = bw * 2 + mw;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int col = q * 4 + e;                            // col = ((c*2 + t)*14 + py)*14 + px
+        const int c = col / 392, rem = col % 392, in_plane = rem % 196;
+        const int py = in_plane / 14, px = in_plane % 14;
+        const uint8_t s = __ldg(src + (size_t)(gy * 14 + py) * src_pitch + (size_t)(gx * 14 + px) * 3 + c);
+        v[e] = __ldg(lut + (int)s * 3 + c);
+    }
+    *reinterpret_cast<float4*>(out + (size_t)(row0 + r) * VIS_ROW_FLOATS + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vis_resample_h_u8(const uint8_t* src, int64_t src_pitch, int rows, int in_w, int channels,
+                      uint8_t* dst, int64_t dst_pitch, int out_w,
+                      const int32_t* k, const int32_t* bounds, int ksize, void* stream) {
+    if (!src || !dst || !k || !bounds || rows <= 0 || in_w <= 0 || out_w <= 0 || ksize <= 0 ||
+        src_pitch < (int64_t)in_w * channels || dst_pitch < (int64_t)out_w * channels) {
+        vis::set_error("vis_resample_h_u8: bad arguments");
+        return VIS_E_INVALID;
+    }
+    dim3 block(64, 4), grid((out_w + 63) / 64, (rows + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (channels) {
+        case 1: k_resample_h<1><<<grid, block, 0, st>>>(src, src_pitch, rows, dst, dst_pitch, out_w, k, bounds, ksize); break;
+        case 2: k_resample_h<2><<<grid, block, 0, st>>>(src, src_pitch, rows, dst, dst_pitch, out_w, k, bounds, ksize); break;
+        case 3: k_resample_h<3><<<grid, block, 0, st>>>(src, src_pitch, rows, dst, dst_pitch, out_w, k, bounds, ksize); break;
+        case 4: k_resample_h<4><<<grid, block, 0, st>>>(src, src_pitch, rows, dst, dst_pitch, out_w, k, bounds, ksize); break;
+        default:
+            vis::set_error("vis_resample_h_u8: %d channels unsupported (1..4)", channels);
+            return VIS_E_INVALID;
+    }
+    return vis::check_launch("vis_resample_h_u8");
+}
+
+int vis_resample_v_u8(const uint8_t* src, int64_t src_pitch, int in_h, int row_bytes,
+                      uint8_t* dst, int64_t dst_pitch, int out_h,
+                      const int32_t* k, const int32_t* bounds, int ksize, void* stream) {
+    if (!src || !dst || !k || !bounds || in_h <= 0 || row_bytes <= 0 || out_h <= 0 || ksize <= 0 ||
+        src_pitch < row_bytes || dst_pitch < row_bytes) {
+        vis::set_error("vis_resample_v_u8: bad arguments");
+        return VIS_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (row_bytes % 4 == 0) && (src_pitch % 4 == 0) && (dst_pitch % 4 == 0) &&
+                     (((uintptr_t)src | (uintptr_t)dst) % 4 == 0);
+    dim3 block(64, 4);
+    if (vec) {
+        dim3 grid((row_bytes / 4 + 63) / 64, (out_h + 3) / 4);
+        k_resample_v<4><<<grid, block, 0, st>>>(src, src_pitch, row_bytes, dst, dst_pitch, out_h, k, bounds, ksize);
+    } else {
+        dim3 grid((row_bytes + 63) / 64, (out_h + 3) / 4);
+        k_resample_v<1><<<grid, block, 0, st>>>(src, src_pitch, row_bytes, dst, dst_pitch, out_h, k, bounds, ksize);
+    }
+    return vis::check_launch("vis_resample_v_u8");
+}
+
+int vis_normalize_patchify(const uint8_t* src, int64_t src_pitch, int h, int w,
+                           const float* lut768, float* pixel_values, int64_t row0, void* stream) {
+    if (!src || !lut768 || !pixel_values || h <= 0 || w <= 0 || h % 28 || w % 28 || src_pitch < (int64_t)w * 3 ||
+        row0 < 0 || ((uintptr_t)pixel_values % 16)) {
+        vis::set_error("vis_normalize_patchify: bad arguments (h=%d w=%d must be multiples of 28)", h, w);
+        return VIS_E_INVALID;
+    }
+    const int gh = h / VIS_PATCH, gw = w / VIS_PATCH, n_rows = gh * gw;
+    dim3 block(128), grid(n_rows, (VIS_ROW_FLOATS / 4 + 127) / 128);
+    k_normalize_patchify<<<grid, block, 0, (cudaStream_t)stream>>>(src, src_pitch, gw, lut768, pixel_values, row0, n_rows);
+    return vis::check_launch("vis_normalize_patchify");
+}
+
+}  // extern "C"

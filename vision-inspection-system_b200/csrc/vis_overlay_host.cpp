@@ -1,0 +1,597 @@
+// vis_overlay_host.cpp — host half of the defect-overlay rasteriser of libvis_b200.so.
+//
+// vis_overlay_expand turns the validated pixel boxes of one frame (utils/image_utils.py:229-257 of the
+// reference) into an ORDERED list of leaf primitives that reproduces, pixel for pixel, what the reference's
+// cv2 calls (utils/image_utils.py:259-313) draw sequentially:
+//     rectangle/line (thickness 2, LINE_AA) -> marker disc (filled) -> marker ring (thickness 3) -> label text.
+// The decomposition follows OpenCV 4.13 modules/imgproc/src/drawing.cpp (ThickLine, PolyLine, EllipseEx,
+// ellipse2Poly, FillConvexPoly, Circle, putText, getTextSize, clipLine); the device (vis_overlay.cu) only ever
+// sees four leaf kinds, each O(1) to evaluate at a pixel:
+//     LINE8   a clipped 8-connected fixed-point line        (cv: Line2)
+//     LINEAA  a clipped antialiased line, 8-bit coverage     (cv: LineAA)
+//     TRAP    rows [ya,yb] between two linear edge walkers   (cv: FillConvexPoly scan loop, one segment pair)
+//     SPANS   up to 16 rows of spans symmetric about cx      (cv: Circle, filled midpoint circle)
+// plus GROUP headers (bounding box + leaf range) that let a tile skip whole boxes.
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "vis_internal.h"
+#include "vis_overlay_leaf.h"
+
+namespace {
+
+constexpr int kShift = 16;
+constexpr int64_t kOne = 1 << kShift;
+constexpr int kLine8 = 8, kLineAA = 16;
+
+struct Pt { int64_t x, y; };
+
+// sine of whole degrees 0..450 as stored by OpenCV (7-decimal literals)
+const float kSin[451] = {
+    0.0000000f, 0.0174524f, 0.0348995f, 0.0523360f, 0.0697565f, 0.0871557f, 0.1045285f, 0.1218693f,
+    0.1391731f, 0.1564345f, 0.1736482f, 0.1908090f, 0.2079117f, 0.2249511f, 0.2419219f, 0.2588190f,
+    0.2756374f, 0.2923717f, 0.3090170f, 0.3255682f, 0.3420201f, 0.3583679f, 0.3746066f, 0.3907311f,
+    0.4067366f, 0.4226183f, 0.4383711f, 0.4539905f, 0.4694716f, 0.4848096f, 0.5000000f, 0.5150381f,
+    0.5299193f, 0.5446390f, 0.5591929f, 0.5735764f, 0.5877853f, 0.6018150f, 0.6156615f, 0.6293204f,
+    0.6427876f, 0.6560590f, 0.6691306f, 0.6819984f, 0.6946584f, 0.7071068f, 0.7193398f, 0.7313537f,
+    0.7431448f, 0.7547096f, 0.7660444f, 0.7771460f, 0.7880108f, 0.7986355f, 0.8090170f, 0.8191520f,
+    0.8290376f, 0.8386706f, 0.8480481f, 0.8571673f, 0.8660254f, 0.8746197f, 0.8829476f, 0.8910065f,
+    0.8987940f, 0.9063078f, 0.9135455f, 0.9205049f, 0.9271839f, 0.9335804f, 0.9396926f, 0.9455186f,
+    0.9510565f, 0.9563048f, 0.9612617f, 0.9659258f, 0.9702957f, 0.9743701f, 0.9781476f, 0.9816272f,
+    0.9848078f, 0.9876883f, 0.9902681f, 0.9925462f, 0.9945219f, 0.9961947f, 0.9975641f, 0.9986295f,
+    0.9993908f, 0.9998477f, 1.0000000f, 0.9998477f, 0.9993908f, 0.9986295f, 0.9975641f, 0.9961947f,
+    0.9945219f, 0.9925462f, 0.9902681f, 0.9876883f, 0.9848078f, 0.9816272f, 0.9781476f, 0.9743701f,
+    0.9702957f, 0.9659258f, 0.9612617f, 0.9563048f, 0.9510565f, 0.9455186f, 0.9396926f, 0.9335804f,
+    0.9271839f, 0.9205049f, 0.9135455f, 0.9063078f, 0.8987940f, 0.8910065f, 0.8829476f, 0.8746197f,
+    0.8660254f, 0.8571673f, 0.8480481f, 0.8386706f, 0.8290376f, 0.8191520f, 0.8090170f, 0.7986355f,
+    0.7880108f, 0.7771460f, 0.7660444f, 0.7547096f, 0.7431448f, 0.7313537f, 0.7193398f, 0.7071068f,
+    0.6946584f, 0.6819984f, 0.6691306f, 0.6560590f, 0.6427876f, 0.6293204f, 0.6156615f, 0.6018150f,
+    0.5877853f, 0.5735764f, 0.5591929f, 0.5446390f, 0.5299193f, 0.5150381f, 0.5000000f, 0.4848096f,
+    0.4694716f, 0.4539905f, 0.4383711f, 0.4226183f, 0.4067366f, 0.3907311f, 0.3746066f, 0.3583679f,
+    0.3420201f, 0.3255682f, 0.3090170f, 0.2923717f, 0.2756374f, 0.2588190f, 0.2419219f, 0.2249511f,
+    0.2079117f, 0.1908090f, 0.1736482f, 0.1564345f, 0.1391731f, 0.1218693f, 0.1045285f, 0.0871557f,
+    0.0697565f, 0.0523360f, 0.0348995f, 0.0174524f, 0.0000000f, -0.0174524f, -0.0348995f, -0.0523360f,
+    -0.0697565f, -0.0871557f, -0.1045285f, -0.1218693f, -0.1391731f, -0.1564345f, -0.1736482f, -0.1908090f,
+    -0.2079117f, -0.2249511f, -0.2419219f, -0.2588190f, -0.2756374f, -0.2923717f, -0.3090170f, -0.3255682f,
+    -0.3420201f, -0.3583679f, -0.3746066f, -0.3907311f, -0.4067366f, -0.4226183f, -0.4383711f, -0.4539905f,
+    -0.4694716f, -0.4848096f, -0.5000000f, -0.5150381f, -0.5299193f, -0.5446390f, -0.5591929f, -0.5735764f,
+    -0.5877853f, -0.6018150f, -0.6156615f, -0.6293204f, -0.6427876f, -0.6560590f, -0.6691306f, -0.6819984f,
+    -0.6946584f, -0.7071068f, -0.7193398f, -0.7313537f, -0.7431448f, -0.7547096f, -0.7660444f, -0.7771460f,
+    -0.7880108f, -0.7986355f, -0.8090170f, -0.8191520f, -0.8290376f, -0.8386706f, -0.8480481f, -0.8571673f,
+    -0.8660254f, -0.8746197f, -0.8829476f, -0.8910065f, -0.8987940f, -0.9063078f, -0.9135455f, -0.9205049f,
+    -0.9271839f, -0.9335804f, -0.9396926f, -0.9455186f, -0.9510565f, -0.9563048f, -0.9612617f, -0.9659258f,
+    -0.9702957f, -0.9743701f, -0.9781476f, -0.9816272f, -0.9848078f, -0.9876883f, -0.9902681f, -0.9925462f,
+    -0.9945219f, -0.9961947f, -0.9975641f, -0.9986295f, -0.9993908f, -0.9998477f, -1.0000000f, -0.9998477f,
+    -0.9993908f, -0.9986295f, -0.9975641f, -0.9961947f, -0.9945219f, -0.9925462f, -0.9902681f, -0.9876883f,
+    -0.9848078f, -0.9816272f, -0.9781476f, -0.9743701f, -0.9702957f, -0.9659258f, -0.9612617f, -0.9563048f,
+    -0.9510565f, -0.9455186f, -0.9396926f, -0.9335804f, -0.9271839f, -0.9205049f, -0.9135455f, -0.9063078f,
+    -0.8987940f, -0.8910065f, -0.8829476f, -0.8746197f, -0.8660254f, -0.8571673f, -0.8480481f, -0.8386706f,
+    -0.8290376f, -0.8191520f, -0.8090170f, -0.7986355f, -0.7880108f, -0.7771460f, -0.7660444f, -0.7547096f,
+    -0.7431448f, -0.7313537f, -0.7193398f, -0.7071068f, -0.6946584f, -0.6819984f, -0.6691306f, -0.6560590f,
+    -0.6427876f, -0.6293204f, -0.6156615f, -0.6018150f, -0.5877853f, -0.5735764f, -0.5591929f, -0.5446390f,
+    -0.5299193f, -0.5150381f, -0.5000000f, -0.4848096f, -0.4694716f, -0.4539905f, -0.4383711f, -0.4226183f,
+    -0.4067366f, -0.3907311f, -0.3746066f, -0.3583679f, -0.3420201f, -0.3255682f, -0.3090170f, -0.2923717f,
+    -0.2756374f, -0.2588190f, -0.2419219f, -0.2249511f, -0.2079117f, -0.1908090f, -0.1736482f, -0.1564345f,
+    -0.1391731f, -0.1218693f, -0.1045285f, -0.0871557f, -0.0697565f, -0.0523360f, -0.0348995f, -0.0174524f,
+    0.0000000f, 0.0174524f, 0.0348995f, 0.0523360f, 0.0697565f, 0.0871557f, 0.1045285f, 0.1218693f,
+    0.1391731f, 0.1564345f, 0.1736482f, 0.1908090f, 0.2079117f, 0.2249511f, 0.2419219f, 0.2588190f,
+    0.2756374f, 0.2923717f, 0.3090170f, 0.3255682f, 0.3420201f, 0.3583679f, 0.3746066f, 0.3907311f,
+    0.4067366f, 0.4226183f, 0.4383711f, 0.4539905f, 0.4694716f, 0.4848096f, 0.5000000f, 0.5150381f,
+    0.5299193f, 0.5446390f, 0.5591929f, 0.5735764f, 0.5877853f, 0.6018150f, 0.6156615f, 0.6293204f,
+    0.6427876f, 0.6560590f, 0.6691306f, 0.6819984f, 0.6946584f, 0.7071068f, 0.7193398f, 0.7313537f,
+    0.7431448f, 0.7547096f, 0.7660444f, 0.7771460f, 0.7880108f, 0.7986355f, 0.8090170f, 0.8191520f,
+    0.8290376f, 0.8386706f, 0.8480481f, 0.8571673f, 0.8660254f, 0.8746197f, 0.8829476f, 0.8910065f,
+    0.8987940f, 0.9063078f, 0.9135455f, 0.9205049f, 0.9271839f, 0.9335804f, 0.9396926f, 0.9455186f,
+    0.9510565f, 0.9563048f, 0.9612617f, 0.9659258f, 0.9702957f, 0.9743701f, 0.9781476f, 0.9816272f,
+    0.9848078f, 0.9876883f, 0.9902681f, 0.9925462f, 0.9945219f, 0.9961947f, 0.9975641f, 0.9986295f,
+    0.9993908f, 0.9998477f, 1.0000000f,
+};
+
+const unsigned char kSlopeCorr[32] = {181, 181, 181, 182, 182, 183, 184, 185, 187, 188, 190, 192, 194, 196, 198, 201,
+                                      203, 206, 209, 211, 214, 218, 221, 224, 227, 231, 235, 238, 242, 246, 250, 254};
+
+inline int round_half_even(double v) { return (int)std::lrint(v); }
+
+// Hershey simplex digit glyphs (g_HersheyGlyphs[700..709]); the reference only ever draws "#<int>" labels
+// with the '#' removed (src/reporting/pdf_generator.py:1303, utils/image_utils.py:240-242)
+const char* glyph_for(unsigned char ch) {
+    static const char* const digits[10] = {
+        "H\\QFNGLJKOKRLWNZQ[S[VZXWYRYOXJVGSFQF",
+        "H\\NJPISFS[",
+        "H\\LKLJMHNGPFTFVGWHXJXLWNUQK[Y[",
+        "H\\MFXFRNUNWOXPYSYUXXVZS[P[MZLYKW",
+        "H\\UFKTZT UFU[",
+        "H\\WFMFLOMNPMSMVNXPYSYUXXVZS[P[MZLYKW",
+        "H\\XIWGTFRFOGMJLOLTMXOZR[S[VZXXYUYTXQVOSNRNOOMQLT",
+        "H\\YFO[ KFYF",
+        "H\\PFMGLILKMMONSOVPXRYTYWXYWZT[P[MZLYKWKTLRNPQOUNWMXKXIWGTFPF",
+        "H\\XMWPURRSQSNRLPKMKLLINGQFRFUGWIXMXRWWUZR[P[MZLX"};
+    return (ch >= '0' && ch <= '9') ? digits[ch - '0'] : nullptr;
+}
+
+class Emitter {
+  public:
+    Emitter(int h, int w, VisLeaf* out, int cap) : h_(h), w_(w), out_(out), cap_(cap) {}
+
+    int count() const { return n_; }
+    bool ok() const { return glyph_ok_; }
+
+    void set_color(int b, int g, int r) { color_ = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16); }
+
+    // ---- group headers: slots [0, n) lead the leaf array, one per box -------------------------------
+    void reserve_headers(int n) {
+        VisLeaf l;
+        std::memset(&l, 0, sizeof l);
+        l.w[0] = LEAF_GROUP;
+        for (int i = 0; i < n; ++i) push(l);
+    }
+    void begin_group() {
+        group_first_ = n_;
+        gx0_ = gy0_ = INT_MAX;
+        gx1_ = gy1_ = INT_MIN;
+    }
+    void end_group(int slot) {                   // header = leaf range + bounding box of everything in it
+        if (slot >= cap_) return;
+        VisLeaf& l = out_[slot];
+        l.w[2] = group_first_;
+        l.w[3] = n_;
+        if (gx0_ > gx1_ || gy0_ > gy1_) { l.w[3] = group_first_; l.w[10] = 1; l.w[11] = 1; return; }   // nothing visible
+        pack_bbox(l, gx0_, gy0_, gx1_, gy1_);
+    }
+
+    // ---- cv::line / cv::rectangle / cv::circle / cv::putText ---------------------------------------
+    void line(int x1, int y1, int x2, int y2, int thickness, int line_type) {
+        Pt a{x1 + thickness, y1 + thickness}, b{x2 + thickness, y2 + thickness};
+        // cv::line first clips the centre line to the image grown by `thickness` (4.13 binary behaviour)
+        if (!clip_line((int64_t)w_ + 2 * thickness, (int64_t)h_ + 2 * thickness, a, b)) return;
+        a.x -= thickness; a.y -= thickness; b.x -= thickness; b.y -= thickness;
+        thick_line(a, b, thickness, line_type, 3, 0);
+    }
+    void rectangle(int x1, int y1, int x2, int y2, int thickness, int line_type) {
+        const Pt v[4] = {{x1, y1}, {x2, y1}, {x2, y2}, {x1, y2}};
+        poly_line(v, 4, true, thickness, line_type, 0);
+    }
+    void circle_filled(int cx, int cy, int radius) { disc(cx, cy, radius); }
+    void circle_outline(int cx, int cy, int radius, int thickness) {          // thickness > 1, LINE_8
+        ellipse({(int64_t)cx << kShift, (int64_t)cy << kShift}, (int64_t)radius << kShift, thickness, kLine8);
+    }
+    bool text_size(const char* text, double scale, int thickness, int* tw, int* th) {
+        double view_x = 0;
+        *th = round_half_even((12 + 9) * scale + (thickness + 1) / 2);
+        for (const char* s = text; *s; ++s) {
+            const char* g = glyph_for((unsigned char)*s);
+            if (!g) { glyph_ok_ = false; return false; }
+            view_x += (((unsigned char)g[1] - 'R') - ((unsigned char)g[0] - 'R')) * scale;
+        }
+        *tw = round_half_even(view_x + thickness);
+        return true;
+    }
+    void put_text(const char* text, int org_x, int org_y, double scale, int thickness) {
+        const int hscale = round_half_even(scale * kOne), vscale = hscale;
+        int64_t view_x = (int64_t)org_x << kShift;
+        const int64_t view_y = ((int64_t)org_y << kShift) - 9 * (int64_t)vscale;
+        std::vector<Pt> pts;
+        for (const char* s = text; *s; ++s) {
+            const char* g = glyph_for((unsigned char)*s);
+            if (!g) { glyph_ok_ = false; return; }
+            const int64_t left = (unsigned char)g[0] - 'R', right = (unsigned char)g[1] - 'R';
+            view_x -= left * hscale;
+            pts.clear();
+            for (const char* p = g + 2;;) {
+                if (*p == ' ' || !*p) {
+                    if (pts.size() > 1) poly_line(pts.data(), (int)pts.size(), false, thickness, kLine8, kShift);
+                    if (!*p++) break;
+                    pts.clear();
+                } else {
+                    const int64_t gx = (unsigned char)p[0] - 'R', gy = (unsigned char)p[1] - 'R';
+                    p += 2;
+                    pts.push_back({gx * hscale + view_x, gy * vscale + view_y});
+                }
+            }
+            view_x += right * hscale;
+        }
+    }
+
+  private:
+    int h_, w_;
+    VisLeaf* out_;
+    int cap_;
+    int n_ = 0;
+    uint32_t color_ = 0;
+    bool glyph_ok_ = true;
+    int gx0_ = INT_MAX, gy0_ = INT_MAX, gx1_ = INT_MIN, gy1_ = INT_MIN;
+    int group_first_ = 0;
+
+    void push(const VisLeaf& l) {
+        if (n_ < cap_) out_[n_] = l;
+        ++n_;
+    }
+    static void pack_bbox(VisLeaf& l, int x0, int y0, int x1, int y1) {
+        l.w[10] = (x0 & 0xffff) | (x1 << 16);
+        l.w[11] = (y0 & 0xffff) | (y1 << 16);
+    }
+    // clamps the box to the image, drops the leaf when nothing is visible
+    void push_boxed(VisLeaf& l, int64_t x0, int64_t y0, int64_t x1, int64_t y1) {
+        x0 = std::max<int64_t>(x0, 0); y0 = std::max<int64_t>(y0, 0);
+        x1 = std::min<int64_t>(x1, w_ - 1); y1 = std::min<int64_t>(y1, h_ - 1);
+        if (x0 > x1 || y0 > y1) return;
+        pack_bbox(l, (int)x0, (int)y0, (int)x1, (int)y1);
+        l.w[1] = (int32_t)color_;
+        gx0_ = std::min(gx0_, (int)x0); gy0_ = std::min(gy0_, (int)y0);
+        gx1_ = std::max(gx1_, (int)x1); gy1_ = std::max(gy1_, (int)y1);
+        push(l);
+    }
+
+    // ---- cv: clipLine on a (scaled) size --------------------------------------------------------
+    static bool clip_line(int64_t width, int64_t height, Pt& p1, Pt& p2) {
+        if (width <= 0 || height <= 0) return false;
+        const int64_t right = width - 1, bottom = height - 1;
+        int64_t &x1 = p1.x, &y1 = p1.y, &x2 = p2.x, &y2 = p2.y;
+        auto code = [&](int64_t x, int64_t y) { return (x < 0) + (x > right) * 2 + (y < 0) * 4 + (y > bottom) * 8; };
+        int c1 = code(x1, y1), c2 = code(x2, y2);
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1 & 12) {
+                const int64_t a = c1 < 8 ? 0 : bottom;
+                x1 += (int64_t)((double)(a - y1) * (x2 - x1) / (y2 - y1));
+                y1 = a;
+                c1 = (x1 < 0) + (x1 > right) * 2;
+            }
+            if (c2 & 12) {
+                const int64_t a = c2 < 8 ? 0 : bottom;
+                x2 += (int64_t)((double)(a - y2) * (x2 - x1) / (y2 - y1));
+                y2 = a;
+                c2 = (x2 < 0) + (x2 > right) * 2;
+            }
+            if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+                if (c1) {
+                    const int64_t a = c1 == 1 ? 0 : right;
+                    y1 += (int64_t)((double)(a - x1) * (y2 - y1) / (x2 - x1));
+                    x1 = a;
+                    c1 = 0;
+                }
+                if (c2) {
+                    const int64_t a = c2 == 1 ? 0 : right;
+                    y2 += (int64_t)((double)(a - x2) * (y2 - y1) / (x2 - x1));
+                    x2 = a;
+                    c2 = 0;
+                }
+            }
+        }
+        return (c1 | c2) == 0;
+    }
+
+    // orientation shared by Line2 and LineAA: major axis, end points ordered along +major, minor step
+    struct Oriented { bool xmajor; Pt a, b; int64_t step; };
+    static Oriented orient(Pt p1, Pt p2) {
+        Oriented o;
+        int64_t dx = p2.x - p1.x, dy = p2.y - p1.y;
+        const int64_t ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+        o.xmajor = ax > ay;
+        if (o.xmajor) {
+            if (dx < 0) { std::swap(p1, p2); dy = -dy; }
+            o.step = (dy * kOne) / (ax | 1);
+        } else {
+            if (dy < 0) { std::swap(p1, p2); dx = -dx; }
+            o.step = (dx * kOne) / (ay | 1);
+        }
+        o.a = p1; o.b = p2;
+        return o;
+    }
+
+    // ---- cv: Line2 -> LINE8 leaf ------------------------------------------------------------------
+    void line8(Pt p1, Pt p2) {
+        if (!clip_line((int64_t)w_ << kShift, (int64_t)h_ << kShift, p1, p2)) return;
+        const Oriented o = orient(p1, p2);
+        VisLeaf l;
+        std::memset(&l, 0, sizeof l);
+        l.w[0] = LEAF_LINE8 | (o.xmajor ? LEAF_FLAG_XMAJOR : 0);
+        const int64_t maj_a = o.xmajor ? o.a.x : o.a.y, maj_b = o.xmajor ? o.b.x : o.b.y;
+        const int64_t min_a = (o.xmajor ? o.a.y : o.a.x) + (kOne >> 1);
+        const int ecount = (int)((maj_b - maj_a) >> kShift);
+        const int m0 = (int)((maj_a + (kOne >> 1)) >> kShift);
+        l.w[2] = m0;
+        l.w[3] = ecount;
+        l.w[4] = (int32_t)min_a;
+        l.w[5] = (int32_t)o.step;
+        const int ex = (int)((o.b.x + (kOne >> 1)) >> kShift), ey = (int)((o.b.y + (kOne >> 1)) >> kShift);
+        l.w[6] = ex;
+        l.w[7] = ey;
+        const int64_t min_end = min_a + o.step * ecount;
+        int64_t lo = std::min(min_a, min_end) >> kShift, hi = std::max(min_a, min_end) >> kShift;
+        int64_t x0, y0, x1, y1;
+        if (o.xmajor) { x0 = m0; x1 = m0 + ecount; y0 = lo; y1 = hi; }
+        else          { y0 = m0; y1 = m0 + ecount; x0 = lo; x1 = hi; }
+        x0 = std::min<int64_t>(x0, ex); x1 = std::max<int64_t>(x1, ex);
+        y0 = std::min<int64_t>(y0, ey); y1 = std::max<int64_t>(y1, ey);
+        push_boxed(l, x0, y0, x1, y1);
+    }
+
+    // ---- cv: LineAA -> LINEAA leaf ----------------------------------------------------------------
+    void line_aa(Pt p1, Pt p2) {
+        if (!clip_line((int64_t)w_ << kShift, (int64_t)h_ << kShift, p1, p2)) return;
+        Oriented o = orient(p1, p2);
+        int64_t maj_a = o.xmajor ? o.a.x : o.a.y, maj_b = o.xmajor ? o.b.x : o.b.y;
+        int64_t min_a = o.xmajor ? o.a.y : o.a.x;
+        maj_b += kOne;
+        const int ecount = (int)((maj_b >> kShift) - (maj_a >> kShift));
+        const int64_t frac = -(maj_a & (kOne - 1));
+        min_a += ((o.step * frac) >> kShift) + (kOne >> 1);
+        int slope = (int)((o.step >> (kShift - 5)) & 0x3f);
+        if (o.step < 0) slope ^= 0x3f;
+        const int64_t i = (maj_a >> (kShift - 7)) & 0x78, j = (maj_b >> (kShift - 7)) & 0x78;
+        slope = (slope & 0x20) ? 0x100 : kSlopeCorr[slope];
+        int ep[9];
+        const int t0 = slope << 7, t1 = ((0x78 - (int)i) | 4) * slope, t2 = ((int)j | 4) * slope;
+        ep[0] = 0;
+        ep[8] = slope;
+        ep[1] = ep[3] = (int)((((((j - i) & 0x78) | 4) * slope) >> 8) & 0x1ff);
+        ep[2] = (t1 >> 8) & 0x1ff;
+        ep[4] = (int)((((((j - i) + 0x80) | 4) * slope) >> 8) & 0x1ff);
+        ep[5] = ((t1 + t0) >> 8) & 0x1ff;
+        ep[6] = (t2 >> 8) & 0x1ff;
+        ep[7] = ((t2 + t0) >> 8) & 0x1ff;
+        VisLeaf l;
+        std::memset(&l, 0, sizeof l);
+        l.w[0] = LEAF_LINEAA | (o.xmajor ? LEAF_FLAG_XMAJOR : 0);
+        const int m0 = (int)(maj_a >> kShift);
+        l.w[2] = m0;
+        l.w[3] = ecount;
+        l.w[4] = (int32_t)min_a;
+        l.w[5] = (int32_t)o.step;
+        l.w[6] = ep[0] | (ep[1] << 10) | (ep[2] << 20);
+        l.w[7] = ep[3] | (ep[4] << 10) | (ep[5] << 20);
+        l.w[8] = ep[6] | (ep[7] << 10) | (ep[8] << 20);
+        const int64_t min_end = min_a + o.step * ecount;
+        const int64_t lo = (std::min(min_a, min_end) >> kShift) - 1, hi = (std::max(min_a, min_end) >> kShift) + 1;
+        if (o.xmajor) push_boxed(l, m0, lo, (int64_t)m0 + ecount, hi);
+        else          push_boxed(l, lo, m0, hi, (int64_t)m0 + ecount);
+    }
+
+    // ---- cv: FillConvexPoly (vertices 16.16) -> edge lines + TRAP leaves -----------------------------
+    void fill_convex(const Pt* v, int n, int line_type) {
+        const int64_t delta = kOne >> 1;
+        const int64_t d1 = line_type < kLineAA ? (kOne >> 1) : kOne - 1, d2 = line_type < kLineAA ? (kOne >> 1) : 0;
+        int64_t xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
+        int imin = 0;
+        Pt prev = v[n - 1];
+        for (int i = 0; i < n; ++i) {
+            const Pt p = v[i];
+            if (p.y < ymin) { ymin = p.y; imin = i; }
+            ymax = std::max(ymax, p.y);
+            xmax = std::max(xmax, p.x);
+            xmin = std::min(xmin, p.x);
+            if (line_type <= 8) line8(prev, p); else line_aa(prev, p);
+            prev = p;
+        }
+        xmin = (xmin + delta) >> kShift; xmax = (xmax + delta) >> kShift;
+        ymin = (ymin + delta) >> kShift; ymax = (ymax + delta) >> kShift;
+        if (n < 3 || (int)xmax < 0 || (int)ymax < 0 || (int)xmin >= w_ || (int)ymin >= h_) return;
+        ymax = std::min<int64_t>(ymax, h_ - 1);
+        struct Walker { int idx, di, ye; int64_t x, dx; int y_set; int64_t x_set; } e[2];
+        int y = (int)ymin, edges = n;
+        for (int i = 0; i < 2; ++i) e[i] = {imin, i == 0 ? 1 : n - 1, y, -kOne, 0, y, -kOne};
+        int run_start = y;                       // first row of the current (segment pair) run
+        auto flush = [&](int y_last) {           // rows [run_start, y_last] share both walkers' segments
+            const int ya = std::max(run_start, 0);
+            if (ya > y_last) return;
+            VisLeaf l;
+            std::memset(&l, 0, sizeof l);
+            l.w[0] = LEAF_TRAP | (line_type < kLineAA ? 0 : LEAF_FLAG_AA);
+            l.w[2] = ya;
+            l.w[3] = y_last;
+            int64_t xs[2], xe[2];
+            for (int i = 0; i < 2; ++i) {
+                xs[i] = e[i].x_set + e[i].dx * (ya - e[i].y_set);
+                xe[i] = e[i].x_set + e[i].dx * (y_last - e[i].y_set);
+                l.w[4 + 2 * i] = (int32_t)xs[i];
+                l.w[5 + 2 * i] = (int32_t)e[i].dx;
+            }
+            const int64_t lo = std::min(std::min(xs[0], xs[1]), std::min(xe[0], xe[1]));
+            const int64_t hi = std::max(std::max(xs[0], xs[1]), std::max(xe[0], xe[1]));
+            push_boxed(l, (lo + d1) >> kShift, ya, (hi + d2) >> kShift, y_last);
+        };
+        do {
+            if (line_type < kLineAA || y < (int)ymax || y == (int)ymin) {
+                for (int i = 0; i < 2; ++i) {
+                    if (y < e[i].ye) continue;
+                    int idx0 = e[i].idx, di = e[i].di, idx = idx0 + di;
+                    if (idx >= n) idx -= n;
+                    for (; edges-- > 0;) {
+                        const int ty = (int)((v[idx].y + delta) >> kShift);
+                        if (ty > y) {
+                            if (y > run_start) flush(y - 1);     // close the run that used the old segment
+                            run_start = y;
+                            const int64_t xs = v[idx0].x, xe = v[idx].x;
+                            e[i].ye = ty;
+                            e[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+                            e[i].x = xs;
+                            e[i].idx = idx;
+                            e[i].y_set = y;
+                            e[i].x_set = xs;
+                            break;
+                        }
+                        idx0 = idx;
+                        idx += di;
+                        if (idx >= n) idx -= n;
+                    }
+                }
+            }
+            if (edges < 0) break;
+            e[0].x += e[0].dx;
+            e[1].x += e[1].dx;
+        } while (++y <= (int)ymax);
+        // rows [run_start, y-1] were scanned with the current pair (y stopped one past the last filled row)
+        if (y - 1 >= run_start) flush(y - 1);
+    }
+
+    // ---- cv: Circle (filled midpoint circle) -> SPANS leaves -----------------------------------------
+    void disc(int cx, int cy, int radius) {
+        std::vector<int> half((size_t)radius + 1, -1);
+        int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+        while (dx >= dy) {
+            half[dy] = std::max(half[dy], dx);
+            half[dx] = std::max(half[dx], dy);
+            ++dy;
+            err += plus;
+            plus += 2;
+            const int mask = (err <= 0) - 1;
+            err -= minus & mask;
+            dx += mask;
+            minus -= mask & 2;
+        }
+        for (int base = -radius; base <= radius; base += 16) {
+            const int rows = std::min(16, radius - base + 1);
+            VisLeaf l;
+            std::memset(&l, 0, sizeof l);
+            l.w[0] = LEAF_SPANS;
+            l.w[2] = cx;
+            l.w[3] = cy + base;
+            l.w[4] = rows;
+            int widest = -1;
+            for (int r = 0; r < rows; ++r) {
+                const int off = base + r, hw = half[off < 0 ? -off : off];      // 0xff marks "no span"
+                const int byte = hw < 0 ? 0xff : hw;
+                l.w[5 + r / 4] |= byte << (8 * (r % 4));
+                widest = std::max(widest, hw);
+            }
+            if (widest < 0) continue;
+            push_boxed(l, (int64_t)cx - widest, (int64_t)cy + base, (int64_t)cx + widest, (int64_t)cy + base + rows - 1);
+        }
+    }
+
+    // ---- cv: EllipseEx (full circle, axis-aligned) -------------------------------------------------
+    void ellipse(Pt center, int64_t axis, int thickness, int line_type) {
+        int delta = (int)((axis + (kOne >> 1)) >> kShift);
+        delta = delta < 3 ? 90 : delta < 10 ? 30 : delta < 15 ? 18 : 5;
+        std::vector<Pt> v;
+        Pt prev{-1, -1};
+        const double cxd = (double)center.x, cyd = (double)center.y, ad = (double)axis;
+        const float alpha = kSin[450], beta = kSin[0];
+        for (int a = 0; a < 360 + delta; a += delta) {
+            const int ang = std::min(a, 360);
+            const double x = ad * kSin[450 - ang], y = ad * kSin[ang];
+            const double px = cxd + x * alpha - y * beta, py = cyd + x * beta + y * alpha;
+            Pt q;
+            q.x = (int64_t)round_half_even(px / (double)kOne) << kShift;
+            q.y = (int64_t)round_half_even(py / (double)kOne) << kShift;
+            q.x += round_half_even(px - q.x);
+            q.y += round_half_even(py - q.y);
+            if (q.x != prev.x || q.y != prev.y) { v.push_back(q); prev = q; }
+        }
+        if (v.size() <= 1) v.assign(2, center);
+        if (thickness >= 0) poly_line(v.data(), (int)v.size(), false, thickness, line_type, kShift);
+        else fill_convex(v.data(), (int)v.size(), line_type);
+    }
+
+    // ---- cv: PolyLine / ThickLine --------------------------------------------------------------------
+    void poly_line(const Pt* v, int count, bool closed, int thickness, int line_type, int shift) {
+        if (count <= 0) return;
+        int flags = 2 + (closed ? 0 : 1);
+        Pt p0 = v[closed ? count - 1 : 0];
+        for (int i = closed ? 0 : 1; i < count; ++i) {
+            thick_line(p0, v[i], thickness, line_type, flags, shift);
+            p0 = v[i];
+            flags = 2;
+        }
+    }
+    void thick_line(Pt p0, Pt p1, int thickness, int line_type, int flags, int shift) {
+        p0.x <<= kShift - shift; p0.y <<= kShift - shift;
+        p1.x <<= kShift - shift; p1.y <<= kShift - shift;
+        if (thickness <= 1) {
+            if (line_type < kLineAA) line8(p0, p1); else line_aa(p0, p1);
+            return;
+        }
+        const double inv = 1.0 / (double)kOne;
+        const double dx = (p0.x - p1.x) * inv, dy = (p1.y - p0.y) * inv;
+        double r = dx * dx + dy * dy;
+        const int odd = thickness & 1;
+        const int64_t half = (int64_t)thickness << (kShift - 1);
+        if (std::fabs(r) > DBL_EPSILON) {
+            r = (half + odd * kOne * 0.5) / std::sqrt(r);
+            const int64_t ox = round_half_even(dy * r), oy = round_half_even(dx * r);
+            const Pt quad[4] = {{p0.x + ox, p0.y + oy}, {p0.x - ox, p0.y - oy}, {p1.x - ox, p1.y - oy}, {p1.x + ox, p1.y + oy}};
+            fill_convex(quad, 4, line_type);
+        }
+        for (int i = 0; i < 2; ++i) {
+            if (flags & (i + 1)) {
+                if (line_type < kLineAA)
+                    disc((int)((p0.x + (kOne >> 1)) >> kShift), (int)((p0.y + (kOne >> 1)) >> kShift),
+                         (int)((half + (kOne >> 1)) >> kShift));
+                else
+                    ellipse(p0, half, -1, line_type);
+            }
+            p0 = p1;
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int n_boxes,
+                                  VisLeaf* leaves, int capacity, int* needed) {
+    if (img_h <= 0 || img_w <= 0 || img_h > 32767 || img_w > 32767 || n_boxes < 0 || (n_boxes && !boxes) ||
+        capacity < 0 || (capacity && !leaves)) {
+        vis::set_error("vis_overlay_expand: bad arguments (h=%d w=%d boxes=%d)", img_h, img_w, n_boxes);
+        return VIS_E_INVALID;
+    }
+    // group headers first (one per box), leaves after: a tile scans the headers and skips whole boxes
+    Emitter em(img_h, img_w, leaves, capacity);
+    em.reserve_headers(n_boxes);
+    for (int i = 0; i < n_boxes; ++i) {
+        const VisBox& b = boxes[i];
+        const int x = b.x, y = b.y, w = b.w, h = b.h;
+        em.begin_group();
+        em.set_color(b.b, b.g, b.r);
+        if (b.dashed) {                          // utils/image_utils.py:260-283: 10 px dashes, 5 px gaps
+            for (int k = 0; k < 2; ++k) {
+                const int yy = k == 0 ? y : y + h;
+                for (int px = x; px < x + w; px += 15) {
+                    const int ex = std::min(px + 10, x + w);
+                    if (ex > px) em.line(px, yy, ex, yy, 2, 16);
+                }
+            }
+            for (int k = 0; k < 2; ++k) {
+                const int xx = k == 0 ? x : x + w;
+                for (int py = y; py < y + h; py += 15) {
+                    const int ey = std::min(py + 10, y + h);
+                    if (ey > py) em.line(xx, py, xx, ey, 2, 16);
+                }
+            }
+        } else {
+            em.rectangle(x, y, x + w, y + h, 2, 16);                      // :286
+        }
+        // marker (:290-302)
+        int radius = (int)(std::max(img_w, img_h) * 0.04);
+        radius = std::max(25, std::min(radius, 60));
+        const int cx = std::max(radius + 5, std::min(x + radius + 5, img_w - radius - 5));
+        const int cy = std::max(radius + 5, std::min(y + radius + 5, img_h - radius - 5));
+        em.set_color(255, 255, 255);
+        em.circle_filled(cx, cy, radius);
+        em.set_color(b.b, b.g, b.r);
+        em.circle_outline(cx, cy, radius, 3);
+        // label (:305-313)
+        const double font_scale = radius / 20.0 * 0.7;
+        const int text_thickness = std::max(2, (int)(font_scale * 2));
+        char label[13];
+        std::memcpy(label, b.label, 12);
+        label[12] = 0;
+        int tw = 0, th = 0;
+        if (!em.text_size(label, font_scale, text_thickness, &tw, &th)) {
+            vis::set_error("vis_overlay_expand: label '%s' has a character outside the built-in Hershey digits", label);
+            return VIS_E_UNSUPPORTED;
+        }
+        em.set_color(0, 0, 0);
+        em.put_text(label, (int)(cx - tw / 2.0), (int)(cy + th / 2.0), font_scale, text_thickness);
+        em.end_group(i);
+    }
+    if (needed) *needed = em.count();
+    if (em.count() > capacity) {
+        vis::set_error("vis_overlay_expand: %d leaves needed, capacity %d", em.count(), capacity);
+        return VIS_E_CAPACITY;
+    }
+    return em.count();
+}

@@ -1,0 +1,360 @@
+"""The device engine: owns tables on one GPU and launches the kernels of libvis_b200.so.
+
+PyTorch is plumbing only (device memory, streams); all compute is in the C-ABI library.  One ``Engine`` per
+process/GPU.  No CPU fallback: constructing an Engine without CUDA raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import geometry as G
+from . import tables as T
+
+
+def _stream_ptr(stream=None) -> C.c_void_p:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+@dataclass
+class _Geometry:
+    """Everything that depends only on (src_h, src_w, dst_h, dst_w) — cached per engine."""
+    src_h: int
+    src_w: int
+    dst_h: int
+    dst_w: int
+    kt: int                      # fused tap class, 0 = generic only
+    hrec: torch.Tensor | None
+    vrec: torch.Tensor | None
+    htable: T.CoeffTable
+    vtable: T.CoeffTable
+    n_rows: int
+    plans: dict                  # vsplit -> StripPlan
+
+
+@dataclass
+class _FusedLaunch:
+    kt: int
+    n_frames: int
+    n_strips: int
+    span_bytes: int
+    strip_w: int
+    frames: torch.Tensor         # device VisFrame[]
+    strips: torch.Tensor         # device VisStrip[]
+
+
+@dataclass
+class BatchPlan:
+    total_rows: int
+    grid_thw: torch.Tensor       # int64 [B, 3] (host)
+    fused: list
+    generic: list                # (frame index, geometry, first output row)
+
+
+class Engine:
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vision-inspection-system_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.L = N.lib()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.lut = torch.from_numpy(T.normalize_lut()).to(self.device)
+        self._dev_tables: dict = {}
+        self._geoms: dict = {}
+        self._batch_plans: dict = {}
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.last_launches = 0           # kernels launched by the most recent public call
+
+    # ------------------------------------------------------------------ tables
+    def _device_table(self, in_size: int, out_size: int, filt: int):
+        key = (in_size, out_size, filt)
+        hit = self._dev_tables.get(key)
+        if hit is None:
+            t = T.coeff_table(in_size, out_size, filt)
+            hit = (t, torch.from_numpy(t.k.copy()).to(self.device), torch.from_numpy(t.bounds.copy()).to(self.device))
+            self._dev_tables[key] = hit
+        return hit
+
+    def _geometry(self, src_h: int, src_w: int, dst_h: int, dst_w: int) -> _Geometry:
+        key = (src_h, src_w, dst_h, dst_w)
+        g = self._geoms.get(key)
+        if g is None:
+            ht = T.coeff_table(src_w, dst_w, N.FILTER_BICUBIC)
+            vt = T.coeff_table(src_h, dst_h, N.FILTER_BICUBIC)
+            kt = T.kt_class(max(ht.max_taps, vt.max_taps))
+            if G.pil_pass_order(src_h, src_w, dst_h, dst_w) == "vh":
+                kt = 0
+            hrec = vrec = None
+            if kt:
+                hrec = torch.from_numpy(T.pack_records(ht, kt)).to(self.device)
+                vrec = torch.from_numpy(T.pack_records(vt, kt)).to(self.device)
+            g = _Geometry(src_h, src_w, dst_h, dst_w, kt, hrec, vrec, ht, vt,
+                          (dst_h // G.PATCH_SIZE) * (dst_w // G.PATCH_SIZE), {})
+            self._geoms[key] = g
+        return g
+
+    def _plan(self, g: _Geometry, vsplit: int) -> T.StripPlan:
+        p = g.plans.get(vsplit)
+        if p is None:
+            p = T.plan_strips(g.dst_h, g.dst_w, g.htable, g.kt, vsplit)
+            g.plans[vsplit] = p
+        return p
+
+    # ------------------------------------------------------------------ generic resample (uint8 -> uint8)
+    def resize_u8(self, img: torch.Tensor, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS, stream=None) -> torch.Tensor:
+        """``PIL.Image.resize((out_w, out_h), filt, reducing_gap=None)`` for a CUDA uint8 HWC (or HW) tensor."""
+        self._check_u8(img)
+        squeeze = img.dim() == 2
+        if squeeze:
+            img = img.unsqueeze(-1)
+        if img.stride(2) != 1 or img.stride(1) != img.shape[2]:
+            img = img.contiguous()
+        h, w, ch = img.shape
+        order = G.pil_pass_order(h, w, out_h, out_w)
+        sp = _stream_ptr(stream)
+        cur, cur_h, cur_w = img, h, w
+        self.last_launches = 0
+        if order == "":
+            cur = img.clone()
+        for axis in order:
+            if axis == "h":
+                t, k, b = self._device_table(cur_w, out_w, filt)
+                dst = torch.empty((cur_h, out_w, ch), dtype=torch.uint8, device=self.device)
+                N.check(self.L.vis_resample_h_u8(cur.data_ptr(), cur.stride(0), cur_h, cur_w, ch,
+                                                 dst.data_ptr(), dst.stride(0), out_w,
+                                                 k.data_ptr(), b.data_ptr(), t.ksize, sp), "vis_resample_h_u8")
+                cur, cur_w = dst, out_w
+            else:
+                t, k, b = self._device_table(cur_h, out_h, filt)
+                dst = torch.empty((out_h, cur_w, ch), dtype=torch.uint8, device=self.device)
+                N.check(self.L.vis_resample_v_u8(cur.data_ptr(), cur.stride(0), cur_h, cur_w * ch,
+                                                 dst.data_ptr(), dst.stride(0), out_h,
+                                                 k.data_ptr(), b.data_ptr(), t.ksize, sp), "vis_resample_v_u8")
+                cur, cur_h = dst, out_h
+            self.last_launches += 1
+        return cur.squeeze(-1) if squeeze else cur
+
+    # ------------------------------------------------------------------ frames -> pixel_values
+    def plan_batch(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
+                   force_generic: bool = False, vsplit: int | None = None) -> "BatchPlan":
+        """Host-side planning for one batch: geometry, output rows, descriptor arrays (uploaded once).
+
+        Plans depend only on pointers and shapes, so they are cached and reused when the same device buffers are
+        submitted again (a streaming loop that refills one staging buffer pays for planning once).
+        """
+        uniform = isinstance(frames, torch.Tensor) and frames.dim() == 4
+        if uniform:
+            self._check_u8(frames)
+            key = ("u", frames.data_ptr(), tuple(frames.shape), tuple(frames.stride()), min_pixels, max_pixels,
+                   force_generic, vsplit)
+        else:
+            frames = list(frames)
+            for f in frames:
+                self._check_u8(f)
+            key = ("l", tuple((f.data_ptr(), tuple(f.shape), tuple(f.stride())) for f in frames), min_pixels,
+                   max_pixels, force_generic, vsplit)
+        plan = self._batch_plans.get(key)
+        if plan is not None:
+            return plan
+        if uniform:
+            b, h, w, c = (int(v) for v in frames.shape)
+            if b == 0:
+                raise ValueError("no frames")
+            shapes = [(h, w)] * b
+            ptrs = frames.data_ptr() + np.arange(b, dtype=np.int64) * frames.stride(0)
+            pitches = np.full(b, frames.stride(1), np.int64)
+            ok_layout = c == 3 and frames.stride(3) == 1 and frames.stride(2) == 3
+        else:
+            if not frames:
+                raise ValueError("no frames")
+            ok_layout = all(f.dim() == 3 and f.shape[2] == 3 and f.stride(2) == 1 and f.stride(1) == 3 for f in frames)
+            shapes = [(int(f.shape[0]), int(f.shape[1])) for f in frames] if ok_layout else []
+            ptrs = np.array([f.data_ptr() for f in frames], np.int64)
+            pitches = np.array([f.stride(0) for f in frames], np.int64)
+        if not ok_layout:
+            raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels (row pitch may be padded)")
+
+        geoms, grids = [], []
+        cache: dict = {}
+        for hw in shapes:
+            g = cache.get(hw)
+            if g is None:
+                dh, dw = G.smart_resize(hw[0], hw[1], G.FACTOR, min_pixels, max_pixels)
+                g = cache[hw] = self._geometry(hw[0], hw[1], dh, dw)
+            geoms.append(g)
+            grids.append(G.grid_thw(g.dst_h, g.dst_w))
+        n_rows = np.array([g.n_rows for g in geoms], np.int64)
+        row0 = np.concatenate([[0], np.cumsum(n_rows)[:-1]]).astype(np.int64)
+        total = int(n_rows.sum())
+
+        plan = BatchPlan(total, torch.tensor(grids, dtype=torch.int64), [], [])
+        groups: dict = {}
+        for i, g in enumerate(geoms):
+            fused = (not force_generic) and g.kt and self.L.vis_fused_supported(
+                int(ptrs[i]), int(pitches[i]), g.src_h, g.src_w, g.dst_h, g.dst_w,
+                g.htable.max_taps, g.vtable.max_taps) == N.VIS_OK
+            if fused:
+                groups.setdefault((g.kt, id(g)), (g, []))[1].append(i)
+            else:
+                plan.generic.append((i, g, int(row0[i])))
+        # one launch per tap class; all geometries of a class share it
+        by_class: dict = {}
+        for (kt, _), (g, idx) in groups.items():
+            by_class.setdefault(kt, []).append((g, np.asarray(idx)))
+        want = 4 * 2 * self.sm_count                 # CTAs wanted: two per SM, a few waves
+        for kt, members in by_class.items():
+            n_class = sum(len(idx) for _, idx in members)
+            fr_parts, st_parts, span, strip_w, base = [], [], 0, 0, 0
+            for g, idx in members:
+                if vsplit is None:
+                    per_frame = len(self._plan(g, 1).strips)
+                    vs = max(1, min(g.dst_h // 56, -(-want // (n_class * per_frame))))
+                else:
+                    vs = vsplit
+                sp = self._plan(g, vs)
+                fr = np.zeros(len(idx), N.FRAME_DTYPE)
+                fr["src"], fr["src_pitch"] = ptrs[idx].astype(np.uint64), pitches[idx]
+                fr["src_h"], fr["src_w"], fr["dst_h"], fr["dst_w"] = g.src_h, g.src_w, g.dst_h, g.dst_w
+                fr["hrec"], fr["vrec"], fr["row0"] = g.hrec.data_ptr(), g.vrec.data_ptr(), row0[idx]
+                st = np.tile(sp.strips, len(idx))
+                st["frame"] = base + np.repeat(np.arange(len(idx), dtype=np.int32), len(sp.strips))
+                fr_parts.append(fr)
+                st_parts.append(st)
+                span, strip_w, base = max(span, sp.span_bytes), max(strip_w, sp.strip_w), base + len(idx)
+            fr_all, st_all = np.concatenate(fr_parts), np.concatenate(st_parts)
+            plan.fused.append(_FusedLaunch(
+                kt, len(fr_all), len(st_all), span, strip_w,
+                torch.from_numpy(fr_all.view(np.uint8).copy()).to(self.device),
+                torch.from_numpy(st_all.view(np.uint8).copy()).to(self.device)))
+        if len(self._batch_plans) >= 64:
+            self._batch_plans.pop(next(iter(self._batch_plans)))
+        self._batch_plans[key] = plan
+        return plan
+
+    def preprocess(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
+                   out: torch.Tensor | None = None, force_generic: bool = False, vsplit: int | None = None):
+        """RGB uint8 HWC CUDA frames -> (pixel_values f32 [sum N_i, 1176] on device, image_grid_thw int64 [B, 3]).
+
+        ``frames``: a ``[B, H, W, 3]`` tensor or a list of ``[H, W, 3]`` tensors (mixed sizes allowed).
+        Same result as ``Qwen2VLImageProcessorPil(size={shortest_edge: min_pixels, longest_edge: max_pixels})``.
+        Work is enqueued on the current CUDA stream; nothing synchronises.
+        """
+        plan = self.plan_batch(frames, min_pixels, max_pixels, force_generic, vsplit)
+        if out is None:
+            out = torch.empty((plan.total_rows, G.ROW_FLOATS), dtype=torch.float32, device=self.device)
+        elif (tuple(out.shape) != (plan.total_rows, G.ROW_FLOATS) or out.dtype != torch.float32
+              or not out.is_contiguous() or out.device != self.device):
+            raise ValueError(f"out must be a contiguous float32 [{plan.total_rows}, {G.ROW_FLOATS}] tensor on {self.device}")
+        sp = _stream_ptr()
+        launches = 0
+        flist = frames if plan.generic else None      # indexable either way ([B,H,W,3] tensor or list)
+        for i, g, r0 in plan.generic:
+            resized = self.resize_u8(flist[i], g.dst_h, g.dst_w, N.FILTER_BICUBIC)
+            launches += self.last_launches + 1
+            N.check(self.L.vis_normalize_patchify(resized.data_ptr(), resized.stride(0), g.dst_h, g.dst_w,
+                                                  self.lut.data_ptr(), out.data_ptr(), r0, sp), "vis_normalize_patchify")
+        for fl in plan.fused:
+            N.check(self.L.vis_preprocess_fused(fl.frames.data_ptr(), fl.n_frames, fl.strips.data_ptr(), fl.n_strips,
+                                                fl.kt, fl.span_bytes, fl.strip_w,
+                                                self.lut.data_ptr(), out.data_ptr(), sp), "vis_preprocess_fused")
+            launches += 1
+        self.last_launches = launches
+        return out, plan.grid_thw
+
+    # ------------------------------------------------------------------ defect overlay
+    def plan_overlay(self, shapes, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium"):
+        """Host half of the overlay for a batch: box validation (reference rules) + expansion into leaves.
+
+        ``shapes``: list of (H, W) per frame.  Returns (leaves uint8 device tensor, per-frame (begin, end) header
+        ranges, number of boxes drawn).
+        """
+        from . import overlay as O
+        parts, ranges, at, drawn = [], [], 0, 0
+        for (h, w), boxes in zip(shapes, boxes_per_frame):
+            px = O.boxes_to_pixels(boxes, w, h, confidence_threshold, criticality)
+            leaves = O.expand_leaves(px, w, h)
+            ranges.append((at, at + len(px)))          # the frame's array starts at `at`; headers come first
+            parts.append(leaves)
+            at += len(leaves)
+            drawn += len(px)
+        all_leaves = np.concatenate(parts) if parts else np.zeros(0, N.LEAF_DTYPE)
+        if len(all_leaves) == 0:
+            all_leaves = np.zeros(1, N.LEAF_DTYPE)
+        d_leaves = torch.from_numpy(all_leaves.view(np.uint8).copy()).to(self.device)
+        return d_leaves, ranges, drawn
+
+    def annotate(self, frames, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium",
+                 inplace: bool = False, plan=None):
+        """Draw the reference's defect overlay on BGR uint8 HWC CUDA frames (``[B,H,W,3]`` tensor or list).
+
+        Returns new tensors (or the inputs when ``inplace``).  Pixels equal what the reference's
+        ``draw_bounding_boxes`` holds just before ``cv2.imwrite``.
+        """
+        uniform = isinstance(frames, torch.Tensor) and frames.dim() == 4
+        flist = list(frames.unbind(0)) if uniform else list(frames)
+        if len(flist) != len(boxes_per_frame):
+            raise ValueError("one box list per frame expected")
+        for f in flist:
+            self._check_u8(f)
+            if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
+        shapes = [(int(f.shape[0]), int(f.shape[1])) for f in flist]
+        if plan is None:
+            plan = self.plan_overlay(shapes, boxes_per_frame, confidence_threshold, criticality)
+        d_leaves, ranges, _ = plan
+        if inplace:
+            outs = flist
+            result = frames
+        elif uniform:
+            result = torch.empty_like(frames)
+            outs = list(result.unbind(0))
+        else:
+            outs = [torch.empty_like(f) for f in flist]
+            result = outs
+        desc = np.zeros(len(flist), N.OVERLAY_FRAME_DTYPE)
+        desc["src"] = [f.data_ptr() for f in flist]
+        desc["dst"] = [o.data_ptr() for o in outs]
+        desc["src_pitch"] = [f.stride(0) for f in flist]
+        desc["dst_pitch"] = [o.stride(0) for o in outs]
+        desc["h"] = [s[0] for s in shapes]
+        desc["w"] = [s[1] for s in shapes]
+        desc["group_begin"] = [r[0] for r in ranges]
+        desc["group_end"] = [r[1] for r in ranges]
+        d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.device)
+        sp = _stream_ptr()
+        max_h, max_w = max(s[0] for s in shapes), max(s[1] for s in shapes)
+        self.last_launches = 0
+        for b0 in range(0, len(flist), 65535):
+            n = min(65535, len(flist) - b0)
+            N.check(self.L.vis_overlay_draw(d_desc.data_ptr() + b0 * N.OVERLAY_FRAME_DTYPE.itemsize, n, max_h, max_w,
+                                            d_leaves.data_ptr(), sp), "vis_overlay_draw")
+            self.last_launches += 1
+        self._keepalive = (d_desc, d_leaves)
+        return result
+
+    # ------------------------------------------------------------------ helpers
+    def _check_u8(self, t: torch.Tensor) -> None:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.uint8:
+            raise TypeError("expected a CUDA uint8 tensor (this engine has no CPU path)")
+        if t.device != self.device:
+            raise ValueError(f"tensor on {t.device}, engine on {self.device}")
+
+
+_engines: dict = {}
+
+
+def get_engine(device=None) -> Engine:
+    """Process-wide engine for ``device`` (default: current CUDA device)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("vision-inspection-system_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    e = _engines.get(dev)
+    if e is None:
+        e = _engines[dev] = Engine(dev)
+    return e

@@ -1,0 +1,168 @@
+"""Drop-in mirror of the reference's ``utils/image_utils`` functions that sit on the accelerated path.
+
+Same names, arguments, return types and error behaviour as the reference:
+
+    load_image(image_path) -> PIL.Image                         utils/image_utils.py:20-43
+    resize_image(img, max_dimension=None) -> PIL.Image          utils/image_utils.py:46-78
+    draw_bounding_boxes(image_path, boxes, output_path,
+                        confidence_threshold="low",
+                        criticality="medium") -> Path           utils/image_utils.py:148-317
+
+plus the entry points the reference delegates to a remote server today (the Qwen2-VL image processor behind
+``_encode_image_optimized``, src/agents/vlm_inspector.py:46-88 / src/agents/vlm_auditor.py:85-108):
+
+    agent_thumbnail(img, role) -> PIL.Image                     geometry half of _encode_image_optimized
+    preprocess_for_vlm(images, *, min_pixels, max_pixels, role) -> (pixel_values, image_grid_thw)
+    normalize = preprocess_for_vlm                              (the "normalize" entry BASELINE.json names)
+
+File decode/encode stays on the host (PIL / cv2 codecs, as in the reference); every resample, normalisation,
+patch layout and overlay pixel is computed by the CUDA library.  Nothing here imports ``utils.config`` (no API-key
+check, no directory creation at import).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import logging
+from pathlib import Path
+
+import numpy as np
+from PIL import Image
+
+from . import geometry as G
+
+logger = logging.getLogger("vision_inspection_system_b200.image_utils")
+
+MAX_IMAGE_DIMENSION = G.INSPECTOR_MAX_SIZE     # config.max_image_dimension default (utils/config.py:184)
+
+_ROLE_MAX_SIZE = {"inspector": G.INSPECTOR_MAX_SIZE, "auditor": G.AUDITOR_MAX_SIZE}
+
+
+def _engine():
+    from .engine import get_engine
+    return get_engine()
+
+
+def load_image(image_path: Path) -> Image.Image:
+    """Load an image file; ``FileNotFoundError`` if absent, ``ValueError`` if it cannot be decoded."""
+    image_path = Path(image_path)
+    if not image_path.exists():
+        raise FileNotFoundError(f"Image not found: {image_path}")
+    try:
+        img = Image.open(image_path)
+        img.load()
+        logger.debug("Loaded image: %s, size: %s, mode: %s", image_path.name, img.size, img.mode)
+        return img
+    except Exception as e:
+        raise ValueError(f"Failed to load image: {e}")
+
+
+def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int) -> Image.Image:
+    """``img.resize(size, filt)`` (reducing_gap=None) with the resampling done on the GPU."""
+    import torch
+    if img.size == tuple(size):
+        return img.copy()
+    mode = img.mode
+    if mode in ("LA", "RGBA"):                       # Pillow resamples these in premultiplied form
+        work = img.convert({"LA": "La", "RGBA": "RGBa"}[mode])
+    elif mode in ("L", "RGB", "RGBX", "CMYK", "YCbCr", "HSV", "LAB", "La", "RGBa"):
+        work = img
+    else:
+        raise NotImplementedError(f"image mode {mode!r} is resampled by Pillow with a non-8bpc or NEAREST path "
+                                  "that this engine does not implement")
+    bands = len(work.getbands())
+    arr = np.frombuffer(work.tobytes(), np.uint8).reshape(work.size[1], work.size[0], bands)
+    dev = torch.from_numpy(arr.copy()).cuda()
+    out = _engine().resize_u8(dev, size[1], size[0], int(filt)).cpu().numpy()
+    res = Image.frombytes(work.mode, tuple(size), out.tobytes())
+    return res.convert(mode) if work.mode != mode else res
+
+
+def resize_image(img: Image.Image, max_dimension: int = None) -> Image.Image:
+    """Fit within ``max_dimension`` keeping the aspect ratio (LANCZOS); returns ``img`` itself when it already fits."""
+    max_dimension = max_dimension or MAX_IMAGE_DIMENSION
+    width, height = img.size
+    target = G.resize_image_size(width, height, max_dimension)
+    if target is None:
+        return img
+    resized = _resample_pil(img, target, Image.Resampling.LANCZOS)
+    logger.debug("Resized image from %s to %s", img.size, resized.size)
+    return resized
+
+
+def agent_thumbnail(img: Image.Image, role: str = "inspector", max_size: int | None = None) -> Image.Image:
+    """The geometry of ``_encode_image_optimized``: LANCZOS thumbnail to fit 2048 (Inspector) / 1024 (Auditor),
+    then RGB for RGBA/P/LA inputs.  The JPEG q85 round trip that follows in the reference is a codec step and is
+    not part of this path."""
+    max_size = max_size or _ROLE_MAX_SIZE[role]
+    if max(img.size) > max_size:
+        tw, th = G.thumbnail_size(img.size[0], img.size[1], max_size)
+        if G.thumbnail_needs_reduce(img.size[0], img.size[1], tw, th):
+            raise NotImplementedError("thumbnail box-reduce pre-pass (>= 4x downscale) is not implemented")
+        if (tw, th) != img.size:
+            img = _resample_pil(img, (tw, th), Image.Resampling.LANCZOS)
+    if img.mode in ("RGBA", "P", "LA"):
+        img = img.convert("RGB")
+    return img
+
+
+def _to_rgb_array(image) -> np.ndarray:
+    """PIL image / path / HWC uint8 array -> RGB uint8 HWC (tf:image_processing_backends.py:437-470 semantics)."""
+    if isinstance(image, (str, Path)):
+        image = load_image(Path(image))
+    if isinstance(image, Image.Image):
+        if image.mode != "RGB":
+            image = image.convert("RGB")
+        return np.asarray(image)
+    arr = np.asarray(image)
+    if arr.dtype != np.uint8 or arr.ndim != 3 or arr.shape[2] != 3:
+        raise ValueError("expected a PIL image, a path or an RGB uint8 HWC array")
+    return arr
+
+
+def preprocess_for_vlm(images, *, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
+                       role: str | None = None):
+    """Frames -> (``pixel_values`` float32 CUDA tensor [sum N_i, 1176], ``image_grid_thw`` int64 tensor [B, 3]).
+
+    ``images``: one or a list of PIL images / paths / RGB uint8 HWC arrays / CUDA uint8 HWC tensors.
+    ``role``: None, or "inspector"/"auditor" to first apply that agent's thumbnail limit (2048 / 1024, LANCZOS).
+    """
+    import torch
+    eng = _engine()
+    if not isinstance(images, (list, tuple)):
+        images = [images]
+    frames = []
+    for im in images:
+        if isinstance(im, torch.Tensor):
+            t = im if im.is_cuda else im.cuda()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(_to_rgb_array(im))).cuda()
+        if role is not None:
+            h, w = int(t.shape[0]), int(t.shape[1])
+            limit = _ROLE_MAX_SIZE[role]
+            if max(h, w) > limit:
+                tw, th = G.thumbnail_size(w, h, limit)
+                if G.thumbnail_needs_reduce(w, h, tw, th):
+                    raise NotImplementedError("thumbnail box-reduce pre-pass (>= 4x downscale) is not implemented")
+                t = eng.resize_u8(t, th, tw, int(Image.Resampling.LANCZOS))
+        frames.append(t)
+    return eng.preprocess(frames, min_pixels=min_pixels, max_pixels=max_pixels)
+
+
+normalize = preprocess_for_vlm
+
+
+def draw_bounding_boxes(image_path: Path, boxes: list, output_path: Path, confidence_threshold: str = "low",
+                        criticality: str = "medium") -> Path:
+    """Annotated copy of ``image_path`` at ``output_path``: dashed/solid 2-px box, numbered marker, as the reference.
+
+    Raises ``ValueError("Failed to load image: ...")`` when the file cannot be read; invalid boxes are skipped with a
+    warning (never raised), exactly like the reference.
+    """
+    import cv2
+    import torch
+    img = cv2.imread(str(image_path))
+    if img is None:
+        raise ValueError(f"Failed to load image: {image_path}")
+    dev = torch.from_numpy(img).cuda()
+    _engine().annotate([dev], [boxes], confidence_threshold, criticality, inplace=True)
+    cv2.imwrite(str(output_path), dev.cpu().numpy())
+    return output_path

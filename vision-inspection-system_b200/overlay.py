@@ -1,0 +1,100 @@
+"""Host logic of the defect overlay: the box handling of the reference's ``draw_bounding_boxes``
+(utils/image_utils.py:176-257) up to the point where it starts calling cv2, then expansion into leaf primitives
+through the C ABI (``vis_overlay_expand``).  Rasterisation itself is the CUDA kernel behind ``vis_overlay_draw``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import numpy as np
+
+from . import _native as N
+
+logger = logging.getLogger("vision_inspection_system_b200.overlay")
+
+_CONFIDENCE_LEVELS = {"low": 1, "medium": 2, "high": 3}
+_RED_BGR = (0, 0, 255)               # CRITICAL / MODERATE (utils/image_utils.py:250)
+_COSMETIC_BGR = (0, 200, 255)        # COSMETIC (utils/image_utils.py:252)
+
+
+def filter_by_confidence(boxes, confidence_threshold: str = "low", criticality: str = "medium") -> list:
+    """utils/image_utils.py:177-189: keep boxes at or above the threshold, or everything when criticality is high."""
+    threshold = _CONFIDENCE_LEVELS.get(confidence_threshold, 1)
+    kept = []
+    for box in boxes:
+        level = _CONFIDENCE_LEVELS.get(box.get("confidence", "medium"), 2)
+        if level >= threshold or criticality == "high":
+            kept.append(box)
+        else:
+            logger.debug("Skipping low-confidence defect: %s (confidence=%s)", box.get("type", "unknown"),
+                         box.get("confidence", "medium"))
+    return kept
+
+
+def boxes_to_pixels(boxes, img_width: int, img_height: int, confidence_threshold: str = "low",
+                    criticality: str = "medium") -> np.ndarray:
+    """Percent boxes -> ``VisBox`` records, skipping (with a warning) exactly the boxes the reference skips."""
+    out = []
+    for i, box in enumerate(filter_by_confidence(boxes, confidence_threshold, criticality)):
+        raw_x, raw_y = box.get("x", 0), box.get("y", 0)
+        raw_w, raw_h = box.get("width", 10), box.get("height", 10)
+        if not (0 <= raw_x <= 100 and 0 <= raw_y <= 100 and 0 < raw_w <= 100 and 0 < raw_h <= 100):
+            logger.warning("Invalid bbox coordinates (out of 0-100 range): %s", box)
+            continue
+        if raw_x + raw_w > 100 or raw_y + raw_h > 100:
+            logger.warning("Bbox exceeds image bounds: x+width=%s, y+height=%s", raw_x + raw_w, raw_y + raw_h)
+            continue
+        area_percent = (raw_w * raw_h) / 100.0
+        if area_percent < 0.1:
+            logger.warning("Bbox too small (area=%.2f%%) - skipping: %s", area_percent, box)
+            continue
+        if area_percent > 50.0:
+            logger.warning("Bbox too large (area=%.2f%%) - likely error, skipping: %s", area_percent, box)
+            continue
+        x = int((raw_x / 100.0) * img_width)          # int() truncation, as the reference
+        y = int((raw_y / 100.0) * img_height)
+        w = int((raw_w / 100.0) * img_width)
+        h = int((raw_h / 100.0) * img_height)
+        x = min(max(0, x), img_width - 1)
+        y = min(max(0, y), img_height - 1)
+        w = min(w, img_width - x)
+        h = min(h, img_height - y)
+        if w <= 0 or h <= 0:
+            logger.warning("Bbox invalid after clamping, skipping: %s", box)
+            continue
+        label_full = box.get("label", f"#{i + 1}")    # index over the confidence-filtered list
+        try:
+            label_text = label_full.replace("#", "")
+        except Exception:
+            label_text = str(i + 1)
+        color = _COSMETIC_BGR if box.get("severity", "MODERATE") == "COSMETIC" else _RED_BGR
+        dashed = box.get("confidence", "medium") == "low"
+        encoded = label_text.encode("latin-1", "replace")
+        if len(encoded) > 11:
+            raise ValueError(f"overlay label too long (max 11 characters): {label_text!r}")
+        out.append((x, y, w, h, color[0], color[1], color[2], 1 if dashed else 0, encoded))
+    arr = np.zeros(len(out), N.BOX_DTYPE)
+    for j, rec in enumerate(out):
+        arr[j] = rec
+    return arr
+
+
+def expand_leaves(pixel_boxes: np.ndarray, img_width: int, img_height: int) -> np.ndarray:
+    """``VisBox`` records of one frame -> its leaf array (group headers first) via ``vis_overlay_expand``."""
+    L = N.lib()
+    n = len(pixel_boxes)
+    if n == 0:
+        return np.zeros(0, N.LEAF_DTYPE)
+    boxes = np.ascontiguousarray(pixel_boxes)
+    cap = 4096 * n
+    while True:
+        leaves = np.zeros(cap, N.LEAF_DTYPE)
+        needed = C.c_int(0)
+        rc = L.vis_overlay_expand(img_height, img_width, boxes.ctypes.data_as(C.c_void_p), n,
+                                  leaves.ctypes.data_as(C.c_void_p), cap, C.byref(needed))
+        if rc == N.VIS_E_CAPACITY:
+            cap = needed.value
+            continue
+        N.check(rc, "vis_overlay_expand")
+        return leaves[:rc]
