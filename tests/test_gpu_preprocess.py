@@ -1,0 +1,163 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Bar: image_grid_thw, patch order and every pixel_values bit identical (integer resample + exact LUT), which is
+stricter than BASELINE.json's 1e-5 post-normalisation tolerance; the tolerance is asserted as well.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_frame
+from oracle import qwen2vl as Q
+from vision_inspection_system_b200 import geometry as G
+from vision_inspection_system_b200 import synth
+
+pytestmark = pytest.mark.gpu
+POST_NORM_TOL = 1e-5          # BASELINE.json north_star: max-abs on fp32 pixel_values
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run(engine, frames, **kw):
+    dev = [torch.from_numpy(np.ascontiguousarray(f)).cuda() for f in frames]
+    pv, grid = engine.preprocess(dev, **kw)
+    torch.cuda.synchronize()
+    return pv.cpu().numpy(), grid.numpy()
+
+
+def check_equal(got, want, what):
+    assert got.shape == want.shape, what
+    assert float(np.abs(got - want).max()) <= POST_NORM_TOL, what
+    assert np.array_equal(got, want), f"{what}: within tolerance but not bit-exact"
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_goldens(engine, goldens, arrays, force_generic):
+    for rec in goldens["qwen"]:
+        frame = golden_frame(rec, arrays)
+        kw = {} if rec["max_pixels"] is None else {"max_pixels": rec["max_pixels"]}
+        pv, grid = run(engine, [frame], force_generic=force_generic, **kw)
+        assert grid[0].tolist() == rec["grid_thw"], rec["name"]
+        assert np.array_equal(pv[rec["sample_rows"]], arrays[f"qwen_{rec['name']}_samples"]), rec["name"]
+        assert sha(pv) == rec["sha256"], rec["name"]
+
+
+def test_fused_path_is_taken_for_the_benchmark_geometry(engine):
+    f = torch.from_numpy(synth.noise_frame(1234, 1080, 1920)).cuda()
+    plan = engine.plan_batch([f])
+    assert len(plan.fused) == 1 and not plan.generic
+    engine.preprocess([f])
+    assert engine.last_launches == 1
+
+
+@pytest.mark.parametrize("shape,max_pixels", [
+    ((1080, 1920), G.DEFAULT_MAX_PIXELS), ((1080, 1920), G.HUB_MAX_PIXELS), ((2160, 3840), G.DEFAULT_MAX_PIXELS),
+    ((720, 1280), G.DEFAULT_MAX_PIXELS), ((480, 640), G.DEFAULT_MAX_PIXELS), ((1536, 2048), G.DEFAULT_MAX_PIXELS),
+    ((1152, 2048), G.DEFAULT_MAX_PIXELS), ((576, 1024), G.DEFAULT_MAX_PIXELS), ((100, 502), G.DEFAULT_MAX_PIXELS),
+    ((64, 96), G.DEFAULT_MAX_PIXELS), ((28, 5600), G.DEFAULT_MAX_PIXELS), ((3000, 20), G.DEFAULT_MAX_PIXELS),
+    ((1, 1), G.DEFAULT_MAX_PIXELS), ((2160, 3840), G.HUB_MAX_PIXELS)])
+def test_against_oracle(engine, shape, max_pixels):
+    frame = synth.noise_frame(hash(shape) % 1000, *shape)
+    want, wgrid = Q.preprocess([frame], max_pixels=max_pixels)
+    for vsplit in (None, 1, 3):
+        pv, grid = run(engine, [frame], max_pixels=max_pixels, vsplit=vsplit)
+        assert np.array_equal(grid, wgrid)
+        check_equal(pv, want, (shape, max_pixels, vsplit))
+
+
+def test_padded_pitch_and_unaligned_views(engine):
+    base = synth.noise_frame(77, 300, 640)
+    want, _ = Q.preprocess([base])
+    padded = torch.zeros((300, 656, 3), dtype=torch.uint8, device="cuda")          # pitch 1968 = 16 * 123
+    padded[:, :640] = torch.from_numpy(base).cuda()
+    pv, _ = engine.preprocess([padded[:, :640]])
+    check_equal(pv.cpu().numpy(), want, "padded pitch (fused)")
+    odd = torch.zeros((300, 641, 3), dtype=torch.uint8, device="cuda")             # pitch 1923: generic path
+    odd[:, :640] = torch.from_numpy(base).cuda()
+    plan = engine.plan_batch([odd[:, :640]])
+    assert plan.generic and not plan.fused
+    pv, _ = engine.preprocess([odd[:, :640]])
+    check_equal(pv.cpu().numpy(), want, "unaligned pitch (generic)")
+
+
+def test_mixed_resolution_batch(engine):
+    shapes = synth.mixed_resolution_shapes(10, seed=9000) + [(3000, 20), (56, 56)]
+    frames = [synth.noise_frame(500 + i, *s) for i, s in enumerate(shapes)]
+    want, wgrid = Q.preprocess(frames)
+    pv, grid = run(engine, frames)
+    assert np.array_equal(grid, wgrid)
+    check_equal(pv, want, "mixed batch")
+
+
+def test_uniform_batch_tensor_and_out_buffer(engine):
+    frames = synth.frames_1080p(5)
+    want, wgrid = Q.preprocess(list(frames))
+    batch = torch.from_numpy(frames).cuda()
+    out = torch.empty((want.shape[0], 1176), dtype=torch.float32, device="cuda")
+    pv, grid = engine.preprocess(batch, out=out)
+    assert pv.data_ptr() == out.data_ptr()
+    assert np.array_equal(grid.numpy(), wgrid)
+    check_equal(pv.cpu().numpy(), want, "uniform batch")
+    pv2, _ = engine.preprocess(batch)                      # cached plan, fresh output
+    assert torch.equal(pv, pv2)
+    with pytest.raises(ValueError):
+        engine.preprocess(batch, out=torch.empty((3, 1176), dtype=torch.float32, device="cuda"))
+
+
+def test_full_size_batch_properties(engine):
+    """BASELINE config 2 at full size (256 x 1080p): size-independent properties instead of a full oracle run."""
+    n = 256
+    base = synth.frames_1080p(8)
+    batch = torch.from_numpy(base).cuda().repeat(n // 8, 1, 1, 1)          # frame i == frame i % 8
+    pv, grid = engine.preprocess(batch)
+    torch.cuda.synchronize()
+    rows = 52 * 94
+    assert pv.shape == (n * rows, 1176) and grid.shape == (n, 3) and (grid == torch.tensor([1, 52, 94])).all()
+    ref8, _ = Q.preprocess(list(base))
+    got = pv.view(n, rows, 1176)
+    assert torch.equal(got[:8].cpu(), torch.from_numpy(ref8).view(8, rows, 1176))           # oracle on the first 8
+    assert torch.equal(got, got[:8].repeat(n // 8, 1, 1))                                    # replicas identical
+    v = pv.view(-1, 3, 2, 14, 14)
+    assert torch.equal(v[:, :, 0], v[:, :, 1])                                               # temporal duplicate
+    lut = torch.from_numpy(Q.normalize_lut()).cuda().view(256, 3)
+    for c in range(3):                                                                       # only table values occur
+        assert torch.isin(v[::97, c].reshape(-1), lut[:, c]).all()
+
+
+def test_constant_and_extreme_frames(engine):
+    lut = Q.normalize_lut().reshape(256, 3)
+    for value in (0, 255, 128):
+        f = np.full((480, 640, 3), value, np.uint8)
+        pv, _ = run(engine, [f])
+        for c in range(3):
+            assert np.all(pv.reshape(-1, 3, 392)[:, c] == lut[value, c])
+
+
+def test_error_behaviour(engine):
+    with pytest.raises(TypeError):
+        engine.preprocess([torch.zeros((10, 10, 3), dtype=torch.uint8)])                    # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        engine.preprocess([torch.zeros((10, 2001, 3), dtype=torch.uint8, device="cuda")])   # aspect ratio > 200
+    with pytest.raises(ValueError):
+        engine.preprocess([])
+
+
+def test_image_utils_preprocess_for_vlm(engine, arrays, goldens):
+    from PIL import Image
+    from vision_inspection_system_b200 import image_utils as IU
+    rec = next(r for r in goldens["qwen"] if r["name"] == "mouri")
+    pv, grid = IU.preprocess_for_vlm(Image.fromarray(arrays["mouri_rgb"]))
+    assert grid.tolist() == [rec["grid_thw"]] and sha(pv.cpu().numpy()) == rec["sha256"]
+    pv2, _ = IU.normalize([arrays["mouri_rgb"]])
+    assert torch.equal(pv, pv2)
+    # dual Inspector / Auditor inputs (BASELINE config 5): agent thumbnail, then the Qwen2-VL processor
+    frame = synth.noise_frame(31, 2160, 3840)
+    for role, limit in (("inspector", 2048), ("auditor", 1024)):
+        want, wgrid = Q.preprocess([Q.agent_thumbnail(frame, limit)])
+        got, ggrid = IU.preprocess_for_vlm(frame, role=role)
+        assert np.array_equal(ggrid.numpy(), wgrid)
+        check_equal(got.cpu().numpy(), want, role)

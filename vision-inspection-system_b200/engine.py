@@ -66,6 +66,7 @@ class Engine:
         self._dev_tables: dict = {}
         self._geoms: dict = {}
         self._batch_plans: dict = {}
+        self._staging: dict = {}
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.last_launches = 0           # kernels launched by the most recent public call
 
@@ -264,6 +265,53 @@ class Engine:
             launches += 1
         self.last_launches = launches
         return out, plan.grid_thw
+
+    def preprocess_host(self, host_frames: torch.Tensor, min_pixels: int = G.DEFAULT_MIN_PIXELS,
+                        max_pixels: int = G.DEFAULT_MAX_PIXELS, out: torch.Tensor | None = None, chunk: int = 32):
+        """Same as ``preprocess`` for a HOST batch ``[B, H, W, 3]`` uint8 (pinned memory recommended).
+
+        Frames are copied to the device in chunks on a side stream into two staging buffers while the previous
+        chunk is being processed, so the PCIe transfer and the kernel overlap.  ``pixel_values`` stays on the device
+        (its consumer is the vision tower); ``image_grid_thw`` is returned on the host.
+        """
+        if host_frames.is_cuda or host_frames.dtype != torch.uint8 or host_frames.dim() != 4 or host_frames.shape[3] != 3:
+            raise TypeError("preprocess_host expects a CPU uint8 [B, H, W, 3] tensor")
+        if not host_frames.is_contiguous():
+            host_frames = host_frames.contiguous()
+        b, h, w, _ = (int(v) for v in host_frames.shape)
+        dh, dw = G.smart_resize(h, w, G.FACTOR, min_pixels, max_pixels)
+        rows = (dh // G.PATCH_SIZE) * (dw // G.PATCH_SIZE)
+        if out is None:
+            out = torch.empty((b * rows, G.ROW_FLOATS), dtype=torch.float32, device=self.device)
+        chunk = max(1, min(chunk, b))
+        key = (chunk, h, w)
+        st = self._staging.get(key)
+        if st is None:
+            st = self._staging[key] = {
+                "buf": [torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)],
+                "ready": [torch.cuda.Event() for _ in range(2)],
+                "free": [torch.cuda.Event() for _ in range(2)],
+                "stream": torch.cuda.Stream(device=self.device)}
+        cur = torch.cuda.current_stream()
+        copy_stream = st["stream"]
+        for ev in st["free"]:
+            ev.record(cur)
+        launches = 0
+        for i, c0 in enumerate(range(0, b, chunk)):
+            n = min(chunk, b - c0)
+            slot = i & 1
+            buf = st["buf"][slot]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(st["free"][slot])
+                buf[:n].copy_(host_frames[c0:c0 + n], non_blocking=True)
+                st["ready"][slot].record(copy_stream)
+            cur.wait_event(st["ready"][slot])
+            self.preprocess(buf[:n], min_pixels, max_pixels, out=out[c0 * rows:(c0 + n) * rows])
+            launches += self.last_launches
+            st["free"][slot].record(cur)
+        self.last_launches = launches
+        grid = torch.tensor([G.grid_thw(dh, dw)] * b, dtype=torch.int64)
+        return out, grid
 
     # ------------------------------------------------------------------ defect overlay
     def plan_overlay(self, shapes, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium"):
