@@ -29,26 +29,29 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 32;          // input rows per chunk == warp width (lane = row in phase H)
 constexpr int kStepPx = 16;         // input pixels per unrolled step (48 B)
 constexpr int kMaxStripW = 336;     // output columns per strip (3 * 336 / 4 = 252 phase-V threads)
+constexpr int kPitch = kMaxStripW + 4;          // H-ring / output-tile row pitch: 340 = 4 * 85 (odd -> conflict free)
+constexpr int kHPlane = kChunk * kPitch;        // one channel plane of the H ring
+constexpr int kOPlane = VIS_PATCH * kPitch;     // one channel plane of the output tile (14 rows)
+constexpr int kVCap = 48;           // vertical records staged per chunk
 constexpr int kSmemBudget = 113 * 1024;   // two CTAs per SM
 
 struct Layout {                     // shared-memory carve-up, fixed per launch (host-computed maxima)
     int stage_pitch;                // bytes per staged input row, odd multiple of 16
-    int hring_pitch;                // bytes per H-ring row, 4 * odd
-    int off_hring, off_hrec, off_lut, off_mbar, total;
+    int off_hring, off_otile, off_hrec, off_vrec, off_lut, off_mbar, total;
 };
 
 __host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-inline Layout make_layout(int span_bytes, int strip_w, int hstride) {
+inline Layout make_layout(int span_bytes, int strip_w, int stride) {
     Layout L;
     L.stage_pitch = align_up(span_bytes, 16);
     if ((L.stage_pitch / 16) % 2 == 0) L.stage_pitch += 16;
-    L.hring_pitch = align_up(strip_w, 4);
-    if ((L.hring_pitch / 4) % 2 == 0) L.hring_pitch += 4;
     int off = kChunk * L.stage_pitch;
-    L.off_hring = off;  off += 3 * kChunk * L.hring_pitch;
+    L.off_hring = off;  off += 3 * kHPlane;
+    L.off_otile = off;  off += 3 * kOPlane;
     off = align_up(off, 16);
-    L.off_hrec = off;   off += (strip_w + 1) * hstride * 4;
+    L.off_hrec = off;   off += (strip_w + 1) * stride * 4;
+    L.off_vrec = off;   off += kVCap * stride * 4;
     L.off_lut = off;    off += 768 * 4;
     L.off_mbar = off;   off += 16;
     L.total = off;
@@ -88,16 +91,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void stg64(float* p, float a, float b) {
-    asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void stg128(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ int clip8i(int acc) { return min(max(acc >> VIS_PRECISION_BITS, 0), 255); }
+// clip8 of Pillow: arithmetic >> 22, clamp to 0..255 (one VIMNMX.RELU)
+__device__ __forceinline__ int clip8i(int acc) { return __vimin_s32_relu(acc >> VIS_PRECISION_BITS, 255); }
 
 template <int KT>
 struct Rec {                        // one coefficient record held in registers (warp-uniform values)
@@ -106,7 +114,7 @@ struct Rec {                        // one coefficient record held in registers 
 };
 
 template <int KT, int STRIDE>
-__device__ __forceinline__ void load_rec_smem(Rec<KT>& r, const int* p) {
+__device__ __forceinline__ void load_rec(Rec<KT>& r, const int* p) {      // p: shared or global, 16-byte aligned
     int tmp[STRIDE];
 #pragma unroll
     for (int q = 0; q < STRIDE / 4; ++q) {
@@ -117,17 +125,31 @@ __device__ __forceinline__ void load_rec_smem(Rec<KT>& r, const int* p) {
     for (int t = 0; t < KT; ++t) r.k[t] = tmp[t];
     r.last = tmp[STRIDE - 1];
 }
-template <int KT, int STRIDE>
-__device__ __forceinline__ void load_rec_gmem(Rec<KT>& r, const int* p) {
-    int tmp[STRIDE];
-#pragma unroll
-    for (int q = 0; q < STRIDE / 4; ++q) {
-        const int4 v = __ldg(reinterpret_cast<const int4*>(p + 4 * q));
-        tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w;
+
+// One finished band of 14 output rows (a row of patches) -> pixel_values.  Thread t < 147 owns the 16-byte chunk
+// q = t % 49 of channel plane c = t / 49 in EVERY patch of the strip; it looks the four values up in the table
+// and writes the chunk to both temporal copies.  A warp therefore writes 512 contiguous bytes per store.
+__device__ __noinline__ void store_band(const unsigned char* __restrict__ otile, const float* __restrict__ lut,
+                                        float* __restrict__ band_out, int n_patches, int gx0) {
+    const int t = threadIdx.x;
+    if (t >= 147) return;
+    const int c = t / 49, q = t - c * 49;
+    const int f0 = 4 * q, f2 = f0 + 2;
+    const int pya = f0 / VIS_PATCH, pxa = f0 - pya * VIS_PATCH;
+    const int pyb = f2 / VIS_PATCH, pxb = f2 - pyb * VIS_PATCH;
+    const unsigned char* sa = otile + c * kOPlane + pya * kPitch + pxa;
+    const unsigned char* sb = otile + c * kOPlane + pyb * kPitch + pxb;
+    const float* l = lut + c * 256;
+    float* dst = band_out + c * 392 + f0;
+    for (int g = 0; g < n_patches; ++g) {
+        const int gx = gx0 + g;
+        const unsigned a = *reinterpret_cast<const unsigned short*>(sa + g * VIS_PATCH);
+        const unsigned b = *reinterpret_cast<const unsigned short*>(sb + g * VIS_PATCH);
+        const float v0 = l[a & 0xff], v1 = l[a >> 8], v2 = l[b & 0xff], v3 = l[b >> 8];
+        float* o = dst + (size_t)((gx >> 1) * 4 + (gx & 1)) * VIS_ROW_FLOATS;
+        stg128(o, v0, v1, v2, v3);
+        stg128(o + 196, v0, v1, v2, v3);
     }
-#pragma unroll
-    for (int t = 0; t < KT; ++t) r.k[t] = tmp[t];
-    r.last = tmp[STRIDE - 1];
 }
 
 // KT: taps per record (both axes), RING: register window (power of two >= KT), STRIDE: int32 slots per record
@@ -144,10 +166,11 @@ k_fused(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ strips
 
     unsigned char* stage = smem;
     unsigned char* hring = smem + L.off_hring;
+    unsigned char* otile = smem + L.off_otile;
     int* hrec = reinterpret_cast<int*>(smem + L.off_hrec);
-    float* lut = reinterpret_cast<float*>(smem + L.off_lut);
+    int* vrec_s = reinterpret_cast<int*>(smem + L.off_vrec);
+    float* lut = reinterpret_cast<float*>(smem + L.off_lut);          // transposed: lut[c * 256 + v]
     const uint32_t mbar = smem_u32(smem + L.off_mbar);
-    const int hplane = kChunk * L.hring_pitch;
 
     // ---- prologue: records of this strip, table, barrier ----
     {
@@ -155,7 +178,7 @@ k_fused(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ strips
         int4* dst = reinterpret_cast<int4*>(hrec);
         const int n4 = (sw + 1) * STRIDE / 4;
         for (int i = tid; i < n4; i += kThreads) dst[i] = __ldg(src + i);
-        for (int i = tid; i < 768; i += kThreads) lut[i] = __ldg(lut768 + i);
+        for (int i = tid; i < 768; i += kThreads) lut[(i % 3) * 256 + i / 3] = __ldg(lut768 + i);
         if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     }
     __syncthreads();
@@ -190,46 +213,40 @@ k_fused(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ strips
     const int xa = x0 + (int)((int64_t)sw * warp / kWarps);
     const int xb = x0 + (int)((int64_t)sw * (warp + 1) / kWarps);
 
-    // ---- phase-V constants: this thread's 4 output columns of one channel ----
+    // ---- phase-V constants: this thread's 4 output columns of one channel (idle threads shadow thread 0) ----
     const int wpr = sw / 4;                       // words per plane row
     const bool v_active = tid < 3 * wpr;
     const int vc = v_active ? tid / wpr : 0;
     const int vwx = v_active ? tid - vc * wpr : 0;
-    const float* lutc = lut + vc;
-    float* out_a;
-    float* out_b;
-    {
-        const int xA = x0 + vwx * 4, xB = xA + 2;
-        const int gA = xA / VIS_PATCH, gB = xB / VIS_PATCH;
-        float* base = pixel_values + (size_t)fr.row0 * VIS_ROW_FLOATS + vc * 392;
-        out_a = base + (size_t)((gA >> 1) * 4 + (gA & 1)) * VIS_ROW_FLOATS + (xA - gA * VIS_PATCH);
-        out_b = base + (size_t)((gB >> 1) * 4 + (gB & 1)) * VIS_ROW_FLOATS + (xB - gB * VIS_PATCH);
-    }
     const int half_gw = fr.dst_w / (2 * VIS_PATCH);
+    const int n_patches = sw / VIS_PATCH, gx0 = x0 / VIS_PATCH;
+    float* const frame_out = pixel_values + (size_t)fr.row0 * VIS_ROW_FLOATS;
     int vring[RING][4];
 #pragma unroll
     for (int s = 0; s < RING; ++s) { vring[s][0] = vring[s][1] = vring[s][2] = vring[s][3] = 0; }
-    int yo = y0;
+    int yo = y0;                                  // next output row (uniform across the CTA)
+    int gy = y0 / VIS_PATCH, py = 0;              // its patch row and row inside the patch (y0 is a multiple of 14)
     Rec<KT> vr;
-    load_rec_gmem<KT, STRIDE>(vr, vrec + (size_t)yo * STRIDE);
-    auto row_offset = [&](int y) -> size_t {
-        const int gy = y / VIS_PATCH, py = y - gy * VIS_PATCH;
-        return (size_t)((gy >> 1) * half_gw * 4 + (gy & 1) * 2) * VIS_ROW_FLOATS + py * VIS_PATCH;
-    };
-    size_t voff = row_offset(yo);
 
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
         const int r0 = r_first + chunk * kChunk;
+        // vertical records for the output rows this chunk can complete: [yo, yo + kVCap), asynchronously
+        const int yo_base = yo;
+        for (int i = tid; i < kVCap * STRIDE / 4; i += kThreads) {
+            const int rec = min(yo_base + i / (STRIDE / 4), fr.dst_h);            // clamp to the sentinel record
+            cp_async16(smem_u32(vrec_s + i * 4), vrec + (size_t)rec * STRIDE + (i % (STRIDE / 4)) * 4);
+        }
         mbar_wait(mbar, chunk & 1);
 
         // ================= phase H =================
         if (xa < xb) {
             int xo = xa;
             Rec<KT> hr;
-            load_rec_smem<KT, STRIDE>(hr, hrec + (xo - x0) * STRIDE);
-            int p = hrec[(xo - x0) * STRIDE + STRIDE - 2] & ~(kStepPx - 1);
+            const int* hp = hrec + (xo - x0) * STRIDE;
+            load_rec<KT, STRIDE>(hr, hp);
+            int p = hp[STRIDE - 2] & ~(kStepPx - 1);
             uint32_t saddr = smem_u32(stage + lane * L.stage_pitch) + (uint32_t)(p - px0) * 3;
-            unsigned char* hdst = hring + lane * L.hring_pitch - x0;
+            unsigned char* hdst = hring + lane * kPitch + (xo - x0);
             int ring[3][RING];
 #pragma unroll
             for (int s = 0; s < RING; ++s) { ring[0][s] = ring[1][s] = ring[2][s] = 0; }
@@ -258,33 +275,46 @@ k_fused(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ strips
                             a1 += ring[1][s] * hr.k[t];
                             a2 += ring[2][s] * hr.k[t];
                         }
-                        hdst[xo] = (unsigned char)clip8i(a0);
-                        hdst[hplane + xo] = (unsigned char)clip8i(a1);
-                        hdst[2 * hplane + xo] = (unsigned char)clip8i(a2);
+                        hdst[0] = (unsigned char)clip8i(a0);
+                        hdst[kHPlane] = (unsigned char)clip8i(a1);
+                        hdst[2 * kHPlane] = (unsigned char)clip8i(a2);
+                        ++hdst;
                         ++xo;
-                        if (xo < xb) load_rec_smem<KT, STRIDE>(hr, hrec + (xo - x0) * STRIDE);
+                        hp += STRIDE;
+                        if (xo < xb) load_rec<KT, STRIDE>(hr, hp);
                         else hr.last = INT_MAX;
                     }
                 }
                 p += kStepPx;
             }
         }
-        __syncthreads();                           // H ring complete, stage buffer free
+        cp_async_wait_all();
+        __syncthreads();                           // H ring + vertical records complete, stage buffer free
         if (warp == 0 && chunk + 1 < n_chunks) issue_chunk(chunk + 1);
 
-        // ================= phase V =================
-        if (v_active) {
-            const unsigned char* hsrc = hring + vc * hplane + vwx * 4;
+        // ================= phase V (all threads, uniform control flow; idle threads do not store) =================
+        {
+            auto fetch_vrec = [&]() {
+                const int rel = yo - yo_base;
+                if (rel < kVCap) load_rec<KT, STRIDE>(vr, vrec_s + rel * STRIDE);
+                else load_rec<KT, STRIDE>(vr, vrec + (size_t)min(yo, fr.dst_h) * STRIDE);
+                if (yo >= y1) vr.last = INT_MAX;
+            };
+            fetch_vrec();
+            const unsigned char* hsrc = hring + vc * kHPlane + vwx * 4;
+            unsigned char* odst = otile + vc * kOPlane + vwx * 4;
 #pragma unroll 1
             for (int g = 0; g < kChunk / RING; ++g) {
                 if (r0 + g * RING >= r_end) break;
+                uint32_t words[RING];
+#pragma unroll
+                for (int u = 0; u < RING; ++u)
+                    words[u] = *reinterpret_cast<const uint32_t*>(hsrc + (g * RING + u) * kPitch);
 #pragma unroll
                 for (int u = 0; u < RING; ++u) {
-                    const int i = g * RING + u;
-                    const uint32_t word = *reinterpret_cast<const uint32_t*>(hsrc + i * L.hring_pitch);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) vring[u][e] = (int)__byte_perm(word, 0, 0x4440 + e);
-                    while (vr.last == r0 + i) {
+                    for (int e = 0; e < 4; ++e) vring[u][e] = (int)__byte_perm(words[u], 0, 0x4440 + e);
+                    while (vr.last == r0 + g * RING + u) {
                         int acc[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) acc[e] = 1 << (VIS_PRECISION_BITS - 1);
@@ -294,20 +324,20 @@ k_fused(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ strips
 #pragma unroll
                             for (int e = 0; e < 4; ++e) acc[e] += vring[s][e] * vr.k[t];
                         }
-                        float f[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) f[e] = lutc[clip8i(acc[e]) * 3];
-                        stg64(out_a + voff, f[0], f[1]);
-                        stg64(out_a + voff + 196, f[0], f[1]);
-                        stg64(out_b + voff, f[2], f[3]);
-                        stg64(out_b + voff + 196, f[2], f[3]);
+                        const uint32_t lo = __byte_perm(clip8i(acc[0]), clip8i(acc[1]), 0x0040);
+                        const uint32_t hi = __byte_perm(clip8i(acc[2]), clip8i(acc[3]), 0x0040);
+                        if (v_active) *reinterpret_cast<uint32_t*>(odst + py * kPitch) = __byte_perm(lo, hi, 0x5410);
                         ++yo;
-                        if (yo < y1) {
-                            load_rec_gmem<KT, STRIDE>(vr, vrec + (size_t)yo * STRIDE);
-                            voff = row_offset(yo);
-                        } else {
-                            vr.last = INT_MAX;
+                        if (++py == VIS_PATCH) {               // a row of patches is complete: write it out
+                            __syncthreads();
+                            store_band(otile, lut,
+                                       frame_out + (size_t)((gy >> 1) * half_gw * 4 + (gy & 1) * 2) * VIS_ROW_FLOATS,
+                                       n_patches, gx0);
+                            __syncthreads();
+                            py = 0;
+                            ++gy;
                         }
+                        fetch_vrec();
                     }
                 }
             }
