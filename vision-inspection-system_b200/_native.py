@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libvis_b200.so"
+LIB_PATH = Path(os.environ["VIS_B200_LIB"]) if os.environ.get("VIS_B200_LIB") else PKG_DIR / "libvis_b200.so"   # override: developer A/B builds
 
 VIS_OK = 0
 VIS_E_INVALID = -1
