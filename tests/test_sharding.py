@@ -1,0 +1,71 @@
+"""Multi-GPU host logic on CPU: shard plans, and the optional gather over a world_size-2 gloo group."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vision_inspection_system_b200 import sharding as S
+from vision_inspection_system_b200 import synth
+
+
+def test_contiguous_shards_cover_everything():
+    for n in (0, 1, 7, 256, 1000):
+        for world in (1, 2, 4, 8):
+            got = [i for r in range(world) for i in S.contiguous_shard(n, r, world)]
+            assert got == list(range(n))
+            sizes = [len(S.contiguous_shard(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        S.contiguous_shard(4, 2, 2)
+
+
+def test_balanced_shards_on_config5_mix():
+    shapes = synth.mixed_resolution_shapes(8192, seed=9000)
+    costs = [S.frame_bytes(h, w) for h, w in shapes]
+    assert S.frame_bytes(1080, 1920) == 29213952
+    assert S.frame_bytes(2160, 3840) == 47876352
+    assert S.frame_bytes(1080, 1920, max_pixels=12845056) == 56854656
+    shards = S.balanced_shards(costs, 8)
+    assert sorted(i for s in shards for i in s) == list(range(8192))
+    loads = [sum(costs[i] for i in s) for s in shards]
+    assert (max(loads) - min(loads)) / max(loads) < 0.002           # greedy largest-first is tight on 8192 items
+    assert shards == S.balanced_shards(costs, 8)                    # deterministic: no communication needed
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        grids = [(1, int(a), int(b)) for a, b in rng.integers(1, 5, (7, 2)) * 2]
+        rows = [g[1] * g[2] for g in grids]
+        full = torch.arange(sum(rows) * 1176, dtype=torch.float32).reshape(-1, 1176)
+        starts = np.concatenate([[0], np.cumsum(rows)])
+        mine = S.balanced_shards(rows, world)[rank]
+        pv = torch.cat([full[starts[i]:starts[i + 1]] for i in mine]) if mine else full[:0]
+        grid = torch.tensor([grids[i] for i in mine], dtype=torch.int64).reshape(-1, 3)
+        out, ogrid = S.gather_patches(pv, grid, mine, dst=0)
+        if rank == 0:
+            q.put((torch.equal(out, full), ogrid.tolist() == [list(g) for g in grids]))
+        else:
+            q.put((out is None, ogrid is None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_patches_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(a and b for a, b in results)

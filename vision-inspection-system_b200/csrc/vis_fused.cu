@@ -154,7 +154,7 @@ __device__ __noinline__ void store_band(const unsigned char* __restrict__ otile,
 
 // KT: taps per record (both axes), RING: register window (power of two >= KT), STRIDE: int32 slots per record
 template <int KT, int RING, int STRIDE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, RING == 8 ? 2 : 1)   // 16-slot windows need > 128 registers
 k_fused(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ strips, Layout L,
         const float* __restrict__ lut768, float* __restrict__ pixel_values) {
     extern __shared__ __align__(128) unsigned char smem[];
