@@ -18,9 +18,19 @@
 //               temporal copies).
 //   The next chunk's bulk copies are issued between the two phases, so they overlap phase V and the other
 //   resident CTA.  Coefficient records are host-built (vis_pack_records): newest-tap-first, zero padded to KT.
-#include <climits>
+#include "vis_fused_common.cuh"
 
-#include "vis_internal.h"
+#include <cstdlib>
+#include <cstring>
+
+using namespace visf;
+
+namespace visf {   // warp-specialised variant, vis_fused_ws.cu
+int ws_layout_bytes(int span_bytes, int strip_w, int stride);
+int ws_smem_max();
+int ws_launch(int cls, const VisFrame* frames, const VisStrip* strips, int n_strips, int span_bytes, int strip_w,
+              const float* lut768, float* pixel_values, cudaStream_t st);
+}
 
 namespace {
 
@@ -40,8 +50,6 @@ struct Layout {                     // shared-memory carve-up, fixed per launch 
     int off_hring, off_otile, off_hrec, off_vrec, off_lut, off_mbar, total;
 };
 
-__host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
-
 inline Layout make_layout(int span_bytes, int strip_w, int stride) {
     Layout L;
     L.stage_pitch = align_up(span_bytes, 16);
@@ -56,74 +64,6 @@ inline Layout make_layout(int span_bytes, int strip_w, int stride) {
     L.off_mbar = off;   off += 16;
     L.total = off;
     return L;
-}
-
-// ---- PTX helpers -----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// spin with a watchdog: a lost bulk copy traps (reported as a CUDA error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void stg128(float* p, float a, float b, float c, float d) {
-    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// clip8 of Pillow: arithmetic >> 22, clamp to 0..255 (one VIMNMX.RELU)
-__device__ __forceinline__ int clip8i(int acc) { return __vimin_s32_relu(acc >> VIS_PRECISION_BITS, 255); }
-
-template <int KT>
-struct Rec {                        // one coefficient record held in registers (warp-uniform values)
-    int k[KT];
-    int last;
-};
-
-template <int KT, int STRIDE>
-__device__ __forceinline__ void load_rec(Rec<KT>& r, const int* p) {      // p: shared or global, 16-byte aligned
-    int tmp[STRIDE];
-#pragma unroll
-    for (int q = 0; q < STRIDE / 4; ++q) {
-        const int4 v = *reinterpret_cast<const int4*>(p + 4 * q);
-        tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w;
-    }
-#pragma unroll
-    for (int t = 0; t < KT; ++t) r.k[t] = tmp[t];
-    r.last = tmp[STRIDE - 1];
 }
 
 // One finished band of 14 output rows (a row of patches) -> pixel_values.  Thread t < 147 owns the 16-byte chunk
@@ -359,6 +299,14 @@ int launch(const VisFrame* frames, const VisStrip* strips, int n_strips, const L
 // taps -> kernel class
 inline int kt_class(int kt) { return kt <= 6 ? 6 : kt <= 8 ? 8 : kt <= 12 ? 12 : kt <= 16 ? 16 : 0; }
 
+// The warp-specialised persistent kernel serves the 8-slot tap classes; VIS_B200_FUSED=phased selects the
+// phase-synchronous kernel instead (developer A/B switch, read per call).
+inline bool use_ws(int cls) {
+    if (cls != 6 && cls != 8) return false;
+    const char* e = std::getenv("VIS_B200_FUSED");
+    return !(e && std::strcmp(e, "phased") == 0);
+}
+
 inline int span_bytes_for(const int32_t* hbounds, int x0, int x1) {
     const int px0 = hbounds[2 * x0] & ~(kStepPx - 1);
     const int px_last = hbounds[2 * (x1 - 1)] + hbounds[2 * (x1 - 1) + 1] - 1;
@@ -407,7 +355,9 @@ int vis_plan_strips(int frame_index, int dst_h, int dst_w, const int32_t* hbound
             worst_span = span > worst_span ? span : worst_span;
             worst_w = (b1 - b0) * 28 > worst_w ? (b1 - b0) * 28 : worst_w;
         }
-        if (make_layout(worst_span, worst_w, hstride).total <= kSmemBudget || per == 1) {
+        const bool fits = use_ws(cls) ? ws_layout_bytes(worst_span, worst_w, hstride) <= ws_smem_max()
+                                      : make_layout(worst_span, worst_w, hstride).total <= kSmemBudget;
+        if (fits || per == 1) {
             best_n = n;
             *span_bytes_out = worst_span;
             *strip_w_out = worst_w;
@@ -444,6 +394,9 @@ int vis_preprocess_fused(const VisFrame* frames, int n_frames, const VisStrip* s
         vis::set_error("vis_preprocess_fused: bad arguments (kt=%d span=%d strip_w=%d)", max_kt, max_span_bytes, max_strip_w);
         return cls == 0 ? VIS_E_UNSUPPORTED : VIS_E_INVALID;
     }
+    if (use_ws(cls))
+        return ws_launch(cls, frames, strips, n_strips, max_span_bytes, max_strip_w, lut768, pixel_values,
+                         (cudaStream_t)stream);
     const Layout L = make_layout(max_span_bytes, max_strip_w, vis_record_stride(cls));
     if (L.total > 227 * 1024) {
         vis::set_error("vis_preprocess_fused: %d bytes of shared memory needed", L.total);

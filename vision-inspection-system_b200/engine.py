@@ -206,7 +206,7 @@ class Engine:
         by_class: dict = {}
         for (kt, _), (g, idx) in groups.items():
             by_class.setdefault(kt, []).append((g, np.asarray(idx)))
-        want = 4 * 2 * self.sm_count                 # CTAs wanted: two per SM, a few waves
+        want = 3 * self.sm_count                     # work items wanted: a few per SM
         for kt, members in by_class.items():
             n_class = sum(len(idx) for _, idx in members)
             fr_parts, st_parts, span, strip_w, base = [], [], 0, 0, 0
