@@ -26,7 +26,7 @@
 using namespace visf;
 
 namespace visf {   // warp-specialised variant, vis_fused_ws.cu
-int ws_layout_bytes(int span_bytes, int strip_w, int stride);
+int ws_layout_bytes(int span_bytes, int strip_w, int cls);
 int ws_smem_max();
 int ws_launch(int cls, const VisFrame* frames, const VisStrip* strips, int n_strips, int span_bytes, int strip_w,
               const float* lut768, float* pixel_values, cudaStream_t st);
@@ -355,7 +355,7 @@ int vis_plan_strips(int frame_index, int dst_h, int dst_w, const int32_t* hbound
             worst_span = span > worst_span ? span : worst_span;
             worst_w = (b1 - b0) * 28 > worst_w ? (b1 - b0) * 28 : worst_w;
         }
-        const bool fits = use_ws(cls) ? ws_layout_bytes(worst_span, worst_w, hstride) <= ws_smem_max()
+        const bool fits = use_ws(cls) ? ws_layout_bytes(worst_span, worst_w, cls) <= ws_smem_max()
                                       : make_layout(worst_span, worst_w, hstride).total <= kSmemBudget;
         if (fits || per == 1) {
             best_n = n;

@@ -25,7 +25,8 @@ constexpr int kThreadsWS = (kHWarps + kVWarps + kSWarps + 1) * 32;      // 800
 constexpr int kVThreads = kVWarps * 32;
 constexpr int kChunk = 32, kStepPx = 16, kMaxStripW = 336;
 constexpr int kPitch = kMaxStripW + 4;            // 340 = 4 * 85: conflict-free lane = row byte stores
-constexpr int kHPlane = kChunk * kPitch, kOPlane = VIS_PATCH * kPitch;
+constexpr int kOPitch = kMaxStripW;               // band tile rows: word stores / u16 loads only, no padding needed
+constexpr int kOPlane = VIS_PATCH * kOPitch;
 constexpr int kVCap = 48;
 constexpr int kSmemMax = 227 * 1024;
 
@@ -33,12 +34,14 @@ enum Bar { SF = 0, SE = 2, HF = 4, HE = 6, OF = 8, OE = 10, kBars = 12 };   // f
 
 struct LayoutWS {
     int stage_pitch;
+    int hplane;                                    // bytes of one channel plane of an H-ring slot: (carry + 32) rows
     int off_stage, off_hring, off_otile, off_hrec, off_vrec, off_lut, off_bar, total;
     int stage_slot, hrec_slot, vrec_slot;          // bytes per ring slot
 };
 
-inline LayoutWS make_layout_ws(int span_bytes, int strip_w, int stride) {
+inline LayoutWS make_layout_ws(int span_bytes, int strip_w, int stride, int carry) {
     LayoutWS L;
+    L.hplane = (carry + kChunk) * kPitch;
     L.stage_pitch = align_up(span_bytes, 16);
     if ((L.stage_pitch / 16) % 2 == 0) L.stage_pitch += 16;
     L.stage_slot = kChunk * L.stage_pitch;
@@ -46,7 +49,7 @@ inline LayoutWS make_layout_ws(int span_bytes, int strip_w, int stride) {
     L.vrec_slot = kVCap * stride * 4;
     int off = 0;
     L.off_stage = off; off += 2 * L.stage_slot;
-    L.off_hring = off; off += 2 * 3 * kHPlane;
+    L.off_hring = off; off += 2 * 3 * L.hplane;
     L.off_otile = off; off += 2 * 3 * kOPlane;
     off = align_up(off, 16);
     L.off_hrec = off;  off += 2 * L.hrec_slot;
@@ -144,7 +147,7 @@ k_fused_ws(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ str
                 mbar_wait(bar(SF, slot), j & 1);
                 if (k >= 2) mbar_wait(bar(HE, slot), (j - 1) & 1);
                 const unsigned char* stage = smem + L.off_stage + slot * L.stage_slot;
-                unsigned char* hring = smem + L.off_hring + slot * 3 * kHPlane;
+                unsigned char* hring = smem + L.off_hring + slot * 3 * L.hplane + (KT - 1) * kPitch;   // rows after the carry area
                 if (xa < xb) {
                     int xo = xa;
                     Rec<KT> hr;
@@ -182,8 +185,8 @@ k_fused_ws(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ str
                                     a2 += ring[2][q] * hr.k[tt];
                                 }
                                 hdst[0] = (unsigned char)clip8i(a0);
-                                hdst[kHPlane] = (unsigned char)clip8i(a1);
-                                hdst[2 * kHPlane] = (unsigned char)clip8i(a2);
+                                hdst[L.hplane] = (unsigned char)clip8i(a1);
+                                hdst[2 * L.hplane] = (unsigned char)clip8i(a2);
                                 ++hdst;
                                 ++xo;
                                 hp += STRIDE;
@@ -202,7 +205,11 @@ k_fused_ws(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ str
             }
         }
     } else if (warp < kHWarps + kVWarps) {
-        // ============================== vertical pass ==============================
+        // ============================== vertical pass (pull order) ==============================
+        // Thread = 4 consecutive output columns of one channel.  For every output row whose tap window ends inside
+        // this chunk it reads the KT tap rows straight from the H ring: the slot holds KT-1 carry rows (copies of the
+        // previous chunk's last rows) directly in front of the 32 fresh rows, so a window never leaves the slot.
+        constexpr int CARRY = KT - 1;
         const int v = tid - kHWarps * 32;
         int k = 0, nb = 0;
         for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
@@ -212,11 +219,7 @@ k_fused_ws(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ str
             const bool v_active = v < 3 * wpr;
             const int vc = v_active ? v / wpr : 0;
             const int vwx = v_active ? v - vc * wpr : 0;
-            int vring[RING][4];
-#pragma unroll
-            for (int q = 0; q < RING; ++q) { vring[q][0] = vring[q][1] = vring[q][2] = vring[q][3] = 0; }
             int yo = t.y0, py = 0;
-            Rec<KT> vr;
             auto stage_vrec = [&](int buf, int first) {          // records [first, first + kVCap) -> vrec ring
                 int* dst = reinterpret_cast<int*>(smem + L.off_vrec + buf * L.vrec_slot);
                 for (int i = v; i < kVCap * STRIDE / 4; i += kVThreads) {
@@ -228,59 +231,68 @@ k_fused_ws(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ str
             for (int c = 0; c < t.n_chunks; ++c, ++k) {
                 const int slot = k & 1, j = k >> 1;
                 const int r0 = t.r_first + c * kChunk;
+                const int r_lim = r0 + kChunk;                   // windows ending before this row are complete
                 cp_async_wait_all();
-                named_bar_sync(1, kVThreads);                    // this chunk's records are visible to all V warps
+                named_bar_sync(1, kVThreads);                    // records + carry rows visible to all V warps
                 mbar_wait(bar(HF, slot), j & 1);
                 const int* vrec_s = reinterpret_cast<const int*>(smem + L.off_vrec + slot * L.vrec_slot);
                 const int yo_base = yo;
-                auto fetch_vrec = [&]() {
-                    const int rel = yo - yo_base;
-                    if (rel < kVCap) load_rec<KT, STRIDE>(vr, vrec_s + rel * STRIDE);
-                    else load_rec<KT, STRIDE>(vr, vrec + (size_t)min(yo, t.fr.dst_h) * STRIDE);
-                    if (yo >= t.y1) vr.last = INT_MAX;
+                const unsigned char* hbase = smem + L.off_hring + slot * 3 * L.hplane + vc * L.hplane + vwx * 4
+                                             + (CARRY - r0) * kPitch;       // + row * kPitch addresses input row `row`
+                auto fetch = [&](Rec<KT>& r, int y) {
+                    const int rel = y - yo_base;
+                    if (rel < kVCap) load_rec<KT, STRIDE>(r, vrec_s + rel * STRIDE);
+                    else load_rec<KT, STRIDE>(r, vrec + (size_t)min(y, t.fr.dst_h) * STRIDE);
+                    if (y >= t.y1) r.last = INT_MAX;
                 };
-                fetch_vrec();
-                const unsigned char* hsrc = smem + L.off_hring + slot * 3 * kHPlane + vc * kHPlane + vwx * 4;
-#pragma unroll 1
-                for (int g = 0; g < kChunk / RING; ++g) {
-                    if (r0 + g * RING >= t.r_end) break;
-                    uint32_t words[RING];
+                auto emit = [&](const Rec<KT>& r) {
+                    const unsigned char* hrow = hbase + r.last * kPitch;
+                    uint32_t wv[KT];
 #pragma unroll
-                    for (int u = 0; u < RING; ++u)
-                        words[u] = *reinterpret_cast<const uint32_t*>(hsrc + (g * RING + u) * kPitch);
+                    for (int tt = 0; tt < KT; ++tt) wv[tt] = *reinterpret_cast<const uint32_t*>(hrow - tt * kPitch);
+                    int acc[4];
 #pragma unroll
-                    for (int u = 0; u < RING; ++u) {
+                    for (int e = 0; e < 4; ++e) acc[e] = 1 << (VIS_PRECISION_BITS - 1);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) vring[u][e] = (int)__byte_perm(words[u], 0, 0x4440 + e);
-                        while (vr.last == r0 + g * RING + u) {
-                            int acc[4];
+                    for (int tt = 0; tt < KT; ++tt) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) acc[e] = 1 << (VIS_PRECISION_BITS - 1);
+                        for (int e = 0; e < 4; ++e) acc[e] += (int)__byte_perm(wv[tt], 0, 0x4440 + e) * r.k[tt];
+                    }
+                    const uint32_t lo = __byte_perm(clip8i(acc[0]), clip8i(acc[1]), 0x0040);
+                    const uint32_t hi = __byte_perm(clip8i(acc[2]), clip8i(acc[3]), 0x0040);
+                    const int os = nb & 1;
+                    if (py == 0 && nb >= 2) mbar_wait(bar(OE, os), ((nb >> 1) - 1) & 1);   // band tile free?
+                    if (v_active)
+                        *reinterpret_cast<uint32_t*>(smem + L.off_otile + os * 3 * kOPlane + vc * kOPlane +
+                                                     py * kOPitch + vwx * 4) = __byte_perm(lo, hi, 0x5410);
+                    ++yo;
+                    if (++py == VIS_PATCH) {                      // band complete: hand it to the store warps
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(OF, os));
+                        ++nb;
+                        py = 0;
+                    }
+                };
+                Rec<KT> ra, rb;                                   // alternate: the next record is always in flight
+                fetch(ra, yo);
+                while (true) {
+                    if (ra.last >= r_lim) break;
+                    fetch(rb, yo + 1);
+                    emit(ra);
+                    if (rb.last >= r_lim) break;
+                    fetch(ra, yo + 1);
+                    emit(rb);
+                }
+                if (c + 1 < t.n_chunks) {
+                    stage_vrec((k + 1) & 1, yo);
+                    if (v_active) {                               // carry: last KT-1 rows -> front of the other slot
+                        const unsigned char* src = smem + L.off_hring + slot * 3 * L.hplane + vc * L.hplane + vwx * 4 + kChunk * kPitch;
+                        unsigned char* dst = smem + L.off_hring + (slot ^ 1) * 3 * L.hplane + vc * L.hplane + vwx * 4;
 #pragma unroll
-                            for (int tt = 0; tt < KT; ++tt) {
-                                const int q = (u - tt) & (RING - 1);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) acc[e] += vring[q][e] * vr.k[tt];
-                            }
-                            const uint32_t lo = __byte_perm(clip8i(acc[0]), clip8i(acc[1]), 0x0040);
-                            const uint32_t hi = __byte_perm(clip8i(acc[2]), clip8i(acc[3]), 0x0040);
-                            const int os = nb & 1;
-                            if (py == 0 && nb >= 2) mbar_wait(bar(OE, os), ((nb >> 1) - 1) & 1);   // band tile free?
-                            if (v_active)
-                                *reinterpret_cast<uint32_t*>(smem + L.off_otile + os * 3 * kOPlane + vc * kOPlane +
-                                                             py * kPitch + vwx * 4) = __byte_perm(lo, hi, 0x5410);
-                            ++yo;
-                            if (++py == VIS_PATCH) {              // band complete: hand it to the store warps
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(bar(OF, os));
-                                ++nb;
-                                py = 0;
-                            }
-                            fetch_vrec();
-                        }
+                        for (int i = 0; i < CARRY; ++i)
+                            *reinterpret_cast<uint32_t*>(dst + i * kPitch) = *reinterpret_cast<const uint32_t*>(src + i * kPitch);
                     }
                 }
-                if (c + 1 < t.n_chunks) stage_vrec((k + 1) & 1, yo);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(HE, slot));       // H-ring slot consumed
             }
@@ -296,8 +308,8 @@ k_fused_ws(const VisFrame* __restrict__ frames, const VisStrip* __restrict__ str
             const int c = item / 49, q = item - c * 49;
             const int f0 = 4 * q, f2 = f0 + 2;
             const int pya = f0 / VIS_PATCH, pyb = f2 / VIS_PATCH;
-            sa[i] = c * kOPlane + pya * kPitch + (f0 - pya * VIS_PATCH);
-            sb[i] = c * kOPlane + pyb * kPitch + (f2 - pyb * VIS_PATCH);
+            sa[i] = c * kOPlane + pya * kOPitch + (f0 - pya * VIS_PATCH);
+            sb[i] = c * kOPlane + pyb * kOPitch + (f2 - pyb * VIS_PATCH);
             go[i] = c * 392 + f0;
             lo[i] = c * 256;
         }
@@ -353,12 +365,14 @@ int launch_ws(const VisFrame* frames, const VisStrip* strips, int n_strips, cons
 namespace visf {
 
 // host hooks used by vis_fused.cu (planning and dispatch)
-int ws_layout_bytes(int span_bytes, int strip_w, int stride) { return make_layout_ws(span_bytes, strip_w, stride).total; }
+int ws_layout_bytes(int span_bytes, int strip_w, int cls) {
+    return make_layout_ws(span_bytes, strip_w, vis_record_stride(cls), cls - 1).total;
+}
 int ws_smem_max() { return kSmemMax; }
 
 int ws_launch(int cls, const VisFrame* frames, const VisStrip* strips, int n_strips, int span_bytes, int strip_w,
               const float* lut768, float* pixel_values, cudaStream_t st) {
-    const LayoutWS L = make_layout_ws(span_bytes, strip_w, vis_record_stride(cls));
+    const LayoutWS L = make_layout_ws(span_bytes, strip_w, vis_record_stride(cls), cls - 1);
     if (L.total > kSmemMax) {
         vis::set_error("vis_preprocess_fused(ws): %d bytes of shared memory needed", L.total);
         return VIS_E_UNSUPPORTED;
