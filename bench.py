@@ -66,36 +66,51 @@ def _cpu_worker(idx_range):
 _CPU_KIND = "reference"
 
 
-def cpu_reference_throughput(n_images: int, cores: int, repeats: int = 1):
-    """images/s of the reference's CPU implementation of the path on `cores` processes (fork, one thread each).
+class CpuArm:
+    """The reference's CPU implementation of the path on `cores` forked workers (one thread each).
 
     kind "reference": the installed transformers Qwen2VLImageProcessorPil (the processor the Inspector/Auditor
     inputs go through server-side; Pillow does the resampling) — kind "port": the plain-C oracle restatement.
+    The pool is created once (imports + processor construction happen in the warm-up), then `run(n)` times n frames.
     """
-    global _CPU_FRAMES, _CPU_KIND
-    import multiprocessing as mp
-    from vision_inspection_system_b200 import synth
-    try:
-        import transformers  # noqa: F401
-        from PIL import Image  # noqa: F401
-        _CPU_KIND = "reference"
-    except Exception:
-        _CPU_KIND = "port"
-    distinct = min(n_images, 32)
-    _CPU_FRAMES = [synth.noise_frame(1234 + i, H, W) for i in range(distinct)]
-    cores = max(1, min(cores, n_images))
-    bounds = [(n_images * k // cores, n_images * (k + 1) // cores) for k in range(cores)]
-    ctx = mp.get_context("fork")
-    best = None
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(0, 1)] * cores)                    # warm-up: imports, processor construction
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            done = sum(pool.map(_cpu_worker, bounds))
-            dt = time.perf_counter() - t0
-            assert done == n_images
-            best = dt if best is None else min(best, dt)
-    return n_images / best, _CPU_KIND, cores, best
+
+    def __init__(self, cores: int):
+        global _CPU_FRAMES, _CPU_KIND
+        import multiprocessing as mp
+        from vision_inspection_system_b200 import synth
+        try:
+            import transformers  # noqa: F401
+            from PIL import Image  # noqa: F401
+            _CPU_KIND = "reference"
+        except Exception:
+            _CPU_KIND = "port"
+        self.kind = _CPU_KIND
+        self.cores = max(1, cores)
+        _CPU_FRAMES = [synth.noise_frame(1234 + i, H, W) for i in range(32)]
+        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.pool.map(_cpu_worker, [(0, 1)] * self.cores)               # warm-up: imports, processor construction
+
+    def run(self, n_images: int) -> float:
+        """seconds of wall clock for n_images frames spread over the workers"""
+        k = min(self.cores, n_images)
+        bounds = [(n_images * i // k, n_images * (i + 1) // k) for i in range(k)]
+        t0 = time.perf_counter()
+        done = sum(self.pool.map(_cpu_worker, bounds))
+        dt = time.perf_counter() - t0
+        assert done == n_images
+        return dt
+
+    def calibrated(self, target_s: float):
+        """(images/s, n, seconds): a sample sized from a short probe so that it takes about target_s seconds"""
+        probe_n = 2 * self.cores
+        rate = probe_n / self.run(probe_n)
+        n = int(max(probe_n, min(rate * target_s, 20000)))
+        dt = self.run(n)
+        return n / dt, n, dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def cpu_model() -> str:
@@ -165,7 +180,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step (default 256 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-images", type=int, default=0, help="size of the bounded CPU sample (0 = 4 per core)")
+    ap.add_argument("--cpu-images", type=int, default=0, help="size of the bounded CPU sample (0 = calibrated to ~15 s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -182,24 +197,25 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n = args.cpu_images or max(4 * cores, 64)
-        vals = []
-        kind = "reference"
+        arm = CpuArm(cores)
+        steps = max(1, args.steps)
+        budget_s = 150.0                               # the whole run stays within a few minutes
+        probe_n = 2 * cores
+        rate = probe_n / arm.run(probe_n)
+        n = args.cpu_images or int(max(cores, min(rate * budget_s / (steps + max(args.warmup, 0)), 4096)))
         for _ in range(max(args.warmup, 0)):
-            pass                                      # the pool warms itself (imports + one frame per worker)
-        for _ in range(max(1, args.steps)):
-            v, kind, used, dt = cpu_reference_throughput(n, cores)
-            vals.append(v)
-            if sum(n / x for x in vals) > 240:        # keep the whole run within a few minutes
-                break
-        v = float(np.median(vals))
-        line = {"metric": METRIC, "value": v, "unit": "images/s", "n_gpus": n_gpus, "steps": len(vals),
-                "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "weak",
+            arm.run(n)
+        t = [arm.run(n) for _ in range(steps)]
+        arm.close()
+        total = float(sum(t))
+        v = n * steps / total
+        line = {"metric": METRIC, "value": v, "unit": "images/s", "n_gpus": n_gpus, "steps": steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8->int32 fixed point->f32", "data": "synthetic", "impl": "reference",
                 "config": dict(config, frames_per_step=n),
-                "cpu_baseline": {"value": v, "unit": "images/s", "cores": used, "kind": kind,
-                                 "sample": f"{n} seeded 1080p noise frames per step over {used} forked workers "
-                                           f"(one thread each) on {cpu_model()}"},
+                "cpu_baseline": {"value": v, "unit": "images/s", "cores": arm.cores, "kind": arm.kind,
+                                 "sample": f"{n} seeded 1080p noise frames per step x {steps} steps over {arm.cores} "
+                                           f"forked workers (one thread each), {total:.1f} s, on {cpu_model()}"},
                 "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -208,10 +224,16 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1) BEFORE CUDA is initialised (fork safety) ----------------
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        n = args.cpu_images or max(4 * cores, 64)
-        v, kind, used, dt = cpu_reference_throughput(n, cores)
-        cpu_baseline = {"value": v, "unit": "images/s", "cores": used, "kind": kind,
-                        "sample": f"{n} seeded 1080p noise frames over {used} forked workers (one thread each), "
+        arm = CpuArm(cores)
+        if args.cpu_images:
+            n = args.cpu_images
+            dt = arm.run(n)
+            v = n / dt
+        else:
+            v, n, dt = arm.calibrated(target_s=15.0)   # ~15 s of wall clock on every core: a bounded sample
+        arm.close()
+        cpu_baseline = {"value": v, "unit": "images/s", "cores": arm.cores, "kind": arm.kind,
+                        "sample": f"{n} seeded 1080p noise frames over {arm.cores} forked workers (one thread each), "
                                   f"{dt:.1f} s, on {cpu_model()} ({cores} logical cores)"}
 
     import torch
@@ -310,6 +332,13 @@ def main():
         peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
     kernel_s = (ms / 1e3) / args.steps                       # one fused launch per step on this rank
     achieved = args.batch * BYTES_PER_IMAGE / kernel_s / 1e9
+    traffic, traffic_src = None, None                        # measured DRAM bytes per launch, from the committed ncu capture
+    try:
+        rec = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(f"k_fused_ws@{args.batch}x1080p")
+        if rec:
+            traffic, traffic_src = rec["dram_bytes_read"] + rec["dram_bytes_write"], rec["source"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -322,8 +351,10 @@ def main():
                               "d2h_bytes_per_step": args.batch * ROWS * 1176 * 4},
         "gpu_launches": launches_per_step * args.steps + e2e_launches * e2e_steps,
         "roofline": {"bound": "hbm", "kernel": "k_fused (vis_preprocess_fused)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "bytes_per_image": BYTES_PER_IMAGE, "launches_timed": launches_per_step * args.steps},
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+                     "traffic_source": traffic_src, "algorithmic_bytes_per_launch": args.batch * BYTES_PER_IMAGE,
+                     "peak_source": peak_src, "bytes_per_image": BYTES_PER_IMAGE,
+                     "launches_timed": launches_per_step * args.steps},
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,
     }
