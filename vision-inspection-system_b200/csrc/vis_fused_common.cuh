@@ -34,13 +34,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// spin with a watchdog: a lost bulk copy traps (reported as a CUDA error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+// slow path of a wait, kept out of line so the hot loops stay small (the kernels are instruction-cache sensitive):
+// back off between polls, and trap instead of hanging the GPU if the phase never completes (lost bulk copy)
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) __trap();
+        __nanosleep(32);
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -56,6 +59,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void stg128(float* p, float a, float b, float c, float d) {
@@ -83,5 +96,18 @@ __device__ __forceinline__ void load_rec(Rec<KT>& r, const int* p) {      // p: 
     r.last = tmp[STRIDE - 1];
 }
 
+// same, from a shared-memory address (explicit ld.shared: never a generic load)
+template <int KT, int STRIDE>
+__device__ __forceinline__ void load_rec_s(Rec<KT>& r, uint32_t addr) {
+    int tmp[STRIDE];
+#pragma unroll
+    for (int q = 0; q < STRIDE / 4; ++q) {
+        const uint4 v = lds128(addr + 16 * q);
+        tmp[4 * q] = (int)v.x; tmp[4 * q + 1] = (int)v.y; tmp[4 * q + 2] = (int)v.z; tmp[4 * q + 3] = (int)v.w;
+    }
+#pragma unroll
+    for (int t = 0; t < KT; ++t) r.k[t] = tmp[t];
+    r.last = tmp[STRIDE - 1];
+}
 
 }  // namespace visf
