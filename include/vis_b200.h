@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 1
+#define VIS_B200_ABI_VERSION 2
 
 /* status codes */
 #define VIS_OK            0
@@ -124,6 +124,55 @@ int vis_plan_strips(int frame_index, int dst_h, int dst_w, const int32_t* hbound
 int vis_preprocess_fused(const VisFrame* frames, int n_frames, const VisStrip* strips, int n_strips,
                          int max_kt, int max_span_bytes, int max_strip_w,
                          const float* lut768, float* pixel_values, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Statically scheduled fused kernel: same computation as vis_preprocess_fused for ONE geometry per
+ * launch whose scale is >= 1 on both axes (at most one output sample ends at any input index).
+ * The host precomputes, from the bounds tables, which input column of every 8-pixel step / which input
+ * row of every 8-row group completes an output sample; the schedule travels as a kernel parameter
+ * (constant bank), so every branch of the resampling loops is warp-uniform and no window bookkeeping
+ * is left on the device.  Geometries it declines (VIS_E_UNSUPPORTED) go to vis_preprocess_fused.
+ * ------------------------------------------------------------------------------------------ */
+#define VIS_SCHED_MAX_STRIPS 16      /* column strips per frame (<= 336 output columns each)       */
+#define VIS_SCHED_MAX_SEGS   8       /* row segments per frame                                     */
+#define VIS_SCHED_SUBS       12      /* column sub-ranges per strip (one per horizontal-pass warp) */
+#define VIS_SCHED_MASK_BYTES 6144
+
+typedef struct VisSchedStrip { int32_t x0, x1, px0, row_bytes; } VisSchedStrip;
+typedef struct VisSchedSub   { uint16_t xa, xb, p0, nsteps, mask_off, pad; } VisSchedSub;
+typedef struct VisSchedSeg   { int32_t y0, y1, r_first, r_end, mask_off, pad; } VisSchedSeg;
+
+typedef struct VisSched {            /* opaque to callers: filled by vis_sched_build, passed back by pointer */
+    int32_t src_h, src_w, dst_h, dst_w;
+    int64_t src_pitch;
+    int32_t kt;                      /* tap class (6 or 8)                                         */
+    int32_t n_strips, n_segs;
+    int32_t stage_pitch, max_strip_w, reserved;
+    VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
+    VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_SUBS];
+    VisSchedSeg   seg[VIS_SCHED_MAX_SEGS];
+    uint8_t       mask[VIS_SCHED_MASK_BYTES];
+} VisSched;
+
+typedef struct VisFrameRef {         /* per frame of a scheduled launch (device array)             */
+    const uint8_t* src;              /* RGB uint8 HWC, 16-byte aligned, row pitch = sched.src_pitch */
+    int64_t        row0;             /* first row of this frame in pixel_values                    */
+} VisFrameRef;
+
+/* sizeof(VisSched), for bindings that treat it as an opaque byte buffer                  [host] */
+int vis_sched_sizeof(void);
+/* hbounds / vbounds: HOST bounds tables of vis_build_coeffs (dst_w x 2, dst_h x 2); vsplit = row segments.
+ * VIS_OK, or VIS_E_UNSUPPORTED when the geometry needs the general kernel.              [host] */
+int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitch,
+                    const int32_t* hbounds, const int32_t* vbounds, int vsplit, VisSched* out);
+/* records for the scheduled kernel: like vis_pack_records, but samples whose window the far border clamps are
+ * moved to the virtual end index the schedule gives them (leading zero coefficients).  kt = sched kt.  [host] */
+int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt,
+                           int32_t* rec, int64_t rec_capacity);
+/* frames: DEVICE array; hrec / vrec: DEVICE records from vis_sched_pack_records.        [device] */
+int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,
+                               const int32_t* hrec, const int32_t* vrec,
+                               const float* lut768, float* pixel_values, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Defect overlay rasteriser.

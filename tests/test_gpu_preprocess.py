@@ -48,10 +48,13 @@ def test_goldens(engine, goldens, arrays, force_generic):
 
 def test_fused_path_is_taken_for_the_benchmark_geometry(engine):
     f = torch.from_numpy(synth.noise_frame(1234, 1080, 1920)).cuda()
+    from vision_inspection_system_b200.engine import _SchedLaunch
     plan = engine.plan_batch([f])
-    assert len(plan.fused) == 1 and not plan.generic
+    assert len(plan.fused) == 1 and not plan.generic and isinstance(plan.fused[0], _SchedLaunch)
     engine.preprocess([f])
     assert engine.last_launches == 1
+    plan = engine.plan_batch([f], path="general")
+    assert len(plan.fused) == 1 and not isinstance(plan.fused[0], _SchedLaunch)
 
 
 @pytest.mark.parametrize("shape,max_pixels", [
@@ -59,14 +62,16 @@ def test_fused_path_is_taken_for_the_benchmark_geometry(engine):
     ((720, 1280), G.DEFAULT_MAX_PIXELS), ((480, 640), G.DEFAULT_MAX_PIXELS), ((1536, 2048), G.DEFAULT_MAX_PIXELS),
     ((1152, 2048), G.DEFAULT_MAX_PIXELS), ((576, 1024), G.DEFAULT_MAX_PIXELS), ((100, 502), G.DEFAULT_MAX_PIXELS),
     ((64, 96), G.DEFAULT_MAX_PIXELS), ((28, 5600), G.DEFAULT_MAX_PIXELS), ((3000, 20), G.DEFAULT_MAX_PIXELS),
+    ((2048, 1536), G.DEFAULT_MAX_PIXELS), ((1080, 1920), 400000), ((1200, 1600), G.DEFAULT_MAX_PIXELS), ((600, 5000), G.DEFAULT_MAX_PIXELS),
     ((1, 1), G.DEFAULT_MAX_PIXELS), ((2160, 3840), G.HUB_MAX_PIXELS)])
 def test_against_oracle(engine, shape, max_pixels):
     frame = synth.noise_frame(hash(shape) % 1000, *shape)
     want, wgrid = Q.preprocess([frame], max_pixels=max_pixels)
-    for vsplit in (None, 1, 3):
-        pv, grid = run(engine, [frame], max_pixels=max_pixels, vsplit=vsplit)
-        assert np.array_equal(grid, wgrid)
-        check_equal(pv, want, (shape, max_pixels, vsplit))
+    for path in ("auto", "general"):             # scheduled kernel where it applies / general fused kernel everywhere
+        for vsplit in (None, 1, 3):
+            pv, grid = run(engine, [frame], max_pixels=max_pixels, vsplit=vsplit, path=path)
+            assert np.array_equal(grid, wgrid)
+            check_equal(pv, want, (shape, max_pixels, vsplit, path))
 
 
 def test_padded_pitch_and_unaligned_views(engine):

@@ -1,0 +1,119 @@
+"""Host logic of the statically scheduled kernel: vis_sched_build's masks must say exactly where Pillow's tap windows
+end (utils: tf:image_transforms.py:367 -> Pillow precompute_coeffs bounds), checked by replaying the device loops on the CPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from vision_inspection_system_b200 import _native as N
+from vision_inspection_system_b200 import geometry as G
+from vision_inspection_system_b200 import tables as T
+
+SUB = np.dtype([("xa", np.uint16), ("xb", np.uint16), ("p0", np.uint16), ("nsteps", np.uint16), ("mask_off", np.uint16),
+                ("pad", np.uint16)])
+STRIP = np.dtype([("x0", np.int32), ("x1", np.int32), ("px0", np.int32), ("row_bytes", np.int32)])
+SEG = np.dtype([("y0", np.int32), ("y1", np.int32), ("r_first", np.int32), ("r_end", np.int32), ("mask_off", np.int32),
+                ("pad", np.int32)])
+SCHED = np.dtype([("head", N.SCHED_HEAD_DTYPE), ("strip", STRIP, (16,)), ("sub", SUB, (16, 12)), ("seg", SEG, (8,)),
+                  ("mask", np.uint8, (6144,))], align=True)
+
+
+def sched_ends_and_records(table, kt):
+    """vis_sched_pack_records, checked: window ends strictly increase, stay within kt slots of the first tap, differ
+    from Pillow's only where the far border clamps, and the shifted coefficients are Pillow's."""
+    L = N.lib()
+    stride = L.vis_record_stride(kt)
+    rec = np.zeros((table.out_size + 1, stride), np.int32)
+    assert L.vis_sched_pack_records(table.out_size, N.i32ptr(table.k), N.i32ptr(table.bounds), table.ksize, kt,
+                                    N.i32ptr(rec), rec.size) == N.VIS_OK
+    first, taps = table.bounds[:, 0], table.bounds[:, 1]
+    ends = rec[:-1, stride - 1]
+    assert (np.diff(ends) > 0).all() and (ends - first + 1 <= kt).all() and (rec[:-1, stride - 2] == first).all()
+    true_last = first + taps - 1
+    moved = ends != true_last
+    assert (true_last[moved] == table.in_size - 1).all() and (ends >= true_last).all()
+    for o in range(table.out_size):
+        sh = ends[o] - true_last[o]
+        want = np.zeros(kt, np.int32)
+        want[sh:sh + taps[o]] = table.k[o, :taps[o]][::-1]
+        assert (rec[o, :kt] == want).all()
+    return ends, rec
+
+
+def build(src_h, src_w, dst_h, dst_w, pitch, vsplit):
+    L = N.lib()
+    assert SCHED.itemsize == L.vis_sched_sizeof()
+    ht = T.coeff_table(src_w, dst_w, N.FILTER_BICUBIC)
+    vt = T.coeff_table(src_h, dst_h, N.FILTER_BICUBIC)
+    buf = np.zeros(1, SCHED)
+    rc = L.vis_sched_build(src_h, src_w, dst_h, dst_w, pitch, N.i32ptr(ht.bounds), N.i32ptr(vt.bounds), vsplit,
+                           buf.ctypes.data_as(C.c_void_p))
+    return rc, buf[0], ht, vt
+
+
+@pytest.mark.parametrize("shape,vsplit,max_pixels", [
+    ((1080, 1920), 1, G.DEFAULT_MAX_PIXELS), ((1080, 1920), 3, G.DEFAULT_MAX_PIXELS), ((2160, 3840), 2, G.HUB_MAX_PIXELS),
+    ((1536, 2048), 8, G.DEFAULT_MAX_PIXELS), ((1152, 2048), 1, G.DEFAULT_MAX_PIXELS), ((2048, 1536), 4, G.DEFAULT_MAX_PIXELS),
+    ((600, 5000), 2, G.DEFAULT_MAX_PIXELS)])
+def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels):
+    h, w = shape
+    dh, dw = G.smart_resize(h, w, G.FACTOR, G.DEFAULT_MIN_PIXELS, max_pixels)
+    pitch = (w * 3 + 15) // 16 * 16
+    rc, s, ht, vt = build(h, w, dh, dw, pitch, vsplit)
+    assert rc == N.VIS_OK, N.lib().vis_last_error()
+    hd = s["head"]
+    assert (hd["dst_h"], hd["dst_w"], hd["kt"]) == (dh, dw, T.kt_class(max(ht.max_taps, vt.max_taps)))
+    hlast, hrec = sched_ends_and_records(ht, int(hd["kt"]))
+    vlast, vrec = sched_ends_and_records(vt, int(hd["kt"]))
+    # horizontal: every output column of every strip is emitted exactly once, at the pixel where its window ends,
+    # after all of its taps have been read (p0 <= first tap), and the staged row segment covers the window
+    covered = np.zeros(dw, np.int32)
+    for st in range(hd["n_strips"]):
+        S = s["strip"][st]
+        assert S["x0"] % 28 == 0 and S["x1"] % 28 == 0 and S["px0"] % 16 == 0 and S["row_bytes"] % 16 == 0
+        assert S["row_bytes"] <= hd["stage_pitch"] and S["px0"] * 3 + S["row_bytes"] <= pitch
+        for u in range(12):
+            U = s["sub"][st][u]
+            xo = int(U["xa"])
+            assert U["p0"] % 8 == 0 and U["p0"] >= S["px0"] and U["p0"] <= ht.bounds[xo, 0]
+            for i in range(U["nsteps"]):
+                m = int(s["mask"][U["mask_off"] + i])
+                for jj in range(8):
+                    if m >> jj & 1:
+                        assert hlast[xo] == U["p0"] + 8 * i + jj
+                        assert (min(hlast[xo], w - 1) + 1) * 3 <= S["px0"] * 3 + S["row_bytes"]
+                        covered[xo] += 1
+                        xo += 1
+            assert xo == U["xb"]
+    assert (covered == 1).all()
+    # vertical: every output row once per segment cover, at the input row where its window ends
+    rows = np.zeros(dh, np.int32)
+    for sg in range(hd["n_segs"]):
+        Gs = s["seg"][sg]
+        yo = int(Gs["y0"])
+        assert Gs["y0"] % 14 == 0 and Gs["y1"] % 14 == 0 and Gs["r_first"] % 16 == 0 and Gs["mask_off"] % 4 == 0
+        assert Gs["r_first"] <= vt.bounds[yo, 0]
+        n_chunks = -(-(Gs["r_end"] - Gs["r_first"]) // 32)
+        for c in range(n_chunks):
+            emitted_here = 0
+            for g in range(4):
+                m = int(s["mask"][Gs["mask_off"] + c * 4 + g])
+                for u in range(8):
+                    if m >> u & 1:
+                        assert vlast[yo] == Gs["r_first"] + c * 32 + g * 8 + u
+                        rows[yo] += 1
+                        yo += 1
+                        emitted_here += 1
+            assert emitted_here <= 32
+        assert yo == Gs["y1"]
+    assert (rows == 1).all()
+
+
+@pytest.mark.parametrize("shape,max_pixels,why", [((1080, 1920), G.HUB_MAX_PIXELS, b"upscale"), ((2160, 3840), G.DEFAULT_MAX_PIXELS, b"taps"),
+                                                  ((100, 502), G.DEFAULT_MAX_PIXELS, b"pitch")])
+def test_schedule_declines_what_it_cannot_express(shape, max_pixels, why):
+    h, w = shape
+    dh, dw = G.smart_resize(h, w, G.FACTOR, G.DEFAULT_MIN_PIXELS, max_pixels)
+    pitch = w * 3 if why == b"pitch" else (w * 3 + 15) // 16 * 16
+    rc, _, _, _ = build(h, w, dh, dw, pitch, 1)
+    assert rc == N.VIS_E_UNSUPPORTED and why in N.lib().vis_last_error()

@@ -1,0 +1,545 @@
+// vis_fused_sched.cu — statically scheduled, warp-specialised hot kernel (frame -> Qwen2-VL pixel_values).
+//
+// Same arithmetic as vis_fused.cu / vis_fused_ws.cu (Pillow 8bpc horizontal pass -> uint8 -> vertical pass -> uint8 ->
+// exact LUT -> patch layout; tf:models/qwen2_vl/image_processing_pil_qwen2_vl.py:164-214), same pipeline of roles over
+// shared-memory rings with full/empty mbarriers:
+//
+//   loader (1 warp)   cp.async.bulk: 32 input row segments per chunk, the strip's horizontal records, and the vertical
+//                     records each chunk will consume                                   -> stage[2], hrec[2], vrec[2]
+//   H      (12 warps) lane = input row, warp = column sub-range; push order: 8 input pixels per step are unpacked into a
+//                     register window, an output pixel is emitted where the schedule says one ends   -> hring[2] (u8 planar)
+//   V      (8 warps)  thread = 4 output columns of one channel; every H-ring row is unpacked once into a register ring,
+//                     an output row is emitted where the schedule says one ends                       -> otile[2] (14-row band)
+//   store  (3 warps)  band -> LUT -> 16-byte stores, both temporal copies                             -> pixel_values
+//
+// What is different: ONE geometry per launch, and the emission pattern ("an output sample's tap window ends at this
+// input index") is precomputed on the host into bit masks that travel in the kernel parameter block (constant bank).
+// Strip, segment, sub-range and mask data are therefore warp-uniform values; the compiler keeps them in uniform
+// registers, every branch in the resampling loops is a uniform branch (no BSSY/BSYNC reconvergence pairs), and the
+// per-sample window bookkeeping (compare against `last`, update, reload) of the general kernels disappears.  The
+// general kernels were instruction-issue bound with ~45 % of their instructions being such bookkeeping
+// (profiles/r01_fused_ws4.txt).
+#include "vis_fused_common.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace visf;
+
+namespace {
+
+constexpr int kHWarps = VIS_SCHED_SUBS, kVWarps = 8, kSWarps = 3;
+// warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
+constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
+constexpr int kThreadsS = (kHWarps + kVWarps + kSWarps + 1) * 32;       // 768
+constexpr int kChunk = 32, kStepPx = 8, kRing = 8, kMaxStripW = 336;
+constexpr int kPitch = kMaxStripW + 4;            // 340 = 4 * 85: conflict-free lane = row byte stores
+constexpr int kOPitch = kMaxStripW;
+constexpr int kOPlane = VIS_PATCH * kOPitch;
+constexpr int kHPlane = kChunk * kPitch;
+constexpr int kVRecs = kChunk + 1;                // vertical records a chunk can touch (scale >= 1): 32 emits + 1 look-ahead
+constexpr int kSmemMax = 227 * 1024;
+
+enum Bar { SF = 0, SE = 2, HF = 4, HE = 6, VF = 8, OF = 10, OE = 12, kBars = 14 };   // full/empty pairs, two slots each
+
+struct LayoutS {
+    int stage_pitch, stage_slot, hrec_slot, vrec_slot;
+    int off_stage, off_hring, off_otile, off_hrec, off_vrec, off_lut, off_bar, total;
+};
+
+inline LayoutS make_layout_s(int stage_pitch, int strip_w, int stride) {
+    LayoutS L;
+    L.stage_pitch = stage_pitch;
+    L.stage_slot = kChunk * stage_pitch;
+    L.hrec_slot = align_up((strip_w + 1) * stride * 4, 16);
+    L.vrec_slot = align_up(kVRecs * stride * 4, 16);
+    int off = 0;
+    L.off_stage = off; off += 2 * L.stage_slot;
+    L.off_hring = off; off += 2 * 3 * kHPlane;
+    L.off_otile = off; off += 2 * 3 * kOPlane;
+    off = align_up(off, 16);
+    L.off_hrec = off;  off += 2 * L.hrec_slot;
+    L.off_vrec = off;  off += 2 * L.vrec_slot;
+    L.off_lut = off;   off += 768 * 4;
+    L.off_bar = off;   off += kBars * 8;
+    L.total = off;
+    return L;
+}
+
+// coefficient part of a record (the window bounds are not needed on the device: the schedule replaces them)
+template <int KT, int STRIDE>
+__device__ __forceinline__ void load_coeffs(int (&k)[KT], uint32_t addr) {
+    static_assert(KT == 6 || KT == 8, "tap classes 6 and 8");
+    const uint4 a = lds128(addr);
+    k[0] = (int)a.x; k[1] = (int)a.y; k[2] = (int)a.z; k[3] = (int)a.w;
+    if (KT == 6) {
+        const uint2 b = lds64(addr + 16);
+        k[4] = (int)b.x; k[5] = (int)b.y;
+    } else {
+        const uint4 b = lds128(addr + 16);
+        k[4] = (int)b.x; k[5] = (int)b.y; k[KT - 2] = (int)b.z; k[KT - 1] = (int)b.w;
+    }
+}
+
+// band `nb` of the output tile ring is complete: publish it to the store warps, then make sure the tile the next
+// band goes to has been drained (out of line: once per 14 output rows, keeps the unrolled emit bodies small)
+__device__ __noinline__ void band_done(uint32_t bar0, int nb, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar0 + (uint32_t)(OF + (nb & 1)) * 8);
+    const int nx = nb + 1;
+    if (nx >= 2) mbar_wait(bar0 + (uint32_t)(OE + (nx & 1)) * 8, ((nx >> 1) - 1) & 1);
+}
+
+template <int KT, int STRIDE>
+__global__ void __launch_bounds__(kThreadsS, 1)
+k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict__ frames, int n_items,
+              const __grid_constant__ LayoutS L, const int* __restrict__ hrec_g, const int* __restrict__ vrec_g,
+              const float* __restrict__ lut768, float* __restrict__ pixel_values) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);               // warp-uniform for the compiler
+    float* lut = reinterpret_cast<float*>(smem + L.off_lut);              // transposed: lut[c * 256 + v]
+    const uint32_t bar0 = smem_u32(smem + L.off_bar);
+    auto bar = [&](int which, int slot) { return bar0 + (uint32_t)(which + slot) * 8; };
+    const int per_frame = sc.n_strips * sc.n_segs;
+
+    for (int i = tid; i < 768; i += kThreadsS) lut[(i % 3) * 256 + i / 3] = __ldg(lut768 + i);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(SF, s), 1);
+            mbar_init(bar(SE, s), kHWarps);
+            mbar_init(bar(HF, s), kHWarps);
+            mbar_init(bar(HE, s), kVWarps);
+            mbar_init(bar(VF, s), 1);
+            mbar_init(bar(OF, s), kVWarps);
+            mbar_init(bar(OE, s), kSWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();                                   // the only CTA-wide barrier
+
+    if (warp == kLBase) {
+        // ============================== loader ==============================
+        int k = 0, sl = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++sl) {
+            const int f = w / per_frame, r = w - f * per_frame;
+            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+            const VisSchedStrip S = sc.strip[st];
+            const VisSchedSeg G = sc.seg[sg];
+            const unsigned char* src = frames[f].src + (size_t)S.px0 * 3;
+            const uint32_t rec_bytes = (uint32_t)(S.x1 - S.x0 + 1) * STRIDE * 4;
+            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            int yo = G.y0;
+            for (int c = 0; c < n_chunks; ++c, ++k) {
+                const int slot = k & 1;
+                const uint32_t prev = ((k >> 1) - 1) & 1;
+                if (k >= 2) mbar_wait(bar(SE, slot), prev);                 // H is done with the stage slot
+                const int r0 = G.r_first + c * kChunk;
+                const int rows = max(0, min(kChunk, sc.src_h - r0));        // r_end may include virtual rows past the image
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(bar(SF, slot), (uint32_t)rows * (uint32_t)S.row_bytes + (c == 0 ? rec_bytes : 0u));
+                }
+                __syncwarp();
+                unsigned char* stage = smem + L.off_stage + slot * L.stage_slot;
+                if (lane < rows)
+                    bulk_g2s(smem_u32(stage + lane * L.stage_pitch), src + (size_t)(r0 + lane) * sc.src_pitch,
+                             (uint32_t)S.row_bytes, bar(SF, slot));
+                if (c == 0 && lane == 0)
+                    bulk_g2s(smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot), hrec_g + (size_t)S.x0 * STRIDE,
+                             rec_bytes, bar(SF, slot));
+                // vertical records this chunk consumes: [yo, yo + 33) (the table ends with a sentinel at dst_h)
+                if (k >= 2) mbar_wait(bar(HE, slot), prev);                 // V is done with the record slot
+                if (lane == 0) {
+                    const uint32_t vbytes = (uint32_t)min(kVRecs, sc.dst_h + 1 - yo) * STRIDE * 4;
+                    fence_proxy_async();
+                    mbar_expect_tx(bar(VF, slot), vbytes);
+                    bulk_g2s(smem_u32(smem + L.off_vrec + slot * L.vrec_slot), vrec_g + (size_t)yo * STRIDE, vbytes,
+                             bar(VF, slot));
+                }
+                const uint32_t m4 = *reinterpret_cast<const uint32_t*>(sc.mask + G.mask_off + c * 4);
+                yo += __popc(m4);
+            }
+        }
+    } else if (warp < kHBase + kHWarps) {
+        // ============================== horizontal pass ==============================
+        const int sub = warp - kHBase;
+        int k = 0, sl = 0;
+        int rg[3][kRing];                                  // the last 8 input pixels per channel (static slots)
+#pragma unroll
+        for (int q = 0; q < kRing; ++q) rg[0][q] = rg[1][q] = rg[2][q] = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++sl) {
+            const int f = w / per_frame, r = w - f * per_frame;
+            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+            const VisSchedStrip S = sc.strip[st];
+            const VisSchedSeg G = sc.seg[sg];
+            const VisSchedSub U = sc.sub[st][sub];
+            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            const uint32_t hrec0 = smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot) + (uint32_t)(U.xa - S.x0) * STRIDE * 4;
+            const uint8_t* const um = sc.mask + U.mask_off;
+            for (int c = 0; c < n_chunks; ++c, ++k) {
+                const int slot = k & 1, j = k >> 1;
+                mbar_wait(bar(SF, slot), j & 1);
+                if (k >= 2) mbar_wait(bar(HE, slot), (j - 1) & 1);
+                uint32_t sa = smem_u32(smem + L.off_stage + slot * L.stage_slot + lane * L.stage_pitch) + (uint32_t)(U.p0 - S.px0) * 3;
+                unsigned char* hdst = smem + L.off_hring + slot * 3 * kHPlane + lane * kPitch + (U.xa - S.x0);
+                uint32_t hp = hrec0;
+                int kf[KT];
+                load_coeffs<KT, STRIDE>(kf, hp);
+#pragma unroll 1
+                for (int i = 0; i < U.nsteps; ++i) {
+                    const uint32_t m = um[i];
+                    uint32_t wv[6];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const uint2 d = lds64(sa + 8 * q);
+                        wv[2 * q] = d.x; wv[2 * q + 1] = d.y;
+                    }
+                    sa += kStepPx * 3;
+#pragma unroll
+                    for (int jj = 0; jj < kStepPx; ++jj) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const int b = 3 * jj + ch;
+                            rg[ch][jj] = (int)__byte_perm(wv[b >> 2], 0, 0x4440 + (b & 3));
+                        }
+                        if (m & (1u << jj)) {
+                            int a0 = 1 << (VIS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+#pragma unroll
+                            for (int tt = 0; tt < KT; ++tt) {
+                                const int q = (jj - tt) & (kRing - 1);
+                                a0 += rg[0][q] * kf[tt];
+                                a1 += rg[1][q] * kf[tt];
+                                a2 += rg[2][q] * kf[tt];
+                            }
+                            hdst[0] = (unsigned char)clip8i(a0);
+                            hdst[kHPlane] = (unsigned char)clip8i(a1);
+                            hdst[2 * kHPlane] = (unsigned char)clip8i(a2);
+                            ++hdst;
+                            hp += STRIDE * 4;
+                            load_coeffs<KT, STRIDE>(kf, hp);          // the slot holds sw + 1 records: always readable
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(SE, slot));          // stage slot may be refilled
+                    mbar_arrive(bar(HF, slot));          // H-ring slot is complete
+                }
+            }
+        }
+    } else if (warp >= kVBase) {
+        // ============================== vertical pass ==============================
+        const int v = tid - kVBase * 32;
+        int k = 0, nb = 0;
+        int ring[kRing][4];                                // the last 8 H-ring rows of this thread's 4 columns
+#pragma unroll
+        for (int q = 0; q < kRing; ++q) ring[q][0] = ring[q][1] = ring[q][2] = ring[q][3] = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int f = w / per_frame, r = w - f * per_frame;
+            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+            const VisSchedStrip S = sc.strip[st];
+            const VisSchedSeg G = sc.seg[sg];
+            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            const int wpr = (S.x1 - S.x0) / 4;
+            const bool v_active = v < 3 * wpr;
+            const int vc = v_active ? v / wpr : 0;
+            const int vwx = v_active ? v - vc * wpr : 0;
+            const uint32_t thr_off = (uint32_t)(vc * kOPlane + vwx * 4);
+            int py = 0;
+            uint32_t otile_thr = smem_u32(smem + L.off_otile + (nb & 1) * 3 * kOPlane) + thr_off;
+            const uint8_t* const gm = sc.mask + G.mask_off;
+            for (int c = 0; c < n_chunks; ++c, ++k) {
+                const int slot = k & 1, j = k >> 1;
+                mbar_wait(bar(VF, slot), j & 1);
+                mbar_wait(bar(HF, slot), j & 1);
+                uint32_t vaddr = smem_u32(smem + L.off_vrec + slot * L.vrec_slot);
+                int kf[KT];
+                load_coeffs<KT, STRIDE>(kf, vaddr);
+                const uint32_t hsrc = smem_u32(smem + L.off_hring + slot * 3 * kHPlane + vc * kHPlane + vwx * 4);
+                const int groups = min(kChunk / kRing, (G.r_end - (G.r_first + c * kChunk) + kRing - 1) / kRing);
+#pragma unroll 1
+                for (int g = 0; g < groups; ++g) {
+                    const uint32_t m = gm[c * (kChunk / kRing) + g];
+                    uint32_t words[kRing];
+#pragma unroll
+                    for (int u = 0; u < kRing; ++u) words[u] = lds32(hsrc + (uint32_t)((g * kRing + u) * kPitch));
+#pragma unroll
+                    for (int u = 0; u < kRing; ++u) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) ring[u][e] = (int)__byte_perm(words[u], 0, 0x4440 + e);
+                        if (m & (1u << u)) {
+                            int acc[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) acc[e] = 1 << (VIS_PRECISION_BITS - 1);
+#pragma unroll
+                            for (int tt = 0; tt < KT; ++tt) {
+                                const int q = (u - tt) & (kRing - 1);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) acc[e] += ring[q][e] * kf[tt];
+                            }
+                            const uint32_t lo = __byte_perm(clip8i(acc[0]), clip8i(acc[1]), 0x0040);
+                            const uint32_t hi = __byte_perm(clip8i(acc[2]), clip8i(acc[3]), 0x0040);
+                            if (v_active) sts32(otile_thr, __byte_perm(lo, hi, 0x5410));
+                            otile_thr += kOPitch;
+                            if (++py == VIS_PATCH) {                  // band complete: hand it to the store warps
+                                band_done(bar0, nb, lane);
+                                ++nb;
+                                py = 0;
+                                otile_thr = smem_u32(smem + L.off_otile + (nb & 1) * 3 * kOPlane) + thr_off;
+                            }
+                            vaddr += STRIDE * 4;
+                            load_coeffs<KT, STRIDE>(kf, vaddr);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(HE, slot));       // H-ring slot and record slot consumed
+            }
+        }
+    } else {
+        // ============================== band store ==============================
+        const int sw_i = warp - kSBase;
+        // lane-constant description of up to five 16-byte chunks (c, q) of a patch row: item = lane + 32 * i < 147
+        int sa[5], sb[5], go[5], lo[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int item = min(lane + 32 * i, 146);
+            const int c = item / 49, q = item - c * 49;
+            const int f0 = 4 * q, f2 = f0 + 2;
+            const int pya = f0 / VIS_PATCH, pyb = f2 / VIS_PATCH;
+            sa[i] = c * kOPlane + pya * kOPitch + (f0 - pya * VIS_PATCH);
+            sb[i] = c * kOPlane + pyb * kOPitch + (f2 - pyb * VIS_PATCH);
+            go[i] = c * 392 + f0;
+            lo[i] = c * 256;
+        }
+        int nb = 0;
+        const int half_gw = sc.dst_w / (2 * VIS_PATCH);
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int f = w / per_frame, r = w - f * per_frame;
+            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+            const VisSchedStrip S = sc.strip[st];
+            const VisSchedSeg G = sc.seg[sg];
+            const int n_patches = (S.x1 - S.x0) / VIS_PATCH, gx0 = S.x0 / VIS_PATCH;
+            float* const frame_out = pixel_values + (size_t)frames[f].row0 * VIS_ROW_FLOATS;
+            for (int gy = G.y0 / VIS_PATCH; gy < G.y1 / VIS_PATCH; ++gy, ++nb) {
+                const int os = nb & 1;
+                mbar_wait(bar(OF, os), (nb >> 1) & 1);
+                const unsigned char* otile = smem + L.off_otile + os * 3 * kOPlane;
+                float* band = frame_out + (size_t)((gy >> 1) * half_gw * 4 + (gy & 1) * 2) * VIS_ROW_FLOATS;
+                for (int g = sw_i; g < n_patches; g += kSWarps) {
+                    const int gx = gx0 + g;
+                    float* prow = band + (size_t)((gx >> 1) * 4 + (gx & 1)) * VIS_ROW_FLOATS;
+                    const unsigned char* pt = otile + g * VIS_PATCH;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        if (lane + 32 * i < 147) {
+                            const unsigned a = *reinterpret_cast<const unsigned short*>(pt + sa[i]);
+                            const unsigned b = *reinterpret_cast<const unsigned short*>(pt + sb[i]);
+                            const float* l = lut + lo[i];
+                            const float v0 = l[a & 0xff], v1 = l[a >> 8], v2 = l[b & 0xff], v3 = l[b >> 8];
+                            stg128(prow + go[i], v0, v1, v2, v3);
+                            stg128(prow + go[i] + 196, v0, v1, v2, v3);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(OE, os));
+            }
+        }
+    }
+}
+
+template <int KT, int STRIDE>
+int launch_sched(const VisSched& sc, const VisFrameRef* frames, int n_frames, const LayoutS& L, const int* hrec,
+                 const int* vrec, const float* lut768, float* pixel_values, cudaStream_t st) {
+    auto kern = k_fused_sched<KT, STRIDE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return vis::cuda_fail(e, "vis_preprocess_fused_sched: cudaFuncSetAttribute");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_items = n_frames * sc.n_strips * sc.n_segs;
+    const int grid = n_items < sms ? n_items : sms;
+    kern<<<grid, kThreadsS, L.total, st>>>(sc, frames, n_items, L, hrec, vrec, lut768, pixel_values);
+    return vis::check_launch("vis_preprocess_fused_sched");
+}
+
+// Window ends as the schedule uses them.  With scale >= 1 the true ends (first + taps - 1) strictly increase, except
+// at the far border where Pillow clamps the window to the image and the last few samples all end at the last input
+// index.  Those are moved to virtual indices past the border (one apart); their records are packed with as many
+// leading zero coefficients, so the virtual samples (whatever the staging buffer holds there) get weight 0.
+// Returns false when some sample would need more than kt slots (upscaling): not expressible as a one-bit schedule.
+inline bool schedule_ends(const int32_t* b, int n, int kt, std::vector<int>& ends) {
+    ends.resize(n);
+    for (int i = 0; i < n; ++i) {
+        int e = b[2 * i] + b[2 * i + 1] - 1;
+        if (i > 0) {
+            if (b[2 * i] < b[2 * i - 2]) return false;
+            if (e <= ends[i - 1]) e = ends[i - 1] + 1;
+        }
+        if (e - b[2 * i] + 1 > kt) return false;
+        ends[i] = e;
+    }
+    return true;
+}
+
+inline int stage_pitch_for(int span_bytes) {
+    int p = align_up(span_bytes, 16);
+    if ((p / 16) % 2 == 0) p += 16;               // odd multiple of 16: conflict-free lane = row wide loads
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vis_sched_sizeof(void) { return (int)sizeof(VisSched); }
+
+int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitch,
+                    const int32_t* hb, const int32_t* vb, int vsplit, VisSched* out) {
+    if (!hb || !vb || !out || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || vsplit < 1) {
+        vis::set_error("vis_sched_build: bad arguments");
+        return VIS_E_INVALID;
+    }
+    auto unsupported = [](const char* why) { vis::set_error("vis_sched_build: %s", why); return VIS_E_UNSUPPORTED; };
+    if (dst_h % 28 || dst_w % 28) return unsupported("output size is not a multiple of 28");
+    if (src_pitch % 16 || src_pitch < (int64_t)src_w * 3) return unsupported("row pitch must be a multiple of 16");
+    if ((int64_t)src_h > 100 * (int64_t)src_w && dst_h < src_h) return unsupported("vertical-first pass order");
+    if (src_w > 65528 || dst_w > 65528) return unsupported("image too wide");
+    const int hkt = vis_max_taps(hb, dst_w), vkt = vis_max_taps(vb, dst_h);
+    const int mk = hkt > vkt ? hkt : vkt;
+    const int cls = mk <= 6 ? 6 : mk <= 8 ? 8 : 0;
+    if (!cls) return unsupported("more than 8 taps");
+    std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
+    if (!schedule_ends(hb, dst_w, cls, hl)) return unsupported("horizontal upscale");
+    if (!schedule_ends(vb, dst_h, cls, vl)) return unsupported("vertical upscale");
+
+    VisSched& s = *out;
+    std::memset(&s, 0, sizeof(s));
+    s.src_h = src_h; s.src_w = src_w; s.dst_h = dst_h; s.dst_w = dst_w; s.src_pitch = src_pitch; s.kt = cls;
+    const int stride = vis_record_stride(cls);
+    auto last = [](const int32_t* b, int i) { return b[2 * i] + b[2 * i + 1] - 1; };
+    auto span_of = [&](int x0, int x1, int* px0) {
+        *px0 = hb[2 * x0] & ~15;                                   // 48-byte aligned: bulk copies need 16
+        int bytes = align_up((last(hb, x1 - 1) + 1) * 3, 16) - *px0 * 3;
+        if ((int64_t)*px0 * 3 + bytes > src_pitch) bytes = (int)(src_pitch - (int64_t)*px0 * 3);
+        return bytes;
+    };
+    // column strips: the widest strips (multiples of 28 columns, <= 336) whose shared-memory layout fits
+    const int blocks = dst_w / 28;
+    int n_strips = 0;
+    for (int per = kMaxStripW / 28; per >= 1 && !n_strips; --per) {
+        const int n = (blocks + per - 1) / per;
+        if (n > VIS_SCHED_MAX_STRIPS) break;
+        int worst_span = 0, worst_w = 0;
+        for (int i = 0; i < n; ++i) {
+            const int b0 = (int)((int64_t)blocks * i / n), b1 = (int)((int64_t)blocks * (i + 1) / n);
+            int px0;
+            const int span = span_of(b0 * 28, b1 * 28, &px0);
+            worst_span = span > worst_span ? span : worst_span;
+            worst_w = (b1 - b0) * 28 > worst_w ? (b1 - b0) * 28 : worst_w;
+        }
+        if (make_layout_s(stage_pitch_for(worst_span), worst_w, stride).total <= kSmemMax) {
+            n_strips = n;
+            s.stage_pitch = stage_pitch_for(worst_span);
+            s.max_strip_w = worst_w;
+        }
+    }
+    if (!n_strips) return unsupported("no strip width fits shared memory");
+    s.n_strips = n_strips;
+    int mask_at = 0;
+    auto mask_room = [&](int bytes) { return mask_at + bytes <= VIS_SCHED_MASK_BYTES; };
+    for (int i = 0; i < n_strips; ++i) {
+        VisSchedStrip& S = s.strip[i];
+        S.x0 = (int)((int64_t)blocks * i / n_strips) * 28;
+        S.x1 = (int)((int64_t)blocks * (i + 1) / n_strips) * 28;
+        S.row_bytes = span_of(S.x0, S.x1, &S.px0);
+        const int sw = S.x1 - S.x0;
+        for (int u = 0; u < VIS_SCHED_SUBS; ++u) {
+            VisSchedSub& U = s.sub[i][u];
+            const int xa = S.x0 + (int)((int64_t)sw * u / VIS_SCHED_SUBS), xb = S.x0 + (int)((int64_t)sw * (u + 1) / VIS_SCHED_SUBS);
+            U.xa = (uint16_t)xa; U.xb = (uint16_t)xb;
+            if (xa >= xb) continue;                                    // nsteps = 0
+            const int p0 = hb[2 * xa] & ~(kStepPx - 1);
+            const int nsteps = (hl[xb - 1] - p0) / kStepPx + 1;
+            if (!mask_room(nsteps) || nsteps > 65535) return unsupported("schedule too large");
+            U.p0 = (uint16_t)p0; U.nsteps = (uint16_t)nsteps; U.mask_off = (uint16_t)mask_at;
+            for (int x = xa; x < xb; ++x) {
+                const int rel = hl[x] - p0;
+                s.mask[mask_at + rel / kStepPx] |= (uint8_t)(1u << (rel % kStepPx));
+            }
+            mask_at += nsteps;
+        }
+    }
+    // row segments: multiples of 14 output rows; chunk bases are multiples of 16 input rows
+    const int prow = dst_h / 14;
+    if (vsplit > prow) vsplit = prow;
+    if (vsplit > VIS_SCHED_MAX_SEGS) vsplit = VIS_SCHED_MAX_SEGS;
+    s.n_segs = vsplit;
+    mask_at = align_up(mask_at, 4);
+    for (int g = 0; g < vsplit; ++g) {
+        VisSchedSeg& G = s.seg[g];
+        G.y0 = (int)((int64_t)prow * g / vsplit) * 14;
+        G.y1 = (int)((int64_t)prow * (g + 1) / vsplit) * 14;
+        G.r_first = vb[2 * G.y0] & ~15;
+        G.r_end = vl[G.y1 - 1] + 1;                                  // may exceed src_h by the virtual rows
+        const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+        const int bytes = n_chunks * (kChunk / kRing);
+        if (!mask_room(bytes)) return unsupported("schedule too large");
+        G.mask_off = mask_at;
+        for (int y = G.y0; y < G.y1; ++y) {
+            const int rel = vl[y] - G.r_first;
+            s.mask[mask_at + rel / kRing] |= (uint8_t)(1u << (rel % kRing));
+        }
+        mask_at += bytes;
+    }
+    return VIS_OK;
+}
+
+int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt,
+                           int32_t* rec, int64_t rec_capacity) {
+    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8)) {
+        vis::set_error("vis_sched_pack_records: bad arguments");
+        return VIS_E_INVALID;
+    }
+    const int stride = vis_record_stride(kt);
+    if (rec_capacity < (int64_t)(out_size + 1) * stride) {
+        vis::set_error("vis_sched_pack_records: capacity too small");
+        return VIS_E_CAPACITY;
+    }
+    std::vector<int> ends;
+    if (!schedule_ends(bounds, out_size, kt, ends)) {
+        vis::set_error("vis_sched_pack_records: table is not schedulable (upscale or too many taps)");
+        return VIS_E_UNSUPPORTED;
+    }
+    std::memset(rec, 0, sizeof(int32_t) * (size_t)(out_size + 1) * stride);
+    for (int o = 0; o < out_size; ++o) {
+        const int first = bounds[2 * o], taps = bounds[2 * o + 1];
+        const int shift = ends[o] - (first + taps - 1);             // leading zero slots for virtual samples
+        int32_t* r = rec + (size_t)o * stride;
+        for (int t = 0; t < taps; ++t) r[shift + t] = k[(size_t)o * ksize + (taps - 1 - t)];
+        r[stride - 2] = first;
+        r[stride - 1] = ends[o];
+    }
+    return VIS_OK;
+}
+
+int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,
+                               const int32_t* hrec, const int32_t* vrec,
+                               const float* lut768, float* pixel_values, void* stream) {
+    if (!sched || !frames || !hrec || !vrec || !lut768 || !pixel_values || n_frames <= 0 ||
+        (sched->kt != 6 && sched->kt != 8) || sched->n_strips <= 0 || sched->n_segs <= 0) {
+        vis::set_error("vis_preprocess_fused_sched: bad arguments");
+        return VIS_E_INVALID;
+    }
+    const LayoutS L = make_layout_s(sched->stage_pitch, sched->max_strip_w, vis_record_stride(sched->kt));
+    if (L.total > kSmemMax) {
+        vis::set_error("vis_preprocess_fused_sched: %d bytes of shared memory needed", L.total);
+        return VIS_E_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sched->kt == 6) return launch_sched<6, 8>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
+    return launch_sched<8, 12>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
+}
+
+}  // extern "C"

@@ -35,6 +35,8 @@ class _Geometry:
     vtable: T.CoeffTable
     n_rows: int
     plans: dict                  # vsplit -> StripPlan
+    scheds: dict                 # (pitch, n_segs) -> VisSched bytes, or None when the scheduled kernel declines
+    srec: list                   # [hrec, vrec] device records of the scheduled kernel (packed on first use)
 
 
 @dataclass
@@ -49,10 +51,21 @@ class _FusedLaunch:
 
 
 @dataclass
+class _SchedLaunch:
+    """One geometry, statically scheduled kernel (vis_preprocess_fused_sched)."""
+    sched: np.ndarray            # the VisSched parameter block (host bytes, opaque)
+    n_frames: int
+    n_items: int
+    frames: torch.Tensor         # device VisFrameRef[]
+    hrec: torch.Tensor
+    vrec: torch.Tensor
+
+
+@dataclass
 class BatchPlan:
     total_rows: int
     grid_thw: torch.Tensor       # int64 [B, 3] (host)
-    fused: list
+    fused: list                  # _FusedLaunch (general kernel, one per tap class) and _SchedLaunch (one per geometry)
     generic: list                # (frame index, geometry, first output row)
 
 
@@ -94,7 +107,7 @@ class Engine:
                 hrec = torch.from_numpy(T.pack_records(ht, kt)).to(self.device)
                 vrec = torch.from_numpy(T.pack_records(vt, kt)).to(self.device)
             g = _Geometry(src_h, src_w, dst_h, dst_w, kt, hrec, vrec, ht, vt,
-                          (dst_h // G.PATCH_SIZE) * (dst_w // G.PATCH_SIZE), {})
+                          (dst_h // G.PATCH_SIZE) * (dst_w // G.PATCH_SIZE), {}, {}, [])
             self._geoms[key] = g
         return g
 
@@ -104,6 +117,29 @@ class Engine:
             p = T.plan_strips(g.dst_h, g.dst_w, g.htable, g.kt, vsplit)
             g.plans[vsplit] = p
         return p
+
+    def _sched(self, g: _Geometry, pitch: int, n_segs: int):
+        """VisSched parameter block for (geometry, row pitch, row segments), or None if the geometry needs the
+        general kernel (upscaling, > 8 taps, schedule too large)."""
+        key = (pitch, n_segs)
+        if key not in g.scheds:
+            buf = np.zeros(self.L.vis_sched_sizeof(), np.uint8)
+            rc = self.L.vis_sched_build(g.src_h, g.src_w, g.dst_h, g.dst_w, pitch, N.i32ptr(g.htable.bounds),
+                                        N.i32ptr(g.vtable.bounds), n_segs, buf.ctypes.data_as(C.c_void_p))
+            if rc == N.VIS_E_UNSUPPORTED:
+                buf = None
+            else:
+                N.check(rc, "vis_sched_build")
+                if not g.srec:
+                    kt = int(np.frombuffer(buf[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["kt"])
+                    stride = self.L.vis_record_stride(kt)
+                    for t in (g.htable, g.vtable):
+                        rec = np.zeros((t.out_size + 1, stride), np.int32)
+                        N.check(self.L.vis_sched_pack_records(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, kt,
+                                                              N.i32ptr(rec), rec.size), "vis_sched_pack_records")
+                        g.srec.append(torch.from_numpy(rec).to(self.device))
+            g.scheds[key] = buf
+        return g.scheds[key]
 
     # ------------------------------------------------------------------ generic resample (uint8 -> uint8)
     def resize_u8(self, img: torch.Tensor, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS, stream=None) -> torch.Tensor:
@@ -141,7 +177,7 @@ class Engine:
 
     # ------------------------------------------------------------------ frames -> pixel_values
     def plan_batch(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
-                   force_generic: bool = False, vsplit: int | None = None) -> "BatchPlan":
+                   force_generic: bool = False, vsplit: int | None = None, path: str = "auto") -> "BatchPlan":
         """Host-side planning for one batch: geometry, output rows, descriptor arrays (uploaded once).
 
         Plans depend only on pointers and shapes, so they are cached and reused when the same device buffers are
@@ -151,13 +187,13 @@ class Engine:
         if uniform:
             self._check_u8(frames)
             key = ("u", frames.data_ptr(), tuple(frames.shape), tuple(frames.stride()), min_pixels, max_pixels,
-                   force_generic, vsplit)
+                   force_generic, vsplit, path)
         else:
             frames = list(frames)
             for f in frames:
                 self._check_u8(f)
             key = ("l", tuple((f.data_ptr(), tuple(f.shape), tuple(f.stride())) for f in frames), min_pixels,
-                   max_pixels, force_generic, vsplit)
+                   max_pixels, force_generic, vsplit, path)
         plan = self._batch_plans.get(key)
         if plan is not None:
             return plan
@@ -202,11 +238,33 @@ class Engine:
                 groups.setdefault((g.kt, id(g)), (g, []))[1].append(i)
             else:
                 plan.generic.append((i, g, int(row0[i])))
-        # one launch per tap class; all geometries of a class share it
+        want = 3 * self.sm_count                     # work items wanted: a few per SM
+        # statically scheduled kernel: one launch per (geometry, pitch) group it accepts
         by_class: dict = {}
         for (kt, _), (g, idx) in groups.items():
-            by_class.setdefault(kt, []).append((g, np.asarray(idx)))
-        want = 3 * self.sm_count                     # work items wanted: a few per SM
+            idx = np.asarray(idx)
+            rest = idx
+            if path != "general":
+                rest_parts = []
+                for pitch in np.unique(pitches[idx]):
+                    sel = idx[pitches[idx] == pitch]
+                    head = self._sched(g, int(pitch), 1)
+                    if head is None:
+                        rest_parts.append(sel)
+                        continue
+                    per = int(np.frombuffer(head[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["n_strips"])
+                    segs = vsplit if vsplit is not None else max(1, min(8, -(-want // (len(sel) * per))))
+                    sched = self._sched(g, int(pitch), max(1, min(segs, g.dst_h // 14)))
+                    hd = np.frombuffer(sched[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]
+                    ref = np.zeros(len(sel), N.FRAME_REF_DTYPE)
+                    ref["src"], ref["row0"] = ptrs[sel].astype(np.uint64), row0[sel]
+                    plan.fused.append(_SchedLaunch(
+                        sched, len(sel), len(sel) * int(hd["n_strips"]) * int(hd["n_segs"]),
+                        torch.from_numpy(ref.view(np.uint8).copy()).to(self.device), g.srec[0], g.srec[1]))
+                rest = np.concatenate(rest_parts) if rest_parts else np.zeros(0, np.int64)
+            if len(rest):
+                by_class.setdefault(kt, []).append((g, rest))
+        # general kernel: one launch per tap class; all geometries of a class share it
         for kt, members in by_class.items():
             n_class = sum(len(idx) for _, idx in members)
             fr_parts, st_parts, span, strip_w, base = [], [], 0, 0, 0
@@ -237,14 +295,18 @@ class Engine:
         return plan
 
     def preprocess(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
-                   out: torch.Tensor | None = None, force_generic: bool = False, vsplit: int | None = None):
+                   out: torch.Tensor | None = None, force_generic: bool = False, vsplit: int | None = None,
+                   path: str = "auto"):
         """RGB uint8 HWC CUDA frames -> (pixel_values f32 [sum N_i, 1176] on device, image_grid_thw int64 [B, 3]).
 
         ``frames``: a ``[B, H, W, 3]`` tensor or a list of ``[H, W, 3]`` tensors (mixed sizes allowed).
         Same result as ``Qwen2VLImageProcessorPil(size={shortest_edge: min_pixels, longest_edge: max_pixels})``.
-        Work is enqueued on the current CUDA stream; nothing synchronises.
+        Work is enqueued on the current CUDA stream; nothing synchronises.  ``path``: "auto" (statically scheduled
+        kernel where it applies, general fused kernel otherwise) or "general" (never the scheduled kernel; tests).
         """
-        plan = self.plan_batch(frames, min_pixels, max_pixels, force_generic, vsplit)
+        if path not in ("auto", "general"):
+            raise ValueError("path must be 'auto' or 'general'")
+        plan = self.plan_batch(frames, min_pixels, max_pixels, force_generic, vsplit, path)
         if out is None:
             out = torch.empty((plan.total_rows, G.ROW_FLOATS), dtype=torch.float32, device=self.device)
         elif (tuple(out.shape) != (plan.total_rows, G.ROW_FLOATS) or out.dtype != torch.float32
@@ -259,6 +321,13 @@ class Engine:
             N.check(self.L.vis_normalize_patchify(resized.data_ptr(), resized.stride(0), g.dst_h, g.dst_w,
                                                   self.lut.data_ptr(), out.data_ptr(), r0, sp), "vis_normalize_patchify")
         for fl in plan.fused:
+            if isinstance(fl, _SchedLaunch):
+                N.check(self.L.vis_preprocess_fused_sched(fl.sched.ctypes.data_as(C.c_void_p), fl.frames.data_ptr(),
+                                                          fl.n_frames, fl.hrec.data_ptr(), fl.vrec.data_ptr(),
+                                                          self.lut.data_ptr(), out.data_ptr(), sp),
+                        "vis_preprocess_fused_sched")
+                launches += 1
+                continue
             N.check(self.L.vis_preprocess_fused(fl.frames.data_ptr(), fl.n_frames, fl.strips.data_ptr(), fl.n_strips,
                                                 fl.kt, fl.span_bytes, fl.strip_w,
                                                 self.lut.data_ptr(), out.data_ptr(), sp), "vis_preprocess_fused")
