@@ -334,7 +334,7 @@ def main():
     achieved = args.batch * BYTES_PER_IMAGE / kernel_s / 1e9
     traffic, traffic_src = None, None                        # measured DRAM bytes per launch, from the committed ncu capture
     try:
-        rec = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(f"k_fused_ws@{args.batch}x1080p")
+        rec = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(f"k_fused_sched@{args.batch}x1080p")
         if rec:
             traffic, traffic_src = rec["dram_bytes_read"] + rec["dram_bytes_write"], rec["source"]
     except Exception:
@@ -350,7 +350,7 @@ def main():
         "e2e_full_readback": {"value": full_value, "unit": "images/s",
                               "d2h_bytes_per_step": args.batch * ROWS * 1176 * 4},
         "gpu_launches": launches_per_step * args.steps + e2e_launches * e2e_steps,
-        "roofline": {"bound": "hbm", "kernel": "k_fused (vis_preprocess_fused)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "k_fused_sched (vis_preprocess_fused_sched)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
                      "traffic_source": traffic_src, "algorithmic_bytes_per_launch": args.batch * BYTES_PER_IMAGE,
                      "peak_source": peak_src, "bytes_per_image": BYTES_PER_IMAGE,
