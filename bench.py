@@ -172,7 +172,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ main
+def emit(line: dict) -> None:
+    """The ONE JSON line, on the real stdout (libraries such as NCCL print banners to fd 1; see main)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the driver: everything any library prints to fd 1 goes to stderr instead
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -218,7 +231,7 @@ def main():
                                            f"forked workers (one thread each), {total:.1f} s, on {cpu_model()}"},
                 "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ---------------- CPU baseline (rank 0, N=1) BEFORE CUDA is initialised (fork safety) ----------------
@@ -358,7 +371,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
