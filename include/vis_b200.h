@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 2
+#define VIS_B200_ABI_VERSION 3
 
 /* status codes */
 #define VIS_OK            0
@@ -207,10 +207,18 @@ typedef struct VisOverlayFrame {
     int32_t        group_begin, group_end;   /* this frame's group headers in leaves[]; its leaf array starts at group_begin */
 } VisOverlayFrame;
 
-/* frames / leaves: DEVICE arrays. One launch draws every frame of the batch (<= 65535 frames).
- * Out of place (dst != src) every pixel is written; in place only tiles a box touches.  [device] */
-int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int max_h, int max_w,
-                     const VisLeaf* leaves, void* stream);
+/* tiles (64x16 pixels) of ONE frame that some leaf can touch, from the sub-group boxes vis_overlay_expand wrote:
+ * tiles_out[i] = tx | ty << 16, row-major.  Returns the count, or VIS_E_CAPACITY with *needed.       [host] */
+int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, int n_boxes,
+                      int32_t* tiles_out, int capacity, int* needed);
+
+typedef struct VisOverlayTile { int32_t frame; int32_t txy; } VisOverlayTile;   /* frame index, tx | ty << 16 */
+
+/* frames / tiles / leaves: DEVICE arrays (<= 65535 frames).  copy_frames != 0: every frame with dst != src is
+ * first copied src -> dst (vectorised), then the listed tiles are drawn in place on dst; frames drawn in place
+ * (dst == src) are only touched inside listed tiles.                                    [device] */
+int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int copy_frames,
+                     const VisOverlayTile* tiles, int n_tiles, const VisLeaf* leaves, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,6 +46,7 @@ SCHED_HEAD_DTYPE = np.dtype([("src_h", np.int32), ("src_w", np.int32), ("dst_h",
                              ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("reserved", np.int32)], align=True)
 
 assert FRAME_DTYPE.itemsize == 56 and STRIP_DTYPE.itemsize == 20 and BOX_DTYPE.itemsize == 32
+OVERLAY_TILE_DTYPE = np.dtype([("frame", np.int32), ("txy", np.int32)], align=True)
 assert LEAF_DTYPE.itemsize == 48 and OVERLAY_FRAME_DTYPE.itemsize == 48
 
 EXPORTS = [
@@ -54,7 +55,7 @@ EXPORTS = [
     "vis_max_taps", "vis_fused_kt_class", "vis_record_stride", "vis_pack_records", "vis_fused_supported",
     "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
     "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_preprocess_fused_sched",
-    "vis_overlay_expand", "vis_overlay_draw",
+    "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_draw",
 ]
 
 
@@ -77,7 +78,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 2:
+        if L.vis_abi_version() != 3:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -108,7 +109,8 @@ def _declare(L: C.CDLL) -> None:
     L.vis_sched_pack_records.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, C.c_int64]
     L.vis_preprocess_fused_sched.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
-    L.vis_overlay_draw.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.vis_overlay_tiles.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
+    L.vis_overlay_draw.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]
     for name in EXPORTS:
         if name != "vis_last_error":
             getattr(L, name).restype = C.c_int

@@ -1,13 +1,13 @@
 // vis_overlay.cu — device half of the defect-overlay rasteriser (cv2 drawing calls of
 // utils/image_utils.py:259-313 in the reference, reproduced pixel for pixel).
 //
-// One CTA owns a 64x16 pixel tile of one frame (256 threads x 4 pixels, 12 bytes per thread kept in
-// registers).  The tile scans the frame's GROUP headers (one per box) in parallel, then for every box whose
-// bounding box touches the tile scans that box's leaves 256 at a time, compacts the touching ones IN ORDER
-// into shared memory (warp ballots + a block prefix), and every thread applies them in list order to its own
-// pixels.  Per-pixel in-order application is what makes the result identical to OpenCV's sequential drawing:
-// fills and LINE_8 points overwrite, LineAA pixels blend (twice, 8-bit alpha) with whatever is there.
-// Tiles that no box touches are a straight 12-byte-per-thread copy (or nothing at all when drawing in place).
+// Only tiles that some leaf can touch are visited: the host lists them (vis_overlay_tiles, from the sub-group boxes),
+// everything else is a plain vectorised frame copy (out of place) or nothing at all (in place).  A CTA owns one
+// listed 64x16 tile; each warp owns a 32x4 sub-tile (lane = 4 pixels, 12 bytes in registers) and culls on its own
+// with ballots: box header -> sub-group headers (one per 32 consecutive leaves) -> leaves; touching leaves are
+// staged IN ORDER in shared memory and every lane applies them in list order to its own pixels.  Per-pixel in-order
+// application is what makes the result identical to OpenCV's sequential drawing: fills and LINE_8 points
+// overwrite, LineAA pixels blend (twice, 8-bit alpha) with whatever is there.
 #include "vis_internal.h"
 #include "vis_overlay_leaf.h"
 
@@ -128,128 +128,157 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
     }
 }
 
-// ordered compaction: threads with `hit` get consecutive slots in thread order; returns the slot (or -1) and total
-__device__ __forceinline__ int compact(bool hit, int* s_warp, int& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) s_warp[warp] = __popc(m);
-    __syncthreads();
-    int before = 0, all = 0;
+// frame copy for out-of-place drawing: rows of `row_bytes` bytes, 16-byte vectors when everything is aligned
+__global__ void __launch_bounds__(256)
+k_overlay_copy(const VisOverlayFrame* __restrict__ frames) {
+    const VisOverlayFrame f = frames[blockIdx.y];
+    if (f.src == f.dst) return;
+    int64_t rows = f.h, row_bytes = (int64_t)f.w * 3;
+    if (f.src_pitch == row_bytes && f.dst_pitch == row_bytes) { row_bytes *= rows; rows = 1; }     // one long row
+    const bool vec = (((uintptr_t)f.src | (uintptr_t)f.dst | (uint64_t)f.src_pitch | (uint64_t)f.dst_pitch) & 15) == 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int64_t per_row = row_bytes / 16, n = rows * per_row;
+        for (int64_t i = t0; i < n; i += 4 * stride) {
+            uint4 v[4];
 #pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k) {
-        const int n = s_warp[k];
-        before += k < warp ? n : 0;
-        all += n;
+            for (int k = 0; k < 4; ++k) {
+                const int64_t j = i + k * stride;
+                if (j < n) v[k] = __ldcs(reinterpret_cast<const uint4*>(f.src + (j / per_row) * f.src_pitch) + j % per_row);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t j = i + k * stride;
+                if (j < n) __stcs(reinterpret_cast<uint4*>(f.dst + (j / per_row) * f.dst_pitch) + j % per_row, v[k]);
+            }
+        }
+        const int64_t tail0 = per_row * 16, tail = row_bytes - tail0;
+        for (int64_t i = t0; i < rows * tail; i += stride)
+            f.dst[(i / tail) * f.dst_pitch + tail0 + i % tail] = f.src[(i / tail) * f.src_pitch + tail0 + i % tail];
+    } else {
+        for (int64_t i = t0; i < rows * row_bytes; i += stride)
+            f.dst[(i / row_bytes) * f.dst_pitch + i % row_bytes] = f.src[(i / row_bytes) * f.src_pitch + i % row_bytes];
     }
-    total = all;
-    __syncthreads();                              // s_warp may be reused right after
-    return hit ? before + __popc(m & ((1u << lane) - 1)) : -1;
 }
 
+// In-place drawing of the touched tiles.  CTA = one 64x16 tile of the host-built tile list; each of its 8 warps owns a
+// 32x4 pixel sub-tile (lane = 4 pixels of one row) and works on its own: box header (uniform test) -> sub-group
+// headers of that box, 32 per ballot -> leaves of touching sub-groups, 32 per ballot -> touching leaves staged IN
+// ORDER in the warp's shared-memory slots and applied per pixel in list order.  No block-wide barrier.
 __global__ void __launch_bounds__(kThreads)
-k_overlay(const VisOverlayFrame* __restrict__ frames, const VisLeaf* __restrict__ leaves) {
-    __shared__ int s_warp[kThreads / 32];
-    __shared__ int s_groups[kThreads];
-    __shared__ int s_leaf[kThreads][VIS_LEAF_WORDS];
+k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile* __restrict__ tiles,
+                const VisLeaf* __restrict__ leaves) {
+    __shared__ int s_leaf[kThreads / 32][32][VIS_LEAF_WORDS];
     __shared__ int s_filter[64];
-
-    const VisOverlayFrame f = frames[blockIdx.z];
-    Tile t;
-    t.x0 = blockIdx.x * kTileW;
-    t.y0 = blockIdx.y * kTileH;
-    if (t.x0 >= f.w || t.y0 >= f.h) return;
-    t.x1 = min(t.x0 + kTileW, f.w) - 1;
-    t.y1 = min(t.y0 + kTileH, f.h) - 1;
-    const int tid = threadIdx.x;
-    const int x = t.x0 + (tid & 15) * kPx, y = t.y0 + (tid >> 4);
-    const int nv = y < f.h ? max(0, min(kPx, f.w - x)) : 0;      // valid pixels of this thread
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 64) s_filter[tid] = c_filter[tid];
+    __syncthreads();
 
-    // ---- load ----
-    int c[kPx][3];
-    const uint8_t* sp = f.src + (size_t)y * f.src_pitch + (size_t)x * 3;
-    const bool in_place = f.src == f.dst;
-    const bool vec_in = ((f.src_pitch | (int64_t)(uintptr_t)f.src) & 3) == 0;
-    if (nv == kPx && vec_in) {
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(sp);
-        const uint32_t a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2);
-        c[0][0] = a & 0xff; c[0][1] = (a >> 8) & 0xff; c[0][2] = (a >> 16) & 0xff;
-        c[1][0] = a >> 24;  c[1][1] = b & 0xff;        c[1][2] = (b >> 8) & 0xff;
-        c[2][0] = (b >> 16) & 0xff; c[2][1] = b >> 24; c[2][2] = d & 0xff;
-        c[3][0] = (d >> 8) & 0xff;  c[3][1] = (d >> 16) & 0xff; c[3][2] = d >> 24;
-    } else {
-#pragma unroll
-        for (int j = 0; j < kPx; ++j)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) c[j][k] = j < nv ? (int)sp[j * 3 + k] : 0;
-    }
+    const VisOverlayTile tl = tiles[blockIdx.x];
+    const VisOverlayFrame f = frames[tl.frame];
+    Tile t;
+    t.x0 = (tl.txy & 0xffff) * kTileW + (warp & 1) * 32;
+    t.y0 = ((unsigned)tl.txy >> 16) * kTileH + (warp >> 1) * 4;
+    if (t.x0 >= f.w || t.y0 >= f.h) return;
+    t.x1 = min(t.x0 + 32, f.w) - 1;
+    t.y1 = min(t.y0 + 4, f.h) - 1;
+    const int x = t.x0 + (lane & 7) * kPx, y = t.y0 + (lane >> 3);
+    const int nv = y < f.h ? max(0, min(kPx, f.w - x)) : 0;      // valid pixels of this lane
 
-    // ---- group headers touching this tile, in order ----
     const VisLeaf* fl = leaves + f.group_begin;       // the frame's leaf array; header indices are relative to it
     const int n_groups = f.group_end - f.group_begin;
-    bool dirty = false;
-    for (int g0 = 0; g0 < n_groups; g0 += kThreads) {
-        const int gi = g0 + tid;
-        bool hit = false;
-        if (gi < n_groups) {
-            const int2 bb = __ldg(reinterpret_cast<const int2*>(&fl[gi].w[10]));
-            hit = touches(t, bb.x, bb.y);
-        }
-        int n_hit;
-        const int slot = compact(hit, s_warp, n_hit);
-        if (slot >= 0) s_groups[slot] = gi;
-        __syncthreads();
-        for (int k = 0; k < n_hit; ++k) {
-            const int g = s_groups[k];
-            const int lb = __ldg(&fl[g].w[2]), le = __ldg(&fl[g].w[3]);
-            for (int l0 = lb; l0 < le; l0 += kThreads) {
-                const int li = l0 + tid;
+    int c[kPx][3];
+    bool loaded = false, dirty = false;
+    uint8_t* const px = f.dst + (size_t)y * f.dst_pitch + (size_t)x * 3;
+    const bool vec = ((f.dst_pitch | (int64_t)(uintptr_t)f.dst) & 3) == 0;
+    int (*my_leaf)[VIS_LEAF_WORDS] = s_leaf[warp];
+
+    for (int g = 0; g < n_groups; ++g) {
+        const int2 gbb = __ldg(reinterpret_cast<const int2*>(&fl[g].w[10]));
+        if (!touches(t, gbb.x, gbb.y)) continue;
+        const int2 h01 = __ldg(reinterpret_cast<const int2*>(&fl[g].w[2]));       // first leaf, end leaf
+        const int2 h23 = __ldg(reinterpret_cast<const int2*>(&fl[g].w[4]));       // first sub-group header, count
+        const int lb = h01.x, le = h01.y, sb = h23.x, ns = h23.y;
+        for (int s0 = 0; s0 < ns; s0 += 32) {
+            const int si = s0 + lane;
+            bool hit = false;
+            if (si < ns) {
+                const int2 bb = __ldg(reinterpret_cast<const int2*>(&fl[sb + si].w[10]));
+                hit = touches(t, bb.x, bb.y);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                const int li = lb + (s0 + k) * LEAF_SUB_LEAVES + lane;
                 bool lhit = false;
                 if (li < le) {
                     const int2 bb = __ldg(reinterpret_cast<const int2*>(&fl[li].w[10]));
-                    lhit = touches(t, bb.x, bb.y) && (__ldg(&fl[li].w[0]) & LEAF_KIND_MASK) > LEAF_GROUP;
+                    lhit = touches(t, bb.x, bb.y);
                 }
-                int n_leaf;
-                const int ls = compact(lhit, s_warp, n_leaf);
-                if (ls >= 0) {
+                const unsigned lm = __ballot_sync(0xffffffffu, lhit);
+                if (!lm) continue;
+                if (!loaded) {                                    // first leaf that reaches this sub-tile: fetch the pixels
+                    loaded = true;
+                    if (nv == kPx && vec) {
+                        const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
+                        const uint32_t a = q[0], b = q[1], d = q[2];
+                        c[0][0] = a & 0xff; c[0][1] = (a >> 8) & 0xff; c[0][2] = (a >> 16) & 0xff;
+                        c[1][0] = a >> 24;  c[1][1] = b & 0xff;        c[1][2] = (b >> 8) & 0xff;
+                        c[2][0] = (b >> 16) & 0xff; c[2][1] = b >> 24; c[2][2] = d & 0xff;
+                        c[3][0] = (d >> 8) & 0xff;  c[3][1] = (d >> 16) & 0xff; c[3][2] = d >> 24;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kPx; ++j)
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) c[j][q] = j < nv ? (int)px[j * 3 + q] : 0;
+                    }
+                }
+                if (lhit) {
                     const int4* src = reinterpret_cast<const int4*>(&fl[li]);
-                    int4* dst = reinterpret_cast<int4*>(s_leaf[ls]);
+                    int4* dst = reinterpret_cast<int4*>(my_leaf[__popc(lm & ((1u << lane) - 1))]);
                     dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
                 }
-                __syncthreads();
+                __syncwarp();
+                const int n_leaf = __popc(lm);
                 if (nv > 0)
-                    for (int q = 0; q < n_leaf; ++q) dirty |= apply_leaf(s_leaf[q], s_filter, x, y, c);
-                __syncthreads();
+                    for (int q = 0; q < n_leaf; ++q) dirty |= apply_leaf(my_leaf[q], s_filter, x, y, c);
+                __syncwarp();
             }
         }
-        __syncthreads();
     }
 
-    // ---- store ----
-    if (nv == 0 || (in_place && !dirty)) return;
-    uint8_t* dp = f.dst + (size_t)y * f.dst_pitch + (size_t)x * 3;
-    const bool vec_out = ((f.dst_pitch | (int64_t)(uintptr_t)f.dst) & 3) == 0;
-    if (nv == kPx && vec_out) {
-        uint32_t* q = reinterpret_cast<uint32_t*>(dp);
+    if (!dirty) return;
+    if (nv == kPx && vec) {
+        uint32_t* q = reinterpret_cast<uint32_t*>(px);
         q[0] = (uint32_t)c[0][0] | ((uint32_t)c[0][1] << 8) | ((uint32_t)c[0][2] << 16) | ((uint32_t)c[1][0] << 24);
         q[1] = (uint32_t)c[1][1] | ((uint32_t)c[1][2] << 8) | ((uint32_t)c[2][0] << 16) | ((uint32_t)c[2][1] << 24);
         q[2] = (uint32_t)c[2][2] | ((uint32_t)c[3][0] << 8) | ((uint32_t)c[3][1] << 16) | ((uint32_t)c[3][2] << 24);
     } else {
         for (int j = 0; j < nv; ++j)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) dp[j * 3 + k] = (uint8_t)c[j][k];
+            for (int q = 0; q < 3; ++q) px[j * 3 + q] = (uint8_t)c[j][q];
     }
 }
 
 }  // namespace
 
-extern "C" int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int max_h, int max_w,
-                                const VisLeaf* leaves, void* stream) {
-    if (!frames || n_frames <= 0 || max_h <= 0 || max_w <= 0 || n_frames > 65535) {
-        vis::set_error("vis_overlay_draw: bad arguments (frames=%d max %dx%d)", n_frames, max_w, max_h);
+extern "C" int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int copy_frames,
+                                const VisOverlayTile* tiles, int n_tiles, const VisLeaf* leaves, void* stream) {
+    if (!frames || n_frames <= 0 || n_frames > 65535 || n_tiles < 0 || (n_tiles && (!tiles || !leaves))) {
+        vis::set_error("vis_overlay_draw: bad arguments (frames=%d tiles=%d)", n_frames, n_tiles);
         return VIS_E_INVALID;
     }
-    dim3 grid((max_w + kTileW - 1) / kTileW, (max_h + kTileH - 1) / kTileH, n_frames);
-    k_overlay<<<grid, kThreads, 0, (cudaStream_t)stream>>>(frames, leaves);
-    return vis::check_launch("vis_overlay_draw");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (copy_frames) {                            // out of place: dst = src first, then draw in place on dst
+        k_overlay_copy<<<dim3(64, n_frames), 256, 0, st>>>(frames);
+        const int rc = vis::check_launch("vis_overlay_draw(copy)");
+        if (rc != VIS_OK) return rc;
+    }
+    if (n_tiles > 0) {
+        k_overlay_tiles<<<n_tiles, kThreads, 0, st>>>(frames, tiles, leaves);
+        return vis::check_launch("vis_overlay_draw");
+    }
+    return VIS_OK;
 }

@@ -135,11 +135,33 @@ class Emitter {
         gx1_ = gy1_ = INT_MIN;
     }
     void end_group(int slot) {                   // header = leaf range + bounding box of everything in it
+        const int first = group_first_, last = n_;
+        // sub-group headers: one per kSubLeaves consecutive leaves (range + union box), appended after the leaves.
+        // Consecutive leaves belong to the same stroke / dash / ring segment, so these boxes are small and let a
+        // tile inside a large defect box skip almost all of its leaves.
+        const int sub_first = n_;
+        for (int a = first; a < last; a += LEAF_SUB_LEAVES) {
+            const int b = std::min(a + LEAF_SUB_LEAVES, last);
+            VisLeaf h;
+            std::memset(&h, 0, sizeof h);
+            h.w[0] = LEAF_GROUP;
+            h.w[2] = a;
+            h.w[3] = b;
+            int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
+            for (int i = a; i < b && i < cap_; ++i) {
+                x0 = std::min(x0, out_[i].w[10] & 0xffff); x1 = std::max(x1, (int)((uint32_t)out_[i].w[10] >> 16));
+                y0 = std::min(y0, out_[i].w[11] & 0xffff); y1 = std::max(y1, (int)((uint32_t)out_[i].w[11] >> 16));
+            }
+            if (x0 <= x1 && y0 <= y1) pack_bbox(h, x0, y0, x1, y1); else { h.w[10] = 1; h.w[11] = 1; }
+            push(h);
+        }
         if (slot >= cap_) return;
         VisLeaf& l = out_[slot];
-        l.w[2] = group_first_;
-        l.w[3] = n_;
-        if (gx0_ > gx1_ || gy0_ > gy1_) { l.w[3] = group_first_; l.w[10] = 1; l.w[11] = 1; return; }   // nothing visible
+        l.w[2] = first;
+        l.w[3] = last;
+        l.w[4] = sub_first;
+        l.w[5] = n_ - sub_first;
+        if (gx0_ > gx1_ || gy0_ > gy1_) { l.w[3] = first; l.w[5] = 0; l.w[10] = 1; l.w[11] = 1; return; }   // nothing visible
         pack_bbox(l, gx0_, gy0_, gx1_, gy1_);
     }
 
@@ -594,4 +616,42 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
         return VIS_E_CAPACITY;
     }
     return em.count();
+}
+
+// Tiles (64x16 pixels, the CTA tile of vis_overlay.cu) that some leaf of the frame can touch, from the sub-group
+// boxes; row-major order, tiles_out[i] = tx | ty << 16.
+extern "C" int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, int n_boxes,
+                                 int32_t* tiles_out, int capacity, int* needed) {
+    if (img_h <= 0 || img_w <= 0 || img_h > 32767 || img_w > 32767 || n_boxes < 0 || (n_boxes && !leaves) ||
+        capacity < 0 || (capacity && !tiles_out)) {
+        vis::set_error("vis_overlay_tiles: bad arguments (h=%d w=%d boxes=%d)", img_h, img_w, n_boxes);
+        return VIS_E_INVALID;
+    }
+    constexpr int kTileW = 64, kTileH = 16;
+    const int tw = (img_w + kTileW - 1) / kTileW, th = (img_h + kTileH - 1) / kTileH;
+    std::vector<uint8_t> mark((size_t)tw * th, 0);
+    for (int g = 0; g < n_boxes; ++g) {
+        const VisLeaf& h = leaves[g];
+        for (int s = h.w[4]; s < h.w[4] + h.w[5]; ++s) {
+            const VisLeaf& sub = leaves[s];
+            const int x0 = sub.w[10] & 0xffff, x1 = (int)((uint32_t)sub.w[10] >> 16);
+            const int y0 = sub.w[11] & 0xffff, y1 = (int)((uint32_t)sub.w[11] >> 16);
+            if (x0 > x1 || y0 > y1) continue;
+            for (int ty = y0 / kTileH; ty <= std::min(y1 / kTileH, th - 1); ++ty)
+                for (int tx = x0 / kTileW; tx <= std::min(x1 / kTileW, tw - 1); ++tx) mark[(size_t)ty * tw + tx] = 1;
+        }
+    }
+    int n = 0;
+    for (int ty = 0; ty < th; ++ty)
+        for (int tx = 0; tx < tw; ++tx)
+            if (mark[(size_t)ty * tw + tx]) {
+                if (n < capacity) tiles_out[n] = tx | (ty << 16);
+                ++n;
+            }
+    if (needed) *needed = n;
+    if (n > capacity) {
+        vis::set_error("vis_overlay_tiles: %d tiles, capacity %d", n, capacity);
+        return VIS_E_CAPACITY;
+    }
+    return n;
 }

@@ -387,22 +387,31 @@ class Engine:
         """Host half of the overlay for a batch: box validation (reference rules) + expansion into leaves.
 
         ``shapes``: list of (H, W) per frame.  Returns (leaves uint8 device tensor, per-frame (begin, end) header
-        ranges, number of boxes drawn).
+        ranges, number of boxes drawn, device tile list, tile count).
         """
         from . import overlay as O
-        parts, ranges, at, drawn = [], [], 0, 0
-        for (h, w), boxes in zip(shapes, boxes_per_frame):
+        parts, ranges, tiles, at, drawn = [], [], [], 0, 0
+        for i, ((h, w), boxes) in enumerate(zip(shapes, boxes_per_frame)):
             px = O.boxes_to_pixels(boxes, w, h, confidence_threshold, criticality)
             leaves = O.expand_leaves(px, w, h)
             ranges.append((at, at + len(px)))          # the frame's array starts at `at`; headers come first
             parts.append(leaves)
+            t = np.zeros(0, N.OVERLAY_TILE_DTYPE)
+            txy = O.touched_tiles(leaves, len(px), w, h)
+            if len(txy):
+                t = np.zeros(len(txy), N.OVERLAY_TILE_DTYPE)
+                t["frame"], t["txy"] = i, txy
+            tiles.append(t)
             at += len(leaves)
             drawn += len(px)
         all_leaves = np.concatenate(parts) if parts else np.zeros(0, N.LEAF_DTYPE)
         if len(all_leaves) == 0:
             all_leaves = np.zeros(1, N.LEAF_DTYPE)
+        all_tiles = np.concatenate(tiles) if tiles else np.zeros(0, N.OVERLAY_TILE_DTYPE)
         d_leaves = torch.from_numpy(all_leaves.view(np.uint8).copy()).to(self.device)
-        return d_leaves, ranges, drawn
+        d_tiles = torch.from_numpy(np.ascontiguousarray(all_tiles).view(np.uint8).copy()).to(self.device) \
+            if len(all_tiles) else torch.zeros(8, dtype=torch.uint8, device=self.device)
+        return d_leaves, ranges, drawn, d_tiles, len(all_tiles)
 
     def annotate(self, frames, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium",
                  inplace: bool = False, plan=None):
@@ -422,7 +431,7 @@ class Engine:
         shapes = [(int(f.shape[0]), int(f.shape[1])) for f in flist]
         if plan is None:
             plan = self.plan_overlay(shapes, boxes_per_frame, confidence_threshold, criticality)
-        d_leaves, ranges, _ = plan
+        d_leaves, ranges, _, d_tiles, n_tiles = plan
         if inplace:
             outs = flist
             result = frames
@@ -443,14 +452,12 @@ class Engine:
         desc["group_end"] = [r[1] for r in ranges]
         d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.device)
         sp = _stream_ptr()
-        max_h, max_w = max(s[0] for s in shapes), max(s[1] for s in shapes)
-        self.last_launches = 0
-        for b0 in range(0, len(flist), 65535):
-            n = min(65535, len(flist) - b0)
-            N.check(self.L.vis_overlay_draw(d_desc.data_ptr() + b0 * N.OVERLAY_FRAME_DTYPE.itemsize, n, max_h, max_w,
-                                            d_leaves.data_ptr(), sp), "vis_overlay_draw")
-            self.last_launches += 1
-        self._keepalive = (d_desc, d_leaves)
+        if len(flist) > 65535:
+            raise ValueError("at most 65535 frames per annotate call")
+        N.check(self.L.vis_overlay_draw(d_desc.data_ptr(), len(flist), 0 if inplace else 1, d_tiles.data_ptr(), n_tiles,
+                                        d_leaves.data_ptr(), sp), "vis_overlay_draw")
+        self.last_launches = (0 if inplace else 1) + (1 if n_tiles else 0)
+        self._keepalive = (d_desc, d_leaves, d_tiles)
         return result
 
     # ------------------------------------------------------------------ helpers

@@ -98,3 +98,15 @@ def expand_leaves(pixel_boxes: np.ndarray, img_width: int, img_height: int) -> n
             continue
         N.check(rc, "vis_overlay_expand")
         return leaves[:rc]
+
+
+def touched_tiles(leaves: np.ndarray, n_boxes: int, img_width: int, img_height: int) -> np.ndarray:
+    """64x16 tiles of one frame that some leaf can touch (``tx | ty << 16``, row-major) via ``vis_overlay_tiles``."""
+    if n_boxes == 0 or len(leaves) == 0:
+        return np.zeros(0, np.int32)
+    L = N.lib()
+    cap = ((img_width + 63) // 64) * ((img_height + 15) // 16)
+    tiles = np.zeros(cap, np.int32)
+    n = N.check(L.vis_overlay_tiles(img_height, img_width, leaves.ctypes.data_as(C.c_void_p), n_boxes,
+                                    tiles.ctypes.data_as(C.c_void_p), cap, None), "vis_overlay_tiles")
+    return tiles[:n]
