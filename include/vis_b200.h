@@ -207,18 +207,27 @@ typedef struct VisOverlayFrame {
     int32_t        group_begin, group_end;   /* this frame's group headers in leaves[]; its leaf array starts at group_begin */
 } VisOverlayFrame;
 
-/* tiles (64x16 pixels) of ONE frame that some leaf can touch, from the sub-group boxes vis_overlay_expand wrote:
- * tiles_out[i] = tx | ty << 16, row-major.  Returns the count, or VIS_E_CAPACITY with *needed.       [host] */
+/* bins the sub-groups of ONE frame (runs of <= 32 consecutive leaves, written by vis_overlay_expand) into the
+ * 64x16-pixel tiles of the draw kernel.  tiles_out: 3 int32 per touched tile, row-major: tx | ty << 16, first ref,
+ * one past last ref.  refs_out: 2 int32 per ref, per tile IN LEAF ORDER: first leaf, one past last leaf (indices
+ * inside the frame's leaf array).  Returns the tile count, or VIS_E_CAPACITY with the needed counts.    [host] */
 int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, int n_boxes,
-                      int32_t* tiles_out, int capacity, int* needed);
+                      int32_t* tiles_out, int tile_capacity, int32_t* refs_out, int ref_capacity,
+                      int* tiles_needed, int* refs_needed);
 
-typedef struct VisOverlayTile { int32_t frame; int32_t txy; } VisOverlayTile;   /* frame index, tx | ty << 16 */
+typedef struct VisOverlayTile {   /* one CTA of the draw kernel */
+    int32_t frame;                /* index into frames[]                                         */
+    int32_t txy;                  /* tx | ty << 16                                               */
+    int32_t ref_begin, ref_end;   /* this tile's refs in the batch-wide refs[] array             */
+} VisOverlayTile;
+typedef struct VisOverlayRef { int32_t leaf_begin, leaf_end; } VisOverlayRef;   /* relative to the frame's leaf array */
 
-/* frames / tiles / leaves: DEVICE arrays (<= 65535 frames).  copy_frames != 0: every frame with dst != src is
- * first copied src -> dst (vectorised), then the listed tiles are drawn in place on dst; frames drawn in place
+/* frames / tiles / refs / leaves: DEVICE arrays (<= 65535 frames).  copy_frames != 0: every frame with dst != src
+ * is first copied src -> dst (vectorised), then the listed tiles are drawn in place on dst; frames drawn in place
  * (dst == src) are only touched inside listed tiles.                                    [device] */
 int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int copy_frames,
-                     const VisOverlayTile* tiles, int n_tiles, const VisLeaf* leaves, void* stream);
+                     const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
+                     const VisLeaf* leaves, void* stream);
 
 #ifdef __cplusplus
 }

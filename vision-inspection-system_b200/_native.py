@@ -46,7 +46,8 @@ SCHED_HEAD_DTYPE = np.dtype([("src_h", np.int32), ("src_w", np.int32), ("dst_h",
                              ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("reserved", np.int32)], align=True)
 
 assert FRAME_DTYPE.itemsize == 56 and STRIP_DTYPE.itemsize == 20 and BOX_DTYPE.itemsize == 32
-OVERLAY_TILE_DTYPE = np.dtype([("frame", np.int32), ("txy", np.int32)], align=True)
+OVERLAY_TILE_DTYPE = np.dtype([("frame", np.int32), ("txy", np.int32), ("ref_begin", np.int32), ("ref_end", np.int32)], align=True)
+OVERLAY_REF_DTYPE = np.dtype([("leaf_begin", np.int32), ("leaf_end", np.int32)], align=True)
 assert LEAF_DTYPE.itemsize == 48 and OVERLAY_FRAME_DTYPE.itemsize == 48
 
 EXPORTS = [
@@ -109,8 +110,8 @@ def _declare(L: C.CDLL) -> None:
     L.vis_sched_pack_records.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, C.c_int64]
     L.vis_preprocess_fused_sched.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
-    L.vis_overlay_tiles.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
-    L.vis_overlay_draw.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]
+    L.vis_overlay_tiles.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, ip, ip]
+    L.vis_overlay_draw.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
     for name in EXPORTS:
         if name != "vis_last_error":
             getattr(L, name).restype = C.c_int

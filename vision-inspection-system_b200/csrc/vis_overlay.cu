@@ -1,10 +1,10 @@
 // vis_overlay.cu — device half of the defect-overlay rasteriser (cv2 drawing calls of
 // utils/image_utils.py:259-313 in the reference, reproduced pixel for pixel).
 //
-// Only tiles that some leaf can touch are visited: the host lists them (vis_overlay_tiles, from the sub-group boxes),
+// Only tiles that some leaf can touch are visited: the host bins the sub-groups into tiles (vis_overlay_tiles),
 // everything else is a plain vectorised frame copy (out of place) or nothing at all (in place).  A CTA owns one
 // listed 64x16 tile; each warp owns a 32x4 sub-tile (lane = 4 pixels, 12 bytes in registers) and culls on its own
-// with ballots: box header -> sub-group headers (one per 32 consecutive leaves) -> leaves; touching leaves are
+// with ballots over the leaves of the tile's sub-groups (runs of 32 consecutive leaves); touching leaves are
 // staged IN ORDER in shared memory and every lane applies them in list order to its own pixels.  Per-pixel in-order
 // application is what makes the result identical to OpenCV's sequential drawing: fills and LINE_8 points
 // overwrite, LineAA pixels blend (twice, 8-bit alpha) with whatever is there.
@@ -163,12 +163,13 @@ k_overlay_copy(const VisOverlayFrame* __restrict__ frames) {
 }
 
 // In-place drawing of the touched tiles.  CTA = one 64x16 tile of the host-built tile list; each of its 8 warps owns a
-// 32x4 pixel sub-tile (lane = 4 pixels of one row) and works on its own: box header (uniform test) -> sub-group
-// headers of that box, 32 per ballot -> leaves of touching sub-groups, 32 per ballot -> touching leaves staged IN
-// ORDER in the warp's shared-memory slots and applied per pixel in list order.  No block-wide barrier.
+// 32x4 pixel sub-tile (lane = 4 pixels of one row) and works on its own, without block-wide barriers: for every
+// sub-group the host binned into this tile (in leaf order) the 32 lanes test the 32 leaf boxes against the
+// sub-tile, the touching leaves are staged IN ORDER in the warp's shared-memory slots and applied per pixel in list
+// order.
 __global__ void __launch_bounds__(kThreads)
 k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile* __restrict__ tiles,
-                const VisLeaf* __restrict__ leaves) {
+                const VisOverlayRef* __restrict__ refs, const VisLeaf* __restrict__ leaves) {
     __shared__ int s_leaf[kThreads / 32][32][VIS_LEAF_WORDS];
     __shared__ int s_filter[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -186,66 +187,54 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
     const int x = t.x0 + (lane & 7) * kPx, y = t.y0 + (lane >> 3);
     const int nv = y < f.h ? max(0, min(kPx, f.w - x)) : 0;      // valid pixels of this lane
 
-    const VisLeaf* fl = leaves + f.group_begin;       // the frame's leaf array; header indices are relative to it
-    const int n_groups = f.group_end - f.group_begin;
+    const VisLeaf* fl = leaves + f.group_begin;       // the frame's leaf array; leaf indices are relative to it
     int c[kPx][3];
     bool loaded = false, dirty = false;
     uint8_t* const px = f.dst + (size_t)y * f.dst_pitch + (size_t)x * 3;
     const bool vec = ((f.dst_pitch | (int64_t)(uintptr_t)f.dst) & 3) == 0;
     int (*my_leaf)[VIS_LEAF_WORDS] = s_leaf[warp];
 
-    for (int g = 0; g < n_groups; ++g) {
-        const int2 gbb = __ldg(reinterpret_cast<const int2*>(&fl[g].w[10]));
-        if (!touches(t, gbb.x, gbb.y)) continue;
-        const int2 h01 = __ldg(reinterpret_cast<const int2*>(&fl[g].w[2]));       // first leaf, end leaf
-        const int2 h23 = __ldg(reinterpret_cast<const int2*>(&fl[g].w[4]));       // first sub-group header, count
-        const int lb = h01.x, le = h01.y, sb = h23.x, ns = h23.y;
-        for (int s0 = 0; s0 < ns; s0 += 32) {
-            const int si = s0 + lane;
-            bool hit = false;
-            if (si < ns) {
-                const int2 bb = __ldg(reinterpret_cast<const int2*>(&fl[sb + si].w[10]));
-                hit = touches(t, bb.x, bb.y);
+    // the refs of this tile, 32 at a time in registers (lane i holds ref r0 + i), consumed in order
+    for (int r0 = tl.ref_begin; r0 < tl.ref_end; r0 += 32) {
+        const int nr = min(32, tl.ref_end - r0);
+        int2 mine = make_int2(0, 0);
+        if (lane < nr) mine = __ldg(reinterpret_cast<const int2*>(refs + r0 + lane));
+        for (int k = 0; k < nr; ++k) {
+            const int lb = __shfl_sync(0xffffffffu, mine.x, k), le = __shfl_sync(0xffffffffu, mine.y, k);
+            const int li = lb + lane;
+            bool lhit = false;
+            if (li < le) {
+                const int2 bb = __ldg(reinterpret_cast<const int2*>(&fl[li].w[10]));
+                lhit = touches(t, bb.x, bb.y);
             }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1;
-                const int li = lb + (s0 + k) * LEAF_SUB_LEAVES + lane;
-                bool lhit = false;
-                if (li < le) {
-                    const int2 bb = __ldg(reinterpret_cast<const int2*>(&fl[li].w[10]));
-                    lhit = touches(t, bb.x, bb.y);
-                }
-                const unsigned lm = __ballot_sync(0xffffffffu, lhit);
-                if (!lm) continue;
-                if (!loaded) {                                    // first leaf that reaches this sub-tile: fetch the pixels
-                    loaded = true;
-                    if (nv == kPx && vec) {
-                        const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
-                        const uint32_t a = q[0], b = q[1], d = q[2];
-                        c[0][0] = a & 0xff; c[0][1] = (a >> 8) & 0xff; c[0][2] = (a >> 16) & 0xff;
-                        c[1][0] = a >> 24;  c[1][1] = b & 0xff;        c[1][2] = (b >> 8) & 0xff;
-                        c[2][0] = (b >> 16) & 0xff; c[2][1] = b >> 24; c[2][2] = d & 0xff;
-                        c[3][0] = (d >> 8) & 0xff;  c[3][1] = (d >> 16) & 0xff; c[3][2] = d >> 24;
-                    } else {
+            const unsigned lm = __ballot_sync(0xffffffffu, lhit);
+            if (!lm) continue;
+            if (!loaded) {                                    // first leaf that reaches this sub-tile: fetch the pixels
+                loaded = true;
+                if (nv == kPx && vec) {
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
+                    const uint32_t a = q[0], b = q[1], d = q[2];
+                    c[0][0] = a & 0xff; c[0][1] = (a >> 8) & 0xff; c[0][2] = (a >> 16) & 0xff;
+                    c[1][0] = a >> 24;  c[1][1] = b & 0xff;        c[1][2] = (b >> 8) & 0xff;
+                    c[2][0] = (b >> 16) & 0xff; c[2][1] = b >> 24; c[2][2] = d & 0xff;
+                    c[3][0] = (d >> 8) & 0xff;  c[3][1] = (d >> 16) & 0xff; c[3][2] = d >> 24;
+                } else {
 #pragma unroll
-                        for (int j = 0; j < kPx; ++j)
+                    for (int j = 0; j < kPx; ++j)
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) c[j][q] = j < nv ? (int)px[j * 3 + q] : 0;
-                    }
+                        for (int q = 0; q < 3; ++q) c[j][q] = j < nv ? (int)px[j * 3 + q] : 0;
                 }
-                if (lhit) {
-                    const int4* src = reinterpret_cast<const int4*>(&fl[li]);
-                    int4* dst = reinterpret_cast<int4*>(my_leaf[__popc(lm & ((1u << lane) - 1))]);
-                    dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
-                }
-                __syncwarp();
-                const int n_leaf = __popc(lm);
-                if (nv > 0)
-                    for (int q = 0; q < n_leaf; ++q) dirty |= apply_leaf(my_leaf[q], s_filter, x, y, c);
-                __syncwarp();
             }
+            if (lhit) {
+                const int4* src = reinterpret_cast<const int4*>(&fl[li]);
+                int4* dst = reinterpret_cast<int4*>(my_leaf[__popc(lm & ((1u << lane) - 1))]);
+                dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
+            }
+            __syncwarp();
+            const int n_leaf = __popc(lm);
+            if (nv > 0)
+                for (int q = 0; q < n_leaf; ++q) dirty |= apply_leaf(my_leaf[q], s_filter, x, y, c);
+            __syncwarp();
         }
     }
 
@@ -265,8 +254,9 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
 }  // namespace
 
 extern "C" int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int copy_frames,
-                                const VisOverlayTile* tiles, int n_tiles, const VisLeaf* leaves, void* stream) {
-    if (!frames || n_frames <= 0 || n_frames > 65535 || n_tiles < 0 || (n_tiles && (!tiles || !leaves))) {
+                                const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
+                                const VisLeaf* leaves, void* stream) {
+    if (!frames || n_frames <= 0 || n_frames > 65535 || n_tiles < 0 || (n_tiles && (!tiles || !refs || !leaves))) {
         vis::set_error("vis_overlay_draw: bad arguments (frames=%d tiles=%d)", n_frames, n_tiles);
         return VIS_E_INVALID;
     }
@@ -277,7 +267,7 @@ extern "C" int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int
         if (rc != VIS_OK) return rc;
     }
     if (n_tiles > 0) {
-        k_overlay_tiles<<<n_tiles, kThreads, 0, st>>>(frames, tiles, leaves);
+        k_overlay_tiles<<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
         return vis::check_launch("vis_overlay_draw");
     }
     return VIS_OK;

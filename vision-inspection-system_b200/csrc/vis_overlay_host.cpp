@@ -618,40 +618,57 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
     return em.count();
 }
 
-// Tiles (64x16 pixels, the CTA tile of vis_overlay.cu) that some leaf of the frame can touch, from the sub-group
-// boxes; row-major order, tiles_out[i] = tx | ty << 16.
+// Bins the frame's sub-groups (runs of <= 32 consecutive leaves with a common box) into the 64x16-pixel CTA tiles of
+// vis_overlay.cu.  tiles_out: one record per touched tile, row-major: {tx | ty << 16, first ref, one past last ref};
+// refs_out: per tile, IN LEAF ORDER, {first leaf, one past last leaf} of every sub-group whose box touches the tile.
 extern "C" int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, int n_boxes,
-                                 int32_t* tiles_out, int capacity, int* needed) {
+                                 int32_t* tiles_out, int tile_capacity, int32_t* refs_out, int ref_capacity,
+                                 int* tiles_needed, int* refs_needed) {
     if (img_h <= 0 || img_w <= 0 || img_h > 32767 || img_w > 32767 || n_boxes < 0 || (n_boxes && !leaves) ||
-        capacity < 0 || (capacity && !tiles_out)) {
+        tile_capacity < 0 || ref_capacity < 0 || (tile_capacity && !tiles_out) || (ref_capacity && !refs_out)) {
         vis::set_error("vis_overlay_tiles: bad arguments (h=%d w=%d boxes=%d)", img_h, img_w, n_boxes);
         return VIS_E_INVALID;
     }
     constexpr int kTileW = 64, kTileH = 16;
     const int tw = (img_w + kTileW - 1) / kTileW, th = (img_h + kTileH - 1) / kTileH;
-    std::vector<uint8_t> mark((size_t)tw * th, 0);
-    for (int g = 0; g < n_boxes; ++g) {
-        const VisLeaf& h = leaves[g];
-        for (int s = h.w[4]; s < h.w[4] + h.w[5]; ++s) {
-            const VisLeaf& sub = leaves[s];
-            const int x0 = sub.w[10] & 0xffff, x1 = (int)((uint32_t)sub.w[10] >> 16);
-            const int y0 = sub.w[11] & 0xffff, y1 = (int)((uint32_t)sub.w[11] >> 16);
-            if (x0 > x1 || y0 > y1) continue;
-            for (int ty = y0 / kTileH; ty <= std::min(y1 / kTileH, th - 1); ++ty)
-                for (int tx = x0 / kTileW; tx <= std::min(x1 / kTileW, tw - 1); ++tx) mark[(size_t)ty * tw + tx] = 1;
-        }
-    }
-    int n = 0;
-    for (int ty = 0; ty < th; ++ty)
-        for (int tx = 0; tx < tw; ++tx)
-            if (mark[(size_t)ty * tw + tx]) {
-                if (n < capacity) tiles_out[n] = tx | (ty << 16);
-                ++n;
+    std::vector<int> count((size_t)tw * th, 0);
+    auto each = [&](auto&& fn) {
+        for (int g = 0; g < n_boxes; ++g) {
+            const VisLeaf& h = leaves[g];
+            for (int s = h.w[4]; s < h.w[4] + h.w[5]; ++s) {
+                const VisLeaf& sub = leaves[s];
+                const int x0 = sub.w[10] & 0xffff, x1 = (int)((uint32_t)sub.w[10] >> 16);
+                const int y0 = sub.w[11] & 0xffff, y1 = (int)((uint32_t)sub.w[11] >> 16);
+                if (x0 > x1 || y0 > y1) continue;
+                for (int ty = y0 / kTileH; ty <= std::min(y1 / kTileH, th - 1); ++ty)
+                    for (int tx = x0 / kTileW; tx <= std::min(x1 / kTileW, tw - 1); ++tx) fn(ty * tw + tx, sub);
             }
-    if (needed) *needed = n;
-    if (n > capacity) {
-        vis::set_error("vis_overlay_tiles: %d tiles, capacity %d", n, capacity);
+        }
+    };
+    each([&](int t, const VisLeaf&) { ++count[t]; });
+    std::vector<int> at((size_t)tw * th, 0);
+    int n_tiles = 0, n_refs = 0;
+    for (int t = 0; t < tw * th; ++t) {
+        at[t] = n_refs;
+        if (!count[t]) continue;
+        if (n_tiles < tile_capacity) {
+            tiles_out[3 * n_tiles] = (t % tw) | ((t / tw) << 16);
+            tiles_out[3 * n_tiles + 1] = n_refs;
+            tiles_out[3 * n_tiles + 2] = n_refs + count[t];
+        }
+        ++n_tiles;
+        n_refs += count[t];
+    }
+    if (tiles_needed) *tiles_needed = n_tiles;
+    if (refs_needed) *refs_needed = n_refs;
+    if (n_tiles > tile_capacity || n_refs > ref_capacity) {
+        vis::set_error("vis_overlay_tiles: %d tiles / %d refs, capacity %d / %d", n_tiles, n_refs, tile_capacity, ref_capacity);
         return VIS_E_CAPACITY;
     }
-    return n;
+    each([&](int t, const VisLeaf& sub) {
+        refs_out[2 * at[t]] = sub.w[2];
+        refs_out[2 * at[t] + 1] = sub.w[3];
+        ++at[t];
+    });
+    return n_tiles;
 }

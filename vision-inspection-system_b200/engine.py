@@ -387,31 +387,33 @@ class Engine:
         """Host half of the overlay for a batch: box validation (reference rules) + expansion into leaves.
 
         ``shapes``: list of (H, W) per frame.  Returns (leaves uint8 device tensor, per-frame (begin, end) header
-        ranges, number of boxes drawn, device tile list, tile count).
+        ranges, number of boxes drawn, device tile list, tile count, device ref list).
         """
         from . import overlay as O
-        parts, ranges, tiles, at, drawn = [], [], [], 0, 0
+        parts, ranges, tiles, refs, at, ref_at, drawn = [], [], [], [], 0, 0, 0
         for i, ((h, w), boxes) in enumerate(zip(shapes, boxes_per_frame)):
             px = O.boxes_to_pixels(boxes, w, h, confidence_threshold, criticality)
             leaves = O.expand_leaves(px, w, h)
             ranges.append((at, at + len(px)))          # the frame's array starts at `at`; headers come first
             parts.append(leaves)
-            t = np.zeros(0, N.OVERLAY_TILE_DTYPE)
-            txy = O.touched_tiles(leaves, len(px), w, h)
-            if len(txy):
-                t = np.zeros(len(txy), N.OVERLAY_TILE_DTYPE)
-                t["frame"], t["txy"] = i, txy
-            tiles.append(t)
+            t3, r2 = O.touched_tiles(leaves, len(px), w, h)
+            if len(t3):
+                t = np.zeros(len(t3), N.OVERLAY_TILE_DTYPE)
+                t["frame"], t["txy"] = i, t3[:, 0]
+                t["ref_begin"], t["ref_end"] = t3[:, 1] + ref_at, t3[:, 2] + ref_at
+                tiles.append(t)
+                refs.append(r2)
+                ref_at += len(r2)
             at += len(leaves)
             drawn += len(px)
         all_leaves = np.concatenate(parts) if parts else np.zeros(0, N.LEAF_DTYPE)
         if len(all_leaves) == 0:
             all_leaves = np.zeros(1, N.LEAF_DTYPE)
-        all_tiles = np.concatenate(tiles) if tiles else np.zeros(0, N.OVERLAY_TILE_DTYPE)
-        d_leaves = torch.from_numpy(all_leaves.view(np.uint8).copy()).to(self.device)
-        d_tiles = torch.from_numpy(np.ascontiguousarray(all_tiles).view(np.uint8).copy()).to(self.device) \
-            if len(all_tiles) else torch.zeros(8, dtype=torch.uint8, device=self.device)
-        return d_leaves, ranges, drawn, d_tiles, len(all_tiles)
+        n_tiles = sum(len(t) for t in tiles)
+        all_tiles = np.concatenate(tiles) if tiles else np.zeros(1, N.OVERLAY_TILE_DTYPE)
+        all_refs = np.concatenate(refs) if refs else np.zeros((1, 2), np.int32)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
+        return up(all_leaves), ranges, drawn, up(all_tiles), n_tiles, up(all_refs)
 
     def annotate(self, frames, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium",
                  inplace: bool = False, plan=None):
@@ -431,7 +433,7 @@ class Engine:
         shapes = [(int(f.shape[0]), int(f.shape[1])) for f in flist]
         if plan is None:
             plan = self.plan_overlay(shapes, boxes_per_frame, confidence_threshold, criticality)
-        d_leaves, ranges, _, d_tiles, n_tiles = plan
+        d_leaves, ranges, _, d_tiles, n_tiles, d_refs = plan
         if inplace:
             outs = flist
             result = frames
@@ -455,9 +457,9 @@ class Engine:
         if len(flist) > 65535:
             raise ValueError("at most 65535 frames per annotate call")
         N.check(self.L.vis_overlay_draw(d_desc.data_ptr(), len(flist), 0 if inplace else 1, d_tiles.data_ptr(), n_tiles,
-                                        d_leaves.data_ptr(), sp), "vis_overlay_draw")
+                                        d_refs.data_ptr(), d_leaves.data_ptr(), sp), "vis_overlay_draw")
         self.last_launches = (0 if inplace else 1) + (1 if n_tiles else 0)
-        self._keepalive = (d_desc, d_leaves, d_tiles)
+        self._keepalive = (d_desc, d_leaves, d_tiles, d_refs)
         return result
 
     # ------------------------------------------------------------------ helpers

@@ -100,13 +100,24 @@ def expand_leaves(pixel_boxes: np.ndarray, img_width: int, img_height: int) -> n
         return leaves[:rc]
 
 
-def touched_tiles(leaves: np.ndarray, n_boxes: int, img_width: int, img_height: int) -> np.ndarray:
-    """64x16 tiles of one frame that some leaf can touch (``tx | ty << 16``, row-major) via ``vis_overlay_tiles``."""
+def touched_tiles(leaves: np.ndarray, n_boxes: int, img_width: int, img_height: int):
+    """Bins one frame's sub-groups into the 64x16 tiles of the draw kernel via ``vis_overlay_tiles``.
+
+    Returns (tiles int32 [n, 3] = (tx | ty << 16, first ref, one past last ref), refs int32 [m, 2] = leaf ranges)."""
     if n_boxes == 0 or len(leaves) == 0:
-        return np.zeros(0, np.int32)
+        return np.zeros((0, 3), np.int32), np.zeros((0, 2), np.int32)
     L = N.lib()
-    cap = ((img_width + 63) // 64) * ((img_height + 15) // 16)
-    tiles = np.zeros(cap, np.int32)
-    n = N.check(L.vis_overlay_tiles(img_height, img_width, leaves.ctypes.data_as(C.c_void_p), n_boxes,
-                                    tiles.ctypes.data_as(C.c_void_p), cap, None), "vis_overlay_tiles")
-    return tiles[:n]
+    tcap = ((img_width + 63) // 64) * ((img_height + 15) // 16)
+    rcap = 4 * tcap
+    while True:
+        tiles = np.zeros((tcap, 3), np.int32)
+        refs = np.zeros((rcap, 2), np.int32)
+        nt, nr = C.c_int(0), C.c_int(0)
+        rc = L.vis_overlay_tiles(img_height, img_width, leaves.ctypes.data_as(C.c_void_p), n_boxes,
+                                 tiles.ctypes.data_as(C.c_void_p), tcap, refs.ctypes.data_as(C.c_void_p), rcap,
+                                 C.byref(nt), C.byref(nr))
+        if rc == N.VIS_E_CAPACITY:
+            tcap, rcap = max(tcap, nt.value), max(rcap, nr.value)
+            continue
+        N.check(rc, "vis_overlay_tiles")
+        return tiles[:nt.value], refs[:nr.value]
