@@ -127,7 +127,8 @@ int vis_preprocess_fused(const VisFrame* frames, int n_frames, const VisStrip* s
 
 /* ------------------------------------------------------------------------------------------
  * Statically scheduled fused kernel: same computation as vis_preprocess_fused for ONE geometry per
- * launch whose scale is >= 1 on both axes (at most one output sample ends at any input index).
+ * launch whose scale is > 0.5 on both axes (at most two output samples end at any input index; one when
+ * nothing is upscaled).
  * The host precomputes, from the bounds tables, which input column of every 8-pixel step / which input
  * row of every 8-row group completes an output sample; the schedule travels as a kernel parameter
  * (constant bank), so every branch of the resampling loops is warp-uniform and no window bookkeeping
@@ -147,7 +148,8 @@ typedef struct VisSched {            /* opaque to callers: filled by vis_sched_b
     int64_t src_pitch;
     int32_t kt;                      /* tap class (6 or 8)                                         */
     int32_t n_strips, n_segs;
-    int32_t stage_pitch, max_strip_w, reserved;
+    int32_t stage_pitch, max_strip_w;
+    int32_t per_index;               /* 1: scale >= 1 on both axes; 2: mild upscale, two mask bytes are live per step */
     VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
     VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_SUBS];
     VisSchedSeg   seg[VIS_SCHED_MAX_SEGS];
@@ -166,8 +168,9 @@ int vis_sched_sizeof(void);
 int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitch,
                     const int32_t* hbounds, const int32_t* vbounds, int vsplit, VisSched* out);
 /* records for the scheduled kernel: like vis_pack_records, but samples whose window the far border clamps are
- * moved to the virtual end index the schedule gives them (leading zero coefficients).  kt = sched kt.  [host] */
-int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt,
+ * moved to the virtual end index the schedule gives them (leading zero coefficients).  kt, per_index: the
+ * schedule's.                                                                             [host] */
+int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt, int per_index,
                            int32_t* rec, int64_t rec_capacity);
 /* frames: DEVICE array; hrec / vrec: DEVICE records from vis_sched_pack_records.        [device] */
 int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,

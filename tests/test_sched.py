@@ -18,17 +18,18 @@ SCHED = np.dtype([("head", N.SCHED_HEAD_DTYPE), ("strip", STRIP, (16,)), ("sub",
                   ("mask", np.uint8, (6144,))], align=True)
 
 
-def sched_ends_and_records(table, kt):
+def sched_ends_and_records(table, kt, per_index=1):
     """vis_sched_pack_records, checked: window ends strictly increase, stay within kt slots of the first tap, differ
     from Pillow's only where the far border clamps, and the shifted coefficients are Pillow's."""
     L = N.lib()
     stride = L.vis_record_stride(kt)
     rec = np.zeros((table.out_size + 1, stride), np.int32)
     assert L.vis_sched_pack_records(table.out_size, N.i32ptr(table.k), N.i32ptr(table.bounds), table.ksize, kt,
-                                    N.i32ptr(rec), rec.size) == N.VIS_OK
+                                    per_index, N.i32ptr(rec), rec.size) == N.VIS_OK
     first, taps = table.bounds[:, 0], table.bounds[:, 1]
     ends = rec[:-1, stride - 1]
-    assert (np.diff(ends) > 0).all() and (ends - first + 1 <= kt).all() and (rec[:-1, stride - 2] == first).all()
+    assert (np.diff(ends) >= 0).all() and (ends - first + 1 <= kt).all() and (rec[:-1, stride - 2] == first).all()
+    assert np.unique(ends, return_counts=True)[1].max() <= per_index
     true_last = first + taps - 1
     moved = ends != true_last
     assert (true_last[moved] == table.in_size - 1).all() and (ends >= true_last).all()
@@ -51,11 +52,12 @@ def build(src_h, src_w, dst_h, dst_w, pitch, vsplit):
     return rc, buf[0], ht, vt
 
 
-@pytest.mark.parametrize("shape,vsplit,max_pixels", [
-    ((1080, 1920), 1, G.DEFAULT_MAX_PIXELS), ((1080, 1920), 3, G.DEFAULT_MAX_PIXELS), ((2160, 3840), 2, G.HUB_MAX_PIXELS),
-    ((1536, 2048), 8, G.DEFAULT_MAX_PIXELS), ((1152, 2048), 1, G.DEFAULT_MAX_PIXELS), ((2048, 1536), 4, G.DEFAULT_MAX_PIXELS),
-    ((600, 5000), 2, G.DEFAULT_MAX_PIXELS)])
-def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels):
+@pytest.mark.parametrize("shape,vsplit,max_pixels,want_per", [
+    ((1080, 1920), 1, G.DEFAULT_MAX_PIXELS, 1), ((1080, 1920), 3, G.DEFAULT_MAX_PIXELS, 1), ((2160, 3840), 2, G.HUB_MAX_PIXELS, 1),
+    ((1536, 2048), 8, G.DEFAULT_MAX_PIXELS, 1), ((1152, 2048), 1, G.DEFAULT_MAX_PIXELS, 1), ((2048, 1536), 4, G.DEFAULT_MAX_PIXELS, 1),
+    ((600, 5000), 2, G.DEFAULT_MAX_PIXELS, 1), ((1080, 1920), 2, G.HUB_MAX_PIXELS, 2), ((720, 1280), 1, G.DEFAULT_MAX_PIXELS, 2),
+    ((480, 640), 3, G.DEFAULT_MAX_PIXELS, 2), ((560, 1000), 1, G.DEFAULT_MAX_PIXELS, 2)])
+def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels, want_per):
     h, w = shape
     dh, dw = G.smart_resize(h, w, G.FACTOR, G.DEFAULT_MIN_PIXELS, max_pixels)
     pitch = (w * 3 + 15) // 16 * 16
@@ -63,8 +65,10 @@ def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels):
     assert rc == N.VIS_OK, N.lib().vis_last_error()
     hd = s["head"]
     assert (hd["dst_h"], hd["dst_w"], hd["kt"]) == (dh, dw, T.kt_class(max(ht.max_taps, vt.max_taps)))
-    hlast, hrec = sched_ends_and_records(ht, int(hd["kt"]))
-    vlast, vrec = sched_ends_and_records(vt, int(hd["kt"]))
+    per = int(hd["per_index"])
+    assert per == want_per
+    hlast, hrec = sched_ends_and_records(ht, int(hd["kt"]), per)
+    vlast, vrec = sched_ends_and_records(vt, int(hd["kt"]), per)
     # horizontal: every output column of every strip is emitted exactly once, at the pixel where its window ends,
     # after all of its taps have been read (p0 <= first tap), and the staged row segment covers the window
     covered = np.zeros(dw, np.int32)
@@ -77,13 +81,15 @@ def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels):
             xo = int(U["xa"])
             assert U["p0"] % 8 == 0 and U["p0"] >= S["px0"] and U["p0"] <= ht.bounds[xo, 0]
             for i in range(U["nsteps"]):
-                m = int(s["mask"][U["mask_off"] + i])
+                m1, m2 = int(s["mask"][U["mask_off"] + 2 * i]), int(s["mask"][U["mask_off"] + 2 * i + 1])
+                assert m2 & ~m1 == 0 and (per == 2 or m2 == 0)
                 for jj in range(8):
-                    if m >> jj & 1:
-                        assert hlast[xo] == U["p0"] + 8 * i + jj
-                        assert (min(hlast[xo], w - 1) + 1) * 3 <= S["px0"] * 3 + S["row_bytes"]
-                        covered[xo] += 1
-                        xo += 1
+                    for m in (m1, m2):
+                        if m >> jj & 1:
+                            assert hlast[xo] == U["p0"] + 8 * i + jj
+                            assert (min(hlast[xo], w - 1) + 1) * 3 <= S["px0"] * 3 + S["row_bytes"]
+                            covered[xo] += 1
+                            xo += 1
             assert xo == U["xb"]
     assert (covered == 1).all()
     # vertical: every output row once per segment cover, at the input row where its window ends
@@ -91,25 +97,27 @@ def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels):
     for sg in range(hd["n_segs"]):
         Gs = s["seg"][sg]
         yo = int(Gs["y0"])
-        assert Gs["y0"] % 14 == 0 and Gs["y1"] % 14 == 0 and Gs["r_first"] % 16 == 0 and Gs["mask_off"] % 4 == 0
+        assert Gs["y0"] % 14 == 0 and Gs["y1"] % 14 == 0 and Gs["r_first"] % 16 == 0 and Gs["mask_off"] % 8 == 0
         assert Gs["r_first"] <= vt.bounds[yo, 0]
         n_chunks = -(-(Gs["r_end"] - Gs["r_first"]) // 32)
         for c in range(n_chunks):
             emitted_here = 0
             for g in range(4):
-                m = int(s["mask"][Gs["mask_off"] + c * 4 + g])
+                m1, m2 = int(s["mask"][Gs["mask_off"] + 2 * (c * 4 + g)]), int(s["mask"][Gs["mask_off"] + 2 * (c * 4 + g) + 1])
+                assert m2 & ~m1 == 0 and (per == 2 or m2 == 0)
                 for u in range(8):
-                    if m >> u & 1:
-                        assert vlast[yo] == Gs["r_first"] + c * 32 + g * 8 + u
-                        rows[yo] += 1
-                        yo += 1
-                        emitted_here += 1
-            assert emitted_here <= 32
+                    for m in (m1, m2):
+                        if m >> u & 1:
+                            assert vlast[yo] == Gs["r_first"] + c * 32 + g * 8 + u
+                            rows[yo] += 1
+                            yo += 1
+                            emitted_here += 1
+            assert emitted_here <= 32 * per
         assert yo == Gs["y1"]
     assert (rows == 1).all()
 
 
-@pytest.mark.parametrize("shape,max_pixels,why", [((1080, 1920), G.HUB_MAX_PIXELS, b"upscale"), ((2160, 3840), G.DEFAULT_MAX_PIXELS, b"taps"),
+@pytest.mark.parametrize("shape,max_pixels,why", [((20, 30), G.DEFAULT_MAX_PIXELS, b"upscale"), ((2160, 3840), G.DEFAULT_MAX_PIXELS, b"taps"),
                                                   ((100, 502), G.DEFAULT_MAX_PIXELS, b"pitch")])
 def test_schedule_declines_what_it_cannot_express(shape, max_pixels, why):
     h, w = shape

@@ -43,7 +43,7 @@ OVERLAY_FRAME_DTYPE = np.dtype([
 FRAME_REF_DTYPE = np.dtype([("src", np.uint64), ("row0", np.int64)], align=True)
 SCHED_HEAD_DTYPE = np.dtype([("src_h", np.int32), ("src_w", np.int32), ("dst_h", np.int32), ("dst_w", np.int32),
                              ("src_pitch", np.int64), ("kt", np.int32), ("n_strips", np.int32), ("n_segs", np.int32),
-                             ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("reserved", np.int32)], align=True)
+                             ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("per_index", np.int32)], align=True)
 
 assert FRAME_DTYPE.itemsize == 56 and STRIP_DTYPE.itemsize == 20 and BOX_DTYPE.itemsize == 32
 OVERLAY_TILE_DTYPE = np.dtype([("frame", np.int32), ("txy", np.int32), ("ref_begin", np.int32), ("ref_end", np.int32)], align=True)
@@ -107,7 +107,7 @@ def _declare(L: C.CDLL) -> None:
     L.vis_preprocess_fused.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.vis_sched_sizeof.argtypes = []
     L.vis_sched_build.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, i32p, i32p, C.c_int, vp]
-    L.vis_sched_pack_records.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, C.c_int64]
+    L.vis_sched_pack_records.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]
     L.vis_preprocess_fused_sched.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
     L.vis_overlay_tiles.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, ip, ip]

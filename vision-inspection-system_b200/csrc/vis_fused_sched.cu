@@ -37,7 +37,7 @@ constexpr int kPitch = kMaxStripW + 4;            // 340 = 4 * 85: conflict-free
 constexpr int kOPitch = kMaxStripW;
 constexpr int kOPlane = VIS_PATCH * kOPitch;
 constexpr int kHPlane = kChunk * kPitch;
-constexpr int kVRecs = kChunk + 1;                // vertical records a chunk can touch (scale >= 1): 32 emits + 1 look-ahead
+constexpr int kVRecsMax = 2 * kChunk + 1;         // vertical records a chunk can touch: <= 2 emits per input row + 1 look-ahead
 constexpr int kSmemMax = 227 * 1024;
 
 enum Bar { SF = 0, SE = 2, HF = 4, HE = 6, VF = 8, OF = 10, OE = 12, kBars = 14 };   // full/empty pairs, two slots each
@@ -52,7 +52,7 @@ inline LayoutS make_layout_s(int stage_pitch, int strip_w, int stride) {
     L.stage_pitch = stage_pitch;
     L.stage_slot = kChunk * stage_pitch;
     L.hrec_slot = align_up((strip_w + 1) * stride * 4, 16);
-    L.vrec_slot = align_up(kVRecs * stride * 4, 16);
+    L.vrec_slot = align_up(kVRecsMax * stride * 4, 16);
     int off = 0;
     L.off_stage = off; off += 2 * L.stage_slot;
     L.off_hring = off; off += 2 * 3 * kHPlane;
@@ -90,7 +90,8 @@ __device__ __noinline__ void band_done(uint32_t bar0, int nb, int lane) {
     if (nx >= 2) mbar_wait(bar0 + (uint32_t)(OE + (nx & 1)) * 8, ((nx >> 1) - 1) & 1);
 }
 
-template <int KT, int STRIDE>
+// UP: up to two output samples may end at one input index (mild upscaling, scale > 0.5): a second mask byte per step
+template <int KT, int STRIDE, bool UP>
 __global__ void __launch_bounds__(kThreadsS, 1)
 k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict__ frames, int n_items,
               const __grid_constant__ LayoutS L, const int* __restrict__ hrec_g, const int* __restrict__ vrec_g,
@@ -151,14 +152,14 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
                 // vertical records this chunk consumes: [yo, yo + 33) (the table ends with a sentinel at dst_h)
                 if (k >= 2) mbar_wait(bar(HE, slot), prev);                 // V is done with the record slot
                 if (lane == 0) {
-                    const uint32_t vbytes = (uint32_t)min(kVRecs, sc.dst_h + 1 - yo) * STRIDE * 4;
+                    const uint32_t vbytes = (uint32_t)min(UP ? kVRecsMax : kChunk + 1, sc.dst_h + 1 - yo) * STRIDE * 4;
                     fence_proxy_async();
                     mbar_expect_tx(bar(VF, slot), vbytes);
                     bulk_g2s(smem_u32(smem + L.off_vrec + slot * L.vrec_slot), vrec_g + (size_t)yo * STRIDE, vbytes,
                              bar(VF, slot));
                 }
-                const uint32_t m4 = *reinterpret_cast<const uint32_t*>(sc.mask + G.mask_off + c * 4);
-                yo += __popc(m4);
+                const uint32_t* m8 = reinterpret_cast<const uint32_t*>(sc.mask + G.mask_off + c * 8);   // 4 groups x (m1, m2)
+                yo += __popc(m8[0]) + __popc(m8[1]);
             }
         }
     } else if (warp < kHBase + kHWarps) {
@@ -188,7 +189,7 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
                 load_coeffs<KT, STRIDE>(kf, hp);
 #pragma unroll 1
                 for (int i = 0; i < U.nsteps; ++i) {
-                    const uint32_t m = um[i];
+                    const uint32_t m = um[2 * i], m2 = UP ? um[2 * i + 1] : 0u;
                     uint32_t wv[6];
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
@@ -203,7 +204,7 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
                             const int b = 3 * jj + ch;
                             rg[ch][jj] = (int)__byte_perm(wv[b >> 2], 0, 0x4440 + (b & 3));
                         }
-                        if (m & (1u << jj)) {
+                        auto emit = [&]() {
                             int a0 = 1 << (VIS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
 #pragma unroll
                             for (int tt = 0; tt < KT; ++tt) {
@@ -218,7 +219,9 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
                             ++hdst;
                             hp += STRIDE * 4;
                             load_coeffs<KT, STRIDE>(kf, hp);          // the slot holds sw + 1 records: always readable
-                        }
+                        };
+                        if (m & (1u << jj)) emit();
+                        if (UP && (m2 & (1u << jj))) emit();
                     }
                 }
                 __syncwarp();
@@ -260,7 +263,7 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
                 const int groups = min(kChunk / kRing, (G.r_end - (G.r_first + c * kChunk) + kRing - 1) / kRing);
 #pragma unroll 1
                 for (int g = 0; g < groups; ++g) {
-                    const uint32_t m = gm[c * (kChunk / kRing) + g];
+                    const uint32_t m = gm[2 * (c * (kChunk / kRing) + g)], m2 = UP ? gm[2 * (c * (kChunk / kRing) + g) + 1] : 0u;
                     uint32_t words[kRing];
 #pragma unroll
                     for (int u = 0; u < kRing; ++u) words[u] = lds32(hsrc + (uint32_t)((g * kRing + u) * kPitch));
@@ -268,7 +271,7 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
                     for (int u = 0; u < kRing; ++u) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) ring[u][e] = (int)__byte_perm(words[u], 0, 0x4440 + e);
-                        if (m & (1u << u)) {
+                        auto emit = [&]() {
                             int acc[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) acc[e] = 1 << (VIS_PRECISION_BITS - 1);
@@ -290,7 +293,9 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
                             }
                             vaddr += STRIDE * 4;
                             load_coeffs<KT, STRIDE>(kf, vaddr);
-                        }
+                        };
+                        if (m & (1u << u)) emit();
+                        if (UP && (m2 & (1u << u))) emit();
                     }
                 }
                 __syncwarp();
@@ -350,10 +355,10 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
     }
 }
 
-template <int KT, int STRIDE>
+template <int KT, int STRIDE, bool UP>
 int launch_sched(const VisSched& sc, const VisFrameRef* frames, int n_frames, const LayoutS& L, const int* hrec,
                  const int* vrec, const float* lut768, float* pixel_values, cudaStream_t st) {
-    auto kern = k_fused_sched<KT, STRIDE>;
+    auto kern = k_fused_sched<KT, STRIDE, UP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return vis::cuda_fail(e, "vis_preprocess_fused_sched: cudaFuncSetAttribute");
     int dev = 0, sms = 148;
@@ -364,18 +369,28 @@ int launch_sched(const VisSched& sc, const VisFrameRef* frames, int n_frames, co
     return vis::check_launch("vis_preprocess_fused_sched");
 }
 
-// Window ends as the schedule uses them.  With scale >= 1 the true ends (first + taps - 1) strictly increase, except
-// at the far border where Pillow clamps the window to the image and the last few samples all end at the last input
-// index.  Those are moved to virtual indices past the border (one apart); their records are packed with as many
-// leading zero coefficients, so the virtual samples (whatever the staging buffer holds there) get weight 0.
-// Returns false when some sample would need more than kt slots (upscaling): not expressible as a one-bit schedule.
-inline bool schedule_ends(const int32_t* b, int n, int kt, std::vector<int>& ends) {
+// Window ends as the schedule uses them: non-decreasing, at most `per_index` samples ending at one input index.
+// With scale >= 1 the true ends (first + taps - 1) strictly increase (per_index = 1), except at the far border where
+// Pillow clamps the window to the image and the last few samples all end at the last input index; with a mild
+// upscale (scale > 0.5) two samples may share an end (per_index = 2).  Samples beyond the capacity of their index are
+// moved to the next (possibly virtual, past the border) index; their records are packed with as many leading zero
+// coefficients, so the extra samples (whatever the staging buffer holds there) get weight 0.
+// Returns false when some sample would need more than kt slots: not expressible as a schedule of this width.
+inline bool schedule_ends(const int32_t* b, int n, int kt, int per_index, std::vector<int>& ends) {
     ends.resize(n);
+    int used = 0;
     for (int i = 0; i < n; ++i) {
         int e = b[2 * i] + b[2 * i + 1] - 1;
         if (i > 0) {
             if (b[2 * i] < b[2 * i - 2]) return false;
-            if (e <= ends[i - 1]) e = ends[i - 1] + 1;
+            if (e < ends[i - 1]) e = ends[i - 1];
+            if (e == ends[i - 1]) {
+                if (used >= per_index) { e += 1; used = 1; } else ++used;
+            } else {
+                used = 1;
+            }
+        } else {
+            used = 1;
         }
         if (e - b[2 * i] + 1 > kt) return false;
         ends[i] = e;
@@ -411,12 +426,17 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const int cls = mk <= 6 ? 6 : mk <= 8 ? 8 : 0;
     if (!cls) return unsupported("more than 8 taps");
     std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
-    if (!schedule_ends(hb, dst_w, cls, hl)) return unsupported("horizontal upscale");
-    if (!schedule_ends(vb, dst_h, cls, vl)) return unsupported("vertical upscale");
+    int per_index = 1;
+    if (!schedule_ends(hb, dst_w, cls, 1, hl) || !schedule_ends(vb, dst_h, cls, 1, vl)) {
+        per_index = 2;                            // mild upscale on some axis: two samples per input index
+        if (!schedule_ends(hb, dst_w, cls, 2, hl)) return unsupported("horizontal upscale beyond two samples per input column");
+        if (!schedule_ends(vb, dst_h, cls, 2, vl)) return unsupported("vertical upscale beyond two samples per input row");
+    }
 
     VisSched& s = *out;
     std::memset(&s, 0, sizeof(s));
     s.src_h = src_h; s.src_w = src_w; s.dst_h = dst_h; s.dst_w = dst_w; s.src_pitch = src_pitch; s.kt = cls;
+    s.per_index = per_index;
     const int stride = vis_record_stride(cls);
     auto last = [](const int32_t* b, int i) { return b[2 * i] + b[2 * i + 1] - 1; };
     auto span_of = [&](int x0, int x1, int* px0) {
@@ -462,13 +482,15 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
             if (xa >= xb) continue;                                    // nsteps = 0
             const int p0 = hb[2 * xa] & ~(kStepPx - 1);
             const int nsteps = (hl[xb - 1] - p0) / kStepPx + 1;
-            if (!mask_room(nsteps) || nsteps > 65535) return unsupported("schedule too large");
+            if (!mask_room(2 * nsteps) || nsteps > 65535) return unsupported("schedule too large");
             U.p0 = (uint16_t)p0; U.nsteps = (uint16_t)nsteps; U.mask_off = (uint16_t)mask_at;
-            for (int x = xa; x < xb; ++x) {
+            for (int x = xa; x < xb; ++x) {                            // per step: first-sample mask, second-sample mask
                 const int rel = hl[x] - p0;
-                s.mask[mask_at + rel / kStepPx] |= (uint8_t)(1u << (rel % kStepPx));
+                uint8_t* m = s.mask + mask_at + 2 * (rel / kStepPx);
+                const uint8_t bit = (uint8_t)(1u << (rel % kStepPx));
+                if (m[0] & bit) m[1] |= bit; else m[0] |= bit;
             }
-            mask_at += nsteps;
+            mask_at += 2 * nsteps;
         }
     }
     // row segments: multiples of 14 output rows; chunk bases are multiples of 16 input rows
@@ -476,7 +498,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     if (vsplit > prow) vsplit = prow;
     if (vsplit > VIS_SCHED_MAX_SEGS) vsplit = VIS_SCHED_MAX_SEGS;
     s.n_segs = vsplit;
-    mask_at = align_up(mask_at, 4);
+    mask_at = align_up(mask_at, 8);
     for (int g = 0; g < vsplit; ++g) {
         VisSchedSeg& G = s.seg[g];
         G.y0 = (int)((int64_t)prow * g / vsplit) * 14;
@@ -484,21 +506,23 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
         G.r_first = vb[2 * G.y0] & ~15;
         G.r_end = vl[G.y1 - 1] + 1;                                  // may exceed src_h by the virtual rows
         const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
-        const int bytes = n_chunks * (kChunk / kRing);
+        const int bytes = 2 * n_chunks * (kChunk / kRing);
         if (!mask_room(bytes)) return unsupported("schedule too large");
         G.mask_off = mask_at;
         for (int y = G.y0; y < G.y1; ++y) {
             const int rel = vl[y] - G.r_first;
-            s.mask[mask_at + rel / kRing] |= (uint8_t)(1u << (rel % kRing));
+            uint8_t* m = s.mask + mask_at + 2 * (rel / kRing);
+            const uint8_t bit = (uint8_t)(1u << (rel % kRing));
+            if (m[0] & bit) m[1] |= bit; else m[0] |= bit;
         }
         mask_at += bytes;
     }
     return VIS_OK;
 }
 
-int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt,
+int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt, int per_index,
                            int32_t* rec, int64_t rec_capacity) {
-    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8)) {
+    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8) || per_index < 1 || per_index > 2) {
         vis::set_error("vis_sched_pack_records: bad arguments");
         return VIS_E_INVALID;
     }
@@ -508,7 +532,7 @@ int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds
         return VIS_E_CAPACITY;
     }
     std::vector<int> ends;
-    if (!schedule_ends(bounds, out_size, kt, ends)) {
+    if (!schedule_ends(bounds, out_size, kt, per_index, ends)) {
         vis::set_error("vis_sched_pack_records: table is not schedulable (upscale or too many taps)");
         return VIS_E_UNSUPPORTED;
     }
@@ -538,8 +562,12 @@ int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames,
         return VIS_E_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (sched->kt == 6) return launch_sched<6, 8>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
-    return launch_sched<8, 12>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
+    if (sched->per_index > 1) {
+        if (sched->kt == 6) return launch_sched<6, 8, true>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
+        return launch_sched<8, 12, true>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
+    }
+    if (sched->kt == 6) return launch_sched<6, 8, false>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
+    return launch_sched<8, 12, false>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
 }
 
 }  // extern "C"

@@ -131,12 +131,13 @@ class Engine:
             else:
                 N.check(rc, "vis_sched_build")
                 if not g.srec:
-                    kt = int(np.frombuffer(buf[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["kt"])
+                    head = np.frombuffer(buf[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]
+                    kt, per_index = int(head["kt"]), int(head["per_index"])
                     stride = self.L.vis_record_stride(kt)
                     for t in (g.htable, g.vtable):
                         rec = np.zeros((t.out_size + 1, stride), np.int32)
                         N.check(self.L.vis_sched_pack_records(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, kt,
-                                                              N.i32ptr(rec), rec.size), "vis_sched_pack_records")
+                                                              per_index, N.i32ptr(rec), rec.size), "vis_sched_pack_records")
                         g.srec.append(torch.from_numpy(rec).to(self.device))
             g.scheds[key] = buf
         return g.scheds[key]
