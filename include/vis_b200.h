@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 3
+#define VIS_B200_ABI_VERSION 5
 
 /* status codes */
 #define VIS_OK            0
@@ -231,6 +231,19 @@ typedef struct VisOverlayRef { int32_t leaf_begin, leaf_end; } VisOverlayRef;   
 int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int copy_frames,
                      const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
                      const VisLeaf* leaves, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Image-quality statistics (SURVEY.md 8f "next" row).  Replaces the array work of
+ * src/safety/image_quality.py:42-125: cv2.cvtColor(BGR2GRAY), cv2.Laplacian(gray, CV_64F).var(), np.mean(gray).
+ * sums[3*i + 0..2] = sum(gray), sum(laplacian), sum(laplacian^2) of frame i, exact int64; the caller finishes
+ * variance, mean and the scores on the host.                                            [device] */
+typedef struct VisQualityFrame {
+    const uint8_t* src;        /* device BGR uint8 HWC */
+    int64_t        pitch;
+    int32_t        h, w;
+} VisQualityFrame;
+int vis_quality_stats(const VisQualityFrame* frames, int n_frames, int max_h, int max_w,
+                      int64_t* sums, void* stream);
 
 #ifdef __cplusplus
 }

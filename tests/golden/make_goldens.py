@@ -12,6 +12,8 @@ What is recorded (versions of every binary are stored next to the vectors):
   * ``overlay``    the reference's own ``utils.image_utils.draw_bounding_boxes`` executed unmodified, with
                    ``cv2.imread`` / ``cv2.imwrite`` intercepted so the BGR array it holds right before the
                    JPEG encode is captured — sha256 + changed-pixel count.
+  * ``quality``    the reference's own ``src.safety.image_quality.assess_image_quality`` on lossless PNG files of seeded
+                   frames — the full result dict.
 The reference has no tests or vectors of its own for this path; these fixtures are the pin.
 """
 from __future__ import annotations
@@ -84,7 +86,48 @@ def qwen_cases():
     return cases
 
 
+def quality_cases():
+    """BGR frames for the image-quality goldens (name -> array); regenerated from seeds by the tests."""
+    pats = synth.pattern_frames(1080, 1920)
+    return {
+        "noise_1080p_seed1234": synth.noise_frame(1234, 1080, 1920),
+        "lowpass_1080p": pats["lowpass"], "vgrad_1080p": pats["vgrad"], "zeros_1080p": pats["zeros"],
+        "full_1080p": pats["full"], "checker_1080p": pats["checker"],
+        "noise_vga_seed2": synth.noise_frame(2, 480, 640), "noise_odd_333x517_seed6": synth.noise_frame(6, 333, 517),
+        "noise_small_64x96_seed12": synth.noise_frame(12, 64, 96), "noise_99x101_seed13": synth.noise_frame(13, 99, 101),
+        "noise_100x100_seed14": synth.noise_frame(14, 100, 100), "noise_1x1_seed10": synth.noise_frame(10, 1, 1),
+        "noise_1x7_seed15": synth.noise_frame(15, 1, 7), "dark_vga": (synth.noise_frame(16, 480, 640) // 12).astype(np.uint8),
+        "bright_vga": (255 - synth.noise_frame(17, 480, 640) // 12).astype(np.uint8),
+    }
+
+
+def quality_goldens():
+    """The reference's own ImageQualityAssessment (src/safety/image_quality.py) on lossless files of quality_cases()."""
+    import cv2
+    import_reference_image_utils()                      # shims + sys.path for the reference tree
+    iq = importlib.import_module("src.safety.image_quality")
+    tmp = Path(tempfile.mkdtemp(prefix="iq_"))
+    out = []
+    cases = dict(quality_cases())
+    mouri = np.load(HERE / "arrays.npz")["mouri_rgb"]
+    cases["mouri_bgr"] = np.ascontiguousarray(mouri[:, :, ::-1])
+    for name, bgr in cases.items():
+        path = tmp / f"{name}.png"
+        cv2.imwrite(str(path), bgr)
+        res = iq.assess_image_quality(path)
+        res.pop("image_path", None)
+        out.append({"name": name, "shape": list(bgr.shape[:2]), "input_sha256": sha(bgr), "result": res})
+        print("quality", name, res.get("quality_score"), res.get("sharpness", {}).get("laplacian_variance"))
+    return out
+
+
 def main():
+    if "--only-quality" in sys.argv:                    # add / refresh the "quality" section of an existing file
+        out = json.loads((HERE / "goldens.json").read_text())
+        out["quality"] = quality_goldens()
+        (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
+        print("updated", HERE / "goldens.json")
+        return
     import cv2
     import PIL
     import transformers
@@ -197,8 +240,9 @@ def main():
                                "changed_pixels": int((res != frame).any(2).sum())})
         print("overlay", name, sha(res)[:16], out["overlay"][-1]["changed_pixels"])
 
-    (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
     np.savez_compressed(HERE / "arrays.npz", **arrays)
+    out["quality"] = quality_goldens()
+    (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
     print("wrote", HERE / "goldens.json", HERE / "arrays.npz")
 
 

@@ -1,0 +1,62 @@
+"""-m gpu: vis_quality_stats (through the C ABI) against the oracle's exact sums and the reference's own results.
+
+Bar: the three int64 sums are bit-exact; the float64 variance finished on the host is within 1e-9 relative of what
+the reference computed (numpy's two-pass variance of the same integers), every score and flag equal."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import quality as Q
+from test_oracle_quality import quality_frames, same_result
+from vision_inspection_system_b200 import synth
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+
+
+def test_sums_are_exact(engine):
+    rng = np.random.default_rng(3)
+    shapes = [(1080, 1920), (480, 640), (333, 517), (1, 1), (1, 9), (9, 1), (2, 2), (17, 129), (16, 128), (2160, 3840)]
+    frames = [rng.integers(0, 256, s + (3,), dtype=np.uint8) for s in shapes]
+    sums, got_shapes = engine.quality_stats([torch.from_numpy(f).cuda() for f in frames])
+    assert got_shapes == shapes and engine.last_launches == 1
+    host = sums.cpu().numpy()
+    for i, f in enumerate(frames):
+        assert tuple(int(v) for v in host[i]) == Q.stats(f), shapes[i]
+
+
+def test_goldens_from_the_reference(engine, goldens, arrays):
+    from vision_inspection_system_b200 import image_quality as IQ
+    frames = quality_frames(arrays)
+    names = [r["name"] for r in goldens["quality"]]
+    results = IQ.assess_frames([torch.from_numpy(np.ascontiguousarray(frames[n])).cuda() for n in names])
+    for rec, got in zip(goldens["quality"], results):
+        same_result(got, rec["result"], 1e-9)
+
+
+def test_uniform_batch_and_padded_pitch(engine):
+    base = synth.frames_1080p(4)
+    sums, _ = engine.quality_stats(torch.from_numpy(base).cuda())
+    for i in range(4):
+        assert tuple(int(v) for v in sums[i].cpu().numpy()) == Q.stats(base[i])
+    padded = torch.zeros((300, 700, 3), dtype=torch.uint8, device="cuda")
+    padded[:, :640] = torch.from_numpy(synth.noise_frame(5, 300, 640)).cuda()
+    s2, _ = engine.quality_stats([padded[:, :640]])
+    assert tuple(int(v) for v in s2[0].cpu().numpy()) == Q.stats(synth.noise_frame(5, 300, 640))
+
+
+def test_assess_image_quality_file_semantics(engine, tmp_path):
+    import cv2
+    from vision_inspection_system_b200 import image_quality as IQ
+    frame = synth.noise_frame(7, 480, 640)
+    p = tmp_path / "frame.png"
+    cv2.imwrite(str(p), frame)
+    res = IQ.assess_image_quality(p)
+    assert res["image_path"] == str(p)
+    res.pop("image_path")
+    same_result(res, Q.assess(frame), 1e-9)
+    bad = IQ.assess_image_quality(tmp_path / "missing.png")          # never raises: failed-result dict
+    assert bad["quality_passed"] is False and bad["quality_score"] == 0.0 and "Failed to load image" in bad["error"]

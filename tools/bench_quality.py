@@ -1,0 +1,52 @@
+"""GPU benchmark of vis_quality_stats: 256 1080p BGR frames device resident; images/s and fraction of the measured HBM
+copy peak (H*W*3 algorithmic bytes per frame); the reference's cv2 path (one thread, in-memory) beside it."""
+import json
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from vision_inspection_system_b200 import synth  # noqa: E402
+from vision_inspection_system_b200.engine import get_engine  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    eng = get_engine()
+    base = torch.from_numpy(synth.frames_1080p(16)).cuda()
+    frames = base.repeat(n // 16, 1, 1, 1).contiguous()
+    for _ in range(3):
+        eng.quality_stats(frames)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(10):
+        eng.quality_stats(frames)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    peak = 6539.9
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        peak = float(json.loads(p.read_text())["hbm_gbs"])
+    cpu_ms = None
+    try:
+        import cv2
+        f = synth.noise_frame(1234, 1080, 1920)
+        t0 = time.perf_counter()
+        for _ in range(8):
+            g = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY)
+            float(cv2.Laplacian(g, cv2.CV_64F).var())
+            float(g.mean())
+        cpu_ms = (time.perf_counter() - t0) / 8 * 1e3
+    except Exception:
+        pass
+    print(json.dumps({"workload": f"{n} 1080p BGR frames", "ms": ms, "images_per_s": n / ms * 1e3,
+                      "hbm_frac": n * 1080 * 1920 * 3 / ms / 1e6 / peak, "cpu_cv2_ms_per_frame": cpu_ms, "peak_gbs": peak}))
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,7 @@ SCHED_HEAD_DTYPE = np.dtype([("src_h", np.int32), ("src_w", np.int32), ("dst_h",
 assert FRAME_DTYPE.itemsize == 56 and STRIP_DTYPE.itemsize == 20 and BOX_DTYPE.itemsize == 32
 OVERLAY_TILE_DTYPE = np.dtype([("frame", np.int32), ("txy", np.int32), ("ref_begin", np.int32), ("ref_end", np.int32)], align=True)
 OVERLAY_REF_DTYPE = np.dtype([("leaf_begin", np.int32), ("leaf_end", np.int32)], align=True)
+QUALITY_FRAME_DTYPE = np.dtype([("src", np.uint64), ("pitch", np.int64), ("h", np.int32), ("w", np.int32)], align=True)
 assert LEAF_DTYPE.itemsize == 48 and OVERLAY_FRAME_DTYPE.itemsize == 48
 
 EXPORTS = [
@@ -56,7 +57,7 @@ EXPORTS = [
     "vis_max_taps", "vis_fused_kt_class", "vis_record_stride", "vis_pack_records", "vis_fused_supported",
     "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
     "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_preprocess_fused_sched",
-    "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_draw",
+    "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_draw", "vis_quality_stats",
 ]
 
 
@@ -79,7 +80,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 3:
+        if L.vis_abi_version() != 5:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -112,6 +113,7 @@ def _declare(L: C.CDLL) -> None:
     L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
     L.vis_overlay_tiles.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, ip, ip]
     L.vis_overlay_draw.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
+    L.vis_quality_stats.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     for name in EXPORTS:
         if name != "vis_last_error":
             getattr(L, name).restype = C.c_int

@@ -463,6 +463,37 @@ class Engine:
         self._keepalive = (d_desc, d_leaves, d_tiles, d_refs)
         return result
 
+    # ------------------------------------------------------------------ image quality statistics
+    def quality_stats(self, frames):
+        """BGR uint8 HWC CUDA frames (``[B,H,W,3]`` tensor or list) -> (int64 CUDA tensor [B, 3] = sum(gray),
+        sum(laplacian), sum(laplacian^2) per frame, exact; list of (H, W)).  One launch for the batch."""
+        uniform = isinstance(frames, torch.Tensor) and frames.dim() == 4
+        flist = list(frames.unbind(0)) if uniform else list(frames)
+        if not flist:
+            raise ValueError("no frames")
+        for f in flist:
+            self._check_u8(f)
+            if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
+        shapes = [(int(f.shape[0]), int(f.shape[1])) for f in flist]
+        desc = np.zeros(len(flist), N.QUALITY_FRAME_DTYPE)
+        desc["src"] = [f.data_ptr() for f in flist]
+        desc["pitch"] = [f.stride(0) for f in flist]
+        desc["h"] = [s[0] for s in shapes]
+        desc["w"] = [s[1] for s in shapes]
+        d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.device)
+        sums = torch.empty((len(flist), 3), dtype=torch.int64, device=self.device)
+        out = []
+        for b0 in range(0, len(flist), 65535):
+            n = min(65535, len(flist) - b0)
+            N.check(self.L.vis_quality_stats(d_desc.data_ptr() + b0 * N.QUALITY_FRAME_DTYPE.itemsize, n,
+                                             max(s[0] for s in shapes[b0:b0 + n]), max(s[1] for s in shapes[b0:b0 + n]),
+                                             sums.data_ptr() + b0 * 24, _stream_ptr()), "vis_quality_stats")
+            out.append(n)
+        self.last_launches = len(out)
+        self._keepalive_q = d_desc
+        return sums, shapes
+
     # ------------------------------------------------------------------ helpers
     def _check_u8(self, t: torch.Tensor) -> None:
         if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.uint8:
