@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 5
+#define VIS_B200_ABI_VERSION 6
 
 /* status codes */
 #define VIS_OK            0
@@ -135,8 +135,8 @@ int vis_preprocess_fused(const VisFrame* frames, int n_frames, const VisStrip* s
  * is left on the device.  Geometries it declines (VIS_E_UNSUPPORTED) go to vis_preprocess_fused.
  * ------------------------------------------------------------------------------------------ */
 #define VIS_SCHED_MAX_STRIPS 16      /* column strips per frame (<= 336 output columns each)       */
-#define VIS_SCHED_MAX_SEGS   8       /* row segments per frame                                     */
-#define VIS_SCHED_SUBS       12      /* column sub-ranges per strip (one per horizontal-pass warp) */
+#define VIS_SCHED_MAX_SEGS   16      /* row segments per frame                                     */
+#define VIS_SCHED_SUBS       12      /* column sub-ranges per strip, at most (one per horizontal-pass warp) */
 #define VIS_SCHED_MASK_BYTES 6144
 
 typedef struct VisSchedStrip { int32_t x0, x1, px0, row_bytes; } VisSchedStrip;
@@ -150,6 +150,10 @@ typedef struct VisSched {            /* opaque to callers: filled by vis_sched_b
     int32_t n_strips, n_segs;
     int32_t stage_pitch, max_strip_w;
     int32_t per_index;               /* 1: scale >= 1 on both axes; 2: mild upscale, two mask bytes are live per step */
+    int32_t ring;                    /* register window of the kernel: 8 (<= 8 taps) or 16 (<= 16 taps)            */
+    int32_t n_subs;                  /* column sub-ranges per strip = horizontal-pass warps (12 / 9)               */
+    int32_t out_mode;                /* VIS_SCHED_OUT_PIXEL_VALUES or VIS_SCHED_OUT_U8                              */
+    int32_t reserved;
     VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
     VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_SUBS];
     VisSchedSeg   seg[VIS_SCHED_MAX_SEGS];
@@ -161,12 +165,15 @@ typedef struct VisFrameRef {         /* per frame of a scheduled launch (device 
     int64_t        row0;             /* first row of this frame in pixel_values                    */
 } VisFrameRef;
 
+#define VIS_SCHED_OUT_PIXEL_VALUES 0   /* LUT + Qwen2-VL patch layout, fp32 (dst_h, dst_w multiples of 28)            */
+#define VIS_SCHED_OUT_U8           1   /* resized RGB uint8 HWC (dst_w multiple of 4): Image.resize / thumbnails      */
+
 /* sizeof(VisSched), for bindings that treat it as an opaque byte buffer                  [host] */
 int vis_sched_sizeof(void);
 /* hbounds / vbounds: HOST bounds tables of vis_build_coeffs (dst_w x 2, dst_h x 2); vsplit = row segments.
  * VIS_OK, or VIS_E_UNSUPPORTED when the geometry needs the general kernel.              [host] */
 int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitch,
-                    const int32_t* hbounds, const int32_t* vbounds, int vsplit, VisSched* out);
+                    const int32_t* hbounds, const int32_t* vbounds, int vsplit, int out_mode, VisSched* out);
 /* records for the scheduled kernel: like vis_pack_records, but samples whose window the far border clamps are
  * moved to the virtual end index the schedule gives them (leading zero coefficients).  kt, per_index: the
  * schedule's.                                                                             [host] */
@@ -176,6 +183,14 @@ int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds
 int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,
                                const int32_t* hrec, const int32_t* vrec,
                                const float* lut768, float* pixel_values, void* stream);
+
+/* Image.resize((dst_w, dst_h), filter) of RGB uint8 HWC frames in ONE fused launch (both passes, uint8 between them,
+ * horizontal first): the agents' thumbnails (src/agents/vlm_inspector.py:64, vlm_auditor.py:91) and resize_image
+ * (utils/image_utils.py:75).  sched: built with VIS_SCHED_OUT_U8 from the filter's bounds tables (<= 16 taps).
+ * frames: DEVICE array of (src, dst) pointers; dst rows are dst_pitch bytes apart (multiple of 4).   [device] */
+typedef struct VisResizeRef { const uint8_t* src; uint8_t* dst; } VisResizeRef;
+int vis_resize_fused_sched(const VisSched* sched, const VisResizeRef* frames, int n_frames, int64_t dst_pitch,
+                           const int32_t* hrec, const int32_t* vrec, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Defect overlay rasteriser.

@@ -49,3 +49,27 @@ def test_resize_image_semantics(engine):
     assert np.array_equal(np.asarray(got), np.asarray(want))
     gray = Image.fromarray(synth.noise_frame(3, 300, 500)[:, :, 0])
     assert np.array_equal(np.asarray(IU.resize_image(gray, 128)), np.asarray(gray.resize((128, 76), Image.Resampling.LANCZOS)))
+
+
+def test_fused_thumbnail_path_and_batches(engine):
+    """RGB LANCZOS thumbnails with <= 16 taps take the fused scheduled kernel (one launch for a whole batch); wider
+    filters, other channel counts and odd widths fall back to the generic passes.  Both give Pillow's bytes."""
+    frames = [synth.noise_frame(30 + i, 1080, 1920) for i in range(3)]
+    dev = [torch.from_numpy(f).cuda() for f in frames]
+    outs = engine.resize_batch_u8(dev, 576, 1024, Q.LANCZOS)
+    assert engine.last_launches == 1
+    for f, o in zip(frames, outs):
+        assert np.array_equal(o.cpu().numpy(), Q.resize(f, 576, 1024, Q.LANCZOS))
+    big = synth.noise_frame(33, 2160, 3840)
+    got = engine.resize_u8(torch.from_numpy(big).cuda(), 1152, 2048, Q.LANCZOS)
+    assert engine.last_launches == 1
+    assert np.array_equal(got.cpu().numpy(), Q.resize(big, 1152, 2048, Q.LANCZOS))
+    got = engine.resize_u8(torch.from_numpy(big).cuda(), 576, 1024, Q.LANCZOS)          # 25 taps: generic passes
+    assert engine.last_launches == 2
+    assert np.array_equal(got.cpu().numpy(), Q.resize(big, 576, 1024, Q.LANCZOS))
+    for out_hw in ((683, 1024), (700, 1000), (1023, 1366), (540, 958)):                  # segments ending inside a band, odd widths
+        a = synth.noise_frame(34, 1365, 2048)
+        got = engine.resize_u8(torch.from_numpy(a).cuda(), out_hw[0], out_hw[1], Q.LANCZOS)
+        assert np.array_equal(got.cpu().numpy(), Q.resize(a, out_hw[0], out_hw[1], Q.LANCZOS)), out_hw
+    same = engine.resize_u8(torch.from_numpy(frames[0]).cuda(), 576, 1024, Q.LANCZOS, fused=False)
+    assert engine.last_launches == 2 and torch.equal(same, outs[0])

@@ -14,8 +14,9 @@ SUB = np.dtype([("xa", np.uint16), ("xb", np.uint16), ("p0", np.uint16), ("nstep
 STRIP = np.dtype([("x0", np.int32), ("x1", np.int32), ("px0", np.int32), ("row_bytes", np.int32)])
 SEG = np.dtype([("y0", np.int32), ("y1", np.int32), ("r_first", np.int32), ("r_end", np.int32), ("mask_off", np.int32),
                 ("pad", np.int32)])
-SCHED = np.dtype([("head", N.SCHED_HEAD_DTYPE), ("strip", STRIP, (16,)), ("sub", SUB, (16, 12)), ("seg", SEG, (8,)),
+SCHED = np.dtype([("head", N.SCHED_HEAD_DTYPE), ("strip", STRIP, (16,)), ("sub", SUB, (16, 12)), ("seg", SEG, (16,)),
                   ("mask", np.uint8, (6144,))], align=True)
+SEG_COUNT = 16
 
 
 def sched_ends_and_records(table, kt, per_index=1):
@@ -41,74 +42,73 @@ def sched_ends_and_records(table, kt, per_index=1):
     return ends, rec
 
 
-def build(src_h, src_w, dst_h, dst_w, pitch, vsplit):
+def build(src_h, src_w, dst_h, dst_w, pitch, vsplit, filt=N.FILTER_BICUBIC, out_mode=N.SCHED_OUT_PIXEL_VALUES):
     L = N.lib()
     assert SCHED.itemsize == L.vis_sched_sizeof()
-    ht = T.coeff_table(src_w, dst_w, N.FILTER_BICUBIC)
-    vt = T.coeff_table(src_h, dst_h, N.FILTER_BICUBIC)
+    ht = T.coeff_table(src_w, dst_w, filt)
+    vt = T.coeff_table(src_h, dst_h, filt)
     buf = np.zeros(1, SCHED)
-    rc = L.vis_sched_build(src_h, src_w, dst_h, dst_w, pitch, N.i32ptr(ht.bounds), N.i32ptr(vt.bounds), vsplit,
+    rc = L.vis_sched_build(src_h, src_w, dst_h, dst_w, pitch, N.i32ptr(ht.bounds), N.i32ptr(vt.bounds), vsplit, out_mode,
                            buf.ctypes.data_as(C.c_void_p))
     return rc, buf[0], ht, vt
 
 
-@pytest.mark.parametrize("shape,vsplit,max_pixels,want_per", [
-    ((1080, 1920), 1, G.DEFAULT_MAX_PIXELS, 1), ((1080, 1920), 3, G.DEFAULT_MAX_PIXELS, 1), ((2160, 3840), 2, G.HUB_MAX_PIXELS, 1),
-    ((1536, 2048), 8, G.DEFAULT_MAX_PIXELS, 1), ((1152, 2048), 1, G.DEFAULT_MAX_PIXELS, 1), ((2048, 1536), 4, G.DEFAULT_MAX_PIXELS, 1),
-    ((600, 5000), 2, G.DEFAULT_MAX_PIXELS, 1), ((1080, 1920), 2, G.HUB_MAX_PIXELS, 2), ((720, 1280), 1, G.DEFAULT_MAX_PIXELS, 2),
-    ((480, 640), 3, G.DEFAULT_MAX_PIXELS, 2), ((560, 1000), 1, G.DEFAULT_MAX_PIXELS, 2)])
-def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels, want_per):
-    h, w = shape
-    dh, dw = G.smart_resize(h, w, G.FACTOR, G.DEFAULT_MIN_PIXELS, max_pixels)
-    pitch = (w * 3 + 15) // 16 * 16
-    rc, s, ht, vt = build(h, w, dh, dw, pitch, vsplit)
-    assert rc == N.VIS_OK, N.lib().vis_last_error()
+def read_mask(mask, off, index, ring):
+    """(first-sample mask, second-sample mask) of step / group `index`: ring / 8 bytes each, little endian."""
+    mb = ring // 8
+    at = int(off) + 2 * mb * index
+    return (int.from_bytes(bytes(mask[at:at + mb]), "little"), int.from_bytes(bytes(mask[at + mb:at + 2 * mb]), "little"))
+
+
+def replay(s, ht, vt, w, pitch, want_per, want_ring, unit):
     hd = s["head"]
-    assert (hd["dst_h"], hd["dst_w"], hd["kt"]) == (dh, dw, T.kt_class(max(ht.max_taps, vt.max_taps)))
-    per = int(hd["per_index"])
-    assert per == want_per
-    hlast, hrec = sched_ends_and_records(ht, int(hd["kt"]), per)
-    vlast, vrec = sched_ends_and_records(vt, int(hd["kt"]), per)
+    ring, per, n_subs = int(hd["ring"]), int(hd["per_index"]), int(hd["n_subs"])
+    assert (per, ring) == (want_per, want_ring) and n_subs == (12 if ring == 8 else 9)
+    dh, dw = int(hd["dst_h"]), int(hd["dst_w"])
+    hlast, _ = sched_ends_and_records(ht, int(hd["kt"]), per)
+    vlast, _ = sched_ends_and_records(vt, int(hd["kt"]), per)
     # horizontal: every output column of every strip is emitted exactly once, at the pixel where its window ends,
     # after all of its taps have been read (p0 <= first tap), and the staged row segment covers the window
     covered = np.zeros(dw, np.int32)
     for st in range(hd["n_strips"]):
         S = s["strip"][st]
-        assert S["x0"] % 28 == 0 and S["x1"] % 28 == 0 and S["px0"] % 16 == 0 and S["row_bytes"] % 16 == 0
+        assert S["x0"] % unit == 0 and S["x1"] % unit == 0 and S["px0"] % 16 == 0 and S["row_bytes"] % 16 == 0
+        assert S["x1"] - S["x0"] <= hd["max_strip_w"] <= 336
         assert S["row_bytes"] <= hd["stage_pitch"] and S["px0"] * 3 + S["row_bytes"] <= pitch
-        for u in range(12):
+        for u in range(n_subs):
             U = s["sub"][st][u]
             xo = int(U["xa"])
-            assert U["p0"] % 8 == 0 and U["p0"] >= S["px0"] and U["p0"] <= ht.bounds[xo, 0]
+            assert U["p0"] % ring == 0 and U["p0"] >= S["px0"] and U["p0"] <= ht.bounds[xo, 0]
             for i in range(U["nsteps"]):
-                m1, m2 = int(s["mask"][U["mask_off"] + 2 * i]), int(s["mask"][U["mask_off"] + 2 * i + 1])
+                m1, m2 = read_mask(s["mask"], U["mask_off"], i, ring)
                 assert m2 & ~m1 == 0 and (per == 2 or m2 == 0)
-                for jj in range(8):
+                for jj in range(ring):
                     for m in (m1, m2):
                         if m >> jj & 1:
-                            assert hlast[xo] == U["p0"] + 8 * i + jj
+                            assert hlast[xo] == U["p0"] + ring * i + jj
                             assert (min(hlast[xo], w - 1) + 1) * 3 <= S["px0"] * 3 + S["row_bytes"]
                             covered[xo] += 1
                             xo += 1
             assert xo == U["xb"]
     assert (covered == 1).all()
-    # vertical: every output row once per segment cover, at the input row where its window ends
+    # vertical: every output row once, at the input row where its window ends; segments tile [0, dst_h)
     rows = np.zeros(dh, np.int32)
+    assert s["seg"][0]["y0"] == 0 and s["seg"][hd["n_segs"] - 1]["y1"] == dh
     for sg in range(hd["n_segs"]):
         Gs = s["seg"][sg]
         yo = int(Gs["y0"])
-        assert Gs["y0"] % 14 == 0 and Gs["y1"] % 14 == 0 and Gs["r_first"] % 16 == 0 and Gs["mask_off"] % 8 == 0
+        assert Gs["y0"] % 14 == 0 and (Gs["y1"] % 14 == 0 or Gs["y1"] == dh) and Gs["r_first"] % 16 == 0 and Gs["mask_off"] % 8 == 0
         assert Gs["r_first"] <= vt.bounds[yo, 0]
         n_chunks = -(-(Gs["r_end"] - Gs["r_first"]) // 32)
         for c in range(n_chunks):
             emitted_here = 0
-            for g in range(4):
-                m1, m2 = int(s["mask"][Gs["mask_off"] + 2 * (c * 4 + g)]), int(s["mask"][Gs["mask_off"] + 2 * (c * 4 + g) + 1])
+            for g in range(32 // ring):
+                m1, m2 = read_mask(s["mask"], Gs["mask_off"], c * (32 // ring) + g, ring)
                 assert m2 & ~m1 == 0 and (per == 2 or m2 == 0)
-                for u in range(8):
+                for u in range(ring):
                     for m in (m1, m2):
                         if m >> u & 1:
-                            assert vlast[yo] == Gs["r_first"] + c * 32 + g * 8 + u
+                            assert vlast[yo] == Gs["r_first"] + c * 32 + g * ring + u
                             rows[yo] += 1
                             yo += 1
                             emitted_here += 1
@@ -117,7 +117,39 @@ def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels, want_per):
     assert (rows == 1).all()
 
 
-@pytest.mark.parametrize("shape,max_pixels,why", [((20, 30), G.DEFAULT_MAX_PIXELS, b"upscale"), ((2160, 3840), G.DEFAULT_MAX_PIXELS, b"taps"),
+@pytest.mark.parametrize("shape,vsplit,max_pixels,want_per,want_ring", [
+    ((1080, 1920), 1, G.DEFAULT_MAX_PIXELS, 1, 8), ((1080, 1920), 3, G.DEFAULT_MAX_PIXELS, 1, 8), ((2160, 3840), 2, G.HUB_MAX_PIXELS, 1, 8),
+    ((1536, 2048), 8, G.DEFAULT_MAX_PIXELS, 1, 8), ((1152, 2048), 1, G.DEFAULT_MAX_PIXELS, 1, 8), ((2048, 1536), 4, G.DEFAULT_MAX_PIXELS, 1, 8),
+    ((600, 5000), 2, G.DEFAULT_MAX_PIXELS, 1, 8), ((1080, 1920), 2, G.HUB_MAX_PIXELS, 2, 8), ((720, 1280), 1, G.DEFAULT_MAX_PIXELS, 2, 8),
+    ((480, 640), 3, G.DEFAULT_MAX_PIXELS, 2, 8), ((560, 1000), 1, G.DEFAULT_MAX_PIXELS, 2, 8),
+    ((2160, 3840), 1, G.DEFAULT_MAX_PIXELS, 1, 16), ((2160, 3840), 16, G.DEFAULT_MAX_PIXELS, 1, 16), ((1080, 1920), 2, 250000, 1, 16)])
+def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels, want_per, want_ring):
+    h, w = shape
+    dh, dw = G.smart_resize(h, w, G.FACTOR, G.DEFAULT_MIN_PIXELS, max_pixels)
+    pitch = (w * 3 + 15) // 16 * 16
+    rc, s, ht, vt = build(h, w, dh, dw, pitch, vsplit)
+    assert rc == N.VIS_OK, N.lib().vis_last_error()
+    hd = s["head"]
+    want_kt = max(ht.max_taps, vt.max_taps)
+    assert (hd["dst_h"], hd["dst_w"]) == (dh, dw) and hd["kt"] == (T.kt_class(want_kt) if want_ring == 8 else (12 if want_kt <= 12 else 16))
+    replay(s, ht, vt, w, pitch, want_per, want_ring, 28)
+
+
+@pytest.mark.parametrize("shape,out,vsplit", [((2160, 3840), (1152, 2048), 1), ((1080, 1920), (576, 1024), 5),
+                                              ((1600, 1200), (1024, 768), 2), ((1536, 2048), (768, 1024), 16),
+                                              ((300, 500), (153, 256), 1), ((1365, 2048), (683, 1024), 3)])
+def test_uint8_resize_schedule(shape, out, vsplit):
+    """VIS_SCHED_OUT_U8 (LANCZOS thumbnails / resize_image): 16-slot kernel, strips in units of 4 columns, last segment
+    ends at dst_h."""
+    (h, w), (dh, dw) = shape, out
+    pitch = (w * 3 + 15) // 16 * 16
+    rc, s, ht, vt = build(h, w, dh, dw, pitch, vsplit, N.FILTER_LANCZOS, N.SCHED_OUT_U8)
+    assert rc == N.VIS_OK, N.lib().vis_last_error()
+    assert s["head"]["out_mode"] == N.SCHED_OUT_U8 and s["head"]["kt"] in (12, 16)
+    replay(s, ht, vt, w, pitch, 1, 16, 4)
+
+
+@pytest.mark.parametrize("shape,max_pixels,why", [((20, 30), G.DEFAULT_MAX_PIXELS, b"upscale"), ((3100, 5500), G.DEFAULT_MAX_PIXELS, b"taps"),
                                                   ((100, 502), G.DEFAULT_MAX_PIXELS, b"pitch")])
 def test_schedule_declines_what_it_cannot_express(shape, max_pixels, why):
     h, w = shape

@@ -43,7 +43,10 @@ OVERLAY_FRAME_DTYPE = np.dtype([
 FRAME_REF_DTYPE = np.dtype([("src", np.uint64), ("row0", np.int64)], align=True)
 SCHED_HEAD_DTYPE = np.dtype([("src_h", np.int32), ("src_w", np.int32), ("dst_h", np.int32), ("dst_w", np.int32),
                              ("src_pitch", np.int64), ("kt", np.int32), ("n_strips", np.int32), ("n_segs", np.int32),
-                             ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("per_index", np.int32)], align=True)
+                             ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("per_index", np.int32), ("ring", np.int32),
+                             ("n_subs", np.int32), ("out_mode", np.int32), ("reserved", np.int32)], align=True)
+SCHED_OUT_PIXEL_VALUES, SCHED_OUT_U8 = 0, 1
+RESIZE_REF_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64)], align=True)
 
 assert FRAME_DTYPE.itemsize == 56 and STRIP_DTYPE.itemsize == 20 and BOX_DTYPE.itemsize == 32
 OVERLAY_TILE_DTYPE = np.dtype([("frame", np.int32), ("txy", np.int32), ("ref_begin", np.int32), ("ref_end", np.int32)], align=True)
@@ -57,6 +60,7 @@ EXPORTS = [
     "vis_max_taps", "vis_fused_kt_class", "vis_record_stride", "vis_pack_records", "vis_fused_supported",
     "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
     "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_preprocess_fused_sched",
+    "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_draw", "vis_quality_stats",
 ]
 
@@ -80,7 +84,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 5:
+        if L.vis_abi_version() != 6:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -107,7 +111,8 @@ def _declare(L: C.CDLL) -> None:
     L.vis_plan_strips.argtypes = [C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.c_int, vp, C.c_int, ip, ip]
     L.vis_preprocess_fused.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.vis_sched_sizeof.argtypes = []
-    L.vis_sched_build.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, i32p, i32p, C.c_int, vp]
+    L.vis_sched_build.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, i32p, i32p, C.c_int, C.c_int, vp]
+    L.vis_resize_fused_sched.argtypes = [vp, vp, C.c_int, C.c_int64, vp, vp, vp]
     L.vis_sched_pack_records.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]
     L.vis_preprocess_fused_sched.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]

@@ -21,10 +21,18 @@
 // (profiles/r01_fused_ws4.txt).
 #include "vis_fused_common.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
 using namespace visf;
+
+namespace visf {   // 16-slot kernel, vis_fused_sched16.cu
+int sched16_subs();
+int sched16_layout_bytes(int stage_pitch, int strip_w, int cls);
+int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
+                   const float* lut768, float* pixel_values, cudaStream_t st);
+}
 
 namespace {
 
@@ -411,24 +419,31 @@ extern "C" {
 int vis_sched_sizeof(void) { return (int)sizeof(VisSched); }
 
 int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitch,
-                    const int32_t* hb, const int32_t* vb, int vsplit, VisSched* out) {
-    if (!hb || !vb || !out || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || vsplit < 1) {
+                    const int32_t* hb, const int32_t* vb, int vsplit, int out_mode, VisSched* out) {
+    if (!hb || !vb || !out || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || vsplit < 1 ||
+        (out_mode != VIS_SCHED_OUT_PIXEL_VALUES && out_mode != VIS_SCHED_OUT_U8)) {
         vis::set_error("vis_sched_build: bad arguments");
         return VIS_E_INVALID;
     }
     auto unsupported = [](const char* why) { vis::set_error("vis_sched_build: %s", why); return VIS_E_UNSUPPORTED; };
-    if (dst_h % 28 || dst_w % 28) return unsupported("output size is not a multiple of 28");
+    const bool u8 = out_mode == VIS_SCHED_OUT_U8;
+    if (!u8 && (dst_h % 28 || dst_w % 28)) return unsupported("output size is not a multiple of 28");
+    if (u8 && dst_w % 4) return unsupported("output width is not a multiple of 4");
     if (src_pitch % 16 || src_pitch < (int64_t)src_w * 3) return unsupported("row pitch must be a multiple of 16");
     if ((int64_t)src_h > 100 * (int64_t)src_w && dst_h < src_h) return unsupported("vertical-first pass order");
     if (src_w > 65528 || dst_w > 65528) return unsupported("image too wide");
     const int hkt = vis_max_taps(hb, dst_w), vkt = vis_max_taps(vb, dst_h);
     const int mk = hkt > vkt ? hkt : vkt;
-    const int cls = mk <= 6 ? 6 : mk <= 8 ? 8 : 0;
-    if (!cls) return unsupported("more than 8 taps");
+    // tap class -> kernel: <= 8 taps: 8-slot register windows (pixel_values only); <= 16 taps: 16-slot kernel
+    const int cls = u8 ? (mk <= 12 ? 12 : mk <= 16 ? 16 : 0) : (mk <= 6 ? 6 : mk <= 8 ? 8 : mk <= 12 ? 12 : mk <= 16 ? 16 : 0);
+    if (!cls) return unsupported("more than 16 taps");
+    const int ring = cls <= 8 ? 8 : 16;
+    const int n_subs = ring == 8 ? 12 : visf::sched16_subs();
     std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
     int per_index = 1;
     if (!schedule_ends(hb, dst_w, cls, 1, hl) || !schedule_ends(vb, dst_h, cls, 1, vl)) {
         per_index = 2;                            // mild upscale on some axis: two samples per input index
+        if (ring != 8) return unsupported("upscaling with more than 8 taps");
         if (!schedule_ends(hb, dst_w, cls, 2, hl)) return unsupported("horizontal upscale beyond two samples per input column");
         if (!schedule_ends(vb, dst_h, cls, 2, vl)) return unsupported("vertical upscale beyond two samples per input row");
     }
@@ -436,7 +451,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     VisSched& s = *out;
     std::memset(&s, 0, sizeof(s));
     s.src_h = src_h; s.src_w = src_w; s.dst_h = dst_h; s.dst_w = dst_w; s.src_pitch = src_pitch; s.kt = cls;
-    s.per_index = per_index;
+    s.per_index = per_index; s.ring = ring; s.n_subs = n_subs; s.out_mode = out_mode;
     const int stride = vis_record_stride(cls);
     auto last = [](const int32_t* b, int i) { return b[2 * i] + b[2 * i + 1] - 1; };
     auto span_of = [&](int x0, int x1, int* px0) {
@@ -445,21 +460,24 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
         if ((int64_t)*px0 * 3 + bytes > src_pitch) bytes = (int)(src_pitch - (int64_t)*px0 * 3);
         return bytes;
     };
-    // column strips: the widest strips (multiples of 28 columns, <= 336) whose shared-memory layout fits
-    const int blocks = dst_w / 28;
+    auto layout_bytes = [&](int pitch, int strip_w) {
+        return ring == 8 ? make_layout_s(pitch, strip_w, stride).total : visf::sched16_layout_bytes(pitch, strip_w, cls);
+    };
+    // column strips: the fewest (widest, <= 336 columns) whose shared-memory layout fits; strip edges are multiples
+    // of 28 columns (pixel_values: whole patches) or 4 columns (uint8 rows: whole 32-bit words of a plane)
+    const int unit = u8 ? 4 : 28;
+    const int blocks = dst_w / unit;
     int n_strips = 0;
-    for (int per = kMaxStripW / 28; per >= 1 && !n_strips; --per) {
-        const int n = (blocks + per - 1) / per;
-        if (n > VIS_SCHED_MAX_STRIPS) break;
+    for (int n = (dst_w + kMaxStripW - 1) / kMaxStripW; n <= VIS_SCHED_MAX_STRIPS && n <= blocks && !n_strips; ++n) {
         int worst_span = 0, worst_w = 0;
         for (int i = 0; i < n; ++i) {
             const int b0 = (int)((int64_t)blocks * i / n), b1 = (int)((int64_t)blocks * (i + 1) / n);
             int px0;
-            const int span = span_of(b0 * 28, b1 * 28, &px0);
+            const int span = span_of(b0 * unit, b1 * unit, &px0);
             worst_span = span > worst_span ? span : worst_span;
-            worst_w = (b1 - b0) * 28 > worst_w ? (b1 - b0) * 28 : worst_w;
+            worst_w = (b1 - b0) * unit > worst_w ? (b1 - b0) * unit : worst_w;
         }
-        if (make_layout_s(stage_pitch_for(worst_span), worst_w, stride).total <= kSmemMax) {
+        if (worst_w <= kMaxStripW && layout_bytes(stage_pitch_for(worst_span), worst_w) <= kSmemMax) {
             n_strips = n;
             s.stage_pitch = stage_pitch_for(worst_span);
             s.max_strip_w = worst_w;
@@ -467,34 +485,35 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     }
     if (!n_strips) return unsupported("no strip width fits shared memory");
     s.n_strips = n_strips;
+    const int step = ring, mbytes = ring / 8;                      // input pixels (rows) per mask word, bytes per mask
     int mask_at = 0;
     auto mask_room = [&](int bytes) { return mask_at + bytes <= VIS_SCHED_MASK_BYTES; };
+    auto set_bit = [&](int base, int rel) {                        // per step: first-sample mask, then second-sample mask
+        uint8_t* m = s.mask + base + 2 * mbytes * (rel / step) + (rel % step) / 8;
+        const uint8_t bit = (uint8_t)(1u << (rel % 8));
+        if (m[0] & bit) m[mbytes] |= bit; else m[0] |= bit;
+    };
     for (int i = 0; i < n_strips; ++i) {
         VisSchedStrip& S = s.strip[i];
-        S.x0 = (int)((int64_t)blocks * i / n_strips) * 28;
-        S.x1 = (int)((int64_t)blocks * (i + 1) / n_strips) * 28;
+        S.x0 = (int)((int64_t)blocks * i / n_strips) * unit;
+        S.x1 = (int)((int64_t)blocks * (i + 1) / n_strips) * unit;
         S.row_bytes = span_of(S.x0, S.x1, &S.px0);
         const int sw = S.x1 - S.x0;
-        for (int u = 0; u < VIS_SCHED_SUBS; ++u) {
+        for (int u = 0; u < n_subs; ++u) {
             VisSchedSub& U = s.sub[i][u];
-            const int xa = S.x0 + (int)((int64_t)sw * u / VIS_SCHED_SUBS), xb = S.x0 + (int)((int64_t)sw * (u + 1) / VIS_SCHED_SUBS);
+            const int xa = S.x0 + (int)((int64_t)sw * u / n_subs), xb = S.x0 + (int)((int64_t)sw * (u + 1) / n_subs);
             U.xa = (uint16_t)xa; U.xb = (uint16_t)xb;
             if (xa >= xb) continue;                                    // nsteps = 0
-            const int p0 = hb[2 * xa] & ~(kStepPx - 1);
-            const int nsteps = (hl[xb - 1] - p0) / kStepPx + 1;
-            if (!mask_room(2 * nsteps) || nsteps > 65535) return unsupported("schedule too large");
+            const int p0 = hb[2 * xa] & ~(step - 1);
+            const int nsteps = (hl[xb - 1] - p0) / step + 1;
+            if (!mask_room(2 * mbytes * nsteps) || nsteps > 65535) return unsupported("schedule too large");
             U.p0 = (uint16_t)p0; U.nsteps = (uint16_t)nsteps; U.mask_off = (uint16_t)mask_at;
-            for (int x = xa; x < xb; ++x) {                            // per step: first-sample mask, second-sample mask
-                const int rel = hl[x] - p0;
-                uint8_t* m = s.mask + mask_at + 2 * (rel / kStepPx);
-                const uint8_t bit = (uint8_t)(1u << (rel % kStepPx));
-                if (m[0] & bit) m[1] |= bit; else m[0] |= bit;
-            }
-            mask_at += 2 * nsteps;
+            for (int x = xa; x < xb; ++x) set_bit(mask_at, hl[x] - p0);
+            mask_at += 2 * mbytes * nsteps;
         }
     }
-    // row segments: multiples of 14 output rows; chunk bases are multiples of 16 input rows
-    const int prow = dst_h / 14;
+    // row segments: edges at multiples of 14 output rows (the last one ends at dst_h); chunk bases are multiples of 16
+    const int prow = (dst_h + 13) / 14;
     if (vsplit > prow) vsplit = prow;
     if (vsplit > VIS_SCHED_MAX_SEGS) vsplit = VIS_SCHED_MAX_SEGS;
     s.n_segs = vsplit;
@@ -502,19 +521,14 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     for (int g = 0; g < vsplit; ++g) {
         VisSchedSeg& G = s.seg[g];
         G.y0 = (int)((int64_t)prow * g / vsplit) * 14;
-        G.y1 = (int)((int64_t)prow * (g + 1) / vsplit) * 14;
+        G.y1 = std::min((int)((int64_t)prow * (g + 1) / vsplit) * 14, dst_h);
         G.r_first = vb[2 * G.y0] & ~15;
         G.r_end = vl[G.y1 - 1] + 1;                                  // may exceed src_h by the virtual rows
         const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
-        const int bytes = 2 * n_chunks * (kChunk / kRing);
+        const int bytes = 2 * mbytes * n_chunks * (kChunk / step);
         if (!mask_room(bytes)) return unsupported("schedule too large");
         G.mask_off = mask_at;
-        for (int y = G.y0; y < G.y1; ++y) {
-            const int rel = vl[y] - G.r_first;
-            uint8_t* m = s.mask + mask_at + 2 * (rel / kRing);
-            const uint8_t bit = (uint8_t)(1u << (rel % kRing));
-            if (m[0] & bit) m[1] |= bit; else m[0] |= bit;
-        }
+        for (int y = G.y0; y < G.y1; ++y) set_bit(mask_at, vl[y] - G.r_first);
         mask_at += bytes;
     }
     return VIS_OK;
@@ -522,7 +536,8 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
 
 int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt, int per_index,
                            int32_t* rec, int64_t rec_capacity) {
-    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8) || per_index < 1 || per_index > 2) {
+    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8 && kt != 12 && kt != 16) ||
+        per_index < 1 || per_index > 2) {
         vis::set_error("vis_sched_pack_records: bad arguments");
         return VIS_E_INVALID;
     }
@@ -552,8 +567,15 @@ int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames,
                                const int32_t* hrec, const int32_t* vrec,
                                const float* lut768, float* pixel_values, void* stream) {
     if (!sched || !frames || !hrec || !vrec || !lut768 || !pixel_values || n_frames <= 0 ||
-        (sched->kt != 6 && sched->kt != 8) || sched->n_strips <= 0 || sched->n_segs <= 0) {
+        sched->out_mode != VIS_SCHED_OUT_PIXEL_VALUES || sched->n_strips <= 0 || sched->n_segs <= 0) {
         vis::set_error("vis_preprocess_fused_sched: bad arguments");
+        return VIS_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sched->ring == 16)
+        return sched16_launch(*sched, frames, n_frames, 0, hrec, vrec, lut768, pixel_values, st);
+    if (sched->ring != 8 || (sched->kt != 6 && sched->kt != 8)) {
+        vis::set_error("vis_preprocess_fused_sched: schedule of an unknown kernel class (ring %d, %d taps)", sched->ring, sched->kt);
         return VIS_E_INVALID;
     }
     const LayoutS L = make_layout_s(sched->stage_pitch, sched->max_strip_w, vis_record_stride(sched->kt));
@@ -561,13 +583,22 @@ int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames,
         vis::set_error("vis_preprocess_fused_sched: %d bytes of shared memory needed", L.total);
         return VIS_E_UNSUPPORTED;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     if (sched->per_index > 1) {
         if (sched->kt == 6) return launch_sched<6, 8, true>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
         return launch_sched<8, 12, true>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
     }
     if (sched->kt == 6) return launch_sched<6, 8, false>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
     return launch_sched<8, 12, false>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
+}
+
+int vis_resize_fused_sched(const VisSched* sched, const VisResizeRef* frames, int n_frames, int64_t dst_pitch,
+                           const int32_t* hrec, const int32_t* vrec, void* stream) {
+    if (!sched || !frames || !hrec || !vrec || n_frames <= 0 || sched->out_mode != VIS_SCHED_OUT_U8 || sched->ring != 16 ||
+        sched->n_strips <= 0 || sched->n_segs <= 0 || dst_pitch % 4 || dst_pitch < (int64_t)sched->dst_w * 3) {
+        vis::set_error("vis_resize_fused_sched: bad arguments");
+        return VIS_E_INVALID;
+    }
+    return sched16_launch(*sched, frames, n_frames, dst_pitch, hrec, vrec, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

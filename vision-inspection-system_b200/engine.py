@@ -125,7 +125,8 @@ class Engine:
         if key not in g.scheds:
             buf = np.zeros(self.L.vis_sched_sizeof(), np.uint8)
             rc = self.L.vis_sched_build(g.src_h, g.src_w, g.dst_h, g.dst_w, pitch, N.i32ptr(g.htable.bounds),
-                                        N.i32ptr(g.vtable.bounds), n_segs, buf.ctypes.data_as(C.c_void_p))
+                                        N.i32ptr(g.vtable.bounds), n_segs, N.SCHED_OUT_PIXEL_VALUES,
+                                        buf.ctypes.data_as(C.c_void_p))
             if rc == N.VIS_E_UNSUPPORTED:
                 buf = None
             else:
@@ -142,10 +143,87 @@ class Engine:
             g.scheds[key] = buf
         return g.scheds[key]
 
+    # ------------------------------------------------------------------ fused resample (uint8 -> uint8), RGB, <= 16 taps
+    def _resize_sched(self, src_h: int, src_w: int, out_h: int, out_w: int, filt: int, pitch: int, n_segs: int):
+        """(VisSched bytes, hrec, vrec) of the fused uint8 resize for this geometry, or None when it needs the generic
+        passes (> 16 taps, upscaling, width not a multiple of 4, vertical-first order)."""
+        key = ("rs", src_h, src_w, out_h, out_w, filt, pitch, n_segs)
+        hit = self._dev_tables.get(key, False)
+        if hit is not False:
+            return hit
+        hit = None
+        if G.pil_pass_order(src_h, src_w, out_h, out_w) == "hv":
+            ht, vt = T.coeff_table(src_w, out_w, filt), T.coeff_table(src_h, out_h, filt)
+            buf = np.zeros(self.L.vis_sched_sizeof(), np.uint8)
+            rc = self.L.vis_sched_build(src_h, src_w, out_h, out_w, pitch, N.i32ptr(ht.bounds), N.i32ptr(vt.bounds), n_segs,
+                                        N.SCHED_OUT_U8, buf.ctypes.data_as(C.c_void_p))
+            if rc != N.VIS_E_UNSUPPORTED:
+                N.check(rc, "vis_sched_build")
+                rkey = ("rsrec", src_h, src_w, out_h, out_w, filt)
+                recs = self._dev_tables.get(rkey)
+                if recs is None:
+                    kt = int(np.frombuffer(buf[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["kt"])
+                    stride = self.L.vis_record_stride(kt)
+                    recs = []
+                    for t in (ht, vt):
+                        rec = np.zeros((t.out_size + 1, stride), np.int32)
+                        N.check(self.L.vis_sched_pack_records(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, kt, 1,
+                                                              N.i32ptr(rec), rec.size), "vis_sched_pack_records")
+                        recs.append(torch.from_numpy(rec).to(self.device))
+                    self._dev_tables[rkey] = recs
+                hit = (buf, recs[0], recs[1])
+        self._dev_tables[key] = hit
+        return hit
+
+    def resize_batch_u8(self, frames, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS) -> list:
+        """``Image.resize((out_w, out_h), filt)`` of a list of same-shape RGB uint8 HWC CUDA frames: ONE fused launch
+        (both passes) when the geometry allows, else the generic passes frame by frame.  Returns new tensors."""
+        frames = list(frames)
+        if not frames:
+            return []
+        f0 = frames[0]
+        fusable = all(f.dim() == 3 and f.shape == f0.shape and f.shape[2] == 3 and f.stride(2) == 1 and f.stride(1) == 3
+                      and f.stride(0) == f0.stride(0) and f.stride(0) % 16 == 0 and f.data_ptr() % 16 == 0 for f in frames)
+        plan = None
+        if fusable:
+            for f in frames:
+                self._check_u8(f)
+            h, w = int(f0.shape[0]), int(f0.shape[1])
+            head = self._resize_sched(h, w, out_h, out_w, filt, int(f0.stride(0)), 1)
+            if head is not None:
+                per = int(np.frombuffer(head[0][:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["n_strips"])
+                segs = max(1, min(16, -(-2 * self.sm_count // (len(frames) * per))))
+                plan = self._resize_sched(h, w, out_h, out_w, filt, int(f0.stride(0)), segs)
+        if plan is None:
+            outs = []
+            launches = 0
+            for f in frames:
+                outs.append(self.resize_u8(f, out_h, out_w, filt, fused=False))
+                launches += self.last_launches
+            self.last_launches = launches
+            return outs
+        sched, hrec, vrec = plan
+        out = torch.empty((len(frames), out_h, out_w, 3), dtype=torch.uint8, device=self.device)
+        ref = np.zeros(len(frames), N.RESIZE_REF_DTYPE)
+        ref["src"] = [f.data_ptr() for f in frames]
+        ref["dst"] = out.data_ptr() + np.arange(len(frames), dtype=np.uint64) * np.uint64(out.stride(0))
+        d_ref = torch.from_numpy(ref.view(np.uint8).copy()).to(self.device)
+        N.check(self.L.vis_resize_fused_sched(sched.ctypes.data_as(C.c_void_p), d_ref.data_ptr(), len(frames), out_w * 3,
+                                              hrec.data_ptr(), vrec.data_ptr(), _stream_ptr()), "vis_resize_fused_sched")
+        self.last_launches = 1
+        self._keepalive_r = d_ref
+        return list(out.unbind(0))
+
     # ------------------------------------------------------------------ generic resample (uint8 -> uint8)
-    def resize_u8(self, img: torch.Tensor, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS, stream=None) -> torch.Tensor:
-        """``PIL.Image.resize((out_w, out_h), filt, reducing_gap=None)`` for a CUDA uint8 HWC (or HW) tensor."""
+    def resize_u8(self, img: torch.Tensor, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS, stream=None,
+                  fused: bool = True) -> torch.Tensor:
+        """``PIL.Image.resize((out_w, out_h), filt, reducing_gap=None)`` for a CUDA uint8 HWC (or HW) tensor.
+
+        RGB frames whose geometry the fused scheduled kernel takes (<= 16 taps, no upscaling) go through it (one launch,
+        both passes); everything else through the two generic passes (``fused=False`` forces those)."""
         self._check_u8(img)
+        if fused and stream is None and img.dim() == 3 and img.shape[2] == 3:
+            return self.resize_batch_u8([img], out_h, out_w, filt)[0]
         squeeze = img.dim() == 2
         if squeeze:
             img = img.unsqueeze(-1)
