@@ -63,7 +63,7 @@ def read_mask(mask, off, index, ring):
 def replay(s, ht, vt, w, pitch, want_per, want_ring, unit):
     hd = s["head"]
     ring, per, n_subs = int(hd["ring"]), int(hd["per_index"]), int(hd["n_subs"])
-    assert (per, ring) == (want_per, want_ring) and n_subs == (12 if ring == 8 else 9)
+    assert (per, ring) == (want_per, want_ring) and n_subs == (12 if ring == 8 else 11)
     dh, dw = int(hd["dst_h"]), int(hd["dst_w"])
     hlast, _ = sched_ends_and_records(ht, int(hd["kt"]), per)
     vlast, _ = sched_ends_and_records(vt, int(hd["kt"]), per)
@@ -73,7 +73,7 @@ def replay(s, ht, vt, w, pitch, want_per, want_ring, unit):
     for st in range(hd["n_strips"]):
         S = s["strip"][st]
         assert S["x0"] % unit == 0 and S["x1"] % unit == 0 and S["px0"] % 16 == 0 and S["row_bytes"] % 16 == 0
-        assert S["x1"] - S["x0"] <= hd["max_strip_w"] <= 336
+        assert S["x1"] - S["x0"] <= hd["max_strip_w"] <= (336 if ring == 8 else 256)
         assert S["row_bytes"] <= hd["stage_pitch"] and S["px0"] * 3 + S["row_bytes"] <= pitch
         for u in range(n_subs):
             U = s["sub"][st][u]

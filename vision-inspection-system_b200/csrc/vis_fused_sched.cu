@@ -29,6 +29,7 @@ using namespace visf;
 
 namespace visf {   // 16-slot kernel, vis_fused_sched16.cu
 int sched16_subs();
+int sched16_max_strip_w();
 int sched16_layout_bytes(int stage_pitch, int strip_w, int cls);
 int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
                    const float* lut768, float* pixel_values, cudaStream_t st);
@@ -439,6 +440,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     if (!cls) return unsupported("more than 16 taps");
     const int ring = cls <= 8 ? 8 : 16;
     const int n_subs = ring == 8 ? 12 : visf::sched16_subs();
+    const int max_w = ring == 8 ? kMaxStripW : visf::sched16_max_strip_w();
     std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
     int per_index = 1;
     if (!schedule_ends(hb, dst_w, cls, 1, hl) || !schedule_ends(vb, dst_h, cls, 1, vl)) {
@@ -468,7 +470,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const int unit = u8 ? 4 : 28;
     const int blocks = dst_w / unit;
     int n_strips = 0;
-    for (int n = (dst_w + kMaxStripW - 1) / kMaxStripW; n <= VIS_SCHED_MAX_STRIPS && n <= blocks && !n_strips; ++n) {
+    for (int n = (dst_w + max_w - 1) / max_w; n <= VIS_SCHED_MAX_STRIPS && n <= blocks && !n_strips; ++n) {
         int worst_span = 0, worst_w = 0;
         for (int i = 0; i < n; ++i) {
             const int b0 = (int)((int64_t)blocks * i / n), b1 = (int)((int64_t)blocks * (i + 1) / n);
@@ -477,7 +479,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
             worst_span = span > worst_span ? span : worst_span;
             worst_w = (b1 - b0) * unit > worst_w ? (b1 - b0) * unit : worst_w;
         }
-        if (worst_w <= kMaxStripW && layout_bytes(stage_pitch_for(worst_span), worst_w) <= kSmemMax) {
+        if (worst_w <= max_w && layout_bytes(stage_pitch_for(worst_span), worst_w) <= kSmemMax) {
             n_strips = n;
             s.stage_pitch = stage_pitch_for(worst_span);
             s.max_strip_w = worst_w;

@@ -6,8 +6,8 @@
 //   * the agents' LANCZOS thumbnails and resize_image (src/agents/vlm_inspector.py:64, vlm_auditor.py:91,
 //     utils/image_utils.py:75; 4K -> 2048x1152 and 1080p -> 1024x576: 13 taps)                       -> uint8 HWC
 // Differences from the 8-slot kernel:
-//   H  (9 warps)  16 input pixels per step (3 x LDS.128), 16-slot register window, 16-bit step masks.
-//   V  (8 warps)  PULL order: for every output row of the schedule the thread reads its KT tap words straight from
+//   H  (11 warps) 16 input pixels per step (3 x LDS.128), 16-slot register window, 16-bit step masks.
+//   V  (6 warps)  PULL order: for every output row of the schedule the thread reads its KT tap words straight from
 //                 the H ring (the slot holds KT-1 carry rows in front of the 32 fresh rows, copied over from the
 //                 previous chunk by the same thread), so no register ring and ONE emit body (a 16-slot register
 //                 ring would need 16 unrolled bodies of ~150 instructions: far beyond the instruction cache).
@@ -19,11 +19,12 @@ using namespace visf;
 
 namespace {
 
-constexpr int kHWarps = 9, kVWarps = 8, kSWarps = 2;
+constexpr int kHWarps = 11, kVWarps = 6, kSWarps = 2;    // H is the heavy role at these scales (profiles/r01_fused_sched16_4k.txt)
 // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
 constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
 constexpr int kThreads16 = (kHWarps + kVWarps + kSWarps + 1) * 32;      // 640: 96 registers per thread
-constexpr int kChunk = 32, kStepPx = 16, kRing = 16, kMaxStripW = 336;
+constexpr int kChunk = 32, kStepPx = 16, kRing = 16;
+constexpr int kMaxStripW16 = kVWarps * 32 / 3 * 4;                      // 256: one V thread per 4 columns of one channel
 constexpr int kVRecs = kChunk + 1;                // vertical records a chunk can touch (scale >= 1): 32 emits + 1 look-ahead
 constexpr int kSmemMax = 227 * 1024;
 
@@ -396,6 +397,8 @@ int launch16(const VisSched& sc, const void* frames, int n_frames, const Layout1
 namespace visf {
 
 int sched16_subs() { return kHWarps; }
+
+int sched16_max_strip_w() { return kMaxStripW16; }
 
 int sched16_layout_bytes(int stage_pitch, int strip_w, int cls) { return make_layout16(stage_pitch, strip_w, cls).total; }
 
