@@ -58,3 +58,25 @@ def test_draw_bounding_boxes_files(engine, tmp_path):
     assert np.array_equal(cv2.imread(str(dst)), OV.draw_bounding_boxes(frame, boxes))
     with pytest.raises(ValueError, match="Failed to load image"):
         IU.draw_bounding_boxes(tmp_path / "missing.png", boxes, dst)
+
+
+def test_config4_full_size_properties(engine):
+    """BASELINE config 4 at full size (1024 annotated 1080p frames): size-independent properties + oracle on a few."""
+    n, distinct = 1024, 32
+    items = [synth.annotated_frame(7000 + i) for i in range(distinct)]
+    items[5] = (items[5][0], [])                                             # a frame without boxes: plain copy
+    frames = torch.from_numpy(np.stack([f for f, _ in items])).cuda().repeat(n // distinct, 1, 1, 1).contiguous()
+    boxes = [items[i % distinct][1] for i in range(n)]
+    out = engine.annotate(frames, boxes)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out[:distinct].repeat(n // distinct, 1, 1, 1))   # replicas identical
+    assert torch.equal(out[5], frames[5])                                    # no boxes -> untouched copy
+    for i in (0, 7, 31):
+        assert np.array_equal(out[i].cpu().numpy(), OV.draw_bounding_boxes(*items[i])), i
+    again = engine.annotate(out, [[] for _ in range(n)])                     # drawing nothing is the identity
+    assert torch.equal(again, out)
+    work = frames.clone()
+    engine.annotate(work, boxes, inplace=True)                               # in place == out of place
+    assert torch.equal(work, out)
+    changed = (out[:distinct] != frames[:distinct]).any(3).sum().item()
+    assert 0 < changed < 0.06 * distinct * 1080 * 1920                       # overlays touch a few percent of the pixels

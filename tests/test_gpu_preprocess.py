@@ -133,6 +133,30 @@ def test_full_size_batch_properties(engine):
         assert torch.isin(v[::97, c].reshape(-1), lut[:, c]).all()
 
 
+def test_full_size_4k_batch_properties(engine):
+    """BASELINE config 3 (4K frames at the Qwen2-VL hub max_pixels, one GPU's shard): properties + oracle on two frames."""
+    n = 16
+    base = synth.frames_4k(2)
+    batch = torch.from_numpy(base).cuda().repeat(n // 2, 1, 1, 1)
+    pv, grid = engine.preprocess(batch, max_pixels=G.HUB_MAX_PIXELS)
+    torch.cuda.synchronize()
+    rows = (2156 // 14) * (3836 // 14)
+    assert pv.shape == (n * rows, 1176) and (grid == torch.tensor([1, 154, 274])).all()
+    got = pv.view(n, rows, 1176)
+    assert torch.equal(got, got[:2].repeat(n // 2, 1, 1))                                    # replicas identical
+    want, _ = Q.preprocess([base[0]], max_pixels=G.HUB_MAX_PIXELS)
+    assert torch.equal(got[0].cpu(), torch.from_numpy(want))
+    v = pv.view(-1, 3, 2, 14, 14)
+    assert torch.equal(v[:, :, 0], v[:, :, 1])                                               # temporal duplicate
+    # default max_pixels on the same frames: the 16-slot kernel (13 taps)
+    pv2, grid2 = engine.preprocess(batch)
+    want2, wgrid2 = Q.preprocess([base[1]])
+    assert (grid2 == torch.tensor(wgrid2[0])).all()
+    r2 = want2.shape[0]
+    assert torch.equal(pv2.view(n, r2, 1176)[1].cpu(), torch.from_numpy(want2))
+    assert torch.equal(pv2.view(n, r2, 1176), pv2.view(n, r2, 1176)[:2].repeat(n // 2, 1, 1))
+
+
 def test_constant_and_extreme_frames(engine):
     lut = Q.normalize_lut().reshape(256, 3)
     for value in (0, 255, 128):
