@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 6
+#define VIS_B200_ABI_VERSION 7
 
 /* status codes */
 #define VIS_OK            0
@@ -259,6 +259,27 @@ typedef struct VisQualityFrame {
 } VisQualityFrame;
 int vis_quality_stats(const VisQualityFrame* frames, int n_frames, int max_h, int max_w,
                       int64_t* sums, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Defect heat-map overlay (SURVEY.md 8f "next" row).  Replaces the array work of create_heatmap_overlay
+ * (utils/image_utils.py:364-601): per-defect Gaussian heat with boosts, cv2.GaussianBlur of each defect region and
+ * of the whole mask (float32, BORDER_REFLECT_101), max-composite, normalisation by the global maximum,
+ * cv2.applyColorMap(COLORMAP_JET) and cv2.addWeighted(img, 0.6, colour, 0.4, 0).  Floating point: specified with a
+ * tolerance (<= 2 levels where the 8-bit heat index flips), not bit-exact.
+ * defects: HOST array in list order (the host mirror of the reference's per-defect scalar code fills it);
+ * kernels: DEVICE float32 Gaussian kernels (cv2.getGaussianKernel values), indexed by koff; jet768: DEVICE BGR table;
+ * scratch: DEVICE, (3*h*w + 1) floats; img / dst: DEVICE BGR uint8 HWC (dst may not alias img).      [device] */
+typedef struct VisHeatDefect {
+    int32_t kind;                    /* 0: box defect, 1: widespread (whole image, no blur)                      */
+    int32_t x, y, w, h;              /* pixel box                                                                 */
+    int32_t x1, y1, x2, y2;          /* region [x1,x2) x [y1,y2) the defect is evaluated and blurred on           */
+    int32_t ksize, koff, pad;        /* odd blur kernel size (1 = none) and its offset in kernels[]              */
+    double  intensity, cx, cy, sigma;
+} VisHeatDefect;
+int vis_heatmap_overlay(const uint8_t* img, int64_t img_pitch, int h, int w,
+                        const VisHeatDefect* defects, int n_defects, const float* kernels,
+                        int final_ksize, int final_koff, const uint8_t* jet768,
+                        float* scratch, uint8_t* dst, int64_t dst_pitch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,8 @@ What is recorded (versions of every binary are stored next to the vectors):
   * ``overlay``    the reference's own ``utils.image_utils.draw_bounding_boxes`` executed unmodified, with
                    ``cv2.imread`` / ``cv2.imwrite`` intercepted so the BGR array it holds right before the
                    JPEG encode is captured — sha256 + changed-pixel count.
+  * ``heatmap``    the reference's own ``utils.image_utils.create_heatmap_overlay`` executed unmodified (imread / imwrite
+                   intercepted): the BGR array before the JPEG encode, stored in arrays.npz (tolerance-compared).
   * ``quality``    the reference's own ``src.safety.image_quality.assess_image_quality`` on lossless PNG files of seeded
                    frames — the full result dict.
 The reference has no tests or vectors of its own for this path; these fixtures are the pin.
@@ -121,7 +123,40 @@ def quality_goldens():
     return out
 
 
+def heatmap_goldens(arrays: dict):
+    """The reference's own create_heatmap_overlay (utils/image_utils.py:320-604), cv2.imread / imwrite intercepted; the
+    BGR array it hands to imwrite is stored (subsampled for the 1080p case) in arrays.npz as heatmap_<name>."""
+    ref = import_reference_image_utils()
+    captured = {}
+    real_imread, real_imwrite = ref.cv2.imread, ref.cv2.imwrite
+    out = []
+    for name, frame, defects, step in synth.heatmap_cases():
+        captured["input"] = frame
+        ref.cv2.imread = lambda path, *a: captured["input"].copy()
+        ref.cv2.imwrite = lambda path, img, *a: captured.__setitem__("output", img.copy()) or True
+        try:
+            ref.create_heatmap_overlay(Path("in.png"), defects, Path("heat.jpg"))
+        finally:
+            ref.cv2.imread, ref.cv2.imwrite = real_imread, real_imwrite
+        res = captured["output"]
+        arrays[f"heatmap_{name}"] = res[::step, ::step].copy()
+        out.append({"name": name, "shape": list(frame.shape[:2]), "input_sha256": sha(frame), "n_defects": len(defects),
+                    "subsample": step, "full_sha256": sha(res)})
+        print("heatmap", name, sha(res)[:16], int((res != frame).any(2).sum()))
+    return out
+
+
 def main():
+    if "--only-heatmap" in sys.argv:                    # add / refresh the "heatmap" section of existing files
+        out = json.loads((HERE / "goldens.json").read_text())
+        arrays = dict(np.load(HERE / "arrays.npz"))
+        out["heatmap"] = heatmap_goldens(arrays)
+        import cv2
+        arrays["jet_bgr"] = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)[0]
+        np.savez_compressed(HERE / "arrays.npz", **arrays)
+        (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
+        print("updated", HERE / "goldens.json", HERE / "arrays.npz")
+        return
     if "--only-quality" in sys.argv:                    # add / refresh the "quality" section of an existing file
         out = json.loads((HERE / "goldens.json").read_text())
         out["quality"] = quality_goldens()
@@ -240,6 +275,8 @@ def main():
                                "changed_pixels": int((res != frame).any(2).sum())})
         print("overlay", name, sha(res)[:16], out["overlay"][-1]["changed_pixels"])
 
+    out["heatmap"] = heatmap_goldens(arrays)
+    arrays["jet_bgr"] = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)[0]
     np.savez_compressed(HERE / "arrays.npz", **arrays)
     out["quality"] = quality_goldens()
     (HERE / "goldens.json").write_text(json.dumps(out, indent=1))

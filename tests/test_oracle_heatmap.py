@@ -1,0 +1,74 @@
+"""The heat-map oracle (numpy restatement of create_heatmap_overlay + GaussianBlur / JET / addWeighted) against the
+arrays captured from the reference's own function, and the host half of the product (per-defect parameters, kernels).
+
+TOLERANCE (floating point path): cv2's separable float32 filter sums in a SIMD-dependent order, so a
+restatement is within MAX_LEVELS of the reference output, with at least MIN_EQUAL of the bytes identical (the
+differing bytes are isolated pixels where the 8-bit heat index flips by one: up to 4 JET levels * 0.4)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import heatmap as OH
+from vision_inspection_system_b200 import heatmap as H
+from vision_inspection_system_b200 import synth
+
+MAX_LEVELS = 2
+MIN_EQUAL = 0.995
+
+
+def close_enough(got: np.ndarray, want: np.ndarray, what):
+    assert got.shape == want.shape and got.dtype == np.uint8, what
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert int(diff.max()) <= MAX_LEVELS, (what, int(diff.max()))
+    assert float((diff == 0).mean()) >= MIN_EQUAL, (what, float((diff == 0).mean()))
+
+
+def test_jet_table_matches_the_captured_one(arrays):
+    assert np.array_equal(H.JET_BGR, arrays["jet_bgr"])
+    cv2 = pytest.importorskip("cv2")
+    assert np.array_equal(H.JET_BGR, cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)[0])
+
+
+def test_gaussian_kernels_match_cv2():
+    cv2 = pytest.importorskip("cv2")
+    for ksize, sigma in ((51, 16.0), (31, 10.8), (31, 4.8), (13, 2.0), (25, 4.0), (7, 1.0), (49, 8.0), (3, 0.5)):
+        assert np.array_equal(H.gaussian_kernel(ksize, sigma), cv2.getGaussianKernel(ksize, sigma, cv2.CV_32F).ravel())
+        assert np.array_equal(OH.gaussian_kernel(ksize, sigma), H.gaussian_kernel(ksize, sigma))
+    rng = np.random.default_rng(1)
+    a = rng.random((97, 131), dtype=np.float32)
+    for ksize, sigma in ((31, 4.8), (51, 16.0), (5, 1.0)):
+        assert np.abs(OH.gaussian_blur(a, ksize, sigma) - cv2.GaussianBlur(a, (ksize, ksize), sigma)).max() < 2e-6
+
+
+def test_oracle_within_tolerance_of_the_reference(goldens, arrays):
+    cases = {name: (frame, defects, step) for name, frame, defects, step in synth.heatmap_cases()}
+    assert len(goldens["heatmap"]) == len(cases)
+    for rec in goldens["heatmap"]:
+        frame, defects, step = cases[rec["name"]]
+        assert hashlib.sha256(np.ascontiguousarray(frame).tobytes()).hexdigest() == rec["input_sha256"], rec["name"]
+        got = OH.create_heatmap_overlay(frame, defects, H.JET_BGR)
+        close_enough(got[::step, ::step], arrays[f"heatmap_{rec['name']}"], rec["name"])
+
+
+def test_host_defect_parameters():
+    """defect_params (product host code) against the oracle's scalar code path on the golden cases: same defects kept,
+    same regions and kernel sizes."""
+    for name, frame, defects, _ in synth.heatmap_cases():
+        h, w = frame.shape[:2]
+        recs, kern, had = H.defect_params(defects, w, h)
+        assert had == bool(defects)
+        heat, _ = OH.heat_mask(defects, w, h)
+        touched = np.zeros((h, w), bool)
+        for r in recs:
+            assert 0 <= r["x1"] < r["x2"] <= w and 0 <= r["y1"] < r["y2"] <= h and r["ksize"] % 2 == 1 and r["ksize"] <= 51
+            touched[r["y1"]:r["y2"], r["x1"]:r["x2"]] = True
+        fk, fkern = H.final_blur(w, h)
+        grow = fk // 2 + 1
+        ys, xs = np.nonzero(heat > 1e-6)
+        if len(ys):                                       # every heated pixel lies inside a region (+ the final blur radius)
+            ok = np.zeros((h, w), bool)
+            for r in recs:
+                ok[max(0, r["y1"] - grow):r["y2"] + grow, max(0, r["x1"] - grow):r["x2"] + grow] = True
+            assert ok[ys, xs].all(), name
+        assert abs(float(fkern.sum()) - 1.0) < 1e-6 and fk == len(fkern)

@@ -541,6 +541,37 @@ class Engine:
         self._keepalive = (d_desc, d_leaves, d_tiles, d_refs)
         return result
 
+    # ------------------------------------------------------------------ defect heat-map overlay
+    def heatmap(self, frame: torch.Tensor, defects: list) -> torch.Tensor:
+        """``create_heatmap_overlay`` for one BGR uint8 HWC CUDA frame and the reference's defect dicts (percent boxes,
+        ``safety_impact``, ``confidence``, ``location``): returns the blended BGR frame (a copy when ``defects`` is
+        empty, like the reference).  Tolerance-specified (float32 blur), see vis_heatmap.cu."""
+        from . import heatmap as H
+        self._check_u8(frame)
+        if frame.dim() != 3 or frame.shape[2] != 3 or frame.stride(2) != 1 or frame.stride(1) != 3:
+            raise ValueError("frame must be [H, W, 3] uint8 with contiguous pixels")
+        h, w = int(frame.shape[0]), int(frame.shape[1])
+        recs, kern, had = H.defect_params(defects, w, h)
+        if not had:
+            self.last_launches = 0
+            return frame.clone()
+        fk, fkern = H.final_blur(w, h)
+        kernels = np.concatenate([kern, fkern]).astype(np.float32)
+        d_kern = torch.from_numpy(kernels).to(self.device)
+        if not hasattr(self, "_jet"):
+            self._jet = torch.from_numpy(H.JET_BGR.copy()).to(self.device)
+        scratch = torch.empty(3 * h * w + 4, dtype=torch.float32, device=self.device)
+        out = torch.empty_like(frame, memory_format=torch.contiguous_format)
+        recs = np.ascontiguousarray(recs)
+        N.check(self.L.vis_heatmap_overlay(frame.data_ptr(), frame.stride(0), h, w,
+                                           recs.ctypes.data_as(C.c_void_p) if len(recs) else None, len(recs),
+                                           d_kern.data_ptr(), fk, len(kern), self._jet.data_ptr(), scratch.data_ptr(),
+                                           out.data_ptr(), out.stride(0), _stream_ptr()), "vis_heatmap_overlay")
+        n_box = int((recs["kind"] == 0).sum() - ((recs["kind"] == 0) & (recs["ksize"] == 1)).sum()) if len(recs) else 0
+        self.last_launches = 1 + len(recs) + 2 * n_box + (2 if fk > 1 else 0) + 2
+        self._keepalive_h = (d_kern, scratch)
+        return out
+
     # ------------------------------------------------------------------ image quality statistics
     def quality_stats(self, frames):
         """BGR uint8 HWC CUDA frames (``[B,H,W,3]`` tensor or list) -> (int64 CUDA tensor [B, 3] = sum(gray),

@@ -7,6 +7,8 @@ Same names, arguments, return types and error behaviour as the reference:
     draw_bounding_boxes(image_path, boxes, output_path,
                         confidence_threshold="low",
                         criticality="medium") -> Path           utils/image_utils.py:148-317
+    create_heatmap_overlay(image_path, defects, output_path,
+                           alpha=0.4, ...) -> Path              utils/image_utils.py:320-604  (tolerance-specified)
 
 plus the entry points the reference delegates to a remote server today (the Qwen2-VL image processor behind
 ``_encode_image_optimized``, src/agents/vlm_inspector.py:46-88 / src/agents/vlm_auditor.py:85-108):
@@ -165,4 +167,24 @@ def draw_bounding_boxes(image_path: Path, boxes: list, output_path: Path, confid
     dev = torch.from_numpy(img).cuda()
     _engine().annotate([dev], [boxes], confidence_threshold, criticality, inplace=True)
     cv2.imwrite(str(output_path), dev.cpu().numpy())
+    return output_path
+
+
+def create_heatmap_overlay(image_path: Path, defects: list, output_path: Path, alpha: float = 0.4,
+                           actual_model_size=None, confidence_threshold: str = "low",
+                           criticality: str = "medium") -> Path:
+    """Semi-transparent JET heat map over the defect regions, saved at ``output_path`` (utils/image_utils.py:320-604).
+
+    As in the reference, ``alpha``, ``actual_model_size``, ``confidence_threshold`` and ``criticality`` are accepted and
+    unused: every defect is drawn and the blend is fixed at 60 % image / 40 % heat map.  Raises
+    ``ValueError("Failed to load image: ...")`` when the file cannot be read.
+    """
+    import cv2
+    import torch
+    logger.info("Creating heatmap overlay for %s", Path(image_path).name)
+    img = cv2.imread(str(image_path))
+    if img is None:
+        raise ValueError(f"Failed to load image: {image_path}")
+    out = _engine().heatmap(torch.from_numpy(img).cuda(), defects)
+    cv2.imwrite(str(output_path), out.cpu().numpy())
     return output_path

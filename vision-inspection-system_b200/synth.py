@@ -72,3 +72,41 @@ def mixed_resolution_shapes(n: int, seed: int = 9000) -> list:
     """Config 5: per-frame (h, w) drawn uniformly from MIXED_RESOLUTIONS."""
     rng = np.random.default_rng(seed)
     return [MIXED_RESOLUTIONS[int(i)] for i in rng.integers(0, len(MIXED_RESOLUTIONS), n)]
+
+
+def random_defects(rng: np.random.Generator, k: int) -> list:
+    """k defect dicts as src/reporting/pdf_generator.py:1262-1279 hands them to create_heatmap_overlay."""
+    sev = ["CRITICAL", "MODERATE", "COSMETIC", "MINOR"]
+    conf = ["high", "medium", "low"]
+    out = []
+    for b in random_boxes(rng, k):
+        out.append({"type": "crack", "bbox": {"x": b["x"], "y": b["y"], "width": b["width"], "height": b["height"]},
+                    "safety_impact": sev[int(rng.integers(0, 4))], "confidence": conf[int(rng.integers(0, 3))],
+                    "location": "surface"})
+    return out
+
+
+
+def heatmap_cases() -> list:
+    """(name, BGR frame, defect list, subsample step) of the heat-map goldens (tests/golden, section "heatmap")."""
+    small, vga = pattern_frames(360, 480), pattern_frames(480, 640)
+    widespread = {"type": "corrosion", "bbox": None, "safety_impact": "MODERATE", "confidence": "medium",
+                  "location": "Entire surface of the panel"}
+    invalid = [{"type": "x", "bbox": {"x": 90, "y": 10, "width": 30, "height": 10}, "safety_impact": "CRITICAL", "confidence": "high"},
+               {"type": "y", "bbox": {"x": 10, "y": 10, "width": 0.1, "height": 0.1}, "safety_impact": "MINOR", "confidence": "low"},
+               {"type": "z", "bbox": {}, "safety_impact": "MINOR", "confidence": "low"}]
+    return [
+        ("hgrad_360x480_3", small["hgrad"], random_defects(np.random.default_rng(8000), 3), 1),
+        ("vgrad_480x640_5", vga["vgrad"], random_defects(np.random.default_rng(8001), 5) + invalid[:1], 1),
+        ("checker_360x480_widespread", small["checker"], [widespread] + random_defects(np.random.default_rng(8002), 1), 1),
+        ("noise_1080p_4", noise_frame(8003, 1080, 1920), random_defects(np.random.default_rng(8003), 4), 8),
+        ("zeros_360x480_critical_high", small["zeros"],
+         [{"type": "crack", "bbox": {"x": 40, "y": 40, "width": 20, "height": 20}, "safety_impact": "CRITICAL",
+           "confidence": "high", "location": "centre"},
+          {"type": "edge", "bbox": {"x": 0, "y": 0, "width": 8, "height": 6}, "safety_impact": "COSMETIC",
+           "confidence": "low", "location": "corner"},
+          {"type": "edge2", "bbox": {"x": 92, "y": 90, "width": 8, "height": 10}, "safety_impact": "UNKNOWN",
+           "confidence": "unsure", "location": "corner"}], 1),
+        ("full_360x480_all_invalid", small["full"], invalid, 1),
+        ("hgrad_360x480_empty", small["hgrad"], [], 1),
+    ]
