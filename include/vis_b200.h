@@ -153,7 +153,7 @@ typedef struct VisSched {            /* opaque to callers: filled by vis_sched_b
     int32_t ring;                    /* register window of the kernel: 8 (<= 8 taps) or 16 (<= 16 taps)            */
     int32_t n_subs;                  /* column sub-ranges per strip = horizontal-pass warps (12 / 9)               */
     int32_t out_mode;                /* VIS_SCHED_OUT_PIXEL_VALUES or VIS_SCHED_OUT_U8                              */
-    int32_t reserved;
+    int32_t h_pull;                  /* 1: 17..32 taps, the horizontal role pulls its window (no step masks)        */
     VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
     VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_SUBS];
     VisSchedSeg   seg[VIS_SCHED_MAX_SEGS];

@@ -62,7 +62,7 @@ def test_fused_path_is_taken_for_the_benchmark_geometry(engine):
     ((720, 1280), G.DEFAULT_MAX_PIXELS), ((480, 640), G.DEFAULT_MAX_PIXELS), ((1536, 2048), G.DEFAULT_MAX_PIXELS),
     ((1152, 2048), G.DEFAULT_MAX_PIXELS), ((576, 1024), G.DEFAULT_MAX_PIXELS), ((100, 502), G.DEFAULT_MAX_PIXELS),
     ((64, 96), G.DEFAULT_MAX_PIXELS), ((28, 5600), G.DEFAULT_MAX_PIXELS), ((3000, 20), G.DEFAULT_MAX_PIXELS),
-    ((2048, 1536), G.DEFAULT_MAX_PIXELS), ((1080, 1920), 400000), ((1200, 1600), G.DEFAULT_MAX_PIXELS), ((600, 5000), G.DEFAULT_MAX_PIXELS),
+    ((2048, 1536), G.DEFAULT_MAX_PIXELS), ((1080, 1920), 400000), ((2160, 3840), 250000), ((3100, 5500), G.DEFAULT_MAX_PIXELS), ((1200, 1600), G.DEFAULT_MAX_PIXELS), ((600, 5000), G.DEFAULT_MAX_PIXELS),
     ((1, 1), G.DEFAULT_MAX_PIXELS), ((2160, 3840), G.HUB_MAX_PIXELS)])
 def test_against_oracle(engine, shape, max_pixels):
     frame = synth.noise_frame(hash(shape) % 1000, *shape)
@@ -81,12 +81,20 @@ def test_padded_pitch_and_unaligned_views(engine):
     padded[:, :640] = torch.from_numpy(base).cuda()
     pv, _ = engine.preprocess([padded[:, :640]])
     check_equal(pv.cpu().numpy(), want, "padded pitch (fused)")
-    odd = torch.zeros((300, 641, 3), dtype=torch.uint8, device="cuda")             # pitch 1923: generic path
+    odd = torch.zeros((300, 641, 3), dtype=torch.uint8, device="cuda")             # pitch 1923: not bulk-copyable
     odd[:, :640] = torch.from_numpy(base).cuda()
     plan = engine.plan_batch([odd[:, :640]])
-    assert plan.generic and not plan.fused
-    pv, _ = engine.preprocess([odd[:, :640]])
+    assert plan.generic and not plan.fused                                          # as submitted: generic passes
+    pv, _ = engine.preprocess([odd[:, :640]], force_generic=True)
     check_equal(pv.cpu().numpy(), want, "unaligned pitch (generic)")
+    pv, _ = engine.preprocess([odd[:, :640]])                                       # default: repacked, fused kernel
+    assert engine.last_launches == 1
+    check_equal(pv.cpu().numpy(), want, "unaligned pitch (repacked)")
+    mouri_like = [synth.noise_frame(80 + i, 100, 502) for i in range(3)]            # 1506-byte rows (BASELINE config 1 shape)
+    wantm, _ = Q.preprocess(mouri_like)
+    pv, _ = engine.preprocess([torch.from_numpy(f).cuda() for f in mouri_like])
+    assert engine.last_launches == 1
+    check_equal(pv.cpu().numpy(), wantm, "502-pixel rows (repacked)")
 
 
 def test_mixed_resolution_batch(engine):

@@ -64,9 +64,13 @@ def test_fused_thumbnail_path_and_batches(engine):
     got = engine.resize_u8(torch.from_numpy(big).cuda(), 1152, 2048, Q.LANCZOS)
     assert engine.last_launches == 1
     assert np.array_equal(got.cpu().numpy(), Q.resize(big, 1152, 2048, Q.LANCZOS))
-    got = engine.resize_u8(torch.from_numpy(big).cuda(), 576, 1024, Q.LANCZOS)          # 25 taps: generic passes
-    assert engine.last_launches == 2
+    got = engine.resize_u8(torch.from_numpy(big).cuda(), 576, 1024, Q.LANCZOS)          # 25 taps: pull-order H role
+    assert engine.last_launches == 1
     assert np.array_equal(got.cpu().numpy(), Q.resize(big, 576, 1024, Q.LANCZOS))
+    for out_hw in ((864, 1536), (432, 768), (270, 480)):                                 # 17, 31 taps: fused; 49 taps: generic
+        got = engine.resize_u8(torch.from_numpy(big).cuda(), out_hw[0], out_hw[1], Q.LANCZOS)
+        assert engine.last_launches == (2 if out_hw[0] == 270 else 1), out_hw
+        assert np.array_equal(got.cpu().numpy(), Q.resize(big, out_hw[0], out_hw[1], Q.LANCZOS)), out_hw
     for out_hw in ((683, 1024), (700, 1000), (1023, 1366), (540, 958)):                  # segments ending inside a band, odd widths
         a = synth.noise_frame(34, 1365, 2048)
         got = engine.resize_u8(torch.from_numpy(a).cuda(), out_hw[0], out_hw[1], Q.LANCZOS)

@@ -70,14 +70,25 @@ def replay(s, ht, vt, w, pitch, want_per, want_ring, unit):
     # horizontal: every output column of every strip is emitted exactly once, at the pixel where its window ends,
     # after all of its taps have been read (p0 <= first tap), and the staged row segment covers the window
     covered = np.zeros(dw, np.int32)
+    h_pull = int(hd["h_pull"])
+    assert h_pull == (1 if hd["kt"] > 16 else 0)
+    if h_pull:                                            # pull-order H: no step masks, only the sub-range edges
+        covered[:] = 1
     for st in range(hd["n_strips"]):
         S = s["strip"][st]
         assert S["x0"] % unit == 0 and S["x1"] % unit == 0 and S["px0"] % 16 == 0 and S["row_bytes"] % 16 == 0
         assert S["x1"] - S["x0"] <= hd["max_strip_w"] <= (336 if ring == 8 else 256)
         assert S["row_bytes"] <= hd["stage_pitch"] and S["px0"] * 3 + S["row_bytes"] <= pitch
+        assert [int(s["sub"][st][u]["xa"]) for u in range(1, n_subs)] == [int(s["sub"][st][u]["xb"]) for u in range(n_subs - 1)]
+        assert s["sub"][st][0]["xa"] == S["x0"] and s["sub"][st][n_subs - 1]["xb"] == S["x1"]
         for u in range(n_subs):
             U = s["sub"][st][u]
             xo = int(U["xa"])
+            if h_pull:
+                assert U["nsteps"] == 0
+                for x in range(int(U["xa"]), int(U["xb"])):      # the pulled window stays inside the staged row (+ pad in front)
+                    assert (hlast[x] - (int(hd["kt"]) - 1) - S["px0"]) * 3 >= -128
+                continue
             assert U["p0"] % ring == 0 and U["p0"] >= S["px0"] and U["p0"] <= ht.bounds[xo, 0]
             for i in range(U["nsteps"]):
                 m1, m2 = read_mask(s["mask"], U["mask_off"], i, ring)
@@ -122,7 +133,8 @@ def replay(s, ht, vt, w, pitch, want_per, want_ring, unit):
     ((1536, 2048), 8, G.DEFAULT_MAX_PIXELS, 1, 8), ((1152, 2048), 1, G.DEFAULT_MAX_PIXELS, 1, 8), ((2048, 1536), 4, G.DEFAULT_MAX_PIXELS, 1, 8),
     ((600, 5000), 2, G.DEFAULT_MAX_PIXELS, 1, 8), ((1080, 1920), 2, G.HUB_MAX_PIXELS, 2, 8), ((720, 1280), 1, G.DEFAULT_MAX_PIXELS, 2, 8),
     ((480, 640), 3, G.DEFAULT_MAX_PIXELS, 2, 8), ((560, 1000), 1, G.DEFAULT_MAX_PIXELS, 2, 8),
-    ((2160, 3840), 1, G.DEFAULT_MAX_PIXELS, 1, 16), ((2160, 3840), 16, G.DEFAULT_MAX_PIXELS, 1, 16), ((1080, 1920), 2, 250000, 1, 16)])
+    ((2160, 3840), 1, G.DEFAULT_MAX_PIXELS, 1, 16), ((2160, 3840), 16, G.DEFAULT_MAX_PIXELS, 1, 16), ((1080, 1920), 2, 250000, 1, 16),
+    ((2160, 3840), 2, 250000, 1, 16), ((3100, 5500), 1, G.DEFAULT_MAX_PIXELS, 1, 16)])
 def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels, want_per, want_ring):
     h, w = shape
     dh, dw = G.smart_resize(h, w, G.FACTOR, G.DEFAULT_MIN_PIXELS, max_pixels)
@@ -131,13 +143,15 @@ def test_schedule_replays_the_tap_windows(shape, vsplit, max_pixels, want_per, w
     assert rc == N.VIS_OK, N.lib().vis_last_error()
     hd = s["head"]
     want_kt = max(ht.max_taps, vt.max_taps)
-    assert (hd["dst_h"], hd["dst_w"]) == (dh, dw) and hd["kt"] == (T.kt_class(want_kt) if want_ring == 8 else (12 if want_kt <= 12 else 16))
+    assert (hd["dst_h"], hd["dst_w"]) == (dh, dw) and hd["kt"] == (T.kt_class(want_kt) if want_ring == 8 else (12 if want_kt <= 12 else 16 if want_kt <= 16 else 24 if want_kt <= 24 else 32))
     replay(s, ht, vt, w, pitch, want_per, want_ring, 28)
 
 
 @pytest.mark.parametrize("shape,out,vsplit", [((2160, 3840), (1152, 2048), 1), ((1080, 1920), (576, 1024), 5),
                                               ((1600, 1200), (1024, 768), 2), ((1536, 2048), (768, 1024), 16),
-                                              ((300, 500), (153, 256), 1), ((1365, 2048), (683, 1024), 3)])
+                                              ((300, 500), (153, 256), 1), ((1365, 2048), (683, 1024), 3),
+                                              ((2160, 3840), (576, 1024), 4), ((2160, 3840), (864, 1536), 1),
+                                              ((3000, 4000), (768, 1024), 2), ((1080, 1920), (360, 640), 1)])
 def test_uint8_resize_schedule(shape, out, vsplit):
     """VIS_SCHED_OUT_U8 (LANCZOS thumbnails / resize_image): 16-slot kernel, strips in units of 4 columns, last segment
     ends at dst_h."""
@@ -145,11 +159,12 @@ def test_uint8_resize_schedule(shape, out, vsplit):
     pitch = (w * 3 + 15) // 16 * 16
     rc, s, ht, vt = build(h, w, dh, dw, pitch, vsplit, N.FILTER_LANCZOS, N.SCHED_OUT_U8)
     assert rc == N.VIS_OK, N.lib().vis_last_error()
-    assert s["head"]["out_mode"] == N.SCHED_OUT_U8 and s["head"]["kt"] in (12, 16)
+    want_kt = max(ht.max_taps, vt.max_taps)
+    assert s["head"]["out_mode"] == N.SCHED_OUT_U8 and s["head"]["kt"] == max(12, (want_kt + 3) // 4 * 4)
     replay(s, ht, vt, w, pitch, 1, 16, 4)
 
 
-@pytest.mark.parametrize("shape,max_pixels,why", [((20, 30), G.DEFAULT_MAX_PIXELS, b"upscale"), ((3100, 5500), G.DEFAULT_MAX_PIXELS, b"taps"),
+@pytest.mark.parametrize("shape,max_pixels,why", [((20, 30), G.DEFAULT_MAX_PIXELS, b"upscale"), ((7000, 10000), G.DEFAULT_MAX_PIXELS, b"taps"),
                                                   ((100, 502), G.DEFAULT_MAX_PIXELS, b"pitch")])
 def test_schedule_declines_what_it_cannot_express(shape, max_pixels, why):
     h, w = shape

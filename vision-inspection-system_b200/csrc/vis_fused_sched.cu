@@ -436,9 +436,12 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const int hkt = vis_max_taps(hb, dst_w), vkt = vis_max_taps(vb, dst_h);
     const int mk = hkt > vkt ? hkt : vkt;
     // tap class -> kernel: <= 8 taps: 8-slot register windows (pixel_values only); <= 16 taps: 16-slot kernel
-    const int cls = u8 ? (mk <= 12 ? 12 : mk <= 16 ? 16 : 0) : (mk <= 6 ? 6 : mk <= 8 ? 8 : mk <= 12 ? 12 : mk <= 16 ? 16 : 0);
-    if (!cls) return unsupported("more than 16 taps");
+    // and, past 16 taps, the same kernel with a pull-order horizontal role (classes 20/24/28/32; 24/32 for pixel_values)
+    int cls = mk <= 12 ? 12 : mk <= 16 ? 16 : mk <= 20 ? 20 : mk <= 24 ? 24 : mk <= 28 ? 28 : mk <= 32 ? 32 : 0;
+    if (!u8) cls = mk <= 6 ? 6 : mk <= 8 ? 8 : cls == 20 ? 24 : cls == 28 ? 32 : cls;
+    if (!cls) return unsupported("more than 32 taps");
     const int ring = cls <= 8 ? 8 : 16;
+    const bool h_pull = cls > 16;
     const int n_subs = ring == 8 ? 12 : visf::sched16_subs();
     const int max_w = ring == 8 ? kMaxStripW : visf::sched16_max_strip_w();
     std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
@@ -453,7 +456,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     VisSched& s = *out;
     std::memset(&s, 0, sizeof(s));
     s.src_h = src_h; s.src_w = src_w; s.dst_h = dst_h; s.dst_w = dst_w; s.src_pitch = src_pitch; s.kt = cls;
-    s.per_index = per_index; s.ring = ring; s.n_subs = n_subs; s.out_mode = out_mode;
+    s.per_index = per_index; s.ring = ring; s.n_subs = n_subs; s.out_mode = out_mode; s.h_pull = h_pull ? 1 : 0;
     const int stride = vis_record_stride(cls);
     auto last = [](const int32_t* b, int i) { return b[2 * i] + b[2 * i + 1] - 1; };
     auto span_of = [&](int x0, int x1, int* px0) {
@@ -505,7 +508,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
             VisSchedSub& U = s.sub[i][u];
             const int xa = S.x0 + (int)((int64_t)sw * u / n_subs), xb = S.x0 + (int)((int64_t)sw * (u + 1) / n_subs);
             U.xa = (uint16_t)xa; U.xb = (uint16_t)xb;
-            if (xa >= xb) continue;                                    // nsteps = 0
+            if (xa >= xb || h_pull) continue;                          // nsteps = 0: nothing to walk (pull order needs no masks)
             const int p0 = hb[2 * xa] & ~(step - 1);
             const int nsteps = (hl[xb - 1] - p0) / step + 1;
             if (!mask_room(2 * mbytes * nsteps) || nsteps > 65535) return unsupported("schedule too large");
@@ -538,7 +541,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
 
 int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt, int per_index,
                            int32_t* rec, int64_t rec_capacity) {
-    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8 && kt != 12 && kt != 16) ||
+    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8 && (kt < 12 || kt > 32 || kt % 4)) ||
         per_index < 1 || per_index > 2) {
         vis::set_error("vis_sched_pack_records: bad arguments");
         return VIS_E_INVALID;

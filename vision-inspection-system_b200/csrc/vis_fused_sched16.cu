@@ -11,6 +11,10 @@
 //                 the H ring (the slot holds KT-1 carry rows in front of the 32 fresh rows, copied over from the
 //                 previous chunk by the same thread), so no register ring and ONE emit body (a 16-slot register
 //                 ring would need 16 unrolled bodies of ~150 instructions: far beyond the instruction cache).
+//   Windows of 17..32 taps (4K -> 1024 LANCZOS thumbnails: 25) keep the same V / store roles; their H role PULLS: for
+//   every output column the lane (= input row) reads the window's bytes from the staged row with 32-bit loads at the
+//   window's (uniform) alignment and multiplies them by the record — no register window, 2x the instructions per MAC of
+//   the push scheme, still far ahead of the generic per-pixel pass.
 //   store (2 warps) pixel_values mode: LUT + 16-byte stores as in the 8-slot kernel; uint8 mode: the planar band is
 //                 interleaved back to RGB with byte permutes and written as coalesced 32-bit words.
 #include "vis_fused_common.cuh"
@@ -49,7 +53,7 @@ inline Layout16 make_layout16(int stage_pitch, int strip_w, int cls) {
     L.hplane = (cls - 1 + kChunk) * L.hpitch;
     L.opitch = strip_w;
     L.oplane = VIS_PATCH * L.opitch;
-    int off = 0;
+    int off = 128;                                 // pull-order H reads up to (kt-1)*3 bytes in front of a row's window
     L.off_stage = off; off += 2 * L.stage_slot;
     L.off_hring = off; off += 2 * 3 * L.hplane;
     L.off_otile = off; off += 2 * 3 * L.oplane;
@@ -64,7 +68,7 @@ inline Layout16 make_layout16(int stage_pitch, int strip_w, int cls) {
 
 template <int KT>
 __device__ __forceinline__ void load_coeffs16(int (&k)[KT], uint32_t addr) {
-    static_assert(KT == 12 || KT == 16, "tap classes 12 and 16");
+    static_assert(KT % 4 == 0 && KT >= 12 && KT <= 32, "tap classes 12..32 in steps of 4");
 #pragma unroll
     for (int q = 0; q < KT / 4; ++q) {
         const uint4 a = lds128(addr + 16 * q);
@@ -77,6 +81,23 @@ __device__ __noinline__ void band_done16(uint32_t bar0, int nb, int lane) {
     if (lane == 0) mbar_arrive(bar0 + (uint32_t)(OF + (nb & 1)) * 8);
     const int nx = nb + 1;
     if (nx >= 2) mbar_wait(bar0 + (uint32_t)(OE + (nx & 1)) * 8, ((nx >> 1) - 1) & 1);
+}
+
+// pull-order horizontal sample: window of KT pixels ending at the record's (virtual) end, bytes [A, A + 3*KT) of the
+// words at `wbase` (A = alignment of the window start, compile time); slot s of the record <-> pixel KT-1-s of the window
+template <int KT, int A>
+__device__ __forceinline__ void hpull(uint32_t wbase, const int (&kf)[KT], int& a0, int& a1, int& a2) {
+    constexpr int W = (A + 3 * KT + 3) / 4;
+    uint32_t wv[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) wv[q] = lds32(wbase + 4 * q);
+#pragma unroll
+    for (int s = 0; s < KT; ++s) {
+        const int b = A + 3 * (KT - 1 - s);
+        a0 += (int)__byte_perm(wv[b >> 2], 0, 0x4440 + (b & 3)) * kf[s];
+        a1 += (int)__byte_perm(wv[(b + 1) >> 2], 0, 0x4440 + ((b + 1) & 3)) * kf[s];
+        a2 += (int)__byte_perm(wv[(b + 2) >> 2], 0, 0x4440 + ((b + 2) & 3)) * kf[s];
+    }
 }
 
 struct FramePtrs { const unsigned char* src; long long second; };      // VisFrameRef / VisResizeRef: same layout
@@ -161,6 +182,50 @@ k_fused_sched16(const __grid_constant__ VisSched sc, const FramePtrs* __restrict
         int rg[3][kRing];                                  // the last 16 input pixels per channel (static slots)
 #pragma unroll
         for (int q = 0; q < kRing; ++q) rg[0][q] = rg[1][q] = rg[2][q] = 0;
+        if (KT > 16) {
+            // ---- pull order (17..32 taps) ----
+            for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++sl) {
+                const int f = w / per_frame, r = w - f * per_frame;
+                const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+                const VisSchedStrip S = sc.strip[st];
+                const VisSchedSeg G = sc.seg[sg];
+                const VisSchedSub U = sc.sub[st][sub];
+                const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+                const uint32_t hrec0 = smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot) + (uint32_t)(U.xa - S.x0) * STRIDE * 4;
+                for (int c = 0; c < n_chunks; ++c, ++k) {
+                    const int slot = k & 1, j = k >> 1;
+                    mbar_wait(bar(SF, slot), j & 1);
+                    if (k >= 2) mbar_wait(bar(HE, slot), (j - 1) & 1);
+                    const uint32_t row = smem_u32(smem + L.off_stage + slot * L.stage_slot + lane * L.stage_pitch);
+                    unsigned char* hdst = smem + L.off_hring + slot * 3 * L.hplane + (CARRY + lane) * L.hpitch + (U.xa - S.x0);
+                    unsigned char* const hdst1 = hdst + L.hplane;
+                    unsigned char* const hdst2 = hdst + 2 * L.hplane;
+                    uint32_t hp = hrec0;
+#pragma unroll 1
+                    for (int xi = 0; xi < U.xb - U.xa; ++xi, hp += STRIDE * 4) {
+                        int kf[KT];
+                        load_coeffs16<KT>(kf, hp);
+                        const int end = (int)lds32(hp + (STRIDE - 1) * 4);              // (virtual) window end of this column
+                        const int o = (end - (KT - 1) - S.px0) * 3;                      // byte offset of the window start, may be < 0
+                        const int al = o & 3;
+                        const uint32_t wbase = row + (uint32_t)(o - al);
+                        int a0 = 1 << (VIS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+                        if (al == 0) hpull<KT, 0>(wbase, kf, a0, a1, a2);
+                        else if (al == 1) hpull<KT, 1>(wbase, kf, a0, a1, a2);
+                        else if (al == 2) hpull<KT, 2>(wbase, kf, a0, a1, a2);
+                        else hpull<KT, 3>(wbase, kf, a0, a1, a2);
+                        hdst[xi] = (unsigned char)clip8i(a0);
+                        hdst1[xi] = (unsigned char)clip8i(a1);
+                        hdst2[xi] = (unsigned char)clip8i(a2);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(bar(SE, slot));
+                        mbar_arrive(bar(HF, slot));
+                    }
+                }
+            }
+        } else
         for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++sl) {
             const int f = w / per_frame, r = w - f * per_frame;
             const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
@@ -404,7 +469,7 @@ int sched16_layout_bytes(int stage_pitch, int strip_w, int cls) { return make_la
 
 int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
                    const float* lut768, float* pixel_values, cudaStream_t st) {
-    if ((sc.kt != 12 && sc.kt != 16) || sc.ring != 16 || sc.n_subs != kHWarps || sc.per_index != 1) {
+    if (sc.kt < 12 || sc.kt > 32 || sc.kt % 4 || sc.ring != 16 || sc.n_subs != kHWarps || sc.per_index != 1) {
         vis::set_error("vis_fused_sched16: schedule of another kernel class (ring %d, %d taps, %d sub-ranges)", sc.ring, sc.kt, sc.n_subs);
         return VIS_E_INVALID;
     }
@@ -414,12 +479,20 @@ int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t
         return VIS_E_UNSUPPORTED;
     }
     const bool u8 = sc.out_mode == VIS_SCHED_OUT_U8;
-    if (sc.kt == 12) {
-        if (u8) return launch16<12, 16, true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st);
-        return launch16<12, 16, false>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st);
+#define VIS_L16(KT) (u8 ? launch16<KT, ((KT + 5) & ~3), true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st) \
+                        : launch16<KT, ((KT + 5) & ~3), false>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st))
+    switch (sc.kt) {
+        case 12: return VIS_L16(12);
+        case 16: return VIS_L16(16);
+        case 24: return VIS_L16(24);
+        case 32: return VIS_L16(32);
+        case 20: if (u8) return launch16<20, 24, true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st); break;
+        case 28: if (u8) return launch16<28, 32, true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st); break;
+        default: break;
     }
-    if (u8) return launch16<16, 20, true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st);
-    return launch16<16, 20, false>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st);
+#undef VIS_L16
+    vis::set_error("vis_fused_sched16: no instantiation for %d taps in this output mode", sc.kt);
+    return VIS_E_UNSUPPORTED;
 }
 
 }  // namespace visf

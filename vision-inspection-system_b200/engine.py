@@ -385,6 +385,8 @@ class Engine:
         """
         if path not in ("auto", "general"):
             raise ValueError("path must be 'auto' or 'general'")
+        if not force_generic and not (isinstance(frames, torch.Tensor) and frames.dim() == 4):
+            frames = self._align_frames(list(frames))
         plan = self.plan_batch(frames, min_pixels, max_pixels, force_generic, vsplit, path)
         if out is None:
             out = torch.empty((plan.total_rows, G.ROW_FLOATS), dtype=torch.float32, device=self.device)
@@ -413,6 +415,31 @@ class Engine:
             launches += 1
         self.last_launches = launches
         return out, plan.grid_thw
+
+    def _align_frames(self, frames: list) -> list:
+        """Frames whose base or row pitch is not a multiple of 16 bytes (e.g. 502-pixel-wide rows) cannot be staged with
+        bulk copies; they are repacked, per shape, into a cached staging tensor with a padded pitch (two device copies
+        per shape) so that they take the fused kernels like everything else."""
+        groups: dict = {}
+        for i, f in enumerate(frames):
+            if (isinstance(f, torch.Tensor) and f.is_cuda and f.dtype == torch.uint8 and f.dim() == 3 and f.shape[2] == 3
+                    and f.stride(2) == 1 and f.stride(1) == 3 and (f.stride(0) % 16 or f.data_ptr() % 16)):
+                groups.setdefault((int(f.shape[0]), int(f.shape[1])), []).append(i)
+        if not groups:
+            return frames
+        frames = list(frames)
+        for (h, w), idx in groups.items():
+            pitch = (w * 3 + 15) // 16 * 16
+            key = ("align", h, w, len(idx))
+            buf = self._staging.get(key)
+            if buf is None:
+                buf = self._staging[key] = torch.zeros((len(idx), h, pitch), dtype=torch.uint8, device=self.device)
+            src = torch.stack([frames[i].reshape(h, w * 3) if frames[i].is_contiguous() else frames[i].contiguous().view(h, w * 3)
+                               for i in idx])
+            buf[:, :, :w * 3].copy_(src)
+            for k, i in enumerate(idx):
+                frames[i] = buf[k].as_strided((h, w, 3), (pitch, 3, 1))
+        return frames
 
     def preprocess_host(self, host_frames: torch.Tensor, min_pixels: int = G.DEFAULT_MIN_PIXELS,
                         max_pixels: int = G.DEFAULT_MAX_PIXELS, out: torch.Tensor | None = None, chunk: int = 32):
