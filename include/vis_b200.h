@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 7
+#define VIS_B200_ABI_VERSION 8
 
 /* status codes */
 #define VIS_OK            0
@@ -239,6 +239,17 @@ typedef struct VisOverlayTile {   /* one CTA of the draw kernel */
     int32_t ref_begin, ref_end;   /* this tile's refs in the batch-wide refs[] array             */
 } VisOverlayTile;
 typedef struct VisOverlayRef { int32_t leaf_begin, leaf_end; } VisOverlayRef;   /* relative to the frame's leaf array */
+
+/* Batch form of vis_overlay_expand + vis_overlay_tiles for n_frames independent frames, spread over n_threads host
+ * threads (0 = all cores).  hw: (h, w) per frame; boxes of frame i = boxes[box_begin[i] .. box_begin[i+1]).
+ * Outputs, ready for vis_overlay_draw after upload: leaves (concatenated per-frame arrays), leaf_begin[n_frames + 1]
+ * (each frame's base = VisOverlayFrame.group_begin; group_end = base + its box count), tiles (frame index and
+ * batch-wide ref ranges filled in), refs.  needed[3] receives the leaf / tile / ref counts; returns the tile count,
+ * or VIS_E_CAPACITY (call again with buffers of the needed sizes).                        [host] */
+int vis_overlay_plan_batch(int n_frames, const int32_t* hw, const VisBox* boxes, const int32_t* box_begin,
+                           VisLeaf* leaves, int64_t leaf_capacity, int32_t* leaf_begin,
+                           VisOverlayTile* tiles, int64_t tile_capacity,
+                           VisOverlayRef* refs, int64_t ref_capacity, int64_t* needed, int n_threads);
 
 /* frames / tiles / refs / leaves: DEVICE arrays (<= 65535 frames).  copy_frames != 0: every frame with dst != src
  * is first copied src -> dst (vectorised), then the listed tiles are drawn in place on dst; frames drawn in place

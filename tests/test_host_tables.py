@@ -139,3 +139,47 @@ def test_leaf_expansion_edge_cases():
     with pytest.raises(N.VisError):                      # glyphs outside the digit table are refused, not guessed
         PO.expand_leaves(PO.boxes_to_pixels([{"x": 10, "y": 10, "width": 20, "height": 20, "label": "#A"}], 500, 300),
                          500, 300)
+
+
+def test_overlay_plan_batch_equals_per_frame_planning():
+    """vis_overlay_plan_batch (threaded) = vis_overlay_expand + vis_overlay_tiles per frame, concatenated."""
+    import ctypes as C
+    from vision_inspection_system_b200 import _native as N
+    from vision_inspection_system_b200 import overlay as O
+    from vision_inspection_system_b200 import synth
+    shapes = [(1080, 1920), (480, 640), (333, 517), (1080, 1920), (97, 211), (2160, 3840)] * 4
+    items = [synth.annotated_frame(900 + i, *s)[1] for i, s in enumerate(shapes)]
+    items[2] = []                                               # a frame without boxes
+    px = [O.boxes_to_pixels(b, w, h, "low", "medium") for (h, w), b in zip(shapes, items)]
+    box_begin = np.concatenate([[0], np.cumsum([len(p) for p in px])]).astype(np.int32)
+    boxes = np.concatenate([p for p in px if len(p)])
+    hw = np.asarray(shapes, np.int32)
+    n = len(shapes)
+    needed = np.zeros(3, np.int64)
+    leaf_begin = np.zeros(n + 1, np.int32)
+    L = N.lib()
+    rc = L.vis_overlay_plan_batch(n, hw.ctypes.data_as(C.c_void_p), boxes.ctypes.data_as(C.c_void_p),
+                                  box_begin.ctypes.data_as(C.c_void_p), None, 0, leaf_begin.ctypes.data_as(C.c_void_p),
+                                  None, 0, None, 0, needed.ctypes.data_as(C.c_void_p), 3)
+    assert rc == N.VIS_E_CAPACITY and (needed > 0).all()
+    leaves = np.zeros(int(needed[0]), N.LEAF_DTYPE)
+    tiles = np.zeros(int(needed[1]), N.OVERLAY_TILE_DTYPE)
+    refs = np.zeros(int(needed[2]), N.OVERLAY_REF_DTYPE)
+    rc = L.vis_overlay_plan_batch(n, hw.ctypes.data_as(C.c_void_p), boxes.ctypes.data_as(C.c_void_p),
+                                  box_begin.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p), len(leaves),
+                                  leaf_begin.ctypes.data_as(C.c_void_p), tiles.ctypes.data_as(C.c_void_p), len(tiles),
+                                  refs.ctypes.data_as(C.c_void_p), len(refs), needed.ctypes.data_as(C.c_void_p), 5)
+    assert rc == len(tiles)
+    at_t = at_r = 0
+    for i, ((h, w), p) in enumerate(zip(shapes, px)):
+        want = O.expand_leaves(p, w, h)
+        assert np.array_equal(leaves[leaf_begin[i]:leaf_begin[i + 1]]["w"], want["w"]), i
+        t3, r2 = O.touched_tiles(want, len(p), w, h)
+        got_t = tiles[at_t:at_t + len(t3)]
+        assert (got_t["frame"] == i).all() and np.array_equal(got_t["txy"], t3[:, 0])
+        assert np.array_equal(got_t["ref_begin"] - at_r, t3[:, 1]) and np.array_equal(got_t["ref_end"] - at_r, t3[:, 2])
+        got_r = refs[at_r:at_r + len(r2)]
+        assert np.array_equal(got_r["leaf_begin"], r2[:, 0]) and np.array_equal(got_r["leaf_end"], r2[:, 1])
+        at_t += len(t3)
+        at_r += len(r2)
+    assert at_t == len(tiles) and at_r == len(refs) and leaf_begin[n] == len(leaves)

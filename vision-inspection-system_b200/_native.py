@@ -61,7 +61,7 @@ EXPORTS = [
     "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
     "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_preprocess_fused_sched",
     "vis_resize_fused_sched",
-    "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
+    "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
 ]
 
 
@@ -84,7 +84,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 7:
+        if L.vis_abi_version() != 8:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -117,6 +117,7 @@ def _declare(L: C.CDLL) -> None:
     L.vis_preprocess_fused_sched.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
     L.vis_overlay_tiles.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, ip, ip]
+    L.vis_overlay_plan_batch.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int]
     L.vis_overlay_draw.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
     L.vis_heatmap_overlay.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp,
                                       C.c_int64, vp]

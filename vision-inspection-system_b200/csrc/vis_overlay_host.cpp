@@ -16,7 +16,10 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <atomic>
 #include <cstring>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "vis_internal.h"
@@ -671,4 +674,88 @@ extern "C" int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, in
         ++at[t];
     });
     return n_tiles;
+}
+
+// Batch form of vis_overlay_expand + vis_overlay_tiles: every frame is independent, so the frames are spread over host
+// threads (the per-frame entry points are reentrant; only the error text is thread local).  Outputs are the
+// concatenated, batch-indexed arrays vis_overlay_draw consumes.
+extern "C" int vis_overlay_plan_batch(int n_frames, const int32_t* hw, const VisBox* boxes, const int32_t* box_begin,
+                                      VisLeaf* leaves, int64_t leaf_capacity, int32_t* leaf_begin,
+                                      VisOverlayTile* tiles, int64_t tile_capacity,
+                                      VisOverlayRef* refs, int64_t ref_capacity, int64_t* needed, int n_threads) {
+    if (n_frames <= 0 || !hw || !box_begin || !leaf_begin || !needed || leaf_capacity < 0 || tile_capacity < 0 ||
+        ref_capacity < 0 || (leaf_capacity && !leaves) || (tile_capacity && !tiles) || (ref_capacity && !refs)) {
+        vis::set_error("vis_overlay_plan_batch: bad arguments");
+        return VIS_E_INVALID;
+    }
+    struct Frame { std::vector<VisLeaf> leaves; std::vector<int32_t> tiles, refs; int rc = VIS_OK; std::string err; };
+    std::vector<Frame> out((size_t)n_frames);
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (int i = next.fetch_add(1); i < n_frames; i = next.fetch_add(1)) {
+            Frame& fr = out[(size_t)i];
+            const int h = hw[2 * i], w = hw[2 * i + 1], nb = box_begin[i + 1] - box_begin[i];
+            const VisBox* b = boxes + box_begin[i];
+            if (nb <= 0) continue;
+            int need = 0;
+            fr.leaves.resize((size_t)nb * 1600);
+            int rc = vis_overlay_expand(h, w, b, nb, fr.leaves.data(), (int)fr.leaves.size(), &need);
+            if (rc == VIS_E_CAPACITY) {
+                fr.leaves.resize((size_t)need);
+                rc = vis_overlay_expand(h, w, b, nb, fr.leaves.data(), (int)fr.leaves.size(), &need);
+            }
+            if (rc < 0) { fr.rc = rc; fr.err = vis_last_error(); continue; }
+            fr.leaves.resize((size_t)rc);
+            int nt = 0, nr = 0;
+            const int tcap = ((w + 63) / 64) * ((h + 15) / 16);
+            fr.tiles.resize((size_t)tcap * 3);
+            fr.refs.resize((size_t)tcap * 8);
+            rc = vis_overlay_tiles(h, w, fr.leaves.data(), nb, fr.tiles.data(), tcap, fr.refs.data(), (int)fr.refs.size() / 2, &nt, &nr);
+            if (rc == VIS_E_CAPACITY) {
+                fr.refs.resize((size_t)nr * 2);
+                rc = vis_overlay_tiles(h, w, fr.leaves.data(), nb, fr.tiles.data(), tcap, fr.refs.data(), nr, &nt, &nr);
+            }
+            if (rc < 0) { fr.rc = rc; fr.err = vis_last_error(); continue; }
+            fr.tiles.resize((size_t)nt * 3);
+            fr.refs.resize((size_t)nr * 2);
+        }
+    };
+    int nth = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nth = std::max(1, std::min(nth, std::min(n_frames, 64)));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nth; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    int64_t nl = 0, nt = 0, nr = 0;
+    for (int i = 0; i < n_frames; ++i) {
+        const Frame& fr = out[(size_t)i];
+        if (fr.rc < 0) { vis::set_error("vis_overlay_plan_batch: frame %d: %s", i, fr.err.c_str()); return fr.rc; }
+        nl += (int64_t)fr.leaves.size(); nt += (int64_t)fr.tiles.size() / 3; nr += (int64_t)fr.refs.size() / 2;
+    }
+    needed[0] = nl; needed[1] = nt; needed[2] = nr;
+    if (nl > leaf_capacity || nt > tile_capacity || nr > ref_capacity || nl > INT32_MAX || nr > INT32_MAX) {
+        vis::set_error("vis_overlay_plan_batch: needs %lld leaves / %lld tiles / %lld refs", (long long)nl, (long long)nt, (long long)nr);
+        return VIS_E_CAPACITY;
+    }
+    int64_t al = 0, at = 0, ar = 0;
+    for (int i = 0; i < n_frames; ++i) {
+        const Frame& fr = out[(size_t)i];
+        leaf_begin[i] = (int32_t)al;
+        if (!fr.leaves.empty()) std::memcpy(leaves + al, fr.leaves.data(), fr.leaves.size() * sizeof(VisLeaf));
+        for (size_t k = 0; k < fr.tiles.size() / 3; ++k) {
+            VisOverlayTile& t = tiles[at++];
+            t.frame = i;
+            t.txy = fr.tiles[3 * k];
+            t.ref_begin = fr.tiles[3 * k + 1] + (int32_t)ar;
+            t.ref_end = fr.tiles[3 * k + 2] + (int32_t)ar;
+        }
+        for (size_t k = 0; k < fr.refs.size() / 2; ++k) {
+            refs[ar].leaf_begin = fr.refs[2 * k];
+            refs[ar].leaf_end = fr.refs[2 * k + 1];
+            ++ar;
+        }
+        al += (int64_t)fr.leaves.size();
+    }
+    leaf_begin[n_frames] = (int32_t)al;
+    return (int)nt;
 }

@@ -496,30 +496,36 @@ class Engine:
         ranges, number of boxes drawn, device tile list, tile count, device ref list).
         """
         from . import overlay as O
-        parts, ranges, tiles, refs, at, ref_at, drawn = [], [], [], [], 0, 0, 0
+        # host rules per frame (Python, like the reference), then ONE threaded C call for expansion + tile binning
+        px_all, box_begin, hw = [], [0], np.zeros((len(shapes), 2), np.int32)
         for i, ((h, w), boxes) in enumerate(zip(shapes, boxes_per_frame)):
             px = O.boxes_to_pixels(boxes, w, h, confidence_threshold, criticality)
-            leaves = O.expand_leaves(px, w, h)
-            ranges.append((at, at + len(px)))          # the frame's array starts at `at`; headers come first
-            parts.append(leaves)
-            t3, r2 = O.touched_tiles(leaves, len(px), w, h)
-            if len(t3):
-                t = np.zeros(len(t3), N.OVERLAY_TILE_DTYPE)
-                t["frame"], t["txy"] = i, t3[:, 0]
-                t["ref_begin"], t["ref_end"] = t3[:, 1] + ref_at, t3[:, 2] + ref_at
-                tiles.append(t)
-                refs.append(r2)
-                ref_at += len(r2)
-            at += len(leaves)
-            drawn += len(px)
-        all_leaves = np.concatenate(parts) if parts else np.zeros(0, N.LEAF_DTYPE)
-        if len(all_leaves) == 0:
-            all_leaves = np.zeros(1, N.LEAF_DTYPE)
-        n_tiles = sum(len(t) for t in tiles)
-        all_tiles = np.concatenate(tiles) if tiles else np.zeros(1, N.OVERLAY_TILE_DTYPE)
-        all_refs = np.concatenate(refs) if refs else np.zeros((1, 2), np.int32)
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
-        return up(all_leaves), ranges, drawn, up(all_tiles), n_tiles, up(all_refs)
+            px_all.append(px)
+            box_begin.append(box_begin[-1] + len(px))
+            hw[i] = (h, w)
+        boxes_arr = np.concatenate(px_all) if box_begin[-1] else np.zeros(1, N.BOX_DTYPE)
+        box_begin = np.asarray(box_begin, np.int32)
+        n = len(shapes)
+        leaf_begin = np.zeros(n + 1, np.int32)
+        needed = np.zeros(3, np.int64)
+        cap = [max(1, int(box_begin[-1]) * 1600), max(1, int(box_begin[-1]) * 160), max(1, int(box_begin[-1]) * 640)]
+        while True:
+            leaves = np.empty(cap[0], N.LEAF_DTYPE)
+            tiles = np.empty(cap[1], N.OVERLAY_TILE_DTYPE)
+            refs = np.empty(cap[2], N.OVERLAY_REF_DTYPE)
+            rc = self.L.vis_overlay_plan_batch(n, hw.ctypes.data_as(C.c_void_p), boxes_arr.ctypes.data_as(C.c_void_p),
+                                               box_begin.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p), cap[0],
+                                               leaf_begin.ctypes.data_as(C.c_void_p), tiles.ctypes.data_as(C.c_void_p), cap[1],
+                                               refs.ctypes.data_as(C.c_void_p), cap[2], needed.ctypes.data_as(C.c_void_p), 0)
+            if rc == N.VIS_E_CAPACITY:
+                cap = [max(1, int(v)) for v in needed]
+                continue
+            N.check(rc, "vis_overlay_plan_batch")
+            break
+        n_leaves, n_tiles, n_refs = (int(v) for v in needed)
+        ranges = [(int(leaf_begin[i]), int(leaf_begin[i]) + int(box_begin[i + 1] - box_begin[i])) for i in range(n)]
+        up = lambda a, k: torch.from_numpy(a[:max(k, 1)].view(np.uint8).reshape(-1)).to(self.device)  # noqa: E731
+        return up(leaves, n_leaves), ranges, int(box_begin[-1]), up(tiles, n_tiles), n_tiles, up(refs, n_refs)
 
     def annotate(self, frames, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium",
                  inplace: bool = False, plan=None):

@@ -7,6 +7,8 @@ from __future__ import annotations
 import ctypes as C
 import logging
 
+import threading
+
 import numpy as np
 
 from . import _native as N
@@ -80,6 +82,19 @@ def boxes_to_pixels(boxes, img_width: int, img_height: int, confidence_threshold
     return arr
 
 
+_tls = threading.local()
+
+
+def _scratch_array(name: str, count: int, dtype) -> np.ndarray:
+    """Grow-only host scratch, one set per thread (batch planning runs frames on a thread pool; the C entry points
+    release the GIL), so that per-frame planning does not allocate and zero a worst-case buffer every time."""
+    pool = _tls.__dict__.setdefault("scratch", {})
+    a = pool.get(name)
+    if a is None or len(a) < count:
+        a = pool[name] = np.empty(max(count, 2 * (len(a) if a is not None else 0)), dtype)
+    return a
+
+
 def expand_leaves(pixel_boxes: np.ndarray, img_width: int, img_height: int) -> np.ndarray:
     """``VisBox`` records of one frame -> its leaf array (group headers first) via ``vis_overlay_expand``."""
     L = N.lib()
@@ -87,17 +102,17 @@ def expand_leaves(pixel_boxes: np.ndarray, img_width: int, img_height: int) -> n
     if n == 0:
         return np.zeros(0, N.LEAF_DTYPE)
     boxes = np.ascontiguousarray(pixel_boxes)
-    cap = 4096 * n
+    cap = 2048 * n
     while True:
-        leaves = np.zeros(cap, N.LEAF_DTYPE)
+        leaves = _scratch_array("leaves", cap, N.LEAF_DTYPE)
         needed = C.c_int(0)
         rc = L.vis_overlay_expand(img_height, img_width, boxes.ctypes.data_as(C.c_void_p), n,
-                                  leaves.ctypes.data_as(C.c_void_p), cap, C.byref(needed))
+                                  leaves.ctypes.data_as(C.c_void_p), len(leaves), C.byref(needed))
         if rc == N.VIS_E_CAPACITY:
             cap = needed.value
             continue
         N.check(rc, "vis_overlay_expand")
-        return leaves[:rc]
+        return leaves[:rc].copy()
 
 
 def touched_tiles(leaves: np.ndarray, n_boxes: int, img_width: int, img_height: int):
@@ -110,14 +125,14 @@ def touched_tiles(leaves: np.ndarray, n_boxes: int, img_width: int, img_height: 
     tcap = ((img_width + 63) // 64) * ((img_height + 15) // 16)
     rcap = 4 * tcap
     while True:
-        tiles = np.zeros((tcap, 3), np.int32)
-        refs = np.zeros((rcap, 2), np.int32)
+        tiles = _scratch_array("tiles", tcap * 3, np.int32)
+        refs = _scratch_array("refs", rcap * 2, np.int32)
         nt, nr = C.c_int(0), C.c_int(0)
         rc = L.vis_overlay_tiles(img_height, img_width, leaves.ctypes.data_as(C.c_void_p), n_boxes,
-                                 tiles.ctypes.data_as(C.c_void_p), tcap, refs.ctypes.data_as(C.c_void_p), rcap,
-                                 C.byref(nt), C.byref(nr))
+                                 tiles.ctypes.data_as(C.c_void_p), len(tiles) // 3, refs.ctypes.data_as(C.c_void_p),
+                                 len(refs) // 2, C.byref(nt), C.byref(nr))
         if rc == N.VIS_E_CAPACITY:
             tcap, rcap = max(tcap, nt.value), max(rcap, nr.value)
             continue
         N.check(rc, "vis_overlay_tiles")
-        return tiles[:nt.value], refs[:nr.value]
+        return tiles[:3 * nt.value].reshape(-1, 3).copy(), refs[:2 * nr.value].reshape(-1, 2).copy()
