@@ -95,6 +95,9 @@ def test_padded_pitch_and_unaligned_views(engine):
     pv, _ = engine.preprocess([torch.from_numpy(f).cuda() for f in mouri_like])
     assert engine.last_launches == 1
     check_equal(pv.cpu().numpy(), wantm, "502-pixel rows (repacked)")
+    pv, _ = engine.preprocess(torch.from_numpy(np.stack(mouri_like)).cuda())        # the same as one [B, H, W, 3] tensor
+    assert engine.last_launches == 1
+    check_equal(pv.cpu().numpy(), wantm, "502-pixel rows, batch tensor (repacked)")
 
 
 def test_mixed_resolution_batch(engine):

@@ -385,8 +385,12 @@ class Engine:
         """
         if path not in ("auto", "general"):
             raise ValueError("path must be 'auto' or 'general'")
-        if not force_generic and not (isinstance(frames, torch.Tensor) and frames.dim() == 4):
-            frames = self._align_frames(list(frames))
+        if not force_generic:
+            if isinstance(frames, torch.Tensor) and frames.dim() == 4:
+                if frames.is_cuda and (frames.stride(1) % 16 or frames.stride(0) % 16 or frames.data_ptr() % 16):
+                    frames = self._align_frames(list(frames.unbind(0)))          # e.g. [B, 100, 502, 3]: 1506-byte rows
+            else:
+                frames = self._align_frames(list(frames))
         plan = self.plan_batch(frames, min_pixels, max_pixels, force_generic, vsplit, path)
         if out is None:
             out = torch.empty((plan.total_rows, G.ROW_FLOATS), dtype=torch.float32, device=self.device)
