@@ -245,7 +245,11 @@ def main():
         else:
             v, n, dt = arm.calibrated(target_s=15.0)   # ~15 s of wall clock on every core: a bounded sample
         arm.close()
+        single = CpuArm(1)                             # one process, one thread
+        t1 = single.run(8)
+        single.close()
         cpu_baseline = {"value": v, "unit": "images/s", "cores": arm.cores, "kind": arm.kind,
+                        "single_thread_value": 8 / t1,
                         "sample": f"{n} seeded 1080p noise frames over {arm.cores} forked workers (one thread each), "
                                   f"{dt:.1f} s, on {cpu_model()} ({cores} logical cores)"}
 

@@ -58,29 +58,50 @@ k_heat_local(VisHeatDefect d, int img_w, float* __restrict__ out, float* __restr
     }
 }
 
-// separable Gaussian on a region of `rw` x `rh` floats with pitch `pitch` (elements); BORDER_REFLECT_101 inside the region
+// separable Gaussian on a region of `rw` x `rh` floats with pitch `pitch` (elements); BORDER_REFLECT_101 inside the
+// region.  Both passes stage their inputs in shared memory (each input element is read from global memory ~1.2x
+// instead of ksize times) and accumulate taps in kernel order with fmaf.
+constexpr int kBlurR = 25;                       // largest radius (ksize <= 51)
+constexpr int kHSeg = 256;                       // outputs per block of the horizontal pass
+constexpr int kVCols = 32, kVRows = 64;          // tile of the vertical pass
+
 __global__ void __launch_bounds__(kT)
 k_heat_blur_h(const float* __restrict__ src, int src_pitch, float* __restrict__ dst, int dst_pitch, int rw, int rh,
               const float* __restrict__ kern, int ksize) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rw * rh) return;
-    const int y = i / rw, x = i - y * rw, r = ksize >> 1;
-    const float* row = src + (size_t)y * src_pitch;
+    __shared__ float row[kHSeg + 2 * kBlurR];
+    __shared__ float kk[2 * kBlurR + 1];
+    const int y = blockIdx.y, x0 = blockIdx.x * kHSeg, r = ksize >> 1;
+    const float* in = src + (size_t)y * src_pitch;
+    for (int i = threadIdx.x; i < kHSeg + 2 * r; i += kT) row[i] = in[reflect101(x0 + i - r, rw)];
+    if (threadIdx.x < ksize) kk[threadIdx.x] = __ldg(kern + threadIdx.x);
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= rw) return;
     float s = 0.f;
-    for (int k = 0; k < ksize; ++k) s = fmaf(__ldg(kern + k), row[reflect101(x + k - r, rw)], s);
+    for (int k = 0; k < ksize; ++k) s = fmaf(kk[k], row[threadIdx.x + k], s);
     dst[(size_t)y * dst_pitch + x] = s;
 }
 // vertical pass; combine: 0 = store, 1 = max into dst
 __global__ void __launch_bounds__(kT)
 k_heat_blur_v(const float* __restrict__ src, int src_pitch, float* __restrict__ dst, int dst_pitch, int rw, int rh,
               const float* __restrict__ kern, int ksize, int combine) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rw * rh) return;
-    const int y = i / rw, x = i - y * rw, r = ksize >> 1;
-    float s = 0.f;
-    for (int k = 0; k < ksize; ++k) s = fmaf(__ldg(kern + k), src[(size_t)reflect101(y + k - r, rh) * src_pitch + x], s);
-    float* o = dst + (size_t)y * dst_pitch + x;
-    *o = combine ? fmaxf(*o, s) : s;
+    __shared__ float tile[kVRows + 2 * kBlurR][kVCols];
+    __shared__ float kk[2 * kBlurR + 1];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8 threads
+    const int x = blockIdx.x * kVCols + tx, y0 = blockIdx.y * kVRows, r = ksize >> 1;
+    for (int i = ty; i < kVRows + 2 * r; i += kT / 32)
+        tile[i][tx] = x < rw ? src[(size_t)reflect101(y0 + i - r, rh) * src_pitch + x] : 0.f;
+    if (threadIdx.x < ksize) kk[threadIdx.x] = __ldg(kern + threadIdx.x);
+    __syncthreads();
+    if (x >= rw) return;
+    for (int j = ty; j < kVRows; j += kT / 32) {
+        const int y = y0 + j;
+        if (y >= rh) break;
+        float s = 0.f;
+        for (int k = 0; k < ksize; ++k) s = fmaf(kk[k], tile[j + k][tx], s);
+        float* o = dst + (size_t)y * dst_pitch + x;
+        *o = combine ? fmaxf(*o, s) : s;
+    }
 }
 
 __global__ void __launch_bounds__(kT)
@@ -146,14 +167,16 @@ extern "C" int vis_heatmap_overlay(const uint8_t* img, int64_t img_pitch, int h,
         const int direct = d.kind == 1 || d.ksize == 1;
         k_heat_local<<<nb, kT, 0, st>>>(d, w, ta, heat, direct);
         if (!direct) {
-            k_heat_blur_h<<<nb, kT, 0, st>>>(ta, rw, tb, rw, rw, rh, kernels + d.koff, d.ksize);
-            k_heat_blur_v<<<nb, kT, 0, st>>>(tb, rw, heat + (size_t)d.y1 * w + d.x1, w, rw, rh, kernels + d.koff, d.ksize, 1);
+            k_heat_blur_h<<<dim3((rw + kHSeg - 1) / kHSeg, rh), kT, 0, st>>>(ta, rw, tb, rw, rw, rh, kernels + d.koff, d.ksize);
+            k_heat_blur_v<<<dim3((rw + kVCols - 1) / kVCols, (rh + kVRows - 1) / kVRows), kT, 0, st>>>(
+                tb, rw, heat + (size_t)d.y1 * w + d.x1, w, rw, rh, kernels + d.koff, d.ksize, 1);
         }
     }
     const float* fin = heat;
     if (final_ksize > 1) {
-        k_heat_blur_h<<<blocks_for(n), kT, 0, st>>>(heat, w, ta, w, w, h, kernels + final_koff, final_ksize);
-        k_heat_blur_v<<<blocks_for(n), kT, 0, st>>>(ta, w, tb, w, w, h, kernels + final_koff, final_ksize, 0);
+        k_heat_blur_h<<<dim3((w + kHSeg - 1) / kHSeg, h), kT, 0, st>>>(heat, w, ta, w, w, h, kernels + final_koff, final_ksize);
+        k_heat_blur_v<<<dim3((w + kVCols - 1) / kVCols, (h + kVRows - 1) / kVRows), kT, 0, st>>>(
+            ta, w, tb, w, w, h, kernels + final_koff, final_ksize, 0);
         fin = tb;
     }
     k_heat_max<<<592, kT, 0, st>>>(fin, n, mx);
