@@ -183,3 +183,33 @@ def test_overlay_plan_batch_equals_per_frame_planning():
         at_t += len(t3)
         at_r += len(r2)
     assert at_t == len(tiles) and at_r == len(refs) and leaf_begin[n] == len(leaves)
+
+
+def test_host_only_image_utils_helpers(tmp_path):
+    """load_image / get_image_info / validate_image: same results and messages as the reference's host code
+    (utils/image_utils.py:20-43, 81-145); no GPU involved."""
+    from PIL import Image
+    from vision_inspection_system_b200 import image_utils as IU
+    p = tmp_path / "frame.png"
+    Image.fromarray(np.zeros((20, 30, 3), np.uint8)).save(p)
+    info = IU.get_image_info(p)
+    assert (info["width"], info["height"], info["mode"], info["format"], info["filename"]) == (30, 20, "RGB", "PNG", "frame.png")
+    assert info["size_bytes"] == p.stat().st_size and info["path"] == str(p)
+    assert IU.validate_image(p) == (True, None)
+    assert IU.validate_image(tmp_path / "none.png") == (False, "File does not exist")
+    bad_ext = tmp_path / "frame.gif"
+    bad_ext.write_bytes(p.read_bytes())
+    ok, msg = IU.validate_image(bad_ext)
+    assert not ok and msg.startswith("Invalid extension 'gif'")
+    tiny = tmp_path / "tiny.png"
+    Image.fromarray(np.zeros((5, 30, 3), np.uint8)).save(tiny)
+    assert IU.validate_image(tiny) == (False, "Image too small (minimum 10x10 pixels)")
+    junk = tmp_path / "junk.jpg"
+    junk.write_bytes(b"not an image")
+    ok, msg = IU.validate_image(junk)
+    assert not ok and msg.startswith("Invalid image file: Failed to load image")
+    assert IU.validate_image(p, max_size_mb=1e-9)[1].startswith("File too large")
+    with pytest.raises(FileNotFoundError):
+        IU.load_image(tmp_path / "none.png")
+    with pytest.raises(ValueError, match="Failed to load image"):
+        IU.load_image(junk)

@@ -57,6 +57,41 @@ def load_image(image_path: Path) -> Image.Image:
         raise ValueError(f"Failed to load image: {e}")
 
 
+def get_image_info(image_path: Path) -> dict:
+    """Image metadata, same keys as the reference (utils/image_utils.py:81-101); host only."""
+    image_path = Path(image_path)
+    img = load_image(image_path)
+    return {"path": str(image_path), "filename": image_path.name, "width": img.size[0], "height": img.size[1],
+            "mode": img.mode, "format": img.format, "size_bytes": image_path.stat().st_size}
+
+
+ALLOWED_EXTENSIONS = ["jpg", "jpeg", "png", "bmp", "tiff", "webp"]     # config.allowed_extensions default (utils/config.py:144)
+MAX_FILE_SIZE_MB = 10                                                   # config.max_file_size_mb default (utils/config.py:143)
+
+
+def validate_image(image_path: Path, allowed_extensions: list = None, max_size_mb: float = None):
+    """(is_valid, error_message) with the reference's checks and messages (utils/image_utils.py:104-145); host only.
+    Defaults mirror the config defaults instead of importing ``utils.config`` (no API-key check at import)."""
+    image_path = Path(image_path)
+    allowed_extensions = allowed_extensions or ALLOWED_EXTENSIONS
+    max_size_mb = max_size_mb or MAX_FILE_SIZE_MB
+    if not image_path.exists():
+        return False, "File does not exist"
+    ext = image_path.suffix.lower().lstrip(".")
+    if ext not in allowed_extensions:
+        return False, f"Invalid extension '{ext}'. Allowed: {allowed_extensions}"
+    size_mb = image_path.stat().st_size / (1024 * 1024)
+    if size_mb > max_size_mb:
+        return False, f"File too large: {size_mb:.1f}MB (max: {max_size_mb}MB)"
+    try:
+        img = load_image(image_path)
+        if img.size[0] < 10 or img.size[1] < 10:
+            return False, "Image too small (minimum 10x10 pixels)"
+    except Exception as e:
+        return False, f"Invalid image file: {e}"
+    return True, None
+
+
 def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int) -> Image.Image:
     """``img.resize(size, filt)`` (reducing_gap=None) with the resampling done on the GPU."""
     import torch
