@@ -213,7 +213,7 @@ typedef struct VisLeaf { int32_t w[VIS_LEAF_WORDS]; } VisLeaf;   /* opaque 48-by
 /* expand the boxes of ONE frame into its leaf array: n_boxes group headers (one per box: leaf range +
  * bounding box, indices relative to the start of this array) followed by the ordered leaves.
  * Returns the leaf count, or VIS_E_CAPACITY with *needed = required count (call again with a larger buffer),
- * or VIS_E_UNSUPPORTED for a label character outside the built-in Hershey digits.     [host] */
+ * or VIS_E_UNSUPPORTED for a label character outside printable ASCII (32..126).          [host] */
 int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int n_boxes,
                        VisLeaf* leaves, int capacity, int* needed);
 

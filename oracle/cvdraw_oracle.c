@@ -453,21 +453,110 @@ static void thick_line(Img* im, P2l p0, P2l p1, const Col* col, int thickness, i
     }
 }
 
-/* ---------------- Hershey simplex glyphs (digits 0-9 = glyphs 700-709 of g_HersheyGlyphs) ---------------- */
+/* ---------------- Hershey simplex glyphs, printable ASCII 32..126 ----------------
+ * cv: HersheySimplex[] -> g_HersheyGlyphs[] (drawing.cpp).  The strings are font DATA of the installed OpenCV 4.13
+ * binary; tests/golden/find_glyphs.py recovers them by rendering every candidate string found in the binary through
+ * cv2.polylines with putText's own geometry and keeping the one that reproduces cv2.putText at four scale /
+ * thickness / line-type settings. */
+static const char* const kSimplexGlyphs[95] = {
+    "JZ",  /*   */
+    "MWRFRT RYQZR[SZRY",  /* ! */
+    "JZNFNM VFVM",  /* quote */
+    "G]OFOb UFUb JQZQ JWZW",  /* # */
+    "H\\PBP_ TBT_ YIWGTFPFMGKIKKLMMNOOUQWRXSYUYXWZT[P[MZKX",  /* $ */
+    "F^[FYGVHSHPGNFLFJGIIIKKMMMOLPJPHNF [FI[ YTWTUUTWTYV[X[ZZ[X[VYT",  /* % */
+    "E_\\O\\N[MZMYNXPVUTXRZP[L[JZIYHWHUISJRQNRMSKSIRGPFNGMIMKNNPQUXWZY[[[\\Z\\Y",  /* & */
+    "NVRFRM",  /* ' */
+    "KYVBTDRGPKOPOTPYR]T`Vb",  /* ( */
+    "KYNBPDRGTKUPUTTYR]P`Nb",  /* ) */
+    "JZRLRX MOWU WOMU",
+    "E_RIR[ IR[R",  /* + */
+    "MWSZR[QZRYSZS\\R^Q_",  /* , */
+    "E_IR[R",  /* - */
+    "MWRYQZR[SZRY",  /* . */
+    "G][BIb",
+    "H\\QFNGLJKOKRLWNZQ[S[VZXWYRYOXJVGSFQF",  /* 0 */
+    "H\\NJPISFS[",  /* 1 */
+    "H\\LKLJMHNGPFTFVGWHXJXLWNUQK[Y[",  /* 2 */
+    "H\\MFXFRNUNWOXPYSYUXXVZS[P[MZLYKW",  /* 3 */
+    "H\\UFKTZT UFU[",  /* 4 */
+    "H\\WFMFLOMNPMSMVNXPYSYUXXVZS[P[MZLYKW",  /* 5 */
+    "H\\XIWGTFRFOGMJLOLTMXOZR[S[VZXXYUYTXQVOSNRNOOMQLT",  /* 6 */
+    "H\\YFO[ KFYF",  /* 7 */
+    "H\\PFMGLILKMMONSOVPXRYTYWXYWZT[P[MZLYKWKTLRNPQOUNWMXKXIWGTFPF",  /* 8 */
+    "H\\XMWPURRSQSNRLPKMKLLINGQFRFUGWIXMXRWWUZR[P[MZLX",  /* 9 */
+    "MWRMQNROSNRM RYQZR[SZRY",  /* : */
+    "MWRMQNROSNRM SZR[QZRYSZS\\R^Q_",  /* ; */
+    "F^ZIJRZ[",  /* < */
+    "E_IO[O IU[U",  /* = */
+    "F^JIZRJ[",  /* > */
+    "I[LKLJMHNGPFTFVGWHXJXLWNVORQRT RYQZR[SZRY",  /* ? */
+    "DaWNVLTKQKOLNMMOMRNTOUQVTVVUWS WKWSXUYV[V\\U]S]O\\L[JYHWGTFQFNGLHJJILHOHRIUJWLYNZQ[T[WZYY",  /* @ */
+    "I[RFJ[ RFZ[ MTWT",  /* A */
+    "G\\KFK[ KFTFWGXHYJYLXNWOTP KPTPWQXRYTYWXYWZT[K[",  /* B */
+    "H]ZKYIWGUFQFOGMILKKNKSLVMXOZQ[U[WZYXZV",  /* C */
+    "G\\KFK[ KFRFUGWIXKYNYSXVWXUZR[K[",  /* D */
+    "H[LFL[ LFYF LPTP L[Y[",  /* E */
+    "HZLFL[ LFYF LPTP",  /* F */
+    "H]ZKYIWGUFQFOGMILKKNKSLVMXOZQ[U[WZYXZVZS USZS",  /* G */
+    "G]KFK[ YFY[ KPYP",  /* H */
+    "NVRFR[",  /* I */
+    "JZVFVVUYTZR[P[NZMYLVLT",  /* J */
+    "G\\KFK[ YFKT POY[",  /* K */
+    "HYLFL[ L[X[",  /* L */
+    "F^JFJ[ JFR[ ZFR[ ZFZ[",  /* M */
+    "G]KFK[ KFY[ YFY[",  /* N */
+    "G]PFNGLIKKJNJSKVLXNZP[T[VZXXYVZSZNYKXIVGTFPF",  /* O */
+    "G\\KFK[ KFTFWGXHYJYMXOWPTQKQ",  /* P */
+    "G]PFNGLIKKJNJSKVLXNZP[T[VZXXYVZSZNYKXIVGTFPF SWY]",  /* Q */
+    "G\\KFK[ KFTFWGXHYJYLXNWOTPKP RPY[",  /* R */
+    "H\\YIWGTFPFMGKIKKLMMNOOUQWRXSYUYXWZT[P[MZKX",  /* S */
+    "JZRFR[ KFYF",  /* T */
+    "G]KFKULXNZQ[S[VZXXYUYF",  /* U */
+    "I[JFR[ ZFR[",  /* V */
+    "F^HFM[ RFM[ RFW[ \\FW[",  /* W */
+    "H\\KFY[ YFK[",  /* X */
+    "I[JFRPR[ ZFRP",  /* Y */
+    "H\\YFK[ KFYF K[Y[",  /* Z */
+    "KYOBOb OBVB ObVb",  /* [ */
+    "G]IL[b",  /* backslash */
+    "KYUBUb NBUB NbUb",  /* ] */
+    "G]JTROZT JTRPZT",  /* ^ */
+    "I[J[Z[",  /* _ */
+    "LXPFUL PFOGUL",  /* ` */
+    "I\\XMX[ XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* a */
+    "H[LFL[ LPNNPMSMUNWPXSXUWXUZS[P[NZLX",  /* b */
+    "I[XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* c */
+    "I\\XFX[ XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* d */
+    "I[LSXSXQWOVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* e */
+    "MYWFUFSGRJR[ OMVM",  /* f */
+    "I\\XMX]W`VaTbQbOa XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* g */
+    "I\\MFM[ MQPNRMUMWNXQX[",  /* h */
+    "NVQFRGSFREQF RMR[",  /* i */
+    "MWRFSGTFSERF SMS^RaPbNb",  /* j */
+    "IZMFM[ WMMW QSX[",  /* k */
+    "NVRFR[",  /* l */
+    "CaGMG[ GQJNLMOMQNRQR[ RQUNWMZM\\N]Q][",  /* m */
+    "I\\MMM[ MQPNRMUMWNXQX[",  /* n */
+    "I\\QMONMPLSLUMXOZQ[T[VZXXYUYSXPVNTMQM",  /* o */
+    "H[LMLb LPNNPMSMUNWPXSXUWXUZS[P[NZLX",  /* p */
+    "I\\XMXb XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* q */
+    "KXOMO[ OSPPRNTMWM",  /* r */
+    "J[XPWNTMQMNNMPNRPSUTWUXWXXWZT[Q[NZMX",  /* s */
+    "MYRFRWSZU[W[ OMVM",  /* t */
+    "I\\MMMWNZP[S[UZXW XMX[",  /* u */
+    "JZLMR[ XMR[",  /* v */
+    "G]JMN[ RMN[ RMV[ ZMV[",  /* w */
+    "J[MMX[ XMM[",  /* x */
+    "JZLMR[ XMR[P_NaLbKb",  /* y */
+    "J[XMM[ MMXM M[X[",  /* z */
+    "KYTBQEPHPJQMSOSPORSTSUQWPZP\\Q_Tb",  /* { */
+    "NVRBRb",  /* | */
+    "KYPBSETHTJSMQOQPURQTQUSWTZT\\S_Pb",  /* } */
+    "F^IUISJPLONOPPTSVTXTZS[Q ISJQLPNPPQTTVUXUZT[Q[O",  /* ~ */
+};
 static const char* simplex_glyph(int c) {
-    switch (c) {
-        case '0': return "H\\QFNGLJKOKRLWNZQ[S[VZXWYRYOXJVGSFQF";
-        case '1': return "H\\NJPISFS[";
-        case '2': return "H\\LKLJMHNGPFTFVGWHXJXLWNUQK[Y[";
-        case '3': return "H\\MFXFRNUNWOXPYSYUXXVZS[P[MZLYKW";
-        case '4': return "H\\UFKTZT UFU[";
-        case '5': return "H\\WFMFLOMNPMSMVNXPYSYUXXVZS[P[MZLYKW";
-        case '6': return "H\\XIWGTFRFOGMJLOLTMXOZR[S[VZXXYUYTXQVOSNRNOOMQLT";
-        case '7': return "H\\YFO[ KFYF";
-        case '8': return "H\\PFMGLILKMMONSOVPXRYTYWXYWZT[P[MZLYKWKTLRNPQOUNWMXKXIWGTFPF";
-        case '9': return "H\\XMWPURRSQSNRLPKMKLLINGQFRFUGWIXMXRWWUZR[P[MZLX";
-        default: return NULL;
-    }
+    return (c >= 32 && c <= 126) ? kSimplexGlyphs[c - 32] : NULL;
 }
 
 /* =============================== exported entry points =============================== */

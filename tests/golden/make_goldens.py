@@ -146,7 +146,46 @@ def heatmap_goldens(arrays: dict):
     return out
 
 
+def label_overlay_cases():
+    """draw_bounding_boxes cases whose labels are not '#<int>' (any printable ASCII)."""
+    texts = ["#A7", "crack-12", "Z", "a|b", "#(x)", "Q9%", "~", "ok!", "{[<>]}", "W_m", "#", ""]
+    cases = []
+    for k, (seed, shape) in enumerate(((7400, (1080, 1920)), (7401, (480, 640)), (7402, (333, 517)))):
+        _, boxes = synth.annotated_frame(seed, *shape)
+        for i, b in enumerate(boxes):
+            b["label"] = texts[(5 * k + i) % len(texts)]
+        cases.append((f"labels_seed{seed}", seed, shape, boxes, "low", "medium"))
+    return cases
+
+
+def overlay_label_goldens():
+    ref = import_reference_image_utils()
+    captured = {}
+    real_imread, real_imwrite = ref.cv2.imread, ref.cv2.imwrite
+    out = []
+    for name, seed, shape, boxes, thr, crit in label_overlay_cases():
+        frame = np.random.default_rng(seed).integers(0, 256, (*shape, 3), dtype=np.uint8)
+        captured["input"] = frame
+        ref.cv2.imread = lambda path, *a: captured["input"].copy()
+        ref.cv2.imwrite = lambda path, img, *a: captured.__setitem__("output", img.copy()) or True
+        try:
+            ref.draw_bounding_boxes(Path("in.png"), boxes, Path("out.jpg"), thr, crit)
+        finally:
+            ref.cv2.imread, ref.cv2.imwrite = real_imread, real_imwrite
+        res = captured["output"]
+        out.append({"name": name, "seed": seed, "shape": list(shape), "boxes": boxes, "confidence_threshold": thr,
+                    "criticality": crit, "sha256": sha(res), "changed_pixels": int((res != frame).any(2).sum())})
+        print("overlay", name, sha(res)[:16], out[-1]["changed_pixels"])
+    return out
+
+
 def main():
+    if "--only-overlay-labels" in sys.argv:             # append / refresh the text-label overlay cases
+        out = json.loads((HERE / "goldens.json").read_text())
+        out["overlay"] = [r for r in out["overlay"] if not r["name"].startswith("labels_")] + overlay_label_goldens()
+        (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
+        print("updated", HERE / "goldens.json")
+        return
     if "--only-heatmap" in sys.argv:                    # add / refresh the "heatmap" section of existing files
         out = json.loads((HERE / "goldens.json").read_text())
         arrays = dict(np.load(HERE / "arrays.npz"))
@@ -275,6 +314,7 @@ def main():
                                "changed_pixels": int((res != frame).any(2).sum())})
         print("overlay", name, sha(res)[:16], out["overlay"][-1]["changed_pixels"])
 
+    out["overlay"] += overlay_label_goldens()
     out["heatmap"] = heatmap_goldens(arrays)
     arrays["jet_bgr"] = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)[0]
     np.savez_compressed(HERE / "arrays.npz", **arrays)

@@ -48,6 +48,20 @@ def test_mixed_sizes_odd_widths_and_empty_lists(engine):
         assert np.array_equal(o.cpu().numpy(), OV.draw_bounding_boxes(f, b))
 
 
+def test_text_labels_beyond_digits(engine):
+    """Labels are any printable ASCII (the reference passes '#<int>', the function accepts anything)."""
+    texts = ["#A7", "crack-12", "Z", "a|b", "#(x)", "Q9%", "~", "ok!", "{[<>]}", "W_m"]
+    items = []
+    for k, shape in enumerate(((480, 640), (1080, 1920), (333, 517))):
+        frame, boxes = synth.annotated_frame(60 + k, *shape)
+        for i, b in enumerate(boxes):
+            b["label"] = texts[(2 * k + i) % len(texts)]
+        items.append((frame, boxes))
+    outs = engine.annotate([torch.from_numpy(f).cuda() for f, _ in items], [b for _, b in items])
+    for (f, b), o in zip(items, outs):
+        assert np.array_equal(o.cpu().numpy(), OV.draw_bounding_boxes(f, b))
+
+
 def test_draw_bounding_boxes_files(engine, tmp_path):
     import cv2
     from vision_inspection_system_b200 import image_utils as IU

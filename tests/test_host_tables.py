@@ -136,8 +136,17 @@ def test_leaf_expansion_edge_cases():
     assert len(px) == 2
     got = apply_leaves(frame, PO.expand_leaves(px, 500, 300))
     assert np.array_equal(got, OV.draw_bounding_boxes(frame, boxes))
-    with pytest.raises(N.VisError):                      # glyphs outside the digit table are refused, not guessed
-        PO.expand_leaves(PO.boxes_to_pixels([{"x": 10, "y": 10, "width": 20, "height": 20, "label": "#A"}], 500, 300),
+    # labels are any printable ASCII (full Hershey simplex table); anything else is refused, not guessed
+    texts = ["#A7", "crack-12", "Z", "a|b", "#(x)", "Q9%", "~", "ok!", "{[<>]}"]
+    for k, shape in enumerate(((300, 500), (480, 640), (1080, 1920))):
+        frame, boxes = synth.annotated_frame(50 + k, *shape)
+        for i, b in enumerate(boxes):
+            b["label"] = texts[(3 * k + i) % len(texts)]
+        px = PO.boxes_to_pixels(boxes, shape[1], shape[0])
+        got = apply_leaves(frame, PO.expand_leaves(px, shape[1], shape[0]))
+        assert np.array_equal(got, OV.draw_bounding_boxes(frame, boxes)), shape
+    with pytest.raises(N.VisError):
+        PO.expand_leaves(PO.boxes_to_pixels([{"x": 10, "y": 10, "width": 20, "height": 20, "label": "#\xe9"}], 500, 300),
                          500, 300)
 
 

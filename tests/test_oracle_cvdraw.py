@@ -57,7 +57,10 @@ def test_primitives_against_cv2():
             L.ocv_circle(P(b), H, W, b.strides[0], x1, y1, r, *col, t, 8)
         else:
             fs = float(rng.uniform(0.4, 2.5))
-            txt = str(int(rng.integers(0, 1000)))
+            if it % 12 == 5:
+                txt = str(int(rng.integers(0, 1000)))
+            else:                                        # any printable ASCII (the full Hershey simplex table)
+                txt = "".join(chr(int(c)) for c in rng.integers(32, 127, int(rng.integers(1, 6))))
             cv2.putText(a, txt, (x1, y1), cv2.FONT_HERSHEY_SIMPLEX, fs, col, t)
             assert L.ocv_put_text(P(b), H, W, b.strides[0], txt.encode(), x1, y1, fs, *col, t) == 0
             tw, th = ctypes.c_int(), ctypes.c_int()
@@ -71,6 +74,35 @@ def test_overlay_against_cv2_calls():
     from vision_inspection_system_b200 import synth
     for seed, shape in ((1, (480, 640)), (2, (720, 1280)), (3, (300, 500)), (4, (1080, 1920))):
         frame, boxes = synth.annotated_frame(seed, *shape)
+        px = OV.select_boxes(boxes, shape[1], shape[0])
+        assert np.array_equal(OV.render(frame, px), OV.render_cv2(frame, px)), seed
+
+
+def test_every_printable_ascii_glyph_against_cv2():
+    cv2 = pytest.importorskip("cv2")
+    L = lib()
+    for c in range(32, 127):
+        for fs, t in ((0.7, 2), (2.1, 2), (1.3, 3)):
+            a = np.zeros((120, 160, 3), np.uint8)
+            b = a.copy()
+            cv2.putText(a, chr(c), (30, 90), cv2.FONT_HERSHEY_SIMPLEX, fs, (255, 200, 50), t)
+            assert L.ocv_put_text(P(b), 120, 160, b.strides[0], chr(c).encode(), 30, 90, fs, 255, 200, 50, t) == 0
+            assert np.array_equal(a, b), (chr(c), fs, t)
+            tw, th = ctypes.c_int(), ctypes.c_int()
+            L.ocv_get_text_size(chr(c).encode(), fs, t, ctypes.byref(tw), ctypes.byref(th))
+            assert (tw.value, th.value) == cv2.getTextSize(chr(c), cv2.FONT_HERSHEY_SIMPLEX, fs, t)[0], chr(c)
+    assert L.ocv_put_text(P(b), 120, 160, b.strides[0], "\xe9".encode("latin-1"), 30, 90, 1.0, 1, 2, 3, 2) != 0   # outside ASCII
+
+
+def test_text_labels_against_cv2_calls():
+    """draw_bounding_boxes with labels other than '#<int>' (any printable ASCII): oracle render == the same cv2 calls."""
+    pytest.importorskip("cv2")
+    from vision_inspection_system_b200 import synth
+    labels = ["#A7", "crack-12", "Z", "a|b", "#(x)", "Q9%", "~"]
+    for seed, shape in ((11, (480, 640)), (12, (1080, 1920))):
+        frame, boxes = synth.annotated_frame(seed, *shape)
+        for i, b in enumerate(boxes):
+            b["label"] = labels[(seed + i) % len(labels)]
         px = OV.select_boxes(boxes, shape[1], shape[0])
         assert np.array_equal(OV.render(frame, px), OV.render_cv2(frame, px)), seed
 

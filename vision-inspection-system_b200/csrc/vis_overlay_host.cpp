@@ -99,21 +99,109 @@ const unsigned char kSlopeCorr[32] = {181, 181, 181, 182, 182, 183, 184, 185, 18
 
 inline int round_half_even(double v) { return (int)std::lrint(v); }
 
-// Hershey simplex digit glyphs (g_HersheyGlyphs[700..709]); the reference only ever draws "#<int>" labels
-// with the '#' removed (src/reporting/pdf_generator.py:1303, utils/image_utils.py:240-242)
+// Hershey simplex glyphs of printable ASCII 32..126 (cv: HersheySimplex[] -> g_HersheyGlyphs[]): font data of the
+// installed OpenCV 4.13 binary, recovered and verified by tests/golden/find_glyphs.py.  The reference only ever draws
+// "#<int>" labels with the '#' removed (src/reporting/pdf_generator.py:1303, utils/image_utils.py:240-242), but
+// draw_bounding_boxes accepts any label text.
 const char* glyph_for(unsigned char ch) {
-    static const char* const digits[10] = {
-        "H\\QFNGLJKOKRLWNZQ[S[VZXWYRYOXJVGSFQF",
-        "H\\NJPISFS[",
-        "H\\LKLJMHNGPFTFVGWHXJXLWNUQK[Y[",
-        "H\\MFXFRNUNWOXPYSYUXXVZS[P[MZLYKW",
-        "H\\UFKTZT UFU[",
-        "H\\WFMFLOMNPMSMVNXPYSYUXXVZS[P[MZLYKW",
-        "H\\XIWGTFRFOGMJLOLTMXOZR[S[VZXXYUYTXQVOSNRNOOMQLT",
-        "H\\YFO[ KFYF",
-        "H\\PFMGLILKMMONSOVPXRYTYWXYWZT[P[MZLYKWKTLRNPQOUNWMXKXIWGTFPF",
-        "H\\XMWPURRSQSNRLPKMKLLINGQFRFUGWIXMXRWWUZR[P[MZLX"};
-    return (ch >= '0' && ch <= '9') ? digits[ch - '0'] : nullptr;
+    static const char* const glyphs[95] = {
+    "JZ",  /*   */
+    "MWRFRT RYQZR[SZRY",  /* ! */
+    "JZNFNM VFVM",  /* quote */
+    "G]OFOb UFUb JQZQ JWZW",  /* # */
+    "H\\PBP_ TBT_ YIWGTFPFMGKIKKLMMNOOUQWRXSYUYXWZT[P[MZKX",  /* $ */
+    "F^[FYGVHSHPGNFLFJGIIIKKMMMOLPJPHNF [FI[ YTWTUUTWTYV[X[ZZ[X[VYT",  /* % */
+    "E_\\O\\N[MZMYNXPVUTXRZP[L[JZIYHWHUISJRQNRMSKSIRGPFNGMIMKNNPQUXWZY[[[\\Z\\Y",  /* & */
+    "NVRFRM",  /* ' */
+    "KYVBTDRGPKOPOTPYR]T`Vb",  /* ( */
+    "KYNBPDRGTKUPUTTYR]P`Nb",  /* ) */
+    "JZRLRX MOWU WOMU",
+    "E_RIR[ IR[R",  /* + */
+    "MWSZR[QZRYSZS\\R^Q_",  /* , */
+    "E_IR[R",  /* - */
+    "MWRYQZR[SZRY",  /* . */
+    "G][BIb",
+    "H\\QFNGLJKOKRLWNZQ[S[VZXWYRYOXJVGSFQF",  /* 0 */
+    "H\\NJPISFS[",  /* 1 */
+    "H\\LKLJMHNGPFTFVGWHXJXLWNUQK[Y[",  /* 2 */
+    "H\\MFXFRNUNWOXPYSYUXXVZS[P[MZLYKW",  /* 3 */
+    "H\\UFKTZT UFU[",  /* 4 */
+    "H\\WFMFLOMNPMSMVNXPYSYUXXVZS[P[MZLYKW",  /* 5 */
+    "H\\XIWGTFRFOGMJLOLTMXOZR[S[VZXXYUYTXQVOSNRNOOMQLT",  /* 6 */
+    "H\\YFO[ KFYF",  /* 7 */
+    "H\\PFMGLILKMMONSOVPXRYTYWXYWZT[P[MZLYKWKTLRNPQOUNWMXKXIWGTFPF",  /* 8 */
+    "H\\XMWPURRSQSNRLPKMKLLINGQFRFUGWIXMXRWWUZR[P[MZLX",  /* 9 */
+    "MWRMQNROSNRM RYQZR[SZRY",  /* : */
+    "MWRMQNROSNRM SZR[QZRYSZS\\R^Q_",  /* ; */
+    "F^ZIJRZ[",  /* < */
+    "E_IO[O IU[U",  /* = */
+    "F^JIZRJ[",  /* > */
+    "I[LKLJMHNGPFTFVGWHXJXLWNVORQRT RYQZR[SZRY",  /* ? */
+    "DaWNVLTKQKOLNMMOMRNTOUQVTVVUWS WKWSXUYV[V\\U]S]O\\L[JYHWGTFQFNGLHJJILHOHRIUJWLYNZQ[T[WZYY",  /* @ */
+    "I[RFJ[ RFZ[ MTWT",  /* A */
+    "G\\KFK[ KFTFWGXHYJYLXNWOTP KPTPWQXRYTYWXYWZT[K[",  /* B */
+    "H]ZKYIWGUFQFOGMILKKNKSLVMXOZQ[U[WZYXZV",  /* C */
+    "G\\KFK[ KFRFUGWIXKYNYSXVWXUZR[K[",  /* D */
+    "H[LFL[ LFYF LPTP L[Y[",  /* E */
+    "HZLFL[ LFYF LPTP",  /* F */
+    "H]ZKYIWGUFQFOGMILKKNKSLVMXOZQ[U[WZYXZVZS USZS",  /* G */
+    "G]KFK[ YFY[ KPYP",  /* H */
+    "NVRFR[",  /* I */
+    "JZVFVVUYTZR[P[NZMYLVLT",  /* J */
+    "G\\KFK[ YFKT POY[",  /* K */
+    "HYLFL[ L[X[",  /* L */
+    "F^JFJ[ JFR[ ZFR[ ZFZ[",  /* M */
+    "G]KFK[ KFY[ YFY[",  /* N */
+    "G]PFNGLIKKJNJSKVLXNZP[T[VZXXYVZSZNYKXIVGTFPF",  /* O */
+    "G\\KFK[ KFTFWGXHYJYMXOWPTQKQ",  /* P */
+    "G]PFNGLIKKJNJSKVLXNZP[T[VZXXYVZSZNYKXIVGTFPF SWY]",  /* Q */
+    "G\\KFK[ KFTFWGXHYJYLXNWOTPKP RPY[",  /* R */
+    "H\\YIWGTFPFMGKIKKLMMNOOUQWRXSYUYXWZT[P[MZKX",  /* S */
+    "JZRFR[ KFYF",  /* T */
+    "G]KFKULXNZQ[S[VZXXYUYF",  /* U */
+    "I[JFR[ ZFR[",  /* V */
+    "F^HFM[ RFM[ RFW[ \\FW[",  /* W */
+    "H\\KFY[ YFK[",  /* X */
+    "I[JFRPR[ ZFRP",  /* Y */
+    "H\\YFK[ KFYF K[Y[",  /* Z */
+    "KYOBOb OBVB ObVb",  /* [ */
+    "G]IL[b",  /* backslash */
+    "KYUBUb NBUB NbUb",  /* ] */
+    "G]JTROZT JTRPZT",  /* ^ */
+    "I[J[Z[",  /* _ */
+    "LXPFUL PFOGUL",  /* ` */
+    "I\\XMX[ XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* a */
+    "H[LFL[ LPNNPMSMUNWPXSXUWXUZS[P[NZLX",  /* b */
+    "I[XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* c */
+    "I\\XFX[ XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* d */
+    "I[LSXSXQWOVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* e */
+    "MYWFUFSGRJR[ OMVM",  /* f */
+    "I\\XMX]W`VaTbQbOa XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* g */
+    "I\\MFM[ MQPNRMUMWNXQX[",  /* h */
+    "NVQFRGSFREQF RMR[",  /* i */
+    "MWRFSGTFSERF SMS^RaPbNb",  /* j */
+    "IZMFM[ WMMW QSX[",  /* k */
+    "NVRFR[",  /* l */
+    "CaGMG[ GQJNLMOMQNRQR[ RQUNWMZM\\N]Q][",  /* m */
+    "I\\MMM[ MQPNRMUMWNXQX[",  /* n */
+    "I\\QMONMPLSLUMXOZQ[T[VZXXYUYSXPVNTMQM",  /* o */
+    "H[LMLb LPNNPMSMUNWPXSXUWXUZS[P[NZLX",  /* p */
+    "I\\XMXb XPVNTMQMONMPLSLUMXOZQ[T[VZXX",  /* q */
+    "KXOMO[ OSPPRNTMWM",  /* r */
+    "J[XPWNTMQMNNMPNRPSUTWUXWXXWZT[Q[NZMX",  /* s */
+    "MYRFRWSZU[W[ OMVM",  /* t */
+    "I\\MMMWNZP[S[UZXW XMX[",  /* u */
+    "JZLMR[ XMR[",  /* v */
+    "G]JMN[ RMN[ RMV[ ZMV[",  /* w */
+    "J[MMX[ XMM[",  /* x */
+    "JZLMR[ XMR[P_NaLbKb",  /* y */
+    "J[XMM[ MMXM M[X[",  /* z */
+    "KYTBQEPHPJQMSOSPORSTSUQWPZP\\Q_Tb",  /* { */
+    "NVRBRb",  /* | */
+    "KYPBSETHTJSMQOQPURQTQUSWTZT\\S_Pb",  /* } */
+    "F^IUISJPLONOPPTSVTXTZS[Q ISJQLPNPPQTTVUXUZT[Q[O",  /* ~ */
+    };
+    return (ch >= 32 && ch <= 126) ? glyphs[ch - 32] : nullptr;
 }
 
 class Emitter {
@@ -606,7 +694,7 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
         label[12] = 0;
         int tw = 0, th = 0;
         if (!em.text_size(label, font_scale, text_thickness, &tw, &th)) {
-            vis::set_error("vis_overlay_expand: label '%s' has a character outside the built-in Hershey digits", label);
+            vis::set_error("vis_overlay_expand: label '%s' has a character outside printable ASCII", label);
             return VIS_E_UNSUPPORTED;
         }
         em.set_color(0, 0, 0);
