@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 8
+#define VIS_B200_ABI_VERSION 9
 
 /* status codes */
 #define VIS_OK            0
@@ -291,6 +291,70 @@ int vis_heatmap_overlay(const uint8_t* img, int64_t img_pitch, int h, int w,
                         const VisHeatDefect* defects, int n_defects, const float* kernels,
                         int final_ksize, int final_koff, const uint8_t* jet768,
                         float* scratch, uint8_t* dst, int64_t dst_pitch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Comparison panel and status stamp (SURVEY.md 8f "next" row 4).
+ * create_side_by_side_comparison (utils/image_utils.py:608-686): both frames cv2.resize()d to a height of 800
+ * (default interpolation INTER_LINEAR), a 40-row header and a 10-column divider filled with 45, two centred
+ * white Hershey labels.  create_status_stamp (utils/image_utils.py:689-739): a 4-channel canvas with a 4-px
+ * LINE_8 rectangle and a text.  Integer arithmetic throughout: bit-exact against OpenCV 4.13.
+ * ------------------------------------------------------------------------------------------ */
+/* what cv::resize does for INTER_LINEAR on 8-bit data (cv: resize.cpp): VIS_RESIZE_COPY when the sizes are equal,
+ * VIS_RESIZE_AREA2 when both scale factors are exactly 2 (OpenCV switches to INTER_AREA's (a+b+c+d+2)>>2 fast path),
+ * VIS_RESIZE_BILINEAR otherwise.                                                       [host] */
+#define VIS_RESIZE_COPY     0
+#define VIS_RESIZE_AREA2    1
+#define VIS_RESIZE_BILINEAR 2
+int vis_resize_linear_mode(int src_h, int src_w, int dst_h, int dst_w);
+/* one axis of the fixed-point bilinear resizer (cv: resize.cpp, the xofs/alpha and yofs/beta tables):
+ * ofs[d] = first source index, coef[2d], coef[2d+1] = 11-bit weights (saturate_cast<short>(w * 2048)) of ofs[d] and
+ * ofs[d] + 1.  is_x != 0 folds the border clamp into the table as OpenCV does for columns; rows keep the raw index
+ * (may be -1 or src_size - 1) and the kernel clamps the row it fetches.                 [host] */
+int vis_linear_table(int src_size, int dst_size, int is_x, int32_t* ofs, int16_t* coef);
+
+typedef struct VisPanel {        /* cv2.resize(src, (dst_w, dst_h)) placed at (org_x, org_y) of the canvas        */
+    const uint8_t* src;          /* device, 3-channel uint8 HWC                                                  */
+    int64_t        src_pitch;
+    int32_t        src_h, src_w;
+    int32_t        dst_h, dst_w;
+    int32_t        org_x, org_y;
+    int32_t        mode;         /* vis_resize_linear_mode                                                       */
+    int32_t        pad;
+    const int32_t* xofs;         /* device tables of vis_linear_table (VIS_RESIZE_BILINEAR only)                 */
+    const int16_t* alpha;
+    const int32_t* yofs;
+    const int16_t* beta;
+} VisPanel;
+/* canvas [h, w, 3] = `fill` everywhere except inside the panels (HOST array, <= 4, non-overlapping); one launch.
+ * Replaces utils/image_utils.py:637-679 (two cv2.resize calls, header/divider fill, hstack, vstack).  [device] */
+int vis_compose_panels(uint8_t* canvas, int64_t canvas_pitch, int h, int w, int fill,
+                       const VisPanel* panels, int n_panels, void* stream);
+
+/* generic draw list on top of the overlay rasteriser: each command becomes one group of leaves (like one VisBox),
+ * so vis_overlay_tiles / vis_overlay_draw(_cn) take the result unchanged.                */
+#define VIS_DRAW_LINE      1     /* cv2.line((x1,y1),(x2,y2), color, thickness, line_type)                        */
+#define VIS_DRAW_RECTANGLE 2     /* cv2.rectangle((x1,y1),(x2,y2), color, thickness >= 1, line_type)              */
+#define VIS_DRAW_CIRCLE    3     /* cv2.circle((x1,y1), x2 = radius, color, thickness: -1 filled or > 1, LINE_8)   */
+#define VIS_DRAW_TEXT      4     /* cv2.putText(text, (x1,y1), FONT_HERSHEY_SIMPLEX, font_scale, color, thickness) */
+typedef struct VisDrawCmd {
+    int32_t kind;
+    int32_t x1, y1, x2, y2;
+    int32_t thickness;
+    int32_t line_type;           /* 8 or 16 (LINE / RECTANGLE)                                                    */
+    uint8_t color[4];            /* B, G, R, A (A is used by 4-channel canvases only)                             */
+    double  font_scale;
+    char    text[64];            /* NUL-terminated, printable ASCII                                               */
+} VisDrawCmd;
+/* cv2.getTextSize(text, FONT_HERSHEY_SIMPLEX, font_scale, thickness)[0]; VIS_E_UNSUPPORTED for a character outside
+ * printable ASCII.                                                                     [host] */
+int vis_text_size(const char* text, double font_scale, int thickness, int* width, int* height);
+/* like vis_overlay_expand, for a draw list: n_cmds group headers followed by the ordered leaves.   [host] */
+int vis_draw_expand(int img_h, int img_w, const VisDrawCmd* cmds, int n_cmds,
+                    VisLeaf* leaves, int capacity, int* needed);
+/* vis_overlay_draw for canvases with `channels` = 3 or 4 interleaved bytes per pixel.   [device] */
+int vis_overlay_draw_cn(const VisOverlayFrame* frames, int n_frames, int channels, int copy_frames,
+                        const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
+                        const VisLeaf* leaves, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ when its CUDA library is missing.
 Contents
     resample_oracle.c   Pillow 8bpc resampler + Qwen2-VL normalize/patchify, restated in plain C
     cvdraw_oracle.c     OpenCV 4.13 drawing primitives used by draw_bounding_boxes, restated in plain C
+    cvresize_oracle.c   OpenCV 4.13 cv2.resize (INTER_LINEAR, 8-bit) used by create_side_by_side_comparison
     qwen2vl.py          smart_resize / thumbnail size rules / whole-frame preprocess (numpy + the C code)
     overlay.py          draw_bounding_boxes box logic on top of cvdraw_oracle.c
 
@@ -29,7 +30,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile the C restatements with gcc (oracle/Makefile)."""
-    srcs = [_DIR / "resample_oracle.c", _DIR / "cvdraw_oracle.c"]
+    srcs = [_DIR / "resample_oracle.c", _DIR / "cvdraw_oracle.c", _DIR / "cvresize_oracle.c"]
     stale = (not _LIB_PATH.exists()) or any(s.stat().st_mtime > _LIB_PATH.stat().st_mtime for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", str(_DIR)] + (["-B"] if force else []), check=True,
@@ -78,3 +79,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.ocv_put_text.restype = c.c_int
     L.ocv_get_text_size.argtypes = [c.c_char_p, c.c_double, c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int)]
     L.ocv_get_text_size.restype = c.c_int
+    # cv2.resize oracle (cvresize_oracle.c)
+    L.ocv_resize_linear_mode.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int]
+    L.ocv_resize_linear_mode.restype = c.c_int
+    L.ocv_resize_linear_u8.argtypes = [u8p, c.c_int, c.c_int, c.c_int64, c.c_int, u8p, c.c_int, c.c_int, c.c_int64]
+    L.ocv_resize_linear_u8.restype = c.c_int

@@ -16,6 +16,8 @@ What is recorded (versions of every binary are stored next to the vectors):
                    intercepted): the BGR array before the JPEG encode, stored in arrays.npz (tolerance-compared).
   * ``quality``    the reference's own ``src.safety.image_quality.assess_image_quality`` on lossless PNG files of seeded
                    frames — the full result dict.
+  * ``compare``    the reference's own ``create_side_by_side_comparison`` and ``create_status_stamp`` executed unmodified
+                   (imread / imwrite intercepted): sha256 of the array handed to ``cv2.imwrite``.
 The reference has no tests or vectors of its own for this path; these fixtures are the pin.
 """
 from __future__ import annotations
@@ -179,10 +181,60 @@ def overlay_label_goldens():
     return out
 
 
+def compare_cases():
+    """(name, (seed, h, w) of the original, (seed, h, w) of the annotated frame, labels or None)."""
+    return [
+        ("pair_1080p", (7500, 1080, 1920), (7501, 1080, 1920), None),
+        ("pair_vga", (7502, 480, 640), (7503, 480, 640), None),
+        ("pair_1600x1200_area", (7504, 1600, 1200), (7505, 1600, 1200), None),
+        ("pair_odd_and_uhd", (7506, 333, 517), (7507, 2160, 3840), None),
+        ("pair_800_copy", (7508, 800, 600), (7509, 800, 1000), None),
+        ("pair_logo_upscale", (7510, 100, 502), (7511, 100, 502), ("Logo (raw)", "Logo #2 ~ {annotated}")),
+        ("pair_mixed_area_bilinear", (7512, 1600, 1201), (7513, 1600, 900), ("A", "B")),
+    ]
+
+
+def stamp_cases():
+    return [("SAFE", (300, 100)), ("UNSAFE", (300, 100)), ("REQUIRES_HUMAN_REVIEW", (300, 100)),
+            ("SAFE", (200, 80)), ("UNSAFE", (640, 200)), ("anything", (97, 41))]
+
+
+def compare_goldens():
+    ref = import_reference_image_utils()
+    real_imread, real_imwrite = ref.cv2.imread, ref.cv2.imwrite
+    captured, out = {}, {"side_by_side": [], "stamp": []}
+    ref.cv2.imwrite = lambda path, img, *a: captured.__setitem__("output", img.copy()) or True
+    try:
+        for name, (s1, h1, w1), (s2, h2, w2), labels in compare_cases():
+            files = {"orig.png": synth.noise_frame(s1, h1, w1), "annot.png": synth.noise_frame(s2, h2, w2)}
+            ref.cv2.imread = lambda path, *a: files[Path(path).name].copy()
+            kw = {} if labels is None else {"labels": labels}
+            ref.create_side_by_side_comparison(Path("orig.png"), Path("annot.png"), Path("cmp/out.jpg"), **kw)
+            res = captured["output"]
+            out["side_by_side"].append({"name": name, "original": [s1, h1, w1], "annotated": [s2, h2, w2],
+                                        "labels": labels, "shape": list(res.shape), "sha256": sha(res)})
+            print("compare", name, res.shape, sha(res)[:16])
+        for verdict, size in stamp_cases():
+            ref.create_status_stamp(verdict, Path("cmp/stamp.png"), size)
+            res = captured["output"]
+            out["stamp"].append({"verdict": verdict, "size": list(size), "shape": list(res.shape), "sha256": sha(res),
+                                 "opaque_pixels": int((res[:, :, 3] > 0).sum())})
+            print("stamp", verdict, size, sha(res)[:16])
+    finally:
+        ref.cv2.imread, ref.cv2.imwrite = real_imread, real_imwrite
+    return out
+
+
 def main():
     if "--only-overlay-labels" in sys.argv:             # append / refresh the text-label overlay cases
         out = json.loads((HERE / "goldens.json").read_text())
         out["overlay"] = [r for r in out["overlay"] if not r["name"].startswith("labels_")] + overlay_label_goldens()
+        (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
+        print("updated", HERE / "goldens.json")
+        return
+    if "--only-compare" in sys.argv:                    # add / refresh the "compare" section of an existing file
+        out = json.loads((HERE / "goldens.json").read_text())
+        out["compare"] = compare_goldens()
         (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
         print("updated", HERE / "goldens.json")
         return
@@ -319,6 +371,7 @@ def main():
     arrays["jet_bgr"] = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)[0]
     np.savez_compressed(HERE / "arrays.npz", **arrays)
     out["quality"] = quality_goldens()
+    out["compare"] = compare_goldens()
     (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
     print("wrote", HERE / "goldens.json", HERE / "arrays.npz")
 

@@ -31,7 +31,7 @@ def _apply(out, w):
     kind = int(w[0] & 0xff)
     if kind <= GROUP:
         return
-    col = np.array([w[1] & 0xff, (w[1] >> 8) & 0xff, (w[1] >> 16) & 0xff], np.int64)
+    col = np.array([(w[1] >> (8 * k)) & 0xff for k in range(out.shape[2])], np.int64)     # B, G, R (, A)
     x0, x1 = int(w[10] & 0xffff), int((w[10] >> 16) & 0xffff)
     y0, y1 = int(w[11] & 0xffff), int((w[11] >> 16) & 0xffff)
     ys, xs = np.mgrid[y0:y1 + 1, x0:x1 + 1]

@@ -53,6 +53,16 @@ OVERLAY_TILE_DTYPE = np.dtype([("frame", np.int32), ("txy", np.int32), ("ref_beg
 OVERLAY_REF_DTYPE = np.dtype([("leaf_begin", np.int32), ("leaf_end", np.int32)], align=True)
 QUALITY_FRAME_DTYPE = np.dtype([("src", np.uint64), ("pitch", np.int64), ("h", np.int32), ("w", np.int32)], align=True)
 assert LEAF_DTYPE.itemsize == 48 and OVERLAY_FRAME_DTYPE.itemsize == 48
+RESIZE_COPY, RESIZE_AREA2, RESIZE_BILINEAR = 0, 1, 2
+PANEL_DTYPE = np.dtype([("src", np.uint64), ("src_pitch", np.int64), ("src_h", np.int32), ("src_w", np.int32),
+                        ("dst_h", np.int32), ("dst_w", np.int32), ("org_x", np.int32), ("org_y", np.int32),
+                        ("mode", np.int32), ("pad", np.int32), ("xofs", np.uint64), ("alpha", np.uint64),
+                        ("yofs", np.uint64), ("beta", np.uint64)], align=True)
+DRAW_LINE, DRAW_RECTANGLE, DRAW_CIRCLE, DRAW_TEXT = 1, 2, 3, 4
+DRAW_CMD_DTYPE = np.dtype([("kind", np.int32), ("x1", np.int32), ("y1", np.int32), ("x2", np.int32), ("y2", np.int32),
+                           ("thickness", np.int32), ("line_type", np.int32), ("color", np.uint8, (4,)),
+                           ("font_scale", np.float64), ("text", "S64")], align=True)
+assert PANEL_DTYPE.itemsize == 80 and DRAW_CMD_DTYPE.itemsize == 104
 
 EXPORTS = [
     "vis_abi_version", "vis_last_error", "vis_coeff_ksize", "vis_build_coeffs", "vis_build_lut",
@@ -62,6 +72,7 @@ EXPORTS = [
     "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_preprocess_fused_sched",
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
+    "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn",
 ]
 
 
@@ -84,7 +95,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 8:
+        if L.vis_abi_version() != 9:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -122,6 +133,12 @@ def _declare(L: C.CDLL) -> None:
     L.vis_heatmap_overlay.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp,
                                       C.c_int64, vp]
     L.vis_quality_stats.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.vis_resize_linear_mode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.vis_linear_table.argtypes = [C.c_int, C.c_int, C.c_int, i32p, vp]
+    L.vis_compose_panels.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.vis_text_size.argtypes = [C.c_char_p, C.c_double, C.c_int, ip, ip]
+    L.vis_draw_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
+    L.vis_overlay_draw_cn.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
     for name in EXPORTS:
         if name != "vis_last_error":
             getattr(L, name).restype = C.c_int

@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 INCLUDE = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libvis_b200.so"
 
-SOURCES = ["vis_host.cpp", "vis_generic.cu", "vis_fused.cu", "vis_fused_ws.cu", "vis_fused_sched.cu", "vis_fused_sched16.cu", "vis_overlay_host.cpp", "vis_overlay.cu", "vis_quality.cu", "vis_heatmap.cu"]
+SOURCES = ["vis_host.cpp", "vis_generic.cu", "vis_fused.cu", "vis_fused_ws.cu", "vis_fused_sched.cu", "vis_fused_sched16.cu", "vis_overlay_host.cpp", "vis_overlay.cu", "vis_quality.cu", "vis_heatmap.cu", "vis_compose.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

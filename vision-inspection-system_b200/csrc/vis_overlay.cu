@@ -28,12 +28,15 @@ __device__ __forceinline__ bool touches(const Tile& t, int wx, int wy) {
     return bx0 <= t.x1 && bx1 >= t.x0 && by0 <= t.y1 && by1 >= t.y0;
 }
 
+template <int CN>
 __device__ __forceinline__ void set_px(int* c, int col) {
     c[0] = col & 0xff; c[1] = (col >> 8) & 0xff; c[2] = (col >> 16) & 0xff;
+    if (CN == 4) c[3] = (unsigned)col >> 24;
 }
+template <int CN>
 __device__ __forceinline__ void blend_px(int* c, int col, int a) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < CN; ++k) {
         const int cc = (col >> (8 * k)) & 0xff;
         int v = c[k];
         v += ((cc - v) * a + 127) >> 8;
@@ -51,7 +54,8 @@ __device__ __forceinline__ int aa_alpha(const int* w, const int* filt, int s, in
 }
 
 // apply one leaf to the thread's 4 pixels (x .. x+3, row y); returns true when the leaf could have written
-__device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x, int y, int (*c)[3]) {
+template <int CN>
+__device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x, int y, int (*c)[CN]) {
     const int bx0 = w[10] & 0xffff, bx1 = (unsigned)w[10] >> 16, by0 = w[11] & 0xffff, by1 = (unsigned)w[11] >> 16;
     if (y < by0 || y > by1 || x + kPx - 1 < bx0 || x > bx1) return false;
     const int kind = w[0] & LEAF_KIND_MASK, col = w[1];
@@ -65,7 +69,7 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
             const int xx1 = (int)((lo + (aa ? 65535 : 32768)) >> 16), xx2 = (int)((hi + (aa ? 0 : 32768)) >> 16);
 #pragma unroll
             for (int j = 0; j < kPx; ++j)
-                if (x + j >= xx1 && x + j <= xx2) set_px(c[j], col);
+                if (x + j >= xx1 && x + j <= xx2) set_px<CN>(c[j], col);
             return true;
         }
         case LEAF_SPANS: {
@@ -75,7 +79,7 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
             if (hw == 0xff) return false;
 #pragma unroll
             for (int j = 0; j < kPx; ++j)
-                if (abs(x + j - w[2]) <= hw) set_px(c[j], col);
+                if (abs(x + j - w[2]) <= hw) set_px<CN>(c[j], col);
             return true;
         }
         case LEAF_LINE8: {
@@ -85,7 +89,7 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
                 for (int j = 0; j < kPx; ++j) {
                     const int i = x + j - m0;
                     const bool on = i >= 0 && i <= ecount && (int)(((int64_t)w[4] + (int64_t)w[5] * i) >> 16) == y;
-                    if (on || (x + j == w[6] && y == w[7])) set_px(c[j], col);
+                    if (on || (x + j == w[6] && y == w[7])) set_px<CN>(c[j], col);
                 }
             } else {
                 const int i = y - m0;
@@ -93,7 +97,7 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
                 const int xx = (int)(((int64_t)w[4] + (int64_t)w[5] * i) >> 16);
 #pragma unroll
                 for (int j = 0; j < kPx; ++j)
-                    if ((in && x + j == xx) || (x + j == w[6] && y == w[7])) set_px(c[j], col);
+                    if ((in && x + j == xx) || (x + j == w[6] && y == w[7])) set_px<CN>(c[j], col);
             }
             return true;
         }
@@ -107,7 +111,7 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
                     const int64_t minor = (int64_t)w[4] + (int64_t)w[5] * s;
                     const int d = y - ((int)(minor >> 16) - 1);
                     if (d < 0 || d > 2) continue;
-                    blend_px(c[j], col, aa_alpha(w, filt, s, e0 - s, minor, d));
+                    blend_px<CN>(c[j], col, aa_alpha(w, filt, s, e0 - s, minor, d));
                 }
             } else {
                 const int s = y - m0;
@@ -118,7 +122,7 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
                 for (int j = 0; j < kPx; ++j) {
                     const int d = x + j - base;
                     if (d < 0 || d > 2) continue;
-                    blend_px(c[j], col, aa_alpha(w, filt, s, e0 - s, minor, d));
+                    blend_px<CN>(c[j], col, aa_alpha(w, filt, s, e0 - s, minor, d));
                 }
             }
             return true;
@@ -130,10 +134,10 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
 
 // frame copy for out-of-place drawing: rows of `row_bytes` bytes, 16-byte vectors when everything is aligned
 __global__ void __launch_bounds__(256)
-k_overlay_copy(const VisOverlayFrame* __restrict__ frames) {
+k_overlay_copy(const VisOverlayFrame* __restrict__ frames, int channels) {
     const VisOverlayFrame f = frames[blockIdx.y];
     if (f.src == f.dst) return;
-    int64_t rows = f.h, row_bytes = (int64_t)f.w * 3;
+    int64_t rows = f.h, row_bytes = (int64_t)f.w * channels;
     if (f.src_pitch == row_bytes && f.dst_pitch == row_bytes) { row_bytes *= rows; rows = 1; }     // one long row
     const bool vec = (((uintptr_t)f.src | (uintptr_t)f.dst | (uint64_t)f.src_pitch | (uint64_t)f.dst_pitch) & 15) == 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -167,6 +171,7 @@ k_overlay_copy(const VisOverlayFrame* __restrict__ frames) {
 // sub-group the host binned into this tile (in leaf order) the 32 lanes test the 32 leaf boxes against the
 // sub-tile, the touching leaves are staged IN ORDER in the warp's shared-memory slots and applied per pixel in list
 // order.
+template <int CN>
 __global__ void __launch_bounds__(kThreads)
 k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile* __restrict__ tiles,
                 const VisOverlayRef* __restrict__ refs, const VisLeaf* __restrict__ leaves) {
@@ -188,9 +193,9 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
     const int nv = y < f.h ? max(0, min(kPx, f.w - x)) : 0;      // valid pixels of this lane
 
     const VisLeaf* fl = leaves + f.group_begin;       // the frame's leaf array; leaf indices are relative to it
-    int c[kPx][3];
+    int c[kPx][CN];
     bool loaded = false, dirty = false;
-    uint8_t* const px = f.dst + (size_t)y * f.dst_pitch + (size_t)x * 3;
+    uint8_t* const px = f.dst + (size_t)y * f.dst_pitch + (size_t)x * CN;
     const bool vec = ((f.dst_pitch | (int64_t)(uintptr_t)f.dst) & 3) == 0;
     int (*my_leaf)[VIS_LEAF_WORDS] = s_leaf[warp];
 
@@ -211,7 +216,15 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
             if (!lm) continue;
             if (!loaded) {                                    // first leaf that reaches this sub-tile: fetch the pixels
                 loaded = true;
-                if (nv == kPx && vec) {
+                if (CN == 4 && nv == kPx && vec) {
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
+#pragma unroll
+                    for (int j = 0; j < kPx; ++j) {
+                        const uint32_t a = q[j];
+#pragma unroll
+                        for (int k = 0; k < CN; ++k) c[j][k] = (a >> (8 * k)) & 0xff;
+                    }
+                } else if (nv == kPx && vec) {
                     const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
                     const uint32_t a = q[0], b = q[1], d = q[2];
                     c[0][0] = a & 0xff; c[0][1] = (a >> 8) & 0xff; c[0][2] = (a >> 16) & 0xff;
@@ -222,7 +235,7 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
 #pragma unroll
                     for (int j = 0; j < kPx; ++j)
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) c[j][q] = j < nv ? (int)px[j * 3 + q] : 0;
+                        for (int q = 0; q < CN; ++q) c[j][q] = j < nv ? (int)px[j * CN + q] : 0;
                 }
             }
             if (lhit) {
@@ -233,13 +246,18 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
             __syncwarp();
             const int n_leaf = __popc(lm);
             if (nv > 0)
-                for (int q = 0; q < n_leaf; ++q) dirty |= apply_leaf(my_leaf[q], s_filter, x, y, c);
+                for (int q = 0; q < n_leaf; ++q) dirty |= apply_leaf<CN>(my_leaf[q], s_filter, x, y, c);
             __syncwarp();
         }
     }
 
     if (!dirty) return;
-    if (nv == kPx && vec) {
+    if (CN == 4 && nv == kPx && vec) {
+        uint32_t* q = reinterpret_cast<uint32_t*>(px);
+#pragma unroll
+        for (int j = 0; j < kPx; ++j)
+            q[j] = (uint32_t)c[j][0] | ((uint32_t)c[j][1] << 8) | ((uint32_t)c[j][2] << 16) | ((uint32_t)c[j][CN - 1] << 24);
+    } else if (nv == kPx && vec) {
         uint32_t* q = reinterpret_cast<uint32_t*>(px);
         q[0] = (uint32_t)c[0][0] | ((uint32_t)c[0][1] << 8) | ((uint32_t)c[0][2] << 16) | ((uint32_t)c[1][0] << 24);
         q[1] = (uint32_t)c[1][1] | ((uint32_t)c[1][2] << 8) | ((uint32_t)c[2][0] << 16) | ((uint32_t)c[2][1] << 24);
@@ -247,28 +265,36 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
     } else {
         for (int j = 0; j < nv; ++j)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) px[j * 3 + q] = (uint8_t)c[j][q];
+            for (int q = 0; q < CN; ++q) px[j * CN + q] = (uint8_t)c[j][q];
     }
 }
 
 }  // namespace
 
-extern "C" int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int copy_frames,
-                                const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
-                                const VisLeaf* leaves, void* stream) {
-    if (!frames || n_frames <= 0 || n_frames > 65535 || n_tiles < 0 || (n_tiles && (!tiles || !refs || !leaves))) {
-        vis::set_error("vis_overlay_draw: bad arguments (frames=%d tiles=%d)", n_frames, n_tiles);
+extern "C" int vis_overlay_draw_cn(const VisOverlayFrame* frames, int n_frames, int channels, int copy_frames,
+                                   const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
+                                   const VisLeaf* leaves, void* stream) {
+    if (!frames || n_frames <= 0 || n_frames > 65535 || n_tiles < 0 || (n_tiles && (!tiles || !refs || !leaves)) ||
+        (channels != 3 && channels != 4)) {
+        vis::set_error("vis_overlay_draw: bad arguments (frames=%d tiles=%d channels=%d)", n_frames, n_tiles, channels);
         return VIS_E_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (copy_frames) {                            // out of place: dst = src first, then draw in place on dst
-        k_overlay_copy<<<dim3(64, n_frames), 256, 0, st>>>(frames);
+        k_overlay_copy<<<dim3(64, n_frames), 256, 0, st>>>(frames, channels);
         const int rc = vis::check_launch("vis_overlay_draw(copy)");
         if (rc != VIS_OK) return rc;
     }
     if (n_tiles > 0) {
-        k_overlay_tiles<<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
+        if (channels == 3) k_overlay_tiles<3><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
+        else               k_overlay_tiles<4><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
         return vis::check_launch("vis_overlay_draw");
     }
     return VIS_OK;
+}
+
+extern "C" int vis_overlay_draw(const VisOverlayFrame* frames, int n_frames, int copy_frames,
+                                const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
+                                const VisLeaf* leaves, void* stream) {
+    return vis_overlay_draw_cn(frames, n_frames, 3, copy_frames, tiles, n_tiles, refs, leaves, stream);
 }

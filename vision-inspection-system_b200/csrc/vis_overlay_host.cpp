@@ -211,7 +211,9 @@ class Emitter {
     int count() const { return n_; }
     bool ok() const { return glyph_ok_; }
 
-    void set_color(int b, int g, int r) { color_ = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16); }
+    void set_color(int b, int g, int r, int a = 0) {
+        color_ = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16) | ((uint32_t)a << 24);
+    }
 
     // ---- group headers: slots [0, n) lead the leaf array, one per box -------------------------------
     void reserve_headers(int n) {
@@ -704,6 +706,80 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
     if (needed) *needed = em.count();
     if (em.count() > capacity) {
         vis::set_error("vis_overlay_expand: %d leaves needed, capacity %d", em.count(), capacity);
+        return VIS_E_CAPACITY;
+    }
+    return em.count();
+}
+
+// cv2.getTextSize(text, FONT_HERSHEY_SIMPLEX, font_scale, thickness)[0] — used by the callers of the draw list to
+// centre their labels (utils/image_utils.py:657, :665, :731 in the reference).
+extern "C" int vis_text_size(const char* text, double font_scale, int thickness, int* width, int* height) {
+    if (!text || !width || !height) {
+        vis::set_error("vis_text_size: null argument");
+        return VIS_E_INVALID;
+    }
+    Emitter em(1, 1, nullptr, 0);
+    if (!em.text_size(text, font_scale, thickness, width, height)) {
+        vis::set_error("vis_text_size: '%s' has a character outside printable ASCII", text);
+        return VIS_E_UNSUPPORTED;
+    }
+    return VIS_OK;
+}
+
+// Draw list -> leaves: one group per command, so tile binning and the draw kernel treat a command like a box.
+// The commands are the cv2 calls of create_side_by_side_comparison (:658, :666) and create_status_stamp (:726, :733).
+extern "C" int vis_draw_expand(int img_h, int img_w, const VisDrawCmd* cmds, int n_cmds,
+                               VisLeaf* leaves, int capacity, int* needed) {
+    if (img_h <= 0 || img_w <= 0 || img_h > 32767 || img_w > 32767 || n_cmds < 0 || (n_cmds && !cmds) ||
+        capacity < 0 || (capacity && !leaves)) {
+        vis::set_error("vis_draw_expand: bad arguments (h=%d w=%d cmds=%d)", img_h, img_w, n_cmds);
+        return VIS_E_INVALID;
+    }
+    Emitter em(img_h, img_w, leaves, capacity);
+    em.reserve_headers(n_cmds);
+    for (int i = 0; i < n_cmds; ++i) {
+        const VisDrawCmd& c = cmds[i];
+        em.begin_group();
+        em.set_color(c.color[0], c.color[1], c.color[2], c.color[3]);
+        const bool lt_ok = c.line_type == 8 || c.line_type == 16;
+        switch (c.kind) {
+            case VIS_DRAW_LINE:
+                if (!lt_ok || c.thickness < 1 || c.thickness > 255) goto bad;
+                em.line(c.x1, c.y1, c.x2, c.y2, c.thickness, c.line_type);
+                break;
+            case VIS_DRAW_RECTANGLE:
+                if (!lt_ok || c.thickness < 1 || c.thickness > 255) goto bad;
+                em.rectangle(c.x1, c.y1, c.x2, c.y2, c.thickness, c.line_type);
+                break;
+            case VIS_DRAW_CIRCLE:
+                if (c.x2 < 0 || c.x2 > 16383 || !(c.thickness < 0 || (c.thickness > 1 && c.thickness <= 255))) goto bad;
+                if (c.thickness < 0) em.circle_filled(c.x1, c.y1, c.x2);
+                else em.circle_outline(c.x1, c.y1, c.x2, c.thickness);
+                break;
+            case VIS_DRAW_TEXT: {
+                char text[65];
+                std::memcpy(text, c.text, 64);
+                text[64] = 0;
+                int tw = 0, th = 0;
+                if (c.thickness < 1 || c.thickness > 255 || !(c.font_scale > 0)) goto bad;
+                if (!em.text_size(text, c.font_scale, c.thickness, &tw, &th)) {
+                    vis::set_error("vis_draw_expand: text '%s' has a character outside printable ASCII", text);
+                    return VIS_E_UNSUPPORTED;
+                }
+                em.put_text(text, c.x1, c.y1, c.font_scale, c.thickness);
+                break;
+            }
+            default:
+            bad:
+                vis::set_error("vis_draw_expand: command %d (kind %d, thickness %d, line type %d) is not drawable",
+                               i, c.kind, c.thickness, c.line_type);
+                return VIS_E_INVALID;
+        }
+        em.end_group(i);
+    }
+    if (needed) *needed = em.count();
+    if (em.count() > capacity) {
+        vis::set_error("vis_draw_expand: %d leaves needed, capacity %d", em.count(), capacity);
         return VIS_E_CAPACITY;
     }
     return em.count();

@@ -609,6 +609,96 @@ class Engine:
         self._keepalive_h = (d_kern, scratch)
         return out
 
+    # ------------------------------------------------------------------ comparison panel / status stamp
+    def _draw_list(self, canvas: torch.Tensor, cmds: np.ndarray) -> int:
+        """Apply a draw list (``compare.*_commands``) in place on a [H, W, 3|4] uint8 CUDA canvas; returns launches.
+        The expanded plan (device leaves, tiles, refs) is cached per (canvas size, draw list)."""
+        from . import compare as CP
+        from . import overlay as O
+        h, w, cn = int(canvas.shape[0]), int(canvas.shape[1]), int(canvas.shape[2])
+        up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
+        cache = self.__dict__.setdefault("_draw_plans", {})
+        key = (h, w, cmds.tobytes())
+        plan = cache.get(key)
+        if plan is None:
+            leaves = CP.expand_commands(cmds, w, h)
+            tiles, refs = O.touched_tiles(leaves, len(cmds), w, h)
+            tl = np.zeros(len(tiles), N.OVERLAY_TILE_DTYPE)
+            if len(tiles):
+                tl["txy"], tl["ref_begin"], tl["ref_end"] = tiles[:, 0], tiles[:, 1], tiles[:, 2]
+            if len(cache) >= 64:
+                cache.clear()
+            plan = cache[key] = (len(tl), up(tl) if len(tl) else None, up(np.ascontiguousarray(refs)) if len(tl) else None,
+                                 up(leaves) if len(tl) else None)
+        n_tiles, d_tiles, d_refs, d_leaves = plan
+        if n_tiles == 0:
+            return 0
+        desc = np.zeros(1, N.OVERLAY_FRAME_DTYPE)
+        desc["src"] = desc["dst"] = canvas.data_ptr()
+        desc["src_pitch"] = desc["dst_pitch"] = canvas.stride(0)
+        desc["h"], desc["w"] = h, w
+        desc["group_begin"], desc["group_end"] = 0, len(cmds)
+        d_desc = up(desc)
+        N.check(self.L.vis_overlay_draw_cn(d_desc.data_ptr(), 1, cn, 0, d_tiles.data_ptr(), n_tiles, d_refs.data_ptr(),
+                                           d_leaves.data_ptr(), _stream_ptr()), "vis_overlay_draw_cn")
+        self._keepalive_d = (d_desc, d_tiles, d_refs, d_leaves)
+        return 1
+
+    def _linear_tables(self, src_size: int, dst_size: int, is_x: bool) -> list:
+        """Device copies of one axis of the bilinear tables (``vis_linear_table``), cached per geometry."""
+        from . import compare as CP
+        cache = self.__dict__.setdefault("_linear_cache", {})
+        key = (src_size, dst_size, is_x)
+        if key not in cache:
+            if len(cache) >= 256:
+                cache.clear()
+            cache[key] = [torch.from_numpy(a).to(self.device) for a in CP.linear_tables(src_size, dst_size, is_x)]
+        return cache[key]
+
+    def side_by_side(self, original: torch.Tensor, annotated: torch.Tensor, labels=None) -> torch.Tensor:
+        """``create_side_by_side_comparison`` for two BGR uint8 HWC CUDA frames: both resized to a height of 800 as
+        ``cv2.resize`` does, a 40-row header and a 10-column divider of gray 45, two centred white labels.  Returns the
+        [840, W1 + 10 + W2, 3] canvas the reference hands to ``cv2.imwrite``; bit-exact.  Two launches."""
+        from . import compare as CP
+        labels = CP.DEFAULT_LABELS if labels is None else labels
+        keep, panels, org_x = [], np.zeros(2, N.PANEL_DTYPE), 0
+        for i, f in enumerate((original, annotated)):
+            self._check_u8(f)
+            if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
+            h, w = int(f.shape[0]), int(f.shape[1])
+            dw = CP.panel_width(h, w)
+            if dw < 1:
+                raise ValueError(f"frame {w}x{h} is too narrow for an {CP.TARGET_HEIGHT}-row panel")
+            mode = N.check(self.L.vis_resize_linear_mode(h, w, CP.TARGET_HEIGHT, dw), "vis_resize_linear_mode")
+            p = panels[i]
+            p["src"], p["src_pitch"], p["src_h"], p["src_w"] = f.data_ptr(), f.stride(0), h, w
+            p["dst_h"], p["dst_w"], p["org_x"], p["org_y"], p["mode"] = CP.TARGET_HEIGHT, dw, org_x, CP.HEADER_HEIGHT, mode
+            if mode == N.RESIZE_BILINEAR:
+                dev = self._linear_tables(w, dw, True) + self._linear_tables(h, CP.TARGET_HEIGHT, False)
+                keep += dev
+                p["xofs"], p["alpha"], p["yofs"], p["beta"] = (t.data_ptr() for t in dev)
+            org_x += dw + CP.DIVIDER_WIDTH
+        left_w, right_w = int(panels[0]["dst_w"]), int(panels[1]["dst_w"])
+        total_w = left_w + CP.DIVIDER_WIDTH + right_w
+        canvas = torch.empty((CP.HEADER_HEIGHT + CP.TARGET_HEIGHT, total_w, 3), dtype=torch.uint8, device=self.device)
+        N.check(self.L.vis_compose_panels(canvas.data_ptr(), canvas.stride(0), int(canvas.shape[0]), total_w, CP.BAR_GRAY,
+                                          panels.ctypes.data_as(C.c_void_p), 2, _stream_ptr()), "vis_compose_panels")
+        self._keepalive_c = keep
+        self.last_launches = 1 + self._draw_list(canvas, CP.header_commands(left_w, right_w, labels))
+        return canvas
+
+    def status_stamp(self, verdict: str, size=(300, 100)) -> torch.Tensor:
+        """``create_status_stamp``: the [height, width, 4] BGRA stamp (transparent background, 4-px border, verdict
+        text) as a CUDA tensor; bit-exact against the reference's array."""
+        from . import compare as CP
+        width, height = int(size[0]), int(size[1])
+        if width <= 0 or height <= 0:
+            raise ValueError("stamp size must be positive")
+        canvas = torch.zeros((height, width, 4), dtype=torch.uint8, device=self.device)
+        self.last_launches = self._draw_list(canvas, CP.stamp_commands(verdict, width, height))
+        return canvas
+
     # ------------------------------------------------------------------ image quality statistics
     def quality_stats(self, frames):
         """BGR uint8 HWC CUDA frames (``[B,H,W,3]`` tensor or list) -> (int64 CUDA tensor [B, 3] = sum(gray),

@@ -9,6 +9,9 @@ Same names, arguments, return types and error behaviour as the reference:
                         criticality="medium") -> Path           utils/image_utils.py:148-317
     create_heatmap_overlay(image_path, defects, output_path,
                            alpha=0.4, ...) -> Path              utils/image_utils.py:320-604  (tolerance-specified)
+    create_side_by_side_comparison(original_path, annotated_path,
+                                   output_path, labels) -> Path utils/image_utils.py:608-686
+    create_status_stamp(verdict, output_path, size) -> Path     utils/image_utils.py:689-739
 
 plus the entry points the reference delegates to a remote server today (the Qwen2-VL image processor behind
 ``_encode_image_optimized``, src/agents/vlm_inspector.py:46-88 / src/agents/vlm_auditor.py:85-108):
@@ -222,4 +225,35 @@ def create_heatmap_overlay(image_path: Path, defects: list, output_path: Path, a
         raise ValueError(f"Failed to load image: {image_path}")
     out = _engine().heatmap(torch.from_numpy(img).cuda(), defects)
     cv2.imwrite(str(output_path), out.cpu().numpy())
+    return output_path
+
+
+def create_side_by_side_comparison(original_path: Path, annotated_path: Path, output_path: Path,
+                                   labels: tuple = ("Original Input", "AI Analysis Layer")) -> Path:
+    """Side-by-side comparison image (utils/image_utils.py:608-686): both files resized to a height of 800, a labelled
+    header bar and a divider.  Raises ``ValueError("Failed to load images for comparison")`` like the reference."""
+    import cv2
+    import torch
+    logger.info("Creating side-by-side comparison")
+    original = cv2.imread(str(original_path))
+    annotated = cv2.imread(str(annotated_path))
+    if original is None or annotated is None:
+        raise ValueError("Failed to load images for comparison")
+    result = _engine().side_by_side(torch.from_numpy(original).cuda(), torch.from_numpy(annotated).cuda(), labels)
+    output_path = Path(output_path)
+    output_path.parent.mkdir(parents=True, exist_ok=True)
+    cv2.imwrite(str(output_path), result.cpu().numpy())
+    logger.info("Saved comparison image: %s", output_path)
+    return output_path
+
+
+def create_status_stamp(verdict: str, output_path: Path, size: tuple = (300, 100)) -> Path:
+    """Status stamp PNG with a transparent background: "SAFE" -> PASSED, "UNSAFE" -> REJECTED, anything else -> REVIEW
+    (utils/image_utils.py:689-739)."""
+    import cv2
+    stamp = _engine().status_stamp(verdict, size)
+    output_path = Path(output_path)
+    output_path.parent.mkdir(parents=True, exist_ok=True)
+    cv2.imwrite(str(output_path), stamp.cpu().numpy())
+    logger.info("Saved status stamp: %s", output_path)
     return output_path
