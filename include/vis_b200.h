@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 9
+#define VIS_B200_ABI_VERSION 10
 
 /* status codes */
 #define VIS_OK            0
@@ -355,6 +355,44 @@ int vis_draw_expand(int img_h, int img_w, const VisDrawCmd* cmds, int n_cmds,
 int vis_overlay_draw_cn(const VisOverlayFrame* frames, int n_frames, int channels, int copy_frames,
                         const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
                         const VisLeaf* leaves, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * JPEG codec stage on the GPU (SURVEY.md 8f "next" row 1) — binding of NVIDIA's nvJPEG (libnvjpeg.so.12), not a
+ * kernel of this library.  Replaces, for JPEG files, Image.open / cv2.imread (utils/image_utils.py:39-41, :170;
+ * src/agents/vlm_inspector.py:59) in front of the kernels and cv2.imwrite / img.save(JPEG) (utils/image_utils.py:316;
+ * src/agents/vlm_inspector.py:73) behind them.  nvJPEG's IDCT / chroma upsampling differ from libjpeg-turbo's:
+ * decoded pixels are specified with a tolerance against the reference's decoders, not bit-exact.
+ * The ONE family that owns device memory: nvJPEG allocates work buffers behind the opaque handle.  A handle is not
+ * thread-safe: one per thread of use.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VisJpeg VisJpeg;
+#define VIS_JPEG_BACKEND_DEFAULT    0
+#define VIS_JPEG_BACKEND_HYBRID     1   /* Huffman decode on the CPU                                              */
+#define VIS_JPEG_BACKEND_GPU_HYBRID 2   /* Huffman decode on the GPU for large batches of baseline streams         */
+#define VIS_JPEG_BACKEND_HARDWARE   3   /* the NVJPG engine (baseline, single scan)                                */
+#define VIS_JPEG_CSS_444 0
+#define VIS_JPEG_CSS_422 1
+#define VIS_JPEG_CSS_420 2
+/* interpolate_chroma != 0: triangle-filter chroma upsampling (closest to libjpeg-turbo's "fancy upsampling").
+ * VIS_E_UNSUPPORTED when the backend does not exist on this GPU.                        [host] */
+int  vis_jpeg_create(int backend, int interpolate_chroma, VisJpeg** out);
+void vis_jpeg_destroy(VisJpeg* j);
+/* size, component count and chroma subsampling (VIS_JPEG_CSS_*, 6 = gray, -1 = other) of a JPEG stream   [host] */
+int  vis_jpeg_info(VisJpeg* j, const uint8_t* data, int64_t length, int* width, int* height, int* components,
+                   int* subsampling);
+/* data: HOST JPEG stream; dst: DEVICE [h, w, 3] uint8 interleaved (RGB, or BGR when bgr != 0)            [device] */
+int  vis_jpeg_decode(VisJpeg* j, const uint8_t* data, int64_t length, uint8_t* dst, int64_t dst_pitch, int h, int w,
+                     int bgr, void* stream);
+/* n streams in one call (nvjpegDecodeBatched); dst[i] must hold the size vis_jpeg_info reports          [device] */
+int  vis_jpeg_decode_batch(VisJpeg* j, int n, const uint8_t* const* data, const int64_t* lengths, uint8_t* const* dst,
+                           const int64_t* dst_pitch, int bgr, int cpu_threads, void* stream);
+/* host buffer size that always holds the encoded stream of an h x w frame                                [host] */
+int64_t vis_jpeg_encode_bound(int h, int w);
+/* src: DEVICE [h, w, 3] uint8 interleaved; out: HOST buffer.  Synchronises `stream` (the stream of bytes is handed
+ * back on the host).  VIS_E_CAPACITY with *length = needed size when `out` is too small.          [device, syncs] */
+int  vis_jpeg_encode(VisJpeg* j, const uint8_t* src, int64_t src_pitch, int h, int w, int bgr, int quality,
+                     int subsampling, int optimized_huffman, uint8_t* out, int64_t capacity, int64_t* length,
+                     void* stream);
 
 #ifdef __cplusplus
 }

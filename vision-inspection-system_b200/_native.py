@@ -54,6 +54,8 @@ OVERLAY_REF_DTYPE = np.dtype([("leaf_begin", np.int32), ("leaf_end", np.int32)],
 QUALITY_FRAME_DTYPE = np.dtype([("src", np.uint64), ("pitch", np.int64), ("h", np.int32), ("w", np.int32)], align=True)
 assert LEAF_DTYPE.itemsize == 48 and OVERLAY_FRAME_DTYPE.itemsize == 48
 RESIZE_COPY, RESIZE_AREA2, RESIZE_BILINEAR = 0, 1, 2
+JPEG_BACKEND_DEFAULT, JPEG_BACKEND_HYBRID, JPEG_BACKEND_GPU_HYBRID, JPEG_BACKEND_HARDWARE = 0, 1, 2, 3
+JPEG_CSS_444, JPEG_CSS_422, JPEG_CSS_420, JPEG_CSS_GRAY = 0, 1, 2, 6
 PANEL_DTYPE = np.dtype([("src", np.uint64), ("src_pitch", np.int64), ("src_h", np.int32), ("src_w", np.int32),
                         ("dst_h", np.int32), ("dst_w", np.int32), ("org_x", np.int32), ("org_y", np.int32),
                         ("mode", np.int32), ("pad", np.int32), ("xofs", np.uint64), ("alpha", np.uint64),
@@ -73,6 +75,8 @@ EXPORTS = [
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
     "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn",
+    "vis_jpeg_create", "vis_jpeg_destroy", "vis_jpeg_info", "vis_jpeg_decode", "vis_jpeg_decode_batch",
+    "vis_jpeg_encode_bound", "vis_jpeg_encode",
 ]
 
 
@@ -95,7 +99,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 9:
+        if L.vis_abi_version() != 10:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -139,8 +143,20 @@ def _declare(L: C.CDLL) -> None:
     L.vis_text_size.argtypes = [C.c_char_p, C.c_double, C.c_int, ip, ip]
     L.vis_draw_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
     L.vis_overlay_draw_cn.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
+    L.vis_jpeg_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.vis_jpeg_destroy.argtypes = [vp]
+    L.vis_jpeg_info.argtypes = [vp, vp, C.c_int64, ip, ip, ip, ip]
+    L.vis_jpeg_decode.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp]
+    L.vis_jpeg_decode_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+    L.vis_jpeg_encode_bound.argtypes = [C.c_int, C.c_int]
+    L.vis_jpeg_encode.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int64,
+                                  C.POINTER(C.c_int64), vp]
     for name in EXPORTS:
-        if name != "vis_last_error":
+        if name in ("vis_jpeg_destroy",):
+            getattr(L, name).restype = None
+        elif name == "vis_jpeg_encode_bound":
+            getattr(L, name).restype = C.c_int64
+        elif name != "vis_last_error":
             getattr(L, name).restype = C.c_int
 
 

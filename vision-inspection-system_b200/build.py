@@ -17,13 +17,14 @@ CSRC = PKG_DIR / "csrc"
 INCLUDE = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libvis_b200.so"
 
-SOURCES = ["vis_host.cpp", "vis_generic.cu", "vis_fused.cu", "vis_fused_ws.cu", "vis_fused_sched.cu", "vis_fused_sched16.cu", "vis_overlay_host.cpp", "vis_overlay.cu", "vis_quality.cu", "vis_heatmap.cu", "vis_compose.cu"]
+SOURCES = ["vis_host.cpp", "vis_generic.cu", "vis_fused.cu", "vis_fused_ws.cu", "vis_fused_sched.cu", "vis_fused_sched16.cu", "vis_overlay_host.cpp", "vis_overlay.cu", "vis_quality.cu", "vis_heatmap.cu", "vis_compose.cu", "vis_jpeg.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
     "-shared",
+    "-lnvjpeg",                      # CUDA toolkit library (codec stage, csrc/vis_jpeg.cpp)
 ]
 
 

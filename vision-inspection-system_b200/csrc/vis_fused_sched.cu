@@ -437,7 +437,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const int mk = hkt > vkt ? hkt : vkt;
     // tap class -> kernel: <= 8 taps: 8-slot register windows (pixel_values only); <= 16 taps: 16-slot kernel
     // and, past 16 taps, the same kernel with a pull-order horizontal role (classes 20/24/28/32; 24/32 for pixel_values)
-    int cls = mk <= 12 ? 12 : mk <= 16 ? 16 : mk <= 20 ? 20 : mk <= 24 ? 24 : mk <= 28 ? 28 : mk <= 32 ? 32 : 0;
+    int cls = mk <= 12 ? 12 : mk <= 13 ? 13 : mk <= 14 ? 14 : mk <= 16 ? 16 : mk <= 20 ? 20 : mk <= 24 ? 24 : mk <= 28 ? 28 : mk <= 32 ? 32 : 0;
     if (!u8) cls = mk <= 6 ? 6 : mk <= 8 ? 8 : cls == 20 ? 24 : cls == 28 ? 32 : cls;
     if (!cls) return unsupported("more than 32 taps");
     const int ring = cls <= 8 ? 8 : 16;
@@ -446,6 +446,9 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const int max_w = ring == 8 ? kMaxStripW : visf::sched16_max_strip_w();
     std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
     int per_index = 1;
+    // an exact class (13, 14) may be too tight for the virtual ends of the far-border samples: widen it
+    while ((cls == 13 || cls == 14) && (!schedule_ends(hb, dst_w, cls, 1, hl) || !schedule_ends(vb, dst_h, cls, 1, vl)))
+        cls = cls == 13 ? 14 : 16;
     if (!schedule_ends(hb, dst_w, cls, 1, hl) || !schedule_ends(vb, dst_h, cls, 1, vl)) {
         per_index = 2;                            // mild upscale on some axis: two samples per input index
         if (ring != 8) return unsupported("upscaling with more than 8 taps");
@@ -541,7 +544,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
 
 int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt, int per_index,
                            int32_t* rec, int64_t rec_capacity) {
-    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8 && (kt < 12 || kt > 32 || kt % 4)) ||
+    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8 && kt != 13 && kt != 14 && (kt < 12 || kt > 32 || kt % 4)) ||
         per_index < 1 || per_index > 2) {
         vis::set_error("vis_sched_pack_records: bad arguments");
         return VIS_E_INVALID;

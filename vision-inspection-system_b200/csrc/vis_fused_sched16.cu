@@ -68,11 +68,16 @@ inline Layout16 make_layout16(int stage_pitch, int strip_w, int cls) {
 
 template <int KT>
 __device__ __forceinline__ void load_coeffs16(int (&k)[KT], uint32_t addr) {
-    static_assert(KT % 4 == 0 && KT >= 12 && KT <= 32, "tap classes 12..32 in steps of 4");
+    static_assert(KT >= 12 && KT <= 32, "tap classes 12..32");
+    // a record holds KT coefficient slots + (first, end) in (KT + 5) & ~3 words: the last 16-byte load of an odd class
+    // reads into those trailing words and the surplus is dropped
 #pragma unroll
-    for (int q = 0; q < KT / 4; ++q) {
+    for (int q = 0; q < (KT + 3) / 4; ++q) {
         const uint4 a = lds128(addr + 16 * q);
-        k[4 * q] = (int)a.x; k[4 * q + 1] = (int)a.y; k[4 * q + 2] = (int)a.z; k[4 * q + 3] = (int)a.w;
+        k[4 * q] = (int)a.x;
+        if (4 * q + 1 < KT) k[4 * q + 1] = (int)a.y;
+        if (4 * q + 2 < KT) k[4 * q + 2] = (int)a.z;
+        if (4 * q + 3 < KT) k[4 * q + 3] = (int)a.w;
     }
 }
 
@@ -469,7 +474,7 @@ int sched16_layout_bytes(int stage_pitch, int strip_w, int cls) { return make_la
 
 int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
                    const float* lut768, float* pixel_values, cudaStream_t st) {
-    if (sc.kt < 12 || sc.kt > 32 || sc.kt % 4 || sc.ring != 16 || sc.n_subs != kHWarps || sc.per_index != 1) {
+    if (sc.kt < 12 || sc.kt > 32 || sc.ring != 16 || sc.n_subs != kHWarps || sc.per_index != 1) {
         vis::set_error("vis_fused_sched16: schedule of another kernel class (ring %d, %d taps, %d sub-ranges)", sc.ring, sc.kt, sc.n_subs);
         return VIS_E_INVALID;
     }
@@ -483,6 +488,8 @@ int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t
                         : launch16<KT, ((KT + 5) & ~3), false>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st))
     switch (sc.kt) {
         case 12: return VIS_L16(12);
+        case 13: return VIS_L16(13);          // exact classes of the strong downscales (4K -> 1316x728, the 1.875x and
+        case 14: return VIS_L16(14);          // 2x LANCZOS thumbnails): 13 taps cost 13 MACs, not 16
         case 16: return VIS_L16(16);
         case 24: return VIS_L16(24);
         case 32: return VIS_L16(32);

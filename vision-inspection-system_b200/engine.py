@@ -699,6 +699,16 @@ class Engine:
         self.last_launches = self._draw_list(canvas, CP.stamp_commands(verdict, width, height))
         return canvas
 
+    # ------------------------------------------------------------------ JPEG codec stage (nvJPEG, opt-in)
+    def jpeg_codec(self, backend: str = "gpu_hybrid"):
+        """The engine's nvJPEG codec for ``backend`` (created on first use; chroma upsampling interpolated, the closest
+        match to libjpeg-turbo).  Tolerance-specified against the host decoders: see ``jpeg.py``."""
+        from .jpeg import JpegCodec
+        cache = self.__dict__.setdefault("_jpeg", {})
+        if backend not in cache:
+            cache[backend] = JpegCodec(self.device, backend, True)
+        return cache[backend]
+
     # ------------------------------------------------------------------ image quality statistics
     def quality_stats(self, frames):
         """BGR uint8 HWC CUDA frames (``[B,H,W,3]`` tensor or list) -> (int64 CUDA tensor [B, 3] = sum(gray),

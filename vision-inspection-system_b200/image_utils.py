@@ -13,6 +13,9 @@ Same names, arguments, return types and error behaviour as the reference:
                                    output_path, labels) -> Path utils/image_utils.py:608-686
     create_status_stamp(verdict, output_path, size) -> Path     utils/image_utils.py:689-739
 
+Every file-level function takes ``codec="host"`` (default: PIL / cv2 codecs exactly as the reference) or
+``codec="nvjpeg"`` (JPEG decode / encode on the GPU through nvJPEG; tolerance-specified, see jpeg.py).
+
 plus the entry points the reference delegates to a remote server today (the Qwen2-VL image processor behind
 ``_encode_image_optimized``, src/agents/vlm_inspector.py:46-88 / src/agents/vlm_auditor.py:85-108):
 
@@ -95,6 +98,63 @@ def validate_image(image_path: Path, allowed_extensions: list = None, max_size_m
     return True, None
 
 
+_CODECS = ("host", "nvjpeg")
+_JPEG_SUFFIXES = (".jpg", ".jpeg", ".jpe")
+
+
+def _check_codec(codec: str) -> None:
+    if codec not in _CODECS:
+        raise ValueError(f"codec must be one of {_CODECS}, got {codec!r}")
+
+
+def _imread_cuda(path, codec: str, bgr: bool = True):
+    """``cv2.imread(path)`` as a BGR uint8 CUDA tensor, or None when the file cannot be decoded.  ``codec="nvjpeg"``
+    decodes JPEG streams on the GPU (a few levels away from libjpeg-turbo, see jpeg.py); anything else, and every file
+    with ``codec="host"``, goes through cv2 exactly like the reference."""
+    import cv2
+    import torch
+    _check_codec(codec)
+    if codec == "nvjpeg":
+        from .jpeg import is_jpeg
+        try:
+            data = Path(path).read_bytes()
+        except OSError:
+            return None
+        if is_jpeg(data):
+            try:
+                return _engine().jpeg_codec().decode(data, bgr=bgr)
+            except Exception as e:          # CMYK, arithmetic coding, damaged stream: let the host decoder decide
+                logger.debug("nvJPEG declined %s (%s); host decode", path, e)
+    img = cv2.imread(str(path))
+    if img is None:
+        return None
+    return torch.from_numpy(img if bgr else np.ascontiguousarray(img[:, :, ::-1])).cuda()
+
+
+def _imwrite_cuda(path, frame, codec: str) -> None:
+    """``cv2.imwrite(path, frame)`` for a BGR uint8 CUDA tensor; ``codec="nvjpeg"`` encodes .jpg/.jpeg on the GPU with
+    cv2's defaults (quality 95, 4:2:0)."""
+    import cv2
+    _check_codec(codec)
+    path = Path(path)
+    if codec == "nvjpeg" and path.suffix.lower() in _JPEG_SUFFIXES and frame.shape[2] == 3:
+        path.write_bytes(_engine().jpeg_codec().encode(frame, quality=95, subsampling="4:2:0", bgr=True))
+        return
+    cv2.imwrite(str(path), frame.cpu().numpy())
+
+
+def decode_image(image_path: Path, bgr: bool = False, codec: str = "nvjpeg"):
+    """File -> [H, W, 3] uint8 CUDA tensor (RGB by default): the device-side counterpart of ``load_image`` for callers
+    that feed ``preprocess_for_vlm`` / ``Engine.annotate`` directly.  Same errors as ``load_image``."""
+    image_path = Path(image_path)
+    if not image_path.exists():
+        raise FileNotFoundError(f"Image not found: {image_path}")
+    t = _imread_cuda(image_path, codec, bgr)
+    if t is None:
+        raise ValueError(f"Failed to load image: {image_path}")
+    return t
+
+
 def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int) -> Image.Image:
     """``img.resize(size, filt)`` (reducing_gap=None) with the resampling done on the GPU."""
     import torch
@@ -159,16 +219,37 @@ def _to_rgb_array(image) -> np.ndarray:
 
 
 def preprocess_for_vlm(images, *, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
-                       role: str | None = None):
+                       role: str | None = None, codec: str = "host"):
     """Frames -> (``pixel_values`` float32 CUDA tensor [sum N_i, 1176], ``image_grid_thw`` int64 tensor [B, 3]).
 
     ``images``: one or a list of PIL images / paths / RGB uint8 HWC arrays / CUDA uint8 HWC tensors.
     ``role``: None, or "inspector"/"auditor" to first apply that agent's thumbnail limit (2048 / 1024, LANCZOS).
+    ``codec``: "host" decodes paths with PIL like the reference; "nvjpeg" decodes the JPEG paths of the list in one
+    batched GPU call (tolerance-specified, see jpeg.py).
     """
     import torch
     eng = _engine()
+    _check_codec(codec)
     if not isinstance(images, (list, tuple)):
         images = [images]
+    images = list(images)
+    if codec == "nvjpeg":
+        from .jpeg import is_jpeg
+        streams = {}
+        for i, im in enumerate(images):
+            if isinstance(im, (str, Path)):
+                if not Path(im).exists():
+                    raise FileNotFoundError(f"Image not found: {im}")
+                data = Path(im).read_bytes()
+                if is_jpeg(data):
+                    streams[i] = data
+        if streams:
+            try:
+                decoded = eng.jpeg_codec().decode_batch(list(streams.values()))
+                for i, t in zip(streams, decoded):
+                    images[i] = t
+            except Exception as e:
+                logger.debug("nvJPEG declined the batch (%s); host decode", e)
     frames = []
     for im in images:
         if isinstance(im, torch.Tensor):
@@ -191,58 +272,51 @@ normalize = preprocess_for_vlm
 
 
 def draw_bounding_boxes(image_path: Path, boxes: list, output_path: Path, confidence_threshold: str = "low",
-                        criticality: str = "medium") -> Path:
+                        criticality: str = "medium", codec: str = "host") -> Path:
     """Annotated copy of ``image_path`` at ``output_path``: dashed/solid 2-px box, numbered marker, as the reference.
 
     Raises ``ValueError("Failed to load image: ...")`` when the file cannot be read; invalid boxes are skipped with a
     warning (never raised), exactly like the reference.
     """
-    import cv2
-    import torch
-    img = cv2.imread(str(image_path))
-    if img is None:
+    dev = _imread_cuda(image_path, codec)
+    if dev is None:
         raise ValueError(f"Failed to load image: {image_path}")
-    dev = torch.from_numpy(img).cuda()
     _engine().annotate([dev], [boxes], confidence_threshold, criticality, inplace=True)
-    cv2.imwrite(str(output_path), dev.cpu().numpy())
+    _imwrite_cuda(output_path, dev, codec)
     return output_path
 
 
 def create_heatmap_overlay(image_path: Path, defects: list, output_path: Path, alpha: float = 0.4,
                            actual_model_size=None, confidence_threshold: str = "low",
-                           criticality: str = "medium") -> Path:
+                           criticality: str = "medium", codec: str = "host") -> Path:
     """Semi-transparent JET heat map over the defect regions, saved at ``output_path`` (utils/image_utils.py:320-604).
 
     As in the reference, ``alpha``, ``actual_model_size``, ``confidence_threshold`` and ``criticality`` are accepted and
     unused: every defect is drawn and the blend is fixed at 60 % image / 40 % heat map.  Raises
     ``ValueError("Failed to load image: ...")`` when the file cannot be read.
     """
-    import cv2
-    import torch
     logger.info("Creating heatmap overlay for %s", Path(image_path).name)
-    img = cv2.imread(str(image_path))
+    img = _imread_cuda(image_path, codec)
     if img is None:
         raise ValueError(f"Failed to load image: {image_path}")
-    out = _engine().heatmap(torch.from_numpy(img).cuda(), defects)
-    cv2.imwrite(str(output_path), out.cpu().numpy())
+    out = _engine().heatmap(img.contiguous(), defects)
+    _imwrite_cuda(output_path, out, codec)
     return output_path
 
 
 def create_side_by_side_comparison(original_path: Path, annotated_path: Path, output_path: Path,
-                                   labels: tuple = ("Original Input", "AI Analysis Layer")) -> Path:
+                                   labels: tuple = ("Original Input", "AI Analysis Layer"), codec: str = "host") -> Path:
     """Side-by-side comparison image (utils/image_utils.py:608-686): both files resized to a height of 800, a labelled
     header bar and a divider.  Raises ``ValueError("Failed to load images for comparison")`` like the reference."""
-    import cv2
-    import torch
     logger.info("Creating side-by-side comparison")
-    original = cv2.imread(str(original_path))
-    annotated = cv2.imread(str(annotated_path))
+    original = _imread_cuda(original_path, codec)
+    annotated = _imread_cuda(annotated_path, codec)
     if original is None or annotated is None:
         raise ValueError("Failed to load images for comparison")
-    result = _engine().side_by_side(torch.from_numpy(original).cuda(), torch.from_numpy(annotated).cuda(), labels)
+    result = _engine().side_by_side(original, annotated, labels)
     output_path = Path(output_path)
     output_path.parent.mkdir(parents=True, exist_ok=True)
-    cv2.imwrite(str(output_path), result.cpu().numpy())
+    _imwrite_cuda(output_path, result, codec)
     logger.info("Saved comparison image: %s", output_path)
     return output_path
 
