@@ -24,6 +24,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+#ifndef VIS_SPIN_NS
+#define VIS_SPIN_NS 32          // back-off between polls of a phase that is not complete yet
+#endif
+#ifndef VIS_WAIT_HINT_NS
+#define VIS_WAIT_HINT_NS 0      // > 0: pass a suspend-time hint to try_wait in the slow path (the warp sleeps in hardware)
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -34,13 +40,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 // slow path of a wait, kept out of line so the hot loops stay small (the kernels are instruction-cache sensitive):
 // back off between polls, and trap instead of hanging the GPU if the phase never completes (lost bulk copy)
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+#if VIS_WAIT_HINT_NS > 0
+    for (unsigned spins = 0; !mbar_try_wait_hint(bar, parity, VIS_WAIT_HINT_NS); ++spins)
+        if (spins > (1u << 24)) __trap();
+#else
     for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins) {
         if (spins > (1u << 26)) __trap();
-        __nanosleep(32);
+        __nanosleep(VIS_SPIN_NS);
     }
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);

@@ -118,6 +118,19 @@ class Engine:
             g.plans[vsplit] = p
         return p
 
+    def _pick_segs(self, items_per_seg: int, src_h: int, max_segs: int) -> int:
+        """Row segments per frame for a scheduled launch.  The persistent kernels hand items (strip x segment) to the
+        CTAs round-robin, so the launch takes ceil(items / SMs) rounds: 448 items on 148 SMs run 4 rounds at 76 %
+        occupancy of the machine.  Pick the count that maximises rounds-efficiency times the cost of a segment start
+        (its first rows are read again by the segment above and the role pipeline refills: ~1.3 % of a 2160-row frame)."""
+        best, best_score = 1, 0.0
+        for segs in range(1, max(1, min(16, max_segs)) + 1):
+            rounds = items_per_seg * segs / self.sm_count
+            score = rounds / -(-items_per_seg * segs // self.sm_count) * src_h / (src_h + (segs - 1) * 28.0)
+            if score > best_score * 1.01:                 # prefer fewer segments unless the gain is real
+                best, best_score = segs, score
+        return best
+
     def _sched(self, g: _Geometry, pitch: int, n_segs: int):
         """VisSched parameter block for (geometry, row pitch, row segments), or None if the geometry needs the
         general kernel (upscaling, > 8 taps, schedule too large)."""
@@ -192,7 +205,7 @@ class Engine:
             head = self._resize_sched(h, w, out_h, out_w, filt, int(f0.stride(0)), 1)
             if head is not None:
                 per = int(np.frombuffer(head[0][:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["n_strips"])
-                segs = max(1, min(16, -(-2 * self.sm_count // (len(frames) * per))))
+                segs = self._pick_segs(len(frames) * per, h, out_h // 14)
                 plan = self._resize_sched(h, w, out_h, out_w, filt, int(f0.stride(0)), segs)
         if plan is None:
             outs = []
@@ -332,7 +345,7 @@ class Engine:
                         rest_parts.append(sel)
                         continue
                     per = int(np.frombuffer(head[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["n_strips"])
-                    segs = vsplit if vsplit is not None else max(1, min(8, -(-want // (len(sel) * per))))
+                    segs = vsplit if vsplit is not None else self._pick_segs(len(sel) * per, g.src_h, g.dst_h // 28)
                     sched = self._sched(g, int(pitch), max(1, min(segs, g.dst_h // 14)))
                     hd = np.frombuffer(sched[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]
                     ref = np.zeros(len(sel), N.FRAME_REF_DTYPE)
