@@ -23,7 +23,13 @@ using namespace visf;
 
 namespace {
 
-constexpr int kHWarps = 11, kVWarps = 6, kSWarps = 2;    // H is the heavy role at these scales (profiles/r01_fused_sched16_4k.txt)
+#ifndef VIS_S16_HWARPS
+#define VIS_S16_HWARPS 12
+#endif
+#ifndef VIS_S16_VWARPS
+#define VIS_S16_VWARPS 6
+#endif
+constexpr int kHWarps = VIS_S16_HWARPS, kVWarps = VIS_S16_VWARPS, kSWarps = 2;    // H is the heavy role at these scales (profiles/r01_fused_sched16_4k.txt)
 // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
 constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
 constexpr int kThreads16 = (kHWarps + kVWarps + kSWarps + 1) * 32;      // 640: 96 registers per thread
