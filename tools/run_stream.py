@@ -45,6 +45,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=512, help="frames of the whole job")
     ap.add_argument("--gather", action="store_true")
+    ap.add_argument("--gather-frames", type=int, default=512,
+                    help="the optional gather collects the Inspector rows of the first G frames of the job on rank 0 "
+                         "(the consumer's chunk; all 8192 frames would be 127 GiB on one GPU)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -91,26 +94,31 @@ def main():
             "rank_bytes_min_over_max": float(min(x.item() for x in loads) / max(x.item() for x in loads))}
     if args.gather and world > 1:
         pv, grid = res["inspector"]
+        n_gather = min(args.gather_frames, args.frames)
+        k_local = sum(1 for i in mine if i < n_gather)               # `mine` is sorted: the chunk is a prefix of it
+        rows_local = int((grid[:k_local, 0] * grid[:k_local, 1] * grid[:k_local, 2]).sum())
+        pv, grid = pv[:rows_local], grid[:k_local]
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        S.gather_patches(pv[:1], grid[:1], mine[:1], dst=0)           # opens the peer connections (not timed)
         dist.barrier()
         torch.cuda.synchronize()
         g0.record()
-        all_pv, all_grid = S.gather_patches(pv, grid, mine, dst=0)
+        all_pv, all_grid = S.gather_patches(pv, grid, mine[:k_local], dst=0)
         g1.record()
         torch.cuda.synchronize()
         if rank == 0:
             # rank 0 recomputes two remote frames itself and compares the gathered rows bit for bit
             rows = (all_grid[:, 0] * all_grid[:, 1] * all_grid[:, 2]).tolist()
             starts = np.concatenate([[0], np.cumsum(rows)])
-            ok = len(rows) == args.frames
-            remote = [i for i in range(args.frames) if i not in set(mine)][:2]
+            ok = len(rows) == n_gather
+            remote = [i for i in range(n_gather) if i not in set(mine)][:2]
             for i in remote:
                 f = torch.from_numpy(synth.noise_frame(9000 + i % 2, *shapes[i])).cuda()
                 want, _ = eng.preprocess(role_inputs(eng, [f], G.INSPECTOR_MAX_SIZE))
                 ok = ok and torch.equal(all_pv[starts[i]:starts[i + 1]], want)
             sec = g0.elapsed_time(g1) / 1e3
             recv = (all_pv.shape[0] - pv.shape[0]) * 1176 * 4
-            line["gather"] = {"ok": bool(ok), "rows_total": int(all_pv.shape[0]), "bytes_received": int(recv),
+            line["gather"] = {"ok": bool(ok), "frames": n_gather, "rows_total": int(all_pv.shape[0]), "bytes_received": int(recv),
                               "seconds": sec, "receiver_GBps": recv / sec / 1e9}
     if rank == 0:
         print(json.dumps(line), flush=True)

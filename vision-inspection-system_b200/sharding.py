@@ -63,12 +63,15 @@ def gather_patches(pixel_values: torch.Tensor, image_grid_thw: torch.Tensor, fra
     dist.all_gather(metas, meta, group=group)
     metas = [m.cpu().tolist() for m in metas]
     payload = torch.cat([ids, grid.reshape(-1)]).to(dev)            # ids then grid, one small message per rank
+    # one batched group of point-to-point operations: the peers' transfers run concurrently into the receiver
+    # (unbatched send/recv pairs on the default group are serialised one after the other)
     if rank != dst:
         if ids.numel():
-            dist.send(payload, dst, group=group)
-            dist.send(pixel_values.contiguous(), dst, group=group)
+            ops = [dist.P2POp(dist.isend, payload, dst, group), dist.P2POp(dist.isend, pixel_values.contiguous(), dst, group)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
         return None, None
-    parts = []
+    parts, ops, pending = [], [], []
     for r in range(world):
         rows, frames = metas[r]
         if frames == 0:
@@ -77,9 +80,13 @@ def gather_patches(pixel_values: torch.Tensor, image_grid_thw: torch.Tensor, fra
             parts.append((ids, grid, pixel_values))
             continue
         buf = torch.empty(frames * 4, dtype=torch.int64, device=dev)
-        dist.recv(buf, r, group=group)
         pv = torch.empty((rows, pixel_values.shape[1]), dtype=pixel_values.dtype, device=dev)
-        dist.recv(pv, r, group=group)
+        ops += [dist.P2POp(dist.irecv, buf, r, group), dist.P2POp(dist.irecv, pv, r, group)]
+        pending.append((frames, buf, pv))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for frames, buf, pv in pending:
         buf = buf.cpu()
         parts.append((buf[:frames], buf[frames:].reshape(frames, 3), pv))
     # restore original frame order: rows of a frame are contiguous inside its rank's tensor
