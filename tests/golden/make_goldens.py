@@ -18,6 +18,8 @@ What is recorded (versions of every binary are stored next to the vectors):
                    frames — the full result dict.
   * ``compare``    the reference's own ``create_side_by_side_comparison`` and ``create_status_stamp`` executed unmodified
                    (imread / imwrite intercepted): sha256 of the array handed to ``cv2.imwrite``.
+  * ``agents``     the reference's own ``_encode_image_optimized`` bodies (Inspector and Auditor), extracted unmodified from
+                   src/agents/*.py and executed on seeded input files: sha256 of the returned data URI.
 The reference has no tests or vectors of its own for this path; these fixtures are the pin.
 """
 from __future__ import annotations
@@ -225,10 +227,69 @@ def compare_goldens():
     return out
 
 
+def agent_cases():
+    """(name, seed, (h, w), mode, file suffix, role, max_size or None) — inputs are written losslessly (PNG) or as the
+    JPEG the case names, then handed to the reference's function as a path."""
+    return [
+        ("inspector_1080p_png", 7600, (1080, 1920), "RGB", ".png", "inspector", None),        # fits: no thumbnail
+        ("inspector_4k_png", 7601, (2160, 3840), "RGB", ".png", "inspector", None),            # -> 2048x1152
+        ("auditor_1080p_png", 7602, (1080, 1920), "RGB", ".png", "auditor", None),             # -> 1024x576
+        ("auditor_4k_png", 7603, (2160, 3840), "RGB", ".png", "auditor", None),                # -> 1024x576, 25 taps
+        ("inspector_rgba_png", 7604, (1200, 1600), "RGBA", ".png", "inspector", 1024),         # alpha -> premultiplied resample -> RGB
+        ("auditor_gray_png", 7605, (900, 1500), "L", ".png", "auditor", None),
+        ("inspector_jpeg_input", 7606, (1536, 2048), "RGB", ".jpg", "inspector", 1024),        # 2x: no draft mode
+        ("auditor_small_png", 7607, (480, 640), "RGB", ".png", "auditor", None),
+    ]
+
+
+def agent_goldens():
+    """The reference's own ``_encode_image_optimized`` bodies (src/agents/vlm_inspector.py, vlm_auditor.py), extracted
+    UNMODIFIED from the files with ``ast`` (the modules themselves import langchain / groq, absent here) and executed."""
+    import ast
+    import base64
+    import io
+    import logging
+    from typing import Optional
+    from PIL import Image
+    funcs = {}
+    for role, rel in (("inspector", "src/agents/vlm_inspector.py"), ("auditor", "src/agents/vlm_auditor.py")):
+        src = (REFERENCE / rel).read_text()
+        tree = ast.parse(src)
+        fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "_encode_image_optimized")
+        ns = {"Image": Image, "io": io, "base64": base64, "Path": Path, "Optional": Optional}
+        exec(compile(ast.Module([fn], []), rel, "exec"), ns)
+        funcs[role] = ns["_encode_image_optimized"]
+
+    class Self:
+        max_image_size = 2048                     # config.max_image_dimension (utils/config.py:184)
+        logger = logging.getLogger("ref_agent")
+
+    tmp = Path(tempfile.mkdtemp(prefix="agent_"))
+    out = []
+    for name, seed, shape, mode, suffix, role, max_size in agent_cases():
+        path = tmp / f"{name}{suffix}"
+        synth.write_agent_input(synth.agent_input_image(seed, shape, mode), path)
+        args = (path,) if max_size is None else (path, max_size)
+        uri = funcs[role](Self(), *args)
+        data = base64.b64decode(uri.split(",", 1)[1])
+        size = Image.open(io.BytesIO(data)).size
+        out.append({"name": name, "seed": seed, "shape": list(shape), "mode": mode, "suffix": suffix, "role": role,
+                    "max_size": max_size, "input_sha256": hashlib.sha256(path.read_bytes()).hexdigest(),
+                    "uri_sha256": hashlib.sha256(uri.encode()).hexdigest(), "jpeg_bytes": len(data), "jpeg_size": list(size)})
+        print("agent", name, size, len(data), out[-1]["uri_sha256"][:16])
+    return out
+
+
 def main():
     if "--only-overlay-labels" in sys.argv:             # append / refresh the text-label overlay cases
         out = json.loads((HERE / "goldens.json").read_text())
         out["overlay"] = [r for r in out["overlay"] if not r["name"].startswith("labels_")] + overlay_label_goldens()
+        (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
+        print("updated", HERE / "goldens.json")
+        return
+    if "--only-agents" in sys.argv:                     # add / refresh the "agents" section of an existing file
+        out = json.loads((HERE / "goldens.json").read_text())
+        out["agents"] = agent_goldens()
         (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
         print("updated", HERE / "goldens.json")
         return
@@ -372,6 +433,7 @@ def main():
     np.savez_compressed(HERE / "arrays.npz", **arrays)
     out["quality"] = quality_goldens()
     out["compare"] = compare_goldens()
+    out["agents"] = agent_goldens()
     (HERE / "goldens.json").write_text(json.dumps(out, indent=1))
     print("wrote", HERE / "goldens.json", HERE / "arrays.npz")
 

@@ -10,6 +10,10 @@ Layout
     engine.py        per-GPU engine: device tables, batch planning, kernel launches
     image_utils.py   drop-in mirror of the reference's utils/image_utils functions on this path
     overlay.py       draw_bounding_boxes box logic -> VisBox -> leaves -> overlay kernel
+    compare.py       create_side_by_side_comparison / create_status_stamp host logic (panel list, draw list)
+    heatmap.py       create_heatmap_overlay host logic; image_quality.py: assess_image_quality
+    jpeg.py          nvJPEG codec stage behind the C ABI (opt-in, tolerance-specified)
+    agents.py        the callers either side: encode_image_optimized, build_visual_evidence_images
     sharding.py      image sharding across the GPUs of one box, optional NCCL gather
     synth.py         seeded synthetic workloads of BASELINE.json's configs
 

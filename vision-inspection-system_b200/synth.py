@@ -110,3 +110,25 @@ def heatmap_cases() -> list:
         ("full_360x480_all_invalid", small["full"], invalid, 1),
         ("hgrad_360x480_empty", small["hgrad"], [], 1),
     ]
+
+
+def agent_input_image(seed: int, shape, mode: str):
+    """PIL input of an ``encode_image_optimized`` case: low-passed pattern (even seeds) or noise (odd seeds) in mode
+    RGB / L / RGBA (noise alpha).  Shared by tests/golden/make_goldens.py and the tests."""
+    from PIL import Image
+    h, w = shape
+    rgb = pattern_frames(h, w)["lowpass"] if seed % 2 == 0 else noise_frame(seed, h, w)
+    if mode == "RGB":
+        return Image.fromarray(rgb)
+    if mode == "L":
+        return Image.fromarray(rgb[:, :, 0].copy())
+    alpha = noise_frame(seed + 1000, h, w)[:, :, 0]
+    return Image.fromarray(np.dstack([rgb, alpha]))
+
+
+def write_agent_input(img, path) -> None:
+    """Lossless PNG, or the JPEG (quality 92) the case names."""
+    if str(path).endswith(".jpg"):
+        img.save(path, format="JPEG", quality=92)
+    else:
+        img.save(path, format="PNG", compress_level=1)
