@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 10
+#define VIS_B200_ABI_VERSION 11
 
 /* status codes */
 #define VIS_OK            0
@@ -50,6 +50,12 @@ int vis_coeff_ksize(int in_size, int out_size, int filter);
 /* k[out_size*ksize] (zero padded), bounds[out_size*2] = (first input index, tap count) */
 int vis_build_coeffs(int in_size, int out_size, int filter, int32_t* k, int32_t* bounds, int* ksize_out);
 
+/* the same tables for a fractional source box [in0, in1) of the axis (Resample.c precompute_coeffs with in0 / in1;
+ * ImagingResample takes a float box): what Image.resize(..., box=...) and the thumbnail's reduce pre-pass need.  [host] */
+int vis_coeff_ksize_box(float in0, float in1, int out_size, int filter);
+int vis_build_coeffs_box(int in_size, float in0, float in1, int out_size, int filter, int32_t* k, int32_t* bounds,
+                         int* ksize_out);
+
 /* 768-entry normalisation table: lut[v*3+c] = (f32(f64(v)*rescale) - f32(mean[c])) / f32(std[c])
  * Replaces tf:image_transforms.py:118-122 (rescale) + :427-439 (normalize) — exact because a
  * uint8 input admits only 256x3 distinct results.                                  [host] */
@@ -68,6 +74,14 @@ int vis_resample_h_u8(const uint8_t* src, int64_t src_pitch, int rows, int in_w,
 int vis_resample_v_u8(const uint8_t* src, int64_t src_pitch, int in_h, int row_bytes,
                       uint8_t* dst, int64_t dst_pitch, int out_h,
                       const int32_t* k, const int32_t* bounds, int ksize, void* stream);
+
+/* Image.reduce((fx, fy), box) — libImaging/Reduce.c, the integer box-average pre-pass Image.thumbnail / Image.resize
+ * insert (reducing_gap = 2.0) when the frame is >= 4x larger than the target (src/agents/vlm_inspector.py:64,
+ * src/agents/vlm_auditor.py:91): every output sample is ((sum + n/2) * M(n)) >> 24 over the n source pixels of its
+ * fx x fy cell (clipped at the right / bottom edge of the box), M(n) = (uint32)(2^32f / (256 n)) in float arithmetic.
+ * box: (x0, y0, x1, y1) source region; dst: [ceil((y1-y0)/fy), ceil((x1-x0)/fx), channels].          [device] */
+int vis_reduce_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int channels, int fx, int fy,
+                  int x0, int y0, int x1, int y1, uint8_t* dst, int64_t dst_pitch, void* stream);
 
 /* resized RGB uint8 HWC [h,w,3] (h,w multiples of 28) -> rows [row0, row0 + (h/14)*(w/14)) of
  * pixel_values [*,1176] f32 in Qwen2-VL patch order (tf:models/qwen2_vl/image_processing_pil_qwen2_vl.py:182-214):

@@ -61,6 +61,14 @@ def _declare(L: ctypes.CDLL) -> None:
     L.orc_coeffs.restype = c.c_int
     L.orc_resize.argtypes = [u8p, c.c_int, c.c_int, c.c_int, u8p, c.c_int, c.c_int, c.c_int]
     L.orc_resize.restype = c.c_int
+    L.orc_ksize_box.argtypes = [c.c_float, c.c_float, c.c_int, c.c_int]
+    L.orc_ksize_box.restype = c.c_int
+    L.orc_coeffs_box.argtypes = [c.c_int, c.c_float, c.c_float, c.c_int, c.c_int, i32p, i32p]
+    L.orc_coeffs_box.restype = c.c_int
+    L.orc_resize_box.argtypes = [u8p, c.c_int, c.c_int, c.c_int, u8p, c.c_int, c.c_int, c.c_int, f32p]
+    L.orc_resize_box.restype = c.c_int
+    L.orc_reduce.argtypes = [u8p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, i32p, u8p]
+    L.orc_reduce.restype = c.c_int
     L.orc_lut.argtypes = [f32p, f32p, c.c_double, f32p]
     L.orc_lut.restype = None
     L.orc_patchify.argtypes = [u8p, c.c_int, c.c_int, f32p, f32p]

@@ -153,13 +153,70 @@ def preprocess(frames, min_pixels: int = DEFAULT_MIN_PIXELS, max_pixels: int = D
     return np.concatenate(rows, axis=0), np.asarray(grids, np.int64)
 
 
-def agent_thumbnail(frame: np.ndarray, max_size: int) -> np.ndarray:
-    """Geometry half of ``_encode_image_optimized`` (src/agents/vlm_inspector.py:59-69): LANCZOS thumbnail to fit
-    ``max_size`` (2048 Inspector, 1024 Auditor); the JPEG round trip is a codec step and is excluded."""
+def reduce(img: np.ndarray, factor, box=None) -> np.ndarray:
+    """``PIL.Image.fromarray(img).reduce(factor, box)`` for uint8 HWC input (libImaging/Reduce.c)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, ch = img.shape
+    fx, fy = factor if isinstance(factor, (tuple, list)) else (factor, factor)
+    box = np.asarray((0, 0, w, h) if box is None else box, np.int32)
+    out = np.empty((-(-(int(box[3]) - int(box[1])) // fy), -(-(int(box[2]) - int(box[0])) // fx), ch), np.uint8)
+    rc = lib().orc_reduce(_u8p(img), h, w, ch, fx, fy, _i32p(box), _u8p(out))
+    if rc:
+        raise RuntimeError(f"orc_reduce failed ({rc})")
+    return out
+
+
+def resize_box(img: np.ndarray, out_h: int, out_w: int, filt: int, box) -> np.ndarray:
+    """``Image.resize((out_w, out_h), filt, box=box, reducing_gap=None)`` (the core ImagingResample with a float box)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, ch = img.shape
+    if h > w * 100 and out_h < h:                           # tall image: vertical pass first (PIL:Image.py:2431-2435)
+        tmp = resize_box(img, out_h, w, filt, (0, box[1], w, box[3]))
+        return resize_box(tmp, out_h, out_w, filt, (box[0], 0, box[2], out_h))
+    out = np.empty((out_h, out_w, ch), np.uint8)
+    fbox = np.asarray(box, np.float32)                      # ImagingResample takes float box[4]
+    rc = lib().orc_resize_box(_u8p(img), h, w, ch, _u8p(out), out_h, out_w, filt, _f32p(fbox))
+    if rc:
+        raise RuntimeError(f"orc_resize_box failed ({rc})")
+    return out
+
+
+_FILTER_SUPPORT = {BICUBIC: 2.0, LANCZOS: 3.0}
+
+
+def reducing_plan(width: int, height: int, out_w: int, out_h: int, filt: int, box=None, reducing_gap: float = 2.0):
+    """The pre-pass ``Image.resize(..., reducing_gap)`` inserts (PIL:Image.py:2407-2424): returns None when no
+    reduction applies, else ((factor_x, factor_y), reduce_box ints, box floats relative to the reduced image)."""
+    box = (0, 0, width, height) if box is None else box
+    factor_x = int((box[2] - box[0]) / out_w / reducing_gap) or 1
+    factor_y = int((box[3] - box[1]) / out_h / reducing_gap) or 1
+    if factor_x <= 1 and factor_y <= 1:
+        return None
+    support = _FILTER_SUPPORT[filt] - 0.5                               # Image._get_safe_box
+    sx, sy = support * (box[2] - box[0]) / out_w, support * (box[3] - box[1]) / out_h
+    rb = (max(0, int(box[0] - sx)), max(0, int(box[1] - sy)),
+          min(width, math.ceil(box[2] + sx)), min(height, math.ceil(box[3] + sy)))
+    new_box = ((box[0] - rb[0]) / factor_x, (box[1] - rb[1]) / factor_y,
+               (box[2] - rb[0]) / factor_x, (box[3] - rb[1]) / factor_y)
+    return (factor_x, factor_y), rb, new_box
+
+
+def resize_reducing(img: np.ndarray, out_h: int, out_w: int, filt: int, box=None, reducing_gap: float = 2.0) -> np.ndarray:
+    """``Image.resize((out_w, out_h), filt, box, reducing_gap)`` for uint8 HWC input: reduce + boxed resample."""
+    h, w = img.shape[:2]
+    plan = reducing_plan(w, h, out_w, out_h, filt, box, reducing_gap)
+    if plan is None:
+        return resize(img, out_h, out_w, filt) if box is None else resize_box(img, out_h, out_w, filt, box)
+    factor, rb, new_box = plan
+    return resize_box(reduce(img, factor, rb), out_h, out_w, filt, new_box)
+
+
+def agent_thumbnail(frame: np.ndarray, max_size: int, box=None) -> np.ndarray:
+    """Geometry half of ``_encode_image_optimized`` (src/agents/vlm_inspector.py:59-69): ``thumbnail((S, S), LANCZOS)``
+    with PIL's default ``reducing_gap=2.0`` (box-reduce pre-pass from 4x downscales on; ``box`` = what a JPEG draft
+    decode hands over); the JPEG round trip is a codec step and is excluded."""
     h, w = frame.shape[:2]
     if max(w, h) <= max_size:
         return frame
     tw, th = thumbnail_size(w, h, max_size)
-    if int(w / tw / 2.0) > 1 or int(h / th / 2.0) > 1:
-        raise NotImplementedError("thumbnail box-reduce pre-pass (>= 4x downscale) is outside the oracle")
-    return resize(frame, th, tw, LANCZOS)
+    return resize_reducing(frame, th, tw, LANCZOS, box)

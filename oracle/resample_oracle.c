@@ -228,3 +228,147 @@ int orc_patchify(const uint8_t* img, int h, int w, const float* lut768, float* o
     (void)gh;
     return 0;
 }
+
+/* =====================================================================================================
+ * Image.thumbnail / Image.resize with reducing_gap (PIL:Image.py:2400-2440, :2831-2915) for frames that are
+ * >= 4x larger than the target: Image.reduce (libImaging/Reduce.c) followed by a resample over a fractional
+ * source box (Resample.c: precompute_coeffs with in0 / in1, ImagingResample's ybox window).
+ * ===================================================================================================== */
+
+/* Resample.c precompute_coeffs with a source box [in0, in1) given as FLOATS (ImagingResample takes float box[4]). */
+int orc_ksize_box(float in0, float in1, int out_size, int filter) {
+    double support; double (*fn)(double);
+    if (orc_filter_support(filter, &support, &fn) || out_size <= 0 || !(in1 > in0)) return -1;
+    double scale = (double)(in1 - in0) / out_size;
+    double filterscale = scale < 1.0 ? 1.0 : scale;
+    return (int)ceil(support * filterscale) * 2 + 1;
+}
+
+int orc_coeffs_box(int in_size, float in0, float in1, int out_size, int filter, int32_t* k, int32_t* bounds) {
+    double support; double (*fn)(double);
+    if (orc_filter_support(filter, &support, &fn) || in_size <= 0 || out_size <= 0 || !(in1 > in0)) return -1;
+    double scale = (double)(in1 - in0) / out_size;
+    double filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    support = support * filterscale;
+    int ksize = (int)ceil(support) * 2 + 1;
+    double* w = (double*)malloc(sizeof(double) * (size_t)ksize);
+    if (!w) return -2;
+    for (int xx = 0; xx < out_size; xx++) {
+        double center = in0 + (xx + 0.5) * scale;
+        double ww = 0.0;
+        double ss = 1.0 / filterscale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        int x;
+        for (x = 0; x < xmax; x++) {
+            double v = fn((x + xmin - center + 0.5) * ss);
+            w[x] = v;
+            ww += v;
+        }
+        for (x = 0; x < xmax; x++) {
+            if (ww != 0.0) w[x] /= ww;
+        }
+        for (; x < ksize; x++) w[x] = 0;
+        for (x = 0; x < ksize; x++) {
+            if (w[x] < 0) k[(size_t)xx * ksize + x] = (int)(-0.5 + w[x] * (1 << PRECISION_BITS));
+            else          k[(size_t)xx * ksize + x] = (int)(0.5 + w[x] * (1 << PRECISION_BITS));
+        }
+        bounds[xx * 2 + 0] = xmin;
+        bounds[xx * 2 + 1] = xmax;
+    }
+    free(w);
+    return ksize;
+}
+
+/* ImagingResample (Resample.c) for a `ch`-channel uint8 HWC image with a float source box (x0, y0, x1, y1):
+ * horizontal pass over the rows the vertical pass will read (ybox_first .. ybox_last), then the vertical pass. */
+int orc_resize_box(const uint8_t* src, int h, int w, int ch, uint8_t* dst, int oh, int ow, int filter, const float* box) {
+    if (h <= 0 || w <= 0 || oh <= 0 || ow <= 0 || ch <= 0 || !box) return -1;
+    const int need_h = ow != w || box[0] != 0.f || box[2] != (float)ow;
+    const int need_v = oh != h || box[1] != 0.f || box[3] != (float)oh;
+    const int ksh = orc_ksize_box(box[0], box[2], ow, filter), ksv = orc_ksize_box(box[1], box[3], oh, filter);
+    if (ksh < 0 || ksv < 0) return -1;
+    int32_t* kh = (int32_t*)malloc(sizeof(int32_t) * (size_t)ow * ksh);
+    int32_t* bh = (int32_t*)malloc(sizeof(int32_t) * (size_t)ow * 2);
+    int32_t* kv = (int32_t*)malloc(sizeof(int32_t) * (size_t)oh * ksv);
+    int32_t* bv = (int32_t*)malloc(sizeof(int32_t) * (size_t)oh * 2);
+    if (!kh || !bh || !kv || !bv) return -2;
+    orc_coeffs_box(w, box[0], box[2], ow, filter, kh, bh);
+    orc_coeffs_box(h, box[1], box[3], oh, filter, kv, bv);
+    const int yfirst = bv[0], ylast = bv[oh * 2 - 2] + bv[oh * 2 - 1];
+    const uint8_t* cur = src;
+    int cur_h = h, cur_w = w, row_off = 0;
+    uint8_t* tmp = NULL;
+    if (need_h) {
+        const int rows = ylast - yfirst;
+        tmp = (uint8_t*)malloc((size_t)rows * ow * ch);
+        if (!tmp) return -2;
+        for (int y = 0; y < rows; y++) {
+            const uint8_t* s = src + (size_t)(y + yfirst) * w * ch;
+            uint8_t* d = tmp + (size_t)y * ow * ch;
+            for (int xx = 0; xx < ow; xx++) {
+                const int xmin = bh[xx * 2], cnt = bh[xx * 2 + 1];
+                const int32_t* kk = kh + (size_t)xx * ksh;
+                for (int c = 0; c < ch; c++) {
+                    uint32_t ss = 1u << (PRECISION_BITS - 1);
+                    for (int x = 0; x < cnt; x++) ss += (uint32_t)((int32_t)s[(size_t)(xmin + x) * ch + c] * kk[x]);
+                    d[(size_t)xx * ch + c] = orc_clip8((int32_t)ss);
+                }
+            }
+        }
+        cur = tmp; cur_h = rows; cur_w = ow; row_off = yfirst;
+    }
+    if (need_v) {
+        for (int yy = 0; yy < oh; yy++) {
+            const int ymin = bv[yy * 2] - row_off, cnt = bv[yy * 2 + 1];
+            const int32_t* kk = kv + (size_t)yy * ksv;
+            uint8_t* d = dst + (size_t)yy * cur_w * ch;
+            for (int i = 0; i < cur_w * ch; i++) {
+                uint32_t ss = 1u << (PRECISION_BITS - 1);
+                for (int y = 0; y < cnt; y++) ss += (uint32_t)((int32_t)cur[(size_t)(ymin + y) * cur_w * ch + i] * kk[y]);
+                d[i] = orc_clip8((int32_t)ss);
+            }
+        }
+    } else {
+        memcpy(dst, cur, (size_t)cur_h * cur_w * ch);
+    }
+    (void)cur_h;
+    free(tmp); free(kh); free(bh); free(kv); free(bv);
+    return 0;
+}
+
+/* Reduce.c division_UINT32: float division, truncated */
+static inline uint32_t orc_division_u32(int divider, int result_bits) {
+    uint32_t max_dividend = (uint32_t)(1 << result_bits) * (uint32_t)divider;
+    float max_int = (1 << 30) * 4.0f;
+    return (uint32_t)(max_int / (float)max_dividend);
+}
+
+/* Image.reduce((fx, fy), box) for a `ch`-channel uint8 HWC image (Reduce.c: ImagingReduce + ImagingReduceCorners):
+ * every output sample is ((sum + n/2) * division_UINT32(n, 8)) >> 24 over the n source pixels of its (possibly
+ * clipped, at the right / bottom edge of the box) fx x fy cell.  dst: dense [ceil(bh/fy)][ceil(bw/fx)][ch]. */
+int orc_reduce(const uint8_t* src, int h, int w, int ch, int fx, int fy, const int* box, uint8_t* dst) {
+    if (h <= 0 || w <= 0 || ch <= 0 || fx < 1 || fy < 1 || !box) return -1;
+    const int x0 = box[0], y0 = box[1], x1 = box[2], y1 = box[3];
+    if (x0 < 0 || y0 < 0 || x1 > w || y1 > h || x1 <= x0 || y1 <= y0) return -1;
+    const int ow = (x1 - x0 + fx - 1) / fx, oh = (y1 - y0 + fy - 1) / fy;
+    for (int oy = 0; oy < oh; oy++) {
+        const int ys = y0 + oy * fy, ye = ys + fy < y1 ? ys + fy : y1;
+        for (int ox = 0; ox < ow; ox++) {
+            const int xs = x0 + ox * fx, xe = xs + fx < x1 ? xs + fx : x1;
+            const int n = (ye - ys) * (xe - xs);
+            const uint32_t mult = orc_division_u32(n, 8), amend = (uint32_t)n / 2;
+            for (int c = 0; c < ch; c++) {
+                uint32_t ss = amend;
+                for (int y = ys; y < ye; y++)
+                    for (int x = xs; x < xe; x++) ss += src[((size_t)y * w + x) * ch + c];
+                dst[((size_t)oy * ow + ox) * ch + c] = (uint8_t)((ss * mult) >> 24);
+            }
+        }
+    }
+    return 0;
+}

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from oracle import qwen2vl as Q
+from vision_inspection_system_b200 import image_utils as IU
 from vision_inspection_system_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -77,3 +78,62 @@ def test_fused_thumbnail_path_and_batches(engine):
         assert np.array_equal(got.cpu().numpy(), Q.resize(a, out_hw[0], out_hw[1], Q.LANCZOS)), out_hw
     same = engine.resize_u8(torch.from_numpy(frames[0]).cuda(), 576, 1024, Q.LANCZOS, fused=False)
     assert engine.last_launches == 2 and torch.equal(same, outs[0])
+
+
+# ---------------------------------------------------------------- thumbnails of very large frames (reduce + boxed resample)
+def test_reduce_against_oracle(engine):
+    rng = np.random.default_rng(51)
+    cases = [((1080, 1920, 3), (2, 2), None), ((333, 517, 3), (3, 2), None), ((100, 502, 4), (5, 7), (3, 1, 499, 97)),
+             ((64, 96, 1), (4, 4), (0, 0, 95, 63)), ((2160, 4096, 3), (2, 2), None), ((50, 50, 3), (1, 6), (10, 0, 50, 50))]
+    for shape, factor, box in cases:
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        got = engine.reduce_u8(torch.from_numpy(a).cuda(), factor, box).cpu().numpy()
+        assert np.array_equal(got, Q.reduce(a, factor, box)), (shape, factor, box)
+
+
+def test_boxed_resize_against_oracle(engine):
+    rng = np.random.default_rng(52)
+    for t in range(12):
+        h, w = (int(v) for v in rng.integers(8, 400, 2))
+        oh, ow = (int(v) for v in rng.integers(1, 200, 2))
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        x0 = float(rng.uniform(0, w - 2)); x1 = float(rng.uniform(x0 + 1, w))
+        y0 = float(rng.uniform(0, h - 2)); y1 = float(rng.uniform(y0 + 1, h))
+        if t % 4 == 0:
+            x0, x1 = 0.0, float(w)
+        filt = (Q.LANCZOS, Q.BICUBIC)[t % 2]
+        got = engine.resize_box_u8(torch.from_numpy(a).cuda(), oh, ow, filt, (x0, y0, x1, y1)).cpu().numpy()
+        assert np.array_equal(got, Q.resize_box(a, oh, ow, filt, (x0, y0, x1, y1))), (h, w, oh, ow, x0, y0, x1, y1)
+
+
+@pytest.mark.parametrize("h,w,limit", [(2160, 4096, 1024), (3000, 5000, 512), (4000, 300, 256), (777, 4001, 500),
+                                       (4000, 6000, 1024)])
+def test_large_frame_thumbnail_equals_pillow(engine, h, w, limit):
+    """From 4x downscales on ``Image.thumbnail`` reduces by an integer factor first: same bytes as Pillow."""
+    from PIL import Image
+    a = synth.noise_frame(h + w, h, w)
+    im = Image.fromarray(a)
+    im.thumbnail((limit, limit), Image.Resampling.LANCZOS)
+    want = np.asarray(im)
+    tw, th = Q.thumbnail_size(w, h, limit)
+    got = engine.resize_reducing_u8(torch.from_numpy(a).cuda(), th, tw, Q.LANCZOS).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(np.asarray(IU.pil_thumbnail(Image.fromarray(a), limit)), want)
+
+
+def test_jpeg_draft_thumbnail_equals_pillow(engine, tmp_path):
+    """An unread JPEG >= 4x larger than the request is decoded by PIL at a DCT-scaled size (draft) and hands a
+    fractional box to the resample: the function form must reproduce ``thumbnail`` on the same file."""
+    from PIL import Image
+    a = synth.pattern_frames(2500, 4100)["lowpass"]
+    path = tmp_path / "big.jpg"
+    Image.fromarray(a).save(path, format="JPEG", quality=90)
+    for limit in (256, 500):
+        ref = Image.open(path)
+        ref.thumbnail((limit, limit), Image.Resampling.LANCZOS)
+        got = IU.pil_thumbnail(Image.open(path), limit)
+        assert got.size == ref.size and np.array_equal(np.asarray(got), np.asarray(ref)), limit
+    # the agents' whole function on that file: same data URI as the plain-PIL restatement
+    from oracle import agents as OA
+    from vision_inspection_system_b200 import agents as A
+    assert A.encode_image_optimized(path, 500, "auditor") == OA.encode_image_optimized(path, 500, "auditor")

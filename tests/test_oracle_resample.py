@@ -87,3 +87,78 @@ def test_against_installed_transformers():
     pv, grid = Q.preprocess(frames)
     assert np.array_equal(grid, want["image_grid_thw"])
     assert np.array_equal(pv, want["pixel_values"])
+
+
+# ---------------------------------------------------------------- thumbnails of very large frames (reduce + boxed resample)
+def test_reduce_matches_pillow():
+    from PIL import Image
+    rng = np.random.default_rng(41)
+    for t in range(40):
+        h, w = (int(v) for v in rng.integers(1, 70, 2))
+        fx, fy = (int(v) for v in rng.integers(1, 8, 2))
+        ch = int(rng.choice([1, 3, 4]))
+        a = rng.integers(0, 256, (h, w, ch), dtype=np.uint8)
+        box = None
+        if t % 2:
+            x0 = int(rng.integers(0, w)); x1 = int(rng.integers(x0 + 1, w + 1))
+            y0 = int(rng.integers(0, h)); y1 = int(rng.integers(y0 + 1, h + 1))
+            box = (x0, y0, x1, y1)
+        im = Image.fromarray(a if ch != 1 else a[:, :, 0], {1: "L", 3: "RGB", 4: "RGBX"}[ch])
+        want = np.asarray(im.reduce((fx, fy), box=box))
+        want = want.reshape(want.shape[0], want.shape[1], -1)
+        assert np.array_equal(Q.reduce(a, (fx, fy), box), want), (h, w, fx, fy, ch, box)
+
+
+def test_boxed_resize_matches_pillow():
+    from PIL import Image
+    rng = np.random.default_rng(42)
+    for t in range(40):
+        h, w = (int(v) for v in rng.integers(4, 120, 2))
+        oh, ow = (int(v) for v in rng.integers(1, 80, 2))
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        x0 = float(rng.uniform(0, w - 2)); x1 = float(rng.uniform(x0 + 1, w))
+        y0 = float(rng.uniform(0, h - 2)); y1 = float(rng.uniform(y0 + 1, h))
+        if t % 3 == 0:
+            x0, y0, x1, y1 = 0, 0, w, h
+        filt = (Q.LANCZOS, Q.BICUBIC)[t % 2]
+        want = np.asarray(Image.fromarray(a).resize((ow, oh), filt, box=(x0, y0, x1, y1), reducing_gap=None))
+        assert np.array_equal(Q.resize_box(a, oh, ow, filt, (x0, y0, x1, y1)), want), (h, w, oh, ow, x0, y0, x1, y1)
+
+
+@pytest.mark.parametrize("h,w,limit", [(2160, 4096, 1024), (3000, 5000, 512), (4000, 300, 256), (1200, 1600, 128),
+                                       (777, 4001, 500), (2304, 2304, 512)])
+def test_thumbnail_with_reduce_prepass_matches_pillow(h, w, limit):
+    """``Image.thumbnail`` from 4x downscales on: reduce by the integer factor, then LANCZOS over a fractional box."""
+    from PIL import Image
+    a = np.random.default_rng(h + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    im = Image.fromarray(a)
+    im.thumbnail((limit, limit), Image.Resampling.LANCZOS)
+    tw, th = Q.thumbnail_size(w, h, limit)
+    assert Q.reducing_plan(w, h, tw, th, Q.LANCZOS) is not None
+    assert np.array_equal(Q.agent_thumbnail(a, limit), np.asarray(im))
+
+
+def test_product_boxed_coefficients_and_plan_match_the_oracle():
+    """vis_build_coeffs_box (product, host) against orc_coeffs_box (oracle); geometry.reducing_plan against the oracle's."""
+    import ctypes as C
+    from oracle import lib as oracle_lib
+    from vision_inspection_system_b200 import geometry as G
+    from vision_inspection_system_b200 import tables as T
+    L = oracle_lib()
+    rng = np.random.default_rng(43)
+    for t in range(60):
+        in_size, out_size = int(rng.integers(2, 3000)), int(rng.integers(1, 900))
+        in0 = float(np.float32(rng.uniform(0, in_size - 1.5)))
+        in1 = float(np.float32(rng.uniform(in0 + 1, in_size)))
+        filt = (Q.LANCZOS, Q.BICUBIC)[t % 2]
+        tab = T.coeff_table_box(in_size, in0, in1, out_size, filt)
+        ks = L.orc_ksize_box(in0, in1, out_size, filt)
+        k = np.zeros((out_size, ks), np.int32)
+        b = np.zeros((out_size, 2), np.int32)
+        assert L.orc_coeffs_box(in_size, in0, in1, out_size, filt, k.ctypes.data_as(C.POINTER(C.c_int32)),
+                                b.ctypes.data_as(C.POINTER(C.c_int32))) == ks
+        assert tab.ksize == ks and np.array_equal(tab.k, k) and np.array_equal(tab.bounds, b), (in_size, in0, in1, out_size)
+    for w, h, limit in [(4096, 2160, 1024), (5000, 3000, 512), (300, 9000, 256), (9001, 777, 500), (3840, 2160, 1024)]:
+        tw, th = G.thumbnail_size(w, h, limit)
+        assert G.reducing_plan(w, h, tw, th, Q.LANCZOS) == Q.reducing_plan(w, h, tw, th, Q.LANCZOS)
+    assert G.reducing_plan(3840, 2160, 1024, 576, Q.LANCZOS) is None

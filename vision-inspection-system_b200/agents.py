@@ -59,11 +59,7 @@ def encode_image_optimized(image_path: Path, max_size: int | None = None, role: 
     img = Image.open(image_path)
     original_size = img.size
     if max(img.size) > max_size:
-        tw, th = G.thumbnail_size(img.size[0], img.size[1], max_size)
-        if G.thumbnail_needs_reduce(img.size[0], img.size[1], tw, th):
-            raise NotImplementedError("thumbnail box-reduce / JPEG draft pre-pass (>= 4x downscale) is not implemented")
-        if (tw, th) != img.size:
-            img = IU._resample_pil(img, (tw, th), Image.Resampling.LANCZOS)
+        img = IU.pil_thumbnail(img, max_size)
         logger.debug("Resized image from %s to %s", original_size, img.size)
     if img.mode in _RGB_MODES[role]:
         img = img.convert("RGB")

@@ -96,6 +96,46 @@ k_normalize_patchify(const uint8_t* __restrict__ src, int64_t src_pitch, int gw,
     *reinterpret_cast<float4*>(out + (size_t)(row0 + r) * VIS_ROW_FLOATS + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+
+// Image.reduce((fx, fy), box) — libImaging/Reduce.c.  One thread per output pixel (all channels): fy rows of fx * CH
+// contiguous bytes; a warp covers 32 * fx * CH contiguous bytes of every source row it touches, so the source is read
+// once with full sectors.  The four cell kinds (interior, clipped at the right edge, at the bottom edge, at both) have
+// their own sample count n, multiplier M(n) and rounding term n / 2, computed on the host exactly as Reduce.c does
+// (float division, truncated).
+struct ReduceParams {
+    int x0, y0, x1, y1, fx, fy, ow, oh;
+    unsigned mult[4], amend[4];           // index = (clipped column) | (clipped row) << 1
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+k_reduce(const uint8_t* __restrict__ src, int64_t src_pitch, uint8_t* __restrict__ dst, int64_t dst_pitch,
+         const ReduceParams p) {
+    const int ox = blockIdx.x * 64 + (threadIdx.x & 63), oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (ox >= p.ow || oy >= p.oh) return;
+    const int xs = p.x0 + ox * p.fx, xe = min(xs + p.fx, p.x1);
+    const int ys = p.y0 + oy * p.fy, ye = min(ys + p.fy, p.y1);
+    const int kind = (xe - xs < p.fx ? 1 : 0) | (ye - ys < p.fy ? 2 : 0);
+    unsigned ss[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) ss[c] = p.amend[kind];
+    for (int y = ys; y < ye; ++y) {
+        const uint8_t* row = src + (int64_t)y * src_pitch + (int64_t)xs * CH;
+        for (int i = 0; i < (xe - xs) * CH; i += CH)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) ss[c] += __ldg(row + i + c);
+    }
+    uint8_t* d = dst + (int64_t)oy * dst_pitch + (int64_t)ox * CH;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) d[c] = (uint8_t)((ss[c] * p.mult[kind]) >> 24);
+}
+
+inline unsigned reduce_multiplier(int n) {        // Reduce.c division_UINT32(n, 8)
+    const uint32_t max_dividend = (uint32_t)(1 << 8) * (uint32_t)n;
+    const float max_int = (1 << 30) * 4.0f;
+    return (unsigned)(max_int / (float)max_dividend);
+}
+
 }  // namespace
 
 extern "C" {
@@ -142,6 +182,35 @@ int vis_resample_v_u8(const uint8_t* src, int64_t src_pitch, int in_h, int row_b
         k_resample_v<1><<<grid, block, 0, st>>>(src, src_pitch, row_bytes, dst, dst_pitch, out_h, k, bounds, ksize);
     }
     return vis::check_launch("vis_resample_v_u8");
+}
+
+int vis_reduce_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int channels, int fx, int fy,
+                  int x0, int y0, int x1, int y1, uint8_t* dst, int64_t dst_pitch, void* stream) {
+    if (!src || !dst || h <= 0 || w <= 0 || channels < 1 || channels > 4 || fx < 1 || fy < 1 || x0 < 0 || y0 < 0 ||
+        x1 > w || y1 > h || x1 <= x0 || y1 <= y0 || src_pitch < (int64_t)w * channels || (int64_t)fx * fy > (1 << 16)) {
+        vis::set_error("vis_reduce_u8: bad arguments (%dx%d, factor %dx%d, box %d,%d,%d,%d)", w, h, fx, fy, x0, y0, x1, y1);
+        return VIS_E_INVALID;
+    }
+    ReduceParams p;
+    p.x0 = x0; p.y0 = y0; p.x1 = x1; p.y1 = y1; p.fx = fx; p.fy = fy;
+    p.ow = (x1 - x0 + fx - 1) / fx;
+    p.oh = (y1 - y0 + fy - 1) / fy;
+    if (dst_pitch < (int64_t)p.ow * channels) {
+        vis::set_error("vis_reduce_u8: destination pitch %lld < %d", (long long)dst_pitch, p.ow * channels);
+        return VIS_E_INVALID;
+    }
+    const int rx = (x1 - x0) % fx ? (x1 - x0) % fx : fx, ry = (y1 - y0) % fy ? (y1 - y0) % fy : fy;
+    const int n[4] = {fx * fy, rx * fy, fx * ry, rx * ry};
+    for (int i = 0; i < 4; ++i) { p.mult[i] = reduce_multiplier(n[i]); p.amend[i] = (unsigned)n[i] / 2; }
+    const dim3 grid((p.ow + 63) / 64, (p.oh + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (channels) {
+        case 1: k_reduce<1><<<grid, 256, 0, st>>>(src, src_pitch, dst, dst_pitch, p); break;
+        case 2: k_reduce<2><<<grid, 256, 0, st>>>(src, src_pitch, dst, dst_pitch, p); break;
+        case 3: k_reduce<3><<<grid, 256, 0, st>>>(src, src_pitch, dst, dst_pitch, p); break;
+        default: k_reduce<4><<<grid, 256, 0, st>>>(src, src_pitch, dst, dst_pitch, p); break;
+    }
+    return vis::check_launch("vis_reduce_u8");
 }
 
 int vis_normalize_patchify(const uint8_t* src, int64_t src_pitch, int h, int w,

@@ -63,10 +63,10 @@ struct Window {
     double scale, filterscale, support;
     int ksize;
 };
-static Window window_for(int in_size, int out_size, const FilterDef& f) {
+static Window window_for(float in0, float in1, int out_size, const FilterDef& f) {
     Window w;
-    // Pillow keeps the source box as float and divides in double
-    w.scale = (double)((float)in_size - (float)0) / out_size;
+    // Pillow keeps the source box as float (ImagingResample's float box[4]) and divides in double
+    w.scale = (double)(in1 - in0) / out_size;
     w.filterscale = w.scale < 1.0 ? 1.0 : w.scale;
     w.support = f.support * w.filterscale;
     w.ksize = (int)std::ceil(w.support) * 2 + 1;
@@ -89,21 +89,41 @@ int vis_coeff_ksize(int in_size, int out_size, int filter) {
         set_error("vis_coeff_ksize: bad arguments (in=%d out=%d filter=%d)", in_size, out_size, filter);
         return VIS_E_INVALID;
     }
-    return window_for(in_size, out_size, f).ksize;
+    return window_for(0.f, (float)in_size, out_size, f).ksize;
+}
+
+int vis_coeff_ksize_box(float in0, float in1, int out_size, int filter) {
+    FilterDef f;
+    if (out_size <= 0 || !(in1 > in0) || !filter_def(filter, &f)) {
+        set_error("vis_coeff_ksize_box: bad arguments (box=[%g,%g) out=%d filter=%d)", (double)in0, (double)in1, out_size, filter);
+        return VIS_E_INVALID;
+    }
+    return window_for(in0, in1, out_size, f).ksize;
 }
 
 int vis_build_coeffs(int in_size, int out_size, int filter, int32_t* k, int32_t* bounds, int* ksize_out) {
-    FilterDef f;
-    if (in_size <= 0 || out_size <= 0 || !k || !bounds || !filter_def(filter, &f)) {
+    if (in_size <= 0) {
         set_error("vis_build_coeffs: bad arguments (in=%d out=%d filter=%d)", in_size, out_size, filter);
         return VIS_E_INVALID;
     }
-    const Window win = window_for(in_size, out_size, f);
+    return vis_build_coeffs_box(in_size, 0.f, (float)in_size, out_size, filter, k, bounds, ksize_out);
+}
+
+int vis_build_coeffs_box(int in_size, float in0, float in1, int out_size, int filter, int32_t* k, int32_t* bounds,
+                         int* ksize_out) {
+    FilterDef f;
+    if (in_size <= 0 || out_size <= 0 || !k || !bounds || !(in1 > in0) || in0 < 0.f || in1 > (float)in_size ||
+        !filter_def(filter, &f)) {
+        set_error("vis_build_coeffs: bad arguments (in=%d box=[%g,%g) out=%d filter=%d)", in_size, (double)in0,
+                  (double)in1, out_size, filter);
+        return VIS_E_INVALID;
+    }
+    const Window win = window_for(in0, in1, out_size, f);
     const double inv_fs = 1.0 / win.filterscale;
     const double fixed_one = (double)(1 << VIS_PRECISION_BITS);
     std::vector<double> w((size_t)win.ksize);
     for (int o = 0; o < out_size; ++o) {
-        const double center = (o + 0.5) * win.scale;
+        const double center = in0 + (o + 0.5) * win.scale;
         int first = (int)(center - win.support + 0.5);      // C truncation, as Pillow
         if (first < 0) first = 0;
         int last = (int)(center + win.support + 0.5);

@@ -267,6 +267,78 @@ class Engine:
             self.last_launches += 1
         return cur.squeeze(-1) if squeeze else cur
 
+    def reduce_u8(self, img: torch.Tensor, factor, box=None) -> torch.Tensor:
+        """``PIL.Image.reduce(factor, box)`` for a CUDA uint8 HWC tensor: integer box average (libImaging/Reduce.c)."""
+        self._check_u8(img)
+        if img.dim() != 3 or img.stride(2) != 1 or img.stride(1) != img.shape[2]:
+            raise ValueError("expected a [H, W, C] uint8 tensor with contiguous pixels")
+        h, w, ch = (int(v) for v in img.shape)
+        fx, fy = (int(v) for v in (factor if isinstance(factor, (tuple, list)) else (factor, factor)))
+        x0, y0, x1, y1 = (0, 0, w, h) if box is None else (int(v) for v in box)
+        out = torch.empty((-(-(y1 - y0) // fy), -(-(x1 - x0) // fx), ch), dtype=torch.uint8, device=self.device)
+        N.check(self.L.vis_reduce_u8(img.data_ptr(), img.stride(0), h, w, ch, fx, fy, x0, y0, x1, y1,
+                                     out.data_ptr(), out.stride(0), _stream_ptr()), "vis_reduce_u8")
+        self.last_launches = 1
+        return out
+
+    def resize_box_u8(self, img: torch.Tensor, out_h: int, out_w: int, filt: int, box) -> torch.Tensor:
+        """``Image.resize((out_w, out_h), filt, box=box, reducing_gap=None)`` for a CUDA uint8 HWC tensor: the core
+        ImagingResample with a fractional source box — horizontal pass over the rows the vertical pass reads, then
+        the vertical pass (generic kernels, boxed coefficient tables)."""
+        self._check_u8(img)
+        if img.dim() != 3 or img.stride(2) != 1 or img.stride(1) != img.shape[2]:
+            raise ValueError("expected a [H, W, C] uint8 tensor with contiguous pixels")
+        h, w, ch = (int(v) for v in img.shape)
+        box = tuple(float(np.float32(v)) for v in box)                  # ImagingResample takes float box[4]
+        if h > w * 100 and out_h < h:                                   # tall image: vertical pass first (PIL:Image.py:2431-2435)
+            tmp = self.resize_box_u8(img, out_h, w, filt, (0.0, box[1], float(w), box[3]))
+            return self.resize_box_u8(tmp, out_h, out_w, filt, (box[0], 0.0, box[2], float(out_h)))
+        need_h = out_w != w or box[0] != 0.0 or box[2] != float(out_w)
+        need_v = out_h != h or box[1] != 0.0 or box[3] != float(out_h)
+        sp = _stream_ptr()
+        self.last_launches = 0
+        vt = T.coeff_table_box(h, box[1], box[3], out_h, filt)
+        y_first = int(vt.bounds[0, 0])
+        y_last = int(vt.bounds[-1, 0] + vt.bounds[-1, 1])
+        cur, row_off = img, 0
+        if need_h:
+            ht = T.coeff_table_box(w, box[0], box[2], out_w, filt)
+            k, b = torch.from_numpy(ht.k).to(self.device), torch.from_numpy(ht.bounds).to(self.device)
+            rows = y_last - y_first
+            dst = torch.empty((rows, out_w, ch), dtype=torch.uint8, device=self.device)
+            N.check(self.L.vis_resample_h_u8(img.data_ptr() + y_first * img.stride(0), img.stride(0), rows, w, ch,
+                                             dst.data_ptr(), dst.stride(0), out_w, k.data_ptr(), b.data_ptr(), ht.ksize, sp),
+                    "vis_resample_h_u8")
+            cur, row_off = dst, y_first
+            self.last_launches += 1
+        if not need_v:
+            return cur.clone() if cur is img else cur
+        bounds = vt.bounds.copy()
+        bounds[:, 0] -= row_off
+        k, b = torch.from_numpy(vt.k).to(self.device), torch.from_numpy(bounds).to(self.device)
+        cur_h, cur_w = int(cur.shape[0]), int(cur.shape[1])
+        dst = torch.empty((out_h, cur_w, ch), dtype=torch.uint8, device=self.device)
+        N.check(self.L.vis_resample_v_u8(cur.data_ptr(), cur.stride(0), cur_h, cur_w * ch, dst.data_ptr(), dst.stride(0),
+                                         out_h, k.data_ptr(), b.data_ptr(), vt.ksize, sp), "vis_resample_v_u8")
+        self.last_launches += 1
+        self._keepalive_b = (k, b)
+        return dst
+
+    def resize_reducing_u8(self, img: torch.Tensor, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS, box=None,
+                           reducing_gap: float = 2.0) -> torch.Tensor:
+        """``Image.resize((out_w, out_h), filt, box, reducing_gap)`` — what ``Image.thumbnail`` calls: an integer
+        ``reduce`` pre-pass when the frame is >= 2 * reducing_gap times larger than the target, then the resample over
+        the (fractional) box of the reduced frame.  Frames below that ratio take the fused kernels unchanged."""
+        h, w = int(img.shape[0]), int(img.shape[1])
+        plan = G.reducing_plan(w, h, out_w, out_h, filt, box, reducing_gap)
+        if plan is None:
+            return self.resize_u8(img, out_h, out_w, filt) if box is None else self.resize_box_u8(img, out_h, out_w, filt, box)
+        factor, reduce_box, new_box = plan
+        reduced = self.reduce_u8(img if img.stride(1) == img.shape[2] else img.contiguous(), factor, reduce_box)
+        out = self.resize_box_u8(reduced, out_h, out_w, filt, new_box)
+        self.last_launches += 1
+        return out
+
     # ------------------------------------------------------------------ frames -> pixel_values
     def plan_batch(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
                    force_generic: bool = False, vsplit: int | None = None, path: str = "auto") -> "BatchPlan":

@@ -77,6 +77,27 @@ def thumbnail_needs_reduce(width: int, height: int, tw: int, th: int, reducing_g
     return (int(width / tw / reducing_gap) or 1) > 1 or (int(height / th / reducing_gap) or 1) > 1
 
 
+_FILTER_SUPPORT = {1: 3.0, 3: 2.0}                 # LANCZOS, BICUBIC (PIL:Image.py _filters_support)
+
+
+def reducing_plan(width: int, height: int, out_w: int, out_h: int, filt: int, box=None, reducing_gap: float = 2.0):
+    """The pre-pass ``Image.resize(..., reducing_gap)`` inserts (PIL:Image.py:2407-2424; ``Image.thumbnail`` passes
+    2.0): None when no reduction applies, else ((factor_x, factor_y), reduce_box of ints — ``Image._get_safe_box`` —,
+    the source box as floats relative to the reduced image)."""
+    box = (0, 0, width, height) if box is None else box
+    factor_x = int((box[2] - box[0]) / out_w / reducing_gap) or 1
+    factor_y = int((box[3] - box[1]) / out_h / reducing_gap) or 1
+    if factor_x <= 1 and factor_y <= 1:
+        return None
+    support = _FILTER_SUPPORT[int(filt)] - 0.5
+    sx, sy = support * (box[2] - box[0]) / out_w, support * (box[3] - box[1]) / out_h
+    rb = (max(0, int(box[0] - sx)), max(0, int(box[1] - sy)),
+          min(width, math.ceil(box[2] + sx)), min(height, math.ceil(box[3] + sy)))
+    new_box = ((box[0] - rb[0]) / factor_x, (box[1] - rb[1]) / factor_y,
+               (box[2] - rb[0]) / factor_x, (box[3] - rb[1]) / factor_y)
+    return (factor_x, factor_y), rb, new_box
+
+
 def resize_image_size(width: int, height: int, max_dimension: int) -> tuple[int, int] | None:
     """Target (w, h) of the reference ``resize_image``; None when it returns the input unchanged."""
     if width <= max_dimension and height <= max_dimension:

@@ -155,14 +155,18 @@ def decode_image(image_path: Path, bgr: bool = False, codec: str = "nvjpeg"):
     return t
 
 
-def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int) -> Image.Image:
-    """``img.resize(size, filt)`` (reducing_gap=None) with the resampling done on the GPU."""
+def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int, box=None, reducing_gap=None) -> Image.Image:
+    """``img.resize(size, filt, box, reducing_gap)`` with the resampling (and the ``reduce`` pre-pass a
+    ``reducing_gap`` asks for) done on the GPU.  As in Pillow, alpha modes are resampled premultiplied and WITHOUT the
+    pre-pass (``Image.resize`` drops ``reducing_gap`` on that branch, PIL:Image.py:2399-2402)."""
     import torch
-    if img.size == tuple(size):
+    full = (0, 0) + img.size
+    box = full if box is None else tuple(box)
+    if img.size == tuple(size) and box == full:
         return img.copy()
     mode = img.mode
     if mode in ("LA", "RGBA"):                       # Pillow resamples these in premultiplied form
-        work = img.convert({"LA": "La", "RGBA": "RGBa"}[mode])
+        work, reducing_gap = img.convert({"LA": "La", "RGBA": "RGBa"}[mode]), None
     elif mode in ("L", "RGB", "RGBX", "CMYK", "YCbCr", "HSV", "LAB", "La", "RGBa"):
         work = img
     else:
@@ -171,9 +175,32 @@ def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int) -> Image.I
     bands = len(work.getbands())
     arr = np.frombuffer(work.tobytes(), np.uint8).reshape(work.size[1], work.size[0], bands)
     dev = torch.from_numpy(arr.copy()).cuda()
-    out = _engine().resize_u8(dev, size[1], size[0], int(filt)).cpu().numpy()
-    res = Image.frombytes(work.mode, tuple(size), out.tobytes())
+    eng = _engine()
+    if reducing_gap is not None:
+        out = eng.resize_reducing_u8(dev, size[1], size[0], int(filt), None if box == full else box, reducing_gap)
+    elif box != full:
+        out = eng.resize_box_u8(dev, size[1], size[0], int(filt), box)
+    else:
+        out = eng.resize_u8(dev, size[1], size[0], int(filt))
+    res = Image.frombytes(work.mode, tuple(size), out.cpu().numpy().tobytes())
     return res.convert(mode) if work.mode != mode else res
+
+
+def pil_thumbnail(img: Image.Image, max_size: int) -> Image.Image:
+    """``img.thumbnail((max_size, max_size), LANCZOS)`` (PIL:Image.py:2831-2915) as a function: the JPEG draft request
+    (a decoder-side 1/2, 1/4, 1/8 scale for streams that are still unread and >= 4x larger than the request — host
+    codec work, done by PIL itself), the integer ``reduce`` pre-pass from 4x downscales on, and the LANCZOS resample over
+    the resulting (possibly fractional) box — the last two on the GPU.  Returns ``img`` itself when it already fits."""
+    size = G.thumbnail_size(img.size[0], img.size[1], max_size)
+    if size is None:
+        return img
+    box = None
+    res = img.draft(None, (int(max_size * 2.0), int(max_size * 2.0)))      # reducing_gap = 2.0, as thumbnail()
+    if res is not None:
+        box = res[1]
+    if img.size == tuple(size):
+        return img
+    return _resample_pil(img, size, Image.Resampling.LANCZOS, box, 2.0)
 
 
 def resize_image(img: Image.Image, max_dimension: int = None) -> Image.Image:
@@ -194,11 +221,7 @@ def agent_thumbnail(img: Image.Image, role: str = "inspector", max_size: int | N
     not part of this path."""
     max_size = max_size or _ROLE_MAX_SIZE[role]
     if max(img.size) > max_size:
-        tw, th = G.thumbnail_size(img.size[0], img.size[1], max_size)
-        if G.thumbnail_needs_reduce(img.size[0], img.size[1], tw, th):
-            raise NotImplementedError("thumbnail box-reduce pre-pass (>= 4x downscale) is not implemented")
-        if (tw, th) != img.size:
-            img = _resample_pil(img, (tw, th), Image.Resampling.LANCZOS)
+        img = pil_thumbnail(img, max_size)
     if img.mode in ("RGBA", "P", "LA"):
         img = img.convert("RGB")
     return img
@@ -255,15 +278,13 @@ def preprocess_for_vlm(images, *, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pi
         if isinstance(im, torch.Tensor):
             t = im if im.is_cuda else im.cuda()
         else:
-            t = torch.from_numpy(np.ascontiguousarray(_to_rgb_array(im))).cuda()
+            t = torch.from_numpy(np.array(_to_rgb_array(im), dtype=np.uint8, order="C")).cuda()       # copy: PIL arrays are read-only
         if role is not None:
             h, w = int(t.shape[0]), int(t.shape[1])
             limit = _ROLE_MAX_SIZE[role]
             if max(h, w) > limit:
                 tw, th = G.thumbnail_size(w, h, limit)
-                if G.thumbnail_needs_reduce(w, h, tw, th):
-                    raise NotImplementedError("thumbnail box-reduce pre-pass (>= 4x downscale) is not implemented")
-                t = eng.resize_u8(t, th, tw, int(Image.Resampling.LANCZOS))
+                t = eng.resize_reducing_u8(t, th, tw, int(Image.Resampling.LANCZOS))
         frames.append(t)
     return eng.preprocess(frames, min_pixels=min_pixels, max_pixels=max_pixels)
 

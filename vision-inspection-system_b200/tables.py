@@ -40,6 +40,20 @@ def coeff_table(in_size: int, out_size: int, filt: int) -> CoeffTable:
     return CoeffTable(in_size, out_size, filt, ksize, k, b, taps)
 
 
+@lru_cache(maxsize=64)
+def coeff_table_box(in_size: int, in0: float, in1: float, out_size: int, filt: int) -> CoeffTable:
+    """Same table for the fractional source box [in0, in1) of the axis (floats, as ImagingResample's box)."""
+    L = N.lib()
+    ksize = N.check(L.vis_coeff_ksize_box(in0, in1, out_size, filt), "vis_coeff_ksize_box")
+    k = np.zeros((out_size, ksize), np.int32)
+    b = np.zeros((out_size, 2), np.int32)
+    ks = C.c_int(0)
+    N.check(L.vis_build_coeffs_box(in_size, in0, in1, out_size, filt, N.i32ptr(k), N.i32ptr(b), C.byref(ks)),
+            "vis_build_coeffs_box")
+    taps = N.check(L.vis_max_taps(N.i32ptr(b), out_size), "vis_max_taps")
+    return CoeffTable(in_size, out_size, filt, ksize, k, b, taps)
+
+
 def normalize_lut(mean=IMAGE_MEAN, std=IMAGE_STD, rescale: float = RESCALE_FACTOR) -> np.ndarray:
     m = np.asarray(mean, np.float32)
     s = np.asarray(std, np.float32)
