@@ -83,6 +83,15 @@ int vis_resample_v_u8(const uint8_t* src, int64_t src_pitch, int in_h, int row_b
 int vis_reduce_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int channels, int fx, int fy,
                   int x0, int y0, int x1, int y1, uint8_t* dst, int64_t dst_pitch, void* stream);
 
+/* Image.resize(size, NEAREST, box): what Pillow runs for palette ("P") and bilevel ("1") frames whatever filter the
+ * caller names (PIL:Image.py:2396-2397; _imaging.c _resize + Geometry.c ImagingScaleAffine) — e.g. a palette PNG
+ * going through the agents' thumbnail (src/agents/vlm_inspector.py:64) before its RGB conversion (:68).
+ * vis_nearest_table [host]: tab[d] = source index of output sample d or -1 (outside: written as 0), walked with the
+ * accumulated double of ImagingScaleAffine.  vis_gather_u8 [device]: dst[y][x] = src[ytab[y]][xtab[x]].            */
+int vis_nearest_table(int in_size, float in0, float in1, int out_size, int32_t* tab);
+int vis_gather_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int channels, uint8_t* dst, int64_t dst_pitch,
+                  int out_h, int out_w, const int32_t* xtab, const int32_t* ytab, void* stream);
+
 /* resized RGB uint8 HWC [h,w,3] (h,w multiples of 28) -> rows [row0, row0 + (h/14)*(w/14)) of
  * pixel_values [*,1176] f32 in Qwen2-VL patch order (tf:models/qwen2_vl/image_processing_pil_qwen2_vl.py:182-214):
  * rescale+normalize through lut768, temporal duplicate (T=2), 14x14 patches, 2x2 merge order.  [device] */

@@ -69,6 +69,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.orc_resize_box.restype = c.c_int
     L.orc_reduce.argtypes = [u8p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, i32p, u8p]
     L.orc_reduce.restype = c.c_int
+    L.orc_nearest_table.argtypes = [c.c_int, c.c_float, c.c_float, c.c_int, i32p]
+    L.orc_nearest_table.restype = c.c_int
     L.orc_lut.argtypes = [f32p, f32p, c.c_double, f32p]
     L.orc_lut.restype = None
     L.orc_patchify.argtypes = [u8p, c.c_int, c.c_int, f32p, f32p]

@@ -181,6 +181,20 @@ def resize_box(img: np.ndarray, out_h: int, out_w: int, filt: int, box) -> np.nd
     return out
 
 
+def resize_nearest(img: np.ndarray, out_h: int, out_w: int, box=None) -> np.ndarray:
+    """``Image.resize((out_w, out_h), NEAREST, box)`` — the path Pillow takes for "P" and "1" images (uint8 HW or HWC)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[:2]
+    box = np.asarray((0, 0, w, h) if box is None else box, np.float32)
+    xt, yt = np.empty(out_w, np.int32), np.empty(out_h, np.int32)
+    lib().orc_nearest_table(w, float(box[0]), float(box[2]), out_w, _i32p(xt))
+    lib().orc_nearest_table(h, float(box[1]), float(box[3]), out_h, _i32p(yt))
+    out = img[np.clip(yt, 0, h - 1)][:, np.clip(xt, 0, w - 1)].copy()
+    out[yt < 0] = 0
+    out[:, xt < 0] = 0
+    return out
+
+
 _FILTER_SUPPORT = {BICUBIC: 2.0, LANCZOS: 3.0}
 
 

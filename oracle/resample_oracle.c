@@ -372,3 +372,19 @@ int orc_reduce(const uint8_t* src, int h, int w, int ch, int fx, int fy, const i
     }
     return 0;
 }
+
+/* Image.resize(size, NEAREST, box) — what Pillow runs for palette ("P") and bilevel ("1") images whatever filter the
+ * caller names (PIL:Image.py:2396-2397): _imaging.c _resize builds the affine a = {(x1-x0)/out, 0, x0, 0, (y1-y0)/out, y0}
+ * and Geometry.c ImagingScaleAffine walks it with an ACCUMULATED double (xo = a[2] + a[0]*0.5; xo += a[0]),
+ * COORD(v) = v < 0 ? -1 : (int)v; samples outside the image are 0.  tab[d] = source index or -1. */
+int orc_nearest_table(int in_size, float in0, float in1, int out_size, int32_t* tab) {
+    if (in_size <= 0 || out_size <= 0 || !tab) return -1;
+    const double a = (double)(in1 - in0) / out_size;
+    double xo = (double)in0 + a * 0.5;
+    for (int x = 0; x < out_size; x++) {
+        const int xin = xo < 0.0 ? -1 : (int)xo;
+        tab[x] = (xin >= 0 && xin < in_size) ? xin : -1;
+        xo += a;
+    }
+    return 0;
+}

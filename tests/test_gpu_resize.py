@@ -137,3 +137,36 @@ def test_jpeg_draft_thumbnail_equals_pillow(engine, tmp_path):
     from oracle import agents as OA
     from vision_inspection_system_b200 import agents as A
     assert A.encode_image_optimized(path, 500, "auditor") == OA.encode_image_optimized(path, 500, "auditor")
+
+
+def test_palette_and_bilevel_frames_take_nearest_like_pillow(engine, tmp_path):
+    """Pillow resamples "P" and "1" images with NEAREST whatever filter is named; a palette PNG larger than the agents'
+    limit is thumbnailed that way BEFORE its RGB conversion (src/agents/vlm_inspector.py:64, :68)."""
+    from PIL import Image
+    rng = np.random.default_rng(61)
+    idx = rng.integers(0, 256, (1500, 2600), dtype=np.uint8)
+    pal = rng.integers(0, 256, 768, dtype=np.uint8).tolist()
+    p_img = Image.fromarray(idx, "P")
+    p_img.putpalette(pal)
+    ref = p_img.copy()
+    ref.thumbnail((1024, 1024), Image.Resampling.LANCZOS)
+    got = IU.pil_thumbnail(p_img, 1024)
+    assert got.mode == "P" and got.size == ref.size
+    assert np.array_equal(np.asarray(got), np.asarray(ref))
+    assert np.array_equal(np.asarray(got.convert("RGB")), np.asarray(ref.convert("RGB")))
+    b_img = Image.fromarray((idx > 127).astype(np.uint8) * 255).convert("1", dither=Image.Dither.NONE)
+    ref = b_img.copy()
+    ref.thumbnail((500, 500), Image.Resampling.LANCZOS)
+    got = IU.pil_thumbnail(b_img, 500)
+    assert got.mode == "1" and np.array_equal(np.asarray(got), np.asarray(ref))
+    # engine level, with a box, against the oracle
+    for box in (None, (3.25, 7.5, 2000.75, 1400.0)):
+        want = Q.resize_nearest(idx, 333, 517, box)
+        assert np.array_equal(engine.resize_nearest_u8(torch.from_numpy(idx).cuda(), 333, 517, box).cpu().numpy(), want)
+    # the agents' whole function on a palette PNG: same data URI as the plain-PIL restatement
+    from oracle import agents as OA
+    from vision_inspection_system_b200 import agents as A
+    path = tmp_path / "palette.png"
+    p_img.save(path)
+    for role in ("inspector", "auditor"):
+        assert A.encode_image_optimized(path, 1024, role) == OA.encode_image_optimized(path, 1024, role), role

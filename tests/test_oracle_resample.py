@@ -162,3 +162,28 @@ def test_product_boxed_coefficients_and_plan_match_the_oracle():
         tw, th = G.thumbnail_size(w, h, limit)
         assert G.reducing_plan(w, h, tw, th, Q.LANCZOS) == Q.reducing_plan(w, h, tw, th, Q.LANCZOS)
     assert G.reducing_plan(3840, 2160, 1024, 576, Q.LANCZOS) is None
+
+
+def test_nearest_resize_matches_pillow_for_palette_images():
+    from PIL import Image
+    rng = np.random.default_rng(44)
+    for t in range(40):
+        h, w = (int(v) for v in rng.integers(1, 300, 2))
+        oh, ow = (int(v) for v in rng.integers(1, 300, 2))
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        box = None
+        if t % 3 == 0:
+            x0 = float(rng.uniform(0, w - 1)); x1 = float(rng.uniform(x0 + 0.5, w))
+            y0 = float(rng.uniform(0, h - 1)); y1 = float(rng.uniform(y0 + 0.5, h))
+            box = (x0, y0, x1, y1)
+        want = np.asarray(Image.fromarray(a, "P").resize((ow, oh), Image.Resampling.LANCZOS, box=box))
+        assert np.array_equal(Q.resize_nearest(a, oh, ow, box), want), (h, w, oh, ow, box)
+    # product host table against the oracle's
+    import ctypes as C
+    from oracle import lib as oracle_lib
+    from vision_inspection_system_b200 import _native as N
+    for in_size, in0, in1, out in [(5000, 0.0, 5000.0, 1024), (300, 3.25, 250.5, 517), (7, 0.0, 7.0, 100), (100, 50.0, 100.0, 3)]:
+        a, b = np.empty(out, np.int32), np.empty(out, np.int32)
+        assert N.lib().vis_nearest_table(in_size, in0, in1, out, N.i32ptr(a)) == 0
+        assert oracle_lib().orc_nearest_table(in_size, in0, in1, out, b.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+        assert np.array_equal(a, b)

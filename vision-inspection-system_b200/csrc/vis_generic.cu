@@ -136,6 +136,20 @@ inline unsigned reduce_multiplier(int n) {        // Reduce.c division_UINT32(n,
     return (unsigned)(max_int / (float)max_dividend);
 }
 
+
+// Image.resize(NEAREST): a gather through host-built index tables (-1 = outside the image: 0)
+__global__ void __launch_bounds__(256)
+k_gather(const uint8_t* __restrict__ src, int64_t src_pitch, int ch, uint8_t* __restrict__ dst, int64_t dst_pitch,
+         int out_h, int out_w, const int32_t* __restrict__ xtab, const int32_t* __restrict__ ytab) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= out_w || y >= out_h) return;
+    const int sx = __ldg(xtab + x), sy = __ldg(ytab + y);
+    uint8_t* d = dst + (int64_t)y * dst_pitch + (int64_t)x * ch;
+    const uint8_t* s = src + (int64_t)max(sy, 0) * src_pitch + (int64_t)max(sx, 0) * ch;
+    const bool inside = sx >= 0 && sy >= 0;
+    for (int c = 0; c < ch; ++c) d[c] = inside ? __ldg(s + c) : (uint8_t)0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -211,6 +225,33 @@ int vis_reduce_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int chann
         default: k_reduce<4><<<grid, 256, 0, st>>>(src, src_pitch, dst, dst_pitch, p); break;
     }
     return vis::check_launch("vis_reduce_u8");
+}
+
+int vis_nearest_table(int in_size, float in0, float in1, int out_size, int32_t* tab) {
+    if (in_size <= 0 || out_size <= 0 || !tab) {
+        vis::set_error("vis_nearest_table: bad arguments (in=%d out=%d)", in_size, out_size);
+        return VIS_E_INVALID;
+    }
+    const double a = (double)(in1 - in0) / out_size;       // float subtraction, as _imaging.c _resize
+    double xo = (double)in0 + a * 0.5;
+    for (int x = 0; x < out_size; ++x) {
+        const int xin = xo < 0.0 ? -1 : (int)xo;
+        tab[x] = (xin >= 0 && xin < in_size) ? xin : -1;
+        xo += a;                                            // accumulated, as ImagingScaleAffine
+    }
+    return VIS_OK;
+}
+
+int vis_gather_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int channels, uint8_t* dst, int64_t dst_pitch,
+                  int out_h, int out_w, const int32_t* xtab, const int32_t* ytab, void* stream) {
+    if (!src || !dst || !xtab || !ytab || h <= 0 || w <= 0 || out_h <= 0 || out_w <= 0 || channels < 1 || channels > 4 ||
+        src_pitch < (int64_t)w * channels || dst_pitch < (int64_t)out_w * channels) {
+        vis::set_error("vis_gather_u8: bad arguments (%dx%d -> %dx%d, %d channels)", w, h, out_w, out_h, channels);
+        return VIS_E_INVALID;
+    }
+    const dim3 grid((out_w + 63) / 64, (out_h + 3) / 4);
+    k_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_pitch, channels, dst, dst_pitch, out_h, out_w, xtab, ytab);
+    return vis::check_launch("vis_gather_u8");
 }
 
 int vis_normalize_patchify(const uint8_t* src, int64_t src_pitch, int h, int w,

@@ -324,6 +324,28 @@ class Engine:
         self._keepalive_b = (k, b)
         return dst
 
+    def resize_nearest_u8(self, img: torch.Tensor, out_h: int, out_w: int, box=None) -> torch.Tensor:
+        """``Image.resize((out_w, out_h), NEAREST, box)`` for a CUDA uint8 HW / HWC tensor — Pillow's path for palette
+        and bilevel images whatever filter is named (index tables on the host, one gather launch)."""
+        self._check_u8(img)
+        squeeze = img.dim() == 2
+        if squeeze:
+            img = img.unsqueeze(-1)
+        if img.stride(2) != 1 or img.stride(1) != img.shape[2]:
+            img = img.contiguous()
+        h, w, ch = (int(v) for v in img.shape)
+        box = (0.0, 0.0, float(w), float(h)) if box is None else tuple(float(np.float32(v)) for v in box)
+        xt, yt = np.empty(out_w, np.int32), np.empty(out_h, np.int32)
+        N.check(self.L.vis_nearest_table(w, box[0], box[2], out_w, N.i32ptr(xt)), "vis_nearest_table")
+        N.check(self.L.vis_nearest_table(h, box[1], box[3], out_h, N.i32ptr(yt)), "vis_nearest_table")
+        d_xt, d_yt = torch.from_numpy(xt).to(self.device), torch.from_numpy(yt).to(self.device)
+        out = torch.empty((out_h, out_w, ch), dtype=torch.uint8, device=self.device)
+        N.check(self.L.vis_gather_u8(img.data_ptr(), img.stride(0), h, w, ch, out.data_ptr(), out.stride(0), out_h, out_w,
+                                     d_xt.data_ptr(), d_yt.data_ptr(), _stream_ptr()), "vis_gather_u8")
+        self.last_launches = 1
+        self._keepalive_n = (d_xt, d_yt)
+        return out.squeeze(-1) if squeeze else out
+
     def resize_reducing_u8(self, img: torch.Tensor, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS, box=None,
                            reducing_gap: float = 2.0) -> torch.Tensor:
         """``Image.resize((out_w, out_h), filt, box, reducing_gap)`` — what ``Image.thumbnail`` calls: an integer

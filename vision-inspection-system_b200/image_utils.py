@@ -165,13 +165,26 @@ def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int, box=None, 
     if img.size == tuple(size) and box == full:
         return img.copy()
     mode = img.mode
+    if mode in ("P", "1"):                           # Pillow forces NEAREST for these, whatever filter is named
+        work = img.convert("L") if mode == "1" else img          # "1" is stored as 0 / 255 bytes
+        arr = np.frombuffer(work.tobytes(), np.uint8).reshape(work.size[1], work.size[0])
+        out = _engine().resize_nearest_u8(torch.from_numpy(arr.copy()).cuda(), size[1], size[0],
+                                          None if box == full else box).cpu().numpy()
+        res = Image.frombytes(work.mode, tuple(size), out.tobytes())
+        if mode == "P":                              # Image._new: the palette and the info dict travel with the result
+            if img.palette is not None:
+                raw = img.palette.mode if img.palette.mode in ("RGB", "RGBA") else "RGB"
+                res.putpalette(img.getpalette(raw), raw)
+            res.info = img.info.copy()
+            return res
+        return res.convert("1", dither=Image.Dither.NONE)
     if mode in ("LA", "RGBA"):                       # Pillow resamples these in premultiplied form
         work, reducing_gap = img.convert({"LA": "La", "RGBA": "RGBa"}[mode]), None
     elif mode in ("L", "RGB", "RGBX", "CMYK", "YCbCr", "HSV", "LAB", "La", "RGBa"):
         work = img
     else:
-        raise NotImplementedError(f"image mode {mode!r} is resampled by Pillow with a non-8bpc or NEAREST path "
-                                  "that this engine does not implement")
+        raise NotImplementedError(f"image mode {mode!r} is resampled by Pillow with a non-8bpc path that this "
+                                  "engine does not implement")
     bands = len(work.getbands())
     arr = np.frombuffer(work.tobytes(), np.uint8).reshape(work.size[1], work.size[0], bands)
     dev = torch.from_numpy(arr.copy()).cuda()
