@@ -92,19 +92,9 @@ def dual_stream(eng, name, n):
 
     def run():
         launches[0] = 0
-        for limit in (G.INSPECTOR_MAX_SIZE, G.AUDITOR_MAX_SIZE):
-            batch = list(frames)
-            groups = {}
-            for i, f in enumerate(frames):                      # thumbnails: one fused launch per source geometry
-                h, w = int(f.shape[0]), int(f.shape[1])
-                if max(h, w) > limit:
-                    groups.setdefault((h, w), []).append(i)
-            for (h, w), idx in groups.items():
-                tw, th = G.thumbnail_size(w, h, limit)
-                outs = eng.resize_batch_u8([frames[i] for i in idx], th, tw, N.FILTER_LANCZOS)
-                launches[0] += eng.last_launches
-                for i, o in zip(idx, outs):
-                    batch[i] = o
+        for role in ("inspector", "auditor"):                       # thumbnails: one fused launch per source geometry
+            batch = eng.agent_inputs(frames, role)
+            launches[0] += eng.last_launches
             eng.preprocess(batch)
             launches[0] += eng.last_launches
     ms = timed(run, reps=3, warm=2)

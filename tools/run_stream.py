@@ -26,21 +26,6 @@ from vision_inspection_system_b200 import synth  # noqa: E402
 from vision_inspection_system_b200.engine import get_engine  # noqa: E402
 
 
-def role_inputs(eng, frames, limit):
-    """thumbnail(limit, LANCZOS) per source geometry (one fused launch each), then the frames for the processor"""
-    batch = list(frames)
-    groups = {}
-    for i, f in enumerate(frames):
-        h, w = int(f.shape[0]), int(f.shape[1])
-        if max(h, w) > limit:
-            groups.setdefault((h, w), []).append(i)
-    for (h, w), idx in groups.items():
-        tw, th = G.thumbnail_size(w, h, limit)
-        for i, o in zip(idx, eng.resize_batch_u8([frames[i] for i in idx], th, tw, N.FILTER_LANCZOS)):
-            batch[i] = o
-    return batch
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=512, help="frames of the whole job")
@@ -69,7 +54,7 @@ def main():
     def step():
         out = {}
         for role, limit in (("inspector", G.INSPECTOR_MAX_SIZE), ("auditor", G.AUDITOR_MAX_SIZE)):
-            out[role] = eng.preprocess(role_inputs(eng, frames, limit))
+            out[role] = eng.preprocess(eng.agent_inputs(frames, role))
         return out
 
     for _ in range(2):
@@ -114,7 +99,7 @@ def main():
             remote = [i for i in range(n_gather) if i not in set(mine)][:2]
             for i in remote:
                 f = torch.from_numpy(synth.noise_frame(9000 + i % 2, *shapes[i])).cuda()
-                want, _ = eng.preprocess(role_inputs(eng, [f], G.INSPECTOR_MAX_SIZE))
+                want, _ = eng.preprocess(eng.agent_inputs([f], "inspector"))
                 ok = ok and torch.equal(all_pv[starts[i]:starts[i + 1]], want)
             sec = g0.elapsed_time(g1) / 1e3
             recv = (all_pv.shape[0] - pv.shape[0]) * 1176 * 4

@@ -361,6 +361,34 @@ class Engine:
         self.last_launches += 1
         return out
 
+    def agent_inputs(self, frames, role: str = "inspector", max_size: int | None = None) -> list:
+        """The frames an agent's Qwen2-VL processor sees: ``thumbnail((S, S), LANCZOS)`` for every RGB frame larger than
+        S (2048 Inspector / 1024 Auditor — src/agents/vlm_inspector.py:63-64, vlm_auditor.py:90-91), the others
+        untouched.  Frames of one source geometry share ONE fused launch; frames >= 4x the limit take Pillow's
+        reduce pre-pass.  Returns a list aligned with ``frames``."""
+        limit = max_size or {"inspector": G.INSPECTOR_MAX_SIZE, "auditor": G.AUDITOR_MAX_SIZE}[role]
+        batch = list(frames.unbind(0)) if isinstance(frames, torch.Tensor) and frames.dim() == 4 else list(frames)
+        groups: dict = {}
+        for i, f in enumerate(batch):
+            h, w = int(f.shape[0]), int(f.shape[1])
+            if max(h, w) > limit:
+                groups.setdefault((h, w, f.stride(0)), []).append(i)
+        launches = 0
+        for (h, w, _), idx in groups.items():
+            tw, th = G.thumbnail_size(w, h, limit)
+            if G.reducing_plan(w, h, tw, th, N.FILTER_LANCZOS) is not None:
+                outs = []
+                for i in idx:
+                    outs.append(self.resize_reducing_u8(batch[i], th, tw, N.FILTER_LANCZOS))
+                    launches += self.last_launches
+            else:
+                outs = self.resize_batch_u8([batch[i] for i in idx], th, tw, N.FILTER_LANCZOS)
+                launches += self.last_launches
+            for i, o in zip(idx, outs):
+                batch[i] = o
+        self.last_launches = launches
+        return batch
+
     # ------------------------------------------------------------------ frames -> pixel_values
     def plan_batch(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
                    force_generic: bool = False, vsplit: int | None = None, path: str = "auto") -> "BatchPlan":

@@ -292,13 +292,9 @@ def preprocess_for_vlm(images, *, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pi
             t = im if im.is_cuda else im.cuda()
         else:
             t = torch.from_numpy(np.array(_to_rgb_array(im), dtype=np.uint8, order="C")).cuda()       # copy: PIL arrays are read-only
-        if role is not None:
-            h, w = int(t.shape[0]), int(t.shape[1])
-            limit = _ROLE_MAX_SIZE[role]
-            if max(h, w) > limit:
-                tw, th = G.thumbnail_size(w, h, limit)
-                t = eng.resize_reducing_u8(t, th, tw, int(Image.Resampling.LANCZOS))
         frames.append(t)
+    if role is not None:
+        frames = eng.agent_inputs(frames, role)          # thumbnails batched per source geometry
     return eng.preprocess(frames, min_pixels=min_pixels, max_pixels=max_pixels)
 
 
