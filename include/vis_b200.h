@@ -92,6 +92,12 @@ int vis_nearest_table(int in_size, float in0, float in1, int out_size, int32_t* 
 int vis_gather_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int channels, uint8_t* dst, int64_t dst_pitch,
                   int out_h, int out_w, const int32_t* xtab, const int32_t* ytab, void* stream);
 
+/* Alpha premultiplication around the resample of "RGBA" / "LA" frames, which Pillow resamples in premultiplied form
+ * (PIL:Image.py:2399-2402 -> libImaging/Convert.c rgbA2rgba / rgba2rgbA, la2lA / lA2la).  In place; channels = 4 (RGBA)
+ * or 2 (LA), alpha last.  forward != 0: c = MULDIV255(c, a) = ((t = c*a + 128) + (t >> 8)) >> 8; forward == 0:
+ * c = min(255, 255*c / a) unless a is 0 or 255 (copied).                                               [device] */
+int vis_alpha_premultiply_u8(uint8_t* img, int64_t pitch, int h, int w, int channels, int forward, void* stream);
+
 /* resized RGB uint8 HWC [h,w,3] (h,w multiples of 28) -> rows [row0, row0 + (h/14)*(w/14)) of
  * pixel_values [*,1176] f32 in Qwen2-VL patch order (tf:models/qwen2_vl/image_processing_pil_qwen2_vl.py:182-214):
  * rescale+normalize through lut768, temporal duplicate (T=2), 14x14 patches, 2x2 merge order.  [device] */

@@ -170,3 +170,33 @@ def test_palette_and_bilevel_frames_take_nearest_like_pillow(engine, tmp_path):
     p_img.save(path)
     for role in ("inspector", "auditor"):
         assert A.encode_image_optimized(path, 1024, role) == OA.encode_image_optimized(path, 1024, role), role
+
+
+def test_alpha_frames_are_resampled_premultiplied_like_pillow(engine):
+    """"RGBA" / "LA": premultiply (Convert.c rgbA2rgba), resample, un-premultiply — all on the device, same bytes as Pillow."""
+    from PIL import Image
+    rng = np.random.default_rng(71)
+    rgba = rng.integers(0, 256, (300, 420, 4), dtype=np.uint8)
+    rgba[:40, :, 3] = 0
+    rgba[40:80, :, 3] = 255
+    dev = torch.from_numpy(rgba.copy()).cuda()
+    engine.alpha_premultiply_(dev, True)
+    assert np.array_equal(dev.cpu().numpy(), np.asarray(Image.fromarray(rgba, "RGBA").convert("RGBa")))
+    dev = torch.from_numpy(rgba.copy()).cuda()
+    engine.alpha_premultiply_(dev, False)
+    assert np.array_equal(dev.cpu().numpy(), np.asarray(Image.frombytes("RGBa", (420, 300), rgba.tobytes()).convert("RGBA")))
+    big = rng.integers(0, 256, (1300, 2500, 4), dtype=np.uint8)
+    for mode, arr in (("RGBA", big), ("LA", big[:, :, [0, 3]])):
+        img = Image.frombytes(mode, (2500, 1300), np.ascontiguousarray(arr).tobytes())
+        ref = img.copy()
+        ref.thumbnail((1024, 1024), Image.Resampling.LANCZOS)
+        got = IU.pil_thumbnail(img, 1024)
+        assert got.mode == mode and got.size == ref.size and got.tobytes() == ref.tobytes(), mode
+        rz = IU.resize_image(img, 1000)
+        want = img.resize((1000, int(1300 * (1000 / 2500))), Image.Resampling.LANCZOS)
+        assert rz.tobytes() == want.tobytes(), mode
+    # a 5000-pixel RGBA frame: Pillow skips the reduce pre-pass on the alpha branch, and so do we
+    huge = Image.frombytes("RGBA", (5000, 700), rng.integers(0, 256, (700, 5000, 4), dtype=np.uint8).tobytes())
+    ref = huge.copy()
+    ref.thumbnail((1024, 1024), Image.Resampling.LANCZOS)
+    assert IU.pil_thumbnail(huge, 1024).tobytes() == ref.tobytes()

@@ -75,7 +75,7 @@ EXPORTS = [
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
     "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn",
-    "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8",
+    "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8", "vis_alpha_premultiply_u8",
     "vis_jpeg_create", "vis_jpeg_destroy", "vis_jpeg_info", "vis_jpeg_decode", "vis_jpeg_decode_batch",
     "vis_jpeg_encode_bound", "vis_jpeg_encode",
 ]
@@ -150,6 +150,7 @@ def _declare(L: C.CDLL) -> None:
                                 C.c_int, vp, C.c_int64, vp]
     L.vis_nearest_table.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, i32p]
     L.vis_gather_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
+    L.vis_alpha_premultiply_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.vis_jpeg_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.vis_jpeg_destroy.argtypes = [vp]
     L.vis_jpeg_info.argtypes = [vp, vp, C.c_int64, ip, ip, ip, ip]

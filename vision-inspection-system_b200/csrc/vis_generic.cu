@@ -150,6 +150,28 @@ k_gather(const uint8_t* __restrict__ src, int64_t src_pitch, int ch, uint8_t* __
     for (int c = 0; c < ch; ++c) d[c] = inside ? __ldg(s + c) : (uint8_t)0;
 }
 
+
+// Convert.c rgbA2rgba / rgba2rgbA (and the LA pair): premultiply / un-premultiply by the last channel, in place
+template <int CH, bool FORWARD>
+__global__ void __launch_bounds__(256)
+k_alpha(uint8_t* __restrict__ img, int64_t pitch, int h, int w) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= w || y >= h) return;
+    uint8_t* p = img + (int64_t)y * pitch + (int64_t)x * CH;
+    const unsigned a = p[CH - 1];
+    if (!FORWARD && (a == 0 || a == 255)) return;
+#pragma unroll
+    for (int c = 0; c < CH - 1; ++c) {
+        const unsigned v = p[c];
+        if (FORWARD) {
+            const unsigned t = v * a + 128;
+            p[c] = (uint8_t)(((t >> 8) + t) >> 8);
+        } else {
+            p[c] = (uint8_t)min(255u, 255u * v / a);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -252,6 +274,23 @@ int vis_gather_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int chann
     const dim3 grid((out_w + 63) / 64, (out_h + 3) / 4);
     k_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_pitch, channels, dst, dst_pitch, out_h, out_w, xtab, ytab);
     return vis::check_launch("vis_gather_u8");
+}
+
+int vis_alpha_premultiply_u8(uint8_t* img, int64_t pitch, int h, int w, int channels, int forward, void* stream) {
+    if (!img || h <= 0 || w <= 0 || (channels != 2 && channels != 4) || pitch < (int64_t)w * channels) {
+        vis::set_error("vis_alpha_premultiply_u8: bad arguments (%dx%d, %d channels)", w, h, channels);
+        return VIS_E_INVALID;
+    }
+    const dim3 grid((w + 63) / 64, (h + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels == 4) {
+        if (forward) k_alpha<4, true><<<grid, 256, 0, st>>>(img, pitch, h, w);
+        else         k_alpha<4, false><<<grid, 256, 0, st>>>(img, pitch, h, w);
+    } else {
+        if (forward) k_alpha<2, true><<<grid, 256, 0, st>>>(img, pitch, h, w);
+        else         k_alpha<2, false><<<grid, 256, 0, st>>>(img, pitch, h, w);
+    }
+    return vis::check_launch("vis_alpha_premultiply_u8");
 }
 
 int vis_normalize_patchify(const uint8_t* src, int64_t src_pitch, int h, int w,

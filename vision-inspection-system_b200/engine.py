@@ -324,6 +324,17 @@ class Engine:
         self._keepalive_b = (k, b)
         return dst
 
+    def alpha_premultiply_(self, img: torch.Tensor, forward: bool = True) -> torch.Tensor:
+        """In place: premultiply (``forward``) or un-premultiply the colour channels of an RGBA / LA CUDA uint8 HWC
+        tensor by its last channel, with Pillow's integer formulas (Convert.c rgbA2rgba / rgba2rgbA)."""
+        self._check_u8(img)
+        if img.dim() != 3 or img.shape[2] not in (2, 4) or img.stride(2) != 1 or img.stride(1) != img.shape[2]:
+            raise ValueError("expected a [H, W, 2|4] uint8 tensor with contiguous pixels")
+        N.check(self.L.vis_alpha_premultiply_u8(img.data_ptr(), img.stride(0), int(img.shape[0]), int(img.shape[1]),
+                                                int(img.shape[2]), 1 if forward else 0, _stream_ptr()),
+                "vis_alpha_premultiply_u8")
+        return img
+
     def resize_nearest_u8(self, img: torch.Tensor, out_h: int, out_w: int, box=None) -> torch.Tensor:
         """``Image.resize((out_w, out_h), NEAREST, box)`` for a CUDA uint8 HW / HWC tensor — Pillow's path for palette
         and bilevel images whatever filter is named (index tables on the host, one gather launch)."""

@@ -178,8 +178,9 @@ def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int, box=None, 
             res.info = img.info.copy()
             return res
         return res.convert("1", dither=Image.Dither.NONE)
-    if mode in ("LA", "RGBA"):                       # Pillow resamples these in premultiplied form
-        work, reducing_gap = img.convert({"LA": "La", "RGBA": "RGBa"}[mode]), None
+    premultiply = mode in ("LA", "RGBA")             # Pillow resamples these in premultiplied form ...
+    if premultiply:
+        work, reducing_gap = img, None               # ... and without the reduce pre-pass
     elif mode in ("L", "RGB", "RGBX", "CMYK", "YCbCr", "HSV", "LAB", "La", "RGBa"):
         work = img
     else:
@@ -189,14 +190,17 @@ def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int, box=None, 
     arr = np.frombuffer(work.tobytes(), np.uint8).reshape(work.size[1], work.size[0], bands)
     dev = torch.from_numpy(arr.copy()).cuda()
     eng = _engine()
+    if premultiply:
+        eng.alpha_premultiply_(dev, True)
     if reducing_gap is not None:
         out = eng.resize_reducing_u8(dev, size[1], size[0], int(filt), None if box == full else box, reducing_gap)
     elif box != full:
         out = eng.resize_box_u8(dev, size[1], size[0], int(filt), box)
     else:
         out = eng.resize_u8(dev, size[1], size[0], int(filt))
-    res = Image.frombytes(work.mode, tuple(size), out.cpu().numpy().tobytes())
-    return res.convert(mode) if work.mode != mode else res
+    if premultiply:
+        eng.alpha_premultiply_(out, False)
+    return Image.frombytes(work.mode, tuple(size), out.cpu().numpy().tobytes())
 
 
 def pil_thumbnail(img: Image.Image, max_size: int) -> Image.Image:
