@@ -124,7 +124,7 @@ def _imread_cuda(path, codec: str, bgr: bool = True):
             try:
                 return _engine().jpeg_codec().decode(data, bgr=bgr)
             except Exception as e:          # CMYK, arithmetic coding, damaged stream: let the host decoder decide
-                logger.debug("nvJPEG declined %s (%s); host decode", path, e)
+                logger.warning("nvJPEG declined %s (%s); decoding on the host like the reference", path, e)
     img = cv2.imread(str(path))
     if img is None:
         return None
@@ -289,7 +289,7 @@ def preprocess_for_vlm(images, *, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pi
                 for i, t in zip(streams, decoded):
                     images[i] = t
             except Exception as e:
-                logger.debug("nvJPEG declined the batch (%s); host decode", e)
+                logger.warning("nvJPEG declined the batch (%s); decoding on the host like the reference", e)
     frames = []
     for im in images:
         if isinstance(im, torch.Tensor):
