@@ -28,7 +28,12 @@ def main():
     shapes = [(1080, 1920)] * n
     t0 = time.perf_counter()
     plan = eng.plan_overlay(shapes, boxes)
-    t_plan = time.perf_counter() - t0
+    t_plan_first = time.perf_counter() - t0              # includes the one-time pinned-buffer allocation
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan = eng.plan_overlay(shapes, boxes)
+    torch.cuda.synchronize()
+    t_plan = time.perf_counter() - t0                    # steady state: box rules, expansion, tile binning, upload
     n_leaves = plan[0].numel() // 48
     out = eng.annotate(frames, boxes, plan=plan)
     torch.cuda.synchronize()
@@ -67,7 +72,7 @@ def main():
         "workload": f"{n} annotated 1080p BGR frames, {sum(len(b) for b in boxes)} boxes, {n_leaves} leaves",
         "out_of_place": {"ms": ms_oop, "images_per_s": n / ms_oop * 1e3, "hbm_frac": n * bytes_img / ms_oop / 1e6 / peak},
         "in_place": {"ms": ms_inp, "images_per_s": n / ms_inp * 1e3},
-        "host_expand_ms_per_frame": t_plan / n * 1e3, "leaf_bytes_per_frame": n_leaves * 48 / n,
+        "host_plan_ms_per_frame": t_plan / n * 1e3, "host_plan_first_call_ms_per_frame": t_plan_first / n * 1e3, "leaf_bytes_per_frame": n_leaves * 48 / n,
         "cpu_cv2_draw_only_ms_per_frame": cpu_ms, "peak_gbs": peak}))
     assert torch.equal(out[:distinct], out[distinct:2 * distinct]) if n >= 2 * distinct else True
 

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "vis_internal.h"
@@ -210,6 +211,44 @@ class Emitter {
 
     int count() const { return n_; }
     bool ok() const { return glyph_ok_; }
+
+    // appends a copy of every leaf of `tpl` moved by (dx, dy) whole pixels: all leaf parameters are affine in the
+    // pixel coordinates (16.16 walkers, pixel rows / columns, packed boxes), so this equals expanding the same calls
+    // at the moved position as long as nothing there is clipped by the image border (the caller checks)
+    void instantiate(const std::vector<VisLeaf>& tpl, int dx, int dy) {
+        for (const VisLeaf& t : tpl) {
+            VisLeaf l = t;
+            const int kind = l.w[0] & LEAF_KIND_MASK;
+            const bool xmajor = l.w[0] & LEAF_FLAG_XMAJOR;
+            switch (kind) {
+                case LEAF_LINE8:
+                    l.w[2] += xmajor ? dx : dy;
+                    l.w[4] += (xmajor ? dy : dx) * (int32_t)kOne;
+                    l.w[6] += dx;
+                    l.w[7] += dy;
+                    break;
+                case LEAF_LINEAA:
+                    l.w[2] += xmajor ? dx : dy;
+                    l.w[4] += (xmajor ? dy : dx) * (int32_t)kOne;
+                    break;
+                case LEAF_TRAP:
+                    l.w[2] += dy; l.w[3] += dy;
+                    l.w[4] += dx * (int32_t)kOne; l.w[6] += dx * (int32_t)kOne;
+                    break;
+                case LEAF_SPANS:
+                    l.w[2] += dx; l.w[3] += dy;
+                    break;
+                default:
+                    continue;
+            }
+            const int x0 = (l.w[10] & 0xffff) + dx, x1 = (int)((uint32_t)l.w[10] >> 16) + dx;
+            const int y0 = (l.w[11] & 0xffff) + dy, y1 = (int)((uint32_t)l.w[11] >> 16) + dy;
+            pack_bbox(l, x0, y0, x1, y1);
+            gx0_ = std::min(gx0_, x0); gy0_ = std::min(gy0_, y0);
+            gx1_ = std::max(gx1_, x1); gy1_ = std::max(gy1_, y1);
+            push(l);
+        }
+    }
 
     void set_color(int b, int g, int r, int a = 0) {
         color_ = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16) | ((uint32_t)a << 24);
@@ -644,6 +683,88 @@ class Emitter {
     }
 };
 
+
+// ---- templates ------------------------------------------------------------------------------------------------------
+// The marker (white disc, coloured ring, label) and an interior dash expand to the same leaves wherever they sit, up to
+// a whole-pixel translation: the leaves are built once on a private canvas and copied with an offset afterwards
+// (Emitter::instantiate) — ~600 leaves per marker and ~20 per dash that the host no longer recomputes per box.
+struct Template {
+    std::vector<VisLeaf> leaves;
+    int ox = 0, oy = 0;              // canvas position of the anchor (marker centre / dash start)
+    int ex = 0, ey = 0;              // marker: half extents (pixels) the instance must have free around its centre
+    bool ok = true;                  // false: a label glyph outside printable ASCII
+};
+
+struct TemplateCache {
+    std::unordered_map<std::string, Template> map;
+    const Template& get(const std::string& key, Template (*build)(const void*), const void* arg) {
+        auto it = map.find(key);
+        if (it != map.end()) return it->second;
+        if (map.size() >= 512) map.clear();
+        return map.emplace(key, build(arg)).first->second;
+    }
+};
+
+struct MarkerSpec { int radius; uint8_t b, g, r; char label[13]; };
+struct DashSpec { int dx, dy, thickness, line_type; uint8_t b, g, r; };
+
+Template build_marker(const void* arg) {
+    const MarkerSpec& m = *static_cast<const MarkerSpec*>(arg);
+    Template t;
+    // half extents: the ring, or the label when it is wider / taller than the ring (any printable ASCII is allowed)
+    const double fs = m.radius / 20.0 * 0.7;
+    const int tt = std::max(2, (int)(fs * 2));
+    int lw = 0, lh = 0;
+    {
+        Emitter probe(1, 1, nullptr, 0);
+        if (!probe.text_size(m.label, fs, tt, &lw, &lh)) { t.ok = false; return t; }
+    }
+    t.ex = std::max(m.radius + 4, lw / 2 + tt + 8);
+    t.ey = std::max(m.radius + 4, lh + tt + 8);
+    const int pad = 8, cxc = t.ex + pad, cyc = t.ey + pad;           // nothing comes near the canvas border
+    t.ox = cxc; t.oy = cyc;
+    std::vector<VisLeaf> buf(4096);
+    for (;;) {
+        Emitter em(2 * cyc + 1, 2 * cxc + 1, buf.data(), (int)buf.size());
+        em.begin_group();
+        em.set_color(255, 255, 255);
+        em.circle_filled(cxc, cyc, m.radius);                         // utils/image_utils.py:299
+        em.set_color(m.b, m.g, m.r);
+        em.circle_outline(cxc, cyc, m.radius, 3);                     // :302
+        const double font_scale = m.radius / 20.0 * 0.7;              // :305-313
+        const int text_thickness = std::max(2, (int)(font_scale * 2));
+        int tw = 0, th = 0;
+        if (!em.text_size(m.label, font_scale, text_thickness, &tw, &th)) { t.ok = false; return t; }
+        em.set_color(0, 0, 0);
+        em.put_text(m.label, (int)(cxc - tw / 2.0), (int)(cyc + th / 2.0), font_scale, text_thickness);
+        if (em.count() <= (int)buf.size()) { buf.resize((size_t)em.count()); break; }
+        buf.resize((size_t)em.count());
+    }
+    t.leaves = std::move(buf);
+    return t;
+}
+
+Template build_dash(const void* arg) {
+    const DashSpec& d = *static_cast<const DashSpec*>(arg);
+    Template t;
+    const int pad = d.thickness + 8;
+    t.ox = t.oy = pad;
+    const int w = d.dx + 2 * pad + 1, h = d.dy + 2 * pad + 1;
+    std::vector<VisLeaf> buf(256);
+    for (;;) {
+        Emitter em(h, w, buf.data(), (int)buf.size());
+        em.begin_group();
+        em.set_color(d.b, d.g, d.r);
+        em.line(pad, pad, pad + d.dx, pad + d.dy, d.thickness, d.line_type);
+        if (em.count() <= (int)buf.size()) { buf.resize((size_t)em.count()); break; }
+        buf.resize((size_t)em.count());
+    }
+    t.leaves = std::move(buf);
+    return t;
+}
+
+thread_local TemplateCache g_templates;
+
 }  // namespace
 
 extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int n_boxes,
@@ -661,19 +782,32 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
         const int x = b.x, y = b.y, w = b.w, h = b.h;
         em.begin_group();
         em.set_color(b.b, b.g, b.r);
+        // a dash whose strokes stay clear of the image border is an instance of the dash template
+        auto dash = [&](int x1, int y1, int x2, int y2) {
+            const int m = 8;
+            if (std::min(x1, x2) >= m && std::min(y1, y2) >= m && std::max(x1, x2) < img_w - m && std::max(y1, y2) < img_h - m) {
+                DashSpec d{x2 - x1, y2 - y1, 2, 16, b.b, b.g, b.r};
+                char key[64];
+                std::snprintf(key, sizeof key, "d%d,%d,%d,%d,%d", d.dx, d.dy, b.b, b.g, b.r);
+                const Template& t = g_templates.get(key, build_dash, &d);
+                em.instantiate(t.leaves, x1 - t.ox, y1 - t.oy);
+            } else {
+                em.line(x1, y1, x2, y2, 2, 16);
+            }
+        };
         if (b.dashed) {                          // utils/image_utils.py:260-283: 10 px dashes, 5 px gaps
             for (int k = 0; k < 2; ++k) {
                 const int yy = k == 0 ? y : y + h;
                 for (int px = x; px < x + w; px += 15) {
                     const int ex = std::min(px + 10, x + w);
-                    if (ex > px) em.line(px, yy, ex, yy, 2, 16);
+                    if (ex > px) dash(px, yy, ex, yy);
                 }
             }
             for (int k = 0; k < 2; ++k) {
                 const int xx = k == 0 ? x : x + w;
                 for (int py = y; py < y + h; py += 15) {
                     const int ey = std::min(py + 10, y + h);
-                    if (ey > py) em.line(xx, py, xx, ey, 2, 16);
+                    if (ey > py) dash(xx, py, xx, ey);
                 }
             }
         } else {
@@ -684,23 +818,38 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
         radius = std::max(25, std::min(radius, 60));
         const int cx = std::max(radius + 5, std::min(x + radius + 5, img_w - radius - 5));
         const int cy = std::max(radius + 5, std::min(y + radius + 5, img_h - radius - 5));
-        em.set_color(255, 255, 255);
-        em.circle_filled(cx, cy, radius);
-        em.set_color(b.b, b.g, b.r);
-        em.circle_outline(cx, cy, radius, 3);
-        // label (:305-313)
-        const double font_scale = radius / 20.0 * 0.7;
-        const int text_thickness = std::max(2, (int)(font_scale * 2));
+        // disc, ring and label (:299-313): an instance of the marker template when the ring and the label stay clear of
+        // the image border (the usual case: the centre is clamped radius + 5 away from it and '#<n>' fits the ring);
+        // expanded in place otherwise (wide free-text labels near an edge, images smaller than the marker)
         char label[13];
         std::memcpy(label, b.label, 12);
         label[12] = 0;
-        int tw = 0, th = 0;
-        if (!em.text_size(label, font_scale, text_thickness, &tw, &th)) {
+        MarkerSpec m{radius, b.b, b.g, b.r, {0}};
+        std::memcpy(m.label, label, 13);
+        char key[64];
+        std::snprintf(key, sizeof key, "m%d,%d,%d,%d,", radius, b.b, b.g, b.r);
+        const Template& t = g_templates.get(std::string(key) + label, build_marker, &m);
+        if (!t.ok) {
             vis::set_error("vis_overlay_expand: label '%s' has a character outside printable ASCII", label);
             return VIS_E_UNSUPPORTED;
         }
-        em.set_color(0, 0, 0);
-        em.put_text(label, (int)(cx - tw / 2.0), (int)(cy + th / 2.0), font_scale, text_thickness);
+        if (cx - t.ex >= 0 && cy - t.ey >= 0 && cx + t.ex < img_w && cy + t.ey < img_h) {
+            em.instantiate(t.leaves, cx - t.ox, cy - t.oy);
+        } else {
+            em.set_color(255, 255, 255);
+            em.circle_filled(cx, cy, radius);
+            em.set_color(b.b, b.g, b.r);
+            em.circle_outline(cx, cy, radius, 3);
+            const double font_scale = radius / 20.0 * 0.7;
+            const int text_thickness = std::max(2, (int)(font_scale * 2));
+            int tw = 0, th = 0;
+            if (!em.text_size(label, font_scale, text_thickness, &tw, &th)) {
+                vis::set_error("vis_overlay_expand: label '%s' has a character outside printable ASCII", label);
+                return VIS_E_UNSUPPORTED;
+            }
+            em.set_color(0, 0, 0);
+            em.put_text(label, (int)(cx - tw / 2.0), (int)(cy + th / 2.0), font_scale, text_thickness);
+        }
         em.end_group(i);
     }
     if (needed) *needed = em.count();
@@ -862,7 +1011,7 @@ extern "C" int vis_overlay_plan_batch(int n_frames, const int32_t* hw, const Vis
             const VisBox* b = boxes + box_begin[i];
             if (nb <= 0) continue;
             int need = 0;
-            fr.leaves.resize((size_t)nb * 1600);
+            fr.leaves.resize((size_t)nb * 1400);
             int rc = vis_overlay_expand(h, w, b, nb, fr.leaves.data(), (int)fr.leaves.size(), &need);
             if (rc == VIS_E_CAPACITY) {
                 fr.leaves.resize((size_t)need);
@@ -901,25 +1050,41 @@ extern "C" int vis_overlay_plan_batch(int n_frames, const int32_t* hw, const Vis
         vis::set_error("vis_overlay_plan_batch: needs %lld leaves / %lld tiles / %lld refs", (long long)nl, (long long)nt, (long long)nr);
         return VIS_E_CAPACITY;
     }
-    int64_t al = 0, at = 0, ar = 0;
+    // offsets of every frame in the three output arrays, then the copy-out spread over the same threads (the leaves
+    // alone are ~280 KB per annotated 1080p frame: a single-threaded merge would cost as much as the expansion)
+    std::vector<int64_t> off_l((size_t)n_frames + 1, 0), off_t((size_t)n_frames + 1, 0), off_r((size_t)n_frames + 1, 0);
     for (int i = 0; i < n_frames; ++i) {
         const Frame& fr = out[(size_t)i];
-        leaf_begin[i] = (int32_t)al;
-        if (!fr.leaves.empty()) std::memcpy(leaves + al, fr.leaves.data(), fr.leaves.size() * sizeof(VisLeaf));
-        for (size_t k = 0; k < fr.tiles.size() / 3; ++k) {
-            VisOverlayTile& t = tiles[at++];
-            t.frame = i;
-            t.txy = fr.tiles[3 * k];
-            t.ref_begin = fr.tiles[3 * k + 1] + (int32_t)ar;
-            t.ref_end = fr.tiles[3 * k + 2] + (int32_t)ar;
-        }
-        for (size_t k = 0; k < fr.refs.size() / 2; ++k) {
-            refs[ar].leaf_begin = fr.refs[2 * k];
-            refs[ar].leaf_end = fr.refs[2 * k + 1];
-            ++ar;
-        }
-        al += (int64_t)fr.leaves.size();
+        off_l[i + 1] = off_l[i] + (int64_t)fr.leaves.size();
+        off_t[i + 1] = off_t[i] + (int64_t)fr.tiles.size() / 3;
+        off_r[i + 1] = off_r[i] + (int64_t)fr.refs.size() / 2;
+        leaf_begin[i] = (int32_t)off_l[i];
     }
+    const int64_t al = off_l[n_frames];
+    next.store(0);
+    auto merge = [&]() {
+        for (int i = next.fetch_add(1); i < n_frames; i = next.fetch_add(1)) {
+            const Frame& fr = out[(size_t)i];
+            if (!fr.leaves.empty()) std::memcpy(leaves + off_l[i], fr.leaves.data(), fr.leaves.size() * sizeof(VisLeaf));
+            const int32_t rbase = (int32_t)off_r[i];
+            VisOverlayTile* t = tiles + off_t[i];
+            for (size_t k = 0; k < fr.tiles.size() / 3; ++k, ++t) {
+                t->frame = i;
+                t->txy = fr.tiles[3 * k];
+                t->ref_begin = fr.tiles[3 * k + 1] + rbase;
+                t->ref_end = fr.tiles[3 * k + 2] + rbase;
+            }
+            VisOverlayRef* r = refs + off_r[i];
+            for (size_t k = 0; k < fr.refs.size() / 2; ++k, ++r) {
+                r->leaf_begin = fr.refs[2 * k];
+                r->leaf_end = fr.refs[2 * k + 1];
+            }
+        }
+    };
+    pool.clear();
+    for (int t = 1; t < nth; ++t) pool.emplace_back(merge);
+    merge();
+    for (auto& t : pool) t.join();
     leaf_begin[n_frames] = (int32_t)al;
     return (int)nt;
 }
