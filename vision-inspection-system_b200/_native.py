@@ -44,7 +44,7 @@ FRAME_REF_DTYPE = np.dtype([("src", np.uint64), ("row0", np.int64)], align=True)
 SCHED_HEAD_DTYPE = np.dtype([("src_h", np.int32), ("src_w", np.int32), ("dst_h", np.int32), ("dst_w", np.int32),
                              ("src_pitch", np.int64), ("kt", np.int32), ("n_strips", np.int32), ("n_segs", np.int32),
                              ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("per_index", np.int32), ("ring", np.int32),
-                             ("n_subs", np.int32), ("out_mode", np.int32), ("h_pull", np.int32)], align=True)
+                             ("n_subs", np.int32), ("out_mode", np.int32), ("h_pull", np.int32), ("n_vwarps", np.int32), ("pad0", np.int32)], align=True)
 SCHED_OUT_PIXEL_VALUES, SCHED_OUT_U8 = 0, 1
 RESIZE_REF_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64)], align=True)
 
@@ -100,7 +100,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 11:
+        if L.vis_abi_version() != 12:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib

@@ -29,7 +29,7 @@ using namespace visf;
 
 namespace visf {   // 16-slot kernel, vis_fused_sched16.cu
 int sched16_subs();
-int sched16_max_strip_w();
+int sched16_max_strip_w(int nv);
 int sched16_layout_bytes(int stage_pitch, int strip_w, int cls);
 int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
                    const float* lut768, float* pixel_values, cudaStream_t st);
@@ -443,7 +443,9 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const int ring = cls <= 8 ? 8 : 16;
     const bool h_pull = cls > 16;
     const int n_subs = ring == 8 ? 12 : visf::sched16_subs();
-    const int max_w = ring == 8 ? kMaxStripW : visf::sched16_max_strip_w();
+    // 16-slot kernel: 4 vertical-pass warps when the vertical downscale is strong (the V role is light), else 6
+    const int n_vwarps = ring == 8 ? 0 : ((double)src_h / dst_h >= 2.4 ? 4 : 6);
+    const int max_w = ring == 8 ? kMaxStripW : visf::sched16_max_strip_w(n_vwarps);
     std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
     int per_index = 1;
     // an exact class (13, 14) may be too tight for the virtual ends of the far-border samples: widen it
@@ -460,6 +462,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     std::memset(&s, 0, sizeof(s));
     s.src_h = src_h; s.src_w = src_w; s.dst_h = dst_h; s.dst_w = dst_w; s.src_pitch = src_pitch; s.kt = cls;
     s.per_index = per_index; s.ring = ring; s.n_subs = n_subs; s.out_mode = out_mode; s.h_pull = h_pull ? 1 : 0;
+    s.n_vwarps = n_vwarps;
     const int stride = vis_record_stride(cls);
     auto last = [](const int32_t* b, int i) { return b[2 * i] + b[2 * i + 1] - 1; };
     auto span_of = [&](int x0, int x1, int* px0) {

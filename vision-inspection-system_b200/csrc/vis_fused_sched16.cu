@@ -26,15 +26,14 @@ namespace {
 #ifndef VIS_S16_HWARPS
 #define VIS_S16_HWARPS 12
 #endif
-#ifndef VIS_S16_VWARPS
-#define VIS_S16_VWARPS 6
-#endif
-constexpr int kHWarps = VIS_S16_HWARPS, kVWarps = VIS_S16_VWARPS, kSWarps = 2;    // H is the heavy role at these scales (profiles/r01_fused_sched16_4k.txt)
+constexpr int kHWarps = VIS_S16_HWARPS, kSWarps = 2;    // H is the heavy role at these scales (profiles/r01_fused_sched16_4k.txt)
 // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
 constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
-constexpr int kThreads16 = (kHWarps + kVWarps + kSWarps + 1) * 32;      // 640: 96 registers per thread
+// vertical-pass warps NV: 6 for the mild downscales (V and H work comparable), 4 for the strong ones (V is light: fewer,
+// fuller warps issue a third fewer instructions and every SMSP holds 3 H + 1 V warp) — picked by vis_sched_build
+constexpr int threads16(int nv) { return (kHWarps + nv + kSWarps + 1) * 32; }      // 672 / 608: <= 96 registers per thread
 constexpr int kChunk = 32, kStepPx = 16, kRing = 16;
-constexpr int kMaxStripW16 = kVWarps * 32 / 3 * 4;                      // 256: one V thread per 4 columns of one channel
+constexpr int max_strip_w16(int nv) { return nv * 32 / 3 * 4; }         // 256 / 168: one V thread per 4 columns of one channel
 constexpr int kVRecs = kChunk + 1;                // vertical records a chunk can touch (scale >= 1): 32 emits + 1 look-ahead
 constexpr int kSmemMax = 227 * 1024;
 
@@ -113,8 +112,8 @@ __device__ __forceinline__ void hpull(uint32_t wbase, const int (&kf)[KT], int& 
 
 struct FramePtrs { const unsigned char* src; long long second; };      // VisFrameRef / VisResizeRef: same layout
 
-template <int KT, int STRIDE, bool U8>
-__global__ void __launch_bounds__(kThreads16, 1)
+template <int KT, int STRIDE, bool U8, int NV>
+__global__ void __launch_bounds__(threads16(NV), 1)
 k_fused_sched16(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ frames, int n_items,
                 const __grid_constant__ Layout16 L, long long dst_pitch, const int* __restrict__ hrec_g,
                 const int* __restrict__ vrec_g, const float* __restrict__ lut768, float* __restrict__ pixel_values) {
@@ -128,15 +127,15 @@ k_fused_sched16(const __grid_constant__ VisSched sc, const FramePtrs* __restrict
     const int per_frame = sc.n_strips * sc.n_segs;
 
     if (!U8)
-        for (int i = tid; i < 768; i += kThreads16) lut[(i % 3) * 256 + i / 3] = __ldg(lut768 + i);
+        for (int i = tid; i < 768; i += (int)blockDim.x) lut[(i % 3) * 256 + i / 3] = __ldg(lut768 + i);
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar(SF, s), 1);
             mbar_init(bar(SE, s), kHWarps);
             mbar_init(bar(HF, s), kHWarps);
-            mbar_init(bar(HE, s), kVWarps);
+            mbar_init(bar(HE, s), NV);
             mbar_init(bar(VF, s), 1);
-            mbar_init(bar(OF, s), kVWarps);
+            mbar_init(bar(OF, s), NV);
             mbar_init(bar(OE, s), kSWarps);
         }
         fence_mbar_init();
@@ -453,17 +452,17 @@ k_fused_sched16(const __grid_constant__ VisSched sc, const FramePtrs* __restrict
     }
 }
 
-template <int KT, int STRIDE, bool U8>
+template <int KT, int STRIDE, bool U8, int NV>
 int launch16(const VisSched& sc, const void* frames, int n_frames, const Layout16& L, int64_t dst_pitch, const int* hrec,
              const int* vrec, const float* lut768, float* pixel_values, cudaStream_t st) {
-    auto kern = k_fused_sched16<KT, STRIDE, U8>;
+    auto kern = k_fused_sched16<KT, STRIDE, U8, NV>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return vis::cuda_fail(e, "vis_fused_sched16: cudaFuncSetAttribute");
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_items = n_frames * sc.n_strips * sc.n_segs;
     const int grid = n_items < sms ? n_items : sms;
-    kern<<<grid, kThreads16, L.total, st>>>(sc, reinterpret_cast<const FramePtrs*>(frames), n_items, L, (long long)dst_pitch,
+    kern<<<grid, threads16(NV), L.total, st>>>(sc, reinterpret_cast<const FramePtrs*>(frames), n_items, L, (long long)dst_pitch,
                                             hrec, vrec, lut768, pixel_values);
     return vis::check_launch("vis_fused_sched16");
 }
@@ -474,13 +473,13 @@ namespace visf {
 
 int sched16_subs() { return kHWarps; }
 
-int sched16_max_strip_w() { return kMaxStripW16; }
+int sched16_max_strip_w(int nv) { return max_strip_w16(nv); }
 
 int sched16_layout_bytes(int stage_pitch, int strip_w, int cls) { return make_layout16(stage_pitch, strip_w, cls).total; }
 
 int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
                    const float* lut768, float* pixel_values, cudaStream_t st) {
-    if (sc.kt < 12 || sc.kt > 32 || sc.ring != 16 || sc.n_subs != kHWarps || sc.per_index != 1) {
+    if (sc.kt < 12 || sc.kt > 32 || sc.ring != 16 || sc.n_subs != kHWarps || sc.per_index != 1 || (sc.n_vwarps != 4 && sc.n_vwarps != 6)) {
         vis::set_error("vis_fused_sched16: schedule of another kernel class (ring %d, %d taps, %d sub-ranges)", sc.ring, sc.kt, sc.n_subs);
         return VIS_E_INVALID;
     }
@@ -490,8 +489,9 @@ int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t
         return VIS_E_UNSUPPORTED;
     }
     const bool u8 = sc.out_mode == VIS_SCHED_OUT_U8;
-#define VIS_L16(KT) (u8 ? launch16<KT, ((KT + 5) & ~3), true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st) \
-                        : launch16<KT, ((KT + 5) & ~3), false>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st))
+#define VIS_L16N(KT, NV) (u8 ? launch16<KT, ((KT + 5) & ~3), true, NV>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st) \
+                            : launch16<KT, ((KT + 5) & ~3), false, NV>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st))
+#define VIS_L16(KT) (sc.n_vwarps == 4 ? VIS_L16N(KT, 4) : VIS_L16N(KT, 6))
     switch (sc.kt) {
         case 12: return VIS_L16(12);
         case 13: return VIS_L16(13);          // exact classes of the strong downscales (4K -> 1316x728, the 1.875x and
@@ -499,10 +499,15 @@ int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t
         case 16: return VIS_L16(16);
         case 24: return VIS_L16(24);
         case 32: return VIS_L16(32);
-        case 20: if (u8) return launch16<20, 24, true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st); break;
-        case 28: if (u8) return launch16<28, 32, true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st); break;
+        case 20: if (u8) return sc.n_vwarps == 4 ? launch16<20, 24, true, 4>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st)
+                                                 : launch16<20, 24, true, 6>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st);
+                 break;
+        case 28: if (u8) return sc.n_vwarps == 4 ? launch16<28, 32, true, 4>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st)
+                                                 : launch16<28, 32, true, 6>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st);
+                 break;
         default: break;
     }
+#undef VIS_L16N
 #undef VIS_L16
     vis::set_error("vis_fused_sched16: no instantiation for %d taps in this output mode", sc.kt);
     return VIS_E_UNSUPPORTED;
