@@ -183,7 +183,7 @@ typedef struct VisSched {            /* opaque to callers: filled by vis_sched_b
     int32_t n_subs;                  /* column sub-ranges per strip = horizontal-pass warps (12 / 9)               */
     int32_t out_mode;                /* VIS_SCHED_OUT_PIXEL_VALUES or VIS_SCHED_OUT_U8                              */
     int32_t h_pull;                  /* 1: 17..32 taps, the horizontal role pulls its window (no step masks)        */
-    int32_t n_vwarps;                /* 16-slot kernel: vertical-pass warps of the launch (6, or 4 for strong downscales) */
+    int32_t n_vwarps;                /* 16-slot kernel: vertical-pass warps of the launch (6 / 4 / 3: fewer for strong downscales) */
     int32_t pad0;                    /* keeps the arrays below 8-byte aligned                                          */
     VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
     VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_SUBS];

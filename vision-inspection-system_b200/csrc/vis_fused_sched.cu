@@ -443,8 +443,9 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const int ring = cls <= 8 ? 8 : 16;
     const bool h_pull = cls > 16;
     const int n_subs = ring == 8 ? 12 : visf::sched16_subs();
-    // 16-slot kernel: 4 vertical-pass warps when the vertical downscale is strong (the V role is light), else 6
-    const int n_vwarps = ring == 8 ? 0 : ((double)src_h / dst_h >= 2.4 ? 4 : 6);
+    // 16-slot kernel: fewer vertical-pass warps the stronger the vertical downscale (the V role gets lighter)
+    const double vscale = (double)src_h / dst_h;
+    const int n_vwarps = ring == 8 ? 0 : cls > 16 ? (vscale >= 3.4 ? 3 : 4) : (vscale >= 2.4 ? 4 : 6);
     const int max_w = ring == 8 ? kMaxStripW : visf::sched16_max_strip_w(n_vwarps);
     std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
     int per_index = 1;

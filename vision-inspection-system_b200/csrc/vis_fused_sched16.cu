@@ -30,7 +30,8 @@ constexpr int kHWarps = VIS_S16_HWARPS, kSWarps = 2;    // H is the heavy role a
 // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
 constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
 // vertical-pass warps NV: 6 for the mild downscales (V and H work comparable), 4 for the strong ones (V is light: fewer,
-// fuller warps issue a third fewer instructions and every SMSP holds 3 H + 1 V warp) — picked by vis_sched_build
+// fuller warps issue a third fewer instructions and every SMSP holds 3 H + 1 V warp), 3 from 3.4x on — picked by
+// vis_sched_build (A/B on 4K frames: 2.97x: 6 -> 56 k, 4 -> 63 k, 3 -> 48 k images/s; 3.75x: 6 -> 29 k, 4 -> 31 k, 3 -> 34 k)
 constexpr int threads16(int nv) { return (kHWarps + nv + kSWarps + 1) * 32; }      // 672 / 608: <= 96 registers per thread
 constexpr int kChunk = 32, kStepPx = 16, kRing = 16;
 constexpr int max_strip_w16(int nv) { return nv * 32 / 3 * 4; }         // 256 / 168: one V thread per 4 columns of one channel
@@ -479,7 +480,7 @@ int sched16_layout_bytes(int stage_pitch, int strip_w, int cls) { return make_la
 
 int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
                    const float* lut768, float* pixel_values, cudaStream_t st) {
-    if (sc.kt < 12 || sc.kt > 32 || sc.ring != 16 || sc.n_subs != kHWarps || sc.per_index != 1 || (sc.n_vwarps != 4 && sc.n_vwarps != 6)) {
+    if (sc.kt < 12 || sc.kt > 32 || sc.ring != 16 || sc.n_subs != kHWarps || sc.per_index != 1 || (sc.kt <= 16 ? (sc.n_vwarps != 4 && sc.n_vwarps != 6) : (sc.n_vwarps != 3 && sc.n_vwarps != 4))) {
         vis::set_error("vis_fused_sched16: schedule of another kernel class (ring %d, %d taps, %d sub-ranges)", sc.ring, sc.kt, sc.n_subs);
         return VIS_E_INVALID;
     }
@@ -491,22 +492,23 @@ int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t
     const bool u8 = sc.out_mode == VIS_SCHED_OUT_U8;
 #define VIS_L16N(KT, NV) (u8 ? launch16<KT, ((KT + 5) & ~3), true, NV>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st) \
                             : launch16<KT, ((KT + 5) & ~3), false, NV>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st))
-#define VIS_L16(KT) (sc.n_vwarps == 4 ? VIS_L16N(KT, 4) : VIS_L16N(KT, 6))
+#define VIS_L16(KT) (sc.n_vwarps == 4 ? VIS_L16N(KT, 4) : VIS_L16N(KT, 6))              /* push-order H: 9..16 taps */
+#define VIS_L16P(KT) (sc.n_vwarps == 3 ? VIS_L16N(KT, 3) : VIS_L16N(KT, 4))             /* pull-order H: 17..32 taps */
+#define VIS_L16PU(KT, ST) (sc.n_vwarps == 3 ? launch16<KT, ST, true, 3>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st) \
+                                            : launch16<KT, ST, true, 4>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st))
     switch (sc.kt) {
         case 12: return VIS_L16(12);
         case 13: return VIS_L16(13);          // exact classes of the strong downscales (4K -> 1316x728, the 1.875x and
         case 14: return VIS_L16(14);          // 2x LANCZOS thumbnails): 13 taps cost 13 MACs, not 16
         case 16: return VIS_L16(16);
-        case 24: return VIS_L16(24);
-        case 32: return VIS_L16(32);
-        case 20: if (u8) return sc.n_vwarps == 4 ? launch16<20, 24, true, 4>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st)
-                                                 : launch16<20, 24, true, 6>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st);
-                 break;
-        case 28: if (u8) return sc.n_vwarps == 4 ? launch16<28, 32, true, 4>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st)
-                                                 : launch16<28, 32, true, 6>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st);
-                 break;
+        case 24: return VIS_L16P(24);
+        case 32: return VIS_L16P(32);
+        case 20: if (u8) return VIS_L16PU(20, 24); break;
+        case 28: if (u8) return VIS_L16PU(28, 32); break;
         default: break;
     }
+#undef VIS_L16P
+#undef VIS_L16PU
 #undef VIS_L16N
 #undef VIS_L16
     vis::set_error("vis_fused_sched16: no instantiation for %d taps in this output mode", sc.kt);
