@@ -1,0 +1,57 @@
+"""-m gpu: randomised geometries through every resampling path (scheduled 8-slot / 16-slot kernels with their tap
+classes, vertical-warp tiers and row segments, general kernels, generic passes, reduce pre-pass) against the oracle.
+Seeded, so a failure names its geometry."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import qwen2vl as Q
+from vision_inspection_system_b200 import geometry as G
+from vision_inspection_system_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def random_shapes(seed, n, lo=(120, 160), hi=(2400, 4200)):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        h = int(rng.integers(lo[0], hi[0]))
+        w = int(rng.integers(lo[1], hi[1]))
+        if rng.random() < 0.5:
+            w = (w + 15) // 16 * 16                      # rows of whole 16-byte vectors take the fused kernels
+        out.append((h, w))
+    return out
+
+
+def test_preprocess_random_geometries(engine):
+    shapes = random_shapes(101, 14)
+    frames = [synth.noise_frame(500 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    for max_pixels in (G.DEFAULT_MAX_PIXELS, G.HUB_MAX_PIXELS):
+        pv, grid = engine.preprocess([torch.from_numpy(f).cuda() for f in frames], max_pixels=max_pixels)
+        want, wgrid = Q.preprocess(frames, max_pixels=max_pixels)
+        assert np.array_equal(grid.numpy(), wgrid), shapes
+        got = pv.cpu().numpy()
+        if not np.array_equal(got, want):
+            rows = np.cumsum([0] + [int(g[1] * g[2]) for g in wgrid])
+            bad = [shapes[i] for i in range(len(shapes)) if not np.array_equal(got[rows[i]:rows[i + 1]], want[rows[i]:rows[i + 1]])]
+            raise AssertionError(f"pixel_values differ for {bad} at max_pixels={max_pixels}")
+
+
+def test_same_geometry_batches_random(engine):
+    """Uniform batches (one scheduled launch, several row segments) for a few random geometries."""
+    for k, (h, w) in enumerate(random_shapes(102, 4, lo=(600, 800))):
+        w = (w + 15) // 16 * 16
+        frames = np.stack([synth.noise_frame(700 + 10 * k + i, h, w) for i in range(5)])
+        pv, grid = engine.preprocess(torch.from_numpy(frames).cuda())
+        want, wgrid = Q.preprocess(list(frames))
+        assert np.array_equal(grid.numpy(), wgrid) and np.array_equal(pv.cpu().numpy(), want), (h, w)
+
+
+@pytest.mark.parametrize("role,limit", [("inspector", 2048), ("auditor", 1024)])
+def test_agent_thumbnails_random_geometries(engine, role, limit):
+    shapes = random_shapes(103 + limit, 10, lo=(700, 1100), hi=(3200, 6400))
+    frames = [synth.noise_frame(900 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    outs = engine.agent_inputs([torch.from_numpy(f).cuda() for f in frames], role)
+    for f, o, s in zip(frames, outs, shapes):
+        assert np.array_equal(o.cpu().numpy(), Q.agent_thumbnail(f, limit)), (role, s)
