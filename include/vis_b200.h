@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 12
+#define VIS_B200_ABI_VERSION 13
 
 /* status codes */
 #define VIS_OK            0
@@ -281,6 +281,29 @@ int vis_overlay_plan_batch(int n_frames, const int32_t* hw, const VisBox* boxes,
                            VisLeaf* leaves, int64_t leaf_capacity, int32_t* leaf_begin,
                            VisOverlayTile* tiles, int64_t tile_capacity,
                            VisOverlayRef* refs, int64_t ref_capacity, int64_t* needed, int n_threads);
+
+/* Marker sprites.  The marker of a box — white disc, coloured ring, black label (utils/image_utils.py:290-313) — is made
+ * of opaque primitives only, so its pixels do not depend on the frame: it is rasterised ONCE per (radius, colour, label)
+ * ON THE DEVICE (vis_overlay_sprite_expand -> vis_overlay_tiles -> vis_overlay_draw_cn on a zeroed BGRA canvas: alpha 255
+ * where something was drawn) and every box that shows it whole gets one sprite leaf instead of its ~600 leaves.  Markers
+ * that touch the image border are still expanded in place.                                 */
+typedef struct VisSprite {
+    int32_t  radius;
+    uint8_t  b, g, r, pad;
+    char     label[12];            /* NUL-terminated, as VisBox.label                                               */
+    uint64_t pixels;               /* DEVICE address of the BGRA canvas, rows of 4 * w bytes                        */
+    int32_t  w, h, ox, oy;         /* canvas size and the position of the marker centre inside it                   */
+} VisSprite;
+/* leaves of ONE marker on its own canvas (one group header first, colours with alpha 255); *w / *h / *ox / *oy receive
+ * the canvas geometry.  Same return convention as vis_overlay_expand.                     [host] */
+int vis_overlay_sprite_expand(int radius, int b, int g, int r, const char* label, VisLeaf* leaves, int capacity,
+                              int* needed, int* w, int* h, int* ox, int* oy);
+/* vis_overlay_plan_batch with a table of rendered sprites (HOST array; may be empty)      [host] */
+int vis_overlay_plan_batch_sprites(int n_frames, const int32_t* hw, const VisBox* boxes, const int32_t* box_begin,
+                                   VisLeaf* leaves, int64_t leaf_capacity, int32_t* leaf_begin,
+                                   VisOverlayTile* tiles, int64_t tile_capacity,
+                                   VisOverlayRef* refs, int64_t ref_capacity, int64_t* needed, int n_threads,
+                                   const VisSprite* sprites, int n_sprites);
 
 /* frames / tiles / refs / leaves: DEVICE arrays (<= 65535 frames).  copy_frames != 0: every frame with dst != src
  * is first copied src -> dst (vectorised), then the listed tiles are drawn in place on dst; frames drawn in place

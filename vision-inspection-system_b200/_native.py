@@ -53,6 +53,10 @@ OVERLAY_TILE_DTYPE = np.dtype([("frame", np.int32), ("txy", np.int32), ("ref_beg
 OVERLAY_REF_DTYPE = np.dtype([("leaf_begin", np.int32), ("leaf_end", np.int32)], align=True)
 QUALITY_FRAME_DTYPE = np.dtype([("src", np.uint64), ("pitch", np.int64), ("h", np.int32), ("w", np.int32)], align=True)
 assert LEAF_DTYPE.itemsize == 48 and OVERLAY_FRAME_DTYPE.itemsize == 48
+SPRITE_DTYPE = np.dtype([("radius", np.int32), ("b", np.uint8), ("g", np.uint8), ("r", np.uint8), ("pad", np.uint8),
+                         ("label", "S12"), ("pixels", np.uint64), ("w", np.int32), ("h", np.int32), ("ox", np.int32),
+                         ("oy", np.int32)], align=True)
+assert SPRITE_DTYPE.itemsize == 48
 RESIZE_COPY, RESIZE_AREA2, RESIZE_BILINEAR = 0, 1, 2
 JPEG_BACKEND_DEFAULT, JPEG_BACKEND_HYBRID, JPEG_BACKEND_GPU_HYBRID, JPEG_BACKEND_HARDWARE = 0, 1, 2, 3
 JPEG_CSS_444, JPEG_CSS_422, JPEG_CSS_420, JPEG_CSS_GRAY = 0, 1, 2, 6
@@ -74,7 +78,7 @@ EXPORTS = [
     "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_preprocess_fused_sched",
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
-    "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn",
+    "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn", "vis_overlay_sprite_expand", "vis_overlay_plan_batch_sprites",
     "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8", "vis_alpha_premultiply_u8",
     "vis_jpeg_create", "vis_jpeg_destroy", "vis_jpeg_info", "vis_jpeg_decode", "vis_jpeg_decode_batch",
     "vis_jpeg_encode_bound", "vis_jpeg_encode",
@@ -100,7 +104,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 12:
+        if L.vis_abi_version() != 13:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -151,6 +155,9 @@ def _declare(L: C.CDLL) -> None:
     L.vis_nearest_table.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, i32p]
     L.vis_gather_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
     L.vis_alpha_premultiply_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.vis_overlay_sprite_expand.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, vp, C.c_int, ip, ip, ip, ip, ip]
+    L.vis_overlay_plan_batch_sprites.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int,
+                                                 vp, C.c_int]
     L.vis_jpeg_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.vis_jpeg_destroy.argtypes = [vp]
     L.vis_jpeg_info.argtypes = [vp, vp, C.c_int64, ip, ip, ip, ip]

@@ -127,6 +127,20 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
             }
             return true;
         }
+        case LEAF_SPRITE: {                       // opaque marker rasterised once: copy the pixels it covers
+            const int sy = y - w[5];
+            if (sy < 0 || sy >= w[7]) return false;
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(((uint64_t)(uint32_t)w[3] << 32) | (uint32_t)w[2]) +
+                                 (size_t)sy * w[6];
+#pragma unroll
+            for (int j = 0; j < kPx; ++j) {
+                const int sx = x + j - w[4];
+                if (sx < 0 || sx >= w[6]) continue;
+                const uint32_t v = __ldg(sp + sx);
+                if (v >> 24) set_px<CN>(c[j], (int)v);
+            }
+            return true;
+        }
         default:
             return false;
     }

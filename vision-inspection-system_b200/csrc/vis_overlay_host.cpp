@@ -212,6 +212,20 @@ class Emitter {
     int count() const { return n_; }
     bool ok() const { return glyph_ok_; }
 
+    // one leaf that copies the covered pixels of a marker sprite placed with its anchor at (cx, cy)
+    void sprite(const VisSprite& sp, int cx, int cy) {
+        VisLeaf l;
+        std::memset(&l, 0, sizeof l);
+        l.w[0] = LEAF_SPRITE;
+        l.w[2] = (int32_t)(uint32_t)(sp.pixels & 0xffffffffu);
+        l.w[3] = (int32_t)(uint32_t)(sp.pixels >> 32);
+        l.w[4] = cx - sp.ox;
+        l.w[5] = cy - sp.oy;
+        l.w[6] = sp.w;
+        l.w[7] = sp.h;
+        push_boxed(l, l.w[4], l.w[5], (int64_t)l.w[4] + sp.w - 1, (int64_t)l.w[5] + sp.h - 1);
+    }
+
     // appends a copy of every leaf of `tpl` moved by (dx, dy) whole pixels: all leaf parameters are affine in the
     // pixel coordinates (16.16 walkers, pixel rows / columns, packed boxes), so this equals expanding the same calls
     // at the moved position as long as nothing there is clipped by the image border (the caller checks)
@@ -705,7 +719,7 @@ struct TemplateCache {
     }
 };
 
-struct MarkerSpec { int radius; uint8_t b, g, r; char label[13]; };
+struct MarkerSpec { int radius; uint8_t b, g, r; char label[13]; uint8_t alpha; };
 struct DashSpec { int dx, dy, thickness, line_type; uint8_t b, g, r; };
 
 Template build_marker(const void* arg) {
@@ -727,15 +741,15 @@ Template build_marker(const void* arg) {
     for (;;) {
         Emitter em(2 * cyc + 1, 2 * cxc + 1, buf.data(), (int)buf.size());
         em.begin_group();
-        em.set_color(255, 255, 255);
+        em.set_color(255, 255, 255, m.alpha);
         em.circle_filled(cxc, cyc, m.radius);                         // utils/image_utils.py:299
-        em.set_color(m.b, m.g, m.r);
+        em.set_color(m.b, m.g, m.r, m.alpha);
         em.circle_outline(cxc, cyc, m.radius, 3);                     // :302
         const double font_scale = m.radius / 20.0 * 0.7;              // :305-313
         const int text_thickness = std::max(2, (int)(font_scale * 2));
         int tw = 0, th = 0;
         if (!em.text_size(m.label, font_scale, text_thickness, &tw, &th)) { t.ok = false; return t; }
-        em.set_color(0, 0, 0);
+        em.set_color(0, 0, 0, m.alpha);
         em.put_text(m.label, (int)(cxc - tw / 2.0), (int)(cyc + th / 2.0), font_scale, text_thickness);
         if (em.count() <= (int)buf.size()) { buf.resize((size_t)em.count()); break; }
         buf.resize((size_t)em.count());
@@ -764,6 +778,19 @@ Template build_dash(const void* arg) {
 }
 
 thread_local TemplateCache g_templates;
+
+// sprites the current expansion may reference (set by vis_overlay_plan_batch_sprites around its per-frame work)
+thread_local const VisSprite* g_sprites = nullptr;
+thread_local int g_n_sprites = 0;
+
+const VisSprite* find_sprite(int radius, const VisBox& b, const char* label) {
+    for (int i = 0; i < g_n_sprites; ++i) {
+        const VisSprite& s = g_sprites[i];
+        if (s.radius == radius && s.b == b.b && s.g == b.g && s.r == b.r && s.pixels && std::strncmp(s.label, label, 12) == 0)
+            return &s;
+    }
+    return nullptr;
+}
 
 }  // namespace
 
@@ -824,7 +851,7 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
         char label[13];
         std::memcpy(label, b.label, 12);
         label[12] = 0;
-        MarkerSpec m{radius, b.b, b.g, b.r, {0}};
+        MarkerSpec m{radius, b.b, b.g, b.r, {0}, 0};
         std::memcpy(m.label, label, 13);
         char key[64];
         std::snprintf(key, sizeof key, "m%d,%d,%d,%d,", radius, b.b, b.g, b.r);
@@ -834,7 +861,11 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
             return VIS_E_UNSUPPORTED;
         }
         if (cx - t.ex >= 0 && cy - t.ey >= 0 && cx + t.ex < img_w && cy + t.ey < img_h) {
-            em.instantiate(t.leaves, cx - t.ox, cy - t.oy);
+            const VisSprite* sp = find_sprite(radius, b, label);
+            if (sp && sp->w == 2 * t.ox + 1 && sp->h == 2 * t.oy + 1 && sp->ox == t.ox && sp->oy == t.oy)
+                em.sprite(*sp, cx, cy);                  // rasterised once on the device: one leaf
+            else
+                em.instantiate(t.leaves, cx - t.ox, cy - t.oy);
         } else {
             em.set_color(255, 255, 255);
             em.circle_filled(cx, cy, radius);
@@ -934,6 +965,36 @@ extern "C" int vis_draw_expand(int img_h, int img_w, const VisDrawCmd* cmds, int
     return em.count();
 }
 
+// Leaves of one marker on its own canvas, colours with alpha 255: drawn once on a zeroed BGRA canvas (on the device) they
+// give the sprite every whole marker of that (radius, colour, label) is copied from.
+extern "C" int vis_overlay_sprite_expand(int radius, int b, int g, int r, const char* label, VisLeaf* leaves, int capacity,
+                                         int* needed, int* w, int* h, int* ox, int* oy) {
+    if (radius < 1 || radius > 4096 || !label || capacity < 0 || (capacity && !leaves) || !w || !h || !ox || !oy ||
+        (b | g | r) < 0 || (b | g | r) > 255) {
+        vis::set_error("vis_overlay_sprite_expand: bad arguments (radius %d)", radius);
+        return VIS_E_INVALID;
+    }
+    MarkerSpec m{radius, (uint8_t)b, (uint8_t)g, (uint8_t)r, {0}, 255};
+    std::strncpy(m.label, label, 12);
+    const Template t = build_marker(&m);
+    if (!t.ok) {
+        vis::set_error("vis_overlay_sprite_expand: label '%s' has a character outside printable ASCII", m.label);
+        return VIS_E_UNSUPPORTED;
+    }
+    *w = 2 * t.ox + 1; *h = 2 * t.oy + 1; *ox = t.ox; *oy = t.oy;
+    Emitter em(*h, *w, leaves, capacity);
+    em.reserve_headers(1);
+    em.begin_group();
+    em.instantiate(t.leaves, 0, 0);
+    em.end_group(0);
+    if (needed) *needed = em.count();
+    if (em.count() > capacity) {
+        vis::set_error("vis_overlay_sprite_expand: %d leaves needed, capacity %d", em.count(), capacity);
+        return VIS_E_CAPACITY;
+    }
+    return em.count();
+}
+
 // Bins the frame's sub-groups (runs of <= 32 consecutive leaves with a common box) into the 64x16-pixel CTA tiles of
 // vis_overlay.cu.  tiles_out: one record per touched tile, row-major: {tx | ty << 16, first ref, one past last ref};
 // refs_out: per tile, IN LEAF ORDER, {first leaf, one past last leaf} of every sub-group whose box touches the tile.
@@ -996,6 +1057,19 @@ extern "C" int vis_overlay_plan_batch(int n_frames, const int32_t* hw, const Vis
                                       VisLeaf* leaves, int64_t leaf_capacity, int32_t* leaf_begin,
                                       VisOverlayTile* tiles, int64_t tile_capacity,
                                       VisOverlayRef* refs, int64_t ref_capacity, int64_t* needed, int n_threads) {
+    return vis_overlay_plan_batch_sprites(n_frames, hw, boxes, box_begin, leaves, leaf_capacity, leaf_begin, tiles,
+                                          tile_capacity, refs, ref_capacity, needed, n_threads, nullptr, 0);
+}
+
+extern "C" int vis_overlay_plan_batch_sprites(int n_frames, const int32_t* hw, const VisBox* boxes, const int32_t* box_begin,
+                                              VisLeaf* leaves, int64_t leaf_capacity, int32_t* leaf_begin,
+                                              VisOverlayTile* tiles, int64_t tile_capacity,
+                                              VisOverlayRef* refs, int64_t ref_capacity, int64_t* needed, int n_threads,
+                                              const VisSprite* sprites, int n_sprites) {
+    if (n_sprites < 0 || (n_sprites && !sprites)) {
+        vis::set_error("vis_overlay_plan_batch: bad sprite table");
+        return VIS_E_INVALID;
+    }
     if (n_frames <= 0 || !hw || !box_begin || !leaf_begin || !needed || leaf_capacity < 0 || tile_capacity < 0 ||
         ref_capacity < 0 || (leaf_capacity && !leaves) || (tile_capacity && !tiles) || (ref_capacity && !refs)) {
         vis::set_error("vis_overlay_plan_batch: bad arguments");
@@ -1005,6 +1079,9 @@ extern "C" int vis_overlay_plan_batch(int n_frames, const int32_t* hw, const Vis
     std::vector<Frame> out((size_t)n_frames);
     std::atomic<int> next(0);
     auto work = [&]() {
+        g_sprites = sprites;                      // thread-local: the expansion of this thread may emit sprite leaves
+        g_n_sprites = n_sprites;
+        struct Reset { ~Reset() { g_sprites = nullptr; g_n_sprites = 0; } } reset;
         for (int i = next.fetch_add(1); i < n_frames; i = next.fetch_add(1)) {
             Frame& fr = out[(size_t)i];
             const int h = hw[2 * i], w = hw[2 * i + 1], nb = box_begin[i + 1] - box_begin[i];

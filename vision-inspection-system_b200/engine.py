@@ -639,6 +639,45 @@ class Engine:
         return out, grid
 
     # ------------------------------------------------------------------ defect overlay
+    def _marker_sprite(self, radius: int, b: int, g: int, r: int, label: bytes):
+        """The marker of (radius, colour, label) rasterised once ON THE DEVICE: its leaves (alpha 255) drawn by the overlay
+        kernel on a zeroed BGRA canvas.  Returns (canvas tensor, w, h, ox, oy); cached per engine."""
+        cache = self.__dict__.setdefault("_sprites", {})
+        key = (radius, b, g, r, label)
+        hit = cache.get(key)
+        if hit is not None:
+            return hit
+        from . import overlay as O
+        w, h, ox, oy, needed = (C.c_int(0) for _ in range(5))
+        cap = 2048
+        while True:
+            leaves = np.empty(cap, N.LEAF_DTYPE)
+            rc = self.L.vis_overlay_sprite_expand(radius, b, g, r, label, leaves.ctypes.data_as(C.c_void_p), cap, C.byref(needed),
+                                                  C.byref(w), C.byref(h), C.byref(ox), C.byref(oy))
+            if rc == N.VIS_E_CAPACITY:
+                cap = needed.value
+                continue
+            N.check(rc, "vis_overlay_sprite_expand")
+            leaves = leaves[:rc].copy()
+            break
+        canvas = torch.zeros((h.value, w.value, 4), dtype=torch.uint8, device=self.device)
+        tiles, refs = O.touched_tiles(leaves, 1, w.value, h.value)
+        tl = np.zeros(len(tiles), N.OVERLAY_TILE_DTYPE)
+        tl["txy"], tl["ref_begin"], tl["ref_end"] = tiles[:, 0], tiles[:, 1], tiles[:, 2]
+        desc = np.zeros(1, N.OVERLAY_FRAME_DTYPE)
+        desc["src"] = desc["dst"] = canvas.data_ptr()
+        desc["src_pitch"] = desc["dst_pitch"] = canvas.stride(0)
+        desc["h"], desc["w"], desc["group_begin"], desc["group_end"] = h.value, w.value, 0, 1
+        up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
+        d = [up(desc), up(tl), up(np.ascontiguousarray(refs)), up(leaves)]
+        N.check(self.L.vis_overlay_draw_cn(d[0].data_ptr(), 1, 4, 0, d[1].data_ptr(), len(tl), d[2].data_ptr(), d[3].data_ptr(),
+                                           _stream_ptr()), "vis_overlay_draw_cn")
+        torch.cuda.current_stream(self.device).synchronize()          # the upload tensors may go; the sprite stays
+        if len(cache) >= 4096:
+            cache.clear()
+        hit = cache[key] = (canvas, w.value, h.value, ox.value, oy.value)
+        return hit
+
     def plan_overlay(self, shapes, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium"):
         """Host half of the overlay for a batch: box validation (reference rules) + expansion into leaves.
 
@@ -654,6 +693,19 @@ class Engine:
             box_begin.append(box_begin[-1] + len(px))
             hw[i] = (h, w)
         boxes_arr = np.concatenate(px_all) if box_begin[-1] else np.zeros(1, N.BOX_DTYPE)
+        # markers are opaque: each distinct (radius, colour, label) of the batch is rasterised once on the device and
+        # referenced by one sprite leaf per box (utils/image_utils.py:292-293 for the radius rule)
+        keys = set()
+        for (h, w), px in zip(shapes, px_all):
+            if len(px):
+                radius = max(25, min(int(max(w, h) * 0.04), 60))
+                keys.update((radius, int(p["b"]), int(p["g"]), int(p["r"]), bytes(p["label"])) for p in px)
+        sprites = np.zeros(max(1, len(keys)), N.SPRITE_DTYPE)
+        keep_sprites = []
+        for i, key in enumerate(sorted(keys)):
+            canvas, sw, sh, sox, soy = self._marker_sprite(*key)
+            keep_sprites.append(canvas)
+            sprites[i] = (key[0], key[1], key[2], key[3], 0, key[4], canvas.data_ptr(), sw, sh, sox, soy)
         box_begin = np.asarray(box_begin, np.int32)
         n = len(shapes)
         leaf_begin = np.zeros(n + 1, np.int32)
@@ -667,10 +719,11 @@ class Engine:
                       for c, dt in zip(cap, (N.LEAF_DTYPE, N.OVERLAY_TILE_DTYPE, N.OVERLAY_REF_DTYPE))]
             leaves, tiles, refs = (t.numpy().view(dt) for t, dt in
                                    zip(pinned, (N.LEAF_DTYPE, N.OVERLAY_TILE_DTYPE, N.OVERLAY_REF_DTYPE)))
-            rc = self.L.vis_overlay_plan_batch(n, hw.ctypes.data_as(C.c_void_p), boxes_arr.ctypes.data_as(C.c_void_p),
-                                               box_begin.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p), cap[0],
-                                               leaf_begin.ctypes.data_as(C.c_void_p), tiles.ctypes.data_as(C.c_void_p), cap[1],
-                                               refs.ctypes.data_as(C.c_void_p), cap[2], needed.ctypes.data_as(C.c_void_p), 0)
+            rc = self.L.vis_overlay_plan_batch_sprites(
+                n, hw.ctypes.data_as(C.c_void_p), boxes_arr.ctypes.data_as(C.c_void_p), box_begin.ctypes.data_as(C.c_void_p),
+                leaves.ctypes.data_as(C.c_void_p), cap[0], leaf_begin.ctypes.data_as(C.c_void_p),
+                tiles.ctypes.data_as(C.c_void_p), cap[1], refs.ctypes.data_as(C.c_void_p), cap[2],
+                needed.ctypes.data_as(C.c_void_p), 0, sprites.ctypes.data_as(C.c_void_p), len(keys))
             if rc == N.VIS_E_CAPACITY:
                 cap = [max(1, int(v)) for v in needed]
                 continue
@@ -680,7 +733,7 @@ class Engine:
         ranges = [(int(leaf_begin[i]), int(leaf_begin[i]) + int(box_begin[i + 1] - box_begin[i])) for i in range(n)]
         up = lambda t, k, dt: t[:max(k, 1) * dt.itemsize].to(self.device, non_blocking=True)  # noqa: E731
         return (up(pinned[0], n_leaves, N.LEAF_DTYPE), ranges, int(box_begin[-1]), up(pinned[1], n_tiles, N.OVERLAY_TILE_DTYPE),
-                n_tiles, up(pinned[2], n_refs, N.OVERLAY_REF_DTYPE))
+                n_tiles, up(pinned[2], n_refs, N.OVERLAY_REF_DTYPE), keep_sprites)     # the plan keeps its sprites alive
 
     def annotate(self, frames, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium",
                  inplace: bool = False, plan=None):
@@ -700,7 +753,7 @@ class Engine:
         shapes = [(int(f.shape[0]), int(f.shape[1])) for f in flist]
         if plan is None:
             plan = self.plan_overlay(shapes, boxes_per_frame, confidence_threshold, criticality)
-        d_leaves, ranges, _, d_tiles, n_tiles, d_refs = plan
+        d_leaves, ranges, _, d_tiles, n_tiles, d_refs = plan[:6]
         if inplace:
             outs = flist
             result = frames
