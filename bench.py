@@ -180,6 +180,26 @@ def emit(line: dict) -> None:
 _REAL_STDOUT = 1
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """One process per GPU on a two-socket box: run this rank (and first-touch its pinned staging buffers) on the CPUs
+    NVML names as local to its GPU, so that every rank's host->device copies leave through its own socket instead of
+    all of them crossing to the socket the launcher happened to start on.  Only the `e2e` leg moves host data; the
+    device-resident `value` is unaffected.  Returns the CPU count bound to, or None when NVML cannot say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     global _REAL_STDOUT
     # keep stdout clean for the driver: everything any library prints to fd 1 goes to stderr instead
@@ -260,6 +280,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -364,6 +385,7 @@ def main():
         "vs_baseline": None, "dtype": "u8->int32 fixed point->f32", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": args.batch * H * W * 3,
                 "d2h_bytes_per_step": args.batch * 1176 * 4,
+                "cpus_bound_per_rank": numa,
                 "note": "pinned host frames -> device pixel_values (consumer is on the GPU); first patch row of "
                         "every frame read back"},
         "e2e_full_readback": {"value": full_value, "unit": "images/s",
