@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 13
+#define VIS_B200_ABI_VERSION 14
 
 /* status codes */
 #define VIS_OK            0
@@ -298,7 +298,16 @@ typedef struct VisSprite {
  * the canvas geometry.  Same return convention as vis_overlay_expand.                     [host] */
 int vis_overlay_sprite_expand(int radius, int b, int g, int r, const char* label, VisLeaf* leaves, int capacity,
                               int* needed, int* w, int* h, int* ox, int* oy);
-/* vis_overlay_plan_batch with a table of rendered sprites (HOST array; may be empty)      [host] */
+/* Dash stamps.  A dash of a low-confidence box (cv2.line, thickness 2, LINE_AA, utils/image_utils.py:264-283) blends with
+ * the frame, so it cannot be a sprite; but WHAT happens to each pixel — an optional opaque write followed by a chain of
+ * blends with fixed 8-bit alphas — does not depend on the frame or the colour.  That chain is recorded once per dash
+ * geometry ON THE DEVICE (vis_overlay_stamp_expand -> vis_overlay_tiles -> vis_overlay_draw_cn with channels = 8 on a
+ * zeroed canvas of 8 bytes per pixel: byte 0 = blend count | 0x80 opaque first | 0x40 overflow, bytes 1..7 = alphas) and
+ * replayed by ONE leaf per interior dash instead of its 19.  A table entry with radius == -1 is a stamp: label holds
+ * "dx,dy", pixels the record canvas.  Stamps whose record overflowed must not be listed.
+ * vis_overlay_stamp_expand: leaves of the dash (0,0)-(dx,dy) on its own canvas, one group header first.   [host] */
+int vis_overlay_stamp_expand(int dx, int dy, VisLeaf* leaves, int capacity, int* needed, int* w, int* h, int* ox, int* oy);
+/* vis_overlay_plan_batch with a table of rendered sprites / stamps (HOST array; may be empty)      [host] */
 int vis_overlay_plan_batch_sprites(int n_frames, const int32_t* hw, const VisBox* boxes, const int32_t* box_begin,
                                    VisLeaf* leaves, int64_t leaf_capacity, int32_t* leaf_begin,
                                    VisOverlayTile* tiles, int64_t tile_capacity,
@@ -405,7 +414,8 @@ int vis_text_size(const char* text, double font_scale, int thickness, int* width
 /* like vis_overlay_expand, for a draw list: n_cmds group headers followed by the ordered leaves.   [host] */
 int vis_draw_expand(int img_h, int img_w, const VisDrawCmd* cmds, int n_cmds,
                     VisLeaf* leaves, int capacity, int* needed);
-/* vis_overlay_draw for canvases with `channels` = 3 or 4 interleaved bytes per pixel.   [device] */
+/* vis_overlay_draw for canvases with `channels` = 3 or 4 interleaved bytes per pixel; channels = 8 records blend chains
+ * (dash stamps, see VisSprite).                                                       [device] */
 int vis_overlay_draw_cn(const VisOverlayFrame* frames, int n_frames, int channels, int copy_frames,
                         const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
                         const VisLeaf* leaves, void* stream);

@@ -28,13 +28,34 @@ __device__ __forceinline__ bool touches(const Tile& t, int wx, int wy) {
     return bx0 <= t.x1 && bx1 >= t.x0 && by0 <= t.y1 && by1 >= t.y0;
 }
 
+// CN == 8 is the RECORD mode used to build dash stamps: a "pixel" is 8 bytes describing what the leaves did to it instead
+// of a colour — byte 0: number of blends recorded (bits 0..5), 0x40 = more than seven (stamp unusable), 0x80 = an opaque
+// write came first; bytes 1..7: the 8-bit alphas of the blends that followed, in order.  Replaying that chain on a frame
+// pixel (LEAF_STAMP) gives exactly what applying the leaves one by one gives.
+constexpr int kRecord = 8;
 template <int CN>
 __device__ __forceinline__ void set_px(int* c, int col) {
+    if (CN == kRecord) {
+        c[0] = 0x80;
+#pragma unroll
+        for (int k = 1; k < kRecord; ++k) c[k] = 0;
+        return;
+    }
     c[0] = col & 0xff; c[1] = (col >> 8) & 0xff; c[2] = (col >> 16) & 0xff;
     if (CN == 4) c[3] = (unsigned)col >> 24;
 }
 template <int CN>
 __device__ __forceinline__ void blend_px(int* c, int col, int a) {
+    if (CN == kRecord) {
+        if (a == 0) return;                                   // ((cc - v) * 0 + 127) >> 8 == 0: no effect on any pixel
+        const int n = c[0] & 0x3f;
+        if (n >= kRecord - 1) { c[0] |= 0x40; return; }
+#pragma unroll
+        for (int k = 1; k < kRecord; ++k)
+            if (k == n + 1) c[k] = a;
+        c[0] += 1;
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < CN; ++k) {
         const int cc = (col >> (8 * k)) & 0xff;
@@ -127,7 +148,31 @@ __device__ __forceinline__ bool apply_leaf(const int* w, const int* filt, int x,
             }
             return true;
         }
+        case LEAF_STAMP: {                        // replay the recorded blend chain of a dash with this leaf's colour
+            if (CN == kRecord) return false;
+            const int sy = y - w[5];
+            if (sy < 0 || sy >= w[7]) return false;
+            const uint2* sp = reinterpret_cast<const uint2*>(((uint64_t)(uint32_t)w[3] << 32) | (uint32_t)w[2]) +
+                              (size_t)sy * w[6];
+#pragma unroll
+            for (int j = 0; j < kPx; ++j) {
+                const int sx = x + j - w[4];
+                if (sx < 0 || sx >= w[6]) continue;
+                const uint2 rec = __ldg(sp + sx);
+                if (!(rec.x & 0xff)) continue;
+                if (rec.x & 0x80) set_px<CN>(c[j], col);
+                const int n = rec.x & 0x3f;
+#pragma unroll
+                for (int i = 0; i < kRecord - 1; ++i) {
+                    if (i >= n) break;
+                    const unsigned word = i < 3 ? rec.x : rec.y;
+                    blend_px<CN>(c[j], col, (int)((word >> (8 * ((i + 1) & 3))) & 0xff));
+                }
+            }
+            return true;
+        }
         case LEAF_SPRITE: {                       // opaque marker rasterised once: copy the pixels it covers
+            if (CN == kRecord) return false;
             const int sy = y - w[5];
             if (sy < 0 || sy >= w[7]) return false;
             const uint32_t* sp = reinterpret_cast<const uint32_t*>(((uint64_t)(uint32_t)w[3] << 32) | (uint32_t)w[2]) +
@@ -238,7 +283,7 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
 #pragma unroll
                         for (int k = 0; k < CN; ++k) c[j][k] = (a >> (8 * k)) & 0xff;
                     }
-                } else if (nv == kPx && vec) {
+                } else if (CN == 3 && nv == kPx && vec) {
                     const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
                     const uint32_t a = q[0], b = q[1], d = q[2];
                     c[0][0] = a & 0xff; c[0][1] = (a >> 8) & 0xff; c[0][2] = (a >> 16) & 0xff;
@@ -271,7 +316,7 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
 #pragma unroll
         for (int j = 0; j < kPx; ++j)
             q[j] = (uint32_t)c[j][0] | ((uint32_t)c[j][1] << 8) | ((uint32_t)c[j][2] << 16) | ((uint32_t)c[j][CN - 1] << 24);
-    } else if (nv == kPx && vec) {
+    } else if (CN == 3 && nv == kPx && vec) {
         uint32_t* q = reinterpret_cast<uint32_t*>(px);
         q[0] = (uint32_t)c[0][0] | ((uint32_t)c[0][1] << 8) | ((uint32_t)c[0][2] << 16) | ((uint32_t)c[1][0] << 24);
         q[1] = (uint32_t)c[1][1] | ((uint32_t)c[1][2] << 8) | ((uint32_t)c[2][0] << 16) | ((uint32_t)c[2][1] << 24);
@@ -289,7 +334,7 @@ extern "C" int vis_overlay_draw_cn(const VisOverlayFrame* frames, int n_frames, 
                                    const VisOverlayTile* tiles, int n_tiles, const VisOverlayRef* refs,
                                    const VisLeaf* leaves, void* stream) {
     if (!frames || n_frames <= 0 || n_frames > 65535 || n_tiles < 0 || (n_tiles && (!tiles || !refs || !leaves)) ||
-        (channels != 3 && channels != 4)) {
+        (channels != 3 && channels != 4 && channels != kRecord)) {
         vis::set_error("vis_overlay_draw: bad arguments (frames=%d tiles=%d channels=%d)", n_frames, n_tiles, channels);
         return VIS_E_INVALID;
     }
@@ -300,8 +345,9 @@ extern "C" int vis_overlay_draw_cn(const VisOverlayFrame* frames, int n_frames, 
         if (rc != VIS_OK) return rc;
     }
     if (n_tiles > 0) {
-        if (channels == 3) k_overlay_tiles<3><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
-        else               k_overlay_tiles<4><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
+        if (channels == 3)      k_overlay_tiles<3><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
+        else if (channels == 4) k_overlay_tiles<4><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
+        else                    k_overlay_tiles<kRecord><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);   // stamp recording
         return vis::check_launch("vis_overlay_draw");
     }
     return VIS_OK;

@@ -226,6 +226,20 @@ class Emitter {
         push_boxed(l, l.w[4], l.w[5], (int64_t)l.w[4] + sp.w - 1, (int64_t)l.w[5] + sp.h - 1);
     }
 
+    // one leaf that replays the recorded blend chains of a dash stamp anchored at (x, y), with the current colour
+    void stamp(const VisSprite& sp, int x, int y, int bx0, int by0, int bx1, int by1) {   // b*: touched box on the canvas
+        VisLeaf l;
+        std::memset(&l, 0, sizeof l);
+        l.w[0] = LEAF_STAMP;
+        l.w[2] = (int32_t)(uint32_t)(sp.pixels & 0xffffffffu);
+        l.w[3] = (int32_t)(uint32_t)(sp.pixels >> 32);
+        l.w[4] = x - sp.ox;
+        l.w[5] = y - sp.oy;
+        l.w[6] = sp.w;
+        l.w[7] = sp.h;
+        push_boxed(l, (int64_t)l.w[4] + bx0, (int64_t)l.w[5] + by0, (int64_t)l.w[4] + bx1, (int64_t)l.w[5] + by1);
+    }
+
     // appends a copy of every leaf of `tpl` moved by (dx, dy) whole pixels: all leaf parameters are affine in the
     // pixel coordinates (16.16 walkers, pixel rows / columns, packed boxes), so this equals expanding the same calls
     // at the moved position as long as nothing there is clipped by the image border (the caller checks)
@@ -706,7 +720,15 @@ struct Template {
     std::vector<VisLeaf> leaves;
     int ox = 0, oy = 0;              // canvas position of the anchor (marker centre / dash start)
     int ex = 0, ey = 0;              // marker: half extents (pixels) the instance must have free around its centre
+    int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1;   // union of the leaf boxes on the canvas
     bool ok = true;                  // false: a label glyph outside printable ASCII
+    void bound() {
+        bx0 = by0 = INT_MAX; bx1 = by1 = INT_MIN;
+        for (const VisLeaf& l : leaves) {
+            bx0 = std::min(bx0, l.w[10] & 0xffff); bx1 = std::max(bx1, (int)((uint32_t)l.w[10] >> 16));
+            by0 = std::min(by0, l.w[11] & 0xffff); by1 = std::max(by1, (int)((uint32_t)l.w[11] >> 16));
+        }
+    }
 };
 
 struct TemplateCache {
@@ -774,6 +796,7 @@ Template build_dash(const void* arg) {
         buf.resize((size_t)em.count());
     }
     t.leaves = std::move(buf);
+    t.bound();
     return t;
 }
 
@@ -782,6 +805,16 @@ thread_local TemplateCache g_templates;
 // sprites the current expansion may reference (set by vis_overlay_plan_batch_sprites around its per-frame work)
 thread_local const VisSprite* g_sprites = nullptr;
 thread_local int g_n_sprites = 0;
+
+const VisSprite* find_stamp(int dx, int dy) {
+    char key[12];
+    std::snprintf(key, sizeof key, "%d,%d", dx, dy);
+    for (int i = 0; i < g_n_sprites; ++i) {
+        const VisSprite& s = g_sprites[i];
+        if (s.radius == -1 && s.pixels && std::strncmp(s.label, key, 12) == 0) return &s;
+    }
+    return nullptr;
+}
 
 const VisSprite* find_sprite(int radius, const VisBox& b, const char* label) {
     for (int i = 0; i < g_n_sprites; ++i) {
@@ -817,7 +850,11 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
                 char key[64];
                 std::snprintf(key, sizeof key, "d%d,%d,%d,%d,%d", d.dx, d.dy, b.b, b.g, b.r);
                 const Template& t = g_templates.get(key, build_dash, &d);
-                em.instantiate(t.leaves, x1 - t.ox, y1 - t.oy);
+                const VisSprite* sp = find_stamp(d.dx, d.dy);
+                if (sp && sp->ox == t.ox && sp->oy == t.oy && sp->w == d.dx + 2 * t.ox + 1 && sp->h == d.dy + 2 * t.oy + 1)
+                    em.stamp(*sp, x1, y1, t.bx0, t.by0, t.bx1, t.by1);   // blend chains recorded once on the device: one leaf
+                else
+                    em.instantiate(t.leaves, x1 - t.ox, y1 - t.oy);
             } else {
                 em.line(x1, y1, x2, y2, 2, 16);
             }
@@ -990,6 +1027,31 @@ extern "C" int vis_overlay_sprite_expand(int radius, int b, int g, int r, const 
     if (needed) *needed = em.count();
     if (em.count() > capacity) {
         vis::set_error("vis_overlay_sprite_expand: %d leaves needed, capacity %d", em.count(), capacity);
+        return VIS_E_CAPACITY;
+    }
+    return em.count();
+}
+
+// Leaves of one dash (0,0)-(dx,dy), thickness 2, LINE_AA, on its own canvas: drawn in record mode (channels = 8) they give
+// the per-pixel blend chains a stamp leaf replays.
+extern "C" int vis_overlay_stamp_expand(int dx, int dy, VisLeaf* leaves, int capacity, int* needed, int* w, int* h,
+                                        int* ox, int* oy) {
+    if (dx < 0 || dy < 0 || dx > 64 || dy > 64 || (dx == 0) == (dy == 0) || capacity < 0 || (capacity && !leaves) || !w || !h ||
+        !ox || !oy) {
+        vis::set_error("vis_overlay_stamp_expand: bad arguments (dash %d,%d)", dx, dy);
+        return VIS_E_INVALID;
+    }
+    DashSpec d{dx, dy, 2, 16, 0, 0, 0};
+    const Template t = build_dash(&d);
+    *w = dx + 2 * t.ox + 1; *h = dy + 2 * t.oy + 1; *ox = t.ox; *oy = t.oy;
+    Emitter em(*h, *w, leaves, capacity);
+    em.reserve_headers(1);
+    em.begin_group();
+    em.instantiate(t.leaves, 0, 0);
+    em.end_group(0);
+    if (needed) *needed = em.count();
+    if (em.count() > capacity) {
+        vis::set_error("vis_overlay_stamp_expand: %d leaves needed, capacity %d", em.count(), capacity);
         return VIS_E_CAPACITY;
     }
     return em.count();

@@ -11,6 +11,7 @@ enum : int {
     LEAF_LINEAA = 3,   // w[2] major start px, w[3] ecount, w[4] minor start (16.16), w[5] step, w[6..8] nine 10-bit end-point factors
     LEAF_TRAP = 4,     // w[2] ya, w[3] yb, w[4] x of walker 0 at ya, w[5] its step, w[6] x of walker 1 at ya, w[7] its step
     LEAF_SPANS = 5,    // w[2] cx, w[3] first row, w[4] rows (<= 16), w[5..8] half-widths, one byte per row (0xff = none)
+    LEAF_STAMP = 7,    // w[1] colour, w[2],w[3] device pointer to the blend-chain records (8 bytes per pixel) of a w[6] x w[7] stamp at (w[4], w[5])
     LEAF_SPRITE = 6,   // w[2],w[3] device pointer (lo, hi) to a BGRA sprite of w[6] x w[7] pixels placed at (w[4], w[5]): pixels with alpha are copied
     LEAF_KIND_MASK = 0xff,
     LEAF_SUB_LEAVES = 32,       // leaves per sub-group header

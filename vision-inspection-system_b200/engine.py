@@ -642,25 +642,33 @@ class Engine:
     def _marker_sprite(self, radius: int, b: int, g: int, r: int, label: bytes):
         """The marker of (radius, colour, label) rasterised once ON THE DEVICE: its leaves (alpha 255) drawn by the overlay
         kernel on a zeroed BGRA canvas.  Returns (canvas tensor, w, h, ox, oy); cached per engine."""
+        return self._render_template(("marker", radius, b, g, r, label), 4,
+                                     lambda *a: self.L.vis_overlay_sprite_expand(radius, b, g, r, label, *a),
+                                     "vis_overlay_sprite_expand")
+
+    def _dash_stamp(self, dx: int, dy: int):
+        """The blend chains of the dash (0,0)-(dx,dy) recorded once ON THE DEVICE (record mode of the overlay kernel: 8
+        bytes per pixel).  Returns (canvas, w, h, ox, oy), or None when a chain overflowed its seven slots."""
+        return self._render_template(("dash", dx, dy), 8, lambda *a: self.L.vis_overlay_stamp_expand(dx, dy, *a),
+                                     "vis_overlay_stamp_expand")
+
+    def _render_template(self, key, channels: int, expand, where: str):
         cache = self.__dict__.setdefault("_sprites", {})
-        key = (radius, b, g, r, label)
-        hit = cache.get(key)
-        if hit is not None:
-            return hit
+        if key in cache:
+            return cache[key]
         from . import overlay as O
         w, h, ox, oy, needed = (C.c_int(0) for _ in range(5))
         cap = 2048
         while True:
             leaves = np.empty(cap, N.LEAF_DTYPE)
-            rc = self.L.vis_overlay_sprite_expand(radius, b, g, r, label, leaves.ctypes.data_as(C.c_void_p), cap, C.byref(needed),
-                                                  C.byref(w), C.byref(h), C.byref(ox), C.byref(oy))
+            rc = expand(leaves.ctypes.data_as(C.c_void_p), cap, C.byref(needed), C.byref(w), C.byref(h), C.byref(ox), C.byref(oy))
             if rc == N.VIS_E_CAPACITY:
                 cap = needed.value
                 continue
-            N.check(rc, "vis_overlay_sprite_expand")
+            N.check(rc, where)
             leaves = leaves[:rc].copy()
             break
-        canvas = torch.zeros((h.value, w.value, 4), dtype=torch.uint8, device=self.device)
+        canvas = torch.zeros((h.value, w.value, channels), dtype=torch.uint8, device=self.device)
         tiles, refs = O.touched_tiles(leaves, 1, w.value, h.value)
         tl = np.zeros(len(tiles), N.OVERLAY_TILE_DTYPE)
         tl["txy"], tl["ref_begin"], tl["ref_end"] = tiles[:, 0], tiles[:, 1], tiles[:, 2]
@@ -670,12 +678,15 @@ class Engine:
         desc["h"], desc["w"], desc["group_begin"], desc["group_end"] = h.value, w.value, 0, 1
         up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
         d = [up(desc), up(tl), up(np.ascontiguousarray(refs)), up(leaves)]
-        N.check(self.L.vis_overlay_draw_cn(d[0].data_ptr(), 1, 4, 0, d[1].data_ptr(), len(tl), d[2].data_ptr(), d[3].data_ptr(),
-                                           _stream_ptr()), "vis_overlay_draw_cn")
-        torch.cuda.current_stream(self.device).synchronize()          # the upload tensors may go; the sprite stays
+        N.check(self.L.vis_overlay_draw_cn(d[0].data_ptr(), 1, channels, 0, d[1].data_ptr(), len(tl), d[2].data_ptr(),
+                                           d[3].data_ptr(), _stream_ptr()), "vis_overlay_draw_cn")
+        torch.cuda.current_stream(self.device).synchronize()          # the upload tensors may go; the canvas stays
+        hit = (canvas, w.value, h.value, ox.value, oy.value)
+        if channels == 8 and bool((canvas[:, :, 0] & 0x40).any()):    # a blend chain overflowed: this dash stays leaves
+            hit = None
         if len(cache) >= 4096:
             cache.clear()
-        hit = cache[key] = (canvas, w.value, h.value, ox.value, oy.value)
+        cache[key] = hit
         return hit
 
     def plan_overlay(self, shapes, boxes_per_frame, confidence_threshold: str = "low", criticality: str = "medium"):
@@ -700,12 +711,23 @@ class Engine:
             if len(px):
                 radius = max(25, min(int(max(w, h) * 0.04), 60))
                 keys.update((radius, int(p["b"]), int(p["g"]), int(p["r"]), bytes(p["label"])) for p in px)
-        sprites = np.zeros(max(1, len(keys)), N.SPRITE_DTYPE)
-        keep_sprites = []
-        for i, key in enumerate(sorted(keys)):
+        # dashes (confidence == "low") are 10 px long, the last one of an edge 1..9: one recorded stamp per length and
+        # orientation, shared by every colour
+        dashes = [(L, 0) for L in range(1, 11)] + [(0, L) for L in range(1, 11)] if any(
+            len(px) and bool(px["dashed"].any()) for px in px_all) else []
+        entries, keep_sprites = [], []
+        for key in sorted(keys):
             canvas, sw, sh, sox, soy = self._marker_sprite(*key)
             keep_sprites.append(canvas)
-            sprites[i] = (key[0], key[1], key[2], key[3], 0, key[4], canvas.data_ptr(), sw, sh, sox, soy)
+            entries.append((key[0], key[1], key[2], key[3], 0, key[4], canvas.data_ptr(), sw, sh, sox, soy))
+        for dx, dy in dashes:
+            hit = self._dash_stamp(dx, dy)
+            if hit is not None:
+                keep_sprites.append(hit[0])
+                entries.append((-1, 0, 0, 0, 0, f"{dx},{dy}".encode(), hit[0].data_ptr(), hit[1], hit[2], hit[3], hit[4]))
+        sprites = np.zeros(max(1, len(entries)), N.SPRITE_DTYPE)
+        for i, e in enumerate(entries):
+            sprites[i] = e
         box_begin = np.asarray(box_begin, np.int32)
         n = len(shapes)
         leaf_begin = np.zeros(n + 1, np.int32)
@@ -723,7 +745,7 @@ class Engine:
                 n, hw.ctypes.data_as(C.c_void_p), boxes_arr.ctypes.data_as(C.c_void_p), box_begin.ctypes.data_as(C.c_void_p),
                 leaves.ctypes.data_as(C.c_void_p), cap[0], leaf_begin.ctypes.data_as(C.c_void_p),
                 tiles.ctypes.data_as(C.c_void_p), cap[1], refs.ctypes.data_as(C.c_void_p), cap[2],
-                needed.ctypes.data_as(C.c_void_p), 0, sprites.ctypes.data_as(C.c_void_p), len(keys))
+                needed.ctypes.data_as(C.c_void_p), 0, sprites.ctypes.data_as(C.c_void_p), len(entries))
             if rc == N.VIS_E_CAPACITY:
                 cap = [max(1, int(v)) for v in needed]
                 continue
