@@ -230,8 +230,11 @@ k_overlay_copy(const VisOverlayFrame* __restrict__ frames, int channels) {
 // sub-group the host binned into this tile (in leaf order) the 32 lanes test the 32 leaf boxes against the
 // sub-tile, the touching leaves are staged IN ORDER in the warp's shared-memory slots and applied per pixel in list
 // order.
+#ifndef VIS_OVERLAY_MIN_BLOCKS
+#define VIS_OVERLAY_MIN_BLOCKS 8          // 32 registers: the kernel is latency bound (dependent loads), occupancy pays for a few spills
+#endif
 template <int CN>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, VIS_OVERLAY_MIN_BLOCKS)
 k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile* __restrict__ tiles,
                 const VisOverlayRef* __restrict__ refs, const VisLeaf* __restrict__ leaves) {
     __shared__ int s_leaf[kThreads / 32][32][VIS_LEAF_WORDS];
