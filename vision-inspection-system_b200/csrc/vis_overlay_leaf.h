@@ -3,6 +3,10 @@
 // w[10] = x0 | x1<<16, w[11] = y0 | y1<<16 (inclusive bounding box, clamped to the image).
 #pragma once
 
+#ifndef VIS_LEAF_SUB_LEAVES
+#define VIS_LEAF_SUB_LEAVES 8       // leaves per sub-group header (<= 32: one lane per leaf in the draw kernel); small groups = tight boxes
+#endif
+
 enum : int {
     LEAF_NOP = 0,
     LEAF_GROUP = 1,    // header: w[2] = first leaf, w[3] = one past last leaf (indices inside the frame's array);
@@ -14,7 +18,7 @@ enum : int {
     LEAF_STAMP = 7,    // w[1] colour, w[2],w[3] device pointer to the blend-chain records (8 bytes per pixel) of a w[6] x w[7] stamp at (w[4], w[5])
     LEAF_SPRITE = 6,   // w[2],w[3] device pointer (lo, hi) to a BGRA sprite of w[6] x w[7] pixels placed at (w[4], w[5]): pixels with alpha are copied
     LEAF_KIND_MASK = 0xff,
-    LEAF_SUB_LEAVES = 32,       // leaves per sub-group header
+    LEAF_SUB_LEAVES = VIS_LEAF_SUB_LEAVES,       // leaves per sub-group header
     LEAF_FLAG_XMAJOR = 0x100,   // LINE8 / LINEAA: x is the major axis
     LEAF_FLAG_AA = 0x200,       // TRAP: antialiased polygon rounding (left +ONE-1, right +0) instead of +ONE/2
 };
