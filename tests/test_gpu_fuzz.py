@@ -55,3 +55,37 @@ def test_agent_thumbnails_random_geometries(engine, role, limit):
     outs = engine.agent_inputs([torch.from_numpy(f).cuda() for f in frames], role)
     for f, o, s in zip(frames, outs, shapes):
         assert np.array_equal(o.cpu().numpy(), Q.agent_thumbnail(f, limit)), (role, s)
+
+
+def test_overlay_random_frames_and_boxes(engine):
+    """Sprites, stamps, translated templates and in-place expansion all mixed: random frame sizes (markers and dashes
+    touching the borders on the small ones), random boxes pushed to the edges, free-text labels; batch and in place."""
+    from oracle import overlay as OV
+    rng = np.random.default_rng(105)
+    shapes = [(97, 211), (130, 150), (300, 500), (480, 640), (333, 517), (720, 1280), (1080, 1920), (65, 400), (400, 66)]
+    items = []
+    for k in range(18):
+        h, w = shapes[k % len(shapes)]
+        frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        boxes = synth.random_boxes(rng, int(rng.integers(1, 7)))
+        for b in boxes[:3]:
+            if rng.random() < 0.5:
+                b["x"] = 0.0
+            if rng.random() < 0.5:
+                b["y"] = 0.0
+            if rng.random() < 0.3:
+                b["x"] = round(100 - b["width"], 1)
+            if rng.random() < 0.3:
+                b["y"] = round(100 - b["height"], 1)
+            if rng.random() < 0.3:
+                b["label"] = ["wide-label!", "#123", "Q", "#7"][int(rng.integers(0, 4))]
+            if rng.random() < 0.5:
+                b["confidence"] = "low"
+        items.append((frame, boxes))
+    outs = engine.annotate([torch.from_numpy(f).cuda() for f, _ in items], [b for _, b in items])
+    for k, ((f, b), o) in enumerate(zip(items, outs)):
+        assert np.array_equal(o.cpu().numpy(), OV.draw_bounding_boxes(f, b)), (k, f.shape)
+    devs = [torch.from_numpy(f.copy()).cuda() for f, _ in items]
+    engine.annotate(devs, [b for _, b in items], inplace=True)
+    for k, ((f, b), d) in enumerate(zip(items, devs)):
+        assert np.array_equal(d.cpu().numpy(), OV.draw_bounding_boxes(f, b)), (k, f.shape, "in place")
