@@ -187,8 +187,8 @@ def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int, box=None, 
         raise NotImplementedError(f"image mode {mode!r} is resampled by Pillow with a non-8bpc path that this "
                                   "engine does not implement")
     bands = len(work.getbands())
-    arr = np.frombuffer(work.tobytes(), np.uint8).reshape(work.size[1], work.size[0], bands)
-    dev = torch.from_numpy(arr.copy()).cuda()
+    arr = np.array(work, dtype=np.uint8).reshape(work.size[1], work.size[0], bands)       # one host copy
+    dev = torch.from_numpy(arr).cuda()
     eng = _engine()
     if premultiply:
         eng.alpha_premultiply_(dev, True)
