@@ -30,6 +30,7 @@ check, no directory creation at import).  There is no CPU fallback.
 from __future__ import annotations
 
 import logging
+import warnings
 from pathlib import Path
 
 import numpy as np
@@ -187,8 +188,10 @@ def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int, box=None, 
         raise NotImplementedError(f"image mode {mode!r} is resampled by Pillow with a non-8bpc path that this "
                                   "engine does not implement")
     bands = len(work.getbands())
-    arr = np.array(work, dtype=np.uint8).reshape(work.size[1], work.size[0], bands)       # one host copy
-    dev = torch.from_numpy(arr).cuda()
+    arr = np.frombuffer(work.tobytes(), np.uint8).reshape(work.size[1], work.size[0], bands)   # one host copy (read-only)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)        # torch notes that the array is read-only; it is only copied
+        dev = torch.from_numpy(arr).cuda()
     eng = _engine()
     if premultiply:
         eng.alpha_premultiply_(dev, True)
