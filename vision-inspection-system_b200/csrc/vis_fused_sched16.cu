@@ -26,7 +26,10 @@ namespace {
 #ifndef VIS_S16_HWARPS
 #define VIS_S16_HWARPS 12
 #endif
-constexpr int kHWarps = VIS_S16_HWARPS, kSWarps = 2;    // H is the heavy role at these scales (profiles/r01_fused_sched16_4k.txt)
+#ifndef VIS_S16_SWARPS
+#define VIS_S16_SWARPS 2
+#endif
+constexpr int kHWarps = VIS_S16_HWARPS, kSWarps = VIS_S16_SWARPS;    // H is the heavy role at these scales (profiles/r01_fused_sched16_4k.txt)
 // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
 constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
 // vertical-pass warps NV: 6 for the mild downscales (V and H work comparable), 4 for the strong ones (V is light: fewer,
