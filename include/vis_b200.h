@@ -256,10 +256,11 @@ typedef struct VisOverlayFrame {
     int32_t        group_begin, group_end;   /* this frame's group headers in leaves[]; its leaf array starts at group_begin */
 } VisOverlayFrame;
 
-/* bins the sub-groups of ONE frame (runs of <= 32 consecutive leaves, written by vis_overlay_expand) into the
- * 64x16-pixel tiles of the draw kernel.  tiles_out: 3 int32 per touched tile, row-major: tx | ty << 16, first ref,
- * one past last ref.  refs_out: 2 int32 per ref, per tile IN LEAF ORDER: first leaf, one past last leaf (indices
- * inside the frame's leaf array).  Returns the tile count, or VIS_E_CAPACITY with the needed counts.    [host] */
+/* bins the leaves of ONE frame (written by vis_overlay_expand; culled per leaf, in leaf order) into the 64x16-pixel tiles
+ * of the draw kernel.  tiles_out: 3 int32 per touched tile, row-major: tx | ty << 16, first ref, one past last ref.
+ * refs_out: 2 int32 per ref, per tile IN LEAF ORDER: first leaf, one past last leaf (indices inside the frame's leaf
+ * array); this function emits single-leaf refs, which the draw kernel fetches 32 at a time (it also accepts longer
+ * runs).  Returns the tile count, or VIS_E_CAPACITY with the needed counts.                               [host] */
 int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, int n_boxes,
                       int32_t* tiles_out, int tile_capacity, int32_t* refs_out, int ref_capacity,
                       int* tiles_needed, int* refs_needed);

@@ -231,7 +231,7 @@ k_overlay_copy(const VisOverlayFrame* __restrict__ frames, int channels) {
 // sub-tile, the touching leaves are staged IN ORDER in the warp's shared-memory slots and applied per pixel in list
 // order.
 #ifndef VIS_OVERLAY_MIN_BLOCKS
-#define VIS_OVERLAY_MIN_BLOCKS 8          // 32 registers: the kernel is latency bound (dependent loads), occupancy pays for a few spills
+#define VIS_OVERLAY_MIN_BLOCKS 6          // 40 registers: the kernel is latency bound (dependent loads), occupancy pays for a few spills
 #endif
 template <int CN>
 __global__ void __launch_bounds__(kThreads, VIS_OVERLAY_MIN_BLOCKS)
@@ -261,11 +261,60 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
     const bool vec = ((f.dst_pitch | (int64_t)(uintptr_t)f.dst) & 3) == 0;
     int (*my_leaf)[VIS_LEAF_WORDS] = s_leaf[warp];
 
+    auto fetch = [&]() {
+        if (CN == 4 && nv == kPx && vec) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
+#pragma unroll
+            for (int j = 0; j < kPx; ++j) {
+                const uint32_t a = q[j];
+#pragma unroll
+                for (int k = 0; k < CN; ++k) c[j][k] = (a >> (8 * k)) & 0xff;
+            }
+        } else if (CN == 3 && nv == kPx && vec) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
+            const uint32_t a = q[0], b = q[1], d = q[2];
+            c[0][0] = a & 0xff; c[0][1] = (a >> 8) & 0xff; c[0][2] = (a >> 16) & 0xff;
+            c[1][0] = a >> 24;  c[1][1] = b & 0xff;        c[1][2] = (b >> 8) & 0xff;
+            c[2][0] = (b >> 16) & 0xff; c[2][1] = b >> 24; c[2][2] = d & 0xff;
+            c[3][0] = (d >> 8) & 0xff;  c[3][1] = (d >> 16) & 0xff; c[3][2] = d >> 24;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPx; ++j)
+#pragma unroll
+                for (int q = 0; q < CN; ++q) c[j][q] = j < nv ? (int)px[j * CN + q] : 0;
+        }
+    };
+
     // the refs of this tile, 32 at a time in registers (lane i holds ref r0 + i), consumed in order
     for (int r0 = tl.ref_begin; r0 < tl.ref_end; r0 += 32) {
         const int nr = min(32, tl.ref_end - r0);
         int2 mine = make_int2(0, 0);
         if (lane < nr) mine = __ldg(reinterpret_cast<const int2*>(refs + r0 + lane));
+        // refs that name single leaves (what vis_overlay_tiles emits: the host culls per leaf): every lane fetches its
+        // whole leaf at once and the 32 of them are culled against the sub-tile with one ballot — two dependent loads
+        // per 32 leaves instead of two per ref
+        if (__all_sync(0xffffffffu, lane >= nr || mine.y == mine.x + 1)) {
+            bool lhit = false;
+            int4 b0 = make_int4(0, 0, 0, 0), b1 = b0, b2 = b0;
+            if (lane < nr) {
+                const int4* src = reinterpret_cast<const int4*>(&fl[mine.x]);
+                b0 = __ldg(src); b1 = __ldg(src + 1); b2 = __ldg(src + 2);
+                lhit = touches(t, b2.z, b2.w);
+            }
+            const unsigned lm = __ballot_sync(0xffffffffu, lhit);
+            if (!lm) continue;
+            if (!loaded) { loaded = true; fetch(); }
+            if (lhit) {
+                int4* dst = reinterpret_cast<int4*>(my_leaf[__popc(lm & ((1u << lane) - 1))]);
+                dst[0] = b0; dst[1] = b1; dst[2] = b2;
+            }
+            __syncwarp();
+            const int n_leaf = __popc(lm);
+            if (nv > 0)
+                for (int q = 0; q < n_leaf; ++q) dirty |= apply_leaf<CN>(my_leaf[q], s_filter, x, y, c);
+            __syncwarp();
+            continue;
+        }
         for (int k = 0; k < nr; ++k) {
             const int lb = __shfl_sync(0xffffffffu, mine.x, k), le = __shfl_sync(0xffffffffu, mine.y, k);
             const int li = lb + lane;
@@ -276,30 +325,7 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
             }
             const unsigned lm = __ballot_sync(0xffffffffu, lhit);
             if (!lm) continue;
-            if (!loaded) {                                    // first leaf that reaches this sub-tile: fetch the pixels
-                loaded = true;
-                if (CN == 4 && nv == kPx && vec) {
-                    const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
-#pragma unroll
-                    for (int j = 0; j < kPx; ++j) {
-                        const uint32_t a = q[j];
-#pragma unroll
-                        for (int k = 0; k < CN; ++k) c[j][k] = (a >> (8 * k)) & 0xff;
-                    }
-                } else if (CN == 3 && nv == kPx && vec) {
-                    const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
-                    const uint32_t a = q[0], b = q[1], d = q[2];
-                    c[0][0] = a & 0xff; c[0][1] = (a >> 8) & 0xff; c[0][2] = (a >> 16) & 0xff;
-                    c[1][0] = a >> 24;  c[1][1] = b & 0xff;        c[1][2] = (b >> 8) & 0xff;
-                    c[2][0] = (b >> 16) & 0xff; c[2][1] = b >> 24; c[2][2] = d & 0xff;
-                    c[3][0] = (d >> 8) & 0xff;  c[3][1] = (d >> 16) & 0xff; c[3][2] = d >> 24;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kPx; ++j)
-#pragma unroll
-                        for (int q = 0; q < CN; ++q) c[j][q] = j < nv ? (int)px[j * CN + q] : 0;
-                }
-            }
+            if (!loaded) { loaded = true; fetch(); }          // first leaf that reaches this sub-tile: fetch the pixels
             if (lhit) {
                 const int4* src = reinterpret_cast<const int4*>(&fl[li]);
                 int4* dst = reinterpret_cast<int4*>(my_leaf[__popc(lm & ((1u << lane) - 1))]);

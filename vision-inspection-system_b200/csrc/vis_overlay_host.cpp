@@ -1071,20 +1071,21 @@ extern "C" int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, in
     constexpr int kTileW = 64, kTileH = 16;
     const int tw = (img_w + kTileW - 1) / kTileW, th = (img_h + kTileH - 1) / kTileH;
     std::vector<int> count((size_t)tw * th, 0);
+    // every leaf of every group, in order, into the tiles its box touches: the refs of a tile name single leaves
     auto each = [&](auto&& fn) {
         for (int g = 0; g < n_boxes; ++g) {
             const VisLeaf& h = leaves[g];
-            for (int s = h.w[4]; s < h.w[4] + h.w[5]; ++s) {
-                const VisLeaf& sub = leaves[s];
-                const int x0 = sub.w[10] & 0xffff, x1 = (int)((uint32_t)sub.w[10] >> 16);
-                const int y0 = sub.w[11] & 0xffff, y1 = (int)((uint32_t)sub.w[11] >> 16);
+            for (int li = h.w[2]; li < h.w[3]; ++li) {
+                const VisLeaf& leaf = leaves[li];
+                const int x0 = leaf.w[10] & 0xffff, x1 = (int)((uint32_t)leaf.w[10] >> 16);
+                const int y0 = leaf.w[11] & 0xffff, y1 = (int)((uint32_t)leaf.w[11] >> 16);
                 if (x0 > x1 || y0 > y1) continue;
                 for (int ty = y0 / kTileH; ty <= std::min(y1 / kTileH, th - 1); ++ty)
-                    for (int tx = x0 / kTileW; tx <= std::min(x1 / kTileW, tw - 1); ++tx) fn(ty * tw + tx, sub);
+                    for (int tx = x0 / kTileW; tx <= std::min(x1 / kTileW, tw - 1); ++tx) fn(ty * tw + tx, li);
             }
         }
     };
-    each([&](int t, const VisLeaf&) { ++count[t]; });
+    each([&](int t, int) { ++count[t]; });
     std::vector<int> at((size_t)tw * th, 0);
     int n_tiles = 0, n_refs = 0;
     for (int t = 0; t < tw * th; ++t) {
@@ -1104,9 +1105,9 @@ extern "C" int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, in
         vis::set_error("vis_overlay_tiles: %d tiles / %d refs, capacity %d / %d", n_tiles, n_refs, tile_capacity, ref_capacity);
         return VIS_E_CAPACITY;
     }
-    each([&](int t, const VisLeaf& sub) {
-        refs_out[2 * at[t]] = sub.w[2];
-        refs_out[2 * at[t] + 1] = sub.w[3];
+    each([&](int t, int li) {
+        refs_out[2 * at[t]] = li;
+        refs_out[2 * at[t] + 1] = li + 1;
         ++at[t];
     });
     return n_tiles;
