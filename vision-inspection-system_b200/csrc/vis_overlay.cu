@@ -1,10 +1,10 @@
 // vis_overlay.cu — device half of the defect-overlay rasteriser (cv2 drawing calls of
 // utils/image_utils.py:259-313 in the reference, reproduced pixel for pixel).
 //
-// Only tiles that some leaf can touch are visited: the host bins the sub-groups into tiles (vis_overlay_tiles),
+// Only tiles that some leaf can touch are visited: the host bins the leaves into tiles (vis_overlay_tiles),
 // everything else is a plain vectorised frame copy (out of place) or nothing at all (in place).  A CTA owns one
 // listed 64x16 tile; each warp owns a 32x4 sub-tile (lane = 4 pixels, 12 bytes in registers) and culls on its own
-// with ballots over the leaves of the tile's sub-groups (runs of 32 consecutive leaves); touching leaves are
+// with ballots over the tile's leaves, fetched 32 at a time; touching leaves are
 // staged IN ORDER in shared memory and every lane applies them in list order to its own pixels.  Per-pixel in-order
 // application is what makes the result identical to OpenCV's sequential drawing: fills and LINE_8 points
 // overwrite, LineAA pixels blend (twice, 8-bit alpha) with whatever is there.
@@ -226,9 +226,9 @@ k_overlay_copy(const VisOverlayFrame* __restrict__ frames, int channels) {
 }
 
 // In-place drawing of the touched tiles.  CTA = one 64x16 tile of the host-built tile list; each of its 8 warps owns a
-// 32x4 pixel sub-tile (lane = 4 pixels of one row) and works on its own, without block-wide barriers: for every
-// sub-group the host binned into this tile (in leaf order) the 32 lanes test the 32 leaf boxes against the
-// sub-tile, the touching leaves are staged IN ORDER in the warp's shared-memory slots and applied per pixel in list
+// 32x4 pixel sub-tile (lane = 4 pixels of one row) and works on its own, without block-wide barriers: the leaves the
+// host binned into this tile (in leaf order) are fetched 32 at a time, one per lane, tested against the sub-tile with
+// one ballot, and the touching ones are staged IN ORDER in the warp's shared-memory slots and applied per pixel in list
 // order.
 #ifndef VIS_OVERLAY_MIN_BLOCKS
 #define VIS_OVERLAY_MIN_BLOCKS 6          // 40 registers: the kernel is latency bound (dependent loads), occupancy pays for a few spills

@@ -296,32 +296,11 @@ class Emitter {
     }
     void end_group(int slot) {                   // header = leaf range + bounding box of everything in it
         const int first = group_first_, last = n_;
-        // sub-group headers: one per kSubLeaves consecutive leaves (range + union box), appended after the leaves.
-        // Consecutive leaves belong to the same stroke / dash / ring segment, so these boxes are small and let a
-        // tile inside a large defect box skip almost all of its leaves.
-        const int sub_first = n_;
-        for (int a = first; a < last; a += LEAF_SUB_LEAVES) {
-            const int b = std::min(a + LEAF_SUB_LEAVES, last);
-            VisLeaf h;
-            std::memset(&h, 0, sizeof h);
-            h.w[0] = LEAF_GROUP;
-            h.w[2] = a;
-            h.w[3] = b;
-            int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
-            for (int i = a; i < b && i < cap_; ++i) {
-                x0 = std::min(x0, out_[i].w[10] & 0xffff); x1 = std::max(x1, (int)((uint32_t)out_[i].w[10] >> 16));
-                y0 = std::min(y0, out_[i].w[11] & 0xffff); y1 = std::max(y1, (int)((uint32_t)out_[i].w[11] >> 16));
-            }
-            if (x0 <= x1 && y0 <= y1) pack_bbox(h, x0, y0, x1, y1); else { h.w[10] = 1; h.w[11] = 1; }
-            push(h);
-        }
         if (slot >= cap_) return;
         VisLeaf& l = out_[slot];
         l.w[2] = first;
         l.w[3] = last;
-        l.w[4] = sub_first;
-        l.w[5] = n_ - sub_first;
-        if (gx0_ > gx1_ || gy0_ > gy1_) { l.w[3] = first; l.w[5] = 0; l.w[10] = 1; l.w[11] = 1; return; }   // nothing visible
+        if (gx0_ > gx1_ || gy0_ > gy1_) { l.w[3] = first; l.w[10] = 1; l.w[11] = 1; return; }   // nothing visible
         pack_bbox(l, gx0_, gy0_, gx1_, gy1_);
     }
 
@@ -1057,9 +1036,9 @@ extern "C" int vis_overlay_stamp_expand(int dx, int dy, VisLeaf* leaves, int cap
     return em.count();
 }
 
-// Bins the frame's sub-groups (runs of <= 32 consecutive leaves with a common box) into the 64x16-pixel CTA tiles of
+// Bins the frame's leaves (culled one by one, in order) into the 64x16-pixel CTA tiles of
 // vis_overlay.cu.  tiles_out: one record per touched tile, row-major: {tx | ty << 16, first ref, one past last ref};
-// refs_out: per tile, IN LEAF ORDER, {first leaf, one past last leaf} of every sub-group whose box touches the tile.
+// refs_out: per tile, IN LEAF ORDER, {leaf, leaf + 1} of every leaf whose box touches the tile.
 extern "C" int vis_overlay_tiles(int img_h, int img_w, const VisLeaf* leaves, int n_boxes,
                                  int32_t* tiles_out, int tile_capacity, int32_t* refs_out, int ref_capacity,
                                  int* tiles_needed, int* refs_needed) {

@@ -116,7 +116,7 @@ def expand_leaves(pixel_boxes: np.ndarray, img_width: int, img_height: int) -> n
 
 
 def touched_tiles(leaves: np.ndarray, n_boxes: int, img_width: int, img_height: int):
-    """Bins one frame's sub-groups into the 64x16 tiles of the draw kernel via ``vis_overlay_tiles``.
+    """Bins one frame's leaves into the 64x16 tiles of the draw kernel via ``vis_overlay_tiles``.
 
     Returns (tiles int32 [n, 3] = (tx | ty << 16, first ref, one past last ref), refs int32 [m, 2] = leaf ranges)."""
     if n_boxes == 0 or len(leaves) == 0:
