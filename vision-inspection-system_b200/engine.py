@@ -949,19 +949,32 @@ class Engine:
         """BGR uint8 HWC CUDA frames (``[B,H,W,3]`` tensor or list) -> (int64 CUDA tensor [B, 3] = sum(gray),
         sum(laplacian), sum(laplacian^2) per frame, exact; list of (H, W)).  One launch for the batch."""
         uniform = isinstance(frames, torch.Tensor) and frames.dim() == 4
-        flist = list(frames.unbind(0)) if uniform else list(frames)
-        if not flist:
-            raise ValueError("no frames")
-        for f in flist:
-            self._check_u8(f)
-            if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
-                raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
-        shapes = [(int(f.shape[0]), int(f.shape[1])) for f in flist]
-        desc = np.zeros(len(flist), N.QUALITY_FRAME_DTYPE)
-        desc["src"] = [f.data_ptr() for f in flist]
-        desc["pitch"] = [f.stride(0) for f in flist]
-        desc["h"] = [s[0] for s in shapes]
-        desc["w"] = [s[1] for s in shapes]
+        if uniform:                                   # a batch tensor: one check, descriptors by arithmetic
+            self._check_u8(frames)
+            if frames.shape[0] == 0:
+                raise ValueError("no frames")
+            if frames.shape[3] != 3 or frames.stride(3) != 1 or frames.stride(2) != 3:
+                raise ValueError("frames must be [B, H, W, 3] uint8 with contiguous pixels")
+            n = int(frames.shape[0])
+            shapes = [(int(frames.shape[1]), int(frames.shape[2]))] * n
+            desc = np.zeros(n, N.QUALITY_FRAME_DTYPE)
+            desc["src"] = np.uint64(frames.data_ptr()) + np.arange(n, dtype=np.uint64) * np.uint64(frames.stride(0))
+            desc["pitch"], desc["h"], desc["w"] = frames.stride(1), shapes[0][0], shapes[0][1]
+            flist = range(n)
+        else:
+            flist = list(frames)
+            if not flist:
+                raise ValueError("no frames")
+            for f in flist:
+                self._check_u8(f)
+                if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                    raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
+            shapes = [(int(f.shape[0]), int(f.shape[1])) for f in flist]
+            desc = np.zeros(len(flist), N.QUALITY_FRAME_DTYPE)
+            desc["src"] = [f.data_ptr() for f in flist]
+            desc["pitch"] = [f.stride(0) for f in flist]
+            desc["h"] = [s_[0] for s_ in shapes]
+            desc["w"] = [s_[1] for s_ in shapes]
         d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.device)
         sums = torch.empty((len(flist), 3), dtype=torch.int64, device=self.device)
         out = []
