@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 14
+#define VIS_B200_ABI_VERSION 15
 
 /* status codes */
 #define VIS_OK            0
@@ -38,6 +38,8 @@ extern "C" {
 
 int         vis_abi_version(void);      /* [host] */
 const char* vis_last_error(void);       /* [host] thread-local, never NULL */
+const char* vis_source_hash(void);      /* [host] hex16 of the sources, header and flags this binary was built from
+                                           (build.py compares it with the tree: a stale binary is rebuilt, never tested) */
 
 /* ------------------------------------------------------------------------------------------
  * Coefficient tables                                                              [host]
@@ -97,6 +99,18 @@ int vis_gather_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int chann
  * or 2 (LA), alpha last.  forward != 0: c = MULDIV255(c, a) = ((t = c*a + 128) + (t >> 8)) >> 8; forward == 0:
  * c = min(255, 255*c / a) unless a is 0 or 255 (copied).                                               [device] */
 int vis_alpha_premultiply_u8(uint8_t* img, int64_t pitch, int h, int w, int channels, int forward, void* stream);
+
+/* Row re-pitch.  The fused kernels stage rows with bulk copies, which need a 16-byte aligned base and pitch; frames that
+ * are not (a 502-pixel-wide RGB frame has 1506-byte rows) are copied, a whole batch per launch, into a caller-owned
+ * staging buffer with an aligned pitch.  descs: DEVICE array; dst and dst_pitch multiples of 16; bytes of a dst row
+ * beyond row_bytes are left untouched.  max_frame_bytes sizes the grid.                                  [device] */
+typedef struct VisRepitch {
+    const uint8_t* src;
+    uint8_t*       dst;
+    int64_t        src_pitch, dst_pitch;
+    int32_t        rows, row_bytes;
+} VisRepitch;
+int vis_repitch_u8(const VisRepitch* descs, int n, int64_t max_frame_bytes, void* stream);
 
 /* resized RGB uint8 HWC [h,w,3] (h,w multiples of 28) -> rows [row0, row0 + (h/14)*(w/14)) of
  * pixel_values [*,1176] f32 in Qwen2-VL patch order (tf:models/qwen2_vl/image_processing_pil_qwen2_vl.py:182-214):
@@ -235,7 +249,8 @@ typedef struct VisBox {        /* a box AFTER the reference's validation + perce
     int32_t x, y, w, h;        /* pixels                                                         */
     uint8_t b, g, r;           /* BGR colour (utils/image_utils.py:250-252)                       */
     uint8_t dashed;            /* 1 iff confidence == "low" (utils/image_utils.py:257)            */
-    char    label[12];         /* NUL-terminated text drawn in the marker ('#' already removed)   */
+    const char* label;         /* HOST pointer: NUL-terminated UTF-8 text drawn in the marker ('#' already removed,
+                                  utils/image_utils.py:240-242), any length; bytes outside 32..126 draw '?' as cv2 does */
 } VisBox;
 
 #define VIS_LEAF_WORDS 12
@@ -244,7 +259,7 @@ typedef struct VisLeaf { int32_t w[VIS_LEAF_WORDS]; } VisLeaf;   /* opaque 48-by
 /* expand the boxes of ONE frame into its leaf array: n_boxes group headers (one per box: leaf range +
  * bounding box, indices relative to the start of this array) followed by the ordered leaves.
  * Returns the leaf count, or VIS_E_CAPACITY with *needed = required count (call again with a larger buffer),
- * or VIS_E_UNSUPPORTED for a label character outside printable ASCII (32..126).          [host] */
+ * Never fails on label content: like cv2.putText, any byte outside printable ASCII is drawn as '?'.   [host] */
 int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int n_boxes,
                        VisLeaf* leaves, int capacity, int* needed);
 
@@ -291,7 +306,7 @@ int vis_overlay_plan_batch(int n_frames, const int32_t* hw, const VisBox* boxes,
 typedef struct VisSprite {
     int32_t  radius;
     uint8_t  b, g, r, pad;
-    char     label[12];            /* NUL-terminated, as VisBox.label                                               */
+    const char* label;             /* HOST pointer, NUL-terminated, as VisBox.label                                 */
     uint64_t pixels;               /* DEVICE address of the BGRA canvas, rows of 4 * w bytes                        */
     int32_t  w, h, ox, oy;         /* canvas size and the position of the marker centre inside it                   */
 } VisSprite;
@@ -399,7 +414,7 @@ int vis_compose_panels(uint8_t* canvas, int64_t canvas_pitch, int h, int w, int 
 #define VIS_DRAW_LINE      1     /* cv2.line((x1,y1),(x2,y2), color, thickness, line_type)                        */
 #define VIS_DRAW_RECTANGLE 2     /* cv2.rectangle((x1,y1),(x2,y2), color, thickness >= 1, line_type)              */
 #define VIS_DRAW_CIRCLE    3     /* cv2.circle((x1,y1), x2 = radius, color, thickness: -1 filled or > 1, LINE_8)   */
-#define VIS_DRAW_TEXT      4     /* cv2.putText(text, (x1,y1), FONT_HERSHEY_SIMPLEX, font_scale, color, thickness) */
+#define VIS_DRAW_TEXT      4     /* cv2.putText(text, (x1,y1), FONT_HERSHEY_SIMPLEX, font_scale, color, thickness >= 2) */
 typedef struct VisDrawCmd {
     int32_t kind;
     int32_t x1, y1, x2, y2;
@@ -407,10 +422,9 @@ typedef struct VisDrawCmd {
     int32_t line_type;           /* 8 or 16 (LINE / RECTANGLE)                                                    */
     uint8_t color[4];            /* B, G, R, A (A is used by 4-channel canvases only)                             */
     double  font_scale;
-    char    text[64];            /* NUL-terminated, printable ASCII                                               */
+    const char* text;            /* HOST pointer, NUL-terminated UTF-8, any length (bytes outside 32..126 draw '?') */
 } VisDrawCmd;
-/* cv2.getTextSize(text, FONT_HERSHEY_SIMPLEX, font_scale, thickness)[0]; VIS_E_UNSUPPORTED for a character outside
- * printable ASCII.                                                                     [host] */
+/* cv2.getTextSize(text, FONT_HERSHEY_SIMPLEX, font_scale, thickness)[0] (bytes outside 32..126 measure as '?').  [host] */
 int vis_text_size(const char* text, double font_scale, int thickness, int* width, int* height);
 /* like vis_overlay_expand, for a draw list: n_cmds group headers followed by the ordered leaves.   [host] */
 int vis_draw_expand(int img_h, int img_w, const VisDrawCmd* cmds, int n_cmds,

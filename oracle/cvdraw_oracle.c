@@ -555,8 +555,10 @@ static const char* const kSimplexGlyphs[95] = {
     "KYPBSETHTJSMQOQPURQTQUSWTZT\\S_Pb",  /* } */
     "F^IUISJPLONOPPTSVTXTZS[Q ISJQLPNPPQTTVUXUZT[Q[O",  /* ~ */
 };
+/* cv: drawing.cpp readCheck(): with FONT_HERSHEY_SIMPLEX every byte outside 32..126 (so every byte of a multi-byte
+ * UTF-8 character) is replaced by '?' — pinned against the installed cv2 in tests/test_oracle_cvdraw.py */
 static const char* simplex_glyph(int c) {
-    return (c >= 32 && c <= 126) ? kSimplexGlyphs[c - 32] : NULL;
+    return kSimplexGlyphs[((c >= 32 && c <= 126) ? c : '?') - 32];
 }
 
 /* =============================== exported entry points =============================== */

@@ -105,14 +105,19 @@ class _CDraw:
 
     def text_size(self, text, fs, thickness):
         w, h = ctypes.c_int(), ctypes.c_int()
-        if self.L.ocv_get_text_size(text.encode("latin-1"), fs, thickness, ctypes.byref(w), ctypes.byref(h)):
+        if self.L.ocv_get_text_size(_cv_bytes(text), fs, thickness, ctypes.byref(w), ctypes.byref(h)):
             raise ValueError(f"glyph outside the oracle's Hershey table: {text!r}")
         return w.value, h.value
 
     def put_text(self, text, org, fs, color, thickness):
-        if self.L.ocv_put_text(self.p, self.h, self.w, self.step, text.encode("latin-1"), org[0], org[1], fs,
+        if self.L.ocv_put_text(self.p, self.h, self.w, self.step, _cv_bytes(text), org[0], org[1], fs,
                                *color, thickness):
             raise ValueError(f"glyph outside the oracle's Hershey table: {text!r}")
+
+
+def _cv_bytes(text: str) -> bytes:
+    """what cv2.putText receives from Python: the UTF-8 bytes, cut at the first NUL"""
+    return text.encode("utf-8", "replace").split(b"\0")[0]
 
 
 class _Cv2Draw:

@@ -91,14 +91,24 @@ def test_every_printable_ascii_glyph_against_cv2():
             tw, th = ctypes.c_int(), ctypes.c_int()
             L.ocv_get_text_size(chr(c).encode(), fs, t, ctypes.byref(tw), ctypes.byref(th))
             assert (tw.value, th.value) == cv2.getTextSize(chr(c), cv2.FONT_HERSHEY_SIMPLEX, fs, t)[0], chr(c)
-    assert L.ocv_put_text(P(b), 120, 160, b.strides[0], "\xe9".encode("latin-1"), 30, 90, 1.0, 1, 2, 3, 2) != 0   # outside ASCII
+    # outside printable ASCII: cv2 draws one '?' per BYTE of the UTF-8 text (cv: readCheck), the reference never raises
+    for text in ("\xe9", "\u65e5\u672c", "a\tb", "\x7f", "caf\xe9 #3"):
+        a = np.zeros((120, 400, 3), np.uint8)
+        b = a.copy()
+        cv2.putText(a, text, (10, 90), cv2.FONT_HERSHEY_SIMPLEX, 1.0, (255, 200, 50), 2)
+        assert L.ocv_put_text(P(b), 120, 400, b.strides[0], text.encode("utf-8"), 10, 90, 1.0, 255, 200, 50, 2) == 0
+        assert np.array_equal(a, b), text
+        tw, th = ctypes.c_int(), ctypes.c_int()
+        assert L.ocv_get_text_size(text.encode("utf-8"), 1.0, 2, ctypes.byref(tw), ctypes.byref(th)) == 0
+        assert (tw.value, th.value) == cv2.getTextSize(text, cv2.FONT_HERSHEY_SIMPLEX, 1.0, 2)[0], text
 
 
 def test_text_labels_against_cv2_calls():
     """draw_bounding_boxes with labels other than '#<int>' (any printable ASCII): oracle render == the same cv2 calls."""
     pytest.importorskip("cv2")
     from vision_inspection_system_b200 import synth
-    labels = ["#A7", "crack-12", "Z", "a|b", "#(x)", "Q9%", "~"]
+    labels = ["#A7", "crack-12", "Z", "a|b", "#(x)", "Q9%", "~", "a label far longer than eleven bytes", "d\xe9faut #2",
+              "\u6b20\u9665", ""]
     for seed, shape in ((11, (480, 640)), (12, (1080, 1920))):
         frame, boxes = synth.annotated_frame(seed, *shape)
         for i, b in enumerate(boxes):

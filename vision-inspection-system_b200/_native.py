@@ -34,7 +34,7 @@ STRIP_DTYPE = np.dtype([("frame", np.int32), ("x0", np.int32), ("x1", np.int32),
                        align=True)
 BOX_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("w", np.int32), ("h", np.int32),
                       ("b", np.uint8), ("g", np.uint8), ("r", np.uint8), ("dashed", np.uint8),
-                      ("label", "S12")], align=True)
+                      ("label", np.uint64)], align=True)      # host pointer to NUL-terminated bytes (see HostRecords)
 LEAF_DTYPE = np.dtype([("w", np.int32, (LEAF_WORDS,))], align=True)
 OVERLAY_FRAME_DTYPE = np.dtype([
     ("src", np.uint64), ("dst", np.uint64), ("src_pitch", np.int64), ("dst_pitch", np.int64),
@@ -54,9 +54,12 @@ OVERLAY_REF_DTYPE = np.dtype([("leaf_begin", np.int32), ("leaf_end", np.int32)],
 QUALITY_FRAME_DTYPE = np.dtype([("src", np.uint64), ("pitch", np.int64), ("h", np.int32), ("w", np.int32)], align=True)
 assert LEAF_DTYPE.itemsize == 48 and OVERLAY_FRAME_DTYPE.itemsize == 48
 SPRITE_DTYPE = np.dtype([("radius", np.int32), ("b", np.uint8), ("g", np.uint8), ("r", np.uint8), ("pad", np.uint8),
-                         ("label", "S12"), ("pixels", np.uint64), ("w", np.int32), ("h", np.int32), ("ox", np.int32),
+                         ("label", np.uint64), ("pixels", np.uint64), ("w", np.int32), ("h", np.int32), ("ox", np.int32),
                          ("oy", np.int32)], align=True)
-assert SPRITE_DTYPE.itemsize == 48
+assert SPRITE_DTYPE.itemsize == 40
+REPITCH_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("src_pitch", np.int64), ("dst_pitch", np.int64),
+                          ("rows", np.int32), ("row_bytes", np.int32)], align=True)
+assert REPITCH_DTYPE.itemsize == 40
 RESIZE_COPY, RESIZE_AREA2, RESIZE_BILINEAR = 0, 1, 2
 JPEG_BACKEND_DEFAULT, JPEG_BACKEND_HYBRID, JPEG_BACKEND_GPU_HYBRID, JPEG_BACKEND_HARDWARE = 0, 1, 2, 3
 JPEG_CSS_444, JPEG_CSS_422, JPEG_CSS_420, JPEG_CSS_GRAY = 0, 1, 2, 6
@@ -67,11 +70,11 @@ PANEL_DTYPE = np.dtype([("src", np.uint64), ("src_pitch", np.int64), ("src_h", n
 DRAW_LINE, DRAW_RECTANGLE, DRAW_CIRCLE, DRAW_TEXT = 1, 2, 3, 4
 DRAW_CMD_DTYPE = np.dtype([("kind", np.int32), ("x1", np.int32), ("y1", np.int32), ("x2", np.int32), ("y2", np.int32),
                            ("thickness", np.int32), ("line_type", np.int32), ("color", np.uint8, (4,)),
-                           ("font_scale", np.float64), ("text", "S64")], align=True)
-assert PANEL_DTYPE.itemsize == 80 and DRAW_CMD_DTYPE.itemsize == 104
+                           ("font_scale", np.float64), ("text", np.uint64)], align=True)
+assert PANEL_DTYPE.itemsize == 80 and DRAW_CMD_DTYPE.itemsize == 48
 
 EXPORTS = [
-    "vis_abi_version", "vis_last_error", "vis_coeff_ksize", "vis_build_coeffs", "vis_build_lut",
+    "vis_abi_version", "vis_last_error", "vis_source_hash", "vis_coeff_ksize", "vis_build_coeffs", "vis_build_lut",
     "vis_resample_h_u8", "vis_resample_v_u8", "vis_normalize_patchify",
     "vis_max_taps", "vis_fused_kt_class", "vis_record_stride", "vis_pack_records", "vis_fused_supported",
     "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
@@ -79,10 +82,50 @@ EXPORTS = [
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
     "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn", "vis_overlay_sprite_expand", "vis_overlay_stamp_expand", "vis_overlay_plan_batch_sprites",
-    "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8", "vis_alpha_premultiply_u8",
+    "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8", "vis_alpha_premultiply_u8", "vis_repitch_u8",
     "vis_jpeg_create", "vis_jpeg_destroy", "vis_jpeg_info", "vis_jpeg_decode", "vis_jpeg_decode_batch",
     "vis_jpeg_encode_bound", "vis_jpeg_encode",
 ]
+
+
+class HostRecords(np.ndarray):
+    """Structured records that hold HOST pointers to strings (``VisBox.label``, ``VisSprite.label``,
+    ``VisDrawCmd.text``): the array keeps the buffers it points into alive (``keep``), views and slices inherit
+    them.  ``np.concatenate`` returns a plain array: keep the parts alive while the result is in use."""
+
+    def __array_finalize__(self, obj):
+        self.keep = getattr(obj, "keep", None)
+
+
+def cv_text(text) -> bytes:
+    """The bytes cv2.putText receives for a Python string: UTF-8, cut at the first NUL."""
+    if isinstance(text, (bytes, bytearray)):
+        return bytes(text).split(b"\0")[0]
+    return str(text).encode("utf-8", "replace").split(b"\0")[0]
+
+
+def host_records(rows: list, dtype: np.dtype, string_field: str) -> "HostRecords":
+    """Records from tuples whose ``string_field`` entry is ``bytes``: the strings are stored in ctypes buffers owned
+    by the returned array and the field receives their addresses."""
+    names = list(dtype.names)
+    k = names.index(string_field)
+    keep, fixed = [], []
+    for row in rows:
+        buf = C.create_string_buffer(row[k])
+        keep.append(buf)
+        fixed.append(tuple(row[:k]) + (C.addressof(buf),) + tuple(row[k + 1:]))
+    arr = np.zeros(len(fixed), dtype)
+    for j, row in enumerate(fixed):
+        arr[j] = row
+    out = arr.view(HostRecords)
+    out.keep = keep
+    return out
+
+
+def record_string(rec, field: str) -> bytes:
+    """The bytes a record's pointer field points to (``b""`` for a null pointer)."""
+    addr = int(rec[field])
+    return C.string_at(addr) if addr else b""
 
 
 class VisError(RuntimeError):
@@ -104,7 +147,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 14:
+        if L.vis_abi_version() != 15:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -115,6 +158,7 @@ def _declare(L: C.CDLL) -> None:
     ip = C.POINTER(C.c_int)
     L.vis_abi_version.restype = C.c_int
     L.vis_last_error.restype = C.c_char_p
+    L.vis_source_hash.restype = C.c_char_p
     L.vis_coeff_ksize.argtypes = [C.c_int, C.c_int, C.c_int]
     L.vis_build_coeffs.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, ip]
     L.vis_build_lut.argtypes = [f32p, f32p, C.c_double, f32p]
@@ -155,6 +199,7 @@ def _declare(L: C.CDLL) -> None:
     L.vis_nearest_table.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, i32p]
     L.vis_gather_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
     L.vis_alpha_premultiply_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.vis_repitch_u8.argtypes = [vp, C.c_int, C.c_int64, vp]
     L.vis_overlay_sprite_expand.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, vp, C.c_int, ip, ip, ip, ip, ip]
     L.vis_overlay_stamp_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, ip, ip, ip, ip, ip]
     L.vis_overlay_plan_batch_sprites.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int,
@@ -172,7 +217,7 @@ def _declare(L: C.CDLL) -> None:
             getattr(L, name).restype = None
         elif name == "vis_jpeg_encode_bound":
             getattr(L, name).restype = C.c_int64
-        elif name != "vis_last_error":
+        elif name not in ("vis_last_error", "vis_source_hash"):
             getattr(L, name).restype = C.c_int
 
 

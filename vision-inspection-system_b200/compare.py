@@ -26,17 +26,25 @@ def panel_width(height: int, width: int, target_h: int = TARGET_HEIGHT) -> int:
 def text_size(text: str, font_scale: float, thickness: int) -> tuple[int, int]:
     """``cv2.getTextSize(text, FONT_HERSHEY_SIMPLEX, font_scale, thickness)[0]`` through the C ABI."""
     w, h = C.c_int(0), C.c_int(0)
-    N.check(N.lib().vis_text_size(text.encode("latin-1", "replace"), float(font_scale), int(thickness),
+    N.check(N.lib().vis_text_size(N.cv_text(text), float(font_scale), int(thickness),
                                   C.byref(w), C.byref(h)), "vis_text_size")
     return w.value, h.value
 
 
 def _cmd(kind, x1, y1, x2, y2, thickness, color, line_type=LINE_8, font_scale=0.0, text=""):
-    encoded = text.encode("latin-1", "replace")
-    if len(encoded) > 63:
-        raise ValueError(f"text too long for one draw command (max 63 characters): {text!r}")
     color = tuple(color) + (0,) * (4 - len(color))
-    return (kind, x1, y1, x2, y2, thickness, line_type, color, font_scale, encoded)
+    return (kind, x1, y1, x2, y2, thickness, line_type, color, font_scale, N.cv_text(text))
+
+
+def commands(rows: list) -> np.ndarray:
+    """``VisDrawCmd`` records from ``_cmd`` tuples (the texts live in buffers the array keeps alive)."""
+    return N.host_records(rows, N.DRAW_CMD_DTYPE, "text")
+
+
+def commands_key(cmds: np.ndarray) -> tuple:
+    """A hashable value identifying a draw list by CONTENT (the records hold pointers, so their bytes do not)."""
+    return tuple((int(c["kind"]), int(c["x1"]), int(c["y1"]), int(c["x2"]), int(c["y2"]), int(c["thickness"]),
+                  int(c["line_type"]), bytes(c["color"]), float(c["font_scale"]), N.record_string(c, "text")) for c in cmds)
 
 
 def header_commands(left_w: int, right_w: int, labels=DEFAULT_LABELS) -> np.ndarray:
@@ -48,7 +56,7 @@ def header_commands(left_w: int, right_w: int, labels=DEFAULT_LABELS) -> np.ndar
     tw, _ = text_size(right_label, 0.7, 2)
     cmds.append(_cmd(N.DRAW_TEXT, left_w + DIVIDER_WIDTH + right_w // 2 - tw // 2, 28, 0, 0, 2, (255, 255, 255),
                      font_scale=0.7, text=right_label))
-    return np.array(cmds, N.DRAW_CMD_DTYPE)
+    return commands(cmds)
 
 
 def stamp_style(verdict: str):
@@ -64,10 +72,10 @@ def stamp_commands(verdict: str, width: int, height: int) -> np.ndarray:
     """``cv2.rectangle(.., border, 4)`` then ``cv2.putText(.., 1.5, colour, 4)`` (utils/image_utils.py:725-733)."""
     text, color, border = stamp_style(verdict)
     tw, th = text_size(text, 1.5, 4)
-    return np.array([
+    return commands([
         _cmd(N.DRAW_RECTANGLE, 5, 5, width - 5, height - 5, 4, border),
         _cmd(N.DRAW_TEXT, (width - tw) // 2, (height + th) // 2, 0, 0, 4, color, font_scale=1.5, text=text),
-    ], N.DRAW_CMD_DTYPE)
+    ])
 
 
 def expand_commands(cmds: np.ndarray, img_width: int, img_height: int) -> np.ndarray:
@@ -76,6 +84,7 @@ def expand_commands(cmds: np.ndarray, img_width: int, img_height: int) -> np.nda
     n = len(cmds)
     if n == 0:
         return np.zeros(0, N.LEAF_DTYPE)
+    owner = cmds                               # the records point into buffers this object keeps alive
     cmds = np.ascontiguousarray(cmds)
     cap = 4096
     while True:
@@ -87,6 +96,7 @@ def expand_commands(cmds: np.ndarray, img_width: int, img_height: int) -> np.nda
             cap = needed.value
             continue
         N.check(rc, "vis_draw_expand")
+        del owner
         return leaves[:rc].copy()
 
 

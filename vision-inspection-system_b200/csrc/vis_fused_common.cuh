@@ -1,5 +1,5 @@
 // vis_fused_common.cuh — PTX helpers and small device utilities shared by the fused kernels
-// (vis_fused.cu: phase-synchronous CTA; vis_fused_ws.cu: warp-specialised persistent CTA).
+// (vis_fused_ws.cu: general warp-specialised persistent CTA; vis_fused_sched*.cu: statically scheduled kernels).
 #pragma once
 #include <climits>
 

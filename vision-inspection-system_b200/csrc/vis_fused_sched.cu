@@ -1,6 +1,6 @@
 // vis_fused_sched.cu — statically scheduled, warp-specialised hot kernel (frame -> Qwen2-VL pixel_values).
 //
-// Same arithmetic as vis_fused.cu / vis_fused_ws.cu (Pillow 8bpc horizontal pass -> uint8 -> vertical pass -> uint8 ->
+// Same arithmetic as vis_fused_ws.cu (Pillow 8bpc horizontal pass -> uint8 -> vertical pass -> uint8 ->
 // exact LUT -> patch layout; tf:models/qwen2_vl/image_processing_pil_qwen2_vl.py:164-214), same pipeline of roles over
 // shared-memory rings with full/empty mbarriers:
 //

@@ -1,7 +1,7 @@
 // vis_fused_ws.cu — warp-specialised persistent variant of the hot kernel (frame -> Qwen2-VL pixel_values).
 //
-// Same arithmetic and the same three stages as vis_fused.cu (Pillow 8bpc horizontal pass -> uint8 -> vertical pass ->
-// uint8 -> exact LUT -> patch layout), but instead of one CTA alternating between phases behind __syncthreads, ONE
+// Arithmetic: tf:models/qwen2_vl/image_processing_pil_qwen2_vl.py:164-214 (Pillow 8bpc horizontal pass -> uint8 -> vertical pass ->
+// uint8 -> exact LUT -> patch layout).  Any mix of geometries with <= 8 taps in one launch: ONE
 // CTA per SM stays resident and its 25 warps run the stages concurrently as a pipeline over shared-memory rings:
 //
 //   loader (1 warp)  cp.async.bulk row segments + the strip's coefficient records  -> stage[2]      (mbarrier tx)
@@ -412,30 +412,103 @@ int launch_ws(const VisFrame* frames, const VisStrip* strips, int n_strips, cons
     return vis::check_launch("vis_preprocess_fused(ws)");
 }
 
+// taps -> class of the general kernel (9+ taps: the scheduled 16-slot kernel or the generic passes)
+inline int kt_class(int kt) { return kt <= 6 ? 6 : kt <= 8 ? 8 : 0; }
+
+inline int span_bytes_for(const int32_t* hbounds, int x0, int x1) {
+    const int px0 = hbounds[2 * x0] & ~15;
+    const int px_last = hbounds[2 * (x1 - 1)] + hbounds[2 * (x1 - 1) + 1] - 1;
+    return align_up((px_last + 1) * 3, 16) - px0 * 3;
+}
+
 }  // namespace
 
-namespace visf {
+extern "C" {
 
-// host hooks used by vis_fused.cu (planning and dispatch)
-int ws_layout_bytes(int span_bytes, int strip_w, int cls) {
-    return make_layout_ws(span_bytes, strip_w, vis_record_stride(cls)).total;
+int vis_fused_kt_class(int kt) { return kt_class(kt); }
+
+int vis_fused_supported(int64_t src_addr, int64_t src_pitch, int src_h, int src_w,
+                        int dst_h, int dst_w, int hkt, int vkt) {
+    if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || dst_h % 28 || dst_w % 28) return VIS_E_UNSUPPORTED;
+    if ((src_addr % 16) || (src_pitch % 16) || src_pitch < (int64_t)src_w * 3) return VIS_E_UNSUPPORTED;
+    if (kt_class(hkt > vkt ? hkt : vkt) == 0) return VIS_E_UNSUPPORTED;
+    if ((int64_t)src_h > 100 * (int64_t)src_w && dst_h < src_h) return VIS_E_UNSUPPORTED;   // vertical-first branch
+    return VIS_OK;
 }
-int ws_smem_max() { return kSmemMax; }
 
-int ws_launch(int cls, const VisFrame* frames, const VisStrip* strips, int n_strips, int span_bytes, int strip_w,
-              const float* lut768, float* pixel_values, cudaStream_t st) {
-    const LayoutWS L = make_layout_ws(span_bytes, strip_w, vis_record_stride(cls));
+int vis_plan_strips_max(int dst_h, int dst_w) {
+    if (dst_h <= 0 || dst_w <= 0) return VIS_E_INVALID;
+    return (dst_w / 28 + 1) * (dst_h / 14 + 1);
+}
+
+// Splits one frame into column strips (width chosen so the CTA fits the two-per-SM shared-memory budget) and
+// `vsplit` row segments.  hbounds: host copy of the horizontal bounds table.  Outputs the widest input span
+// (bytes) and strip width over the emitted strips, which size the launch's shared memory.
+int vis_plan_strips(int frame_index, int dst_h, int dst_w, const int32_t* hbounds, int kt, int vsplit,
+                    VisStrip* strips, int capacity, int* span_bytes_out, int* strip_w_out) {
+    const int cls = kt_class(kt);
+    if (dst_h <= 0 || dst_w <= 0 || dst_h % 28 || dst_w % 28 || !hbounds || !strips || cls == 0 || vsplit < 1) {
+        vis::set_error("vis_plan_strips: bad arguments");
+        return VIS_E_INVALID;
+    }
+    const int hstride = vis_record_stride(cls);
+    const int blocks = dst_w / 28;
+    int best_n = 0;
+    for (int per = kMaxStripW / 28; per >= 1; --per) {       // widest strips that fit the budget
+        const int n = (blocks + per - 1) / per;
+        int worst_span = 0, worst_w = 0;
+        for (int s = 0; s < n; ++s) {
+            const int b0 = (int)((int64_t)blocks * s / n), b1 = (int)((int64_t)blocks * (s + 1) / n);
+            const int span = span_bytes_for(hbounds, b0 * 28, b1 * 28);
+            worst_span = span > worst_span ? span : worst_span;
+            worst_w = (b1 - b0) * 28 > worst_w ? (b1 - b0) * 28 : worst_w;
+        }
+            const bool fits = make_layout_ws(worst_span, worst_w, hstride).total <= kSmemMax;
+        if (fits || per == 1) {
+            best_n = n;
+            *span_bytes_out = worst_span;
+            *strip_w_out = worst_w;
+            break;
+        }
+    }
+    const int prow = dst_h / 14;
+    if (vsplit > prow) vsplit = prow;
+    if (best_n * vsplit > capacity) {
+        vis::set_error("vis_plan_strips: capacity %d < %d", capacity, best_n * vsplit);
+        return VIS_E_CAPACITY;
+    }
+    int n_out = 0;
+    for (int v = 0; v < vsplit; ++v) {
+        const int ya = (int)((int64_t)prow * v / vsplit) * 14, yb = (int)((int64_t)prow * (v + 1) / vsplit) * 14;
+        for (int s = 0; s < best_n; ++s) {
+            VisStrip& o = strips[n_out++];
+            o.frame = frame_index;
+            o.x0 = (int)((int64_t)blocks * s / best_n) * 28;
+            o.x1 = (int)((int64_t)blocks * (s + 1) / best_n) * 28;
+            o.y0 = ya;
+            o.y1 = yb;
+        }
+    }
+    return n_out;
+}
+
+int vis_preprocess_fused(const VisFrame* frames, int n_frames, const VisStrip* strips, int n_strips,
+                         int max_kt, int max_span_bytes, int max_strip_w,
+                         const float* lut768, float* pixel_values, void* stream) {
+    const int cls = kt_class(max_kt);
+    if (!frames || !strips || !lut768 || !pixel_values || n_frames <= 0 || n_strips <= 0 || cls == 0 ||
+        max_span_bytes <= 0 || max_strip_w <= 0 || max_strip_w > kMaxStripW || max_strip_w % 28) {
+        vis::set_error("vis_preprocess_fused: bad arguments (kt=%d span=%d strip_w=%d)", max_kt, max_span_bytes, max_strip_w);
+        return cls == 0 ? VIS_E_UNSUPPORTED : VIS_E_INVALID;
+    }
+    const LayoutWS L = make_layout_ws(max_span_bytes, max_strip_w, vis_record_stride(cls));
     if (L.total > kSmemMax) {
-        vis::set_error("vis_preprocess_fused(ws): %d bytes of shared memory needed", L.total);
+        vis::set_error("vis_preprocess_fused: %d bytes of shared memory needed", L.total);
         return VIS_E_UNSUPPORTED;
     }
-    switch (cls) {
-        case 6: return launch_ws<6, 8, 8>(frames, strips, n_strips, L, lut768, pixel_values, st);
-        case 8: return launch_ws<8, 8, 12>(frames, strips, n_strips, L, lut768, pixel_values, st);
-        default:
-            vis::set_error("vis_preprocess_fused(ws): tap class %d has no warp-specialised instantiation", cls);
-            return VIS_E_UNSUPPORTED;
-    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cls == 6) return launch_ws<6, 8, 8>(frames, strips, n_strips, L, lut768, pixel_values, st);
+    return launch_ws<8, 8, 12>(frames, strips, n_strips, L, lut768, pixel_values, st);
 }
 
-}  // namespace visf
+}  // extern "C"

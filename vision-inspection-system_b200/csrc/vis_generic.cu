@@ -4,10 +4,12 @@
 // normalize+patchify pass, each a separate launch on one image.  They serve
 //   * resize_image / agent thumbnails (LANCZOS, uint8 out) — utils/image_utils.py:75,
 //     src/agents/vlm_inspector.py:64, src/agents/vlm_auditor.py:91;
-//   * geometries the fused kernel (vis_fused.cu) declines: > 16 taps, the tall-image vertical-first
+//   * geometries the fused kernel (vis_fused_sched*.cu, vis_fused_ws.cu) declines: > 16 taps, the tall-image vertical-first
 //     branch (PIL:Image.py:2431-2435), unaligned row pitches.
 // Arithmetic: Pillow ImagingResampleHorizontal_8bpc / ImagingResampleVertical_8bpc — int32 accumulate of
 // uint8 x 22-bit coefficients, +2^21, arithmetic >>22, clamp to 0..255, uint8 between the passes.
+#include <algorithm>
+
 #include "vis_internal.h"
 
 namespace {
@@ -172,6 +174,36 @@ k_alpha(uint8_t* __restrict__ img, int64_t pitch, int h, int w) {
     }
 }
 
+// Row re-pitch: frames whose base or row pitch is not a multiple of 16 bytes (502-pixel rows: 1506 bytes) cannot be
+// staged by the fused kernels' bulk copies; this copies them, a batch per launch, into a staging buffer with an aligned
+// pitch.  thread = 16 destination bytes: the covering aligned source words are funnel-shifted into place, one 16-byte store.
+__global__ void __launch_bounds__(256) k_repitch(const VisRepitch* __restrict__ descs) {
+    const VisRepitch r = descs[blockIdx.y];
+    const int chunks = (r.row_bytes + 15) >> 4;
+    const long long total = (long long)r.rows * chunks;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / chunks), c = (int)(i - (long long)row * chunks);
+        const int n = min(16, r.row_bytes - 16 * c);
+        const uintptr_t a = (uintptr_t)(r.src + (size_t)row * r.src_pitch + 16 * c);
+        const int sh = (int)(a & 3);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(a - sh);
+        const int nwords = (sh + n + 3) >> 2;                   // aligned words holding the n bytes
+        uint32_t v[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) v[q] = q < nwords ? __ldg(w + q) : 0u;
+        uint4 o;
+        o.x = __funnelshift_r(v[0], v[1], 8 * sh); o.y = __funnelshift_r(v[1], v[2], 8 * sh);
+        o.z = __funnelshift_r(v[2], v[3], 8 * sh); o.w = __funnelshift_r(v[3], v[4], 8 * sh);
+        uint8_t* d = r.dst + (size_t)row * r.dst_pitch + 16 * c;
+        if (n == 16) {
+            *reinterpret_cast<uint4*>(d) = o;
+        } else {                                                  // row tail: only the row's own bytes are written
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+            for (int b = 0; b < n; ++b) d[b] = (uint8_t)(ow[b >> 2] >> (8 * (b & 3)));
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -304,6 +336,16 @@ int vis_normalize_patchify(const uint8_t* src, int64_t src_pitch, int h, int w,
     dim3 block(128), grid(n_rows, (VIS_ROW_FLOATS / 4 + 127) / 128);
     k_normalize_patchify<<<grid, block, 0, (cudaStream_t)stream>>>(src, src_pitch, gw, lut768, pixel_values, row0, n_rows);
     return vis::check_launch("vis_normalize_patchify");
+}
+
+int vis_repitch_u8(const VisRepitch* descs, int n, int64_t max_frame_bytes, void* stream) {
+    if (!descs || n <= 0 || n > 65535 || max_frame_bytes <= 0) {
+        vis::set_error("vis_repitch_u8: bad arguments (n=%d)", n);
+        return VIS_E_INVALID;
+    }
+    const int blocks = (int)std::min<int64_t>(1024, (max_frame_bytes / 16 + 255) / 256 + 1);
+    k_repitch<<<dim3(blocks, n), 256, 0, (cudaStream_t)stream>>>(descs);
+    return vis::check_launch("vis_repitch_u8");
 }
 
 }  // extern "C"

@@ -83,6 +83,13 @@ int vis_abi_version(void) { return VIS_B200_ABI_VERSION; }
 
 const char* vis_last_error(void) { return g_err; }
 
+#ifndef VIS_SOURCE_HASH_VALUE
+#define VIS_SOURCE_HASH_VALUE "unstamped-build!"
+#endif
+// the marker is what build.py greps in the binary to decide whether it is up to date (content, not mtimes)
+static const char g_source_hash[] = "VIS_SOURCE_HASH=" VIS_SOURCE_HASH_VALUE;
+const char* vis_source_hash(void) { return g_source_hash + 16; }
+
 int vis_coeff_ksize(int in_size, int out_size, int filter) {
     FilterDef f;
     if (in_size <= 0 || out_size <= 0 || !filter_def(filter, &f)) {

@@ -202,7 +202,8 @@ const char* glyph_for(unsigned char ch) {
     "KYPBSETHTJSMQOQPURQTQUSWTZT\\S_Pb",  /* } */
     "F^IUISJPLONOPPTSVTXTZS[Q ISJQLPNPPQTTVUXUZT[Q[O",  /* ~ */
     };
-    return (ch >= 32 && ch <= 126) ? glyphs[ch - 32] : nullptr;
+    // cv: readCheck() — with FONT_HERSHEY_SIMPLEX every byte outside 32..126 (UTF-8 continuation bytes included) is '?'
+    return glyphs[(ch >= 32 && ch <= 126) ? ch - 32 : '?' - 32];
 }
 
 class Emitter {
@@ -700,7 +701,7 @@ struct Template {
     int ox = 0, oy = 0;              // canvas position of the anchor (marker centre / dash start)
     int ex = 0, ey = 0;              // marker: half extents (pixels) the instance must have free around its centre
     int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1;   // union of the leaf boxes on the canvas
-    bool ok = true;                  // false: a label glyph outside printable ASCII
+    bool ok = true;                  // false: no template (a label too wide for a private canvas)
     void bound() {
         bx0 = by0 = INT_MAX; bx1 = by1 = INT_MIN;
         for (const VisLeaf& l : leaves) {
@@ -720,7 +721,7 @@ struct TemplateCache {
     }
 };
 
-struct MarkerSpec { int radius; uint8_t b, g, r; char label[13]; uint8_t alpha; };
+struct MarkerSpec { int radius; uint8_t b, g, r; const char* label; uint8_t alpha; };
 struct DashSpec { int dx, dy, thickness, line_type; uint8_t b, g, r; };
 
 Template build_marker(const void* arg) {
@@ -732,10 +733,12 @@ Template build_marker(const void* arg) {
     int lw = 0, lh = 0;
     {
         Emitter probe(1, 1, nullptr, 0);
-        if (!probe.text_size(m.label, fs, tt, &lw, &lh)) { t.ok = false; return t; }
+        probe.text_size(m.label, fs, tt, &lw, &lh);
     }
     t.ex = std::max(m.radius + 4, lw / 2 + tt + 8);
     t.ey = std::max(m.radius + 4, lh + tt + 8);
+    if (t.ex > 8000 || t.ey > 8000) { t.ok = false; return t; }      // a label wider than any frame it could sit in whole:
+                                                                      // no template, the caller expands (and clips) in place
     const int pad = 8, cxc = t.ex + pad, cyc = t.ey + pad;           // nothing comes near the canvas border
     t.ox = cxc; t.oy = cyc;
     std::vector<VisLeaf> buf(4096);
@@ -786,11 +789,11 @@ thread_local const VisSprite* g_sprites = nullptr;
 thread_local int g_n_sprites = 0;
 
 const VisSprite* find_stamp(int dx, int dy) {
-    char key[12];
+    char key[24];
     std::snprintf(key, sizeof key, "%d,%d", dx, dy);
     for (int i = 0; i < g_n_sprites; ++i) {
         const VisSprite& s = g_sprites[i];
-        if (s.radius == -1 && s.pixels && std::strncmp(s.label, key, 12) == 0) return &s;
+        if (s.radius == -1 && s.pixels && s.label && std::strcmp(s.label, key) == 0) return &s;
     }
     return nullptr;
 }
@@ -798,7 +801,7 @@ const VisSprite* find_stamp(int dx, int dy) {
 const VisSprite* find_sprite(int radius, const VisBox& b, const char* label) {
     for (int i = 0; i < g_n_sprites; ++i) {
         const VisSprite& s = g_sprites[i];
-        if (s.radius == radius && s.b == b.b && s.g == b.g && s.r == b.r && s.pixels && std::strncmp(s.label, label, 12) == 0)
+        if (s.radius == radius && s.b == b.b && s.g == b.g && s.r == b.r && s.pixels && s.label && std::strcmp(s.label, label) == 0)
             return &s;
     }
     return nullptr;
@@ -864,19 +867,12 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
         // disc, ring and label (:299-313): an instance of the marker template when the ring and the label stay clear of
         // the image border (the usual case: the centre is clamped radius + 5 away from it and '#<n>' fits the ring);
         // expanded in place otherwise (wide free-text labels near an edge, images smaller than the marker)
-        char label[13];
-        std::memcpy(label, b.label, 12);
-        label[12] = 0;
-        MarkerSpec m{radius, b.b, b.g, b.r, {0}, 0};
-        std::memcpy(m.label, label, 13);
+        const char* label = b.label ? b.label : "";                  // any length, any bytes (cv2.putText draws them all)
+        MarkerSpec m{radius, b.b, b.g, b.r, label, 0};
         char key[64];
         std::snprintf(key, sizeof key, "m%d,%d,%d,%d,", radius, b.b, b.g, b.r);
         const Template& t = g_templates.get(std::string(key) + label, build_marker, &m);
-        if (!t.ok) {
-            vis::set_error("vis_overlay_expand: label '%s' has a character outside printable ASCII", label);
-            return VIS_E_UNSUPPORTED;
-        }
-        if (cx - t.ex >= 0 && cy - t.ey >= 0 && cx + t.ex < img_w && cy + t.ey < img_h) {
+        if (t.ok && cx - t.ex >= 0 && cy - t.ey >= 0 && cx + t.ex < img_w && cy + t.ey < img_h) {
             const VisSprite* sp = find_sprite(radius, b, label);
             if (sp && sp->w == 2 * t.ox + 1 && sp->h == 2 * t.oy + 1 && sp->ox == t.ox && sp->oy == t.oy)
                 em.sprite(*sp, cx, cy);                  // rasterised once on the device: one leaf
@@ -890,10 +886,7 @@ extern "C" int vis_overlay_expand(int img_h, int img_w, const VisBox* boxes, int
             const double font_scale = radius / 20.0 * 0.7;
             const int text_thickness = std::max(2, (int)(font_scale * 2));
             int tw = 0, th = 0;
-            if (!em.text_size(label, font_scale, text_thickness, &tw, &th)) {
-                vis::set_error("vis_overlay_expand: label '%s' has a character outside printable ASCII", label);
-                return VIS_E_UNSUPPORTED;
-            }
+            em.text_size(label, font_scale, text_thickness, &tw, &th);
             em.set_color(0, 0, 0);
             em.put_text(label, (int)(cx - tw / 2.0), (int)(cy + th / 2.0), font_scale, text_thickness);
         }
@@ -953,11 +946,9 @@ extern "C" int vis_draw_expand(int img_h, int img_w, const VisDrawCmd* cmds, int
                 else em.circle_outline(c.x1, c.y1, c.x2, c.thickness);
                 break;
             case VIS_DRAW_TEXT: {
-                char text[65];
-                std::memcpy(text, c.text, 64);
-                text[64] = 0;
+                const char* text = c.text ? c.text : "";
                 int tw = 0, th = 0;
-                if (c.thickness < 1 || c.thickness > 255 || !(c.font_scale > 0)) goto bad;
+                if (c.thickness < 2 || c.thickness > 255 || !(c.font_scale > 0)) goto bad;   // 1-px strokes are not pinned against cv2 (the reference never draws them)
                 if (!em.text_size(text, c.font_scale, c.thickness, &tw, &th)) {
                     vis::set_error("vis_draw_expand: text '%s' has a character outside printable ASCII", text);
                     return VIS_E_UNSUPPORTED;
@@ -990,11 +981,10 @@ extern "C" int vis_overlay_sprite_expand(int radius, int b, int g, int r, const 
         vis::set_error("vis_overlay_sprite_expand: bad arguments (radius %d)", radius);
         return VIS_E_INVALID;
     }
-    MarkerSpec m{radius, (uint8_t)b, (uint8_t)g, (uint8_t)r, {0}, 255};
-    std::strncpy(m.label, label, 12);
+    MarkerSpec m{radius, (uint8_t)b, (uint8_t)g, (uint8_t)r, label, 255};
     const Template t = build_marker(&m);
     if (!t.ok) {
-        vis::set_error("vis_overlay_sprite_expand: label '%s' has a character outside printable ASCII", m.label);
+        vis::set_error("vis_overlay_sprite_expand: the label is too wide for a sprite (it is expanded in place instead)");
         return VIS_E_UNSUPPORTED;
     }
     *w = 2 * t.ox + 1; *h = 2 * t.oy + 1; *ox = t.ox; *oy = t.oy;

@@ -6,6 +6,8 @@ process/GPU.  No CPU fallback: constructing an Engine without CUDA raises.
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import threading
 from dataclasses import dataclass
 
 import numpy as np
@@ -28,7 +30,7 @@ class _Geometry:
     src_w: int
     dst_h: int
     dst_w: int
-    kt: int                      # fused tap class, 0 = generic only
+    kt: int                      # tap class of the general fused kernel (6 / 8); 0: scheduled kernel or generic passes only
     hrec: torch.Tensor | None
     vrec: torch.Tensor | None
     htable: T.CoeffTable
@@ -82,6 +84,8 @@ class Engine:
         self._staging: dict = {}
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.last_launches = 0           # kernels launched by the most recent public call
+        self._lock = threading.RLock()   # public entry points are serialised: caches and staging buffers are shared
+        self._tls = threading.local()    # per-thread state (nvJPEG handles are not thread-safe)
 
     # ------------------------------------------------------------------ tables
     def _device_table(self, in_size: int, out_size: int, filt: int):
@@ -99,9 +103,7 @@ class Engine:
         if g is None:
             ht = T.coeff_table(src_w, dst_w, N.FILTER_BICUBIC)
             vt = T.coeff_table(src_h, dst_h, N.FILTER_BICUBIC)
-            kt = T.kt_class(max(ht.max_taps, vt.max_taps))
-            if G.pil_pass_order(src_h, src_w, dst_h, dst_w) == "vh":
-                kt = 0
+            kt = T.kt_class(max(ht.max_taps, vt.max_taps))     # class of the GENERAL fused kernel (6 / 8), 0 beyond
             hrec = vrec = None
             if kt:
                 hrec = torch.from_numpy(T.pack_records(ht, kt)).to(self.device)
@@ -456,17 +458,16 @@ class Engine:
         plan = BatchPlan(total, torch.tensor(grids, dtype=torch.int64), [], [])
         groups: dict = {}
         for i, g in enumerate(geoms):
-            fused = (not force_generic) and g.kt and self.L.vis_fused_supported(
-                int(ptrs[i]), int(pitches[i]), g.src_h, g.src_w, g.dst_h, g.dst_w,
-                g.htable.max_taps, g.vtable.max_taps) == N.VIS_OK
-            if fused:
-                groups.setdefault((g.kt, id(g)), (g, []))[1].append(i)
+            # the fused kernels stage rows with bulk copies: 16-byte aligned base and pitch, horizontal pass first
+            aligned = ptrs[i] % 16 == 0 and pitches[i] % 16 == 0 and pitches[i] >= g.src_w * 3
+            if not force_generic and aligned and G.pil_pass_order(g.src_h, g.src_w, g.dst_h, g.dst_w) != "vh":
+                groups.setdefault(id(g), (g, []))[1].append(i)
             else:
                 plan.generic.append((i, g, int(row0[i])))
         want = 3 * self.sm_count                     # work items wanted: a few per SM
-        # statically scheduled kernel: one launch per (geometry, pitch) group it accepts
+        # statically scheduled kernels (8-slot: <= 8 taps, 16-slot: 9..32 taps): one launch per (geometry, pitch)
         by_class: dict = {}
-        for (kt, _), (g, idx) in groups.items():
+        for g, idx in groups.values():
             idx = np.asarray(idx)
             rest = idx
             if path != "general":
@@ -480,6 +481,8 @@ class Engine:
                     per = int(np.frombuffer(head[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["n_strips"])
                     segs = vsplit if vsplit is not None else self._pick_segs(len(sel) * per, g.src_h, g.dst_h // 28)
                     sched = self._sched(g, int(pitch), max(1, min(segs, g.dst_h // 14)))
+                    if sched is None:                # every segment adds chunk-rounded mask bytes: the multi-segment
+                        sched = head                 # schedule may not fit where the one-segment schedule did
                     hd = np.frombuffer(sched[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]
                     ref = np.zeros(len(sel), N.FRAME_REF_DTYPE)
                     ref["src"], ref["row0"] = ptrs[sel].astype(np.uint64), row0[sel]
@@ -487,8 +490,10 @@ class Engine:
                         sched, len(sel), len(sel) * int(hd["n_strips"]) * int(hd["n_segs"]),
                         torch.from_numpy(ref.view(np.uint8).copy()).to(self.device), g.srec[0], g.srec[1]))
                 rest = np.concatenate(rest_parts) if rest_parts else np.zeros(0, np.int64)
-            if len(rest):
-                by_class.setdefault(kt, []).append((g, rest))
+            if len(rest) and g.kt:
+                by_class.setdefault(g.kt, []).append((g, rest))
+            else:                                    # 9+ taps the schedule declined: generic passes
+                plan.generic.extend((int(i), g, int(row0[i])) for i in rest)
         # general kernel: one launch per tap class; all geometries of a class share it
         for kt, members in by_class.items():
             n_class = sum(len(idx) for _, idx in members)
@@ -531,6 +536,7 @@ class Engine:
         """
         if path not in ("auto", "general"):
             raise ValueError("path must be 'auto' or 'general'")
+        self._align_launches = 0
         if not force_generic:
             if isinstance(frames, torch.Tensor) and frames.dim() == 4:
                 if frames.is_cuda and (frames.stride(1) % 16 or frames.stride(0) % 16 or frames.data_ptr() % 16):
@@ -544,7 +550,7 @@ class Engine:
               or not out.is_contiguous() or out.device != self.device):
             raise ValueError(f"out must be a contiguous float32 [{plan.total_rows}, {G.ROW_FLOATS}] tensor on {self.device}")
         sp = _stream_ptr()
-        launches = 0
+        launches = self._align_launches
         flist = frames if plan.generic else None      # indexable either way ([B,H,W,3] tensor or list)
         for i, g, r0 in plan.generic:
             resized = self.resize_u8(flist[i], g.dst_h, g.dst_w, N.FILTER_BICUBIC)
@@ -568,8 +574,8 @@ class Engine:
 
     def _align_frames(self, frames: list) -> list:
         """Frames whose base or row pitch is not a multiple of 16 bytes (e.g. 502-pixel-wide rows) cannot be staged with
-        bulk copies; they are repacked, per shape, into a cached staging tensor with a padded pitch (two device copies
-        per shape) so that they take the fused kernels like everything else."""
+        bulk copies; all of them are repacked by ONE ``vis_repitch_u8`` launch into cached staging tensors with a padded
+        pitch (one per shape) so that they take the fused kernels like everything else."""
         groups: dict = {}
         for i, f in enumerate(frames):
             if (isinstance(f, torch.Tensor) and f.is_cuda and f.dtype == torch.uint8 and f.dim() == 3 and f.shape[2] == 3
@@ -578,17 +584,26 @@ class Engine:
         if not groups:
             return frames
         frames = list(frames)
+        n = sum(len(idx) for idx in groups.values())
+        desc = np.zeros(n, N.REPITCH_DTYPE)
+        k, biggest, sources = 0, 0, []
         for (h, w), idx in groups.items():
             pitch = (w * 3 + 15) // 16 * 16
             key = ("align", h, w, len(idx))
             buf = self._staging.get(key)
             if buf is None:
                 buf = self._staging[key] = torch.zeros((len(idx), h, pitch), dtype=torch.uint8, device=self.device)
-            src = torch.stack([frames[i].reshape(h, w * 3) if frames[i].is_contiguous() else frames[i].contiguous().view(h, w * 3)
-                               for i in idx])
-            buf[:, :, :w * 3].copy_(src)
-            for k, i in enumerate(idx):
-                frames[i] = buf[k].as_strided((h, w, 3), (pitch, 3, 1))
+            biggest = max(biggest, h * pitch)
+            for j, i in enumerate(idx):
+                f = frames[i]
+                desc[k] = (f.data_ptr(), buf[j].data_ptr(), f.stride(0), pitch, h, w * 3)
+                sources.append(f)
+                frames[i] = buf[j].as_strided((h, w, 3), (pitch, 3, 1))
+                k += 1
+        d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.device)
+        N.check(self.L.vis_repitch_u8(d_desc.data_ptr(), n, biggest, _stream_ptr()), "vis_repitch_u8")
+        self._keepalive_a = (d_desc, sources)
+        self._align_launches = 1
         return frames
 
     def preprocess_host(self, host_frames: torch.Tensor, min_pixels: int = G.DEFAULT_MIN_PIXELS,
@@ -642,9 +657,15 @@ class Engine:
     def _marker_sprite(self, radius: int, b: int, g: int, r: int, label: bytes):
         """The marker of (radius, colour, label) rasterised once ON THE DEVICE: its leaves (alpha 255) drawn by the overlay
         kernel on a zeroed BGRA canvas.  Returns (canvas tensor, w, h, ox, oy); cached per engine."""
-        return self._render_template(("marker", radius, b, g, r, label), 4,
-                                     lambda *a: self.L.vis_overlay_sprite_expand(radius, b, g, r, label, *a),
-                                     "vis_overlay_sprite_expand")
+        try:
+            return self._render_template(("marker", radius, b, g, r, label), 4,
+                                         lambda *a: self.L.vis_overlay_sprite_expand(radius, b, g, r, label, *a),
+                                         "vis_overlay_sprite_expand")
+        except N.VisError as e:
+            if e.code != N.VIS_E_UNSUPPORTED:         # a label wider than any private canvas: expanded in place instead
+                raise
+            self.__dict__.setdefault("_sprites", {})[("marker", radius, b, g, r, label)] = None
+            return None
 
     def _dash_stamp(self, dx: int, dy: int):
         """The blend chains of the dash (0,0)-(dx,dy) recorded once ON THE DEVICE (record mode of the overlay kernel: 8
@@ -680,10 +701,13 @@ class Engine:
         d = [up(desc), up(tl), up(np.ascontiguousarray(refs)), up(leaves)]
         N.check(self.L.vis_overlay_draw_cn(d[0].data_ptr(), 1, channels, 0, d[1].data_ptr(), len(tl), d[2].data_ptr(),
                                            d[3].data_ptr(), _stream_ptr()), "vis_overlay_draw_cn")
-        torch.cuda.current_stream(self.device).synchronize()          # the upload tensors may go; the canvas stays
         hit = (canvas, w.value, h.value, ox.value, oy.value)
-        if channels == 8 and bool((canvas[:, :, 0] & 0x40).any()):    # a blend chain overflowed: this dash stays leaves
-            hit = None
+        if channels == 8:
+            # a blend chain that overflowed its seven slots (flag 0x40 in byte 0 of the record) means this dash stays
+            # leaves: checked on the host from a copy of the (at most ~1 KB) record canvas — once per dash geometry per engine
+            if (canvas.cpu().numpy()[:, :, 0] & 0x40).any():
+                hit = None
+        # (no synchronisation: the upload tensors go back to torch's stream-ordered allocator, the canvas stays)
         if len(cache) >= 4096:
             cache.clear()
         cache[key] = hit
@@ -710,14 +734,17 @@ class Engine:
         for (h, w), px in zip(shapes, px_all):
             if len(px):
                 radius = max(25, min(int(max(w, h) * 0.04), 60))
-                keys.update((radius, int(p["b"]), int(p["g"]), int(p["r"]), bytes(p["label"])) for p in px)
+                keys.update((radius, int(p["b"]), int(p["g"]), int(p["r"]), O.box_label(p)) for p in px)
         # dashes (confidence == "low") are 10 px long, the last one of an edge 1..9: one recorded stamp per length and
         # orientation, shared by every colour
         dashes = [(L, 0) for L in range(1, 11)] + [(0, L) for L in range(1, 11)] if any(
             len(px) and bool(px["dashed"].any()) for px in px_all) else []
         entries, keep_sprites = [], []
         for key in sorted(keys):
-            canvas, sw, sh, sox, soy = self._marker_sprite(*key)
+            hit = self._marker_sprite(*key)
+            if hit is None:
+                continue
+            canvas, sw, sh, sox, soy = hit
             keep_sprites.append(canvas)
             entries.append((key[0], key[1], key[2], key[3], 0, key[4], canvas.data_ptr(), sw, sh, sox, soy))
         for dx, dy in dashes:
@@ -725,9 +752,7 @@ class Engine:
             if hit is not None:
                 keep_sprites.append(hit[0])
                 entries.append((-1, 0, 0, 0, 0, f"{dx},{dy}".encode(), hit[0].data_ptr(), hit[1], hit[2], hit[3], hit[4]))
-        sprites = np.zeros(max(1, len(entries)), N.SPRITE_DTYPE)
-        for i, e in enumerate(entries):
-            sprites[i] = e
+        sprites = N.host_records(entries, N.SPRITE_DTYPE, "label") if entries else np.zeros(1, N.SPRITE_DTYPE)
         box_begin = np.asarray(box_begin, np.int32)
         n = len(shapes)
         leaf_begin = np.zeros(n + 1, np.int32)
@@ -853,7 +878,7 @@ class Engine:
         h, w, cn = int(canvas.shape[0]), int(canvas.shape[1]), int(canvas.shape[2])
         up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
         cache = self.__dict__.setdefault("_draw_plans", {})
-        key = (h, w, cmds.tobytes())
+        key = (h, w, CP.commands_key(cmds))
         plan = cache.get(key)
         if plan is None:
             leaves = CP.expand_commands(cmds, w, h)
@@ -939,8 +964,8 @@ class Engine:
         """The engine's nvJPEG codec for ``backend`` (created on first use; chroma upsampling interpolated, the closest
         match to libjpeg-turbo).  Tolerance-specified against the host decoders: see ``jpeg.py``."""
         from .jpeg import JpegCodec
-        cache = self.__dict__.setdefault("_jpeg", {})
-        if backend not in cache:
+        cache = self._tls.__dict__.setdefault("jpeg", {})      # one codec per THREAD and backend (Streamlit sessions
+        if backend not in cache:                               # run on separate threads; a VisJpeg handle must not be shared)
             cache[backend] = JpegCodec(self.device, backend, True)
         return cache[backend]
 
@@ -996,7 +1021,24 @@ class Engine:
             raise ValueError(f"tensor on {t.device}, engine on {self.device}")
 
 
+def _locked(fn):
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with self._lock:
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+# The engine is shared process-wide (get_engine) and the reference's callers may sit on several threads (Streamlit runs
+# one script thread per session): every public entry point holds the engine's lock while it plans and enqueues.
+for _name in ("resize_batch_u8", "resize_u8", "reduce_u8", "resize_box_u8", "alpha_premultiply_", "resize_nearest_u8",
+              "resize_reducing_u8", "agent_inputs", "plan_batch", "preprocess", "preprocess_host", "plan_overlay", "annotate",
+              "heatmap", "side_by_side", "status_stamp", "quality_stats"):
+    setattr(Engine, _name, _locked(getattr(Engine, _name)))
+del _name
+
 _engines: dict = {}
+_engines_lock = threading.Lock()
 
 
 def get_engine(device=None) -> Engine:
@@ -1006,7 +1048,8 @@ def get_engine(device=None) -> Engine:
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
-    e = _engines.get(dev)
-    if e is None:
-        e = _engines[dev] = Engine(dev)
+    with _engines_lock:
+        e = _engines.get(dev)
+        if e is None:
+            e = _engines[dev] = Engine(dev)
     return e

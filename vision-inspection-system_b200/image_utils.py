@@ -116,12 +116,14 @@ def _imread_cuda(path, codec: str, bgr: bool = True):
     import torch
     _check_codec(codec)
     if codec == "nvjpeg":
-        from .jpeg import is_jpeg
+        from .jpeg import exif_orientation, is_jpeg
         try:
             data = Path(path).read_bytes()
         except OSError:
             return None
-        if is_jpeg(data):
+        # cv2.imread rotates by the EXIF Orientation tag, nvJPEG does not: such files (phone cameras) keep the host
+        # decoder so that percent boxes land on the same pixels as in the reference
+        if is_jpeg(data) and exif_orientation(data) == 1:
             try:
                 return _engine().jpeg_codec().decode(data, bgr=bgr)
             except Exception as e:          # CMYK, arithmetic coding, damaged stream: let the host decoder decide

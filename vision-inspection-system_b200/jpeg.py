@@ -26,6 +26,41 @@ def is_jpeg(data: bytes) -> bool:
     return len(data) > 3 and data[0] == 0xFF and data[1] == 0xD8 and data[2] == 0xFF
 
 
+def exif_orientation(data: bytes) -> int:
+    """The EXIF Orientation tag (1..8) of a JPEG stream, 1 when absent or unreadable.  ``cv2.imread`` applies it by
+    default (utils/image_utils.py:170, :347, :629 in the reference go through cv2.imread); nvJPEG and PIL do not."""
+    import struct
+    pos, n = 2, len(data)
+    while pos + 4 <= n and data[pos] == 0xFF:
+        marker = data[pos + 1]
+        if marker in (0xD8, 0x01) or 0xD0 <= marker <= 0xD7:          # markers without a length
+            pos += 2
+            continue
+        if marker == 0xDA or marker == 0xD9:                          # start of scan / end of image: no EXIF ahead
+            break
+        seg_len = struct.unpack(">H", data[pos + 2:pos + 4])[0]
+        if marker == 0xE1 and data[pos + 4:pos + 10] == b"Exif\0\0":
+            tiff = data[pos + 10:pos + 2 + seg_len]
+            if len(tiff) < 8 or tiff[:2] not in (b"II", b"MM"):
+                return 1
+            e = "<" if tiff[:2] == b"II" else ">"
+            ifd = struct.unpack(e + "I", tiff[4:8])[0]
+            if ifd + 2 > len(tiff):
+                return 1
+            count = struct.unpack(e + "H", tiff[ifd:ifd + 2])[0]
+            for i in range(count):
+                ent = tiff[ifd + 2 + 12 * i:ifd + 14 + 12 * i]
+                if len(ent) < 12:
+                    return 1
+                tag, typ = struct.unpack(e + "HH", ent[:4])
+                if tag == 0x0112:
+                    v = struct.unpack(e + "H", ent[8:10])[0] if typ == 3 else struct.unpack(e + "I", ent[8:12])[0]
+                    return v if 1 <= v <= 8 else 1
+            return 1
+        pos += 2 + seg_len
+    return 1
+
+
 class JpegCodec:
     """One nvJPEG handle on one device (not thread-safe: one codec per thread of use)."""
 

@@ -36,7 +36,8 @@ def filter_by_confidence(boxes, confidence_threshold: str = "low", criticality: 
 
 def boxes_to_pixels(boxes, img_width: int, img_height: int, confidence_threshold: str = "low",
                     criticality: str = "medium") -> np.ndarray:
-    """Percent boxes -> ``VisBox`` records, skipping (with a warning) exactly the boxes the reference skips."""
+    """Percent boxes -> ``VisBox`` records, skipping (with a warning) exactly the boxes the reference skips.  Like
+    the reference (utils/image_utils.py:192-313) this never raises on the content of a box: labels may be any text."""
     out = []
     for i, box in enumerate(filter_by_confidence(boxes, confidence_threshold, criticality)):
         raw_x, raw_y = box.get("x", 0), box.get("y", 0)
@@ -72,14 +73,14 @@ def boxes_to_pixels(boxes, img_width: int, img_height: int, confidence_threshold
             label_text = str(i + 1)
         color = _COSMETIC_BGR if box.get("severity", "MODERATE") == "COSMETIC" else _RED_BGR
         dashed = box.get("confidence", "medium") == "low"
-        encoded = label_text.encode("latin-1", "replace")
-        if len(encoded) > 11:
-            raise ValueError(f"overlay label too long (max 11 characters): {label_text!r}")
-        out.append((x, y, w, h, color[0], color[1], color[2], 1 if dashed else 0, encoded))
-    arr = np.zeros(len(out), N.BOX_DTYPE)
-    for j, rec in enumerate(out):
-        arr[j] = rec
-    return arr
+        # any text, any length: cv2.putText receives the UTF-8 bytes and draws '?' for every byte outside 32..126
+        out.append((x, y, w, h, color[0], color[1], color[2], 1 if dashed else 0, N.cv_text(label_text)))
+    return N.host_records(out, N.BOX_DTYPE, "label")
+
+
+def box_label(rec) -> bytes:
+    """The label bytes of one ``VisBox`` record."""
+    return N.record_string(rec, "label")
 
 
 _tls = threading.local()
