@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """bench.py — images/s for 1080p -> Qwen2-VL pixel_values (+ % of the HBM roofline) at N GPUs of one box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--legs all|headline]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of 256 synthetic 1920x1080 RGB frames per GPU
 (BASELINE.json configs[1]); batches shard by image across ranks with no collective (weak scaling).
 Prints ONE JSON line on rank 0:
-  value        whole-job images/s with the frames already resident in HBM (CUDA events, max over ranks)
-  e2e          same metric through the public host-buffer API: pinned host frames -> device pixel_values,
-               H2D copies inside the timed region, plus a small result read-back (see DESIGN.md "Measurement")
-  roofline     algorithmic HBM bytes of the fused kernel / its measured duration vs the measured copy peak
-  cpu_baseline the reference CPU path (transformers Qwen2VLImageProcessorPil) timed on this box's host cores
+  value         whole-job images/s with the frames already resident in HBM (CUDA events, max over ranks): the headline
+  sustained     the same launch repeated back to back for >= 3 s, with the median SM clock seen during it
+  e2e           same metric through the public host-buffer API: pinned host frames -> device pixel_values, H2D copies
+                inside the timed region, plus a small result read-back (the consumer is the vision tower on the GPU)
+  e2e_full_readback   ... with the WHOLE pixel_values tensor copied back to pinned host memory as well (full duplex)
+  e2e_jpeg      ... with the frames crossing PCIe as JPEG streams and decoded on the GPU (nvJPEG)
+  configs       every other BASELINE.json config (4K at both max_pixels, overlay, mixed dual stream, thumbnails), each
+                with its own algorithmic bytes, roofline fraction and clock sample
+  roofline      algorithmic HBM bytes of the fused kernel / its measured duration vs the measured copy peak
+  cpu_baseline  the reference CPU path (transformers Qwen2VLImageProcessorPil) timed on this box's host cores
 `--impl reference` times only that CPU path, with every host core, on the same workload definition.
+Every device timing uses a CACHED batch plan (host planning happens in the warm-up, as in a streaming loop that
+refills the same staging buffers): `plan_cached` says so in the line.
 """
 from __future__ import annotations
 
 import argparse
+import io
 import json
+import math
 import os
 import subprocess
 import sys
@@ -37,6 +46,7 @@ ROWS = (DST_H // 14) * (DST_W // 14)           # 4888 patch rows per frame
 BYTES_PER_IMAGE = H * W * 3 + ROWS * 1176 * 4  # algorithmic HBM bytes: uint8 read + fp32 write = 29 213 952
 METRIC = "images/s 1080p->Qwen2-VL pixel_values"
 WORKLOAD = "256 synthetic 1920x1080 RGB frames per GPU -> Qwen2-VL pixel_values (min_pixels 3136, max_pixels 1003520)"
+INT_MAC_LANES_PER_CLK_PER_SM = 62.0            # measured IMAD / IDP.4A issue rate (profiles/r02_ubench_pipes.jsonl)
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
@@ -125,50 +135,69 @@ def cpu_model() -> str:
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms for the whole run, each sample stamped on receipt, so
+    that every leg reports the clocks seen during ITS timed region (`window`)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
-        self.lines = []
+        self.samples = []           # (t, sm_mhz, max_mhz, power_w, [reasons])
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
+            t = time.time()
+            parts = [p.strip() for p in line.strip().split(",")]
             if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                sm, mx = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            try:
+                power = float(parts[3])
+            except ValueError:
+                power = None
+            reasons = [name for name, val in zip(self.NAMES, parts[5:9]) if val.lower().startswith("active")]
+            self.samples.append((t, sm, mx, power, reasons))
+
+    def window(self, t0: float, t1: float, pad: float = 0.0) -> dict:
+        """clocks seen in [t0, t1] (wall clock); a leg shorter than the sampling period borrows the nearest sample"""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        if t1 - t0 < 0.35:
+            time.sleep(0.12)
+        rows = [s for s in self.samples if t0 - pad <= s[0] <= t1 + pad]
+        borrowed = False
+        if not rows and self.samples:
+            mid = 0.5 * (t0 + t1)
+            rows, borrowed = [min(self.samples, key=lambda s: abs(s[0] - mid))], True
+        sm = [r[1] for r in rows]
+        reasons = sorted({x for r in rows for x in r[4]})
+        power = [r[3] for r in rows if r[3] is not None]
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+               "sm_max_mhz": max(r[2] for r in rows) if rows else None, "power_w_max": max(power) if power else None,
+               "reasons": reasons, "samples": len(rows)}
+        if borrowed:
+            out["note"] = "leg shorter than the 100 ms sampling period: nearest sample"
+        return out
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
 
 
 # ------------------------------------------------------------------------------------------ main
@@ -183,7 +212,7 @@ _REAL_STDOUT = 1
 def bind_to_gpu_numa_node(local_rank: int):
     """One process per GPU on a two-socket box: run this rank (and first-touch its pinned staging buffers) on the CPUs
     NVML names as local to its GPU, so that every rank's host->device copies leave through its own socket instead of
-    all of them crossing to the socket the launcher happened to start on.  Only the `e2e` leg moves host data; the
+    all of them crossing to the socket the launcher happened to start on.  Only the `e2e` legs move host data; the
     device-resident `value` is unaffected.  Returns the CPU count bound to, or None when NVML cannot say."""
     try:
         import pynvml
@@ -200,6 +229,15 @@ def bind_to_gpu_numa_node(local_rank: int):
     return None
 
 
+def resample_macs(src_h, src_w, dst_h, dst_w, filt) -> int:
+    """integer multiply-accumulates of one Pillow 8bpc two-pass resample (3 channels): the compute side of the roofline"""
+    from vision_inspection_system_b200 import tables as T
+    ht, vt = T.coeff_table(src_w, dst_w, filt), T.coeff_table(src_h, dst_h, filt)
+    h_macs = int(ht.bounds[:, 1].sum()) * src_h * 3 if dst_w != src_w else 0
+    v_macs = int(vt.bounds[:, 1].sum()) * dst_w * 3 if dst_h != src_h else 0
+    return h_macs + v_macs
+
+
 def main():
     global _REAL_STDOUT
     # keep stdout clean for the driver: everything any library prints to fd 1 goes to stderr instead
@@ -214,6 +252,9 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step (default 256 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=0, help="size of the bounded CPU sample (0 = calibrated to ~15 s)")
+    ap.add_argument("--legs", choices=["all", "headline"], default="all",
+                    help="headline: value + e2e only; all: also sustained, e2e_full_readback, e2e_jpeg and every other config")
+    ap.add_argument("--sustain-s", type=float, default=3.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -245,8 +286,9 @@ def main():
         line = {"metric": METRIC, "value": v, "unit": "images/s", "n_gpus": n_gpus, "steps": steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8->int32 fixed point->f32", "data": "synthetic", "impl": "reference",
-                "config": dict(config, frames_per_step=n),
+                "config": config,                      # the SAME config object as our arm (the step is a bounded sample of it)
                 "cpu_baseline": {"value": v, "unit": "images/s", "cores": arm.cores, "kind": arm.kind,
+                                 "frames_per_step": n,
                                  "sample": f"{n} seeded 1080p noise frames per step x {steps} steps over {arm.cores} "
                                            f"forked workers (one thread each), {total:.1f} s, on {cpu_model()}"},
                 "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -274,6 +316,9 @@ def main():
                                   f"{dt:.1f} s, on {cpu_model()} ({cores} logical cores)"}
 
     import torch
+    from vision_inspection_system_b200 import _native as N
+    from vision_inspection_system_b200 import geometry as G
+    from vision_inspection_system_b200 import sharding as S
     from vision_inspection_system_b200 import synth
     from vision_inspection_system_b200.engine import get_engine
 
@@ -286,6 +331,16 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = get_engine()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
 
     # ---------------- inputs: seeded noise, distinct per rank, resident in HBM ----------------
     distinct = min(args.batch, 32)
@@ -302,32 +357,84 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """ms for `steps` calls: barrier + synchronize on both sides, CUDA events, MAX over ranks; also the wall window"""
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t0 = time.time()
         start.record()
         for _ in range(steps):
             fn()
         end.record()
         barrier()
+        t1 = time.time()
         ms = start.elapsed_time(end)
         if dist is not None:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+        return ms, (t0, t1)
 
-    # ---------------- device-resident throughput ----------------
+    def clocks_of(win):
+        return sampler.window(*win) if rank == 0 else None
+
+    def all_ok(flag: bool) -> bool:
+        """True iff `flag` holds on EVERY rank (a leg one rank cannot run is skipped by all: the timed loops hold barriers)"""
+        if dist is None:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def leg(fn, units_per_call, bytes_per_call, min_s=0.6, warm=2, macs_per_call=0, note=None, max_reps=2000):
+        """One device-resident config leg: warm-up (the batch plan is built and cached there), a calibration call, then
+        as many calls as fill ~min_s seconds, timed as above; `units` are whole-job (all ranks)."""
+        for _ in range(warm):
+            fn()
+        launches = eng.last_launches
+        ms1, _ = timed(fn, 1)
+        reps = int(min(max(3, math.ceil(min_s * 1e3 / max(ms1, 1e-3))), max_reps))
+        ms, win = timed(fn, reps)
+        per = ms / reps
+        ck = clocks_of(win)
+        rec = {"ms": per, "reps": reps, "images_per_s": n_gpus * units_per_call / per * 1e3,
+               "images_per_s_per_gpu": units_per_call / per * 1e3,
+               "algorithmic_bytes": int(bytes_per_call), "achieved_gbs": bytes_per_call / per / 1e6,
+               "frac": bytes_per_call / per / 1e6 / peak, "launches_per_call": launches, "clocks": ck}
+        if macs_per_call:
+            mhz = (ck or {}).get("sm_mhz") or 1965.0
+            rec["int_macs"] = int(macs_per_call)
+            rec["int_mac_issue_frac"] = macs_per_call / (per * 1e-3) / (sm_count * INT_MAC_LANES_PER_CLK_PER_SM * mhz * 1e6)
+        if note:
+            rec["note"] = note
+        return rec
+
+    # ---------------- device-resident throughput: the headline ----------------
     def step_device():
         eng.preprocess(frames, out=out)
 
     for _ in range(args.warmup):
         step_device()
     launches_per_step = eng.last_launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms = timed(step_device, args.steps)
+    ms, win = timed(step_device, args.steps)
     value = n_gpus * args.batch * args.steps / (ms / 1e3)
+    gpu_launches = launches_per_step * args.steps
+
+    # ---------------- sustained: the same launch back to back for >= sustain_s seconds ----------------
+    sustained = None
+    if args.legs == "all":
+        per_ms = ms / args.steps
+        reps = int(max(args.steps, math.ceil(args.sustain_s * 1e3 / per_ms)))
+        ms_s, win_s = timed(step_device, reps)
+        ach = args.batch * BYTES_PER_IMAGE / (ms_s / reps / 1e3) / 1e9
+        sustained = {"seconds": ms_s / 1e3, "launches": reps * launches_per_step, "ms_per_step": ms_s / reps,
+                     "value": n_gpus * args.batch * reps / (ms_s / 1e3), "unit": "images/s",
+                     "achieved_gbs": ach, "frac": ach / peak, "clocks": clocks_of(win_s)}
+        gpu_launches += reps * launches_per_step
+    # clocks of the headline: its 20 launches take ~26 ms, less than one nvidia-smi period, so the sample window also
+    # covers the sustained leg that follows immediately with the same launch (every leg carries its own sample as well)
+    clocks = clocks_of((win[0], win_s[1]) if sustained else win)
+    if clocks is not None and sustained:
+        clocks["window"] = "headline + sustained leg (same launch, back to back)"
 
     # ---------------- end to end: pinned host frames -> device pixel_values (+ small read-back) ----------------
     probe = torch.empty((args.batch, 1176), dtype=torch.float32).pin_memory()
@@ -339,37 +446,202 @@ def main():
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()
     e2e_launches = eng.last_launches
-    ms_e2e = timed(step_e2e, e2e_steps)
+    ms_e2e, win_e2e = timed(step_e2e, e2e_steps)
     e2e_value = n_gpus * args.batch * e2e_steps / (ms_e2e / 1e3)
+    gpu_launches += e2e_launches * e2e_steps
 
-    # strict variant: the whole pixel_values tensor copied back to pinned host memory as well (reported separately)
-    full_value = None
-    try:
-        if world > 1:                      # N x 5.9 GB of pinned host memory: measured at N=1 only
-            raise RuntimeError("skipped")
-        host_out = torch.empty((args.batch * ROWS, 1176), dtype=torch.float32).pin_memory()
+    # strict variant: the whole pixel_values tensor copied back to pinned host memory as well, chunk by chunk on a
+    # third stream while the next chunk uploads (PCIe is full duplex)
+    full = {"value": None, "unit": "images/s", "d2h_bytes_per_step": args.batch * ROWS * 1176 * 4,
+            "h2d_bytes_per_step": args.batch * H * W * 3}
+    host_out = None
+    if args.legs == "all":
+        try:
+            try:
+                host_out = torch.empty((args.batch * ROWS, 1176), dtype=torch.float32).pin_memory()
+            except Exception:
+                host_out = None
+            if not all_ok(host_out is not None):
+                raise RuntimeError("could not pin the 5.9 GB result buffer on every rank")
 
-        def step_full():
-            pv, _grid = eng.preprocess_host(host_pinned, out=out)
-            host_out.copy_(pv, non_blocking=True)
+            def step_full():
+                eng.preprocess_host(host_pinned, out=out, host_out=host_out)
 
-        step_full()
-        ms_full = timed(step_full, 2)
-        full_value = n_gpus * args.batch * 2 / (ms_full / 1e3)
-    except Exception:
-        pass
-    clocks = sampler.stop() if rank == 0 else None
+            step_full()
+            ms_full, win_full = timed(step_full, 3)
+            full["value"] = n_gpus * args.batch * 3 / (ms_full / 1e3)
+            full["note"] = ("pinned host frames -> device -> pinned host pixel_values; the read-back of chunk i runs on a "
+                            "third stream while chunk i+1 uploads")
+            full["clocks"] = clocks_of(win_full)
+            gpu_launches += eng.last_launches * 4
+            torch.cuda.synchronize()
+            check = host_out[:ROWS].clone()
+            full["readback_equals_device"] = bool(torch.equal(check, out[:ROWS].cpu()))
+        except Exception as e:                         # e.g. not enough pinnable host memory for N x 5.9 GB
+            full["note"] = f"skipped: {type(e).__name__}: {e}"
+        host_out = None
 
+    # JPEG streams over PCIe, decoded on the GPU (nvJPEG): ~9x fewer bytes per frame than raw RGB
+    e2e_jpeg = None
+    if args.legs == "all":
+        try:
+            from PIL import Image
+            natural = synth.pattern_frames(H, W)["lowpass"]
+            rng = np.random.default_rng(77 + rank)
+            streams = []
+            for i in range(16):
+                buf = io.BytesIO()
+                Image.fromarray(np.roll(natural, int(rng.integers(0, W)), axis=1)).save(buf, "JPEG", quality=90, subsampling=2)
+                streams.append(buf.getvalue())
+            streams = [streams[i % 16] for i in range(args.batch)]
+
+            def step_jpeg():
+                pv, _grid = eng.preprocess_jpeg(streams, out=out)
+                probe.copy_(pv.view(args.batch, ROWS, 1176)[:, 0], non_blocking=True)
+
+            ok = True
+            try:
+                step_jpeg()
+            except Exception as e:
+                ok, why = False, f"{type(e).__name__}: {e}"
+            if not all_ok(ok):
+                raise RuntimeError("nvJPEG leg failed on a rank" if ok else why)
+            jl = eng.last_launches
+            ms_j, win_j = timed(step_jpeg, 2)
+            e2e_jpeg = {"value": n_gpus * args.batch * 2 / (ms_j / 1e3), "unit": "images/s",
+                        "h2d_bytes_per_step": int(sum(len(s) for s in streams)), "d2h_bytes_per_step": args.batch * 1176 * 4,
+                        "clocks": clocks_of(win_j),
+                        "note": "host JPEG streams (1080p, q90, 4:2:0, low-pass synthetic content) -> nvJPEG batched decode "
+                                "on the GPU -> the same kernels; bounded by the nvJPEG decode stage (library, GPU Huffman)"}
+            gpu_launches += jl * 3
+        except Exception as e:
+            e2e_jpeg = {"value": None, "note": f"skipped: {type(e).__name__}: {e}"}
+
+    # ---------------- every other BASELINE config, device resident ----------------
+    configs = None
+    if args.legs == "all":
+        configs = {}
+        del frames, out
+        torch.cuda.empty_cache()
+
+        def out_rows(h, w, max_pixels):
+            dh, dw = G.smart_resize(h, w, G.FACTOR, G.DEFAULT_MIN_PIXELS, max_pixels)
+            return (dh // 14) * (dw // 14), (dh, dw)
+
+        def uniform_leg(name, shape, n, max_pixels, seed0, distinct_n=8):
+            h, w = shape
+            basef = torch.from_numpy(np.stack([synth.noise_frame(seed0 + 1000 * rank + i, h, w) for i in range(distinct_n)])).cuda()
+            fr = basef.repeat(n // distinct_n, 1, 1, 1).contiguous()
+            rows, dst = out_rows(h, w, max_pixels)
+            o = torch.empty((n * rows, 1176), dtype=torch.float32, device="cuda")
+            macs = n * resample_macs(h, w, dst[0], dst[1], N.FILTER_BICUBIC)
+            configs[name] = leg(lambda: eng.preprocess(fr, max_pixels=max_pixels, out=o), n, n * (h * w * 3 + rows * 4704),
+                                macs_per_call=macs, note=f"{n} frames per GPU, {h}x{w} -> {dst[0]}x{dst[1]} "
+                                f"(max_pixels {max_pixels}), bytes = frame read + pixel_values written")
+            del fr, o, basef
+            torch.cuda.empty_cache()
+
+        # config 2, second line: the Qwen2-VL-7B hub max_pixels; config 3: 4K at both settings
+        uniform_leg("1080p_hub_max_pixels", (1080, 1920), 128, G.HUB_MAX_PIXELS, 1234)
+        uniform_leg("4k_default_max_pixels", (2160, 3840), 64, G.DEFAULT_MAX_PIXELS, 4000)
+        uniform_leg("4k_hub_max_pixels", (2160, 3840), 32, G.HUB_MAX_PIXELS, 4000)
+
+        # the agents' LANCZOS thumbnails (src/agents/vlm_inspector.py:64, vlm_auditor.py:91), uint8 in -> uint8 out
+        def thumb_leg(name, shape, limit, n):
+            h, w = shape
+            tw, th = G.thumbnail_size(w, h, limit)
+            fr = [torch.from_numpy(synth.noise_frame(4000 + i % 4, h, w)).cuda() for i in range(4)]
+            fr = [fr[i % 4] for i in range(n)]
+            macs = n * resample_macs(h, w, th, tw, N.FILTER_LANCZOS)
+            configs[name] = leg(lambda: eng.resize_batch_u8(fr, th, tw, N.FILTER_LANCZOS), n, n * (h * w * 3 + th * tw * 3),
+                                macs_per_call=macs, note=f"{n} frames per GPU, {h}x{w} -> {th}x{tw} LANCZOS uint8, one fused "
+                                "launch; bytes = frame read + thumbnail written; compute bound (see int_mac_issue_frac)")
+            del fr
+            torch.cuda.empty_cache()
+
+        thumb_leg("thumbnail_4k_to_2048", (2160, 3840), 2048, 32)
+        thumb_leg("thumbnail_4k_to_1024", (2160, 3840), 1024, 32)
+        thumb_leg("thumbnail_1080p_to_1024", (1080, 1920), 1024, 64)
+
+        # config 5: a slice of the mixed-resolution dual Inspector + Auditor stream, byte-balanced over the ranks
+        per_gpu = 192
+        shapes = synth.mixed_resolution_shapes(per_gpu * n_gpus, seed=9000)
+        costs = [S.frame_bytes(h, w) for h, w in shapes]
+        mine = S.balanced_shards(costs, n_gpus)[rank]
+        cache, fr = {}, []
+        for i in mine:
+            s = shapes[i]
+            if s not in cache:
+                cache[s] = [torch.from_numpy(synth.noise_frame(9000 + k, *s)).cuda() for k in range(2)]
+            fr.append(cache[s][i % 2])
+        job_bytes, job_macs = 0, 0
+        for (h, w) in shapes:                                   # whole job: frame once + both roles' pixel_values
+            job_bytes += h * w * 3
+            for limit in (G.INSPECTOR_MAX_SIZE, G.AUDITOR_MAX_SIZE):
+                hh, ww = h, w
+                if max(h, w) > limit:
+                    ww, hh = G.thumbnail_size(w, h, limit)
+                    job_macs += resample_macs(h, w, hh, ww, N.FILTER_LANCZOS)
+                rows, dst = out_rows(hh, ww, G.DEFAULT_MAX_PIXELS)
+                job_bytes += rows * 4704
+                if max(h, w) > limit or limit == G.INSPECTOR_MAX_SIZE:      # frames no role thumbnails are resampled once
+                    job_macs += resample_macs(hh, ww, dst[0], dst[1], N.FILTER_BICUBIC)
+        res = eng.preprocess_dual(fr)
+        total_rows = res["inspector"][0].shape[0] + res["auditor"][0].shape[0]
+        del res
+        dual_out = torch.empty((total_rows, 1176), dtype=torch.float32, device="cuda")
+        rec = leg(lambda: eng.preprocess_dual(fr, out=dual_out), len(shapes) / n_gpus, job_bytes / n_gpus,
+                  macs_per_call=job_macs / n_gpus,
+                  note=f"{per_gpu} frames per GPU of the seed-9000 mixed-resolution stream, both agents' inputs per frame "
+                       "(thumbnail 2048 / 1024 LANCZOS -> processor); bytes = frame once + both pixel_values, the "
+                       "thumbnails in between are not credited; frames <= 1024 px are resampled once and stored twice")
+        rec["frames_per_s"] = rec.pop("images_per_s")
+        rec["frames_per_s_per_gpu"] = rec.pop("images_per_s_per_gpu")
+        configs["dual_inspector_auditor_stream"] = rec
+        del fr, cache, dual_out
+        torch.cuda.empty_cache()
+
+        # config 4: defect overlay on 1024 annotated 1080p BGR frames per GPU
+        n_ov, d_ov = 1024, 64
+        items = [synth.annotated_frame(7000 + i) for i in range(d_ov)]
+        ofr = torch.from_numpy(np.stack([f for f, _ in items])).cuda().repeat(n_ov // d_ov, 1, 1, 1).contiguous()
+        boxes = [items[i % d_ov][1] for i in range(n_ov)]
+        oshapes = [(1080, 1920)] * n_ov
+        plan = eng.plan_overlay(oshapes, boxes)                 # first call: pinned-buffer allocation, sprites, stamps
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        plan = eng.plan_overlay(oshapes, boxes)
+        torch.cuda.synchronize()
+        plan_ms = (time.perf_counter() - t0) * 1e3              # steady state: box rules, expansion, tile binning, upload
+        ov_bytes = n_ov * 2 * 1080 * 1920 * 3
+        configs["overlay_out_of_place"] = leg(lambda: eng.annotate(ofr, boxes, plan=plan), n_ov, ov_bytes,
+                                              note=f"{n_ov} annotated 1080p BGR frames per GPU, {sum(len(b) for b in boxes)} boxes; "
+                                              "frame copy + in-order tile draw, plan (host) cached; bytes = 2*H*W*3 per frame")
+        work = ofr.clone()
+        rec = leg(lambda: eng.annotate(work, boxes, plan=plan, inplace=True), n_ov, ov_bytes, note="drawn in place: only the touched 64x16 tiles move; "
+                  "frac is quoted against the out-of-place bytes for comparison and may exceed 1")
+        configs["overlay_in_place"] = rec
+        t0 = time.perf_counter()
+        for _ in range(2):
+            eng.annotate(ofr, boxes)
+        torch.cuda.synchronize()
+        api_ms = (time.perf_counter() - t0) / 2 * 1e3
+        configs["overlay_host_plan"] = {"plan_overlay_ms_per_call": plan_ms, "plan_overlay_ms_per_frame": plan_ms / n_ov,
+                                        "annotate_api_ms_per_call": api_ms,
+                                        "annotate_api_images_per_s_per_gpu": n_ov / api_ms * 1e3,
+                                        "note": "wall clock on this rank, host planning (box rules in Python, expansion + tile "
+                                                "binning in C++, upload) INCLUDED: what one un-planned annotate() call costs"}
+        del ofr, work, plan
+        torch.cuda.empty_cache()
+        gpu_launches += sum(int(v.get("launches_per_call", 0)) * int(v.get("reps", 0)) for v in configs.values())
+
+    if rank == 0:
+        sampler.stop()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
     kernel_s = (ms / 1e3) / args.steps                       # one fused launch per step on this rank
     achieved = args.batch * BYTES_PER_IMAGE / kernel_s / 1e9
     traffic, traffic_src = None, None                        # measured DRAM bytes per launch, from the committed ncu capture
@@ -383,19 +655,23 @@ def main():
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8->int32 fixed point->f32", "data": "synthetic", "config": config,
+        "plan_cached": True,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": args.batch * H * W * 3,
                 "d2h_bytes_per_step": args.batch * 1176 * 4,
-                "cpus_bound_per_rank": numa,
+                "cpus_bound_per_rank": numa, "clocks": clocks_of(win_e2e),
                 "note": "pinned host frames -> device pixel_values (consumer is on the GPU); first patch row of "
-                        "every frame read back"},
-        "e2e_full_readback": {"value": full_value, "unit": "images/s",
-                              "d2h_bytes_per_step": args.batch * ROWS * 1176 * 4},
-        "gpu_launches": launches_per_step * args.steps + e2e_launches * e2e_steps,
+                        "every frame read back; see e2e_full_readback for the whole tensor brought back"},
+        "e2e_full_readback": full,
+        "e2e_jpeg": e2e_jpeg,
+        "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "kernel": "k_fused_sched (vis_preprocess_fused_sched)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
                      "traffic_source": traffic_src, "algorithmic_bytes_per_launch": args.batch * BYTES_PER_IMAGE,
                      "peak_source": peak_src, "bytes_per_image": BYTES_PER_IMAGE,
-                     "launches_timed": launches_per_step * args.steps},
+                     "launches_timed": launches_per_step * args.steps,
+                     "sustained_frac": sustained["frac"] if sustained else None},
+        "sustained": sustained,
+        "configs": configs,
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,
     }

@@ -228,6 +228,15 @@ int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds
 int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,
                                const int32_t* hrec, const int32_t* vrec,
                                const float* lut768, float* pixel_values, void* stream);
+/* The same with an optional second destination per frame.  Dual Inspector + Auditor inputs
+ * (src/agents/vlm_inspector.py:59-69 thumbnail 2048, src/agents/vlm_auditor.py:87-96 thumbnail 1024): a frame that
+ * neither agent thumbnails (longer side <= 1024) gives both processors the SAME pixel_values rows; dup_rows[i] >= 0
+ * (DEVICE int64[n_frames], or NULL) names the first row of frame i's copy in the same pixel_values allocation, written
+ * from the same registers as the primary rows — computed once, never copied.  8-slot kernel (<= 8 taps) only:
+ * VIS_E_UNSUPPORTED otherwise.                                                            [device] */
+int vis_preprocess_fused_sched_dup(const VisSched* sched, const VisFrameRef* frames, int n_frames,
+                                   const int32_t* hrec, const int32_t* vrec,
+                                   const float* lut768, float* pixel_values, const int64_t* dup_rows, void* stream);
 
 /* Image.resize((dst_w, dst_h), filter) of RGB uint8 HWC frames in ONE fused launch (both passes, uint8 between them,
  * horizontal first): the agents' thumbnails (src/agents/vlm_inspector.py:64, vlm_auditor.py:91) and resize_image

@@ -140,3 +140,28 @@ def test_pipeline_after_the_decode_stays_bit_exact(engine, tmp_path):
         IU.decode_image(tmp_path / "bad.jpg")
     with pytest.raises(ValueError):
         IU.draw_bounding_boxes(path, boxes, tmp_path / "x.jpg", codec="turbo")
+
+
+def test_exif_orientation_follows_cv2(tmp_path):
+    """A phone-camera JPEG with EXIF Orientation 6 / 8 / 3: cv2.imread (the reference's decoder for the overlay, heat map
+    and comparison panel, utils/image_utils.py:170) rotates it, nvJPEG does not — such files keep the host decoder, so
+    the frame, its H/W and the pixels the percent boxes land on equal the reference's exactly."""
+    import cv2
+    from vision_inspection_system_b200.jpeg import exif_orientation
+    rgb = synth.pattern_frames(480, 640)["lowpass"]
+    _, boxes = synth.annotated_frame(7000, 480, 640)
+    for orientation in (6, 8, 3):
+        buf = io.BytesIO()
+        ex = Image.Exif()
+        ex[0x0112] = orientation
+        Image.fromarray(rgb).save(buf, "JPEG", quality=90, exif=ex)
+        path = tmp_path / f"o{orientation}.jpg"
+        path.write_bytes(buf.getvalue())
+        assert exif_orientation(buf.getvalue()) == orientation
+        want = cv2.imread(str(path))
+        assert want.shape == ((640, 480, 3) if orientation in (6, 8) else (480, 640, 3))
+        got = IU.decode_image(path, bgr=True, codec="nvjpeg")
+        assert np.array_equal(got.cpu().numpy(), want)
+        out = IU.draw_bounding_boxes(path, boxes, tmp_path / f"o{orientation}.png", codec="nvjpeg")
+        assert np.array_equal(cv2.imread(str(out)), OV.draw_bounding_boxes(want, boxes))
+    assert exif_orientation(jpeg_bytes(rgb)) == 1 and exif_orientation(b"\xff\xd8\xff\xe1") == 1

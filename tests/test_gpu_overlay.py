@@ -49,8 +49,10 @@ def test_mixed_sizes_odd_widths_and_empty_lists(engine):
 
 
 def test_text_labels_beyond_digits(engine):
-    """Labels are any printable ASCII (the reference passes '#<int>', the function accepts anything)."""
-    texts = ["#A7", "crack-12", "Z", "a|b", "#(x)", "Q9%", "~", "ok!", "{[<>]}", "W_m"]
+    """Labels are any text of any length (the reference passes '#<int>', cv2.putText accepts anything and draws '?'
+    for every byte outside printable ASCII; labels wider than the frame are clipped; non-strings fall back to the index)."""
+    texts = ["#A7", "crack-12", "Z", "a|b", "#(x)", "Q9%", "~", "ok!", "{[<>]}", "W_m",
+             "a label far longer than eleven bytes", "d\xe9faut #2", "\u6b20\u9665", "", "x" * 300, 17]   # never raises
     items = []
     for k, shape in enumerate(((480, 640), (1080, 1920), (333, 517))):
         frame, boxes = synth.annotated_frame(60 + k, *shape)

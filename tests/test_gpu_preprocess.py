@@ -88,15 +88,15 @@ def test_padded_pitch_and_unaligned_views(engine):
     pv, _ = engine.preprocess([odd[:, :640]], force_generic=True)
     check_equal(pv.cpu().numpy(), want, "unaligned pitch (generic)")
     pv, _ = engine.preprocess([odd[:, :640]])                                       # default: repacked, fused kernel
-    assert engine.last_launches == 1
+    assert engine.last_launches == 2     # vis_repitch_u8 + the fused launch
     check_equal(pv.cpu().numpy(), want, "unaligned pitch (repacked)")
     mouri_like = [synth.noise_frame(80 + i, 100, 502) for i in range(3)]            # 1506-byte rows (BASELINE config 1 shape)
     wantm, _ = Q.preprocess(mouri_like)
     pv, _ = engine.preprocess([torch.from_numpy(f).cuda() for f in mouri_like])
-    assert engine.last_launches == 1
+    assert engine.last_launches == 2     # vis_repitch_u8 + the fused launch
     check_equal(pv.cpu().numpy(), wantm, "502-pixel rows (repacked)")
     pv, _ = engine.preprocess(torch.from_numpy(np.stack(mouri_like)).cuda())        # the same as one [B, H, W, 3] tensor
-    assert engine.last_launches == 1
+    assert engine.last_launches == 2     # vis_repitch_u8 + the fused launch
     check_equal(pv.cpu().numpy(), wantm, "502-pixel rows, batch tensor (repacked)")
 
 
@@ -186,6 +186,25 @@ def test_error_behaviour(engine):
         engine.preprocess([])
 
 
+def test_config1_jpeg_file_known_answer(engine):
+    """BASELINE config 1 as written: the reference's own Mouri.jpg FILE -> load_image -> preprocess_for_vlm must give the
+    known answer of SURVEY.md 8(c) (grid [1, 8, 36], 288 rows, sha256[:16] 01e0d93015585789, decoded RGB 13b0ebd773d68238)."""
+    from pathlib import Path
+    from vision_inspection_system_b200 import image_utils as IU
+    path = Path(__file__).parent / "golden" / "Mouri.jpg"
+    img = IU.load_image(path)
+    assert img.size == (502, 100) and sha(np.asarray(img.convert("RGB")))[:16] == "13b0ebd773d68238"
+    for source in (img, path, str(path)):
+        pv, grid = IU.preprocess_for_vlm(source)
+        assert grid.tolist() == [[1, 8, 36]] and tuple(pv.shape) == (288, 1176)
+        assert sha(pv.cpu().numpy())[:16] == "01e0d93015585789"
+    pv, grid = IU.preprocess_for_vlm([path, img], role="inspector")          # 502 px: no thumbnail for either role
+    assert grid.tolist() == [[1, 8, 36]] * 2 and sha(pv[:288].cpu().numpy())[:16] == "01e0d93015585789"
+    assert torch.equal(pv[:288], pv[288:])
+    with pytest.raises(FileNotFoundError):
+        IU.load_image(path.with_name("missing.jpg"))
+
+
 def test_image_utils_preprocess_for_vlm(engine, arrays, goldens):
     from PIL import Image
     from vision_inspection_system_b200 import image_utils as IU
@@ -201,3 +220,27 @@ def test_image_utils_preprocess_for_vlm(engine, arrays, goldens):
         got, ggrid = IU.preprocess_for_vlm(frame, role=role)
         assert np.array_equal(ggrid.numpy(), wgrid)
         check_equal(got.cpu().numpy(), want, role)
+
+
+def test_preprocess_dual_equals_two_role_passes(engine):
+    """BASELINE config 5 entry point: both agents' inputs in one pass == thumbnail(2048 / 1024, LANCZOS) -> processor per
+    role (src/agents/vlm_inspector.py:59-69, vlm_auditor.py:87-96), bit-exact; frames neither role thumbnails are
+    resampled once and stored to both tensors; frames of one geometry share a launch across roles and sources."""
+    shapes = [(480, 640), (720, 1280), (1080, 1920), (1536, 2048), (2160, 3840), (100, 502), (1080, 1920), (480, 640),
+              (2160, 3840), (100, 502)]
+    frames = [synth.noise_frame(9100 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    dev = [torch.from_numpy(f).cuda() for f in frames]
+    res = engine.preprocess_dual(dev)
+    launches = engine.last_launches
+    torch.cuda.synchronize()
+    for role, limit in (("inspector", 2048), ("auditor", 1024)):
+        want, wgrid = Q.preprocess([Q.agent_thumbnail(f, limit) for f in frames])
+        pv, grid = res[role]
+        assert np.array_equal(grid.numpy(), wgrid), role
+        check_equal(pv.cpu().numpy(), want, role)
+    assert res["inspector"][0].data_ptr() + res["inspector"][0].numel() * 4 == res["auditor"][0].data_ptr()   # one allocation
+    # 5 thumbnail launches (720p/1080p/1536 Auditor, 4K both) + 1 re-pitch (502-px rows) + one processor launch per
+    # distinct input geometry (8: the Auditor's 1024x576 thumbnails of 720p, 1080p and 4K frames share one)
+    assert launches <= 14, launches
+    again = engine.preprocess_dual(dev, out=torch.empty_like(torch.cat([res["inspector"][0], res["auditor"][0]])))
+    assert torch.equal(again["auditor"][0], res["auditor"][0]) and torch.equal(again["inspector"][0], res["inspector"][0])

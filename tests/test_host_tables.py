@@ -232,3 +232,22 @@ def test_host_only_image_utils_helpers(tmp_path):
         IU.load_image(tmp_path / "none.png")
     with pytest.raises(ValueError, match="Failed to load image"):
         IU.load_image(junk)
+
+
+def test_exif_orientation_parser():
+    """jpeg.exif_orientation: the tag cv2.imread honours; 1 for files without EXIF or with damaged segments."""
+    import io
+    from PIL import Image
+    from vision_inspection_system_b200.jpeg import exif_orientation
+    im = Image.fromarray(np.random.default_rng(0).integers(0, 255, (40, 60, 3), dtype=np.uint8))
+    plain = io.BytesIO()
+    im.save(plain, "JPEG")
+    assert exif_orientation(plain.getvalue()) == 1
+    for o in range(1, 9):
+        b = io.BytesIO()
+        ex = Image.Exif()
+        ex[0x0112] = o
+        im.save(b, "JPEG", exif=ex)
+        assert exif_orientation(b.getvalue()) == o
+    data = b.getvalue()
+    assert exif_orientation(data[:30]) == 1 and exif_orientation(b"") == 1 and exif_orientation(b"\xff\xd8\xff\xe1\x00") == 1

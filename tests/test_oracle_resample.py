@@ -46,6 +46,11 @@ def test_mouri_known_answer(goldens, arrays):
     assert sha(pv)[:16] == "01e0d93015585789"
     assert sha(arrays["mouri_rgb"])[:16] == "13b0ebd773d68238"
     assert abs(float(pv.min()) - -1.7922626) < 1e-6 and abs(float(pv.max()) - 2.145897) < 1e-6
+    # the same through the FILE (tests/golden/Mouri.jpg is the reference's own fixture, 9 KB): host decode -> oracle
+    from pathlib import Path
+    from PIL import Image
+    decoded = np.asarray(Image.open(Path(__file__).parent / "golden" / "Mouri.jpg").convert("RGB"))
+    assert np.array_equal(decoded, arrays["mouri_rgb"])
 
 
 def test_thumbnail_goldens(goldens, arrays):

@@ -57,6 +57,47 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_subgroup(rank, world, port, q):
+    """world 3, gather inside the sub-group {1, 2}: group rank 0 is GLOBAL rank 1 (P2POp peers are global)."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        group = dist.new_group([1, 2])
+        ok = True
+        if rank in (1, 2):
+            grids = [(1, 2, 4), (1, 4, 2), (1, 2, 2)]
+            rows = [g[1] * g[2] for g in grids]
+            full = torch.arange(sum(rows) * 1176, dtype=torch.float32).reshape(-1, 1176)
+            starts = np.concatenate([[0], np.cumsum(rows)])
+            mine = [0, 2] if rank == 1 else [1]
+            pv = torch.cat([full[starts[i]:starts[i + 1]] for i in mine])
+            grid = torch.tensor([grids[i] for i in mine], dtype=torch.int64).reshape(-1, 3)
+            out, ogrid = S.gather_patches(pv, grid, mine, dst=0, group=group)
+            ok = (torch.equal(out, full) and ogrid.tolist() == [list(g) for g in grids]) if rank == 1 else out is None
+            # nobody has a frame: empty tensors on dst, not an exception
+            out, ogrid = S.gather_patches(full[:0], torch.zeros((0, 3), dtype=torch.int64), [], dst=0, group=group)
+            ok = ok and ((out.shape == (0, 1176) and ogrid.shape == (0, 3)) if rank == 1 else out is None)
+        q.put((ok, True))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_patches_subgroup_world3():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_subgroup, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(a and b for a, b in results)
+
+
 def test_gather_patches_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

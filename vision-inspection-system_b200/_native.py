@@ -78,7 +78,7 @@ EXPORTS = [
     "vis_resample_h_u8", "vis_resample_v_u8", "vis_normalize_patchify",
     "vis_max_taps", "vis_fused_kt_class", "vis_record_stride", "vis_pack_records", "vis_fused_supported",
     "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
-    "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_preprocess_fused_sched",
+    "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_preprocess_fused_sched", "vis_preprocess_fused_sched_dup",
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
     "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn", "vis_overlay_sprite_expand", "vis_overlay_stamp_expand", "vis_overlay_plan_batch_sprites",
@@ -179,6 +179,7 @@ def _declare(L: C.CDLL) -> None:
     L.vis_resize_fused_sched.argtypes = [vp, vp, C.c_int, C.c_int64, vp, vp, vp]
     L.vis_sched_pack_records.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]
     L.vis_preprocess_fused_sched.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    L.vis_preprocess_fused_sched_dup.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
     L.vis_overlay_tiles.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, ip, ip]
     L.vis_overlay_plan_batch.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int]

@@ -100,11 +100,13 @@ __device__ __noinline__ void band_done(uint32_t bar0, int nb, int lane) {
 }
 
 // UP: up to two output samples may end at one input index (mild upscaling, scale > 0.5): a second mask byte per step
-template <int KT, int STRIDE, bool UP>
+// DUP: frames may name a second destination for their rows (dual Inspector + Auditor inputs, vis_preprocess_fused_sched_dup)
+template <int KT, int STRIDE, bool UP, bool DUP>
 __global__ void __launch_bounds__(kThreadsS, 1)
 k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict__ frames, int n_items,
               const __grid_constant__ LayoutS L, const int* __restrict__ hrec_g, const int* __restrict__ vrec_g,
-              const float* __restrict__ lut768, float* __restrict__ pixel_values) {
+              const float* __restrict__ lut768, float* __restrict__ pixel_values,
+              const long long* __restrict__ dup_rows) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);               // warp-uniform for the compiler
@@ -336,6 +338,10 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
             const VisSchedSeg G = sc.seg[sg];
             const int n_patches = (S.x1 - S.x0) / VIS_PATCH, gx0 = S.x0 / VIS_PATCH;
             float* const frame_out = pixel_values + (size_t)frames[f].row0 * VIS_ROW_FLOATS;
+            // dual Inspector + Auditor inputs: a frame neither agent thumbnails gives both the SAME rows — they are
+            // written to the second tensor from the same registers (dup_rows[f] >= 0), not computed or copied again
+            const long long dup = DUP ? dup_rows[f] : -1;
+            const long long dup_off = DUP && dup >= 0 ? (dup - frames[f].row0) * (long long)VIS_ROW_FLOATS : 0;
             for (int gy = G.y0 / VIS_PATCH; gy < G.y1 / VIS_PATCH; ++gy, ++nb) {
                 const int os = nb & 1;
                 mbar_wait(bar(OF, os), (nb >> 1) & 1);
@@ -354,6 +360,10 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
                             const float v0 = l[a & 0xff], v1 = l[a >> 8], v2 = l[b & 0xff], v3 = l[b >> 8];
                             stg128(prow + go[i], v0, v1, v2, v3);
                             stg128(prow + go[i] + 196, v0, v1, v2, v3);
+                            if (DUP && dup >= 0) {
+                                stg128(prow + dup_off + go[i], v0, v1, v2, v3);
+                                stg128(prow + dup_off + go[i] + 196, v0, v1, v2, v3);
+                            }
                         }
                     }
                 }
@@ -364,17 +374,17 @@ k_fused_sched(const __grid_constant__ VisSched sc, const VisFrameRef* __restrict
     }
 }
 
-template <int KT, int STRIDE, bool UP>
+template <int KT, int STRIDE, bool UP, bool DUP>
 int launch_sched(const VisSched& sc, const VisFrameRef* frames, int n_frames, const LayoutS& L, const int* hrec,
-                 const int* vrec, const float* lut768, float* pixel_values, cudaStream_t st) {
-    auto kern = k_fused_sched<KT, STRIDE, UP>;
+                 const int* vrec, const float* lut768, float* pixel_values, const long long* dup_rows, cudaStream_t st) {
+    auto kern = k_fused_sched<KT, STRIDE, UP, DUP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return vis::cuda_fail(e, "vis_preprocess_fused_sched: cudaFuncSetAttribute");
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_items = n_frames * sc.n_strips * sc.n_segs;
     const int grid = n_items < sms ? n_items : sms;
-    kern<<<grid, kThreadsS, L.total, st>>>(sc, frames, n_items, L, hrec, vrec, lut768, pixel_values);
+    kern<<<grid, kThreadsS, L.total, st>>>(sc, frames, n_items, L, hrec, vrec, lut768, pixel_values, dup_rows);
     return vis::check_launch("vis_preprocess_fused_sched");
 }
 
@@ -575,17 +585,23 @@ int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds
     return VIS_OK;
 }
 
-int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,
-                               const int32_t* hrec, const int32_t* vrec,
-                               const float* lut768, float* pixel_values, void* stream) {
+int vis_preprocess_fused_sched_dup(const VisSched* sched, const VisFrameRef* frames, int n_frames,
+                                   const int32_t* hrec, const int32_t* vrec,
+                                   const float* lut768, float* pixel_values, const int64_t* dup_rows, void* stream) {
     if (!sched || !frames || !hrec || !vrec || !lut768 || !pixel_values || n_frames <= 0 ||
         sched->out_mode != VIS_SCHED_OUT_PIXEL_VALUES || sched->n_strips <= 0 || sched->n_segs <= 0) {
         vis::set_error("vis_preprocess_fused_sched: bad arguments");
         return VIS_E_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (sched->ring == 16)
+    const long long* dup = reinterpret_cast<const long long*>(dup_rows);
+    if (sched->ring == 16) {
+        if (dup) {
+            vis::set_error("vis_preprocess_fused_sched_dup: duplicate rows are served by the 8-slot kernel only (<= 8 taps)");
+            return VIS_E_UNSUPPORTED;
+        }
         return sched16_launch(*sched, frames, n_frames, 0, hrec, vrec, lut768, pixel_values, st);
+    }
     if (sched->ring != 8 || (sched->kt != 6 && sched->kt != 8)) {
         vis::set_error("vis_preprocess_fused_sched: schedule of an unknown kernel class (ring %d, %d taps)", sched->ring, sched->kt);
         return VIS_E_INVALID;
@@ -595,12 +611,17 @@ int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames,
         vis::set_error("vis_preprocess_fused_sched: %d bytes of shared memory needed", L.total);
         return VIS_E_UNSUPPORTED;
     }
-    if (sched->per_index > 1) {
-        if (sched->kt == 6) return launch_sched<6, 8, true>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
-        return launch_sched<8, 12, true>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
-    }
-    if (sched->kt == 6) return launch_sched<6, 8, false>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
-    return launch_sched<8, 12, false>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, st);
+#define VIS_LS(KT, ST, UP) (dup ? launch_sched<KT, ST, UP, true>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, dup, st) \
+                                : launch_sched<KT, ST, UP, false>(*sched, frames, n_frames, L, hrec, vrec, lut768, pixel_values, dup, st))
+    if (sched->per_index > 1) return sched->kt == 6 ? VIS_LS(6, 8, true) : VIS_LS(8, 12, true);
+    return sched->kt == 6 ? VIS_LS(6, 8, false) : VIS_LS(8, 12, false);
+#undef VIS_LS
+}
+
+int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,
+                               const int32_t* hrec, const int32_t* vrec,
+                               const float* lut768, float* pixel_values, void* stream) {
+    return vis_preprocess_fused_sched_dup(sched, frames, n_frames, hrec, vrec, lut768, pixel_values, nullptr, stream);
 }
 
 int vis_resize_fused_sched(const VisSched* sched, const VisResizeRef* frames, int n_frames, int64_t dst_pitch,

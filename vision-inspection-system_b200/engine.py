@@ -61,6 +61,7 @@ class _SchedLaunch:
     frames: torch.Tensor         # device VisFrameRef[]
     hrec: torch.Tensor
     vrec: torch.Tensor
+    dup: torch.Tensor | None = None   # device int64[n_frames]: first row of each frame's second copy, -1 for none
 
 
 @dataclass
@@ -190,26 +191,44 @@ class Engine:
         self._dev_tables[key] = hit
         return hit
 
+    def _resize_plan(self, frames: list, out_h: int, out_w: int, filt: int):
+        """Everything ONE fused ``vis_resize_fused_sched`` launch over same-shape RGB frames needs — (schedule, records,
+        device descriptors, the [n, out_h, out_w, 3] result tensor) — or None when the geometry needs the generic passes.
+        The plan stays valid while the frames keep their addresses (``preprocess_dual`` caches it)."""
+        f0 = frames[0]
+        fusable = all(f.dim() == 3 and f.shape == f0.shape and f.shape[2] == 3 and f.stride(2) == 1 and f.stride(1) == 3
+                      and f.stride(0) == f0.stride(0) and f.stride(0) % 16 == 0 and f.data_ptr() % 16 == 0 for f in frames)
+        if not fusable:
+            return None
+        for f in frames:
+            self._check_u8(f)
+        h, w = int(f0.shape[0]), int(f0.shape[1])
+        head = self._resize_sched(h, w, out_h, out_w, filt, int(f0.stride(0)), 1)
+        if head is None:
+            return None
+        per = int(np.frombuffer(head[0][:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["n_strips"])
+        segs = self._pick_segs(len(frames) * per, h, out_h // 14)
+        sched, hrec, vrec = self._resize_sched(h, w, out_h, out_w, filt, int(f0.stride(0)), segs) or head
+        out = torch.empty((len(frames), out_h, out_w, 3), dtype=torch.uint8, device=self.device)
+        ref = np.zeros(len(frames), N.RESIZE_REF_DTYPE)
+        ref["src"] = [f.data_ptr() for f in frames]
+        ref["dst"] = out.data_ptr() + np.arange(len(frames), dtype=np.uint64) * np.uint64(out.stride(0))
+        d_ref = torch.from_numpy(ref.view(np.uint8).copy()).to(self.device)
+        return (sched, hrec, vrec, d_ref, len(frames), out_w * 3, out)
+
+    def _run_resize(self, rp) -> None:
+        sched, hrec, vrec, d_ref, n, dst_pitch, _ = rp
+        N.check(self.L.vis_resize_fused_sched(sched.ctypes.data_as(C.c_void_p), d_ref.data_ptr(), n, dst_pitch,
+                                              hrec.data_ptr(), vrec.data_ptr(), _stream_ptr()), "vis_resize_fused_sched")
+
     def resize_batch_u8(self, frames, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS) -> list:
         """``Image.resize((out_w, out_h), filt)`` of a list of same-shape RGB uint8 HWC CUDA frames: ONE fused launch
         (both passes) when the geometry allows, else the generic passes frame by frame.  Returns new tensors."""
         frames = list(frames)
         if not frames:
             return []
-        f0 = frames[0]
-        fusable = all(f.dim() == 3 and f.shape == f0.shape and f.shape[2] == 3 and f.stride(2) == 1 and f.stride(1) == 3
-                      and f.stride(0) == f0.stride(0) and f.stride(0) % 16 == 0 and f.data_ptr() % 16 == 0 for f in frames)
-        plan = None
-        if fusable:
-            for f in frames:
-                self._check_u8(f)
-            h, w = int(f0.shape[0]), int(f0.shape[1])
-            head = self._resize_sched(h, w, out_h, out_w, filt, int(f0.stride(0)), 1)
-            if head is not None:
-                per = int(np.frombuffer(head[0][:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["n_strips"])
-                segs = self._pick_segs(len(frames) * per, h, out_h // 14)
-                plan = self._resize_sched(h, w, out_h, out_w, filt, int(f0.stride(0)), segs)
-        if plan is None:
+        rp = self._resize_plan(frames, out_h, out_w, filt)
+        if rp is None:
             outs = []
             launches = 0
             for f in frames:
@@ -217,17 +236,10 @@ class Engine:
                 launches += self.last_launches
             self.last_launches = launches
             return outs
-        sched, hrec, vrec = plan
-        out = torch.empty((len(frames), out_h, out_w, 3), dtype=torch.uint8, device=self.device)
-        ref = np.zeros(len(frames), N.RESIZE_REF_DTYPE)
-        ref["src"] = [f.data_ptr() for f in frames]
-        ref["dst"] = out.data_ptr() + np.arange(len(frames), dtype=np.uint64) * np.uint64(out.stride(0))
-        d_ref = torch.from_numpy(ref.view(np.uint8).copy()).to(self.device)
-        N.check(self.L.vis_resize_fused_sched(sched.ctypes.data_as(C.c_void_p), d_ref.data_ptr(), len(frames), out_w * 3,
-                                              hrec.data_ptr(), vrec.data_ptr(), _stream_ptr()), "vis_resize_fused_sched")
+        self._run_resize(rp)
         self.last_launches = 1
-        self._keepalive_r = d_ref
-        return list(out.unbind(0))
+        self._keepalive_r = rp[3]
+        return list(rp[6].unbind(0))
 
     # ------------------------------------------------------------------ generic resample (uint8 -> uint8)
     def resize_u8(self, img: torch.Tensor, out_h: int, out_w: int, filt: int = N.FILTER_LANCZOS, stream=None,
@@ -404,23 +416,28 @@ class Engine:
 
     # ------------------------------------------------------------------ frames -> pixel_values
     def plan_batch(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
-                   force_generic: bool = False, vsplit: int | None = None, path: str = "auto") -> "BatchPlan":
+                   force_generic: bool = False, vsplit: int | None = None, path: str = "auto",
+                   rows=None, dup_rows=None, total_rows: int | None = None) -> "BatchPlan":
         """Host-side planning for one batch: geometry, output rows, descriptor arrays (uploaded once).
 
         Plans depend only on pointers and shapes, so they are cached and reused when the same device buffers are
         submitted again (a streaming loop that refills one staging buffer pays for planning once).
+        ``rows`` (first output row per frame; default: frames back to back), ``dup_rows`` (first row of a second copy
+        of a frame's rows, -1 for none) and ``total_rows`` place the frames in a larger tensor: ``preprocess_dual``.
         """
         uniform = isinstance(frames, torch.Tensor) and frames.dim() == 4
+        placed = (None if rows is None else tuple(int(v) for v in rows),
+                  None if dup_rows is None else tuple(int(v) for v in dup_rows), total_rows)
         if uniform:
             self._check_u8(frames)
             key = ("u", frames.data_ptr(), tuple(frames.shape), tuple(frames.stride()), min_pixels, max_pixels,
-                   force_generic, vsplit, path)
+                   force_generic, vsplit, path, placed)
         else:
             frames = list(frames)
             for f in frames:
                 self._check_u8(f)
             key = ("l", tuple((f.data_ptr(), tuple(f.shape), tuple(f.stride())) for f in frames), min_pixels,
-                   max_pixels, force_generic, vsplit, path)
+                   max_pixels, force_generic, vsplit, path, placed)
         plan = self._batch_plans.get(key)
         if plan is not None:
             return plan
@@ -452,8 +469,17 @@ class Engine:
             geoms.append(g)
             grids.append(G.grid_thw(g.dst_h, g.dst_w))
         n_rows = np.array([g.n_rows for g in geoms], np.int64)
-        row0 = np.concatenate([[0], np.cumsum(n_rows)[:-1]]).astype(np.int64)
-        total = int(n_rows.sum())
+        if rows is None:
+            row0 = np.concatenate([[0], np.cumsum(n_rows)[:-1]]).astype(np.int64)
+            total = int(n_rows.sum())
+        else:
+            row0 = np.asarray(rows, np.int64)
+            if row0.shape != n_rows.shape or total_rows is None:
+                raise ValueError("rows: one first row per frame, with total_rows")
+            total = int(total_rows)
+        dup = np.full(len(geoms), -1, np.int64) if dup_rows is None else np.asarray(dup_rows, np.int64)
+        if dup.shape != n_rows.shape:
+            raise ValueError("dup_rows: one entry per frame")
 
         plan = BatchPlan(total, torch.tensor(grids, dtype=torch.int64), [], [])
         groups: dict = {}
@@ -464,6 +490,8 @@ class Engine:
                 groups.setdefault(id(g), (g, []))[1].append(i)
             else:
                 plan.generic.append((i, g, int(row0[i])))
+                if dup[i] >= 0:                       # no shared store on this path: the copy is computed again
+                    plan.generic.append((i, g, int(dup[i])))
         want = 3 * self.sm_count                     # work items wanted: a few per SM
         # statically scheduled kernels (8-slot: <= 8 taps, 16-slot: 9..32 taps): one launch per (geometry, pitch)
         by_class: dict = {}
@@ -484,16 +512,26 @@ class Engine:
                     if sched is None:                # every segment adds chunk-rounded mask bytes: the multi-segment
                         sched = head                 # schedule may not fit where the one-segment schedule did
                     hd = np.frombuffer(sched[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]
-                    ref = np.zeros(len(sel), N.FRAME_REF_DTYPE)
-                    ref["src"], ref["row0"] = ptrs[sel].astype(np.uint64), row0[sel]
+                    src_ptr, first_row, d_dup = ptrs[sel], row0[sel], None
+                    if (dup[sel] >= 0).any():
+                        if int(hd["ring"]) == 8:     # second destination written from the same registers
+                            d_dup = torch.from_numpy(dup[sel].copy()).to(self.device)
+                        else:                        # 16-slot kernel: the copy is a second work item
+                            extra = sel[dup[sel] >= 0]
+                            src_ptr, first_row = np.concatenate([src_ptr, ptrs[extra]]), np.concatenate([first_row, dup[extra]])
+                    ref = np.zeros(len(src_ptr), N.FRAME_REF_DTYPE)
+                    ref["src"], ref["row0"] = src_ptr.astype(np.uint64), first_row
                     plan.fused.append(_SchedLaunch(
-                        sched, len(sel), len(sel) * int(hd["n_strips"]) * int(hd["n_segs"]),
-                        torch.from_numpy(ref.view(np.uint8).copy()).to(self.device), g.srec[0], g.srec[1]))
+                        sched, len(ref), len(ref) * int(hd["n_strips"]) * int(hd["n_segs"]),
+                        torch.from_numpy(ref.view(np.uint8).copy()).to(self.device), g.srec[0], g.srec[1], d_dup))
                 rest = np.concatenate(rest_parts) if rest_parts else np.zeros(0, np.int64)
             if len(rest) and g.kt:
                 by_class.setdefault(g.kt, []).append((g, rest))
             else:                                    # 9+ taps the schedule declined: generic passes
-                plan.generic.extend((int(i), g, int(row0[i])) for i in rest)
+                for i in rest:
+                    plan.generic.append((int(i), g, int(row0[i])))
+                    if dup[i] >= 0:
+                        plan.generic.append((int(i), g, int(dup[i])))
         # general kernel: one launch per tap class; all geometries of a class share it
         for kt, members in by_class.items():
             n_class = sum(len(idx) for _, idx in members)
@@ -505,10 +543,14 @@ class Engine:
                 else:
                     vs = vsplit
                 sp = self._plan(g, vs)
+                first_row = row0[idx]
+                if (dup[idx] >= 0).any():             # general kernel: the copy is a second frame entry
+                    extra = idx[dup[idx] >= 0]
+                    idx, first_row = np.concatenate([idx, extra]), np.concatenate([first_row, dup[extra]])
                 fr = np.zeros(len(idx), N.FRAME_DTYPE)
                 fr["src"], fr["src_pitch"] = ptrs[idx].astype(np.uint64), pitches[idx]
                 fr["src_h"], fr["src_w"], fr["dst_h"], fr["dst_w"] = g.src_h, g.src_w, g.dst_h, g.dst_w
-                fr["hrec"], fr["vrec"], fr["row0"] = g.hrec.data_ptr(), g.vrec.data_ptr(), row0[idx]
+                fr["hrec"], fr["vrec"], fr["row0"] = g.hrec.data_ptr(), g.vrec.data_ptr(), first_row
                 st = np.tile(sp.strips, len(idx))
                 st["frame"] = base + np.repeat(np.arange(len(idx), dtype=np.int32), len(sp.strips))
                 fr_parts.append(fr)
@@ -526,7 +568,7 @@ class Engine:
 
     def preprocess(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
                    out: torch.Tensor | None = None, force_generic: bool = False, vsplit: int | None = None,
-                   path: str = "auto"):
+                   path: str = "auto", rows=None, dup_rows=None, total_rows: int | None = None):
         """RGB uint8 HWC CUDA frames -> (pixel_values f32 [sum N_i, 1176] on device, image_grid_thw int64 [B, 3]).
 
         ``frames``: a ``[B, H, W, 3]`` tensor or a list of ``[H, W, 3]`` tensors (mixed sizes allowed).
@@ -543,14 +585,18 @@ class Engine:
                     frames = self._align_frames(list(frames.unbind(0)))          # e.g. [B, 100, 502, 3]: 1506-byte rows
             else:
                 frames = self._align_frames(list(frames))
-        plan = self.plan_batch(frames, min_pixels, max_pixels, force_generic, vsplit, path)
+        plan = self.plan_batch(frames, min_pixels, max_pixels, force_generic, vsplit, path, rows, dup_rows, total_rows)
+        out = self._run_plan(plan, frames, out, self._align_launches)
+        return out, plan.grid_thw
+
+    def _run_plan(self, plan: "BatchPlan", frames, out, launches: int = 0):
+        """Enqueue the launches of a batch plan on the current stream (``frames``: what the plan was made for)."""
         if out is None:
             out = torch.empty((plan.total_rows, G.ROW_FLOATS), dtype=torch.float32, device=self.device)
         elif (tuple(out.shape) != (plan.total_rows, G.ROW_FLOATS) or out.dtype != torch.float32
               or not out.is_contiguous() or out.device != self.device):
             raise ValueError(f"out must be a contiguous float32 [{plan.total_rows}, {G.ROW_FLOATS}] tensor on {self.device}")
         sp = _stream_ptr()
-        launches = self._align_launches
         flist = frames if plan.generic else None      # indexable either way ([B,H,W,3] tensor or list)
         for i, g, r0 in plan.generic:
             resized = self.resize_u8(flist[i], g.dst_h, g.dst_w, N.FILTER_BICUBIC)
@@ -559,9 +605,10 @@ class Engine:
                                                   self.lut.data_ptr(), out.data_ptr(), r0, sp), "vis_normalize_patchify")
         for fl in plan.fused:
             if isinstance(fl, _SchedLaunch):
-                N.check(self.L.vis_preprocess_fused_sched(fl.sched.ctypes.data_as(C.c_void_p), fl.frames.data_ptr(),
-                                                          fl.n_frames, fl.hrec.data_ptr(), fl.vrec.data_ptr(),
-                                                          self.lut.data_ptr(), out.data_ptr(), sp),
+                N.check(self.L.vis_preprocess_fused_sched_dup(fl.sched.ctypes.data_as(C.c_void_p), fl.frames.data_ptr(),
+                                                              fl.n_frames, fl.hrec.data_ptr(), fl.vrec.data_ptr(),
+                                                              self.lut.data_ptr(), out.data_ptr(),
+                                                              fl.dup.data_ptr() if fl.dup is not None else None, sp),
                         "vis_preprocess_fused_sched")
                 launches += 1
                 continue
@@ -570,29 +617,144 @@ class Engine:
                                                 self.lut.data_ptr(), out.data_ptr(), sp), "vis_preprocess_fused")
             launches += 1
         self.last_launches = launches
-        return out, plan.grid_thw
+        return out
 
-    def _align_frames(self, frames: list) -> list:
+    def preprocess_dual(self, frames, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
+                        out: torch.Tensor | None = None):
+        """Both agents' Qwen2-VL inputs of a batch of RGB uint8 HWC CUDA frames in one pass (BASELINE config 5):
+        Inspector = ``thumbnail((2048, 2048), LANCZOS)`` then the processor (src/agents/vlm_inspector.py:59-69),
+        Auditor = ``thumbnail((1024, 1024), LANCZOS)`` then the processor (src/agents/vlm_auditor.py:87-96).
+
+        Returns ``{"inspector": (pixel_values, image_grid_thw), "auditor": (...)}``; the two ``pixel_values`` are views
+        of ONE allocation (Inspector rows first).  Thumbnails: one fused launch per (source geometry, role that needs
+        one).  Processor: ONE plan over both roles' inputs, so frames of one geometry share a launch whatever role or
+        source they come from (every Auditor thumbnail of a 16:9 frame is 1024x576).  A frame neither role thumbnails
+        (longer side <= 1024) is resampled ONCE and its rows are stored to both tensors from the same registers.
+        The whole pass (thumbnail staging tensors, descriptors, batch plan) is cached per set of frame addresses: a
+        streaming loop that refills the same buffers pays for planning once.
+        """
+        batch = list(frames.unbind(0)) if isinstance(frames, torch.Tensor) and frames.dim() == 4 else list(frames)
+        n = len(batch)
+        if n == 0:
+            raise ValueError("no frames")
+        for f in batch:
+            self._check_u8(f)
+        key = (tuple((f.data_ptr(), tuple(f.shape), tuple(f.stride())) for f in batch), min_pixels, max_pixels)
+        cache = self.__dict__.setdefault("_dual_plans", {})
+        dp = cache.get(key)
+        if dp is None:
+            dp = self._plan_dual(batch, min_pixels, max_pixels)
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            cache[key] = dp
+        launches = 0
+        work = dp["work"]
+        if dp["slow"]:                                   # thumbnails the fused kernel declines: recomputed, not cached
+            work = list(work)
+            for role_offset, role, idx in dp["slow"]:
+                outs = self.agent_inputs([batch[i] for i in idx], role)
+                launches += self.last_launches
+                for i, o in zip(idx, outs):
+                    work[dp["slot"][(role, i)]] = o
+            plan = self.plan_batch(work, min_pixels, max_pixels, rows=dp["rows"], dup_rows=dp["dup"], total_rows=dp["total"])
+        else:
+            plan = dp["plan"]
+        for rp in dp["thumbs"]:
+            self._run_resize(rp)
+            launches += 1
+        if dp["align"] is not None:
+            self._run_align(dp["align"])
+            launches += 1
+        pv = self._run_plan(plan, work, out, launches)
+        ti = dp["total_i"]
+        return {"inspector": (pv[:ti], dp["grid_i"]), "auditor": (pv[ti:], dp["grid_a"])}
+
+    def _plan_dual(self, batch: list, min_pixels: int, max_pixels: int) -> dict:
+        n = len(batch)
+        inputs = {"inspector": list(batch), "auditor": list(batch)}
+        thumbs, slow = [], []
+        for role, limit in (("inspector", G.INSPECTOR_MAX_SIZE), ("auditor", G.AUDITOR_MAX_SIZE)):
+            groups: dict = {}
+            for i, f in enumerate(batch):
+                h, w = int(f.shape[0]), int(f.shape[1])
+                if max(h, w) > limit:
+                    groups.setdefault((h, w, f.stride(0)), []).append(i)
+            for (h, w, _), idx in groups.items():
+                tw, th = G.thumbnail_size(w, h, limit)
+                rp = None
+                if G.reducing_plan(w, h, tw, th, N.FILTER_LANCZOS) is None:
+                    rp = self._resize_plan([batch[i] for i in idx], th, tw, N.FILTER_LANCZOS)
+                if rp is None:                           # reduce pre-pass (>= 4x) or generic passes: per call
+                    slow.append((0, role, idx))
+                    for i in idx:
+                        inputs[role][i] = None
+                else:
+                    thumbs.append(rp)
+                    for i, o in zip(idx, rp[6].unbind(0)):
+                        inputs[role][i] = o
+        insp, aud = inputs["inspector"], inputs["auditor"]
+        shared = [insp[i] is batch[i] and aud[i] is batch[i] for i in range(n)]
+
+        def shape_of(role, i):
+            f = inputs[role][i]
+            if f is not None:
+                return int(f.shape[0]), int(f.shape[1])
+            limit = G.INSPECTOR_MAX_SIZE if role == "inspector" else G.AUDITOR_MAX_SIZE
+            tw, th = G.thumbnail_size(int(batch[i].shape[1]), int(batch[i].shape[0]), limit)
+            return th, tw
+
+        def n_rows(role, i):
+            h, w = shape_of(role, i)
+            dh, dw = G.smart_resize(h, w, G.FACTOR, min_pixels, max_pixels)
+            return (dh // G.PATCH_SIZE) * (dw // G.PATCH_SIZE), G.grid_thw(dh, dw)
+        info_i = [n_rows("inspector", i) for i in range(n)]
+        info_a = [n_rows("auditor", i) for i in range(n)]
+        rows_i = np.array([r for r, _ in info_i], np.int64)
+        rows_a = np.array([r for r, _ in info_a], np.int64)
+        total_i, total_a = int(rows_i.sum()), int(rows_a.sum())
+        at_i = np.concatenate([[0], np.cumsum(rows_i)[:-1]]).astype(np.int64)
+        at_a = total_i + np.concatenate([[0], np.cumsum(rows_a)[:-1]]).astype(np.int64)
+        own_a = [i for i in range(n) if not shared[i]]
+        work = list(insp) + [aud[i] for i in own_a]
+        slot = {("inspector", i): i for i in range(n)}
+        slot.update({("auditor", i): n + k for k, i in enumerate(own_a)})
+        rows = np.concatenate([at_i, at_a[own_a]]).astype(np.int64)
+        dup = np.full(len(work), -1, np.int64)
+        dup[:n] = np.where(np.asarray(shared), at_a, -1)
+        dp = {"thumbs": thumbs, "slow": slow, "slot": slot, "rows": rows, "dup": dup, "total": total_i + total_a,
+              "total_i": total_i, "grid_i": torch.tensor([g for _, g in info_i], dtype=torch.int64),
+              "grid_a": torch.tensor([g for _, g in info_a], dtype=torch.int64), "align": None, "plan": None}
+        if not slow:
+            work, dp["align"] = self._align_frames(work, plan_only=True)
+            dp["plan"] = self.plan_batch(work, min_pixels, max_pixels, rows=rows, dup_rows=dup, total_rows=dp["total"])
+        dp["work"] = work
+        return dp
+
+    def _align_frames(self, frames: list, plan_only: bool = False):
         """Frames whose base or row pitch is not a multiple of 16 bytes (e.g. 502-pixel-wide rows) cannot be staged with
-        bulk copies; all of them are repacked by ONE ``vis_repitch_u8`` launch into cached staging tensors with a padded
-        pitch (one per shape) so that they take the fused kernels like everything else."""
+        bulk copies; all of them are repacked by ONE ``vis_repitch_u8`` launch into staging tensors with a padded pitch
+        (one per shape) so that they take the fused kernels like everything else.  ``plan_only``: return
+        (frames, re-runnable launch or None) with PRIVATE staging tensors instead of launching (``preprocess_dual``)."""
         groups: dict = {}
         for i, f in enumerate(frames):
             if (isinstance(f, torch.Tensor) and f.is_cuda and f.dtype == torch.uint8 and f.dim() == 3 and f.shape[2] == 3
                     and f.stride(2) == 1 and f.stride(1) == 3 and (f.stride(0) % 16 or f.data_ptr() % 16)):
                 groups.setdefault((int(f.shape[0]), int(f.shape[1])), []).append(i)
         if not groups:
-            return frames
+            return (frames, None) if plan_only else frames
         frames = list(frames)
         n = sum(len(idx) for idx in groups.values())
         desc = np.zeros(n, N.REPITCH_DTYPE)
-        k, biggest, sources = 0, 0, []
+        k, biggest, sources, bufs = 0, 0, [], []
         for (h, w), idx in groups.items():
             pitch = (w * 3 + 15) // 16 * 16
             key = ("align", h, w, len(idx))
-            buf = self._staging.get(key)
+            buf = None if plan_only else self._staging.get(key)
             if buf is None:
-                buf = self._staging[key] = torch.zeros((len(idx), h, pitch), dtype=torch.uint8, device=self.device)
+                buf = torch.zeros((len(idx), h, pitch), dtype=torch.uint8, device=self.device)
+                if not plan_only:
+                    self._staging[key] = buf
+            bufs.append(buf)
             biggest = max(biggest, h * pitch)
             for j, i in enumerate(idx):
                 f = frames[i]
@@ -600,19 +762,28 @@ class Engine:
                 sources.append(f)
                 frames[i] = buf[j].as_strided((h, w, 3), (pitch, 3, 1))
                 k += 1
-        d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.device)
-        N.check(self.L.vis_repitch_u8(d_desc.data_ptr(), n, biggest, _stream_ptr()), "vis_repitch_u8")
-        self._keepalive_a = (d_desc, sources)
+        ap = (torch.from_numpy(desc.view(np.uint8).copy()).to(self.device), n, biggest, sources, bufs)
+        if plan_only:
+            return frames, ap
+        self._run_align(ap)
+        self._keepalive_a = ap
         self._align_launches = 1
         return frames
 
+    def _run_align(self, ap) -> None:
+        N.check(self.L.vis_repitch_u8(ap[0].data_ptr(), ap[1], ap[2], _stream_ptr()), "vis_repitch_u8")
+
     def preprocess_host(self, host_frames: torch.Tensor, min_pixels: int = G.DEFAULT_MIN_PIXELS,
-                        max_pixels: int = G.DEFAULT_MAX_PIXELS, out: torch.Tensor | None = None, chunk: int = 32):
+                        max_pixels: int = G.DEFAULT_MAX_PIXELS, out: torch.Tensor | None = None, chunk: int = 32,
+                        host_out: torch.Tensor | None = None):
         """Same as ``preprocess`` for a HOST batch ``[B, H, W, 3]`` uint8 (pinned memory recommended).
 
         Frames are copied to the device in chunks on a side stream into two staging buffers while the previous
         chunk is being processed, so the PCIe transfer and the kernel overlap.  ``pixel_values`` stays on the device
-        (its consumer is the vision tower); ``image_grid_thw`` is returned on the host.
+        (its consumer is the vision tower); ``image_grid_thw`` is returned on the host.  ``host_out`` (pinned float32
+        ``[rows, 1176]``): each chunk's rows are ALSO copied back on a third stream as soon as its kernel has finished,
+        while the next chunk is still going up — PCIe is full duplex, so the read-back overlaps the upload; the
+        current stream waits for the last copy, so synchronising it makes ``host_out`` complete.
         """
         if host_frames.is_cuda or host_frames.dtype != torch.uint8 or host_frames.dim() != 4 or host_frames.shape[3] != 3:
             raise TypeError("preprocess_host expects a CPU uint8 [B, H, W, 3] tensor")
@@ -631,9 +802,13 @@ class Engine:
                 "buf": [torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)],
                 "ready": [torch.cuda.Event() for _ in range(2)],
                 "free": [torch.cuda.Event() for _ in range(2)],
-                "stream": torch.cuda.Stream(device=self.device)}
+                "stream": torch.cuda.Stream(device=self.device),
+                "down": torch.cuda.Stream(device=self.device), "done": torch.cuda.Event()}
         cur = torch.cuda.current_stream()
-        copy_stream = st["stream"]
+        copy_stream, down = st["stream"], st["down"]
+        if host_out is not None and (host_out.is_cuda or host_out.dtype != torch.float32 or
+                                     tuple(host_out.shape) != (b * rows, G.ROW_FLOATS) or not host_out.is_contiguous()):
+            raise ValueError(f"host_out must be a contiguous CPU float32 [{b * rows}, {G.ROW_FLOATS}] tensor")
         for ev in st["free"]:
             ev.record(cur)
         launches = 0
@@ -649,9 +824,43 @@ class Engine:
             self.preprocess(buf[:n], min_pixels, max_pixels, out=out[c0 * rows:(c0 + n) * rows])
             launches += self.last_launches
             st["free"][slot].record(cur)
+            if host_out is not None:
+                st["done"].record(cur)
+                with torch.cuda.stream(down):
+                    down.wait_event(st["done"])
+                    host_out[c0 * rows:(c0 + n) * rows].copy_(out[c0 * rows:(c0 + n) * rows], non_blocking=True)
+        if host_out is not None:
+            cur.wait_stream(down)
         self.last_launches = launches
         grid = torch.tensor([G.grid_thw(dh, dw)] * b, dtype=torch.int64)
         return out, grid
+
+    def preprocess_jpeg(self, streams, min_pixels: int = G.DEFAULT_MIN_PIXELS, max_pixels: int = G.DEFAULT_MAX_PIXELS,
+                        out: torch.Tensor | None = None, chunk: int = 256):
+        """JPEG byte streams (host) -> (pixel_values, image_grid_thw): the streams cross PCIe COMPRESSED (~0.7 MB instead
+        of 6.2 MB for a 1080p frame), are decoded on the GPU in batches (nvJPEG, ``jpeg.py``: a few levels away from
+        libjpeg-turbo, so this entry point is tolerance-specified like every ``codec="nvjpeg"`` path) and go through the
+        same kernels as ``preprocess``.  Replaces Image.open + the processor (src/agents/vlm_inspector.py:59)."""
+        streams = list(streams)
+        if not streams:
+            raise ValueError("no streams")
+        codec = self.jpeg_codec()
+        sizes = [codec.info(s)[:2] for s in streams]
+        n_rows = []
+        for w, h in sizes:
+            dh, dw = G.smart_resize(h, w, G.FACTOR, min_pixels, max_pixels)
+            n_rows.append((dh // G.PATCH_SIZE) * (dw // G.PATCH_SIZE))
+        at = np.concatenate([[0], np.cumsum(n_rows)]).astype(np.int64)
+        if out is None:
+            out = torch.empty((int(at[-1]), G.ROW_FLOATS), dtype=torch.float32, device=self.device)
+        launches, grids = 0, []
+        for c0 in range(0, len(streams), chunk):
+            frames = codec.decode_batch(streams[c0:c0 + chunk])
+            _, grid = self.preprocess(frames, min_pixels, max_pixels, out=out[int(at[c0]):int(at[min(c0 + chunk, len(streams))])])
+            launches += self.last_launches
+            grids.append(grid)
+        self.last_launches = launches
+        return out, torch.cat(grids)
 
     # ------------------------------------------------------------------ defect overlay
     def _marker_sprite(self, radius: int, b: int, g: int, r: int, label: bytes):
@@ -1032,7 +1241,7 @@ def _locked(fn):
 # The engine is shared process-wide (get_engine) and the reference's callers may sit on several threads (Streamlit runs
 # one script thread per session): every public entry point holds the engine's lock while it plans and enqueues.
 for _name in ("resize_batch_u8", "resize_u8", "reduce_u8", "resize_box_u8", "alpha_premultiply_", "resize_nearest_u8",
-              "resize_reducing_u8", "agent_inputs", "plan_batch", "preprocess", "preprocess_host", "plan_overlay", "annotate",
+              "resize_reducing_u8", "agent_inputs", "plan_batch", "preprocess", "preprocess_dual", "preprocess_host", "preprocess_jpeg", "plan_overlay", "annotate",
               "heatmap", "side_by_side", "status_stamp", "quality_stats"):
     setattr(Engine, _name, _locked(getattr(Engine, _name)))
 del _name

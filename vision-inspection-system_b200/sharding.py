@@ -52,7 +52,9 @@ def gather_patches(pixel_values: torch.Tensor, image_grid_thw: torch.Tensor, fra
     why it is not part of the headline metric.
     """
     import torch.distributed as dist
+    # `dst` and the ranks below are GROUP ranks; P2POp peers are GLOBAL ranks: translate (identity for the default group)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     dev = pixel_values.device
     ids = torch.as_tensor(list(frame_ids), dtype=torch.int64)
     grid = image_grid_thw.to(torch.int64).cpu()
@@ -67,7 +69,8 @@ def gather_patches(pixel_values: torch.Tensor, image_grid_thw: torch.Tensor, fra
     # (unbatched send/recv pairs on the default group are serialised one after the other)
     if rank != dst:
         if ids.numel():
-            ops = [dist.P2POp(dist.isend, payload, dst, group), dist.P2POp(dist.isend, pixel_values.contiguous(), dst, group)]
+            ops = [dist.P2POp(dist.isend, payload, peer(dst), group),
+                   dist.P2POp(dist.isend, pixel_values.contiguous(), peer(dst), group)]
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
         return None, None
@@ -81,7 +84,7 @@ def gather_patches(pixel_values: torch.Tensor, image_grid_thw: torch.Tensor, fra
             continue
         buf = torch.empty(frames * 4, dtype=torch.int64, device=dev)
         pv = torch.empty((rows, pixel_values.shape[1]), dtype=pixel_values.dtype, device=dev)
-        ops += [dist.P2POp(dist.irecv, buf, r, group), dist.P2POp(dist.irecv, pv, r, group)]
+        ops += [dist.P2POp(dist.irecv, buf, peer(r), group), dist.P2POp(dist.irecv, pv, peer(r), group)]
         pending.append((frames, buf, pv))
     if ops:
         for req in dist.batch_isend_irecv(ops):
@@ -98,4 +101,6 @@ def gather_patches(pixel_values: torch.Tensor, image_grid_thw: torch.Tensor, fra
             entries.append((int(ids_r[k]), grid_r[k], pv_r[at:at + n]))
             at += n
     entries.sort(key=lambda e: e[0])
+    if not entries:                                  # no rank had a frame
+        return pixel_values.new_zeros((0, pixel_values.shape[1])), torch.zeros((0, 3), dtype=torch.int64)
     return torch.cat([e[2] for e in entries]), torch.stack([e[1] for e in entries])
