@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 15
+#define VIS_B200_ABI_VERSION 16
 
 /* status codes */
 #define VIS_OK            0
@@ -198,7 +198,7 @@ typedef struct VisSched {            /* opaque to callers: filled by vis_sched_b
     int32_t out_mode;                /* VIS_SCHED_OUT_PIXEL_VALUES or VIS_SCHED_OUT_U8                              */
     int32_t h_pull;                  /* 1: 17..32 taps, the horizontal role pulls its window (no step masks)        */
     int32_t n_vwarps;                /* 16-slot kernel: vertical-pass warps of the launch (6 / 4 / 3: fewer for strong downscales) */
-    int32_t pad0;                    /* keeps the arrays below 8-byte aligned                                          */
+    int32_t dp_words;                /* > 0: packed-byte kernel (vis_fused_dp.cu), W words of 4 taps per window (4..9)  */
     VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
     VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_SUBS];
     VisSchedSeg   seg[VIS_SCHED_MAX_SEGS];
@@ -212,6 +212,8 @@ typedef struct VisFrameRef {         /* per frame of a scheduled launch (device 
 
 #define VIS_SCHED_OUT_PIXEL_VALUES 0   /* LUT + Qwen2-VL patch layout, fp32 (dst_h, dst_w multiples of 28)            */
 #define VIS_SCHED_OUT_U8           1   /* resized RGB uint8 HWC (dst_w multiple of 4): Image.resize / thumbnails      */
+#define VIS_SCHED_FLAG_DP4A    0x100   /* OR-ed into out_mode: serve 9+ tap geometries with the packed-byte (IDP.4A) kernel
+                                          instead of the 16-slot IMAD kernel (same results; the faster one where measured) */
 
 /* sizeof(VisSched), for bindings that treat it as an opaque byte buffer                  [host] */
 int vis_sched_sizeof(void);
@@ -224,6 +226,13 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
  * schedule's.                                                                             [host] */
 int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt, int per_index,
                            int32_t* rec, int64_t rec_capacity);
+/* records for the packed-byte kernel (sched.dp_words = words > 0): per output sample 3 limb rows of `words` 32-bit
+ * words, byte j of word q = that limb of the coefficient of input index 4 * ((end >> 2) - (words - 1) + q) + j, where
+ * `end` is the sample's scheduled window end; coefficient k = k0 + 256 k1 + 65536 k2, k0 / k1 unsigned bytes, k2 signed.
+ * rec: (out_size + 1) * vis_sched_record_stride_dp(words) int32.                              [host] */
+int vis_sched_record_stride_dp(int words);
+int vis_sched_pack_records_dp(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int words,
+                              int32_t* rec, int64_t rec_capacity);
 /* frames: DEVICE array; hrec / vrec: DEVICE records from vis_sched_pack_records.        [device] */
 int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,
                                const int32_t* hrec, const int32_t* vrec,

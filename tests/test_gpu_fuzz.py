@@ -89,3 +89,30 @@ def test_overlay_random_frames_and_boxes(engine):
     engine.annotate(devs, [b for _, b in items], inplace=True)
     for k, ((f, b), d) in enumerate(zip(items, devs)):
         assert np.array_equal(d.cpu().numpy(), OV.draw_bounding_boxes(f, b)), (k, f.shape, "in place")
+
+
+def test_both_kernel_families_for_long_windows(engine):
+    """9+ tap geometries are served by the packed-byte (IDP.4A) kernel by default and by the 16-slot IMAD kernel on
+    request: both bit-exact against the oracle — 4K at the default max_pixels (13 taps), bicubic 2x downscales, the
+    agents' LANCZOS thumbnails (13 and 25 taps), odd segment counts."""
+    frames4k = [synth.noise_frame(4000 + i, 2160, 3840) for i in range(3)]
+    want4k, wgrid = Q.preprocess(frames4k)
+    mid = [synth.noise_frame(4100 + i, 1536, 2048) for i in range(5)]
+    wantmid, _ = Q.preprocess(mid)
+    thumbs = [(2160, 3840, 2048), (2160, 3840, 1024), (1080, 1920, 1024), (1600, 2560, 1024), (1234, 3008, 1024)]
+    tframes = [synth.noise_frame(4200 + i, h, w) for i, (h, w, _) in enumerate(thumbs)]
+    try:
+        for dp in (True, False):
+            engine.use_dp4a(dp)
+            pv, grid = engine.preprocess(torch.from_numpy(np.stack(frames4k)).cuda())
+            assert np.array_equal(grid.numpy(), wgrid) and np.array_equal(pv.cpu().numpy(), want4k), ("4k", dp)
+            plan = engine.plan_batch(torch.from_numpy(np.stack(frames4k)).cuda())
+            assert not plan.generic and len(plan.fused) == 1
+            pv, _ = engine.preprocess(torch.from_numpy(np.stack(mid)).cuda(), vsplit=3)
+            assert np.array_equal(pv.cpu().numpy(), wantmid), ("1536x2048", dp)
+            for f, (h, w, limit) in zip(tframes, thumbs):
+                got = engine.agent_inputs([torch.from_numpy(f).cuda()], max_size=limit)[0]
+                assert engine.last_launches == 1, (h, w, limit, dp)
+                assert np.array_equal(got.cpu().numpy(), Q.agent_thumbnail(f, limit)), (h, w, limit, dp)
+    finally:
+        engine.use_dp4a(True)

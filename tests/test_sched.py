@@ -71,7 +71,7 @@ def replay(s, ht, vt, w, pitch, want_per, want_ring, unit):
     # after all of its taps have been read (p0 <= first tap), and the staged row segment covers the window
     covered = np.zeros(dw, np.int32)
     h_pull = int(hd["h_pull"])
-    assert h_pull == (1 if hd["kt"] > 16 else 0)
+    assert h_pull == (1 if hd["kt"] > 16 and not hd["dp_words"] else 0)       # the packed-byte kernel pushes every class
     if h_pull:                                            # pull-order H: no step masks, only the sub-range edges
         covered[:] = 1
     for st in range(hd["n_strips"]):
@@ -172,3 +172,58 @@ def test_schedule_declines_what_it_cannot_express(shape, max_pixels, why):
     pitch = w * 3 if why == b"pitch" else (w * 3 + 15) // 16 * 16
     rc, _, _, _ = build(h, w, dh, dw, pitch, 1)
     assert rc == N.VIS_E_UNSUPPORTED and why in N.lib().vis_last_error()
+
+
+@pytest.mark.parametrize("shape,out,filt,mode,want_words", [
+    ((2160, 3840), (728, 1316), N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES, 4),      # 13 taps
+    ((2160, 3840), (1152, 2048), N.FILTER_LANCZOS, N.SCHED_OUT_U8, 4),               # 13 taps
+    ((2160, 3840), (576, 1024), N.FILTER_LANCZOS, N.SCHED_OUT_U8, 7),                # 25 taps
+    ((1400, 1424), (1024, 1040), N.FILTER_LANCZOS, N.SCHED_OUT_U8, 4),               # 9..10 taps
+    ((1600, 2560), (640, 1024), N.FILTER_LANCZOS, N.SCHED_OUT_U8, 5),                # 17 taps
+    ((3000, 4000), (768, 1024), N.FILTER_LANCZOS, N.SCHED_OUT_U8, 7)])
+def test_packed_byte_records(shape, out, filt, mode, want_words):
+    """VIS_SCHED_FLAG_DP4A: the schedule names the packed-byte kernel with W words per window; its records hold every
+    coefficient as three byte limbs at the byte the kernel multiplies with that input sample, zero elsewhere — replayed
+    here with the kernel's arithmetic (three dot products of packed words, recombined mod 2^32) on random rows."""
+    import ctypes as C
+    (h, w), (dh, dw) = shape, out
+    pitch = (w * 3 + 15) // 16 * 16
+    rc, s, ht, vt = build(h, w, dh, dw, pitch, 2, filt, mode | N.SCHED_FLAG_DP4A)
+    assert rc == N.VIS_OK, N.lib().vis_last_error()
+    hd = s["head"]
+    words = int(hd["dp_words"])
+    assert words == want_words and hd["ring"] == 16 and hd["kt"] == 4 * words - 3 and hd["h_pull"] == 0
+    replay(s, ht, vt, w, pitch, 1, 16, 28 if mode == N.SCHED_OUT_PIXEL_VALUES else 4)
+    L = N.lib()
+    stride = L.vis_sched_record_stride_dp(words)
+    assert stride >= 3 * words and stride % 4 == 0
+    rng = np.random.default_rng(5)
+    for t in (ht, vt):
+        rec = np.zeros((t.out_size + 1, stride), np.int32)
+        N.check(L.vis_sched_pack_records_dp(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, words, N.i32ptr(rec),
+                                            rec.size), "vis_sched_pack_records_dp")
+        by = rec.view(np.uint8).reshape(t.out_size + 1, stride * 4)
+        k0 = by[:, :4 * words].astype(np.int64)
+        k1 = by[:, 4 * words:8 * words].astype(np.int64)
+        k2 = by[:, 8 * words:12 * words].view(np.int8).astype(np.int64)
+        coeff = k0 + 256 * k1 + 65536 * k2                       # [out + 1, 4 * words] coefficient per window byte
+        assert not coeff[t.out_size].any()                       # sentinel record
+        ends = np.zeros(t.out_size, np.int64)                    # the schedule's window ends (same rule as the builder)
+        e_prev = -1
+        for o in range(t.out_size):
+            e = max(int(t.bounds[o, 0] + t.bounds[o, 1] - 1), e_prev)
+            if e == e_prev:
+                e += 1
+            ends[o], e_prev = e, e
+        line = rng.integers(0, 256, t.in_size + 64, dtype=np.int64)          # samples past the border: weight 0
+        for o in list(range(0, t.out_size, max(1, t.out_size // 97))) + [t.out_size - 1, t.out_size - 2]:
+            first, taps = (int(v) for v in t.bounds[o])
+            base = 4 * ((int(ends[o]) >> 2) - (words - 1))
+            assert base <= first and first + taps - 1 <= ends[o] < base + 4 * words
+            full = np.zeros(4 * words, np.int64)
+            full[first - base:first - base + taps] = t.k[o, :taps]
+            assert np.array_equal(coeff[o], full), (o, first, taps)
+            px = np.array([line[base + j] if base + j >= 0 else 255 for j in range(4 * words)], np.int64)
+            acc = (1 << 21) + int((px * k0[o]).sum()) + (int((px * k1[o]).sum()) << 8) + (int((px * k2[o]).sum()) << 16)
+            want = (1 << 21) + int((line[first:first + taps] * t.k[o, :taps]).sum())
+            assert acc == want

@@ -26,7 +26,7 @@ LIB_PATH = PKG_DIR / "libvis_b200.so"
 OBJ_DIR = PKG_DIR.parent / "build" / "obj"
 
 SOURCES = ["vis_host.cpp", "vis_generic.cu", "vis_fused_ws.cu", "vis_fused_sched.cu", "vis_fused_sched16.cu",
-           "vis_dual.cu", "vis_overlay_host.cpp", "vis_overlay.cu", "vis_quality.cu", "vis_heatmap.cu", "vis_compose.cu",
+           "vis_fused_dp.cu", "vis_overlay_host.cpp", "vis_overlay.cu", "vis_quality.cu", "vis_heatmap.cu", "vis_compose.cu",
            "vis_jpeg.cpp"]
 
 NVCC_FLAGS = [
@@ -76,19 +76,19 @@ def is_stale() -> bool:
     return built_hash() != source_hash()
 
 
-def _compile_one(nvcc: str, src: Path, stamp: str, verbose: bool) -> Path:
+def _compile_one(nvcc: str, src: Path, stamp: str, verbose: bool, defines=(), obj_dir: Path = OBJ_DIR) -> Path:
     h = hashlib.sha256(src.read_bytes())
     for p in _headers():
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
-    extra = []
+    h.update(" ".join([*NVCC_FLAGS, *defines]).encode())
+    extra = list(defines)
     if src.name == "vis_host.cpp":                      # the one translation unit that carries the stamp
-        extra = [f'-DVIS_SOURCE_HASH_VALUE="{stamp}"']
+        extra.append(f'-DVIS_SOURCE_HASH_VALUE="{stamp}"')
         h.update(stamp.encode())
-    obj = OBJ_DIR / f"{src.stem}.{h.hexdigest()[:16]}.o"
+    obj = obj_dir / f"{src.stem}.{h.hexdigest()[:16]}.o"
     if obj.exists():
         return obj
-    for old in OBJ_DIR.glob(f"{src.stem}.*.o"):
+    for old in obj_dir.glob(f"{src.stem}.*.o"):
         old.unlink()
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", str(INCLUDE), "-I", str(CSRC), "-c", "-o", str(obj), str(src)]
     if verbose:
@@ -124,6 +124,28 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+def build_variant(name: str, defines: list) -> Path:
+    """Developer A/B builds: the same sources with extra -D flags -> variants/libvis_<name>.so (git-ignored; selected at
+    run time with VIS_B200_LIB=...).  Never what build() / the tests / bench.py load."""
+    nvcc = _nvcc()
+    out_dir = PKG_DIR.parent / "variants"
+    obj_dir = PKG_DIR.parent / "build" / f"obj_{name}"
+    out_dir.mkdir(exist_ok=True)
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    stamp = source_hash()
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(lambda s: _compile_one(nvcc, s, stamp, False, defines, obj_dir), _sources()))
+    out = out_dir / f"libvis_{name}.so"
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", *LINK_FLAGS, "-o", str(out), *map(str, objs)],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 if __name__ == "__main__":
-    out = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(out, built_hash())
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":      # build.py --variant name -DX=1 -DY=2
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        out = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(out, built_hash())

@@ -35,6 +35,15 @@ int sched16_launch(const VisSched& sc, const void* frames, int n_frames, int64_t
                    const float* lut768, float* pixel_values, cudaStream_t st);
 }
 
+namespace visf {   // packed-byte (IDP.4A) kernel, vis_fused_dp.cu
+int dp_subs();
+int dp_max_strip_w(int nv);
+int dp_layout_bytes(int stage_pitch, int strip_w, int words);
+int dp_record_stride(int words);
+int dp_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
+              const float* lut768, float* pixel_values, cudaStream_t st);
+}
+
 namespace {
 
 constexpr int kHWarps = VIS_SCHED_SUBS, kVWarps = 8, kSWarps = 3;
@@ -432,11 +441,13 @@ int vis_sched_sizeof(void) { return (int)sizeof(VisSched); }
 int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitch,
                     const int32_t* hb, const int32_t* vb, int vsplit, int out_mode, VisSched* out) {
     if (!hb || !vb || !out || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || vsplit < 1 ||
-        (out_mode != VIS_SCHED_OUT_PIXEL_VALUES && out_mode != VIS_SCHED_OUT_U8)) {
+        ((out_mode & 0xff) != VIS_SCHED_OUT_PIXEL_VALUES && (out_mode & 0xff) != VIS_SCHED_OUT_U8)) {
         vis::set_error("vis_sched_build: bad arguments");
         return VIS_E_INVALID;
     }
     auto unsupported = [](const char* why) { vis::set_error("vis_sched_build: %s", why); return VIS_E_UNSUPPORTED; };
+    const bool want_dp = (out_mode & VIS_SCHED_FLAG_DP4A) != 0;
+    out_mode &= 0xff;
     const bool u8 = out_mode == VIS_SCHED_OUT_U8;
     if (!u8 && (dst_h % 28 || dst_w % 28)) return unsupported("output size is not a multiple of 28");
     if (u8 && dst_w % 4) return unsupported("output width is not a multiple of 4");
@@ -451,13 +462,21 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     if (!u8) cls = mk <= 6 ? 6 : mk <= 8 ? 8 : cls == 20 ? 24 : cls == 28 ? 32 : cls;
     if (!cls) return unsupported("more than 32 taps");
     const int ring = cls <= 8 ? 8 : 16;
-    const bool h_pull = cls > 16;
-    const int n_subs = ring == 8 ? 12 : visf::sched16_subs();
-    // 16-slot kernel: fewer vertical-pass warps the stronger the vertical downscale (the V role gets lighter)
-    const double vscale = (double)src_h / dst_h;
-    const int n_vwarps = ring == 8 ? 0 : cls > 16 ? (vscale >= 3.4 ? 3 : 4) : (vscale >= 2.4 ? 4 : 6);
-    const int max_w = ring == 8 ? kMaxStripW : visf::sched16_max_strip_w(n_vwarps);
     std::vector<int> hl, vl;                      // scheduled window ends (virtual past the far border)
+    // packed-byte kernel: a window is W words of 4 taps ending in the word of its (virtual) end: any window of up to
+    // 4W - 3 taps fits whatever its alignment; W grows until the far-border samples (virtual ends) fit as well
+    int dp_words = 0;
+    if (want_dp && ring == 16) {
+        for (int w = (mk + 3 + 3) / 4 < 4 ? 4 : (mk + 3 + 3) / 4; w <= 9 && !dp_words; ++w)
+            if (schedule_ends(hb, dst_w, 4 * w - 3, 1, hl) && schedule_ends(vb, dst_h, 4 * w - 3, 1, vl)) dp_words = w;
+        if (dp_words) cls = 4 * dp_words - 3;
+    }
+    const bool h_pull = !dp_words && cls > 16;
+    const int n_subs = ring == 8 ? 12 : dp_words ? visf::dp_subs() : visf::sched16_subs();
+    // 16-slot kernels: fewer vertical-pass warps the stronger the vertical downscale (the V role gets lighter)
+    const double vscale = (double)src_h / dst_h;
+    const int n_vwarps = ring == 8 ? 0 : dp_words ? (vscale >= 2.4 ? 4 : 6) : cls > 16 ? (vscale >= 3.4 ? 3 : 4) : (vscale >= 2.4 ? 4 : 6);
+    const int max_w = ring == 8 ? kMaxStripW : dp_words ? visf::dp_max_strip_w(n_vwarps) : visf::sched16_max_strip_w(n_vwarps);
     int per_index = 1;
     // an exact class (13, 14) may be too tight for the virtual ends of the far-border samples: widen it
     while ((cls == 13 || cls == 14) && (!schedule_ends(hb, dst_w, cls, 1, hl) || !schedule_ends(vb, dst_h, cls, 1, vl)))
@@ -473,8 +492,8 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     std::memset(&s, 0, sizeof(s));
     s.src_h = src_h; s.src_w = src_w; s.dst_h = dst_h; s.dst_w = dst_w; s.src_pitch = src_pitch; s.kt = cls;
     s.per_index = per_index; s.ring = ring; s.n_subs = n_subs; s.out_mode = out_mode; s.h_pull = h_pull ? 1 : 0;
-    s.n_vwarps = n_vwarps;
-    const int stride = vis_record_stride(cls);
+    s.n_vwarps = n_vwarps; s.dp_words = dp_words;
+    const int stride = dp_words ? visf::dp_record_stride(dp_words) : vis_record_stride(cls);
     auto last = [](const int32_t* b, int i) { return b[2 * i] + b[2 * i + 1] - 1; };
     auto span_of = [&](int x0, int x1, int* px0) {
         *px0 = hb[2 * x0] & ~15;                                   // 48-byte aligned: bulk copies need 16
@@ -483,7 +502,8 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
         return bytes;
     };
     auto layout_bytes = [&](int pitch, int strip_w) {
-        return ring == 8 ? make_layout_s(pitch, strip_w, stride).total : visf::sched16_layout_bytes(pitch, strip_w, cls);
+        return ring == 8 ? make_layout_s(pitch, strip_w, stride).total
+                         : dp_words ? visf::dp_layout_bytes(pitch, strip_w, dp_words) : visf::sched16_layout_bytes(pitch, strip_w, cls);
     };
     // column strips: the fewest (widest, <= 336 columns) whose shared-memory layout fits; strip edges are multiples
     // of 28 columns (pixel_values: whole patches) or 4 columns (uint8 rows: whole 32-bit words of a plane)
@@ -558,7 +578,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
 
 int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int kt, int per_index,
                            int32_t* rec, int64_t rec_capacity) {
-    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || (kt != 6 && kt != 8 && kt != 13 && kt != 14 && (kt < 12 || kt > 32 || kt % 4)) ||
+    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || kt < 6 || kt > 33 ||
         per_index < 1 || per_index > 2) {
         vis::set_error("vis_sched_pack_records: bad arguments");
         return VIS_E_INVALID;
@@ -585,6 +605,52 @@ int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds
     return VIS_OK;
 }
 
+int vis_sched_record_stride_dp(int words) {
+    if (words < 4 || words > 9) return VIS_E_INVALID;
+    return visf::dp_record_stride(words);
+}
+
+int vis_sched_pack_records_dp(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int words,
+                              int32_t* rec, int64_t rec_capacity) {
+    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || words < 4 || words > 9) {
+        vis::set_error("vis_sched_pack_records_dp: bad arguments");
+        return VIS_E_INVALID;
+    }
+    const int stride = visf::dp_record_stride(words);
+    if (rec_capacity < (int64_t)(out_size + 1) * stride) {
+        vis::set_error("vis_sched_pack_records_dp: capacity too small");
+        return VIS_E_CAPACITY;
+    }
+    std::vector<int> ends;
+    if (!schedule_ends(bounds, out_size, 4 * words - 3, 1, ends)) {
+        vis::set_error("vis_sched_pack_records_dp: table is not schedulable with %d words (upscale or too many taps)", words);
+        return VIS_E_UNSUPPORTED;
+    }
+    std::memset(rec, 0, sizeof(int32_t) * (size_t)(out_size + 1) * stride);
+    for (int o = 0; o < out_size; ++o) {
+        const int first = bounds[2 * o], taps = bounds[2 * o + 1], end = ends[o];
+        const int base = 4 * ((end >> 2) - (words - 1));            // input index of byte 0 of word 0 (may be negative)
+        if (end < first + taps - 1 || first < base) {
+            vis::set_error("vis_sched_pack_records_dp: window of sample %d ([%d, %d), end %d) does not fit %d words", o, first,
+                           first + taps, end, words);
+            return VIS_E_UNSUPPORTED;
+        }
+        unsigned char* r = reinterpret_cast<unsigned char*>(rec + (size_t)o * stride);
+        for (int t = 0; t < taps; ++t) {
+            const int32_t c = k[(size_t)o * ksize + t];
+            if (c < -(1 << 23) || c >= (1 << 23)) {
+                vis::set_error("vis_sched_pack_records_dp: coefficient %d outside three byte limbs", c);
+                return VIS_E_UNSUPPORTED;
+            }
+            const int at = first + t - base;                         // byte position inside the W-word window
+            r[at] = (unsigned char)(c & 0xff);
+            r[4 * words + at] = (unsigned char)((c >> 8) & 0xff);
+            r[8 * words + at] = (unsigned char)((c >> 16) & 0xff);   // signed limb (arithmetic shift), two's complement byte
+        }
+    }
+    return VIS_OK;
+}
+
 int vis_preprocess_fused_sched_dup(const VisSched* sched, const VisFrameRef* frames, int n_frames,
                                    const int32_t* hrec, const int32_t* vrec,
                                    const float* lut768, float* pixel_values, const int64_t* dup_rows, void* stream) {
@@ -600,6 +666,7 @@ int vis_preprocess_fused_sched_dup(const VisSched* sched, const VisFrameRef* fra
             vis::set_error("vis_preprocess_fused_sched_dup: duplicate rows are served by the 8-slot kernel only (<= 8 taps)");
             return VIS_E_UNSUPPORTED;
         }
+        if (sched->dp_words) return dp_launch(*sched, frames, n_frames, 0, hrec, vrec, lut768, pixel_values, st);
         return sched16_launch(*sched, frames, n_frames, 0, hrec, vrec, lut768, pixel_values, st);
     }
     if (sched->ring != 8 || (sched->kt != 6 && sched->kt != 8)) {
@@ -631,6 +698,7 @@ int vis_resize_fused_sched(const VisSched* sched, const VisResizeRef* frames, in
         vis::set_error("vis_resize_fused_sched: bad arguments");
         return VIS_E_INVALID;
     }
+    if (sched->dp_words) return dp_launch(*sched, frames, n_frames, dst_pitch, hrec, vrec, nullptr, nullptr, (cudaStream_t)stream);
     return sched16_launch(*sched, frames, n_frames, dst_pitch, hrec, vrec, nullptr, nullptr, (cudaStream_t)stream);
 }
 

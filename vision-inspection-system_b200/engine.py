@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import os
 import threading
 from dataclasses import dataclass
 
@@ -85,8 +86,21 @@ class Engine:
         self._staging: dict = {}
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.last_launches = 0           # kernels launched by the most recent public call
+        # 9+ tap geometries: the packed-byte (IDP.4A) kernel unless VIS_B200_DP4A=0 selects the 16-slot IMAD kernel
+        # (developer A/B switch; both are bit-exact)
+        self.dp4a = os.environ.get("VIS_B200_DP4A", "1") != "0"
         self._lock = threading.RLock()   # public entry points are serialised: caches and staging buffers are shared
         self._tls = threading.local()    # per-thread state (nvJPEG handles are not thread-safe)
+
+    def use_dp4a(self, on: bool) -> None:
+        """Select the kernel family of 9+ tap geometries — packed bytes / IDP.4A (default) or the 16-slot IMAD kernel —
+        and drop every cached schedule and plan (A/B runs and the tests that keep both families green)."""
+        with self._lock:
+            self.dp4a = bool(on)
+            self._geoms.clear()
+            self._dev_tables.clear()
+            self._batch_plans.clear()
+            self.__dict__.pop("_dual_plans", None)
 
     # ------------------------------------------------------------------ tables
     def _device_table(self, in_size: int, out_size: int, filt: int):
@@ -134,28 +148,41 @@ class Engine:
                 best, best_score = segs, score
         return best
 
+    def _sched_records(self, head, tables) -> list:
+        """Device records of a scheduled launch for the (horizontal, vertical) coefficient tables, in the format of the
+        kernel the schedule names: packed byte limbs (dp_words > 0) or int32 coefficients."""
+        kt, per_index, words = int(head["kt"]), int(head["per_index"]), int(head["dp_words"])
+        out = []
+        for t in tables:
+            if words:
+                stride = N.check(self.L.vis_sched_record_stride_dp(words), "vis_sched_record_stride_dp")
+                rec = np.zeros((t.out_size + 1, stride), np.int32)
+                N.check(self.L.vis_sched_pack_records_dp(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, words,
+                                                         N.i32ptr(rec), rec.size), "vis_sched_pack_records_dp")
+            else:
+                stride = self.L.vis_record_stride(kt)
+                rec = np.zeros((t.out_size + 1, stride), np.int32)
+                N.check(self.L.vis_sched_pack_records(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, kt, per_index,
+                                                      N.i32ptr(rec), rec.size), "vis_sched_pack_records")
+            out.append(torch.from_numpy(rec).to(self.device))
+        return out
+
     def _sched(self, g: _Geometry, pitch: int, n_segs: int):
         """VisSched parameter block for (geometry, row pitch, row segments), or None if the geometry needs the
         general kernel (upscaling, > 8 taps, schedule too large)."""
         key = (pitch, n_segs)
         if key not in g.scheds:
             buf = np.zeros(self.L.vis_sched_sizeof(), np.uint8)
+            mode = N.SCHED_OUT_PIXEL_VALUES | (N.SCHED_FLAG_DP4A if self.dp4a else 0)
             rc = self.L.vis_sched_build(g.src_h, g.src_w, g.dst_h, g.dst_w, pitch, N.i32ptr(g.htable.bounds),
-                                        N.i32ptr(g.vtable.bounds), n_segs, N.SCHED_OUT_PIXEL_VALUES,
-                                        buf.ctypes.data_as(C.c_void_p))
+                                        N.i32ptr(g.vtable.bounds), n_segs, mode, buf.ctypes.data_as(C.c_void_p))
             if rc == N.VIS_E_UNSUPPORTED:
                 buf = None
             else:
                 N.check(rc, "vis_sched_build")
                 if not g.srec:
                     head = np.frombuffer(buf[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]
-                    kt, per_index = int(head["kt"]), int(head["per_index"])
-                    stride = self.L.vis_record_stride(kt)
-                    for t in (g.htable, g.vtable):
-                        rec = np.zeros((t.out_size + 1, stride), np.int32)
-                        N.check(self.L.vis_sched_pack_records(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, kt,
-                                                              per_index, N.i32ptr(rec), rec.size), "vis_sched_pack_records")
-                        g.srec.append(torch.from_numpy(rec).to(self.device))
+                    g.srec.extend(self._sched_records(head, (g.htable, g.vtable)))
             g.scheds[key] = buf
         return g.scheds[key]
 
@@ -171,22 +198,16 @@ class Engine:
         if G.pil_pass_order(src_h, src_w, out_h, out_w) == "hv":
             ht, vt = T.coeff_table(src_w, out_w, filt), T.coeff_table(src_h, out_h, filt)
             buf = np.zeros(self.L.vis_sched_sizeof(), np.uint8)
+            mode = N.SCHED_OUT_U8 | (N.SCHED_FLAG_DP4A if self.dp4a else 0)
             rc = self.L.vis_sched_build(src_h, src_w, out_h, out_w, pitch, N.i32ptr(ht.bounds), N.i32ptr(vt.bounds), n_segs,
-                                        N.SCHED_OUT_U8, buf.ctypes.data_as(C.c_void_p))
+                                        mode, buf.ctypes.data_as(C.c_void_p))
             if rc != N.VIS_E_UNSUPPORTED:
                 N.check(rc, "vis_sched_build")
                 rkey = ("rsrec", src_h, src_w, out_h, out_w, filt)
                 recs = self._dev_tables.get(rkey)
                 if recs is None:
-                    kt = int(np.frombuffer(buf[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]["kt"])
-                    stride = self.L.vis_record_stride(kt)
-                    recs = []
-                    for t in (ht, vt):
-                        rec = np.zeros((t.out_size + 1, stride), np.int32)
-                        N.check(self.L.vis_sched_pack_records(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, kt, 1,
-                                                              N.i32ptr(rec), rec.size), "vis_sched_pack_records")
-                        recs.append(torch.from_numpy(rec).to(self.device))
-                    self._dev_tables[rkey] = recs
+                    head = np.frombuffer(buf[:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]
+                    recs = self._dev_tables[rkey] = self._sched_records(head, (ht, vt))
                 hit = (buf, recs[0], recs[1])
         self._dev_tables[key] = hit
         return hit
