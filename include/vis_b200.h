@@ -179,7 +179,8 @@ int vis_preprocess_fused(const VisFrame* frames, int n_frames, const VisStrip* s
  * ------------------------------------------------------------------------------------------ */
 #define VIS_SCHED_MAX_STRIPS 16      /* column strips per frame (<= 336 output columns each)       */
 #define VIS_SCHED_MAX_SEGS   16      /* row segments per frame                                     */
-#define VIS_SCHED_SUBS       12      /* column sub-ranges per strip, at most (one per horizontal-pass warp) */
+#define VIS_SCHED_SUBS       12      /* column sub-ranges per strip of the 8- and 16-slot kernels (one per horizontal-pass warp) */
+#define VIS_SCHED_MAX_SUBS   20      /* ... at most (the packed-byte kernel runs 16 horizontal-pass warps)        */
 #define VIS_SCHED_MASK_BYTES 6144
 
 typedef struct VisSchedStrip { int32_t x0, x1, px0, row_bytes; } VisSchedStrip;
@@ -194,13 +195,13 @@ typedef struct VisSched {            /* opaque to callers: filled by vis_sched_b
     int32_t stage_pitch, max_strip_w;
     int32_t per_index;               /* 1: scale >= 1 on both axes; 2: mild upscale, two mask bytes are live per step */
     int32_t ring;                    /* register window of the kernel: 8 (<= 8 taps) or 16 (<= 16 taps)            */
-    int32_t n_subs;                  /* column sub-ranges per strip = horizontal-pass warps (12 / 9)               */
+    int32_t n_subs;                  /* column sub-ranges per strip = horizontal-pass warps of the kernel (12 / 16) */
     int32_t out_mode;                /* VIS_SCHED_OUT_PIXEL_VALUES or VIS_SCHED_OUT_U8                              */
     int32_t h_pull;                  /* 1: 17..32 taps, the horizontal role pulls its window (no step masks)        */
     int32_t n_vwarps;                /* 16-slot kernel: vertical-pass warps of the launch (6 / 4 / 3: fewer for strong downscales) */
     int32_t dp_words;                /* > 0: packed-byte kernel (vis_fused_dp.cu), W words of 4 taps per window (4..9)  */
     VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
-    VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_SUBS];
+    VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_MAX_SUBS];
     VisSchedSeg   seg[VIS_SCHED_MAX_SEGS];
     uint8_t       mask[VIS_SCHED_MASK_BYTES];
 } VisSched;

@@ -14,7 +14,7 @@ SUB = np.dtype([("xa", np.uint16), ("xb", np.uint16), ("p0", np.uint16), ("nstep
 STRIP = np.dtype([("x0", np.int32), ("x1", np.int32), ("px0", np.int32), ("row_bytes", np.int32)])
 SEG = np.dtype([("y0", np.int32), ("y1", np.int32), ("r_first", np.int32), ("r_end", np.int32), ("mask_off", np.int32),
                 ("pad", np.int32)])
-SCHED = np.dtype([("head", N.SCHED_HEAD_DTYPE), ("strip", STRIP, (16,)), ("sub", SUB, (16, 12)), ("seg", SEG, (16,)),
+SCHED = np.dtype([("head", N.SCHED_HEAD_DTYPE), ("strip", STRIP, (16,)), ("sub", SUB, (16, 20)), ("seg", SEG, (16,)),
                   ("mask", np.uint8, (6144,))], align=True)
 SEG_COUNT = 16
 

@@ -29,7 +29,11 @@ using namespace visf;
 
 namespace {
 
-constexpr int kHWarps = 12, kSWarps = 2;
+#ifndef VIS_DP_HWARPS
+#define VIS_DP_HWARPS 12
+#endif
+constexpr int kHWarps = VIS_DP_HWARPS, kSWarps = 2;     // A/B on 4K frames: 12 -> 70.4 k, 16 -> 66.2 k, 20 -> 65.4 k images/s (profiles/r02_dp_hwarps.txt)
+static_assert(kHWarps <= VIS_SCHED_MAX_SUBS, "schedule holds at most VIS_SCHED_MAX_SUBS sub-ranges per strip");
 // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
 constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
 constexpr int threads_dp(int nv) { return (kHWarps + nv + kSWarps + 1) * 32; }
