@@ -104,8 +104,30 @@ __device__ __forceinline__ void load_rec_dp(uint32_t (&k)[3 * W], uint32_t addr)
 }
 
 // one output byte: W packed words (4 taps each) against the record's three limb rows; Pillow's (acc + 2^21) >> 22, clip8
+#ifndef VIS_DP_SERIAL_LIMBS
+#define VIS_DP_SERIAL_LIMBS 0
+#endif
+__device__ __forceinline__ int shl8(int v) {        // funnel shift: stays on the ALU pipe (a plain << 8 becomes IMAD.SHL,
+    int d;                                          // which competes with IDP.4A for the one integer-MAC pipe)
+    asm("shf.l.clamp.b32 %0, %1, %2, 8;" : "=r"(d) : "r"(0), "r"(v));
+    return d;
+}
 template <int W>
 __device__ __forceinline__ int mac_dp(const uint32_t* px, const uint32_t (&k)[3 * W]) {
+#if VIS_DP_SERIAL_LIMBS
+    // Horner over the limbs: the accumulator of a limb starts from the finished higher limb << 8; the rounding constant
+    // 2^21 enters as 32 in the 2^16 limb.  No recombination on the MAC pipe.
+    int a = 1 << (VIS_PRECISION_BITS - 1 - 16);
+#pragma unroll
+    for (int q = 0; q < W; ++q) a = dp4a_us(px[q], k[2 * W + q], a);
+    a = shl8(a);
+#pragma unroll
+    for (int q = 0; q < W; ++q) a = dp4a_uu(px[q], k[W + q], a);
+    a = shl8(a);
+#pragma unroll
+    for (int q = 0; q < W; ++q) a = dp4a_uu(px[q], k[q], a);
+    return clip8i(a);
+#else
     int a0 = 1 << (VIS_PRECISION_BITS - 1), a1 = 0, a2 = 0;
 #pragma unroll
     for (int q = 0; q < W; ++q) {
@@ -114,6 +136,7 @@ __device__ __forceinline__ int mac_dp(const uint32_t* px, const uint32_t (&k)[3 
         a2 = dp4a_us(px[q], k[2 * W + q], a2);
     }
     return clip8i(a0 + (a1 << 8) + (a2 << 16));
+#endif
 }
 
 __device__ __noinline__ void band_done_dp(uint32_t bar0, int nb, int lane) {

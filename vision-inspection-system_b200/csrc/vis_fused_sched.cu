@@ -44,6 +44,10 @@ int dp_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_
               const float* lut768, float* pixel_values, cudaStream_t st);
 }
 
+#ifndef VIS_DP_NV_SPLIT
+#define VIS_DP_NV_SPLIT 2.4       // packed-byte kernel: 4 vertical-pass warps from this vertical scale on, 6 below
+#endif
+
 namespace {
 
 constexpr int kHWarps = VIS_SCHED_SUBS, kVWarps = 8, kSWarps = 3;
@@ -475,7 +479,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const int n_subs = ring == 8 ? 12 : dp_words ? visf::dp_subs() : visf::sched16_subs();
     // 16-slot kernels: fewer vertical-pass warps the stronger the vertical downscale (the V role gets lighter)
     const double vscale = (double)src_h / dst_h;
-    const int n_vwarps = ring == 8 ? 0 : dp_words ? (vscale >= 2.4 ? 4 : 6) : cls > 16 ? (vscale >= 3.4 ? 3 : 4) : (vscale >= 2.4 ? 4 : 6);
+    const int n_vwarps = ring == 8 ? 0 : dp_words ? (vscale >= VIS_DP_NV_SPLIT ? 4 : 6) : cls > 16 ? (vscale >= 3.4 ? 3 : 4) : (vscale >= 2.4 ? 4 : 6);
     const int max_w = ring == 8 ? kMaxStripW : dp_words ? visf::dp_max_strip_w(n_vwarps) : visf::sched16_max_strip_w(n_vwarps);
     int per_index = 1;
     // an exact class (13, 14) may be too tight for the virtual ends of the far-border samples: widen it
