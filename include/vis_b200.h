@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 16
+#define VIS_B200_ABI_VERSION 17
 
 /* status codes */
 #define VIS_OK            0
@@ -99,6 +99,22 @@ int vis_gather_u8(const uint8_t* src, int64_t src_pitch, int h, int w, int chann
  * or 2 (LA), alpha last.  forward != 0: c = MULDIV255(c, a) = ((t = c*a + 128) + (t >> 8)) >> 8; forward == 0:
  * c = min(255, 255*c / a) unless a is 0 or 255 (copied).                                               [device] */
 int vis_alpha_premultiply_u8(uint8_t* img, int64_t pitch, int h, int w, int channels, int forward, void* stream);
+
+/* Modes Pillow does not resample as 8 bits per channel — "I;16" / "I;16L" / "I;16B", "I" (int32), "F" (float32) — go
+ * through its double-precision passes (libImaging/Resample.c ImagingResampleHorizontal/Vertical_16bpc / _32bpc): that is
+ * what img.resize(new_size, LANCZOS) at utils/image_utils.py:75 runs for such frames.  vis_build_coeffs_f64 [host]: the
+ * normalised weights as doubles, k[out_size * ksize] (ksize = vis_coeff_ksize), bounds as vis_build_coeffs.
+ * vis_resample_hp [device]: one pass (vertical = 0: along rows, h rows of w samples -> out_size samples; vertical = 1:
+ * along columns), sum of pixel * k in tap order with one rounding per multiply and add, then ROUND_UP / the two CLIP8 byte
+ * writes of the 16-bit path / the float conversion, exactly as Pillow.  Single channel.                              */
+#define VIS_HP_U16LE 0
+#define VIS_HP_U16BE 1
+#define VIS_HP_I32   2
+#define VIS_HP_F32   3
+int vis_build_coeffs_f64(int in_size, int out_size, int filter, double* k, int32_t* bounds, int* ksize_out);
+int vis_resample_hp(const uint8_t* src, int64_t src_pitch, int h, int w, int kind, int vertical,
+                    uint8_t* dst, int64_t dst_pitch, int out_size, const double* k, const int32_t* bounds, int ksize,
+                    void* stream);
 
 /* Row re-pitch.  The fused kernels stage rows with bulk copies, which need a 16-byte aligned base and pitch; frames that
  * are not (a 502-pixel-wide RGB frame has 1506-byte rows) are copied, a whole batch per launch, into a caller-owned

@@ -234,3 +234,73 @@ def agent_thumbnail(frame: np.ndarray, max_size: int, box=None) -> np.ndarray:
         return frame
     tw, th = thumbnail_size(w, h, max_size)
     return resize_reducing(frame, th, tw, LANCZOS, box)
+
+
+def resize_hp(arr: np.ndarray, out_h: int, out_w: int, filt: int = LANCZOS) -> np.ndarray:
+    """Test infrastructure.  ``Image.resize((out_w, out_h), filt)`` for the single-channel modes Pillow resamples in
+    double precision — uint16 ("I;16"), int32 ("I"), float32 ("F") arrays — restating libImaging/Resample.c
+    ImagingResampleHorizontal/Vertical_16bpc and _32bpc: normalised double weights (precompute_coeffs without the
+    fixed-point conversion), ss += pixel * k in tap order, ROUND_UP (x86 cvttsd2si: INT_MIN when out of range), and for
+    the 16-bit path Pillow's two CLIP8 byte writes (low = CLIP8(ss % 256) with C remainder, high = CLIP8(ss >> 8))."""
+    import math
+
+    def table(in_size, out_size):
+        support0 = 3.0 if filt == LANCZOS else 2.0
+        scale = in_size / out_size
+        fs = max(scale, 1.0)
+        support = support0 * fs
+        rows = []
+        for o in range(out_size):
+            center = (o + 0.5) * scale
+            first = max(int(center - support + 0.5), 0)
+            last = min(int(center + support + 0.5), in_size)
+            w = []
+            for t in range(last - first):
+                x = (t + first - center + 0.5) * (1.0 / fs)
+                if filt == LANCZOS:
+                    def sinc(v):
+                        if v == 0.0:
+                            return 1.0
+                        v = v * math.pi
+                        return math.sin(v) / v
+                    w.append(sinc(x) * sinc(x / 3) if -3.0 <= x < 3.0 else 0.0)
+                else:
+                    a, x = -0.5, abs(x)
+                    w.append(((a + 2.0) * x - (a + 3.0)) * x * x + 1 if x < 1.0 else
+                             (((x - 5) * x + 8) * x - 4) * a if x < 2.0 else 0.0)
+            total = 0.0
+            for v in w:
+                total += v
+            rows.append((first, [v / total if total != 0.0 else v for v in w]))
+        return rows
+
+    def round_up(ss):
+        v = np.where(ss >= 0.0, ss + 0.5, ss - 0.5)
+        ok = (v > -2147483649.0) & (v < 2147483648.0)
+        return np.where(ok, np.trunc(np.where(ok, v, 0.0)), -2147483648.0).astype(np.int64)
+
+    def one_pass(a, out_size, axis):
+        a = np.moveaxis(a, axis, 0)
+        out = np.empty((out_size,) + a.shape[1:], a.dtype)
+        for o, (first, w) in enumerate(table(a.shape[0], out_size)):
+            ss = np.zeros(a.shape[1:], np.float64)
+            for t, k in enumerate(w):
+                ss = ss + a[first + t].astype(np.float64) * k
+            if a.dtype == np.uint16:
+                r = round_up(ss)
+                lo = np.clip(np.fmod(r, 256), 0, 255)            # C remainder keeps the sign of r
+                hi = np.clip(r >> 8, 0, 255)
+                out[o] = (lo + 256 * hi).astype(np.uint16)
+            elif a.dtype == np.int32:
+                out[o] = round_up(ss).astype(np.int32)
+            else:
+                out[o] = ss.astype(np.float32)
+        return np.moveaxis(out, 0, axis)
+
+    h, w = arr.shape
+    cur = arr
+    need_h, need_v = out_w != w, out_h != h                    # PIL:Image.py:2431-2435: tall frames go vertical first
+    order = ("vh" if (h > w * 100 and out_h < h) else "hv") if need_h and need_v else ("h" if need_h else "") + ("v" if need_v else "")
+    for axis in order:
+        cur = one_pass(cur, out_w, 1) if axis == "h" else one_pass(cur, out_h, 0)
+    return cur.copy()

@@ -192,3 +192,25 @@ def test_nearest_resize_matches_pillow_for_palette_images():
         assert N.lib().vis_nearest_table(in_size, in0, in1, out, N.i32ptr(a)) == 0
         assert oracle_lib().orc_nearest_table(in_size, in0, in1, out, b.ctypes.data_as(C.POINTER(C.c_int32))) == 0
         assert np.array_equal(a, b)
+
+
+def test_double_precision_modes_against_pillow():
+    """"I;16", "I" and "F" frames: Pillow resamples them in double precision (ImagingResample*_16bpc / _32bpc), which is
+    what the reference's resize_image (utils/image_utils.py:75) runs for them.  The oracle's restatement is bit-exact with
+    the installed Pillow, overshoot and the 16-bit path's two CLIP8 byte writes included."""
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    cases = [("I;16", rng.integers(0, 65536, (300, 400), dtype=np.uint16)),
+             ("I;16", np.where(rng.random((120, 500)) < 0.5, 0, 65535).astype(np.uint16)),      # overshoot both ways
+             ("I", rng.integers(-2 ** 31, 2 ** 31 - 1, (200, 300), dtype=np.int32)),              # out of range -> INT_MIN
+             ("I", rng.integers(-50000, 50000, (257, 333), dtype=np.int32)),
+             ("F", rng.normal(0, 1000, (300, 400)).astype(np.float32))]
+    for mode, arr in cases:
+        h, w = arr.shape
+        im = Image.fromarray(arr)
+        assert im.mode == mode
+        for (oh, ow), filt in (((h // 2, w // 2), Q.LANCZOS), ((h * 2 // 3, w - 7), Q.BICUBIC), ((h, w // 3), Q.LANCZOS),
+                               ((h + 40, w + 60), Q.LANCZOS)):
+            want = np.asarray(im.resize((ow, oh), Image.Resampling(filt)))
+            got = Q.resize_hp(arr, oh, ow, filt)
+            assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), (mode, oh, ow, filt)

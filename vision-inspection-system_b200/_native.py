@@ -61,6 +61,7 @@ assert SPRITE_DTYPE.itemsize == 40
 REPITCH_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("src_pitch", np.int64), ("dst_pitch", np.int64),
                           ("rows", np.int32), ("row_bytes", np.int32)], align=True)
 assert REPITCH_DTYPE.itemsize == 40
+HP_U16LE, HP_U16BE, HP_I32, HP_F32 = 0, 1, 2, 3
 RESIZE_COPY, RESIZE_AREA2, RESIZE_BILINEAR = 0, 1, 2
 JPEG_BACKEND_DEFAULT, JPEG_BACKEND_HYBRID, JPEG_BACKEND_GPU_HYBRID, JPEG_BACKEND_HARDWARE = 0, 1, 2, 3
 JPEG_CSS_444, JPEG_CSS_422, JPEG_CSS_420, JPEG_CSS_GRAY = 0, 1, 2, 6
@@ -83,7 +84,7 @@ EXPORTS = [
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
     "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn", "vis_overlay_sprite_expand", "vis_overlay_stamp_expand", "vis_overlay_plan_batch_sprites",
-    "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8", "vis_alpha_premultiply_u8", "vis_repitch_u8",
+    "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8", "vis_alpha_premultiply_u8", "vis_repitch_u8", "vis_build_coeffs_f64", "vis_resample_hp",
     "vis_jpeg_create", "vis_jpeg_destroy", "vis_jpeg_info", "vis_jpeg_decode", "vis_jpeg_decode_batch",
     "vis_jpeg_encode_bound", "vis_jpeg_encode",
 ]
@@ -148,7 +149,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 16:
+        if L.vis_abi_version() != 17:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -204,6 +205,8 @@ def _declare(L: C.CDLL) -> None:
     L.vis_gather_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
     L.vis_alpha_premultiply_u8.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.vis_repitch_u8.argtypes = [vp, C.c_int, C.c_int64, vp]
+    L.vis_build_coeffs_f64.argtypes = [C.c_int, C.c_int, C.c_int, vp, i32p, ip]
+    L.vis_resample_hp.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int, vp, vp, C.c_int, vp]
     L.vis_overlay_sprite_expand.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, vp, C.c_int, ip, ip, ip, ip, ip]
     L.vis_overlay_stamp_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, ip, ip, ip, ip, ip]
     L.vis_overlay_plan_batch_sprites.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int,

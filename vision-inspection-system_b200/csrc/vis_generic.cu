@@ -9,6 +9,7 @@
 // Arithmetic: Pillow ImagingResampleHorizontal_8bpc / ImagingResampleVertical_8bpc — int32 accumulate of
 // uint8 x 22-bit coefficients, +2^21, arithmetic >>22, clamp to 0..255, uint8 between the passes.
 #include <algorithm>
+#include <climits>
 
 #include "vis_internal.h"
 
@@ -204,6 +205,51 @@ __global__ void __launch_bounds__(256) k_repitch(const VisRepitch* __restrict__ 
     }
 }
 
+// Pillow's double-precision resample passes for the modes that are not 8 bits per channel (libImaging/Resample.c
+// ImagingResampleHorizontal/Vertical_16bpc and _32bpc — what img.resize(..., LANCZOS) at utils/image_utils.py:75 runs for
+// "I;16", "I" and "F" frames): ss = sum of pixel * k[x] in tap order, one rounding per multiply and per add (no FMA: the
+// reference's wheels target baseline x86-64), then the mode's conversion.  One thread per output sample; correctness path.
+__device__ __forceinline__ int round_up_x86(double f) {                 // ROUND_UP + x86 cvttsd2si (out of range: INT_MIN)
+    const double v = f >= 0.0 ? __dadd_rn(f, 0.5) : __dadd_rn(f, -0.5);
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+    return (int)v;
+}
+__device__ __forceinline__ int clip8_int(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+
+template <int KIND, bool VERT>
+__global__ void __launch_bounds__(256)
+k_resample_hp(const uint8_t* __restrict__ src, int64_t src_pitch, uint8_t* __restrict__ dst, int64_t dst_pitch, int out_w,
+              int out_h, const double* __restrict__ k, const int* __restrict__ bounds, int ksize) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= out_w || y >= out_h) return;
+    const int o = VERT ? y : x;
+    const int first = bounds[2 * o], taps = bounds[2 * o + 1];
+    const double* kk = k + (size_t)o * ksize;
+    constexpr int BPP = KIND <= VIS_HP_U16BE ? 2 : 4;
+    double ss = 0.0;
+    for (int t = 0; t < taps; ++t) {
+        const uint8_t* p = VERT ? src + (size_t)(first + t) * src_pitch + (size_t)x * BPP
+                                : src + (size_t)y * src_pitch + (size_t)(first + t) * BPP;
+        double v;
+        if (KIND == VIS_HP_U16LE) v = (double)(p[0] + (p[1] << 8));
+        else if (KIND == VIS_HP_U16BE) v = (double)(p[1] + (p[0] << 8));
+        else if (KIND == VIS_HP_I32) v = (double)*reinterpret_cast<const int*>(p);
+        else v = (double)*reinterpret_cast<const float*>(p);
+        ss = __dadd_rn(ss, __dmul_rn(v, kk[t]));
+    }
+    uint8_t* q = dst + (size_t)y * dst_pitch + (size_t)x * BPP;
+    if (KIND <= VIS_HP_U16BE) {
+        const int r = round_up_x86(ss);
+        const uint8_t lo = (uint8_t)clip8_int(r % 256), hi = (uint8_t)clip8_int(r >> 8);     // Pillow's two CLIP8s, as is
+        q[KIND == VIS_HP_U16LE ? 0 : 1] = lo;
+        q[KIND == VIS_HP_U16LE ? 1 : 0] = hi;
+    } else if (KIND == VIS_HP_I32) {
+        *reinterpret_cast<int*>(q) = round_up_x86(ss);
+    } else {
+        *reinterpret_cast<float*>(q) = (float)ss;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -346,6 +392,31 @@ int vis_repitch_u8(const VisRepitch* descs, int n, int64_t max_frame_bytes, void
     const int blocks = (int)std::min<int64_t>(1024, (max_frame_bytes / 16 + 255) / 256 + 1);
     k_repitch<<<dim3(blocks, n), 256, 0, (cudaStream_t)stream>>>(descs);
     return vis::check_launch("vis_repitch_u8");
+}
+
+int vis_resample_hp(const uint8_t* src, int64_t src_pitch, int h, int w, int kind, int vertical,
+                    uint8_t* dst, int64_t dst_pitch, int out_size, const double* k, const int32_t* bounds, int ksize,
+                    void* stream) {
+    const int bpp = (kind == VIS_HP_U16LE || kind == VIS_HP_U16BE) ? 2 : 4;
+    if (!src || !dst || !k || !bounds || h <= 0 || w <= 0 || out_size <= 0 || ksize <= 0 || kind < VIS_HP_U16LE || kind > VIS_HP_F32 ||
+        src_pitch < (int64_t)w * bpp || dst_pitch < (int64_t)(vertical ? w : out_size) * bpp ||
+        ((kind >= VIS_HP_I32) && (((uintptr_t)src | (uintptr_t)dst | (uintptr_t)src_pitch | (uintptr_t)dst_pitch) & 3))) {
+        vis::set_error("vis_resample_hp: bad arguments (%dx%d -> %d, kind %d)", w, h, out_size, kind);
+        return VIS_E_INVALID;
+    }
+    const int out_w = vertical ? w : out_size, out_h = vertical ? out_size : h;
+    const dim3 grid((out_w + 63) / 64, (out_h + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VIS_HP(K) (vertical ? k_resample_hp<K, true><<<grid, 256, 0, st>>>(src, src_pitch, dst, dst_pitch, out_w, out_h, k, bounds, ksize) \
+                            : k_resample_hp<K, false><<<grid, 256, 0, st>>>(src, src_pitch, dst, dst_pitch, out_w, out_h, k, bounds, ksize))
+    switch (kind) {
+        case VIS_HP_U16LE: VIS_HP(VIS_HP_U16LE); break;
+        case VIS_HP_U16BE: VIS_HP(VIS_HP_U16BE); break;
+        case VIS_HP_I32:   VIS_HP(VIS_HP_I32); break;
+        default:           VIS_HP(VIS_HP_F32); break;
+    }
+#undef VIS_HP
+    return vis::check_launch("vis_resample_hp");
 }
 
 }  // extern "C"

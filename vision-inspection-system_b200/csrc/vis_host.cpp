@@ -154,6 +154,39 @@ int vis_build_coeffs_box(int in_size, float in0, float in1, int out_size, int fi
     return VIS_OK;
 }
 
+// Pillow's precompute_coeffs for the modes it resamples in double precision (I;16, I, F — libImaging/Resample.c
+// ImagingResampleHorizontal_16bpc / _32bpc): the normalised weights stay doubles, nothing is converted to fixed point.
+int vis_build_coeffs_f64(int in_size, int out_size, int filter, double* k, int32_t* bounds, int* ksize_out) {
+    FilterDef f;
+    if (in_size <= 0 || out_size <= 0 || !k || !bounds || !filter_def(filter, &f)) {
+        set_error("vis_build_coeffs_f64: bad arguments (in=%d out=%d filter=%d)", in_size, out_size, filter);
+        return VIS_E_INVALID;
+    }
+    const Window win = window_for(0.f, (float)in_size, out_size, f);
+    const double inv_fs = 1.0 / win.filterscale;
+    for (int o = 0; o < out_size; ++o) {
+        const double center = (o + 0.5) * win.scale;
+        int first = (int)(center - win.support + 0.5);
+        if (first < 0) first = 0;
+        int last = (int)(center + win.support + 0.5);
+        if (last > in_size) last = in_size;
+        const int taps = last - first;
+        double* row = k + (size_t)o * win.ksize;
+        double total = 0.0;
+        for (int t = 0; t < taps; ++t) {
+            row[t] = f.fn((t + first - center + 0.5) * inv_fs);
+            total += row[t];
+        }
+        for (int t = 0; t < taps; ++t)
+            if (total != 0.0) row[t] /= total;
+        for (int t = taps; t < win.ksize; ++t) row[t] = 0.0;
+        bounds[2 * o] = first;
+        bounds[2 * o + 1] = taps;
+    }
+    if (ksize_out) *ksize_out = win.ksize;
+    return VIS_OK;
+}
+
 int vis_build_lut(const float mean[3], const float stdv[3], double rescale, float* lut768) {
     if (!mean || !stdv || !lut768) {
         set_error("vis_build_lut: null argument");

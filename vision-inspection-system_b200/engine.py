@@ -302,6 +302,38 @@ class Engine:
             self.last_launches += 1
         return cur.squeeze(-1) if squeeze else cur
 
+    def resize_hp(self, img: torch.Tensor, out_h: int, out_w: int, filt: int, kind: int) -> torch.Tensor:
+        """``Image.resize((out_w, out_h), filt)`` for the single-channel modes Pillow resamples in double precision:
+        ``img`` is the raw image memory as a CUDA uint8 tensor ``[H, W * bytes_per_pixel]`` (``kind``: N.HP_U16LE /
+        HP_U16BE for "I;16" / "I;16B", HP_I32 for "I", HP_F32 for "F").  Same pass order as the 8-bit path (horizontal
+        first; vertical first for frames more than 100x taller than wide), bit-exact with Pillow."""
+        self._check_u8(img)
+        bpp = 2 if kind in (N.HP_U16LE, N.HP_U16BE) else 4
+        if img.dim() != 2 or img.stride(1) != 1 or img.shape[1] % bpp:
+            raise ValueError("expected the raw image memory as a [H, W * bytes_per_pixel] uint8 tensor")
+        h, w = int(img.shape[0]), int(img.shape[1]) // bpp
+        sp = _stream_ptr()
+        cur, cur_h, cur_w = img, h, w
+        self.last_launches = 0
+        order = G.pil_pass_order(h, w, out_h, out_w)
+        if order == "":
+            return img.clone()
+        keep = []
+        for axis in order:
+            vertical = axis == "v"
+            k, b = T.coeff_table_f64(cur_h if vertical else cur_w, out_h if vertical else out_w, filt)
+            dk, db = torch.from_numpy(k).to(self.device), torch.from_numpy(b).to(self.device)
+            nh, nw = (out_h, cur_w) if vertical else (cur_h, out_w)
+            dst = torch.empty((nh, nw * bpp), dtype=torch.uint8, device=self.device)
+            N.check(self.L.vis_resample_hp(cur.data_ptr(), cur.stride(0), cur_h, cur_w, kind, 1 if vertical else 0,
+                                           dst.data_ptr(), dst.stride(0), out_h if vertical else out_w, dk.data_ptr(),
+                                           db.data_ptr(), k.shape[1], sp), "vis_resample_hp")
+            keep += [dk, db, cur]
+            cur, cur_h, cur_w = dst, nh, nw
+            self.last_launches += 1
+        self._keepalive_hp = keep
+        return cur
+
     def reduce_u8(self, img: torch.Tensor, factor, box=None) -> torch.Tensor:
         """``PIL.Image.reduce(factor, box)`` for a CUDA uint8 HWC tensor: integer box average (libImaging/Reduce.c)."""
         self._check_u8(img)
@@ -1261,7 +1293,7 @@ def _locked(fn):
 
 # The engine is shared process-wide (get_engine) and the reference's callers may sit on several threads (Streamlit runs
 # one script thread per session): every public entry point holds the engine's lock while it plans and enqueues.
-for _name in ("resize_batch_u8", "resize_u8", "reduce_u8", "resize_box_u8", "alpha_premultiply_", "resize_nearest_u8",
+for _name in ("resize_batch_u8", "resize_u8", "resize_hp", "reduce_u8", "resize_box_u8", "alpha_premultiply_", "resize_nearest_u8",
               "resize_reducing_u8", "agent_inputs", "plan_batch", "preprocess", "preprocess_dual", "preprocess_host", "preprocess_jpeg", "plan_overlay", "annotate",
               "heatmap", "side_by_side", "status_stamp", "quality_stats"):
     setattr(Engine, _name, _locked(getattr(Engine, _name)))

@@ -100,6 +100,8 @@ def validate_image(image_path: Path, allowed_extensions: list = None, max_size_m
 
 
 _CODECS = ("host", "nvjpeg")
+# modes Pillow resamples in double precision: (vis_resample_hp kind, bytes per pixel); tobytes() of "I" / "F" is native order
+_HP_MODES = {"I;16": (0, 2), "I;16L": (0, 2), "I;16B": (1, 2), "I": (2, 4), "F": (3, 4)}
 _JPEG_SUFFIXES = (".jpg", ".jpeg", ".jpe")
 
 
@@ -186,9 +188,19 @@ def _resample_pil(img: Image.Image, size: tuple[int, int], filt: int, box=None, 
         work, reducing_gap = img, None               # ... and without the reduce pre-pass
     elif mode in ("L", "RGB", "RGBX", "CMYK", "YCbCr", "HSV", "LAB", "La", "RGBa"):
         work = img
+    elif mode in _HP_MODES:
+        # "I;16", "I", "F": Pillow's double-precision passes (ImagingResample*_16bpc / _32bpc), one channel
+        if box != full or reducing_gap is not None:
+            raise NotImplementedError(f"box / reducing_gap resampling of mode {mode!r} images is not implemented")
+        kind, bpp = _HP_MODES[mode]
+        raw = np.frombuffer(img.tobytes(), np.uint8).reshape(img.size[1], img.size[0] * bpp)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            dev = torch.from_numpy(raw).cuda()
+        out = _engine().resize_hp(dev, size[1], size[0], int(filt), kind)
+        return Image.frombytes(mode, tuple(size), out.cpu().numpy().tobytes())
     else:
-        raise NotImplementedError(f"image mode {mode!r} is resampled by Pillow with a non-8bpc path that this "
-                                  "engine does not implement")
+        raise NotImplementedError(f"image mode {mode!r} is not resampled by this engine")
     bands = len(work.getbands())
     arr = np.frombuffer(work.tobytes(), np.uint8).reshape(work.size[1], work.size[0], bands)   # one host copy (read-only)
     with warnings.catch_warnings():

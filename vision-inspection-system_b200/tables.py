@@ -54,6 +54,19 @@ def coeff_table_box(in_size: int, in0: float, in1: float, out_size: int, filt: i
     return CoeffTable(in_size, out_size, filt, ksize, k, b, taps)
 
 
+@lru_cache(maxsize=64)
+def coeff_table_f64(in_size: int, out_size: int, filt: int):
+    """(k float64 [out_size, ksize], bounds int32 [out_size, 2]) — Pillow's double-precision weights, for the modes it
+    does not resample as 8 bits per channel ("I;16", "I", "F")."""
+    L = N.lib()
+    ksize = N.check(L.vis_coeff_ksize(in_size, out_size, filt), "vis_coeff_ksize")
+    k = np.zeros((out_size, ksize), np.float64)
+    b = np.zeros((out_size, 2), np.int32)
+    N.check(L.vis_build_coeffs_f64(in_size, out_size, filt, k.ctypes.data_as(C.c_void_p), N.i32ptr(b), None),
+            "vis_build_coeffs_f64")
+    return k, b
+
+
 def normalize_lut(mean=IMAGE_MEAN, std=IMAGE_STD, rescale: float = RESCALE_FACTOR) -> np.ndarray:
     m = np.asarray(mean, np.float32)
     s = np.asarray(std, np.float32)
