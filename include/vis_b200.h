@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 17
+#define VIS_B200_ABI_VERSION 18
 
 /* status codes */
 #define VIS_OK            0
@@ -390,10 +390,9 @@ int vis_quality_stats(const VisQualityFrame* frames, int n_frames, int max_h, in
  * (utils/image_utils.py:364-601): per-defect Gaussian heat with boosts, cv2.GaussianBlur of each defect region and
  * of the whole mask (float32, BORDER_REFLECT_101), max-composite, normalisation by the global maximum,
  * cv2.applyColorMap(COLORMAP_JET) and cv2.addWeighted(img, 0.6, colour, 0.4, 0).  Floating point: specified with a
- * tolerance (<= 2 levels where the 8-bit heat index flips), not bit-exact.
- * defects: HOST array in list order (the host mirror of the reference's per-defect scalar code fills it);
- * kernels: DEVICE float32 Gaussian kernels (cv2.getGaussianKernel values), indexed by koff; jet768: DEVICE BGR table;
- * scratch: DEVICE, (3*h*w + 1) floats; img / dst: DEVICE BGR uint8 HWC (dst may not alias img).      [device] */
+ * tolerance (+-1 on the 8-bit heat index = <= 2 output levels), not bit-exact.
+ * The host mirror of the reference's per-defect scalar code fills VisHeatDefect in list order;
+ * kernels: DEVICE float32 Gaussian kernels (cv2.getGaussianKernel values), indexed by koff; jet768: DEVICE BGR table. */
 typedef struct VisHeatDefect {
     int32_t kind;                    /* 0: box defect, 1: widespread (whole image, no blur)                      */
     int32_t x, y, w, h;              /* pixel box                                                                 */
@@ -401,10 +400,30 @@ typedef struct VisHeatDefect {
     int32_t ksize, koff, pad;        /* odd blur kernel size (1 = none) and its offset in kernels[]              */
     double  intensity, cx, cy, sigma;
 } VisHeatDefect;
-int vis_heatmap_overlay(const uint8_t* img, int64_t img_pitch, int h, int w,
-                        const VisHeatDefect* defects, int n_defects, const float* kernels,
-                        int final_ksize, int final_koff, const uint8_t* jet768,
-                        float* scratch, uint8_t* dst, int64_t dst_pitch, void* stream);
+typedef struct VisHeatItem {         /* one defect of one frame of a batch                                          */
+    VisHeatDefect d;
+    int32_t frame;                   /* index into frames[]                                                        */
+    int32_t pad;
+    int64_t tmp_off;                 /* float offset of its region buffer in tmp[] ((x2-x1)*(y2-y1) floats; box defects
+                                        with ksize > 1)                                                            */
+    int64_t tab_off;                 /* double offset of its two 1-D Gaussian factor tables in tabs[]: (x2-x1) + (y2-y1) */
+} VisHeatItem;
+typedef struct VisHeatFrame {
+    const uint8_t* src;              /* device BGR uint8 HWC                                                        */
+    uint8_t*       dst;              /* device BGR uint8 HWC (may not alias src)                                    */
+    int64_t        src_pitch, dst_pitch;
+    int32_t        h, w;
+    int64_t        plane_off;        /* float offset of this frame's h*w plane in heat[] / fa[] / fb[]              */
+    int32_t        final_ksize, final_koff;   /* whole-mask blur: odd size (1 = none) and offset in kernels[]        */
+} VisHeatFrame;
+/* The whole batch in six launches.  frames / items: DEVICE arrays (items in the reference's list order per frame; every
+ * region inside its frame, ksize odd and <= 51); max_w / max_h / max_rw / max_rh: maxima over the frames and the item
+ * regions (they size the grids); heat / fa / fb: plane_floats floats each; tmp / tabs: as the item offsets say;
+ * max_bits: n_frames words.  All scratch is the caller's; heat and max_bits are cleared here.          [device] */
+int vis_heatmap_batch(const VisHeatFrame* frames, int n_frames, const VisHeatItem* items, int n_items,
+                      int max_w, int max_h, int max_rw, int max_rh, int64_t plane_floats,
+                      const float* kernels, const uint8_t* jet768, float* heat, float* fa, float* fb,
+                      float* tmp, double* tabs, unsigned int* max_bits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Comparison panel and status stamp (SURVEY.md 8f "next" row 4).

@@ -1,4 +1,4 @@
-"""-m gpu: vis_heatmap_overlay (through the C ABI) against the arrays captured from the reference's own
+"""-m gpu: vis_heatmap_batch (through the C ABI) against the arrays captured from the reference's own
 create_heatmap_overlay and against the oracle.  Floating-point path: tolerance stated in test_oracle_heatmap.py
 (<= 2 levels, >= 99.5 % of the bytes identical)."""
 import numpy as np
@@ -46,3 +46,28 @@ def test_create_heatmap_overlay_files(engine, tmp_path):
     close_enough(cv2.imread(str(dst)), OH.create_heatmap_overlay(frame, defects, H.JET_BGR), "file round trip")
     with pytest.raises(ValueError, match="Failed to load image"):
         IU.create_heatmap_overlay(tmp_path / "missing.png", defects, dst)
+
+
+def test_batch_equals_per_frame_and_oracle(engine):
+    """heatmap_batch: mixed sizes, a frame without defects (plain copy), a widespread defect, many defects per frame —
+    six launches for the whole batch, every frame within the tolerance of the oracle and IDENTICAL to its own per-frame call."""
+    shapes = [(333, 517), (720, 1280), (97, 211), (1080, 1920), (480, 640), (600, 50)]
+    frames, defects = [], []
+    for i, shape in enumerate(shapes):
+        rng = np.random.default_rng(40 + i)
+        frames.append(rng.integers(0, 256, shape + (3,), dtype=np.uint8))
+        defects.append(synth.random_defects(rng, int(rng.integers(1, 7))))
+    defects[2] = []                                                                   # untouched copy
+    defects[4] = defects[4] + [{"bbox": None, "location": "corrosion on the entire surface", "safety_impact": "MODERATE",
+                                "confidence": "high"}]
+    dev = [torch.from_numpy(f).cuda() for f in frames]
+    outs = engine.heatmap_batch(dev, defects)
+    assert engine.last_launches == 6
+    for f, d, o, dv in zip(frames, defects, outs, dev):
+        got = o.cpu().numpy()
+        close_enough(got, OH.create_heatmap_overlay(f, d, H.JET_BGR), f.shape)
+        assert np.array_equal(engine.heatmap(dv, d).cpu().numpy(), got), f.shape          # batching changes nothing
+    assert np.array_equal(outs[2].cpu().numpy(), frames[2])
+    same = torch.from_numpy(np.stack([frames[3]] * 3)).cuda()                              # a [B, H, W, 3] tensor
+    outs3 = engine.heatmap_batch(same, [defects[3]] * 3)
+    assert all(torch.equal(o, outs[3]) for o in outs3)

@@ -24,6 +24,17 @@ def close_enough(got: np.ndarray, want: np.ndarray, what):
     assert float((diff == 0).mean()) >= MIN_EQUAL, (what, float((diff == 0).mean()))
 
 
+def test_tolerance_is_one_heat_index_step():
+    """Why MAX_LEVELS is 2 and not 1: the specification is +-1 on the 8-bit HEAT INDEX (float32 sums in a
+    different order flip `(heat / max * 255).astype(uint8)` at a truncation boundary).  One index step moves a JET channel
+    by at most 5 levels, the blend weighs the colour 0.4: round(0.4 * 5) = 2 output levels.  A tolerance of 1 output level
+    would demand identical indices, i.e. bit-identical float32 blurs, which cv2 itself does not give across SIMD paths."""
+    step = int(np.abs(np.diff(H.JET_BGR.astype(np.int32), axis=0)).max())
+    assert step == 5 and round(0.4 * step) == MAX_LEVELS
+    two_steps = int(np.abs(H.JET_BGR[2:].astype(np.int32) - H.JET_BGR[:-2].astype(np.int32)).max())
+    assert round(0.4 * two_steps) > MAX_LEVELS          # an index off by two would be caught
+
+
 def test_jet_table_matches_the_captured_one(arrays):
     assert np.array_equal(H.JET_BGR, arrays["jet_bgr"])
     cv2 = pytest.importorskip("cv2")

@@ -62,6 +62,10 @@ REPITCH_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("src_pitch", 
                           ("rows", np.int32), ("row_bytes", np.int32)], align=True)
 assert REPITCH_DTYPE.itemsize == 40
 HP_U16LE, HP_U16BE, HP_I32, HP_F32 = 0, 1, 2, 3
+HEAT_FRAME_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("src_pitch", np.int64), ("dst_pitch", np.int64),
+                             ("h", np.int32), ("w", np.int32), ("plane_off", np.int64), ("final_ksize", np.int32),
+                             ("final_koff", np.int32)], align=True)
+assert HEAT_FRAME_DTYPE.itemsize == 56
 RESIZE_COPY, RESIZE_AREA2, RESIZE_BILINEAR = 0, 1, 2
 JPEG_BACKEND_DEFAULT, JPEG_BACKEND_HYBRID, JPEG_BACKEND_GPU_HYBRID, JPEG_BACKEND_HARDWARE = 0, 1, 2, 3
 JPEG_CSS_444, JPEG_CSS_422, JPEG_CSS_420, JPEG_CSS_GRAY = 0, 1, 2, 6
@@ -82,7 +86,7 @@ EXPORTS = [
     "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
     "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_sched_record_stride_dp", "vis_sched_pack_records_dp", "vis_preprocess_fused_sched", "vis_preprocess_fused_sched_dup",
     "vis_resize_fused_sched",
-    "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_overlay",
+    "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_batch",
     "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn", "vis_overlay_sprite_expand", "vis_overlay_stamp_expand", "vis_overlay_plan_batch_sprites",
     "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8", "vis_alpha_premultiply_u8", "vis_repitch_u8", "vis_build_coeffs_f64", "vis_resample_hp",
     "vis_jpeg_create", "vis_jpeg_destroy", "vis_jpeg_info", "vis_jpeg_decode", "vis_jpeg_decode_batch",
@@ -149,7 +153,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 17:
+        if L.vis_abi_version() != 18:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -188,8 +192,8 @@ def _declare(L: C.CDLL) -> None:
     L.vis_overlay_tiles.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, ip, ip]
     L.vis_overlay_plan_batch.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int]
     L.vis_overlay_draw.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
-    L.vis_heatmap_overlay.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp,
-                                      C.c_int64, vp]
+    L.vis_heatmap_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, vp,
+                                    vp, vp, vp, vp]
     L.vis_quality_stats.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.vis_resize_linear_mode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.vis_linear_table.argtypes = [C.c_int, C.c_int, C.c_int, i32p, vp]

@@ -1,17 +1,24 @@
 // vis_heatmap.cu — device half of create_heatmap_overlay (utils/image_utils.py:320-604; SURVEY.md 8f "next" row 2).
 //
-// Per frame (one stream-ordered sequence, no synchronisation, caller-owned scratch of 3 float planes):
-//   k_heat_clear      heat = 0
-//   per defect        k_heat_local: analytic heat of the defect on its region (float64 exp, boosts, 4-sigma cut-off)
-//                     -> tmp_a; k_heat_blur_h / k_heat_blur_v: separable Gaussian (float32, BORDER_REFLECT_101 inside
-//                     the REGION, as cv2.GaussianBlur on the sliced array does); the vertical pass max-combines into
-//                     heat.  Widespread defects max-combine their Gaussian directly.
-//   final blur        k_heat_blur_h / k_heat_blur_v over the whole mask (reflect at the image border)
-//   k_heat_max        global maximum (non-negative floats: atomicMax on the bit pattern)
+// BATCH form (round 2): any number of frames and defects in SIX launches, whatever the batch size —
+//   k_heat_tables     per defect, the two 1-D factors of its Gaussian, exp(-(x-cx)^2 / 2 sigma^2) and the same in y, in
+//                     float64 like the reference's numpy expression (one exp per region column / row instead of one per
+//                     region pixel: the 2-D value is their product, within 2 ulp(double) of exp of the sum, long before
+//                     the float32 rounding that follows)
+//   k_heat_defect_h   analytic heat of a defect (intensity * Gaussian, boosts inside the box, min(1, .), 4-sigma cut-off,
+//                     all float64, cast to float32) evaluated straight into shared memory, reflected at the REGION
+//                     border as cv2.GaussianBlur on the sliced array does, and blurred horizontally; widespread defects
+//                     and 1-tap kernels max-combine into the heat plane directly
+//   k_heat_defect_v   vertical blur of every defect region, max-combined into its frame's heat plane (atomicMax on the
+//                     bit pattern: the values are non-negative floats)
+//   k_heat_final_h/v  the whole-mask blur (reflect at the image border) + the frame's maximum
 //   k_heat_colorize   idx = uint8(heat / max * 255) (truncation), JET colour, saturate(round(0.6*img + 0.4*colour))
+// Both blur passes are register tiled: a thread produces 8 consecutive outputs from one sliding window (8 FMA per pair of
+// shared-memory reads), the horizontal pass keeps its row de-interleaved by 8 so that lanes read consecutive words.
 // Floating point: cv2's separable filter accumulates in float32 in a SIMD-dependent order, so this path is specified
-// with a tolerance (tests: <= 2 levels on isolated pixels where the 8-bit heat index flips), not bit-exactness.
-// Bound: HBM (a few passes over H*W floats + the frame).
+// with a tolerance (+-1 on the 8-bit heat index = <= 2 output levels, tests/test_oracle_heatmap.py), not bit-exactness.
+// Bound: fp32 FMA issue — the reference's defects reach the sigma cap, so every defect is a ~50-tap separable blur over
+// a region of up to (8 sigma + 31)^2 pixels: ~640 M FMA per 1080p frame with 3-4 defects against ~140 MB of traffic.
 #include "vis_internal.h"
 
 namespace {
@@ -24,162 +31,271 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void k_heat_clear(float* __restrict__ p, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
-}
-
-// analytic heat of one defect on its region (row-major region buffer `out`, or max into `heat` for kind 1 / ksize 1)
-__global__ void __launch_bounds__(kT)
-k_heat_local(VisHeatDefect d, int img_w, float* __restrict__ out, float* __restrict__ heat, int direct) {
-    const int rw = d.x2 - d.x1, rh = d.y2 - d.y1;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rw * rh) return;
-    const int ly = i / rw, lx = i - ly * rw;
-    const int gx = d.x1 + lx, gy = d.y1 + ly;
-    const double ddx = (double)gx - d.cx, ddy = (double)gy - d.cy;
-    const double dist_sq = ddx * ddx + ddy * ddy;
-    float v;
-    if (d.kind == 1) {
-        v = (float)(d.intensity * exp(-dist_sq / (2.0 * (d.sigma * d.sigma))));
-    } else {
-        double g = d.intensity * exp(-dist_sq / (2.0 * (d.sigma * d.sigma)));
-        const bool in_box = gx >= d.x && gx < d.x + d.w && gy >= d.y && gy < d.y + d.h;
-        const double ex = ddx / fmax(d.w / 2.0, 1.0), ey = ddy / fmax(d.h / 2.0, 1.0);
-        const double boost = (ex * ex + ey * ey < 1.2 * 1.2) ? 1.8 : (in_box ? 1.4 : 1.0);
-        g = fmin(1.0, g * boost);
-        const double lim = 4.0 * d.sigma;
-        v = dist_sq < lim * lim ? (float)g : 0.f;
-    }
-    if (direct) {
-        float* h = heat + (size_t)gy * img_w + gx;
-        *h = fmaxf(*h, v);
-    } else {
-        out[i] = v;
-    }
-}
-
-// separable Gaussian on a region of `rw` x `rh` floats with pitch `pitch` (elements); BORDER_REFLECT_101 inside the
-// region.  Both passes stage their inputs in shared memory (each input element is read from global memory ~1.2x
-// instead of ksize times) and accumulate taps in kernel order with fmaf.
 constexpr int kBlurR = 25;                       // largest radius (ksize <= 51)
-constexpr int kHSeg = 256;                       // outputs per block of the horizontal pass
-constexpr int kVCols = 32, kVRows = 64;          // tile of the vertical pass
+constexpr int kOut = 8;                          // outputs per thread of both passes
+constexpr int kHSeg = 512, kHRows = 4;           // horizontal pass: 4 rows x 512 outputs per block (64 threads per row)
+constexpr int kHLen = kHSeg + 2 * kBlurR + 6;    // staged row, padded to a multiple of 8 (568)
+constexpr int kHPhase = kHLen / kOut;            // 71: element i lives at (i % 8) * 71 + i / 8 -> lanes read consecutive words
+constexpr int kVCols = 32, kVRows = 64;          // vertical pass: 32 columns x 64 output rows per block
+constexpr int kVTile = kVRows + 56;              // rows staged: the last thread's rounded window ends at row 56 + 63
+constexpr int kWPad = kOut - 1;                  // zero weights in front of / behind the kernel: no tap predicates
+static_assert(kHLen % kOut == 0, "staged row must de-interleave evenly");
 
-__global__ void __launch_bounds__(kT)
-k_heat_blur_h(const float* __restrict__ src, int src_pitch, float* __restrict__ dst, int dst_pitch, int rw, int rh,
-              const float* __restrict__ kern, int ksize) {
-    __shared__ float row[kHSeg + 2 * kBlurR];
-    __shared__ float kk[2 * kBlurR + 1];
-    const int y = blockIdx.y, x0 = blockIdx.x * kHSeg, r = ksize >> 1;
-    const float* in = src + (size_t)y * src_pitch;
-    for (int i = threadIdx.x; i < kHSeg + 2 * r; i += kT) row[i] = in[reflect101(x0 + i - r, rw)];
-    if (threadIdx.x < ksize) kk[threadIdx.x] = __ldg(kern + threadIdx.x);
-    __syncthreads();
-    const int x = x0 + threadIdx.x;
-    if (x >= rw) return;
-    float s = 0.f;
-    for (int k = 0; k < ksize; ++k) s = fmaf(kk[k], row[threadIdx.x + k], s);
-    dst[(size_t)y * dst_pitch + x] = s;
-}
-// vertical pass; combine: 0 = store, 1 = max into dst
-__global__ void __launch_bounds__(kT)
-k_heat_blur_v(const float* __restrict__ src, int src_pitch, float* __restrict__ dst, int dst_pitch, int rw, int rh,
-              const float* __restrict__ kern, int ksize, int combine) {
-    __shared__ float tile[kVRows + 2 * kBlurR][kVCols];
-    __shared__ float kk[2 * kBlurR + 1];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8 threads
-    const int x = blockIdx.x * kVCols + tx, y0 = blockIdx.y * kVRows, r = ksize >> 1;
-    for (int i = ty; i < kVRows + 2 * r; i += kT / 32)
-        tile[i][tx] = x < rw ? src[(size_t)reflect101(y0 + i - r, rh) * src_pitch + x] : 0.f;
-    if (threadIdx.x < ksize) kk[threadIdx.x] = __ldg(kern + threadIdx.x);
-    __syncthreads();
-    if (x >= rw) return;
-    for (int j = ty; j < kVRows; j += kT / 32) {
-        const int y = y0 + j;
-        if (y >= rh) break;
-        float s = 0.f;
-        for (int k = 0; k < ksize; ++k) s = fmaf(kk[k], tile[j + k][tx], s);
-        float* o = dst + (size_t)y * dst_pitch + x;
-        *o = combine ? fmaxf(*o, s) : s;
+constexpr int kWLen = kWPad + 64 + 8;           // padded weights: kWPad zeros, the kernel, zeros up to the rounded window
+__device__ __forceinline__ void load_weights(float* wp, const float* __restrict__ kern, int ksize) {
+    for (int i = threadIdx.x; i < kWLen; i += kT) {
+        const int t = i - kWPad;
+        wp[i] = (t >= 0 && t < ksize) ? __ldg(kern + t) : 0.f;
     }
 }
 
+// analytic heat of a box defect / widespread defect at region-local (lx, ly), float64 like the reference, from the 1-D tables
+__device__ __forceinline__ float heat_value(const VisHeatDefect& d, const double* __restrict__ tx, const double* __restrict__ ty,
+                                            int lx, int ly) {
+    const int gx = d.x1 + lx, gy = d.y1 + ly;
+    const double g0 = d.intensity * (tx[lx] * ty[ly]);
+    if (d.kind == 1) return (float)g0;
+    const double ddx = (double)gx - d.cx, ddy = (double)gy - d.cy;
+    const bool in_box = gx >= d.x && gx < d.x + d.w && gy >= d.y && gy < d.y + d.h;
+    const double ex = ddx / fmax(d.w / 2.0, 1.0), ey = ddy / fmax(d.h / 2.0, 1.0);
+    const double boost = (ex * ex + ey * ey < 1.2 * 1.2) ? 1.8 : (in_box ? 1.4 : 1.0);
+    const double g = fmin(1.0, g0 * boost);
+    const double lim = 4.0 * d.sigma;
+    return (ddx * ddx + ddy * ddy) < lim * lim ? (float)g : 0.f;
+}
+
+__global__ void __launch_bounds__(kT) k_heat_tables(const VisHeatItem* __restrict__ items, double* __restrict__ tabs) {
+    const VisHeatItem& it = items[blockIdx.y];
+    const int rw = it.d.x2 - it.d.x1, rh = it.d.y2 - it.d.y1;
+    const int t = blockIdx.x * kT + threadIdx.x;
+    if (t >= rw + rh) return;
+    const double c = t < rw ? (double)(it.d.x1 + t) - it.d.cx : (double)(it.d.y1 + t - rw) - it.d.cy;
+    tabs[it.tab_off + t] = exp(-(c * c) / (2.0 * (it.d.sigma * it.d.sigma)));
+}
+
+// 8 outputs from one sliding window: value(k) for k = 0 .. n-1 with n = 8 + 2r rounded up to 8 (the surplus meets zero
+// weights and zero-filled staging).  Weights sit in a 15-register window that advances 8 taps per block of 8 values, so
+// a block is 8 value reads + 2 vector weight reads for 64 FMA; output j accumulates its taps in ascending order.
+template <typename F>
+__device__ __forceinline__ void window8(float (&acc)[kOut], const float* wp, int r, F value) {
+#pragma unroll
+    for (int j = 0; j < kOut; ++j) acc[j] = 0.f;
+    float w[2 * kOut - 1];
+#pragma unroll
+    for (int j = 0; j < kOut - 1; ++j) w[j] = wp[j];              // taps -7 .. -1 of the padded kernel (zeros)
+    const int n = (kOut + 2 * r + kOut - 1) & ~(kOut - 1);
+#pragma unroll 1
+    for (int kb = 0; kb < n; kb += kOut) {
+#pragma unroll
+        for (int q = 0; q < kOut; ++q) w[kOut - 1 + q] = wp[kWPad + kb + q];
+        // w[i] = weight of tap (kb + i - 7): output j at value kb + kk uses tap kb + kk - j -> w[7 + kk - j]
+#pragma unroll
+        for (int kk = 0; kk < kOut; ++kk) {
+            const float v = value(kb + kk);
+#pragma unroll
+            for (int j = 0; j < kOut; ++j) acc[j] = fmaf(w[kOut - 1 + kk - j], v, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kOut - 1; ++j) w[j] = w[j + kOut];
+    }
+}
+
+__device__ __forceinline__ void atomic_max_f(float* p, float v) {      // non-negative floats: bit order = value order
+    atomicMax(reinterpret_cast<unsigned int*>(p), __float_as_uint(fmaxf(v, 0.f)));
+}
+
 __global__ void __launch_bounds__(kT)
-k_heat_max(const float* __restrict__ p, size_t n, unsigned int* __restrict__ out) {
+k_heat_defect_h(const VisHeatItem* __restrict__ items, const VisHeatFrame* __restrict__ frames, const double* __restrict__ tabs,
+                const float* __restrict__ kernels, float* __restrict__ tmp, float* __restrict__ heat) {
+    __shared__ float rows[kHRows][kHLen];
+    __shared__ float wp[kWLen];
+    const VisHeatItem& it = items[blockIdx.z];
+    const VisHeatDefect& d = it.d;
+    const int rw = d.x2 - d.x1, rh = d.y2 - d.y1;
+    const int x0 = blockIdx.x * kHSeg, y0 = blockIdx.y * kHRows;
+    if (x0 >= rw || y0 >= rh) return;
+    const double* tx = tabs + it.tab_off;
+    const double* ty = tx + rw;
+    const VisHeatFrame& fr = frames[it.frame];
+    const bool direct = d.kind == 1 || d.ksize == 1;
+    if (direct) {                                      // no blur: max-combine the analytic heat itself
+        float* plane = heat + fr.plane_off;
+        for (int i = threadIdx.x; i < kHRows * kHSeg; i += kT) {
+            const int ly = y0 + i / kHSeg, lx = x0 + i % kHSeg;
+            if (ly < rh && lx < rw) atomic_max_f(plane + (size_t)(d.y1 + ly) * fr.w + d.x1 + lx, heat_value(d, tx, ty, lx, ly));
+        }
+        return;
+    }
+    const int r = d.ksize >> 1;
+    load_weights(wp, kernels + d.koff, d.ksize);
+    const int span = kHSeg + 2 * r;
+    for (int i = threadIdx.x; i < kHRows * kHLen; i += kT) {             // the padding behind `span` is zero-filled
+        const int row = i / kHLen, idx = i - row * kHLen;
+        const int ly = y0 + row;
+        float v = 0.f;
+        if (ly < rh && idx < span) v = heat_value(d, tx, ty, reflect101(x0 + idx - r, rw), ly);
+        rows[row][(idx % kOut) * kHPhase + idx / kOut] = v;
+    }
+    __syncthreads();
+    const int row = threadIdx.x >> 6, c = threadIdx.x & 63;
+    const int ly = y0 + row, lx = x0 + c * kOut;
+    if (ly >= rh || lx >= rw) return;
+    float acc[kOut];
+    const float* rp = rows[row];
+    window8(acc, wp, r, [&](int k) { const int i = c * kOut + k; return rp[(i % kOut) * kHPhase + i / kOut]; });
+    float* o = tmp + it.tmp_off + (size_t)ly * rw + lx;
+#pragma unroll
+    for (int j = 0; j < kOut; ++j)
+        if (lx + j < rw) o[j] = acc[j];
+}
+
+// vertical pass of a defect region: tmp -> max into the frame's heat plane
+__global__ void __launch_bounds__(kT)
+k_heat_defect_v(const VisHeatItem* __restrict__ items, const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels,
+                const float* __restrict__ tmp, float* __restrict__ heat) {
+    __shared__ float tile[kVTile][kVCols];
+    __shared__ float wp[kWLen];
+    const VisHeatItem& it = items[blockIdx.z];
+    const VisHeatDefect& d = it.d;
+    if (d.kind == 1 || d.ksize == 1) return;
+    const int rw = d.x2 - d.x1, rh = d.y2 - d.y1;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int x = blockIdx.x * kVCols + lane, y0 = blockIdx.y * kVRows;
+    if (blockIdx.x * kVCols >= rw || y0 >= rh) return;
+    const int r = d.ksize >> 1;
+    load_weights(wp, kernels + d.koff, d.ksize);
+    const float* src = tmp + it.tmp_off;
+    for (int i = grp; i < kVTile; i += kT / 32)                            // rows behind the window are zero-filled
+        tile[i][lane] = (x < rw && i < kVRows + 2 * r) ? src[(size_t)reflect101(y0 + i - r, rh) * rw + x] : 0.f;
+    __syncthreads();
+    if (x >= rw) return;
+    float acc[kOut];
+    window8(acc, wp, r, [&](int k) { return tile[grp * kOut + k][lane]; });
+    const VisHeatFrame& fr = frames[it.frame];
+    float* plane = heat + fr.plane_off;
+#pragma unroll
+    for (int j = 0; j < kOut; ++j) {
+        const int y = y0 + grp * kOut + j;
+        if (y < rh) atomic_max_f(plane + (size_t)(d.y1 + y) * fr.w + d.x1 + x, acc[j]);
+    }
+}
+
+// whole-mask blur, horizontal: heat -> fa (reflect at the image border)
+__global__ void __launch_bounds__(kT)
+k_heat_final_h(const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels, const float* __restrict__ heat,
+               float* __restrict__ fa) {
+    __shared__ float rows[kHRows][kHLen];
+    __shared__ float wp[kWLen];
+    const VisHeatFrame& fr = frames[blockIdx.z];
+    const int x0 = blockIdx.x * kHSeg, y0 = blockIdx.y * kHRows;
+    if (x0 >= fr.w || y0 >= fr.h) return;
+    const int r = fr.final_ksize >> 1;
+    load_weights(wp, kernels + fr.final_koff, fr.final_ksize);
+    const float* plane = heat + fr.plane_off;
+    const int span = kHSeg + 2 * r;
+    for (int i = threadIdx.x; i < kHRows * kHLen; i += kT) {
+        const int row = i / kHLen, idx = i - row * kHLen;
+        const int y = y0 + row;
+        rows[row][(idx % kOut) * kHPhase + idx / kOut] =
+            (y < fr.h && idx < span) ? plane[(size_t)y * fr.w + reflect101(x0 + idx - r, fr.w)] : 0.f;
+    }
+    __syncthreads();
+    const int row = threadIdx.x >> 6, c = threadIdx.x & 63;
+    const int y = y0 + row, x = x0 + c * kOut;
+    if (y >= fr.h || x >= fr.w) return;
+    float acc[kOut];
+    const float* rp = rows[row];
+    window8(acc, wp, r, [&](int k) { const int i = c * kOut + k; return rp[(i % kOut) * kHPhase + i / kOut]; });
+    float* o = fa + fr.plane_off + (size_t)y * fr.w + x;
+#pragma unroll
+    for (int j = 0; j < kOut; ++j)
+        if (x + j < fr.w) o[j] = acc[j];
+}
+
+// whole-mask blur, vertical: fa -> fb, and the frame's maximum
+__global__ void __launch_bounds__(kT)
+k_heat_final_v(const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels, const float* __restrict__ fa,
+               float* __restrict__ fb, unsigned int* __restrict__ max_bits) {
+    __shared__ float tile[kVTile][kVCols];
+    __shared__ float wp[kWLen];
+    const VisHeatFrame& fr = frames[blockIdx.z];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int x = blockIdx.x * kVCols + lane, y0 = blockIdx.y * kVRows;
+    if (blockIdx.x * kVCols >= fr.w || y0 >= fr.h) return;
+    const int r = fr.final_ksize >> 1;
+    load_weights(wp, kernels + fr.final_koff, fr.final_ksize);
+    const float* src = fa + fr.plane_off;
+    for (int i = grp; i < kVTile; i += kT / 32)
+        tile[i][lane] = (x < fr.w && i < kVRows + 2 * r) ? src[(size_t)reflect101(y0 + i - r, fr.h) * fr.w + x] : 0.f;
+    __syncthreads();
     float m = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, p[i]);
+    if (x < fr.w) {
+        float acc[kOut];
+        window8(acc, wp, r, [&](int k) { return tile[grp * kOut + k][lane]; });
+        float* o = fb + fr.plane_off;
+#pragma unroll
+        for (int j = 0; j < kOut; ++j) {
+            const int y = y0 + grp * kOut + j;
+            if (y < fr.h) {
+                o[(size_t)y * fr.w + x] = acc[j];
+                m = fmaxf(m, acc[j]);
+            }
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));     // non-negative: bit order = value order
+    if (lane == 0 && m > 0.f) atomicMax(max_bits + blockIdx.z, __float_as_uint(m));
 }
 
 __global__ void __launch_bounds__(kT)
-k_heat_colorize(const uint8_t* __restrict__ img, int64_t img_pitch, const float* __restrict__ heat, int w, int h,
-                const unsigned int* __restrict__ max_bits, const uint8_t* __restrict__ jet, uint8_t* __restrict__ dst,
-                int64_t dst_pitch) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * h) return;
-    const int y = i / w, x = i - y * w;
-    const float mx = __uint_as_float(*max_bits);
-    const float v = heat[i];
-    // numpy: (heat / max * 255).astype(uint8) in float32, truncation toward zero
-    const float t = mx > 0.f ? __fmul_rn(__fdiv_rn(v, mx), 255.f) : __fmul_rn(v, 255.f);
-    const int idx = min(max((int)t, 0), 255);
-    const uint8_t* s = img + (size_t)y * img_pitch + (size_t)x * 3;
-    uint8_t* o = dst + (size_t)y * dst_pitch + (size_t)x * 3;
+k_heat_colorize(const VisHeatFrame* __restrict__ frames, const float* __restrict__ fb, const unsigned int* __restrict__ max_bits,
+                const uint8_t* __restrict__ jet) {
+    const VisHeatFrame& fr = frames[blockIdx.y];
+    const float mx = __uint_as_float(max_bits[blockIdx.y]);
+    const float* plane = fb + fr.plane_off;
+    const long long n = (long long)fr.w * fr.h;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+        const int y = (int)(i / fr.w), x = (int)(i - (long long)y * fr.w);
+        const float v = plane[i];
+        // numpy: (heat / max * 255).astype(uint8) in float32, truncation toward zero
+        const float t = mx > 0.f ? __fmul_rn(__fdiv_rn(v, mx), 255.f) : __fmul_rn(v, 255.f);
+        const int idx = min(max((int)t, 0), 255);
+        const uint8_t* s = fr.src + (size_t)y * fr.src_pitch + (size_t)x * 3;
+        uint8_t* o = fr.dst + (size_t)y * fr.dst_pitch + (size_t)x * 3;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        // cv2.addWeighted(img, 0.6, colour, 0.4, 0): float32, round half to even, saturate
-        const float r = __fadd_rn(__fmul_rn((float)s[c], 0.6f), __fmul_rn((float)__ldg(jet + idx * 3 + c), 0.4f));
-        o[c] = (uint8_t)min(max(__float2int_rn(r), 0), 255);
+        for (int c = 0; c < 3; ++c) {
+            // cv2.addWeighted(img, 0.6, colour, 0.4, 0): float32, round half to even, saturate
+            const float rr = __fadd_rn(__fmul_rn((float)s[c], 0.6f), __fmul_rn((float)__ldg(jet + idx * 3 + c), 0.4f));
+            o[c] = (uint8_t)min(max(__float2int_rn(rr), 0), 255);
+        }
     }
 }
-
-inline int blocks_for(size_t n) { return (int)((n + kT - 1) / kT); }
 
 }  // namespace
 
-extern "C" int vis_heatmap_overlay(const uint8_t* img, int64_t img_pitch, int h, int w,
-                                   const VisHeatDefect* defects, int n_defects, const float* kernels,
-                                   int final_ksize, int final_koff, const uint8_t* jet768,
-                                   float* scratch, uint8_t* dst, int64_t dst_pitch, void* stream) {
-    if (!img || !dst || !scratch || !jet768 || !kernels || h <= 0 || w <= 0 || n_defects < 0 || (n_defects && !defects) ||
-        img_pitch < (int64_t)w * 3 || dst_pitch < (int64_t)w * 3 || final_ksize < 1 || (final_ksize & 1) == 0) {
-        vis::set_error("vis_heatmap_overlay: bad arguments");
+extern "C" int vis_heatmap_batch(const VisHeatFrame* frames, int n_frames, const VisHeatItem* items, int n_items,
+                                 int max_w, int max_h, int max_rw, int max_rh, int64_t plane_floats,
+                                 const float* kernels, const uint8_t* jet768, float* heat, float* fa, float* fb,
+                                 float* tmp, double* tabs, unsigned int* max_bits, void* stream) {
+    if (!frames || n_frames <= 0 || n_frames > 65535 || n_items < 0 || n_items > 65535 || (n_items && (!items || !tmp || !tabs)) ||
+        !kernels || !jet768 || !heat || !fa || !fb || !max_bits || max_w <= 0 || max_h <= 0 || plane_floats <= 0 ||
+        (n_items && (max_rw <= 0 || max_rh <= 0))) {
+        vis::set_error("vis_heatmap_batch: bad arguments (frames=%d items=%d)", n_frames, n_items);
         return VIS_E_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)w * h;
-    float* heat = scratch;                 // h*w
-    float* ta = scratch + n;               // h*w (region buffers live at its start)
-    float* tb = scratch + 2 * n;           // h*w, then one uint for the maximum
-    unsigned int* mx = reinterpret_cast<unsigned int*>(scratch + 3 * n);
-    k_heat_clear<<<592, kT, 0, st>>>(heat, n);
-    cudaMemsetAsync(mx, 0, sizeof(unsigned int), st);
-    for (int i = 0; i < n_defects; ++i) {
-        const VisHeatDefect& d = defects[i];
-        const int rw = d.x2 - d.x1, rh = d.y2 - d.y1;
-        if (rw <= 0 || rh <= 0 || d.x1 < 0 || d.y1 < 0 || d.x2 > w || d.y2 > h || d.ksize < 1 || d.ksize > 51 || (d.ksize & 1) == 0) {
-            vis::set_error("vis_heatmap_overlay: defect %d has an invalid region or kernel", i);
-            return VIS_E_INVALID;
-        }
-        const int nb = blocks_for((size_t)rw * rh);
-        const int direct = d.kind == 1 || d.ksize == 1;
-        k_heat_local<<<nb, kT, 0, st>>>(d, w, ta, heat, direct);
-        if (!direct) {
-            k_heat_blur_h<<<dim3((rw + kHSeg - 1) / kHSeg, rh), kT, 0, st>>>(ta, rw, tb, rw, rw, rh, kernels + d.koff, d.ksize);
-            k_heat_blur_v<<<dim3((rw + kVCols - 1) / kVCols, (rh + kVRows - 1) / kVRows), kT, 0, st>>>(
-                tb, rw, heat + (size_t)d.y1 * w + d.x1, w, rw, rh, kernels + d.koff, d.ksize, 1);
-        }
+    cudaError_t e = cudaMemsetAsync(heat, 0, sizeof(float) * (size_t)plane_floats, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(max_bits, 0, sizeof(unsigned int) * (size_t)n_frames, st);
+    if (e != cudaSuccess) return vis::cuda_fail(e, "vis_heatmap_batch: cudaMemsetAsync");
+    if (n_items) {
+        k_heat_tables<<<dim3((max_rw + max_rh + kT - 1) / kT, n_items), kT, 0, st>>>(items, tabs);
+        k_heat_defect_h<<<dim3((max_rw + kHSeg - 1) / kHSeg, (max_rh + kHRows - 1) / kHRows, n_items), kT, 0, st>>>(
+            items, frames, tabs, kernels, tmp, heat);
+        k_heat_defect_v<<<dim3((max_rw + kVCols - 1) / kVCols, (max_rh + kVRows - 1) / kVRows, n_items), kT, 0, st>>>(
+            items, frames, kernels, tmp, heat);
     }
-    const float* fin = heat;
-    if (final_ksize > 1) {
-        k_heat_blur_h<<<dim3((w + kHSeg - 1) / kHSeg, h), kT, 0, st>>>(heat, w, ta, w, w, h, kernels + final_koff, final_ksize);
-        k_heat_blur_v<<<dim3((w + kVCols - 1) / kVCols, (h + kVRows - 1) / kVRows), kT, 0, st>>>(
-            ta, w, tb, w, w, h, kernels + final_koff, final_ksize, 0);
-        fin = tb;
-    }
-    k_heat_max<<<592, kT, 0, st>>>(fin, n, mx);
-    k_heat_colorize<<<blocks_for(n), kT, 0, st>>>(img, img_pitch, fin, w, h, mx, jet768, dst, dst_pitch);
-    return vis::check_launch("vis_heatmap_overlay");
+    k_heat_final_h<<<dim3((max_w + kHSeg - 1) / kHSeg, (max_h + kHRows - 1) / kHRows, n_frames), kT, 0, st>>>(frames, kernels, heat, fa);
+    k_heat_final_v<<<dim3((max_w + kVCols - 1) / kVCols, (max_h + kVRows - 1) / kVRows, n_frames), kT, 0, st>>>(frames, kernels, fa, fb, max_bits);
+    k_heat_colorize<<<dim3(592, n_frames), kT, 0, st>>>(frames, fb, max_bits, jet768);
+    return vis::check_launch("vis_heatmap_batch");
 }

@@ -1105,31 +1105,87 @@ class Engine:
         """``create_heatmap_overlay`` for one BGR uint8 HWC CUDA frame and the reference's defect dicts (percent boxes,
         ``safety_impact``, ``confidence``, ``location``): returns the blended BGR frame (a copy when ``defects`` is
         empty, like the reference).  Tolerance-specified (float32 blur), see vis_heatmap.cu."""
+        return self.heatmap_batch([frame], [defects])[0]
+
+    def heatmap_batch(self, frames, defects_per_frame) -> list:
+        """``create_heatmap_overlay`` for a batch of BGR uint8 HWC CUDA frames (a ``[B,H,W,3]`` tensor or a list, mixed
+        sizes allowed): SIX launches for the whole batch.  Returns a list of new frames, aligned with the input."""
         from . import heatmap as H
-        self._check_u8(frame)
-        if frame.dim() != 3 or frame.shape[2] != 3 or frame.stride(2) != 1 or frame.stride(1) != 3:
-            raise ValueError("frame must be [H, W, 3] uint8 with contiguous pixels")
-        h, w = int(frame.shape[0]), int(frame.shape[1])
-        recs, kern, had = H.defect_params(defects, w, h)
-        if not had:
+        batch = list(frames.unbind(0)) if isinstance(frames, torch.Tensor) and frames.dim() == 4 else list(frames)
+        if len(batch) != len(defects_per_frame):
+            raise ValueError("one defect list per frame expected")
+        for f in batch:
+            self._check_u8(f)
+            if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
+        outs = [None] * len(batch)
+        fdesc, items, kernels, kcache = [], [], [], {}
+        koff = plane = tmp = tab = 0
+
+        def kernel_offset(k: np.ndarray) -> int:
+            nonlocal koff
+            key = k.tobytes()
+            if key not in kcache:
+                kcache[key] = koff
+                kernels.append(k)
+                koff += len(k)
+            return kcache[key]
+        live = []
+        for i, (f, defects) in enumerate(zip(batch, defects_per_frame)):
+            h, w = int(f.shape[0]), int(f.shape[1])
+            recs, kern, had = H.defect_params(defects, w, h)
+            if not had:                               # no defects: the reference writes the image back unchanged
+                outs[i] = f.clone()
+                continue
+            fk, fkern = H.final_blur(w, h)
+            out = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+            outs[i] = out
+            fdesc.append((f.data_ptr(), out.data_ptr(), f.stride(0), out.stride(0), h, w, plane, fk, kernel_offset(fkern)))
+            for r in recs:
+                rw, rh = int(r["x2"] - r["x1"]), int(r["y2"] - r["y1"])
+                ks = int(r["ksize"])
+                if rw <= 0 or rh <= 0 or r["x1"] < 0 or r["y1"] < 0 or r["x2"] > w or r["y2"] > h or ks < 1 or ks > 51 or ks % 2 == 0:
+                    raise ValueError("heat-map defect with an invalid region or blur kernel")
+                it = np.zeros((), H.ITEM_DTYPE)
+                it["d"] = r
+                if ks > 1:
+                    it["d"]["koff"] = kernel_offset(kern[int(r["koff"]):int(r["koff"]) + ks])
+                it["frame"], it["tab_off"] = len(fdesc) - 1, tab
+                tab += rw + rh
+                if int(r["kind"]) == 0 and ks > 1:
+                    it["tmp_off"] = tmp
+                    tmp += rw * rh
+                items.append(it)
+            plane += h * w
+            live.append(i)
+        if not fdesc:
             self.last_launches = 0
-            return frame.clone()
-        fk, fkern = H.final_blur(w, h)
-        kernels = np.concatenate([kern, fkern]).astype(np.float32)
-        d_kern = torch.from_numpy(kernels).to(self.device)
+            return outs
+        if len(fdesc) > 65535 or len(items) > 65535:
+            raise ValueError("at most 65535 frames / defects per heatmap_batch call")
+        fr = np.zeros(len(fdesc), N.HEAT_FRAME_DTYPE)
+        for j, row in enumerate(fdesc):
+            fr[j] = row
+        it_arr = np.array(items, H.ITEM_DTYPE) if items else np.zeros(1, H.ITEM_DTYPE)
+        up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
+        d_fr, d_it = up(fr), up(it_arr)
+        d_kern = torch.from_numpy(np.concatenate(kernels).astype(np.float32)).to(self.device)
         if not hasattr(self, "_jet"):
             self._jet = torch.from_numpy(H.JET_BGR.copy()).to(self.device)
-        scratch = torch.empty(3 * h * w + 4, dtype=torch.float32, device=self.device)
-        out = torch.empty_like(frame, memory_format=torch.contiguous_format)
-        recs = np.ascontiguousarray(recs)
-        N.check(self.L.vis_heatmap_overlay(frame.data_ptr(), frame.stride(0), h, w,
-                                           recs.ctypes.data_as(C.c_void_p) if len(recs) else None, len(recs),
-                                           d_kern.data_ptr(), fk, len(kern), self._jet.data_ptr(), scratch.data_ptr(),
-                                           out.data_ptr(), out.stride(0), _stream_ptr()), "vis_heatmap_overlay")
-        n_box = int((recs["kind"] == 0).sum() - ((recs["kind"] == 0) & (recs["ksize"] == 1)).sum()) if len(recs) else 0
-        self.last_launches = 1 + len(recs) + 2 * n_box + (2 if fk > 1 else 0) + 2
-        self._keepalive_h = (d_kern, scratch)
-        return out
+        planes = torch.empty((3, plane), dtype=torch.float32, device=self.device)
+        d_tmp = torch.empty(max(tmp, 1), dtype=torch.float32, device=self.device)
+        d_tab = torch.empty(max(tab, 1), dtype=torch.float64, device=self.device)
+        d_max = torch.empty(len(fdesc), dtype=torch.int32, device=self.device)
+        max_rw = max((int(it["d"]["x2"] - it["d"]["x1"]) for it in items), default=0)
+        max_rh = max((int(it["d"]["y2"] - it["d"]["y1"]) for it in items), default=0)
+        N.check(self.L.vis_heatmap_batch(d_fr.data_ptr(), len(fdesc), d_it.data_ptr() if items else None, len(items),
+                                         int(fr["w"].max()), int(fr["h"].max()), max_rw, max_rh, plane,
+                                         d_kern.data_ptr(), self._jet.data_ptr(), planes[0].data_ptr(), planes[1].data_ptr(),
+                                         planes[2].data_ptr(), d_tmp.data_ptr(), d_tab.data_ptr(), d_max.data_ptr(),
+                                         _stream_ptr()), "vis_heatmap_batch")
+        self.last_launches = 3 + (3 if items else 0)
+        self._keepalive_h = (d_fr, d_it, d_kern, planes, d_tmp, d_tab, d_max)
+        return outs
 
     # ------------------------------------------------------------------ comparison panel / status stamp
     def _draw_list(self, canvas: torch.Tensor, cmds: np.ndarray) -> int:
@@ -1295,7 +1351,7 @@ def _locked(fn):
 # one script thread per session): every public entry point holds the engine's lock while it plans and enqueues.
 for _name in ("resize_batch_u8", "resize_u8", "resize_hp", "reduce_u8", "resize_box_u8", "alpha_premultiply_", "resize_nearest_u8",
               "resize_reducing_u8", "agent_inputs", "plan_batch", "preprocess", "preprocess_dual", "preprocess_host", "preprocess_jpeg", "plan_overlay", "annotate",
-              "heatmap", "side_by_side", "status_stamp", "quality_stats"):
+              "heatmap", "heatmap_batch", "side_by_side", "status_stamp", "quality_stats"):
     setattr(Engine, _name, _locked(getattr(Engine, _name)))
 del _name
 

@@ -32,6 +32,10 @@ HEAT_DTYPE = np.dtype([
     ("ksize", np.int32), ("koff", np.int32), ("pad", np.int32),                     # blur kernel size, offset into kernels[]
     ("intensity", np.float64), ("cx", np.float64), ("cy", np.float64), ("sigma", np.float64)], align=True)
 
+# VisHeatItem: a defect of a batch (include/vis_b200.h)
+ITEM_DTYPE = np.dtype([("d", HEAT_DTYPE), ("frame", np.int32), ("pad", np.int32), ("tmp_off", np.int64), ("tab_off", np.int64)],
+                      align=True)
+
 _SEVERITY_WEIGHT = {"CRITICAL": 1.0, "MODERATE": 0.75, "COSMETIC": 0.5, "MINOR": 0.5}        # image_utils.py:376-381
 _CONFIDENCE_FACTOR = {"high": 1.0, "medium": 0.75, "low": 0.55}                               # :386
 _WIDESPREAD = ("entire surface", "everywhere", "whole component", "complete surface")         # :398
