@@ -406,7 +406,7 @@ typedef struct VisHeatItem {         /* one defect of one frame of a batch      
     int32_t pad;
     int64_t tmp_off;                 /* float offset of its region buffer in tmp[] ((x2-x1)*(y2-y1) floats; box defects
                                         with ksize > 1)                                                            */
-    int64_t tab_off;                 /* double offset of its two 1-D Gaussian factor tables in tabs[]: (x2-x1) + (y2-y1) */
+    int64_t tab_off;                 /* double offset of its 1-D tables in tabs[]: 3 * ((x2-x1) + (y2-y1)) doubles     */
 } VisHeatItem;
 typedef struct VisHeatFrame {
     const uint8_t* src;              /* device BGR uint8 HWC                                                        */

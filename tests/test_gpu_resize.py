@@ -213,8 +213,9 @@ def test_resize_image_double_precision_modes(engine):
               Image.fromarray(rng.integers(-2 ** 31, 2 ** 31 - 1, (900, 2500), dtype=np.int32)),
               Image.fromarray(rng.integers(-70000, 70000, (2300, 700), dtype=np.int32)),
               Image.fromarray(rng.normal(0, 1000, (1200, 2400)).astype(np.float32))]
-    be = Image.frombytes("I;16B", (2600, 1300), a16.byteswap().tobytes())
-    images[1] = be
+    images[1] = Image.frombytes("I;16B", (2600, 1300), a16.byteswap().tobytes())
+    images.append(Image.frombytes("I;16N", (2600, 1300), a16.tobytes()))     # Pillow reads these words big-endian (sic)
+    images.append(Image.frombytes("I;16L", (2600, 1300), a16.tobytes()))
     for im in images:
         for limit in (2048, 1000):
             want = im.resize(IU.G.resize_image_size(im.size[0], im.size[1], limit), Image.Resampling.LANCZOS)

@@ -1,10 +1,11 @@
 // vis_heatmap.cu — device half of create_heatmap_overlay (utils/image_utils.py:320-604; SURVEY.md 8f "next" row 2).
 //
 // BATCH form (round 2): any number of frames and defects in SIX launches, whatever the batch size —
-//   k_heat_tables     per defect, the two 1-D factors of its Gaussian, exp(-(x-cx)^2 / 2 sigma^2) and the same in y, in
-//                     float64 like the reference's numpy expression (one exp per region column / row instead of one per
-//                     region pixel: the 2-D value is their product, within 2 ulp(double) of exp of the sum, long before
-//                     the float32 rounding that follows)
+//   k_heat_tables     per defect, everything that depends on one coordinate: the two 1-D factors of its Gaussian,
+//                     exp(-(x-cx)^2 / 2 sigma^2) and the same in y, in float64 like the reference's numpy expression (one
+//                     exp per region column / row instead of one per region pixel: the 2-D value is their product, within
+//                     2 ulp(double) of exp of the sum, long before the float32 rounding that follows), and the squared
+//                     distances of the boost and cut-off tests
 //   k_heat_defect_h   analytic heat of a defect (intensity * Gaussian, boosts inside the box, min(1, .), 4-sigma cut-off,
 //                     all float64, cast to float32) evaluated straight into shared memory, reflected at the REGION
 //                     border as cv2.GaussianBlur on the sliced array does, and blurred horizontally; widespread defects
@@ -37,66 +38,68 @@ constexpr int kHSeg = 512, kHRows = 4;           // horizontal pass: 4 rows x 51
 constexpr int kHLen = kHSeg + 2 * kBlurR + 6;    // staged row, padded to a multiple of 8 (568)
 constexpr int kHPhase = kHLen / kOut;            // 71: element i lives at (i % 8) * 71 + i / 8 -> lanes read consecutive words
 constexpr int kVCols = 32, kVRows = 64;          // vertical pass: 32 columns x 64 output rows per block
-constexpr int kVTile = kVRows + 56;              // rows staged: the last thread's rounded window ends at row 56 + 63
-constexpr int kWPad = kOut - 1;                  // zero weights in front of / behind the kernel: no tap predicates
+constexpr int kVTile = kVRows + 2 * kBlurR;       // rows staged
+constexpr int kRDefect = 25, kRFinal = 15;       // window radii of the two launch classes (51 / 31 taps at most)
 static_assert(kHLen % kOut == 0, "staged row must de-interleave evenly");
 
-constexpr int kWLen = kWPad + 64 + 8;           // padded weights: kWPad zeros, the kernel, zeros up to the rounded window
-__device__ __forceinline__ void load_weights(float* wp, const float* __restrict__ kern, int ksize) {
-    for (int i = threadIdx.x; i < kWLen; i += kT) {
-        const int t = i - kWPad;
-        wp[i] = (t >= 0 && t < ksize) ? __ldg(kern + t) : 0.f;
-    }
+// The kernel of a launch class is held in REGISTERS, centred in a window of compile-time radius R (smaller kernels are
+// padded with zero weights; the reference's kernels are 49..51 taps for defects, <= 31 for the final blur), so the taps
+// unroll completely: per staged value one shared-memory read and up to 8 FMA with register operands only.
+template <int R>
+__device__ __forceinline__ void load_weights(float (&w)[2 * R + 1], const float* __restrict__ kern, int ksize) {
+    const int pad = R - (ksize >> 1);
+#pragma unroll
+    for (int t = 0; t < 2 * R + 1; ++t) w[t] = (t >= pad && t < pad + ksize) ? __ldg(kern + t - pad) : 0.f;
 }
 
-// analytic heat of a box defect / widespread defect at region-local (lx, ly), float64 like the reference, from the 1-D tables
-__device__ __forceinline__ float heat_value(const VisHeatDefect& d, const double* __restrict__ tx, const double* __restrict__ ty,
-                                            int lx, int ly) {
-    const int gx = d.x1 + lx, gy = d.y1 + ly;
-    const double g0 = d.intensity * (tx[lx] * ty[ly]);
+// analytic heat of a box defect / widespread defect at region-local (lx, ly), float64 like the reference.  Everything
+// that depends on one coordinate only comes from the defect's 1-D tables (k_heat_tables): the Gaussian factors, the
+// squared normalised distances of the boost test ((dx / max(w/2, 1))^2: the divisions leave the per-pixel path) and the
+// squared distances of the 4-sigma cut-off — same operations, same roundings, evaluated once per column / row.
+struct HeatTabs { const double *tx, *ty, *bx, *by, *qx, *qy; };
+__device__ __forceinline__ HeatTabs heat_tabs(const double* __restrict__ tabs, const VisHeatItem& it) {
+    const int rw = it.d.x2 - it.d.x1, rh = it.d.y2 - it.d.y1;
+    const double* p = tabs + it.tab_off;
+    return {p, p + rw, p + rw + rh, p + 2 * rw + rh, p + 2 * (rw + rh), p + 3 * rw + 2 * rh};
+}
+__device__ __forceinline__ float heat_value(const VisHeatDefect& d, const HeatTabs& t, int lx, int ly) {
+    const double g0 = d.intensity * (t.tx[lx] * t.ty[ly]);
     if (d.kind == 1) return (float)g0;
-    const double ddx = (double)gx - d.cx, ddy = (double)gy - d.cy;
+    const int gx = d.x1 + lx, gy = d.y1 + ly;
     const bool in_box = gx >= d.x && gx < d.x + d.w && gy >= d.y && gy < d.y + d.h;
-    const double ex = ddx / fmax(d.w / 2.0, 1.0), ey = ddy / fmax(d.h / 2.0, 1.0);
-    const double boost = (ex * ex + ey * ey < 1.2 * 1.2) ? 1.8 : (in_box ? 1.4 : 1.0);
+    const double boost = (t.bx[lx] + t.by[ly] < 1.2 * 1.2) ? 1.8 : (in_box ? 1.4 : 1.0);
     const double g = fmin(1.0, g0 * boost);
     const double lim = 4.0 * d.sigma;
-    return (ddx * ddx + ddy * ddy) < lim * lim ? (float)g : 0.f;
+    return (t.qx[lx] + t.qy[ly]) < lim * lim ? (float)g : 0.f;
 }
 
 __global__ void __launch_bounds__(kT) k_heat_tables(const VisHeatItem* __restrict__ items, double* __restrict__ tabs) {
     const VisHeatItem& it = items[blockIdx.y];
-    const int rw = it.d.x2 - it.d.x1, rh = it.d.y2 - it.d.y1;
+    const VisHeatDefect& d = it.d;
+    const int rw = d.x2 - d.x1, rh = d.y2 - d.y1;
     const int t = blockIdx.x * kT + threadIdx.x;
     if (t >= rw + rh) return;
-    const double c = t < rw ? (double)(it.d.x1 + t) - it.d.cx : (double)(it.d.y1 + t - rw) - it.d.cy;
-    tabs[it.tab_off + t] = exp(-(c * c) / (2.0 * (it.d.sigma * it.d.sigma)));
+    const bool is_x = t < rw;
+    const double c = is_x ? (double)(d.x1 + t) - d.cx : (double)(d.y1 + t - rw) - d.cy;
+    const double e = c / fmax((is_x ? d.w : d.h) / 2.0, 1.0);
+    double* p = tabs + it.tab_off;
+    p[t] = exp(-(c * c) / (2.0 * (d.sigma * d.sigma)));          // tx | ty
+    p[rw + rh + t] = e * e;                                        // bx | by
+    p[2 * (rw + rh) + t] = c * c;                                  // qx | qy
 }
 
-// 8 outputs from one sliding window: value(k) for k = 0 .. n-1 with n = 8 + 2r rounded up to 8 (the surplus meets zero
-// weights and zero-filled staging).  Weights sit in a 15-register window that advances 8 taps per block of 8 values, so
-// a block is 8 value reads + 2 vector weight reads for 64 FMA; output j accumulates its taps in ascending order.
-template <typename F>
-__device__ __forceinline__ void window8(float (&acc)[kOut], const float* wp, int r, F value) {
+// 8 outputs from one sliding window of radius R: value(k), k = 0 .. 8 + 2R - 1, is staged element (first output - R + k);
+// output j accumulates taps t = k - j in ascending order.
+template <int R, typename F>
+__device__ __forceinline__ void window8(float (&acc)[kOut], const float (&w)[2 * R + 1], F value) {
 #pragma unroll
     for (int j = 0; j < kOut; ++j) acc[j] = 0.f;
-    float w[2 * kOut - 1];
 #pragma unroll
-    for (int j = 0; j < kOut - 1; ++j) w[j] = wp[j];              // taps -7 .. -1 of the padded kernel (zeros)
-    const int n = (kOut + 2 * r + kOut - 1) & ~(kOut - 1);
-#pragma unroll 1
-    for (int kb = 0; kb < n; kb += kOut) {
+    for (int k = 0; k < kOut + 2 * R; ++k) {
+        const float v = value(k);
 #pragma unroll
-        for (int q = 0; q < kOut; ++q) w[kOut - 1 + q] = wp[kWPad + kb + q];
-        // w[i] = weight of tap (kb + i - 7): output j at value kb + kk uses tap kb + kk - j -> w[7 + kk - j]
-#pragma unroll
-        for (int kk = 0; kk < kOut; ++kk) {
-            const float v = value(kb + kk);
-#pragma unroll
-            for (int j = 0; j < kOut; ++j) acc[j] = fmaf(w[kOut - 1 + kk - j], v, acc[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < kOut - 1; ++j) w[j] = w[j + kOut];
+        for (int j = 0; j < kOut; ++j)
+            if (k - j >= 0 && k - j <= 2 * R) acc[j] = fmaf(w[k - j], v, acc[j]);
     }
 }
 
@@ -108,32 +111,31 @@ __global__ void __launch_bounds__(kT)
 k_heat_defect_h(const VisHeatItem* __restrict__ items, const VisHeatFrame* __restrict__ frames, const double* __restrict__ tabs,
                 const float* __restrict__ kernels, float* __restrict__ tmp, float* __restrict__ heat) {
     __shared__ float rows[kHRows][kHLen];
-    __shared__ float wp[kWLen];
     const VisHeatItem& it = items[blockIdx.z];
     const VisHeatDefect& d = it.d;
     const int rw = d.x2 - d.x1, rh = d.y2 - d.y1;
     const int x0 = blockIdx.x * kHSeg, y0 = blockIdx.y * kHRows;
     if (x0 >= rw || y0 >= rh) return;
-    const double* tx = tabs + it.tab_off;
-    const double* ty = tx + rw;
+    const HeatTabs tb = heat_tabs(tabs, it);
     const VisHeatFrame& fr = frames[it.frame];
     const bool direct = d.kind == 1 || d.ksize == 1;
     if (direct) {                                      // no blur: max-combine the analytic heat itself
         float* plane = heat + fr.plane_off;
         for (int i = threadIdx.x; i < kHRows * kHSeg; i += kT) {
             const int ly = y0 + i / kHSeg, lx = x0 + i % kHSeg;
-            if (ly < rh && lx < rw) atomic_max_f(plane + (size_t)(d.y1 + ly) * fr.w + d.x1 + lx, heat_value(d, tx, ty, lx, ly));
+            if (ly < rh && lx < rw) atomic_max_f(plane + (size_t)(d.y1 + ly) * fr.w + d.x1 + lx, heat_value(d, tb, lx, ly));
         }
         return;
     }
-    const int r = d.ksize >> 1;
-    load_weights(wp, kernels + d.koff, d.ksize);
-    const int span = kHSeg + 2 * r;
-    for (int i = threadIdx.x; i < kHRows * kHLen; i += kT) {             // the padding behind `span` is zero-filled
-        const int row = i / kHLen, idx = i - row * kHLen;
+    constexpr int R = kRDefect;
+    float w[2 * R + 1];
+    load_weights<R>(w, kernels + d.koff, d.ksize);
+    constexpr int span = kHSeg + 2 * R;
+    for (int i = threadIdx.x; i < kHRows * span; i += kT) {
+        const int row = i / span, idx = i - row * span;
         const int ly = y0 + row;
         float v = 0.f;
-        if (ly < rh && idx < span) v = heat_value(d, tx, ty, reflect101(x0 + idx - r, rw), ly);
+        if (ly < rh) v = heat_value(d, tb, reflect101(x0 + idx - R, rw), ly);
         rows[row][(idx % kOut) * kHPhase + idx / kOut] = v;
     }
     __syncthreads();
@@ -141,8 +143,8 @@ k_heat_defect_h(const VisHeatItem* __restrict__ items, const VisHeatFrame* __res
     const int ly = y0 + row, lx = x0 + c * kOut;
     if (ly >= rh || lx >= rw) return;
     float acc[kOut];
-    const float* rp = rows[row];
-    window8(acc, wp, r, [&](int k) { const int i = c * kOut + k; return rp[(i % kOut) * kHPhase + i / kOut]; });
+    const float* rp = rows[row] + c;
+    window8<R>(acc, w, [&](int k) { return rp[(k % kOut) * kHPhase + k / kOut]; });      // element c*8 + k
     float* o = tmp + it.tmp_off + (size_t)ly * rw + lx;
 #pragma unroll
     for (int j = 0; j < kOut; ++j)
@@ -154,7 +156,6 @@ __global__ void __launch_bounds__(kT)
 k_heat_defect_v(const VisHeatItem* __restrict__ items, const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels,
                 const float* __restrict__ tmp, float* __restrict__ heat) {
     __shared__ float tile[kVTile][kVCols];
-    __shared__ float wp[kWLen];
     const VisHeatItem& it = items[blockIdx.z];
     const VisHeatDefect& d = it.d;
     if (d.kind == 1 || d.ksize == 1) return;
@@ -162,15 +163,16 @@ k_heat_defect_v(const VisHeatItem* __restrict__ items, const VisHeatFrame* __res
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int x = blockIdx.x * kVCols + lane, y0 = blockIdx.y * kVRows;
     if (blockIdx.x * kVCols >= rw || y0 >= rh) return;
-    const int r = d.ksize >> 1;
-    load_weights(wp, kernels + d.koff, d.ksize);
+    constexpr int R = kRDefect;
+    float w[2 * R + 1];
+    load_weights<R>(w, kernels + d.koff, d.ksize);
     const float* src = tmp + it.tmp_off;
-    for (int i = grp; i < kVTile; i += kT / 32)                            // rows behind the window are zero-filled
-        tile[i][lane] = (x < rw && i < kVRows + 2 * r) ? src[(size_t)reflect101(y0 + i - r, rh) * rw + x] : 0.f;
+    for (int i = grp; i < kVRows + 2 * R; i += kT / 32)
+        tile[i][lane] = x < rw ? src[(size_t)reflect101(y0 + i - R, rh) * rw + x] : 0.f;
     __syncthreads();
     if (x >= rw) return;
     float acc[kOut];
-    window8(acc, wp, r, [&](int k) { return tile[grp * kOut + k][lane]; });
+    window8<R>(acc, w, [&](int k) { return tile[grp * kOut + k][lane]; });
     const VisHeatFrame& fr = frames[it.frame];
     float* plane = heat + fr.plane_off;
 #pragma unroll
@@ -185,27 +187,26 @@ __global__ void __launch_bounds__(kT)
 k_heat_final_h(const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels, const float* __restrict__ heat,
                float* __restrict__ fa) {
     __shared__ float rows[kHRows][kHLen];
-    __shared__ float wp[kWLen];
     const VisHeatFrame& fr = frames[blockIdx.z];
     const int x0 = blockIdx.x * kHSeg, y0 = blockIdx.y * kHRows;
     if (x0 >= fr.w || y0 >= fr.h) return;
-    const int r = fr.final_ksize >> 1;
-    load_weights(wp, kernels + fr.final_koff, fr.final_ksize);
+    constexpr int R = kRFinal;
+    float w[2 * R + 1];
+    load_weights<R>(w, kernels + fr.final_koff, fr.final_ksize);
     const float* plane = heat + fr.plane_off;
-    const int span = kHSeg + 2 * r;
-    for (int i = threadIdx.x; i < kHRows * kHLen; i += kT) {
-        const int row = i / kHLen, idx = i - row * kHLen;
+    constexpr int span = kHSeg + 2 * R;
+    for (int i = threadIdx.x; i < kHRows * span; i += kT) {
+        const int row = i / span, idx = i - row * span;
         const int y = y0 + row;
-        rows[row][(idx % kOut) * kHPhase + idx / kOut] =
-            (y < fr.h && idx < span) ? plane[(size_t)y * fr.w + reflect101(x0 + idx - r, fr.w)] : 0.f;
+        rows[row][(idx % kOut) * kHPhase + idx / kOut] = y < fr.h ? plane[(size_t)y * fr.w + reflect101(x0 + idx - R, fr.w)] : 0.f;
     }
     __syncthreads();
     const int row = threadIdx.x >> 6, c = threadIdx.x & 63;
     const int y = y0 + row, x = x0 + c * kOut;
     if (y >= fr.h || x >= fr.w) return;
     float acc[kOut];
-    const float* rp = rows[row];
-    window8(acc, wp, r, [&](int k) { const int i = c * kOut + k; return rp[(i % kOut) * kHPhase + i / kOut]; });
+    const float* rp = rows[row] + c;
+    window8<R>(acc, w, [&](int k) { return rp[(k % kOut) * kHPhase + k / kOut]; });
     float* o = fa + fr.plane_off + (size_t)y * fr.w + x;
 #pragma unroll
     for (int j = 0; j < kOut; ++j)
@@ -216,22 +217,22 @@ k_heat_final_h(const VisHeatFrame* __restrict__ frames, const float* __restrict_
 __global__ void __launch_bounds__(kT)
 k_heat_final_v(const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels, const float* __restrict__ fa,
                float* __restrict__ fb, unsigned int* __restrict__ max_bits) {
-    __shared__ float tile[kVTile][kVCols];
-    __shared__ float wp[kWLen];
+    __shared__ float tile[kVRows + 2 * kRFinal][kVCols];
     const VisHeatFrame& fr = frames[blockIdx.z];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int x = blockIdx.x * kVCols + lane, y0 = blockIdx.y * kVRows;
     if (blockIdx.x * kVCols >= fr.w || y0 >= fr.h) return;
-    const int r = fr.final_ksize >> 1;
-    load_weights(wp, kernels + fr.final_koff, fr.final_ksize);
+    constexpr int R = kRFinal;
+    float w[2 * R + 1];
+    load_weights<R>(w, kernels + fr.final_koff, fr.final_ksize);
     const float* src = fa + fr.plane_off;
-    for (int i = grp; i < kVTile; i += kT / 32)
-        tile[i][lane] = (x < fr.w && i < kVRows + 2 * r) ? src[(size_t)reflect101(y0 + i - r, fr.h) * fr.w + x] : 0.f;
+    for (int i = grp; i < kVRows + 2 * R; i += kT / 32)
+        tile[i][lane] = x < fr.w ? src[(size_t)reflect101(y0 + i - R, fr.h) * fr.w + x] : 0.f;
     __syncthreads();
     float m = 0.f;
     if (x < fr.w) {
         float acc[kOut];
-        window8(acc, wp, r, [&](int k) { return tile[grp * kOut + k][lane]; });
+        window8<R>(acc, w, [&](int k) { return tile[grp * kOut + k][lane]; });
         float* o = fb + fr.plane_off;
 #pragma unroll
         for (int j = 0; j < kOut; ++j) {
@@ -247,27 +248,57 @@ k_heat_final_v(const VisHeatFrame* __restrict__ frames, const float* __restrict_
     if (lane == 0 && m > 0.f) atomicMax(max_bits + blockIdx.z, __float_as_uint(m));
 }
 
+__device__ __forceinline__ int heat_index(float v, float mx) {
+    // numpy: (heat / max * 255).astype(uint8) in float32, truncation toward zero
+    const float t = mx > 0.f ? __fmul_rn(__fdiv_rn(v, mx), 255.f) : __fmul_rn(v, 255.f);
+    return min(max((int)t, 0), 255);
+}
+__device__ __forceinline__ uint32_t blend_byte(uint32_t img, uint32_t col) {
+    // cv2.addWeighted(img, 0.6, colour, 0.4, 0): float32, round half to even, saturate
+    const float r = __fadd_rn(__fmul_rn((float)img, 0.6f), __fmul_rn((float)col, 0.4f));
+    return (uint32_t)min(max(__float2int_rn(r), 0), 255);
+}
+
+// thread = 4 pixels (one float4 of heat, three 32-bit words of BGR in, three out) when the frame allows; JET in shared memory
 __global__ void __launch_bounds__(kT)
 k_heat_colorize(const VisHeatFrame* __restrict__ frames, const float* __restrict__ fb, const unsigned int* __restrict__ max_bits,
                 const uint8_t* __restrict__ jet) {
+    __shared__ uint8_t sjet[768];
+    for (int i = threadIdx.x; i < 768; i += kT) sjet[i] = __ldg(jet + i);
+    __syncthreads();
     const VisHeatFrame& fr = frames[blockIdx.y];
     const float mx = __uint_as_float(max_bits[blockIdx.y]);
     const float* plane = fb + fr.plane_off;
+    const bool vec = (fr.w & 3) == 0 && ((fr.src_pitch | fr.dst_pitch) & 3) == 0 && (fr.plane_off & 3) == 0 &&
+                     (((uintptr_t)fr.src | (uintptr_t)fr.dst) & 3) == 0;
+    if (vec) {
+        const int wq = fr.w >> 2;
+        const long long n = (long long)wq * fr.h;
+        for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+            const int y = (int)(i / wq), q = (int)(i - (long long)y * wq);
+            const float4 hv = *reinterpret_cast<const float4*>(plane + (size_t)y * fr.w + 4 * q);
+            const uint32_t* s = reinterpret_cast<const uint32_t*>(fr.src + (size_t)y * fr.src_pitch) + 3 * q;
+            uint32_t* o = reinterpret_cast<uint32_t*>(fr.dst + (size_t)y * fr.dst_pitch) + 3 * q;
+            const uint32_t in[3] = {__ldcs(s), __ldcs(s + 1), __ldcs(s + 2)};
+            const int idx[4] = {heat_index(hv.x, mx), heat_index(hv.y, mx), heat_index(hv.z, mx), heat_index(hv.w, mx)};
+            uint32_t out[3] = {0u, 0u, 0u};
+#pragma unroll
+            for (int b = 0; b < 12; ++b) {                     // byte b = pixel b / 3, channel b % 3
+                const uint32_t v = blend_byte((in[b >> 2] >> (8 * (b & 3))) & 0xffu, sjet[idx[b / 3] * 3 + b % 3]);
+                out[b >> 2] |= v << (8 * (b & 3));
+            }
+            __stcs(o, out[0]); __stcs(o + 1, out[1]); __stcs(o + 2, out[2]);
+        }
+        return;
+    }
     const long long n = (long long)fr.w * fr.h;
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
         const int y = (int)(i / fr.w), x = (int)(i - (long long)y * fr.w);
-        const float v = plane[i];
-        // numpy: (heat / max * 255).astype(uint8) in float32, truncation toward zero
-        const float t = mx > 0.f ? __fmul_rn(__fdiv_rn(v, mx), 255.f) : __fmul_rn(v, 255.f);
-        const int idx = min(max((int)t, 0), 255);
+        const int idx = heat_index(plane[i], mx);
         const uint8_t* s = fr.src + (size_t)y * fr.src_pitch + (size_t)x * 3;
         uint8_t* o = fr.dst + (size_t)y * fr.dst_pitch + (size_t)x * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            // cv2.addWeighted(img, 0.6, colour, 0.4, 0): float32, round half to even, saturate
-            const float rr = __fadd_rn(__fmul_rn((float)s[c], 0.6f), __fmul_rn((float)__ldg(jet + idx * 3 + c), 0.4f));
-            o[c] = (uint8_t)min(max(__float2int_rn(rr), 0), 255);
-        }
+        for (int c = 0; c < 3; ++c) o[c] = (uint8_t)blend_byte(s[c], sjet[idx * 3 + c]);
     }
 }
 

@@ -1107,84 +1107,107 @@ class Engine:
         empty, like the reference).  Tolerance-specified (float32 blur), see vis_heatmap.cu."""
         return self.heatmap_batch([frame], [defects])[0]
 
-    def heatmap_batch(self, frames, defects_per_frame) -> list:
-        """``create_heatmap_overlay`` for a batch of BGR uint8 HWC CUDA frames (a ``[B,H,W,3]`` tensor or a list, mixed
-        sizes allowed): SIX launches for the whole batch.  Returns a list of new frames, aligned with the input."""
+    def plan_heatmap(self, shapes, defects_per_frame) -> dict:
+        """Host half of the heat map for a batch: the reference's per-defect scalar code (``heatmap.defect_params``), the
+        Gaussian kernels, and the item / offset tables of ``vis_heatmap_batch`` (uploaded here).  ``shapes``: (H, W) per
+        frame.  Reusable for any frames of those shapes."""
         from . import heatmap as H
-        batch = list(frames.unbind(0)) if isinstance(frames, torch.Tensor) and frames.dim() == 4 else list(frames)
-        if len(batch) != len(defects_per_frame):
-            raise ValueError("one defect list per frame expected")
-        for f in batch:
-            self._check_u8(f)
-            if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
-                raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
-        outs = [None] * len(batch)
-        fdesc, items, kernels, kcache = [], [], [], {}
+        items, kernels, kcache, frames = [], [], {}, []
         koff = plane = tmp = tab = 0
 
         def kernel_offset(k: np.ndarray) -> int:
             nonlocal koff
             key = k.tobytes()
-            if key not in kcache:
-                kcache[key] = koff
+            at = kcache.get(key)
+            if at is None:
+                at = kcache[key] = koff
                 kernels.append(k)
                 koff += len(k)
-            return kcache[key]
-        live = []
-        for i, (f, defects) in enumerate(zip(batch, defects_per_frame)):
-            h, w = int(f.shape[0]), int(f.shape[1])
+            return at
+        copies = []
+        for i, ((h, w), defects) in enumerate(zip(shapes, defects_per_frame)):
             recs, kern, had = H.defect_params(defects, w, h)
             if not had:                               # no defects: the reference writes the image back unchanged
-                outs[i] = f.clone()
+                copies.append(i)
                 continue
             fk, fkern = H.final_blur(w, h)
-            out = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
-            outs[i] = out
-            fdesc.append((f.data_ptr(), out.data_ptr(), f.stride(0), out.stride(0), h, w, plane, fk, kernel_offset(fkern)))
-            for r in recs:
-                rw, rh = int(r["x2"] - r["x1"]), int(r["y2"] - r["y1"])
-                ks = int(r["ksize"])
-                if rw <= 0 or rh <= 0 or r["x1"] < 0 or r["y1"] < 0 or r["x2"] > w or r["y2"] > h or ks < 1 or ks > 51 or ks % 2 == 0:
+            frames.append((i, h, w, plane, fk, kernel_offset(fkern)))
+            if len(recs):
+                rw, rh, ks = recs["x2"] - recs["x1"], recs["y2"] - recs["y1"], recs["ksize"]
+                if ((rw <= 0) | (rh <= 0) | (recs["x1"] < 0) | (recs["y1"] < 0) | (recs["x2"] > w) | (recs["y2"] > h) |
+                        (ks < 1) | (ks > 51) | (ks % 2 == 0)).any():
                     raise ValueError("heat-map defect with an invalid region or blur kernel")
-                it = np.zeros((), H.ITEM_DTYPE)
-                it["d"] = r
-                if ks > 1:
-                    it["d"]["koff"] = kernel_offset(kern[int(r["koff"]):int(r["koff"]) + ks])
-                it["frame"], it["tab_off"] = len(fdesc) - 1, tab
-                tab += rw + rh
-                if int(r["kind"]) == 0 and ks > 1:
-                    it["tmp_off"] = tmp
-                    tmp += rw * rh
+                it = np.zeros(len(recs), H.ITEM_DTYPE)
+                it["d"] = recs
+                for j in np.nonzero(ks > 1)[0]:
+                    o = int(recs["koff"][j])
+                    it["d"]["koff"][j] = kernel_offset(kern[o:o + int(ks[j])])
+                it["frame"] = len(frames) - 1
+                tsz = 3 * (rw.astype(np.int64) + rh)
+                it["tab_off"] = tab + np.concatenate([[0], np.cumsum(tsz)[:-1]])
+                tab += int(tsz.sum())
+                blurred = (recs["kind"] == 0) & (ks > 1)
+                rsz = np.where(blurred, rw.astype(np.int64) * rh, 0)
+                it["tmp_off"] = tmp + np.concatenate([[0], np.cumsum(rsz)[:-1]])
+                tmp += int(rsz.sum())
                 items.append(it)
             plane += h * w
-            live.append(i)
-        if not fdesc:
+        if len(frames) > 65535 or sum(len(it) for it in items) > 65535:
+            raise ValueError("at most 65535 frames / defects per heatmap_batch call")
+        it_arr = np.concatenate(items) if items else np.zeros(0, H.ITEM_DTYPE)
+        up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
+        plan = {"copies": copies, "frames": frames, "n_items": len(it_arr), "plane": plane, "tmp": tmp, "tab": tab,
+                "shapes": [tuple(s_) for s_ in shapes]}
+        if frames:
+            plan["d_items"] = up(it_arr) if len(it_arr) else None
+            plan["d_kern"] = torch.from_numpy(np.concatenate(kernels).astype(np.float32)).to(self.device)
+            plan["max_rw"] = int((it_arr["d"]["x2"] - it_arr["d"]["x1"]).max()) if len(it_arr) else 0
+            plan["max_rh"] = int((it_arr["d"]["y2"] - it_arr["d"]["y1"]).max()) if len(it_arr) else 0
+        return plan
+
+    def heatmap_batch(self, frames, defects_per_frame=None, plan: dict | None = None) -> list:
+        """``create_heatmap_overlay`` for a batch of BGR uint8 HWC CUDA frames (a ``[B,H,W,3]`` tensor or a list, mixed
+        sizes allowed): SIX launches for the whole batch.  Returns a list of new frames, aligned with the input.
+        ``plan``: a ``plan_heatmap`` result for these shapes (the host half, reusable)."""
+        from . import heatmap as H
+        batch = list(frames.unbind(0)) if isinstance(frames, torch.Tensor) and frames.dim() == 4 else list(frames)
+        for f in batch:
+            self._check_u8(f)
+            if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
+        shapes = [(int(f.shape[0]), int(f.shape[1])) for f in batch]
+        if plan is None:
+            if defects_per_frame is None or len(batch) != len(defects_per_frame):
+                raise ValueError("one defect list per frame expected")
+            plan = self.plan_heatmap(shapes, defects_per_frame)
+        elif plan["shapes"] != shapes:
+            raise ValueError("the plan was made for other frame shapes")
+        outs = [None] * len(batch)
+        for i in plan["copies"]:
+            outs[i] = batch[i].clone()
+        if not plan["frames"]:
             self.last_launches = 0
             return outs
-        if len(fdesc) > 65535 or len(items) > 65535:
-            raise ValueError("at most 65535 frames / defects per heatmap_batch call")
-        fr = np.zeros(len(fdesc), N.HEAT_FRAME_DTYPE)
-        for j, row in enumerate(fdesc):
-            fr[j] = row
-        it_arr = np.array(items, H.ITEM_DTYPE) if items else np.zeros(1, H.ITEM_DTYPE)
-        up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
-        d_fr, d_it = up(fr), up(it_arr)
-        d_kern = torch.from_numpy(np.concatenate(kernels).astype(np.float32)).to(self.device)
+        fr = np.zeros(len(plan["frames"]), N.HEAT_FRAME_DTYPE)
+        for j, (i, h, w, plane_off, fk, fkoff) in enumerate(plan["frames"]):
+            out = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+            outs[i] = out
+            fr[j] = (batch[i].data_ptr(), out.data_ptr(), batch[i].stride(0), out.stride(0), h, w, plane_off, fk, fkoff)
+        d_fr = torch.from_numpy(fr.view(np.uint8).reshape(-1).copy()).to(self.device)
         if not hasattr(self, "_jet"):
             self._jet = torch.from_numpy(H.JET_BGR.copy()).to(self.device)
-        planes = torch.empty((3, plane), dtype=torch.float32, device=self.device)
-        d_tmp = torch.empty(max(tmp, 1), dtype=torch.float32, device=self.device)
-        d_tab = torch.empty(max(tab, 1), dtype=torch.float64, device=self.device)
-        d_max = torch.empty(len(fdesc), dtype=torch.int32, device=self.device)
-        max_rw = max((int(it["d"]["x2"] - it["d"]["x1"]) for it in items), default=0)
-        max_rh = max((int(it["d"]["y2"] - it["d"]["y1"]) for it in items), default=0)
-        N.check(self.L.vis_heatmap_batch(d_fr.data_ptr(), len(fdesc), d_it.data_ptr() if items else None, len(items),
-                                         int(fr["w"].max()), int(fr["h"].max()), max_rw, max_rh, plane,
-                                         d_kern.data_ptr(), self._jet.data_ptr(), planes[0].data_ptr(), planes[1].data_ptr(),
-                                         planes[2].data_ptr(), d_tmp.data_ptr(), d_tab.data_ptr(), d_max.data_ptr(),
-                                         _stream_ptr()), "vis_heatmap_batch")
-        self.last_launches = 3 + (3 if items else 0)
-        self._keepalive_h = (d_fr, d_it, d_kern, planes, d_tmp, d_tab, d_max)
+        planes = torch.empty((3, plan["plane"]), dtype=torch.float32, device=self.device)
+        d_tmp = torch.empty(max(plan["tmp"], 1), dtype=torch.float32, device=self.device)
+        d_tab = torch.empty(max(plan["tab"], 1), dtype=torch.float64, device=self.device)
+        d_max = torch.empty(len(fr), dtype=torch.int32, device=self.device)
+        n_items = plan["n_items"]
+        N.check(self.L.vis_heatmap_batch(d_fr.data_ptr(), len(fr), plan["d_items"].data_ptr() if n_items else None, n_items,
+                                         int(fr["w"].max()), int(fr["h"].max()), plan["max_rw"], plan["max_rh"], plan["plane"],
+                                         plan["d_kern"].data_ptr(), self._jet.data_ptr(), planes[0].data_ptr(),
+                                         planes[1].data_ptr(), planes[2].data_ptr(), d_tmp.data_ptr(), d_tab.data_ptr(),
+                                         d_max.data_ptr(), _stream_ptr()), "vis_heatmap_batch")
+        self.last_launches = 3 + (3 if n_items else 0)
+        self._keepalive_h = (d_fr, plan, planes, d_tmp, d_tab, d_max)
         return outs
 
     # ------------------------------------------------------------------ comparison panel / status stamp
@@ -1351,7 +1374,7 @@ def _locked(fn):
 # one script thread per session): every public entry point holds the engine's lock while it plans and enqueues.
 for _name in ("resize_batch_u8", "resize_u8", "resize_hp", "reduce_u8", "resize_box_u8", "alpha_premultiply_", "resize_nearest_u8",
               "resize_reducing_u8", "agent_inputs", "plan_batch", "preprocess", "preprocess_dual", "preprocess_host", "preprocess_jpeg", "plan_overlay", "annotate",
-              "heatmap", "heatmap_batch", "side_by_side", "status_stamp", "quality_stats"):
+              "heatmap", "plan_heatmap", "heatmap_batch", "side_by_side", "status_stamp", "quality_stats"):
     setattr(Engine, _name, _locked(getattr(Engine, _name)))
 del _name
 

@@ -8,6 +8,7 @@ max, JET colouring and the 0.6/0.4 blend — runs in the CUDA library (vis_heatm
 from __future__ import annotations
 
 import base64
+import functools
 import logging
 import zlib
 
@@ -41,11 +42,18 @@ _CONFIDENCE_FACTOR = {"high": 1.0, "medium": 0.75, "low": 0.55}                 
 _WIDESPREAD = ("entire surface", "everywhere", "whole component", "complete surface")         # :398
 
 
-def gaussian_kernel(ksize: int, sigma: float) -> np.ndarray:
-    """cv2.getGaussianKernel(ksize, sigma, CV_32F) for sigma > 0: exp in double, normalised in double, cast to float."""
+@functools.lru_cache(maxsize=1024)
+def _gaussian_kernel(ksize: int, sigma: float) -> np.ndarray:
     x = np.arange(ksize, dtype=np.float64) - (ksize - 1) * 0.5
     t = np.exp((-0.5 / (sigma * sigma)) * x * x)
-    return (t * (1.0 / t.sum())).astype(np.float32)
+    k = (t * (1.0 / t.sum())).astype(np.float32)
+    k.setflags(write=False)
+    return k
+
+
+def gaussian_kernel(ksize: int, sigma: float) -> np.ndarray:
+    """cv2.getGaussianKernel(ksize, sigma, CV_32F) for sigma > 0: exp in double, normalised in double, cast to float."""
+    return _gaussian_kernel(int(ksize), float(sigma))
 
 
 def blur_kernel_size(sigma: float, cap: int) -> int:
@@ -72,11 +80,9 @@ def defect_params(defects: list, width: int, height: int):
         has_valid_bbox = bool(bbox and bbox.get("x") is not None and bbox.get("y") is not None
                               and bbox.get("width", 0) > 0 and bbox.get("height", 0) > 0)
         if bbox is None and any(kw in location for kw in _WIDESPREAD):
-            r = np.zeros((), HEAT_DTYPE)
-            r["kind"], r["intensity"], r["ksize"] = 1, intensity, 1
-            r["cx"], r["cy"], r["sigma"] = width // 2, height // 2, (max(width, height) // 2) * 0.7
-            r["x1"], r["y1"], r["x2"], r["y2"] = 0, 0, width, height
-            recs.append(r)
+            # (kind, x, y, w, h, x1, y1, x2, y2, ksize, koff, pad, intensity, cx, cy, sigma)
+            recs.append((1, 0, 0, 0, 0, 0, 0, width, height, 1, 0, 0, intensity, width // 2, height // 2,
+                         (max(width, height) // 2) * 0.7))
             continue
         if not has_valid_bbox:
             continue
@@ -115,17 +121,11 @@ def defect_params(defects: list, width: int, height: int):
             continue
         bsig = sigma * 0.4
         ksize = blur_kernel_size(bsig, 51)
-        r = np.zeros((), HEAT_DTYPE)
-        r["kind"], r["intensity"], r["cx"], r["cy"], r["sigma"] = 0, intensity, cx, cy, sigma
-        r["x"], r["y"], r["w"], r["h"] = x, y, w, h
-        r["x1"], r["y1"], r["x2"], r["y2"] = x1, y1, x2, y2
-        r["ksize"] = ksize if ksize > 1 else 1
-        r["koff"] = koff
+        recs.append((0, x, y, w, h, x1, y1, x2, y2, ksize if ksize > 1 else 1, koff, 0, intensity, cx, cy, sigma))
         if ksize > 1:
             k = gaussian_kernel(ksize, bsig)
             kernels.append(k)
             koff += len(k)
-        recs.append(r)
     rec_arr = np.array(recs, HEAT_DTYPE) if recs else np.zeros(0, HEAT_DTYPE)
     kern = np.concatenate(kernels) if kernels else np.zeros(1, np.float32)
     return rec_arr, kern, had

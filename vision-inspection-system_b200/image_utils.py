@@ -101,7 +101,10 @@ def validate_image(image_path: Path, allowed_extensions: list = None, max_size_m
 
 _CODECS = ("host", "nvjpeg")
 # modes Pillow resamples in double precision: (vis_resample_hp kind, bytes per pixel); tobytes() of "I" / "F" is native order
-_HP_MODES = {"I;16": (0, 2), "I;16L": (0, 2), "I;16B": (1, 2), "I": (2, 4), "F": (3, 4)}
+# Byte order of the 16-bit modes AS PILLOW 12.2 RESAMPLES THEM on a little-endian host (Resample.c keys the order on the
+# mode name "I;16N" only): "I;16B" words are read little-endian, "I;16N" words big-endian.  Mirrored, not corrected: the
+# reference's resize_image returns exactly those bytes (tests/test_gpu_resize.py pins all four names against Pillow).
+_HP_MODES = {"I;16": (0, 2), "I;16L": (0, 2), "I;16B": (0, 2), "I;16N": (1, 2), "I": (2, 4), "F": (3, 4)}
 _JPEG_SUFFIXES = (".jpg", ".jpeg", ".jpe")
 
 
