@@ -244,3 +244,13 @@ def test_preprocess_dual_equals_two_role_passes(engine):
     assert launches <= 14, launches
     again = engine.preprocess_dual(dev, out=torch.empty_like(torch.cat([res["inspector"][0], res["auditor"][0]])))
     assert torch.equal(again["auditor"][0], res["auditor"][0]) and torch.equal(again["inspector"][0], res["inspector"][0])
+    # a frame >= 4x the Auditor's limit takes Pillow's reduce pre-pass (not cacheable as one fused launch): still exact,
+    # next to an unaligned 502-pixel frame in the same call; twice, because the second call reuses the cached plan
+    big = [synth.noise_frame(9200, 2200, 4400), synth.noise_frame(9201, 100, 502), synth.noise_frame(9202, 1080, 1920)]
+    dev_big = [torch.from_numpy(f).cuda() for f in big]
+    for _ in range(2):
+        res = engine.preprocess_dual(dev_big)
+        for role, limit in (("inspector", 2048), ("auditor", 1024)):
+            want, wgrid = Q.preprocess([Q.agent_thumbnail(f, limit) for f in big])
+            assert np.array_equal(res[role][1].numpy(), wgrid), role
+            check_equal(res[role][0].cpu().numpy(), want, ("reduce pre-pass", role))
