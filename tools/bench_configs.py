@@ -91,12 +91,8 @@ def dual_stream(eng, name, n):
     launches = [0]
 
     def run():
-        launches[0] = 0
-        for role in ("inspector", "auditor"):                       # thumbnails: one fused launch per source geometry
-            batch = eng.agent_inputs(frames, role)
-            launches[0] += eng.last_launches
-            eng.preprocess(batch)
-            launches[0] += eng.last_launches
+        eng.preprocess_dual(frames)                     # cached plan: thumbnails per source geometry, one plan over both roles
+        launches[0] = eng.last_launches
     ms = timed(run, reps=3, warm=2)
     report(name, n, ms, nbytes, launches[0], "mixed resolutions, Inspector (2048) + Auditor (1024) inputs per frame; "
            "bytes = frame once + both pixel_values (thumbnails not credited)")
