@@ -104,6 +104,9 @@ __device__ __forceinline__ void load_rec_dp(uint32_t (&k)[3 * W], uint32_t addr)
 }
 
 // one output byte: W packed words (4 taps each) against the record's three limb rows; Pillow's (acc + 2^21) >> 22, clip8
+#ifndef VIS_DP_PREFETCH
+#define VIS_DP_PREFETCH 0      // A/B: ping-pong prefetch of the next emit's coefficients: 70.4 k -> 70.0 k images/s on 4K (profiles/r02_dp_prefetch_rejected.txt)
+#endif
 #ifndef VIS_DP_SERIAL_LIMBS
 #define VIS_DP_SERIAL_LIMBS 0
 #endif
@@ -246,6 +249,13 @@ k_fused_dp(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ fr
                 // this lane's byte in column (U.xa - S.x0) of channel 0; a column is cpitch bytes, a channel hplane
                 uint32_t hdst = smem_u32(smem + L.off_hring + slot * 3 * L.hplane + (U.xa - S.x0) * L.cpitch + CARRY + lane);
                 uint32_t hp = hrec0;
+#if VIS_DP_PREFETCH
+                // the coefficients of the NEXT emit are requested while the current one multiplies: two register sets
+                // that swap roles every emit (two copies of each emit body instead of 3W moves per emit)
+                uint32_t ka[3 * W], kb[3 * W];
+                load_rec_dp<W>(ka, hp);
+                bool odd = false;
+#endif
 #pragma unroll 1
                 for (int i = 0; i < U.nsteps; ++i) {
                     const uint32_t m = (uint32_t)um[4 * i] | ((uint32_t)um[4 * i + 1] << 8);
@@ -267,11 +277,7 @@ k_fused_dp(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ fr
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int cnt = __popc((m >> (4 * g)) & 0xfu);   // windows ending in word group g (uniform)
-#pragma unroll 1
-                        for (int e = 0; e < cnt; ++e) {
-                            uint32_t kw[3 * W];
-                            load_rec_dp<W>(kw, hp);
-                            hp += STRIDE * 4;
+                        auto emit = [&](const uint32_t (&kw)[3 * W]) {
                             const int v0 = mac_dp<W>(&win[0][g], kw);
                             const int v1 = mac_dp<W>(&win[1][g], kw);
                             const int v2 = mac_dp<W>(&win[2][g], kw);
@@ -279,6 +285,19 @@ k_fused_dp(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ fr
                             asm volatile("st.shared.u8 [%0], %1;" ::"r"(hdst + (uint32_t)L.hplane), "r"(v1) : "memory");
                             asm volatile("st.shared.u8 [%0], %1;" ::"r"(hdst + 2u * (uint32_t)L.hplane), "r"(v2) : "memory");
                             hdst += (uint32_t)L.cpitch;
+                        };
+#pragma unroll 1
+                        for (int e = 0; e < cnt; ++e) {
+#if VIS_DP_PREFETCH
+                            hp += STRIDE * 4;                  // the slot holds sw + 1 records: always readable
+                            if (!odd) { load_rec_dp<W>(kb, hp); emit(ka); } else { load_rec_dp<W>(ka, hp); emit(kb); }
+                            odd = !odd;
+#else
+                            uint32_t kw[3 * W];
+                            load_rec_dp<W>(kw, hp);
+                            hp += STRIDE * 4;
+                            emit(kw);
+#endif
                         }
                     }
 #pragma unroll
