@@ -29,10 +29,13 @@ using namespace visf;
 
 namespace {
 
+#ifndef VIS_DP_SWARPS
+#define VIS_DP_SWARPS 2
+#endif
 #ifndef VIS_DP_HWARPS
 #define VIS_DP_HWARPS 12
 #endif
-constexpr int kHWarps = VIS_DP_HWARPS, kSWarps = 2;     // A/B on 4K frames: 12 -> 70.4 k, 16 -> 66.2 k, 20 -> 65.4 k images/s (profiles/r02_dp_hwarps.txt)
+constexpr int kHWarps = VIS_DP_HWARPS, kSWarps = VIS_DP_SWARPS;     // A/B on 4K frames: 12 -> 70.4 k, 16 -> 66.2 k, 20 -> 65.4 k images/s (profiles/r02_dp_hwarps.txt)
 static_assert(kHWarps <= VIS_SCHED_MAX_SUBS, "schedule holds at most VIS_SCHED_MAX_SUBS sub-ranges per strip");
 // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
 constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
@@ -104,6 +107,9 @@ __device__ __forceinline__ void load_rec_dp(uint32_t (&k)[3 * W], uint32_t addr)
 }
 
 // one output byte: W packed words (4 taps each) against the record's three limb rows; Pillow's (acc + 2^21) >> 22, clip8
+#ifndef VIS_DP_LAZY
+#define VIS_DP_LAZY 0
+#endif
 #ifndef VIS_DP_PREFETCH
 #define VIS_DP_PREFETCH 0      // A/B: ping-pong prefetch of the next emit's coefficients: 70.4 k -> 70.0 k images/s on 4K (profiles/r02_dp_prefetch_rejected.txt)
 #endif
@@ -267,6 +273,7 @@ k_fused_dp(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ fr
                     }
                     sa += kStepPx * 3;
                     // de-interleave: pixels 4q..4q+3 of a channel are bytes c, c+3, c+6, c+9 of raw[3q..3q+2]
+#if !VIS_DP_LAZY
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t r0 = raw[3 * q], r1 = raw[3 * q + 1], r2 = raw[3 * q + 2];
@@ -274,8 +281,17 @@ k_fused_dp(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ fr
                         win[1][W - 1 + q] = __byte_perm(__byte_perm(r0, r1, 0x0741), r2, 0x6210);
                         win[2][W - 1 + q] = __byte_perm(__byte_perm(r0, r1, 0x0052), r2, 0x7410);
                     }
+#endif
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
+#if VIS_DP_LAZY
+                        {   // word group g is de-interleaved right before its emits: permutes between the dot-product bursts
+                            const uint32_t r0 = raw[3 * g], r1 = raw[3 * g + 1], r2 = raw[3 * g + 2];
+                            win[0][W - 1 + g] = __byte_perm(__byte_perm(r0, r1, 0x0630), r2, 0x5210);
+                            win[1][W - 1 + g] = __byte_perm(__byte_perm(r0, r1, 0x0741), r2, 0x6210);
+                            win[2][W - 1 + g] = __byte_perm(__byte_perm(r0, r1, 0x0052), r2, 0x7410);
+                        }
+#endif
                         const int cnt = __popc((m >> (4 * g)) & 0xfu);   // windows ending in word group g (uniform)
                         auto emit = [&](const uint32_t (&kw)[3 * W]) {
                             const int v0 = mac_dp<W>(&win[0][g], kw);
