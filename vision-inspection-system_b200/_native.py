@@ -101,30 +101,46 @@ class HostRecords(np.ndarray):
 
     def __array_finalize__(self, obj):
         self.keep = getattr(obj, "keep", None)
+        self.strings = None                 # the strings of a freshly built array, in record order (not kept by views)
 
 
 def cv_text(text) -> bytes:
     """The bytes cv2.putText receives for a Python string: UTF-8, cut at the first NUL."""
     if isinstance(text, (bytes, bytearray)):
-        return bytes(text).split(b"\0")[0]
-    return str(text).encode("utf-8", "replace").split(b"\0")[0]
+        b = bytes(text)
+    else:
+        b = str(text).encode("utf-8", "replace")
+    return b.split(b"\0")[0] if b"\0" in b else b
+
+
+# Short strings ('1' .. '99', the default panel labels) recur on every frame: their buffers are interned once (bounded),
+# everything else gets a buffer owned by the array that points at it.
+_INTERNED: dict = {}
+_INTERN_MAX, _INTERN_LEN = 4096, 32
+
+
+def _string_address(b: bytes, keep: list) -> int:
+    hit = _INTERNED.get(b)
+    if hit is not None:
+        return hit[1]
+    buf = C.create_string_buffer(b)
+    addr = C.addressof(buf)
+    if len(b) <= _INTERN_LEN and len(_INTERNED) < _INTERN_MAX:
+        _INTERNED[b] = (buf, addr)
+    else:
+        keep.append(buf)
+    return addr
 
 
 def host_records(rows: list, dtype: np.dtype, string_field: str) -> "HostRecords":
     """Records from tuples whose ``string_field`` entry is ``bytes``: the strings are stored in ctypes buffers owned
-    by the returned array and the field receives their addresses."""
-    names = list(dtype.names)
-    k = names.index(string_field)
-    keep, fixed = [], []
-    for row in rows:
-        buf = C.create_string_buffer(row[k])
-        keep.append(buf)
-        fixed.append(tuple(row[:k]) + (C.addressof(buf),) + tuple(row[k + 1:]))
-    arr = np.zeros(len(fixed), dtype)
-    for j, row in enumerate(fixed):
-        arr[j] = row
-    out = arr.view(HostRecords)
+    by the returned array (or interned) and the field receives their addresses."""
+    k = dtype.names.index(string_field)
+    keep: list = []
+    fixed = [row[:k] + (_string_address(row[k], keep),) + row[k + 1:] for row in rows]
+    out = (np.array(fixed, dtype) if fixed else np.zeros(0, dtype)).view(HostRecords)
     out.keep = keep
+    out.strings = [row[k] for row in rows]
     return out
 
 

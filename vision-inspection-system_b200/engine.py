@@ -996,7 +996,8 @@ class Engine:
         for (h, w), px in zip(shapes, px_all):
             if len(px):
                 radius = max(25, min(int(max(w, h) * 0.04), 60))
-                keys.update((radius, int(p["b"]), int(p["g"]), int(p["r"]), O.box_label(p)) for p in px)
+                labels = px.strings if getattr(px, "strings", None) is not None else [O.box_label(p) for p in px]
+                keys.update(zip([radius] * len(px), px["b"].tolist(), px["g"].tolist(), px["r"].tolist(), labels))
         # dashes (confidence == "low") are 10 px long, the last one of an edge 1..9: one recorded stamp per length and
         # orientation, shared by every colour
         dashes = [(L, 0) for L in range(1, 11)] + [(0, L) for L in range(1, 11)] if any(

@@ -23,6 +23,8 @@ _COSMETIC_BGR = (0, 200, 255)        # COSMETIC (utils/image_utils.py:252)
 def filter_by_confidence(boxes, confidence_threshold: str = "low", criticality: str = "medium") -> list:
     """utils/image_utils.py:177-189: keep boxes at or above the threshold, or everything when criticality is high."""
     threshold = _CONFIDENCE_LEVELS.get(confidence_threshold, 1)
+    if threshold <= 1 or criticality == "high":      # nothing can fall below "low": the reference keeps every box
+        return boxes
     kept = []
     for box in boxes:
         level = _CONFIDENCE_LEVELS.get(box.get("confidence", "medium"), 2)
@@ -39,9 +41,11 @@ def boxes_to_pixels(boxes, img_width: int, img_height: int, confidence_threshold
     """Percent boxes -> ``VisBox`` records, skipping (with a warning) exactly the boxes the reference skips.  Like
     the reference (utils/image_utils.py:192-313) this never raises on the content of a box: labels may be any text."""
     out = []
+    cv_text = N.cv_text
     for i, box in enumerate(filter_by_confidence(boxes, confidence_threshold, criticality)):
-        raw_x, raw_y = box.get("x", 0), box.get("y", 0)
-        raw_w, raw_h = box.get("width", 10), box.get("height", 10)
+        get = box.get
+        raw_x, raw_y = get("x", 0), get("y", 0)
+        raw_w, raw_h = get("width", 10), get("height", 10)
         if not (0 <= raw_x <= 100 and 0 <= raw_y <= 100 and 0 < raw_w <= 100 and 0 < raw_h <= 100):
             logger.warning("Invalid bbox coordinates (out of 0-100 range): %s", box)
             continue
@@ -66,15 +70,15 @@ def boxes_to_pixels(boxes, img_width: int, img_height: int, confidence_threshold
         if w <= 0 or h <= 0:
             logger.warning("Bbox invalid after clamping, skipping: %s", box)
             continue
-        label_full = box.get("label", f"#{i + 1}")    # index over the confidence-filtered list
+        label_full = get("label", f"#{i + 1}")        # index over the confidence-filtered list
         try:
             label_text = label_full.replace("#", "")
         except Exception:
             label_text = str(i + 1)
-        color = _COSMETIC_BGR if box.get("severity", "MODERATE") == "COSMETIC" else _RED_BGR
-        dashed = box.get("confidence", "medium") == "low"
+        color = _COSMETIC_BGR if get("severity", "MODERATE") == "COSMETIC" else _RED_BGR
         # any text, any length: cv2.putText receives the UTF-8 bytes and draws '?' for every byte outside 32..126
-        out.append((x, y, w, h, color[0], color[1], color[2], 1 if dashed else 0, N.cv_text(label_text)))
+        out.append((x, y, w, h, color[0], color[1], color[2], 1 if get("confidence", "medium") == "low" else 0,
+                    cv_text(label_text)))
     return N.host_records(out, N.BOX_DTYPE, "label")
 
 
