@@ -983,25 +983,24 @@ class Engine:
         """
         from . import overlay as O
         # host rules per frame (Python, like the reference), then ONE threaded C call for expansion + tile binning
-        px_all, box_begin, hw = [], [0], np.zeros((len(shapes), 2), np.int32)
+        rows_all, box_begin, hw = [], [0], np.zeros((len(shapes), 2), np.int32)
+        keys, any_dashed = set(), False
         for i, ((h, w), boxes) in enumerate(zip(shapes, boxes_per_frame)):
-            px = O.boxes_to_pixels(boxes, w, h, confidence_threshold, criticality)
-            px_all.append(px)
-            box_begin.append(box_begin[-1] + len(px))
+            rows = O.box_rows(boxes, w, h, confidence_threshold, criticality)
+            rows_all.extend(rows)
+            box_begin.append(box_begin[-1] + len(rows))
             hw[i] = (h, w)
-        boxes_arr = np.concatenate(px_all) if box_begin[-1] else np.zeros(1, N.BOX_DTYPE)
-        # markers are opaque: each distinct (radius, colour, label) of the batch is rasterised once on the device and
-        # referenced by one sprite leaf per box (utils/image_utils.py:292-293 for the radius rule)
-        keys = set()
-        for (h, w), px in zip(shapes, px_all):
-            if len(px):
+            if rows:
+                # markers are opaque: each distinct (radius, colour, label) of the batch is rasterised once on the device
+                # and referenced by one sprite leaf per box (utils/image_utils.py:292-293 for the radius rule)
                 radius = max(25, min(int(max(w, h) * 0.04), 60))
-                labels = px.strings if getattr(px, "strings", None) is not None else [O.box_label(p) for p in px]
-                keys.update(zip([radius] * len(px), px["b"].tolist(), px["g"].tolist(), px["r"].tolist(), labels))
+                for r in rows:
+                    keys.add((radius, r[4], r[5], r[6], r[8]))
+                    any_dashed = any_dashed or bool(r[7])
+        boxes_arr = N.host_records(rows_all, N.BOX_DTYPE, "label") if rows_all else np.zeros(1, N.BOX_DTYPE)
         # dashes (confidence == "low") are 10 px long, the last one of an edge 1..9: one recorded stamp per length and
         # orientation, shared by every colour
-        dashes = [(L, 0) for L in range(1, 11)] + [(0, L) for L in range(1, 11)] if any(
-            len(px) and bool(px["dashed"].any()) for px in px_all) else []
+        dashes = [(L, 0) for L in range(1, 11)] + [(0, L) for L in range(1, 11)] if any_dashed else []
         entries, keep_sprites = [], []
         for key in sorted(keys):
             hit = self._marker_sprite(*key)

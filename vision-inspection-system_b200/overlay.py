@@ -40,6 +40,12 @@ def boxes_to_pixels(boxes, img_width: int, img_height: int, confidence_threshold
                     criticality: str = "medium") -> np.ndarray:
     """Percent boxes -> ``VisBox`` records, skipping (with a warning) exactly the boxes the reference skips.  Like
     the reference (utils/image_utils.py:192-313) this never raises on the content of a box: labels may be any text."""
+    return N.host_records(box_rows(boxes, img_width, img_height, confidence_threshold, criticality), N.BOX_DTYPE, "label")
+
+
+def box_rows(boxes, img_width: int, img_height: int, confidence_threshold: str = "low", criticality: str = "medium") -> list:
+    """The same as plain tuples ``(x, y, w, h, b, g, r, dashed, label bytes)`` — what a batch planner concatenates before it
+    builds ONE record array (1024 small structured arrays cost more to concatenate than to fill)."""
     out = []
     cv_text = N.cv_text
     for i, box in enumerate(filter_by_confidence(boxes, confidence_threshold, criticality)):
@@ -79,7 +85,7 @@ def boxes_to_pixels(boxes, img_width: int, img_height: int, confidence_threshold
         # any text, any length: cv2.putText receives the UTF-8 bytes and draws '?' for every byte outside 32..126
         out.append((x, y, w, h, color[0], color[1], color[2], 1 if get("confidence", "medium") == "low" else 0,
                     cv_text(label_text)))
-    return N.host_records(out, N.BOX_DTYPE, "label")
+    return out
 
 
 def box_label(rec) -> bytes:
