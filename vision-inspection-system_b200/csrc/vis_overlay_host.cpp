@@ -1114,32 +1114,36 @@ extern "C" int vis_overlay_plan_batch_sprites(int n_frames, const int32_t* hw, c
         g_sprites = sprites;                      // thread-local: the expansion of this thread may emit sprite leaves
         g_n_sprites = n_sprites;
         struct Reset { ~Reset() { g_sprites = nullptr; g_n_sprites = 0; } } reset;
+        static thread_local std::vector<VisLeaf> scratch_l;
+        static thread_local std::vector<int32_t> scratch_t, scratch_r;
         for (int i = next.fetch_add(1); i < n_frames; i = next.fetch_add(1)) {
             Frame& fr = out[(size_t)i];
             const int h = hw[2 * i], w = hw[2 * i + 1], nb = box_begin[i + 1] - box_begin[i];
             const VisBox* b = boxes + box_begin[i];
             if (nb <= 0) continue;
+            // worst-case scratch lives once per thread and is never zero-filled (value-initialising 1400 leaves per box
+            // and a full tile grid per frame used to cost more than the expansion itself); a frame keeps exact-size copies
             int need = 0;
-            fr.leaves.resize((size_t)nb * 1400);
-            int rc = vis_overlay_expand(h, w, b, nb, fr.leaves.data(), (int)fr.leaves.size(), &need);
+            if (scratch_l.size() < (size_t)nb * 1400) scratch_l.resize((size_t)nb * 1400);
+            int rc = vis_overlay_expand(h, w, b, nb, scratch_l.data(), (int)scratch_l.size(), &need);
             if (rc == VIS_E_CAPACITY) {
-                fr.leaves.resize((size_t)need);
-                rc = vis_overlay_expand(h, w, b, nb, fr.leaves.data(), (int)fr.leaves.size(), &need);
+                scratch_l.resize((size_t)need);
+                rc = vis_overlay_expand(h, w, b, nb, scratch_l.data(), (int)scratch_l.size(), &need);
             }
             if (rc < 0) { fr.rc = rc; fr.err = vis_last_error(); continue; }
-            fr.leaves.resize((size_t)rc);
+            fr.leaves.assign(scratch_l.begin(), scratch_l.begin() + rc);
             int nt = 0, nr = 0;
             const int tcap = ((w + 63) / 64) * ((h + 15) / 16);
-            fr.tiles.resize((size_t)tcap * 3);
-            fr.refs.resize((size_t)tcap * 8);
-            rc = vis_overlay_tiles(h, w, fr.leaves.data(), nb, fr.tiles.data(), tcap, fr.refs.data(), (int)fr.refs.size() / 2, &nt, &nr);
+            if (scratch_t.size() < (size_t)tcap * 3) scratch_t.resize((size_t)tcap * 3);
+            if (scratch_r.size() < (size_t)tcap * 8) scratch_r.resize((size_t)tcap * 8);
+            rc = vis_overlay_tiles(h, w, fr.leaves.data(), nb, scratch_t.data(), tcap, scratch_r.data(), (int)scratch_r.size() / 2, &nt, &nr);
             if (rc == VIS_E_CAPACITY) {
-                fr.refs.resize((size_t)nr * 2);
-                rc = vis_overlay_tiles(h, w, fr.leaves.data(), nb, fr.tiles.data(), tcap, fr.refs.data(), nr, &nt, &nr);
+                scratch_r.resize((size_t)nr * 2);
+                rc = vis_overlay_tiles(h, w, fr.leaves.data(), nb, scratch_t.data(), tcap, scratch_r.data(), nr, &nt, &nr);
             }
             if (rc < 0) { fr.rc = rc; fr.err = vis_last_error(); continue; }
-            fr.tiles.resize((size_t)nt * 3);
-            fr.refs.resize((size_t)nr * 2);
+            fr.tiles.assign(scratch_t.begin(), scratch_t.begin() + (size_t)nt * 3);
+            fr.refs.assign(scratch_r.begin(), scratch_r.begin() + (size_t)nr * 2);
         }
     };
     int nth = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
