@@ -4,17 +4,53 @@
 //   cv2.cvtColor(BGR2GRAY)            -> gray = (3735*B + 19235*G + 9798*R + 2^14) >> 15   (cv: RGB2Gray<uchar>, 15-bit)
 //   cv2.Laplacian(gray, CV_64F).var() -> 3x3 kernel [0 1 0; 1 -4 1; 0 1 0], BORDER_REFLECT_101; integer valued
 //   np.mean(gray)
-// One pass over the BGR frame: a CTA converts a 128x32 tile plus a one-pixel halo to gray in shared memory (packed, four
-// pixels per word), every thread evaluates the Laplacians of four words in packed 16-bit lanes, and the three sums the
-// caller needs — sum(gray), sum(lap), sum(lap^2) — are reduced exactly in int64 (warp shuffles, one atomicAdd per CTA).  Variance and scores are
-// finished on the host from these exact sums.  Bound: HBM (H*W*3 bytes read per frame).
-#include "vis_internal.h"
+// One pass over the BGR frame.  A CTA owns up to eight adjacent 128-pixel strips of a 72-row band; a producer warp
+// streams the band's rows (one cp.async.bulk of up to 3 KB per row, plus 16 bytes of halo either side) through a ring
+// of shared-memory stages guarded by mbarriers, so the bytes in flight do not depend on what the compute warps are
+// doing.  A compute WARP owns one strip and walks down it; a lane owns four pixels (12 bytes = three words, read
+// conflict-free from the stage) of every row and keeps the gray rows above / at / below in registers, in two packed
+// 16-bit lanes each (even pixels, odd pixels).  The gray conversion is eight IDP.2A on the raw words
+// with weights doubled, so that the result is byte 2 of the accumulator (no shift, no unaligned pixel extraction); the
+// horizontal neighbours of a lane's first / last pixel come from the adjacent lanes by shuffle (the strip's own halo
+// columns are converted once per 32 rows, one row per lane, and broadcast); the four Laplacians of a lane are two
+// packed 16-bit sums biased by 1024.  Sums are kept biased (sum v, sum v^2, count) and unbiased once per band in int64;
+// the three sums the caller needs — sum(gray), sum(lap), sum(lap^2) — are reduced exactly (warp shuffles, one
+// atomicAdd triple per CTA of eight strips).  Variance and scores are finished on the host from these exact sums.
+// Frames whose rows are not 16-byte aligned take the same walk with per-lane 32-bit global loads (4-byte aligned) or
+// byte loads (anything else, and the partial strip at the right edge).  Bound: HBM (H*W*3 bytes read per frame, + 2
+// halo rows per band).
+#include "vis_fused_common.cuh"
 
 namespace {
+using namespace visf;
 
-constexpr int kTW = 128, kTH = 32, kThreads = 256;
-constexpr int kTilesPerCta = 8;                   // a CTA walks 8 tiles down its column: launch overhead, reduction and atomics per 256 rows
-constexpr int kRowWords = kTW / 4 + 2;            // one word of left halo (its last byte is used), 32 tile words, one of right halo
+#ifndef VIS_Q_BAND
+#define VIS_Q_BAND 72
+#endif
+#ifndef VIS_Q_AHEAD
+#define VIS_Q_AHEAD 4
+#endif
+#ifndef VIS_Q_MINB
+#define VIS_Q_MINB 3
+#endif
+#ifndef VIS_Q_K
+#define VIS_Q_K 8
+#endif
+#ifndef VIS_Q_S
+#define VIS_Q_S 3
+#endif
+constexpr int kStripW = 128;                      // pixels per warp-row: 32 lanes x 4 pixels
+constexpr int kStripBytes = kStripW * 3;
+constexpr int kBandRows = VIS_Q_BAND;             // rows a warp walks: two halo rows re-read per 72 (1080 = 15 bands)
+constexpr int kAhead = VIS_Q_AHEAD;               // global-load walk: rows in flight per warp (divides 32)
+constexpr int kWarps = 8;                         // compute warps = strips of a CTA; warp 8 is the producer
+constexpr int kThreads = (kWarps + 1) * 32;
+constexpr int kK = VIS_Q_K, kS = VIS_Q_S;         // rows per stage (<= 32), stages of the ring
+constexpr int kPad = 16;                          // halo bytes either side of a staged row (one pixel is used)
+constexpr int kRowPitch = kPad + kWarps * kStripBytes + kPad;
+constexpr int kStageBytes = kK * kRowPitch;
+constexpr int kSmemBytes = kS * kStageBytes;
+static_assert(kK <= 32 && 32 % kAhead == 0, "a lane converts the halo pixels of one row of a stage / of 32 rows");
 
 __device__ __forceinline__ int reflect101(int i, int n) {       // cv: BORDER_REFLECT_101, n >= 1
     if (n == 1) return 0;
@@ -23,109 +59,258 @@ __device__ __forceinline__ int reflect101(int i, int n) {       // cv: BORDER_RE
     return min(max(i, 0), n - 1);
 }
 
-// cv: RGB2Gray<uchar> on a BGR pixel held in the low three bytes of `p`: two packed 16 x 8-bit dot products
-__device__ __forceinline__ unsigned gray_of(unsigned p) {
-    const unsigned acc = __dp2a_hi(9798u, p, 1u << 14);                    // R * 9798 (+ 0 * byte 3) + rounding
-    return __dp2a_lo(3735u | (19235u << 16), p, acc) >> 15;                // + B * 3735 + G * 19235
-}
-__device__ __forceinline__ unsigned gray_bytes(const unsigned char* p) {
-    return gray_of((unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16));
+// cv: RGB2Gray<uchar> with the weights doubled: gray = byte 2 of (2*3735*B + 2*19235*G + 2*9798*R + 2^15), byte 3 = 0
+constexpr unsigned kWB = 2 * 3735, kWG = 2 * 19235, kWR = 2 * 9798, kRound = 1u << 15;
+constexpr unsigned kW_BG = kWB | (kWG << 16), kW_R0 = kWR, kW_0B = kWB << 16, kW_GR = kWG | (kWR << 16);
+
+__device__ __forceinline__ unsigned gray2(unsigned b, unsigned g, unsigned r) { return kWB * b + kWG * g + kWR * r + kRound; }
+__device__ __forceinline__ unsigned gray2_bytes(const unsigned char* p) { return gray2(p[0], p[1], p[2]); }
+
+struct Row { unsigned e, o; };                    // gray of pixels (0, 2) and (1, 3) of the lane, 16-bit lanes
+
+// three aligned words = four BGR pixels -> the two packed gray lanes: 8 IDP.2A + 2 PRMT
+__device__ __forceinline__ Row gray_row(unsigned a, unsigned b, unsigned c) {
+    const unsigned p0 = __dp2a_hi(kW_R0, a, __dp2a_lo(kW_BG, a, kRound));            // B G R .
+    const unsigned p1 = __dp2a_lo(kW_GR, b, __dp2a_hi(kW_0B, a, kRound));            // . . . B | G R
+    const unsigned p2 = __dp2a_lo(kW_R0, c, __dp2a_hi(kW_BG, b, kRound));            // . . B G | R
+    const unsigned p3 = __dp2a_hi(kW_GR, c, __dp2a_lo(kW_0B, c, kRound));            // . B G R
+    return Row{__byte_perm(p0, p2, 0x7632), __byte_perm(p1, p3, 0x7632)};
 }
 
-// Phase 1 converts the tile and its one-pixel halo to gray, packed four pixels per 32-bit word (tile column 4q .. 4q+3
-// in word q + 1 of its row; the halos are the last byte of word 0 and the first byte of word 33).  Phase 2 works on
-// whole words: the left / right neighbours come from funnel shifts, the four Laplacians of a word are evaluated in two
-// packed 16-bit lanes (biased by 1024 so that no borrow crosses a lane), and the three sums stay in 32-bit registers
-// until the warp reduction (|lap| <= 1020).
-__global__ void __launch_bounds__(kThreads)
-k_quality(const VisQualityFrame* __restrict__ frames, long long* __restrict__ sums) {
-    __shared__ unsigned g[kTH + 2][kRowWords];
-    __shared__ long long red[3][kThreads / 32];
-    // the frame index is the FASTEST grid dimension: the CTAs resident at any moment belong to many frames, so their
-    // final atomicAdds land on different sums (510 CTAs of one 1080p frame adding to one 24-byte record serialise in L2)
-    const VisQualityFrame f = frames[blockIdx.x];
-    const int x0 = blockIdx.y * kTW;
-    if (x0 >= f.w || (int)blockIdx.z * kTilesPerCta * kTH >= f.h) return;
-    const int tid = threadIdx.x;
-    int sg = 0, sl = 0, sl2 = 0;                  // a thread sees <= 128 pixels: sum(lap^2) < 2^27
-    for (int t = 0; t < kTilesPerCta; ++t) {
-    const int y0 = ((int)blockIdx.z * kTilesPerCta + t) * kTH;
-    if (y0 >= f.h) break;                         // uniform
-    if (t) __syncthreads();                       // the previous tile's words are consumed
-    const bool fast = ((f.pitch | (int64_t)(uintptr_t)f.src) & 3) == 0 && x0 + kTW <= f.w;
-    if (fast) {                                   // interior columns: 4 pixels = three aligned 32-bit loads per thread
-        for (int i = tid; i < (kTH + 2) * (kTW / 4); i += kThreads) {
-            const int r = i / (kTW / 4), q = i - r * (kTW / 4);
-            const int y = reflect101(y0 + r - 1, f.h);
-            const uint32_t* p = reinterpret_cast<const uint32_t*>(f.src + (size_t)y * f.pitch + (size_t)(x0 + 4 * q) * 3);
-            const uint32_t a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
-            const unsigned g0 = gray_of(a), g1 = gray_of(__byte_perm(a, b, 0x0543));
-            const unsigned g2 = gray_of(__byte_perm(b, d, 0x0432)), g3 = gray_of(d >> 8);
-            g[r][1 + q] = __byte_perm(__byte_perm(g0, g1, 0x0040), __byte_perm(g2, g3, 0x0040), 0x5410);
-        }
-        for (int i = tid; i < (kTH + 2) * 2; i += kThreads) {      // the two halo columns
-            const int r = i >> 1, right = i & 1;
-            const int y = reflect101(y0 + r - 1, f.h), x = reflect101(right ? x0 + kTW : x0 - 1, f.w);
-            const unsigned v = gray_bytes(f.src + (size_t)y * f.pitch + (size_t)x * 3);
-            g[r][right ? kRowWords - 1 : 0] = right ? v : v << 24;
-        }
-    } else {                                      // edge tiles / unaligned frames: byte by byte (indices reflected)
-        unsigned char* gb = reinterpret_cast<unsigned char*>(&g[0][0]);
-        for (int i = tid; i < (kTH + 2) * (kTW + 2); i += kThreads) {
-            const int r = i / (kTW + 2), c = i - r * (kTW + 2);                 // c = 0 is the left halo
-            const int y = reflect101(y0 + r - 1, f.h), x = reflect101(x0 + c - 1, f.w);
-            gb[r * kRowWords * 4 + 3 + c] = (unsigned char)gray_bytes(f.src + (size_t)y * f.pitch + (size_t)x * 3);
-        }
+// one row of the walk: the Laplacians of the lane's four pixels from the gray rows above / at / below, accumulated biased
+struct Acc { unsigned sg, sv, sv2; };
+__device__ __forceinline__ void lap_row(const Row& up, const Row& own, const Row& down, unsigned gl, unsigned gr, int lane,
+                                        unsigned me, unsigned mo, bool masked, Acc& a) {
+    unsigned o_prev = __shfl_up_sync(0xffffffffu, own.o, 1), e_next = __shfl_down_sync(0xffffffffu, own.e, 1);
+    if (lane == 0) o_prev = gl;                                           // the strip's halo columns
+    if (lane == 31) e_next = gr;
+    const unsigned left_e = __byte_perm(o_prev, own.o, 0x5432);           // (pixel -1, pixel 1)
+    const unsigned right_o = __byte_perm(own.e, e_next, 0x5432);          // (pixel 2, pixel 4)
+    unsigned le = up.e + down.e + left_e + own.o + 0x04000400u - 4u * own.e;           // lap + 1024 per 16-bit lane
+    unsigned lo = up.o + down.o + own.e + right_o + 0x04000400u - 4u * own.o;
+    unsigned ge = own.e, go = own.o;
+    if (masked) { le &= me; lo &= mo; ge &= me; go &= mo; }
+    const unsigned v0 = le & 0xffffu, v2 = le >> 16, v1 = lo & 0xffffu, v3 = lo >> 16;
+    a.sv2 += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
+    a.sv = __dp2a_lo(le, 0x0101u, __dp2a_lo(lo, 0x0101u, a.sv));
+    a.sg = __dp2a_lo(ge, 0x0101u, __dp2a_lo(go, 0x0101u, a.sg));
+}
+
+// a halo pixel's doubled accumulator -> the lane position lap_row() wants (left: high lane, right: low lane)
+__device__ __forceinline__ unsigned halo_left(unsigned g2) { return g2 & 0x00ff0000u; }
+__device__ __forceinline__ unsigned halo_right(unsigned g2) { return (g2 >> 16) & 0xffu; }
+
+// the strip's halo columns of 32 rows: lane r converts row yg + r
+__device__ __forceinline__ void halo_columns(const VisQualityFrame& f, int yg, int lane, int xl, int xr, unsigned& hl, unsigned& hr) {
+    const unsigned char* row = f.src + (size_t)min(yg + lane, f.h - 1) * f.pitch;
+    hl = halo_left(gray2_bytes(row + (size_t)xl * 3));
+    hr = halo_right(gray2_bytes(row + (size_t)xr * 3));
+}
+
+__device__ __forceinline__ void finish_band(const Acc& a, long long n, long long& out_g, long long& out_l, long long& out_l2) {
+    out_g = a.sg;                                 // per lane and band: sum v^2 <= 2044^2 * 4 * 72 < 2^32
+    out_l = (long long)a.sv - 1024 * n;
+    out_l2 = (long long)a.sv2 - 2048ll * a.sv + 1048576ll * n;
+}
+
+// ---- the staged walk: rows come from the CTA's ring ------------------------------------------------------------------
+// Sequence row i of a band is frame row reflect101(yb - 1 + i): i = 0 is the row above the band, i = rows + 1 the row
+// below it; stage st of the ring holds sequence rows st*kK .. st*kK + kK - 1.
+struct Ring { uint32_t data, full, empty; };      // shared-space addresses: stages, kS full barriers, kS empty barriers
+
+__device__ __forceinline__ void produce_band(const VisQualityFrame& f, const Ring& ring, int yb, int ye, int x0c, int n_ring) {
+    const int x_end = x0c + n_ring * kStripW;
+    const bool has_left = x0c > 0, has_right = x_end < f.w;               // (then >= 6 more pixels: see ring_strip())
+    const uint32_t bytes = (has_left ? kPad : 0) + n_ring * kStripBytes + (has_right ? kPad : 0);
+    const unsigned char* col = f.src + (size_t)x0c * 3 - (has_left ? kPad : 0);
+    const uint32_t dst0 = ring.data + (has_left ? 0 : kPad);
+    const int n_seq = ye - yb + 2;
+    for (int st = 0, i0 = 0; i0 < n_seq; ++st, i0 += kK) {
+        const int slot = st % kS, cnt = min(kK, n_seq - i0);
+        if (st >= kS) mbar_wait(ring.empty + 8 * slot, ((st / kS) - 1) & 1);
+        mbar_expect_tx(ring.full + 8 * slot, cnt * bytes);
+        for (int j = 0; j < cnt; ++j)
+            bulk_g2s(dst0 + slot * kStageBytes + j * kRowPitch, col + (size_t)reflect101(yb - 1 + i0 + j, f.h) * f.pitch, bytes,
+                     ring.full + 8 * slot);
     }
-    __syncthreads();
-    const int q = tid & 31, rb = (tid >> 5) * 4;                              // word column, first of 4 consecutive rows
-    const int vx = min(4, f.w - (x0 + 4 * q));                                // valid pixels of this word (<= 0: none)
-    if (vx > 0) {
-        unsigned up = g[rb][q + 1], own = g[rb + 1][q + 1];
+}
+
+__device__ __forceinline__ void walk_band_ring(const VisQualityFrame& f, const Ring& ring, int warp, int x0, int yb, int ye, int lane,
+                                               long long& out_g, long long& out_l, long long& out_l2) {
+    const uint32_t lane_off = kPad + warp * kStripBytes + lane * 12;
+    // the halo pixels, as byte offsets in a staged row: pixel x0 - 1 / x0 + 128, reflected at the frame's edges
+    const uint32_t off_l = kPad + warp * kStripBytes + (x0 > 0 ? -3 : 3);
+    const uint32_t off_r = kPad + warp * kStripBytes + (x0 + kStripW < f.w ? kStripBytes : kStripBytes - 6);
+    const int n_seq = ye - yb + 2;
+    Row up{0, 0}, own{0, 0};
+    Acc acc{0, 0, 0};
+    unsigned hl_prev = 0, hr_prev = 0, hl = 0, hr = 0;
+    for (int st = 0, i0 = 0; i0 < n_seq; ++st, i0 += kK) {
+        const int slot = st % kS, cnt = min(kK, n_seq - i0);
+        const uint32_t base = ring.data + slot * kStageBytes;
+        mbar_wait(ring.full + 8 * slot, (st / kS) & 1);
+        hl_prev = hl; hr_prev = hr;
+        {                                         // lane j converts the halo pixels of row j of the stage
+            const uint32_t row = base + min(lane, cnt - 1) * kRowPitch;
+            unsigned b0, b1, b2, c0, c1, c2;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b0) : "r"(row + off_l));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b1) : "r"(row + off_l + 1));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b2) : "r"(row + off_l + 2));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c0) : "r"(row + off_r));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c1) : "r"(row + off_r + 1));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c2) : "r"(row + off_r + 2));
+            hl = halo_left(gray2(b0, b1, b2));
+            hr = halo_right(gray2(c0, c1, c2));
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int r = rb + k;
-            const unsigned down = g[r + 2][q + 1], prev = g[r + 1][q], next = g[r + 1][q + 2];
-            if (y0 + r < f.h) {
-                const unsigned left = __funnelshift_l(prev, own, 8), right = __funnelshift_r(own, next, 8);
-                // even (0, 2) and odd (1, 3) pixels of the word in 16-bit lanes
-                const unsigned oe = own & 0x00ff00ffu, oo = (own >> 8) & 0x00ff00ffu;
-                const unsigned se = (up & 0x00ff00ffu) + (down & 0x00ff00ffu) + (left & 0x00ff00ffu) + (right & 0x00ff00ffu);
-                const unsigned so = ((up >> 8) & 0x00ff00ffu) + ((down >> 8) & 0x00ff00ffu) + ((left >> 8) & 0x00ff00ffu) +
-                                    ((right >> 8) & 0x00ff00ffu);
-                const unsigned le = se + 0x04000400u - 4u * oe, lo = so + 0x04000400u - 4u * oo;   // lap + 1024 per lane
-                const int l0 = (int)(le & 0xffffu) - 1024, l2 = (int)(le >> 16) - 1024;
-                const int l1 = (int)(lo & 0xffffu) - 1024, l3 = (int)(lo >> 16) - 1024;
-                if (vx == 4) {
-                    sg += (int)__dp4a(own, 0x01010101u, 0u);
-                    sl += l0 + l1 + l2 + l3;
-                    sl2 += l0 * l0 + l1 * l1 + l2 * l2 + l3 * l3;
-                } else {                                                        // the word straddles the right image edge
-                    const int l[4] = {l0, l1, l2, l3};
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        if (j < vx) { sg += (int)((own >> (8 * j)) & 0xffu); sl += l[j]; sl2 += l[j] * l[j]; }
+        for (int j = 0; j < kK; ++j) {
+            if (j < cnt) {                        // uniform
+                const uint32_t p = base + j * kRowPitch + lane_off;
+                const Row down = gray_row(lds32(p), lds32(p + 4), lds32(p + 8));
+                if (i0 + j >= 2) {                // `own` is sequence row i0 + j - 1: row j - 1 of this stage or the last of the previous
+                    const unsigned gl = j ? __shfl_sync(0xffffffffu, hl, j ? j - 1 : 0) : __shfl_sync(0xffffffffu, hl_prev, kK - 1);
+                    const unsigned gr = j ? __shfl_sync(0xffffffffu, hr, j ? j - 1 : 0) : __shfl_sync(0xffffffffu, hr_prev, kK - 1);
+                    lap_row(up, own, down, gl, gr, lane, 0, 0, false, acc);
                 }
+                up = own;
+                own = down;
             }
-            up = own;
-            own = down;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ring.empty + 8 * slot);
+    }
+    finish_band(acc, 4ll * (ye - yb), out_g, out_l, out_l2);
+}
+
+// ---- the same walk on global loads: frames whose rows are only 4-byte aligned ------------------------------------------
+// three aligned 32-bit loads per lane and row, issued kAhead rows before they are converted (a rotating register window)
+__device__ __noinline__ void walk_band_ldg(const VisQualityFrame& f, int x0, int yb, int ye, int lane,
+                                           long long& out_g, long long& out_l, long long& out_l2) {
+    const unsigned char* lane_ptr = f.src + (size_t)(x0 + 4 * lane) * 3;
+    const int xl = reflect101(x0 - 1, f.w), xr = reflect101(x0 + kStripW, f.w);
+    auto row_ptr = [&](int y) { return reinterpret_cast<const uint32_t*>(lane_ptr + (size_t)(y < f.h ? y : reflect101(y, f.h)) * f.pitch); };
+    uint32_t ra[kAhead], rb[kAhead], rc[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {            // rows yb + 1 .. yb + kAhead: the rows below the first kAhead rows
+        const uint32_t* p = row_ptr(min(yb + 1 + k, ye));
+        ra[k] = __ldg(p); rb[k] = __ldg(p + 1); rc[k] = __ldg(p + 2);
+    }
+    Row up, own;
+    {
+        const uint32_t* p = row_ptr(reflect101(yb - 1, f.h));
+        const uint32_t* q = row_ptr(yb);
+        const uint32_t a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), b0 = __ldg(q), b1 = __ldg(q + 1), b2 = __ldg(q + 2);
+        up = gray_row(a0, a1, a2);
+        own = gray_row(b0, b1, b2);
+    }
+    Acc acc{0, 0, 0};
+    unsigned hl = 0, hr = 0;
+    for (int y = yb; y < ye; y += kAhead) {
+        if (((y - yb) & 31) == 0) halo_columns(f, y, lane, xl, xr, hl, hr);            // kAhead divides 32
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) {
+            if (y + k < ye) {                     // uniform
+                const Row down = gray_row(ra[k], rb[k], rc[k]);
+                if (y + k + 1 + kAhead <= ye) {
+                    const uint32_t* p = row_ptr(y + k + 1 + kAhead);
+                    ra[k] = __ldg(p); rb[k] = __ldg(p + 1); rc[k] = __ldg(p + 2);
+                }
+                const int r = (y + k - yb) & 31;
+                lap_row(up, own, down, __shfl_sync(0xffffffffu, hl, r), __shfl_sync(0xffffffffu, hr, r), lane, 0, 0, false, acc);
+                up = own;
+                own = down;
+            }
         }
     }
-    }                                             // tiles of this CTA
-    long long lsg = sg, lsl = sl, lsl2 = sl2;
+    finish_band(acc, 4ll * (ye - yb), out_g, out_l, out_l2);
+}
+
+// ---- edge strips and unaligned frames: byte by byte, columns reflected, the pixels beyond the right edge masked out ----
+__device__ __noinline__ void walk_band_edge(const VisQualityFrame& f, int x0, int yb, int ye, int lane,
+                                            long long& out_g, long long& out_l, long long& out_l2) {
+    const int x = x0 + 4 * lane;
+    const int vx = min(max(f.w - x, 0), 4);                               // valid pixels of this lane's word
+    const unsigned me = (vx > 0 ? 0x0000ffffu : 0u) | (vx > 2 ? 0xffff0000u : 0u);
+    const unsigned mo = (vx > 1 ? 0x0000ffffu : 0u) | (vx > 3 ? 0xffff0000u : 0u);
+    const int xl = reflect101(x0 - 1, f.w), xr = reflect101(x0 + kStripW, f.w);
+    auto load_row = [&](int y) {
+        unsigned g[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lsg += __shfl_down_sync(0xffffffffu, lsg, o);
-        lsl += __shfl_down_sync(0xffffffffu, lsl, o);
-        lsl2 += __shfl_down_sync(0xffffffffu, lsl2, o);
+        for (int j = 0; j < 4; ++j)
+            g[j] = gray2_bytes(f.src + (size_t)y * f.pitch + (size_t)reflect101(x + j, f.w) * 3);
+        return Row{__byte_perm(g[0], g[2], 0x7632), __byte_perm(g[1], g[3], 0x7632)};
+    };
+    Row up = load_row(reflect101(yb - 1, f.h)), own = load_row(yb);
+    Acc acc{0, 0, 0};
+    unsigned hl = 0, hr = 0;
+    for (int y = yb; y < ye; ++y) {
+        const int r = (y - yb) & 31;
+        if (r == 0) halo_columns(f, y, lane, xl, xr, hl, hr);
+        const Row down = load_row(reflect101(y + 1, f.h));
+        lap_row(up, own, down, __shfl_sync(0xffffffffu, hl, r), __shfl_sync(0xffffffffu, hr, r), lane, me, mo, true, acc);
+        up = own;
+        own = down;
     }
-    if ((tid & 31) == 0) { red[0][tid >> 5] = lsg; red[1][tid >> 5] = lsl; red[2][tid >> 5] = lsl2; }
+    finish_band(acc, (long long)vx * (ye - yb), out_g, out_l, out_l2);
+}
+
+// a strip goes through the ring when it is whole and its right halo pixel is either the reflection of one of its own
+// pixels (the strip ends the row) or comes with 16 whole bytes of the same row (>= 6 more pixels)
+__device__ __forceinline__ bool ring_strip(int x0, int w) { return x0 + kStripW == w || x0 + kStripW + 6 <= w; }
+
+__global__ void __launch_bounds__(kThreads, VIS_Q_MINB)
+k_quality(const VisQualityFrame* __restrict__ frames, long long* __restrict__ sums) {
+    extern __shared__ __align__(128) unsigned char q_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * kS];
+    __shared__ long long red[3][kWarps];
+    // the frame index is the FASTEST grid dimension: the CTAs resident at any moment belong to many frames, so their
+    // final atomicAdds land on different sums (the CTAs of one frame adding to one 24-byte record serialise in L2)
+    const int fi = blockIdx.x, cta = blockIdx.y;
+    const VisQualityFrame f = frames[fi];
+    // a band's strips are split into groups of <= 8 adjacent strips, as evenly as possible; a CTA = (band, group)
+    const int strips = (f.w + kStripW - 1) / kStripW, bands = (f.h + kBandRows - 1) / kBandRows;
+    const int groups = (strips + kWarps - 1) / kWarps, per = (strips + groups - 1) / groups;
+    if (cta >= bands * groups) return;            // uniform
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int band = cta / groups, s0 = (cta - band * groups) * per, ns = min(per, strips - s0);
+    const int yb = band * kBandRows, ye = min(yb + kBandRows, f.h);
+    const int align = (int)((f.pitch | (int64_t)(uintptr_t)f.src) & 15);
+    int n_ring = 0;                               // the ring's strips are a prefix of the CTA's (only a row's last strips can fail)
+    if (align == 0)
+        while (n_ring < ns && ring_strip((s0 + n_ring) * kStripW, f.w)) ++n_ring;
+    Ring ring{smem_u32(q_smem), smem_u32(&bars[0]), smem_u32(&bars[kS])};
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kS; ++s) {
+            mbar_init(ring.full + 8 * s, 1);
+            mbar_init(ring.empty + 8 * s, max(n_ring, 1));
+        }
+        fence_mbar_init();
+    }
     __syncthreads();
-    if (tid < 3) {
+    long long sg = 0, sl = 0, sl2 = 0;
+    if (warp == kWarps) {
+        if (n_ring > 0 && lane == 0) produce_band(f, ring, yb, ye, s0 * kStripW, n_ring);
+    } else if (warp < ns) {
+        const int x0 = (s0 + warp) * kStripW;
+        if (warp < n_ring) walk_band_ring(f, ring, warp, x0, yb, ye, lane, sg, sl, sl2);
+        else if ((align & 3) == 0 && x0 + kStripW <= f.w) walk_band_ldg(f, x0, yb, ye, lane, sg, sl, sl2);
+        else walk_band_edge(f, x0, yb, ye, lane, sg, sl, sl2);
+    }
+    if (warp < kWarps) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sg += __shfl_down_sync(0xffffffffu, sg, o);
+            sl += __shfl_down_sync(0xffffffffu, sl, o);
+            sl2 += __shfl_down_sync(0xffffffffu, sl2, o);
+        }
+        if (lane == 0) { red[0][warp] = sg; red[1][warp] = sl; red[2][warp] = sl2; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
         long long t = 0;
 #pragma unroll
-        for (int k = 0; k < kThreads / 32; ++k) t += red[tid][k];
-        atomicAdd(reinterpret_cast<unsigned long long*>(sums + 3 * (size_t)blockIdx.x + tid), (unsigned long long)t);
+        for (int k = 0; k < kWarps; ++k) t += red[threadIdx.x][k];
+        atomicAdd(reinterpret_cast<unsigned long long*>(sums + 3 * (size_t)fi + threadIdx.x), (unsigned long long)t);
     }
 }
 
@@ -137,10 +322,22 @@ extern "C" int vis_quality_stats(const VisQualityFrame* frames, int n_frames, in
         vis::set_error("vis_quality_stats: bad arguments (frames=%d max %dx%d)", n_frames, max_w, max_h);
         return VIS_E_INVALID;
     }
+    const long long strips = (max_w + kStripW - 1) / kStripW, bands = (max_h + kBandRows - 1) / kBandRows;
+    const long long ctas = bands * ((strips + kWarps - 1) / kWarps);
+    if (ctas > 65535) {
+        vis::set_error("vis_quality_stats: frames of %dx%d are beyond the grid (%lld CTAs per frame)", max_w, max_h, ctas);
+        return VIS_E_UNSUPPORTED;
+    }
+    static bool attr_set = false;                 // idempotent; a race sets it twice
+    if (!attr_set) {
+        cudaError_t ea = cudaFuncSetAttribute(k_quality, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (ea != cudaSuccess) return vis::cuda_fail(ea, "vis_quality_stats: cudaFuncSetAttribute");
+        attr_set = true;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(int64_t) * 3 * (size_t)n_frames, st);
     if (e != cudaSuccess) return vis::cuda_fail(e, "vis_quality_stats: cudaMemsetAsync");
-    dim3 grid(n_frames, (max_w + kTW - 1) / kTW, (max_h + kTH * kTilesPerCta - 1) / (kTH * kTilesPerCta));
-    k_quality<<<grid, kThreads, 0, st>>>(frames, reinterpret_cast<long long*>(sums));
+    dim3 grid(n_frames, (unsigned)ctas);
+    k_quality<<<grid, kThreads, kSmemBytes, st>>>(frames, reinterpret_cast<long long*>(sums));
     return vis::check_launch("vis_quality_stats");
 }
