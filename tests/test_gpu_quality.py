@@ -19,10 +19,14 @@ sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
 
 def test_sums_are_exact(engine):
     rng = np.random.default_rng(3)
-    shapes = [(1080, 1920), (480, 640), (333, 517), (1, 1), (1, 9), (9, 1), (2, 2), (17, 129), (16, 128), (2160, 3840)]
+    # whole strips through the bulk-copy ring (16-byte aligned rows), rows that are only 4-byte aligned, byte-aligned rows,
+    # partial last strips with >= 6 / < 6 pixels (the right halo of the last ring strip), one-row / one-column frames
+    shapes = [(1080, 1920), (480, 640), (333, 517), (1, 1), (1, 9), (9, 1), (2, 2), (17, 129), (16, 128), (2160, 3840),
+              (1, 128), (3, 256), (36, 256), (37, 256), (75, 2048), (100, 1152), (100, 1030), (40, 1157), (40, 1158), (181, 133),
+              (200, 132), (500, 3), (64, 127), (19, 40)]
     frames = [rng.integers(0, 256, s + (3,), dtype=np.uint8) for s in shapes]
     sums, got_shapes = engine.quality_stats([torch.from_numpy(f).cuda() for f in frames])
-    assert got_shapes == shapes and engine.last_launches == 1
+    assert got_shapes == shapes and engine.last_launches == 2
     host = sums.cpu().numpy()
     for i, f in enumerate(frames):
         assert tuple(int(v) for v in host[i]) == Q.stats(f), shapes[i]

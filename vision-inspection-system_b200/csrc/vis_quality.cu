@@ -4,7 +4,7 @@
 //   cv2.cvtColor(BGR2GRAY)            -> gray = (3735*B + 19235*G + 9798*R + 2^14) >> 15   (cv: RGB2Gray<uchar>, 15-bit)
 //   cv2.Laplacian(gray, CV_64F).var() -> 3x3 kernel [0 1 0; 1 -4 1; 0 1 0], BORDER_REFLECT_101; integer valued
 //   np.mean(gray)
-// One pass over the BGR frame.  A CTA owns up to eight adjacent 128-pixel strips of a 72-row band; a producer warp
+// One pass over the BGR frame.  A CTA owns up to eight adjacent 128-pixel strips of a band of rows (18 .. 180, by batch size); a producer warp
 // streams the band's rows (one cp.async.bulk of up to 3 KB per row, plus 16 bytes of halo either side) through a ring
 // of shared-memory stages guarded by mbarriers, so the bytes in flight do not depend on what the compute warps are
 // doing.  A compute WARP owns one strip and walks down it; a lane owns four pixels (12 bytes = three words, read
@@ -25,23 +25,23 @@ namespace {
 using namespace visf;
 
 #ifndef VIS_Q_BAND
-#define VIS_Q_BAND 72
+#define VIS_Q_BAND 0                              // > 0: a fixed band height instead of the host's choice (A/B builds)
 #endif
 #ifndef VIS_Q_AHEAD
 #define VIS_Q_AHEAD 4
 #endif
 #ifndef VIS_Q_MINB
-#define VIS_Q_MINB 3
+#define VIS_Q_MINB 4
 #endif
 #ifndef VIS_Q_K
 #define VIS_Q_K 8
 #endif
 #ifndef VIS_Q_S
-#define VIS_Q_S 3
+#define VIS_Q_S 2
 #endif
 constexpr int kStripW = 128;                      // pixels per warp-row: 32 lanes x 4 pixels
 constexpr int kStripBytes = kStripW * 3;
-constexpr int kBandRows = VIS_Q_BAND;             // rows a warp walks: two halo rows re-read per 72 (1080 = 15 bands)
+constexpr int kMaxBandRows = 256;                 // rows a warp walks, chosen per launch: sum v^2 <= 2044^2 * 4 * 256 < 2^32
 constexpr int kAhead = VIS_Q_AHEAD;               // global-load walk: rows in flight per warp (divides 32)
 constexpr int kWarps = 8;                         // compute warps = strips of a CTA; warp 8 is the producer
 constexpr int kThreads = (kWarps + 1) * 32;
@@ -50,7 +50,7 @@ constexpr int kPad = 16;                          // halo bytes either side of a
 constexpr int kRowPitch = kPad + kWarps * kStripBytes + kPad;
 constexpr int kStageBytes = kK * kRowPitch;
 constexpr int kSmemBytes = kS * kStageBytes;
-static_assert(kK <= 32 && 32 % kAhead == 0, "a lane converts the halo pixels of one row of a stage / of 32 rows");
+static_assert(kK <= 16 && kAhead <= 16 && 32 % kAhead == 0, "a lane converts the halo pixels of one row of a stage / of 32 rows");
 
 __device__ __forceinline__ int reflect101(int i, int n) {       // cv: BORDER_REFLECT_101, n >= 1
     if (n == 1) return 0;
@@ -78,7 +78,14 @@ __device__ __forceinline__ Row gray_row(unsigned a, unsigned b, unsigned c) {
 }
 
 // one row of the walk: the Laplacians of the lane's four pixels from the gray rows above / at / below, accumulated biased
-struct Acc { unsigned sg, sv, sv2; };
+// sums per lane and band: gray and v = lap + 1024 first in packed 16-bit lanes (pg, pv: flushed every <= 16 rows), v^2 as
+// v * (v & 255) and v * (v >> 8) (two IDP.2A on the packed lanes against their own bytes; <= 2044 * 255 * 4 * 256 < 2^32)
+struct Acc { unsigned pg, pv, sg, sv, qa, qb; };
+__device__ __forceinline__ void flush(Acc& a) {
+    a.sg += (a.pg & 0xffffu) + (a.pg >> 16);
+    a.sv += (a.pv & 0xffffu) + (a.pv >> 16);
+    a.pg = a.pv = 0;
+}
 __device__ __forceinline__ void lap_row(const Row& up, const Row& own, const Row& down, unsigned gl, unsigned gr, int lane,
                                         unsigned me, unsigned mo, bool masked, Acc& a) {
     unsigned o_prev = __shfl_up_sync(0xffffffffu, own.o, 1), e_next = __shfl_down_sync(0xffffffffu, own.e, 1);
@@ -90,10 +97,11 @@ __device__ __forceinline__ void lap_row(const Row& up, const Row& own, const Row
     unsigned lo = up.o + down.o + own.e + right_o + 0x04000400u - 4u * own.o;
     unsigned ge = own.e, go = own.o;
     if (masked) { le &= me; lo &= mo; ge &= me; go &= mo; }
-    const unsigned v0 = le & 0xffffu, v2 = le >> 16, v1 = lo & 0xffffu, v3 = lo >> 16;
-    a.sv2 += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
-    a.sv = __dp2a_lo(le, 0x0101u, __dp2a_lo(lo, 0x0101u, a.sv));
-    a.sg = __dp2a_lo(ge, 0x0101u, __dp2a_lo(go, 0x0101u, a.sg));
+    a.pg += ge + go;                                                      // <= 510 per lane and row
+    a.pv += le + lo;                                                      // <= 4088 per lane and row
+    const unsigned be = __byte_perm(le, 0, 0x3120), bo = __byte_perm(lo, 0, 0x3120);   // (low bytes | high bytes) of the two lanes
+    a.qa = __dp2a_lo(le, be, __dp2a_lo(lo, bo, a.qa));
+    a.qb = __dp2a_hi(le, be, __dp2a_hi(lo, bo, a.qb));
 }
 
 // a halo pixel's doubled accumulator -> the lane position lap_row() wants (left: high lane, right: low lane)
@@ -108,9 +116,9 @@ __device__ __forceinline__ void halo_columns(const VisQualityFrame& f, int yg, i
 }
 
 __device__ __forceinline__ void finish_band(const Acc& a, long long n, long long& out_g, long long& out_l, long long& out_l2) {
-    out_g = a.sg;                                 // per lane and band: sum v^2 <= 2044^2 * 4 * 72 < 2^32
+    out_g = a.sg;
     out_l = (long long)a.sv - 1024 * n;
-    out_l2 = (long long)a.sv2 - 2048ll * a.sv + 1048576ll * n;
+    out_l2 = (long long)a.qa + 256ll * a.qb - 2048ll * a.sv + 1048576ll * n;
 }
 
 // ---- the staged walk: rows come from the CTA's ring ------------------------------------------------------------------
@@ -135,6 +143,39 @@ __device__ __forceinline__ void produce_band(const VisQualityFrame& f, const Rin
     }
 }
 
+// one stage of the ring: FIRST = the band's first stage (its first two rows only fill `up` and `own`), FULL = all kK rows
+template <bool FIRST, bool FULL>
+__device__ __forceinline__ void walk_stage(uint32_t base, uint32_t lane_off, uint32_t off_l, uint32_t off_r, int cnt, int lane,
+                                           Row& up, Row& own, unsigned& hl, unsigned& hr, Acc& acc) {
+    const unsigned hl_prev = hl, hr_prev = hr;
+    {                                             // lane j converts the halo pixels of row j of the stage
+        const uint32_t row = base + (FULL ? min(lane, kK - 1) : min(lane, cnt - 1)) * kRowPitch;
+        unsigned b0, b1, b2, c0, c1, c2;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b0) : "r"(row + off_l));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b1) : "r"(row + off_l + 1));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b2) : "r"(row + off_l + 2));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c0) : "r"(row + off_r));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c1) : "r"(row + off_r + 1));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c2) : "r"(row + off_r + 2));
+        hl = halo_left(gray2(b0, b1, b2));
+        hr = halo_right(gray2(c0, c1, c2));
+    }
+#pragma unroll
+    for (int j = 0; j < kK; ++j) {
+        if (FULL || j < cnt) {                    // uniform
+            const uint32_t p = base + j * kRowPitch + lane_off;
+            const Row down = gray_row(lds32(p), lds32(p + 4), lds32(p + 8));
+            if (!FIRST || j >= 2) {               // `own` is row j - 1 of this stage, or the last row of the previous one
+                const unsigned gl = j ? __shfl_sync(0xffffffffu, hl, j ? j - 1 : 0) : __shfl_sync(0xffffffffu, hl_prev, kK - 1);
+                const unsigned gr = j ? __shfl_sync(0xffffffffu, hr, j ? j - 1 : 0) : __shfl_sync(0xffffffffu, hr_prev, kK - 1);
+                lap_row(up, own, down, gl, gr, lane, 0, 0, false, acc);
+            }
+            up = own;
+            own = down;
+        }
+    }
+}
+
 __device__ __forceinline__ void walk_band_ring(const VisQualityFrame& f, const Ring& ring, int warp, int x0, int yb, int ye, int lane,
                                                long long& out_g, long long& out_l, long long& out_l2) {
     const uint32_t lane_off = kPad + warp * kStripBytes + lane * 12;
@@ -143,39 +184,16 @@ __device__ __forceinline__ void walk_band_ring(const VisQualityFrame& f, const R
     const uint32_t off_r = kPad + warp * kStripBytes + (x0 + kStripW < f.w ? kStripBytes : kStripBytes - 6);
     const int n_seq = ye - yb + 2;
     Row up{0, 0}, own{0, 0};
-    Acc acc{0, 0, 0};
-    unsigned hl_prev = 0, hr_prev = 0, hl = 0, hr = 0;
+    Acc acc{0, 0, 0, 0, 0, 0};
+    unsigned hl = 0, hr = 0;
     for (int st = 0, i0 = 0; i0 < n_seq; ++st, i0 += kK) {
         const int slot = st % kS, cnt = min(kK, n_seq - i0);
         const uint32_t base = ring.data + slot * kStageBytes;
         mbar_wait(ring.full + 8 * slot, (st / kS) & 1);
-        hl_prev = hl; hr_prev = hr;
-        {                                         // lane j converts the halo pixels of row j of the stage
-            const uint32_t row = base + min(lane, cnt - 1) * kRowPitch;
-            unsigned b0, b1, b2, c0, c1, c2;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b0) : "r"(row + off_l));
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b1) : "r"(row + off_l + 1));
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b2) : "r"(row + off_l + 2));
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c0) : "r"(row + off_r));
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c1) : "r"(row + off_r + 1));
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c2) : "r"(row + off_r + 2));
-            hl = halo_left(gray2(b0, b1, b2));
-            hr = halo_right(gray2(c0, c1, c2));
-        }
-#pragma unroll
-        for (int j = 0; j < kK; ++j) {
-            if (j < cnt) {                        // uniform
-                const uint32_t p = base + j * kRowPitch + lane_off;
-                const Row down = gray_row(lds32(p), lds32(p + 4), lds32(p + 8));
-                if (i0 + j >= 2) {                // `own` is sequence row i0 + j - 1: row j - 1 of this stage or the last of the previous
-                    const unsigned gl = j ? __shfl_sync(0xffffffffu, hl, j ? j - 1 : 0) : __shfl_sync(0xffffffffu, hl_prev, kK - 1);
-                    const unsigned gr = j ? __shfl_sync(0xffffffffu, hr, j ? j - 1 : 0) : __shfl_sync(0xffffffffu, hr_prev, kK - 1);
-                    lap_row(up, own, down, gl, gr, lane, 0, 0, false, acc);
-                }
-                up = own;
-                own = down;
-            }
-        }
+        if (st == 0) walk_stage<true, false>(base, lane_off, off_l, off_r, cnt, lane, up, own, hl, hr, acc);
+        else if (cnt == kK) walk_stage<false, true>(base, lane_off, off_l, off_r, cnt, lane, up, own, hl, hr, acc);
+        else walk_stage<false, false>(base, lane_off, off_l, off_r, cnt, lane, up, own, hl, hr, acc);
+        flush(acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(ring.empty + 8 * slot);
     }
@@ -184,7 +202,7 @@ __device__ __forceinline__ void walk_band_ring(const VisQualityFrame& f, const R
 
 // ---- the same walk on global loads: frames whose rows are only 4-byte aligned ------------------------------------------
 // three aligned 32-bit loads per lane and row, issued kAhead rows before they are converted (a rotating register window)
-__device__ __noinline__ void walk_band_ldg(const VisQualityFrame& f, int x0, int yb, int ye, int lane,
+__device__ __forceinline__ void walk_band_ldg(const VisQualityFrame& f, int x0, int yb, int ye, int lane,
                                            long long& out_g, long long& out_l, long long& out_l2) {
     const unsigned char* lane_ptr = f.src + (size_t)(x0 + 4 * lane) * 3;
     const int xl = reflect101(x0 - 1, f.w), xr = reflect101(x0 + kStripW, f.w);
@@ -203,7 +221,7 @@ __device__ __noinline__ void walk_band_ldg(const VisQualityFrame& f, int x0, int
         up = gray_row(a0, a1, a2);
         own = gray_row(b0, b1, b2);
     }
-    Acc acc{0, 0, 0};
+    Acc acc{0, 0, 0, 0, 0, 0};
     unsigned hl = 0, hr = 0;
     for (int y = yb; y < ye; y += kAhead) {
         if (((y - yb) & 31) == 0) halo_columns(f, y, lane, xl, xr, hl, hr);            // kAhead divides 32
@@ -221,12 +239,13 @@ __device__ __noinline__ void walk_band_ldg(const VisQualityFrame& f, int x0, int
                 own = down;
             }
         }
+        flush(acc);
     }
     finish_band(acc, 4ll * (ye - yb), out_g, out_l, out_l2);
 }
 
 // ---- edge strips and unaligned frames: byte by byte, columns reflected, the pixels beyond the right edge masked out ----
-__device__ __noinline__ void walk_band_edge(const VisQualityFrame& f, int x0, int yb, int ye, int lane,
+__device__ __forceinline__ void walk_band_edge(const VisQualityFrame& f, int x0, int yb, int ye, int lane,
                                             long long& out_g, long long& out_l, long long& out_l2) {
     const int x = x0 + 4 * lane;
     const int vx = min(max(f.w - x, 0), 4);                               // valid pixels of this lane's word
@@ -241,13 +260,14 @@ __device__ __noinline__ void walk_band_edge(const VisQualityFrame& f, int x0, in
         return Row{__byte_perm(g[0], g[2], 0x7632), __byte_perm(g[1], g[3], 0x7632)};
     };
     Row up = load_row(reflect101(yb - 1, f.h)), own = load_row(yb);
-    Acc acc{0, 0, 0};
+    Acc acc{0, 0, 0, 0, 0, 0};
     unsigned hl = 0, hr = 0;
     for (int y = yb; y < ye; ++y) {
         const int r = (y - yb) & 31;
         if (r == 0) halo_columns(f, y, lane, xl, xr, hl, hr);
         const Row down = load_row(reflect101(y + 1, f.h));
         lap_row(up, own, down, __shfl_sync(0xffffffffu, hl, r), __shfl_sync(0xffffffffu, hr, r), lane, me, mo, true, acc);
+        flush(acc);
         up = own;
         own = down;
     }
@@ -258,44 +278,30 @@ __device__ __noinline__ void walk_band_edge(const VisQualityFrame& f, int x0, in
 // pixels (the strip ends the row) or comes with 16 whole bytes of the same row (>= 6 more pixels)
 __device__ __forceinline__ bool ring_strip(int x0, int w) { return x0 + kStripW == w || x0 + kStripW + 6 <= w; }
 
-__global__ void __launch_bounds__(kThreads, VIS_Q_MINB)
-k_quality(const VisQualityFrame* __restrict__ frames, long long* __restrict__ sums) {
-    extern __shared__ __align__(128) unsigned char q_smem[];
-    __shared__ __align__(8) uint64_t bars[2 * kS];
-    __shared__ long long red[3][kWarps];
-    // the frame index is the FASTEST grid dimension: the CTAs resident at any moment belong to many frames, so their
-    // final atomicAdds land on different sums (the CTAs of one frame adding to one 24-byte record serialise in L2)
-    const int fi = blockIdx.x, cta = blockIdx.y;
-    const VisQualityFrame f = frames[fi];
-    // a band's strips are split into groups of <= 8 adjacent strips, as evenly as possible; a CTA = (band, group)
-    const int strips = (f.w + kStripW - 1) / kStripW, bands = (f.h + kBandRows - 1) / kBandRows;
+// A CTA = (band, group): a band's strips are split into groups of <= 8 adjacent strips, as evenly as possible.  The first
+// n_ring strips of the group go through the ring (k_quality_ring), the others (a row's last strips, unaligned frames)
+// through k_quality_rest: two kernels, so that neither carries the other's code.
+struct Task { int ns, n_ring, s0, yb, ye, align; bool valid; };
+__device__ __forceinline__ Task task_of(const VisQualityFrame& f, int cta, int band_rows) {
+    Task t{};
+    const int strips = (f.w + kStripW - 1) / kStripW, bands = (f.h + band_rows - 1) / band_rows;
     const int groups = (strips + kWarps - 1) / kWarps, per = (strips + groups - 1) / groups;
-    if (cta >= bands * groups) return;            // uniform
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int band = cta / groups, s0 = (cta - band * groups) * per, ns = min(per, strips - s0);
-    const int yb = band * kBandRows, ye = min(yb + kBandRows, f.h);
-    const int align = (int)((f.pitch | (int64_t)(uintptr_t)f.src) & 15);
-    int n_ring = 0;                               // the ring's strips are a prefix of the CTA's (only a row's last strips can fail)
-    if (align == 0)
-        while (n_ring < ns && ring_strip((s0 + n_ring) * kStripW, f.w)) ++n_ring;
-    Ring ring{smem_u32(q_smem), smem_u32(&bars[0]), smem_u32(&bars[kS])};
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kS; ++s) {
-            mbar_init(ring.full + 8 * s, 1);
-            mbar_init(ring.empty + 8 * s, max(n_ring, 1));
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    long long sg = 0, sl = 0, sl2 = 0;
-    if (warp == kWarps) {
-        if (n_ring > 0 && lane == 0) produce_band(f, ring, yb, ye, s0 * kStripW, n_ring);
-    } else if (warp < ns) {
-        const int x0 = (s0 + warp) * kStripW;
-        if (warp < n_ring) walk_band_ring(f, ring, warp, x0, yb, ye, lane, sg, sl, sl2);
-        else if ((align & 3) == 0 && x0 + kStripW <= f.w) walk_band_ldg(f, x0, yb, ye, lane, sg, sl, sl2);
-        else walk_band_edge(f, x0, yb, ye, lane, sg, sl, sl2);
-    }
+    t.valid = cta < bands * groups;
+    if (!t.valid) return t;
+    const int band = cta / groups;
+    t.s0 = (cta - band * groups) * per;
+    t.ns = min(per, strips - t.s0);
+    t.yb = band * band_rows;
+    t.ye = min(t.yb + band_rows, f.h);
+    t.align = (int)((f.pitch | (int64_t)(uintptr_t)f.src) & 15);
+    if (t.align == 0)                             // the ring's strips are a prefix of the group's (only a row's last strips can fail)
+        while (t.n_ring < t.ns && ring_strip((t.s0 + t.n_ring) * kStripW, f.w)) ++t.n_ring;
+    return t;
+}
+
+// the three sums of the CTA's compute warps -> one atomicAdd triple on the frame's record
+__device__ __forceinline__ void add_sums(long long (*red)[kWarps], int warp, int lane, long long sg, long long sl, long long sl2,
+                                         long long* frame_sums) {
     if (warp < kWarps) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -310,8 +316,55 @@ k_quality(const VisQualityFrame* __restrict__ frames, long long* __restrict__ su
         long long t = 0;
 #pragma unroll
         for (int k = 0; k < kWarps; ++k) t += red[threadIdx.x][k];
-        atomicAdd(reinterpret_cast<unsigned long long*>(sums + 3 * (size_t)fi + threadIdx.x), (unsigned long long)t);
+        atomicAdd(reinterpret_cast<unsigned long long*>(frame_sums + threadIdx.x), (unsigned long long)t);
     }
+}
+
+// The frame index is the FASTEST grid dimension of both kernels: the CTAs resident at any moment belong to many frames,
+// so their final atomicAdds land on different sums (the CTAs of one frame adding to one 24-byte record serialise in L2).
+__global__ void __launch_bounds__(kThreads, VIS_Q_MINB)
+k_quality_ring(const VisQualityFrame* __restrict__ frames, long long* __restrict__ sums, int band_rows) {
+    extern __shared__ __align__(128) unsigned char q_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * kS];
+    __shared__ long long red[3][kWarps];
+    const int fi = blockIdx.x;
+    const VisQualityFrame f = frames[fi];
+    const Task t = task_of(f, blockIdx.y, band_rows);
+    if (!t.valid || t.n_ring == 0) return;        // uniform
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Ring ring{smem_u32(q_smem), smem_u32(&bars[0]), smem_u32(&bars[kS])};
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kS; ++s) {
+            mbar_init(ring.full + 8 * s, 1);
+            mbar_init(ring.empty + 8 * s, t.n_ring);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    long long sg = 0, sl = 0, sl2 = 0;
+    if (warp == kWarps) {
+        if (lane == 0) produce_band(f, ring, t.yb, t.ye, t.s0 * kStripW, t.n_ring);
+    } else if (warp < t.n_ring) {
+        walk_band_ring(f, ring, warp, (t.s0 + warp) * kStripW, t.yb, t.ye, lane, sg, sl, sl2);
+    }
+    add_sums(red, warp, lane, sg, sl, sl2, sums + 3 * (size_t)fi);
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_quality_rest(const VisQualityFrame* __restrict__ frames, long long* __restrict__ sums, int band_rows) {
+    __shared__ long long red[3][kWarps];
+    const int fi = blockIdx.x;
+    const VisQualityFrame f = frames[fi];
+    const Task t = task_of(f, blockIdx.y, band_rows);
+    if (!t.valid || t.n_ring == t.ns) return;     // uniform
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long sg = 0, sl = 0, sl2 = 0;
+    if (warp >= t.n_ring && warp < t.ns) {
+        const int x0 = (t.s0 + warp) * kStripW;
+        if ((t.align & 3) == 0 && x0 + kStripW <= f.w) walk_band_ldg(f, x0, t.yb, t.ye, lane, sg, sl, sl2);
+        else walk_band_edge(f, x0, t.yb, t.ye, lane, sg, sl, sl2);
+    }
+    add_sums(red, warp, lane, sg, sl, sl2, sums + 3 * (size_t)fi);
 }
 
 }  // namespace
@@ -322,15 +375,31 @@ extern "C" int vis_quality_stats(const VisQualityFrame* frames, int n_frames, in
         vis::set_error("vis_quality_stats: bad arguments (frames=%d max %dx%d)", n_frames, max_w, max_h);
         return VIS_E_INVALID;
     }
-    const long long strips = (max_w + kStripW - 1) / kStripW, bands = (max_h + kBandRows - 1) / kBandRows;
-    const long long ctas = bands * ((strips + kWarps - 1) / kWarps);
+    // Band height: tall bands re-read fewer halo rows and fill the ring less often, short ones give a small batch enough
+    // CTAs; the tallest of the list that still yields ~4 CTAs per resident slot (4 per SM), else the shortest.
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const long long strips = (max_w + kStripW - 1) / kStripW, groups = (strips + kWarps - 1) / kWarps;
+    int band_rows = VIS_Q_BAND;
+    if (band_rows <= 0) {
+        static const int kChoices[] = {180, 120, 72, 36, 18};
+        band_rows = kChoices[4];
+        for (int c : kChoices)
+            if ((long long)n_frames * groups * ((max_h + c - 1) / c) >= 4ll * VIS_Q_MINB * sms) { band_rows = c; break; }
+    }
+    static_assert(VIS_Q_BAND <= kMaxBandRows, "band too tall for the 32-bit sums");
+    const long long ctas = groups * ((max_h + band_rows - 1) / band_rows);
     if (ctas > 65535) {
         vis::set_error("vis_quality_stats: frames of %dx%d are beyond the grid (%lld CTAs per frame)", max_w, max_h, ctas);
         return VIS_E_UNSUPPORTED;
     }
     static bool attr_set = false;                 // idempotent; a race sets it twice
     if (!attr_set) {
-        cudaError_t ea = cudaFuncSetAttribute(k_quality, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t ea = cudaFuncSetAttribute(k_quality_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (ea != cudaSuccess) return vis::cuda_fail(ea, "vis_quality_stats: cudaFuncSetAttribute");
         attr_set = true;
     }
@@ -338,6 +407,9 @@ extern "C" int vis_quality_stats(const VisQualityFrame* frames, int n_frames, in
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(int64_t) * 3 * (size_t)n_frames, st);
     if (e != cudaSuccess) return vis::cuda_fail(e, "vis_quality_stats: cudaMemsetAsync");
     dim3 grid(n_frames, (unsigned)ctas);
-    k_quality<<<grid, kThreads, kSmemBytes, st>>>(frames, reinterpret_cast<long long*>(sums));
+    k_quality_ring<<<grid, kThreads, kSmemBytes, st>>>(frames, reinterpret_cast<long long*>(sums), band_rows);
+    cudaError_t el = cudaGetLastError();
+    if (el != cudaSuccess) return vis::cuda_fail(el, "vis_quality_stats: k_quality_ring");
+    k_quality_rest<<<grid, kWarps * 32, 0, st>>>(frames, reinterpret_cast<long long*>(sums), band_rows);
     return vis::check_launch("vis_quality_stats");
 }

@@ -1313,7 +1313,7 @@ class Engine:
     # ------------------------------------------------------------------ image quality statistics
     def quality_stats(self, frames):
         """BGR uint8 HWC CUDA frames (``[B,H,W,3]`` tensor or list) -> (int64 CUDA tensor [B, 3] = sum(gray),
-        sum(laplacian), sum(laplacian^2) per frame, exact; list of (H, W)).  One launch for the batch."""
+        sum(laplacian), sum(laplacian^2) per frame, exact; list of (H, W)).  Two launches for the batch."""
         uniform = isinstance(frames, torch.Tensor) and frames.dim() == 4
         if uniform:                                   # a batch tensor: one check, descriptors by arithmetic
             self._check_u8(frames)
@@ -1350,7 +1350,7 @@ class Engine:
                                              max(s[0] for s in shapes[b0:b0 + n]), max(s[1] for s in shapes[b0:b0 + n]),
                                              sums.data_ptr() + b0 * 24, _stream_ptr()), "vis_quality_stats")
             out.append(n)
-        self.last_launches = len(out)
+        self.last_launches = 2 * len(out)            # the ring kernel and the kernel of the remaining strips
         self._keepalive_q = d_desc
         return sums, shapes
 
