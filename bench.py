@@ -664,6 +664,29 @@ def main():
                                                 "binning in C++, upload) INCLUDED: what one un-planned annotate() call costs"}
         del ofr, work, plan
         torch.cuda.empty_cache()
+
+        # "next" rows of the scope table, on the same footing: image-quality statistics (three exact sums per frame) and
+        # the defect heat map (tolerance-specified), both as ONE batch call on device-resident 1080p BGR frames
+        n_q = 256
+        qfr = torch.from_numpy(synth.frames_1080p(16)).cuda().repeat(n_q // 16, 1, 1, 1).contiguous()
+        configs["quality_stats_1080p"] = leg(lambda: eng.quality_stats(qfr), n_q, n_q * 1080 * 1920 * 3,
+                                             note=f"{n_q} 1080p BGR frames per GPU -> sum(gray), sum(lap), sum(lap^2) per frame, exact int64; "
+                                             "frame descriptors cached for the repeated batch tensor (like the batch plans); bytes = H*W*3 per frame (read only)")
+        del qfr
+        n_h = 64
+        hfr, hdef = [], []
+        for i in range(n_h):
+            rng = np.random.default_rng(8100 + i)
+            hfr.append(torch.from_numpy(rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)).cuda())
+            hdef.append(synth.random_defects(rng, int(rng.integers(1, 7))))
+        hplan = eng.plan_heatmap([(1080, 1920)] * n_h, hdef)
+        rec = leg(lambda: eng.heatmap_batch(hfr, plan=hplan), n_h, n_h * 2 * 1080 * 1920 * 3, warm=3,
+                  note=f"{n_h} 1080p BGR frames per GPU, {sum(len(d) for d in hdef)} defects; analytic heat, two Gaussian blurs per defect and "
+                  "per frame (float32), max-composite, JET blend; per-defect host parameters cached (plan); bytes = 2*H*W*3 per "
+                  "frame; the bound of this leg is the fp32 FMA pipe (<= ~56 k images/s), not HBM")
+        configs["heatmap_overlay_1080p"] = rec
+        del hfr, hplan
+        torch.cuda.empty_cache()
         gpu_launches += sum(int(v.get("launches_per_call", 0)) * int(v.get("reps", 0)) for v in configs.values())
 
     if rank == 0:

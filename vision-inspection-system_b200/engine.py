@@ -1323,9 +1323,13 @@ class Engine:
                 raise ValueError("frames must be [B, H, W, 3] uint8 with contiguous pixels")
             n = int(frames.shape[0])
             shapes = [(int(frames.shape[1]), int(frames.shape[2]))] * n
-            desc = np.zeros(n, N.QUALITY_FRAME_DTYPE)
-            desc["src"] = np.uint64(frames.data_ptr()) + np.arange(n, dtype=np.uint64) * np.uint64(frames.stride(0))
-            desc["pitch"], desc["h"], desc["w"] = frames.stride(1), shapes[0][0], shapes[0][1]
+            key = (frames.data_ptr(), tuple(frames.shape), frames.stride(0), frames.stride(1))
+            cached = self._quality_desc if getattr(self, "_quality_desc", None) and self._quality_desc[0] == key else None
+            desc = None
+            if cached is None:                        # the same batch tensor again (a streaming loop): descriptors stay on the device
+                desc = np.zeros(n, N.QUALITY_FRAME_DTYPE)
+                desc["src"] = np.uint64(frames.data_ptr()) + np.arange(n, dtype=np.uint64) * np.uint64(frames.stride(0))
+                desc["pitch"], desc["h"], desc["w"] = frames.stride(1), shapes[0][0], shapes[0][1]
             flist = range(n)
         else:
             flist = list(frames)
@@ -1341,13 +1345,18 @@ class Engine:
             desc["pitch"] = [f.stride(0) for f in flist]
             desc["h"] = [s_[0] for s_ in shapes]
             desc["w"] = [s_[1] for s_ in shapes]
-        d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.device)
+        if uniform and cached is not None:
+            d_desc = cached[1]
+        else:
+            d_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.device)
+            if uniform:
+                self._quality_desc = (key, d_desc)
         sums = torch.empty((len(flist), 3), dtype=torch.int64, device=self.device)
         out = []
         for b0 in range(0, len(flist), 65535):
             n = min(65535, len(flist) - b0)
-            N.check(self.L.vis_quality_stats(d_desc.data_ptr() + b0 * N.QUALITY_FRAME_DTYPE.itemsize, n,
-                                             max(s[0] for s in shapes[b0:b0 + n]), max(s[1] for s in shapes[b0:b0 + n]),
+            mh, mw = (shapes[0] if uniform else (max(s[0] for s in shapes[b0:b0 + n]), max(s[1] for s in shapes[b0:b0 + n])))
+            N.check(self.L.vis_quality_stats(d_desc.data_ptr() + b0 * N.QUALITY_FRAME_DTYPE.itemsize, n, mh, mw,
                                              sums.data_ptr() + b0 * 24, _stream_ptr()), "vis_quality_stats")
             out.append(n)
         self.last_launches = 2 * len(out)            # the ring kernel and the kernel of the remaining strips
