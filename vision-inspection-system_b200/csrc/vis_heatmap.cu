@@ -34,22 +34,23 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 constexpr int kBlurR = 25;                       // largest radius (ksize <= 51)
 constexpr int kOut = 8;                          // outputs per thread of both passes
-constexpr int kHSeg = 512, kHRows = 4;           // horizontal pass: 4 rows x 512 outputs per block (64 threads per row)
+constexpr int kHSeg = 512, kHRows = 4;           // horizontal pass: 512 outputs x 4 rows per step (64 threads per row) ...
+constexpr int kHBlkRows = 16;                    // ... and four steps per block: 16 rows staged at once
 constexpr int kHLen = kHSeg + 2 * kBlurR + 6;    // staged row, padded to a multiple of 8 (568)
 constexpr int kHPhase = kHLen / kOut;            // 71: element i lives at (i % 8) * 71 + i / 8 -> lanes read consecutive words
-constexpr int kVCols = 32, kVRows = 64;          // vertical pass: 32 columns x 64 output rows per block
-constexpr int kVTile = kVRows + 2 * kBlurR;       // rows staged
+constexpr int kVCols = 32, kVRows = 64;          // vertical pass: 32 columns x 64 output rows per step ...
+constexpr int kVBlkRows = 192;                   // ... and three steps per block: 192 + 2R rows staged at once
 constexpr int kRDefect = 25, kRFinal = 15;       // window radii of the two launch classes (51 / 31 taps at most)
 static_assert(kHLen % kOut == 0, "staged row must de-interleave evenly");
+static_assert(kHBlkRows % kHRows == 0 && kVBlkRows % kVRows == 0, "whole steps per block");
 
-// The kernel of a launch class is held in REGISTERS, centred in a window of compile-time radius R (smaller kernels are
-// padded with zero weights; the reference's kernels are 49..51 taps for defects, <= 31 for the final blur), so the taps
-// unroll completely: per staged value one shared-memory read and up to 8 FMA with register operands only.
+// The kernel of a launch class sits in shared memory, centred in a window of compile-time radius R (smaller kernels are
+// padded with zero weights; the reference's kernels are 49..51 taps for defects, <= 31 for the final blur), loaded ONCE
+// per block; the taps unroll completely and a thread keeps the eight weights its sliding window needs in registers.
 template <int R>
-__device__ __forceinline__ void load_weights(float (&w)[2 * R + 1], const float* __restrict__ kern, int ksize) {
+__device__ __forceinline__ void load_weights(float* sw, const float* __restrict__ kern, int ksize) {
     const int pad = R - (ksize >> 1);
-#pragma unroll
-    for (int t = 0; t < 2 * R + 1; ++t) w[t] = (t >= pad && t < pad + ksize) ? __ldg(kern + t - pad) : 0.f;
+    for (int t = threadIdx.x; t < 2 * R + 1; t += kT) sw[t] = (t >= pad && t < pad + ksize) ? __ldg(kern + t - pad) : 0.f;
 }
 
 // analytic heat of a box defect / widespread defect at region-local (lx, ly), float64 like the reference.  Everything
@@ -91,15 +92,21 @@ __global__ void __launch_bounds__(kT) k_heat_tables(const VisHeatItem* __restric
 // 8 outputs from one sliding window of radius R: value(k), k = 0 .. 8 + 2R - 1, is staged element (first output - R + k);
 // output j accumulates taps t = k - j in ascending order.
 template <int R, typename F>
-__device__ __forceinline__ void window8(float (&acc)[kOut], const float (&w)[2 * R + 1], F value) {
+__device__ __forceinline__ void window8(float (&acc)[kOut], const float* sw, F value) {
 #pragma unroll
     for (int j = 0; j < kOut; ++j) acc[j] = 0.f;
+    float w[kOut];                                // w[i] = weight of tap (k - i) at step k: a sliding set of eight
+#pragma unroll
+    for (int i = 0; i < kOut; ++i) w[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < kOut + 2 * R; ++k) {
+#pragma unroll
+        for (int i = kOut - 1; i > 0; --i) w[i] = w[i - 1];
+        w[0] = k <= 2 * R ? sw[k] : 0.f;          // one broadcast read per step
         const float v = value(k);
 #pragma unroll
         for (int j = 0; j < kOut; ++j)
-            if (k - j >= 0 && k - j <= 2 * R) acc[j] = fmaf(w[k - j], v, acc[j]);
+            if (k - j >= 0 && k - j <= 2 * R) acc[j] = fmaf(w[j], v, acc[j]);
     }
 }
 
@@ -107,141 +114,160 @@ __device__ __forceinline__ void atomic_max_f(float* p, float v) {      // non-ne
     atomicMax(reinterpret_cast<unsigned int*>(p), __float_as_uint(fmaxf(v, 0.f)));
 }
 
+// horizontal step shared by both classes: 4 staged rows (de-interleaved by 8) x 512 outputs, thread = 8 outputs
+template <int R>
+__device__ __forceinline__ void h_steps(const float (*rows)[kHLen], const float* sw, int n_rows, int n_cols, float* out, size_t out_pitch) {
+    const int c = threadIdx.x & 63;
+    if (c * kOut >= n_cols) return;
+#pragma unroll 1
+    for (int row = threadIdx.x >> 6; row < n_rows; row += kHRows) {
+        float acc[kOut];
+        const float* rp = rows[row] + c;
+        window8<R>(acc, sw, [&](int k) { return rp[(k % kOut) * kHPhase + k / kOut]; });      // element c*8 + k
+        float* o = out + (size_t)row * out_pitch + c * kOut;
+#pragma unroll
+        for (int j = 0; j < kOut; ++j)
+            if (c * kOut + j < n_cols) o[j] = acc[j];
+    }
+}
+
 __global__ void __launch_bounds__(kT)
 k_heat_defect_h(const VisHeatItem* __restrict__ items, const VisHeatFrame* __restrict__ frames, const double* __restrict__ tabs,
                 const float* __restrict__ kernels, float* __restrict__ tmp, float* __restrict__ heat) {
-    __shared__ float rows[kHRows][kHLen];
+    __shared__ float rows[kHBlkRows][kHLen];
+    __shared__ float sw[2 * kRDefect + 1];
     const VisHeatItem& it = items[blockIdx.z];
     const VisHeatDefect& d = it.d;
     const int rw = d.x2 - d.x1, rh = d.y2 - d.y1;
-    const int x0 = blockIdx.x * kHSeg, y0 = blockIdx.y * kHRows;
+    const int x0 = blockIdx.x * kHSeg, y0 = blockIdx.y * kHBlkRows;
     if (x0 >= rw || y0 >= rh) return;
     const HeatTabs tb = heat_tabs(tabs, it);
     const VisHeatFrame& fr = frames[it.frame];
+    const int n_rows = min(kHBlkRows, rh - y0);
     const bool direct = d.kind == 1 || d.ksize == 1;
     if (direct) {                                      // no blur: max-combine the analytic heat itself
         float* plane = heat + fr.plane_off;
-        for (int i = threadIdx.x; i < kHRows * kHSeg; i += kT) {
+        for (int i = threadIdx.x; i < n_rows * kHSeg; i += kT) {
             const int ly = y0 + i / kHSeg, lx = x0 + i % kHSeg;
-            if (ly < rh && lx < rw) atomic_max_f(plane + (size_t)(d.y1 + ly) * fr.w + d.x1 + lx, heat_value(d, tb, lx, ly));
+            if (lx < rw) atomic_max_f(plane + (size_t)(d.y1 + ly) * fr.w + d.x1 + lx, heat_value(d, tb, lx, ly));
         }
         return;
     }
     constexpr int R = kRDefect;
-    float w[2 * R + 1];
-    load_weights<R>(w, kernels + d.koff, d.ksize);
+    load_weights<R>(sw, kernels + d.koff, d.ksize);
+    // Staging, thread = column: everything that depends on the column (reflected at the REGION border) is fetched once,
+    // then the rows of the block are walked with the row's three table values read as warp-uniform loads.  The
+    // operations on a pixel are exactly heat_value()'s (same float64 roundings, same comparisons).
     constexpr int span = kHSeg + 2 * R;
-    for (int i = threadIdx.x; i < kHRows * span; i += kT) {
-        const int row = i / span, idx = i - row * span;
-        const int ly = y0 + row;
-        float v = 0.f;
-        if (ly < rh) v = heat_value(d, tb, reflect101(x0 + idx - R, rw), ly);
-        rows[row][(idx % kOut) * kHPhase + idx / kOut] = v;
+    const double lim2 = (4.0 * d.sigma) * (4.0 * d.sigma);
+    for (int idx = threadIdx.x; idx < span; idx += kT) {
+        const int lx = reflect101(x0 + idx - R, rw), gx = d.x1 + lx;
+        const double txv = tb.tx[lx], bxv = tb.bx[lx], qxv = tb.qx[lx];
+        const bool in_x = gx >= d.x && gx < d.x + d.w;
+        float* col = &rows[0][(idx % kOut) * kHPhase + idx / kOut];
+#pragma unroll 4
+        for (int r = 0; r < n_rows; ++r) {
+            const int ly = y0 + r, gy = d.y1 + ly;
+            const double g0 = d.intensity * (txv * tb.ty[ly]);
+            const bool in_box = in_x && gy >= d.y && gy < d.y + d.h;
+            const double boost = (bxv + tb.by[ly] < 1.2 * 1.2) ? 1.8 : (in_box ? 1.4 : 1.0);
+            const double g = fmin(1.0, g0 * boost);
+            col[r * kHLen] = (qxv + tb.qy[ly]) < lim2 ? (float)g : 0.f;
+        }
     }
     __syncthreads();
-    const int row = threadIdx.x >> 6, c = threadIdx.x & 63;
-    const int ly = y0 + row, lx = x0 + c * kOut;
-    if (ly >= rh || lx >= rw) return;
-    float acc[kOut];
-    const float* rp = rows[row] + c;
-    window8<R>(acc, w, [&](int k) { return rp[(k % kOut) * kHPhase + k / kOut]; });      // element c*8 + k
-    float* o = tmp + it.tmp_off + (size_t)ly * rw + lx;
+    h_steps<R>(rows, sw, n_rows, min(kHSeg, rw - x0), tmp + it.tmp_off + (size_t)y0 * rw + x0, (size_t)rw);
+}
+
+// vertical step shared by both classes: the staged tile holds rows y0 - R .. y0 + kVBlkRows + R of 32 columns; a warp
+// produces 8 consecutive rows of its lane's column per step, 64 rows per step and block
+template <int R, typename Emit>
+__device__ __forceinline__ void v_steps(const float (*tile)[kVCols], const float* sw, int n_rows, Emit emit) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int r0 = (threadIdx.x >> 5) * kOut; r0 < n_rows; r0 += kVRows) {
+        float acc[kOut];
+        window8<R>(acc, sw, [&](int k) { return tile[r0 + k][lane]; });
 #pragma unroll
-    for (int j = 0; j < kOut; ++j)
-        if (lx + j < rw) o[j] = acc[j];
+        for (int j = 0; j < kOut; ++j)
+            if (r0 + j < n_rows) emit(r0 + j, acc[j]);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void v_stage(float (*tile)[kVCols], const float* __restrict__ src, int pitch, int x, bool x_ok, int y0, int h) {
+    const int lane = threadIdx.x & 31;
+    const int n = min(kVBlkRows, h - y0) + 2 * R;
+    for (int i = threadIdx.x >> 5; i < n; i += kT / 32)
+        tile[i][lane] = x_ok ? src[(size_t)reflect101(y0 + i - R, h) * pitch + x] : 0.f;
 }
 
 // vertical pass of a defect region: tmp -> max into the frame's heat plane
 __global__ void __launch_bounds__(kT)
 k_heat_defect_v(const VisHeatItem* __restrict__ items, const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels,
                 const float* __restrict__ tmp, float* __restrict__ heat) {
-    __shared__ float tile[kVTile][kVCols];
+    __shared__ float tile[kVBlkRows + 2 * kRDefect][kVCols];
+    __shared__ float sw[2 * kRDefect + 1];
     const VisHeatItem& it = items[blockIdx.z];
     const VisHeatDefect& d = it.d;
     if (d.kind == 1 || d.ksize == 1) return;
     const int rw = d.x2 - d.x1, rh = d.y2 - d.y1;
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int x = blockIdx.x * kVCols + lane, y0 = blockIdx.y * kVRows;
+    const int x = blockIdx.x * kVCols + (threadIdx.x & 31), y0 = blockIdx.y * kVBlkRows;
     if (blockIdx.x * kVCols >= rw || y0 >= rh) return;
     constexpr int R = kRDefect;
-    float w[2 * R + 1];
-    load_weights<R>(w, kernels + d.koff, d.ksize);
-    const float* src = tmp + it.tmp_off;
-    for (int i = grp; i < kVRows + 2 * R; i += kT / 32)
-        tile[i][lane] = x < rw ? src[(size_t)reflect101(y0 + i - R, rh) * rw + x] : 0.f;
+    load_weights<R>(sw, kernels + d.koff, d.ksize);
+    v_stage<R>(tile, tmp + it.tmp_off, rw, x, x < rw, y0, rh);
     __syncthreads();
     if (x >= rw) return;
-    float acc[kOut];
-    window8<R>(acc, w, [&](int k) { return tile[grp * kOut + k][lane]; });
     const VisHeatFrame& fr = frames[it.frame];
-    float* plane = heat + fr.plane_off;
-#pragma unroll
-    for (int j = 0; j < kOut; ++j) {
-        const int y = y0 + grp * kOut + j;
-        if (y < rh) atomic_max_f(plane + (size_t)(d.y1 + y) * fr.w + d.x1 + x, acc[j]);
-    }
+    float* plane = heat + fr.plane_off + (size_t)(d.y1 + y0) * fr.w + d.x1 + x;
+    const int fw = fr.w;
+    v_steps<R>(tile, sw, min(kVBlkRows, rh - y0), [&](int r, float v) { atomic_max_f(plane + (size_t)r * fw, v); });
 }
 
 // whole-mask blur, horizontal: heat -> fa (reflect at the image border)
 __global__ void __launch_bounds__(kT)
 k_heat_final_h(const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels, const float* __restrict__ heat,
                float* __restrict__ fa) {
-    __shared__ float rows[kHRows][kHLen];
+    __shared__ float rows[kHBlkRows][kHLen];
+    __shared__ float sw[2 * kRFinal + 1];
     const VisHeatFrame& fr = frames[blockIdx.z];
-    const int x0 = blockIdx.x * kHSeg, y0 = blockIdx.y * kHRows;
+    const int x0 = blockIdx.x * kHSeg, y0 = blockIdx.y * kHBlkRows;
     if (x0 >= fr.w || y0 >= fr.h) return;
     constexpr int R = kRFinal;
-    float w[2 * R + 1];
-    load_weights<R>(w, kernels + fr.final_koff, fr.final_ksize);
-    const float* plane = heat + fr.plane_off;
+    load_weights<R>(sw, kernels + fr.final_koff, fr.final_ksize);
+    const float* plane = heat + fr.plane_off + (size_t)y0 * fr.w;
+    const int n_rows = min(kHBlkRows, fr.h - y0);
     constexpr int span = kHSeg + 2 * R;
-    for (int i = threadIdx.x; i < kHRows * span; i += kT) {
-        const int row = i / span, idx = i - row * span;
-        const int y = y0 + row;
-        rows[row][(idx % kOut) * kHPhase + idx / kOut] = y < fr.h ? plane[(size_t)y * fr.w + reflect101(x0 + idx - R, fr.w)] : 0.f;
+    for (int idx = threadIdx.x; idx < span; idx += kT) {            // thread = column, reflected once
+        const float* src = plane + reflect101(x0 + idx - R, fr.w);
+        float* col = &rows[0][(idx % kOut) * kHPhase + idx / kOut];
+#pragma unroll 4
+        for (int r = 0; r < n_rows; ++r) col[r * kHLen] = src[(size_t)r * fr.w];
     }
     __syncthreads();
-    const int row = threadIdx.x >> 6, c = threadIdx.x & 63;
-    const int y = y0 + row, x = x0 + c * kOut;
-    if (y >= fr.h || x >= fr.w) return;
-    float acc[kOut];
-    const float* rp = rows[row] + c;
-    window8<R>(acc, w, [&](int k) { return rp[(k % kOut) * kHPhase + k / kOut]; });
-    float* o = fa + fr.plane_off + (size_t)y * fr.w + x;
-#pragma unroll
-    for (int j = 0; j < kOut; ++j)
-        if (x + j < fr.w) o[j] = acc[j];
+    h_steps<R>(rows, sw, n_rows, min(kHSeg, fr.w - x0), fa + fr.plane_off + (size_t)y0 * fr.w + x0, (size_t)fr.w);
 }
 
 // whole-mask blur, vertical: fa -> fb, and the frame's maximum
 __global__ void __launch_bounds__(kT)
 k_heat_final_v(const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels, const float* __restrict__ fa,
                float* __restrict__ fb, unsigned int* __restrict__ max_bits) {
-    __shared__ float tile[kVRows + 2 * kRFinal][kVCols];
+    __shared__ float tile[kVBlkRows + 2 * kRFinal][kVCols];
+    __shared__ float sw[2 * kRFinal + 1];
     const VisHeatFrame& fr = frames[blockIdx.z];
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int x = blockIdx.x * kVCols + lane, y0 = blockIdx.y * kVRows;
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * kVCols + lane, y0 = blockIdx.y * kVBlkRows;
     if (blockIdx.x * kVCols >= fr.w || y0 >= fr.h) return;
     constexpr int R = kRFinal;
-    float w[2 * R + 1];
-    load_weights<R>(w, kernels + fr.final_koff, fr.final_ksize);
-    const float* src = fa + fr.plane_off;
-    for (int i = grp; i < kVRows + 2 * R; i += kT / 32)
-        tile[i][lane] = x < fr.w ? src[(size_t)reflect101(y0 + i - R, fr.h) * fr.w + x] : 0.f;
+    load_weights<R>(sw, kernels + fr.final_koff, fr.final_ksize);
+    v_stage<R>(tile, fa + fr.plane_off, fr.w, x, x < fr.w, y0, fr.h);
     __syncthreads();
     float m = 0.f;
     if (x < fr.w) {
-        float acc[kOut];
-        window8<R>(acc, w, [&](int k) { return tile[grp * kOut + k][lane]; });
-        float* o = fb + fr.plane_off;
-#pragma unroll
-        for (int j = 0; j < kOut; ++j) {
-            const int y = y0 + grp * kOut + j;
-            if (y < fr.h) {
-                o[(size_t)y * fr.w + x] = acc[j];
-                m = fmaxf(m, acc[j]);
-            }
-        }
+        float* o = fb + fr.plane_off + (size_t)y0 * fr.w + x;
+        const int fw = fr.w;
+        v_steps<R>(tile, sw, min(kVBlkRows, fr.h - y0), [&](int r, float v) { o[(size_t)r * fw] = v; m = fmaxf(m, v); });
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
@@ -320,13 +346,13 @@ extern "C" int vis_heatmap_batch(const VisHeatFrame* frames, int n_frames, const
     if (e != cudaSuccess) return vis::cuda_fail(e, "vis_heatmap_batch: cudaMemsetAsync");
     if (n_items) {
         k_heat_tables<<<dim3((max_rw + max_rh + kT - 1) / kT, n_items), kT, 0, st>>>(items, tabs);
-        k_heat_defect_h<<<dim3((max_rw + kHSeg - 1) / kHSeg, (max_rh + kHRows - 1) / kHRows, n_items), kT, 0, st>>>(
+        k_heat_defect_h<<<dim3((max_rw + kHSeg - 1) / kHSeg, (max_rh + kHBlkRows - 1) / kHBlkRows, n_items), kT, 0, st>>>(
             items, frames, tabs, kernels, tmp, heat);
-        k_heat_defect_v<<<dim3((max_rw + kVCols - 1) / kVCols, (max_rh + kVRows - 1) / kVRows, n_items), kT, 0, st>>>(
+        k_heat_defect_v<<<dim3((max_rw + kVCols - 1) / kVCols, (max_rh + kVBlkRows - 1) / kVBlkRows, n_items), kT, 0, st>>>(
             items, frames, kernels, tmp, heat);
     }
-    k_heat_final_h<<<dim3((max_w + kHSeg - 1) / kHSeg, (max_h + kHRows - 1) / kHRows, n_frames), kT, 0, st>>>(frames, kernels, heat, fa);
-    k_heat_final_v<<<dim3((max_w + kVCols - 1) / kVCols, (max_h + kVRows - 1) / kVRows, n_frames), kT, 0, st>>>(frames, kernels, fa, fb, max_bits);
+    k_heat_final_h<<<dim3((max_w + kHSeg - 1) / kHSeg, (max_h + kHBlkRows - 1) / kHBlkRows, n_frames), kT, 0, st>>>(frames, kernels, heat, fa);
+    k_heat_final_v<<<dim3((max_w + kVCols - 1) / kVCols, (max_h + kVBlkRows - 1) / kVBlkRows, n_frames), kT, 0, st>>>(frames, kernels, fa, fb, max_bits);
     k_heat_colorize<<<dim3(592, n_frames), kT, 0, st>>>(frames, fb, max_bits, jet768);
     return vis::check_launch("vis_heatmap_batch");
 }
