@@ -131,7 +131,7 @@ __device__ __forceinline__ void h_steps(const float (*rows)[kHLen], const float*
     }
 }
 
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 4)
 k_heat_defect_h(const VisHeatItem* __restrict__ items, const VisHeatFrame* __restrict__ frames, const double* __restrict__ tabs,
                 const float* __restrict__ kernels, float* __restrict__ tmp, float* __restrict__ heat) {
     __shared__ float rows[kHBlkRows][kHLen];
@@ -196,10 +196,17 @@ __device__ __forceinline__ void v_steps(const float (*tile)[kVCols], const float
 
 template <int R>
 __device__ __forceinline__ void v_stage(float (*tile)[kVCols], const float* __restrict__ src, int pitch, int x, bool x_ok, int y0, int h) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int n = min(kVBlkRows, h - y0) + 2 * R;
-    for (int i = threadIdx.x >> 5; i < n; i += kT / 32)
-        tile[i][lane] = x_ok ? src[(size_t)reflect101(y0 + i - R, h) * pitch + x] : 0.f;
+    if (!x_ok) {
+        for (int i = grp; i < n; i += kT / 32) tile[i][lane] = 0.f;
+    } else if (y0 >= R && y0 + n - R <= h) {            // interior block: no reflection, loads four at a time
+        const float* p = src + (size_t)(y0 - R) * pitch + x;
+#pragma unroll 4
+        for (int i = grp; i < n; i += kT / 32) tile[i][lane] = p[(size_t)i * pitch];
+    } else {
+        for (int i = grp; i < n; i += kT / 32) tile[i][lane] = src[(size_t)reflect101(y0 + i - R, h) * pitch + x];
+    }
 }
 
 // vertical pass of a defect region: tmp -> max into the frame's heat plane
@@ -250,7 +257,7 @@ k_heat_final_h(const VisHeatFrame* __restrict__ frames, const float* __restrict_
 }
 
 // whole-mask blur, vertical: fa -> fb, and the frame's maximum
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 5)
 k_heat_final_v(const VisHeatFrame* __restrict__ frames, const float* __restrict__ kernels, const float* __restrict__ fa,
                float* __restrict__ fb, unsigned int* __restrict__ max_bits) {
     __shared__ float tile[kVBlkRows + 2 * kRFinal][kVCols];
