@@ -52,8 +52,9 @@ constexpr int kStageBytes = kK * kRowPitch;
 constexpr int kSmemBytes = kS * kStageBytes;
 static_assert(kK <= 16 && kAhead <= 16 && 32 % kAhead == 0, "a lane converts the halo pixels of one row of a stage / of 32 rows");
 
-__device__ __forceinline__ int reflect101(int i, int n) {       // cv: BORDER_REFLECT_101, n >= 1
-    if (n == 1) return 0;
+// cv: BORDER_REFLECT_101 for -n < i < 2n (one reflection), n >= 1; the clamp covers n = 1 (every index -> 0) and the
+// far side of frames narrower than a strip, whose pixels are masked out anyway
+__device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
     if (i >= n) i = 2 * n - 2 - i;
     return min(max(i, 0), n - 1);
