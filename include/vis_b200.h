@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 18
+#define VIS_B200_ABI_VERSION 19
 
 /* status codes */
 #define VIS_OK            0
@@ -462,6 +462,18 @@ typedef struct VisPanel {        /* cv2.resize(src, (dst_w, dst_h)) placed at (o
  * Replaces utils/image_utils.py:637-679 (two cv2.resize calls, header/divider fill, hstack, vstack).  [device] */
 int vis_compose_panels(uint8_t* canvas, int64_t canvas_pitch, int h, int w, int fill,
                        const VisPanel* panels, int n_panels, void* stream);
+/* The same for a BATCH of canvases in one launch (a report run composes one panel per inspected image).  canvases is a
+ * DEVICE array; the library cannot validate it: every panel's `mode` must be vis_resize_linear_mode of its sizes, its
+ * tables those of vis_linear_table, panels of a canvas must not overlap.  max_h / max_w: the largest canvas.  [device] */
+typedef struct VisPanelCanvas {
+    uint8_t* canvas;             /* device, [h, w, 3] uint8, rows of `pitch` bytes                                */
+    int64_t  pitch;
+    int32_t  h, w;
+    int32_t  fill;               /* 0..255: every byte outside the panels                                         */
+    int32_t  n_panels;           /* 0..4                                                                          */
+    VisPanel panels[4];
+} VisPanelCanvas;
+int vis_compose_panels_batch(const VisPanelCanvas* canvases, int n_canvases, int max_h, int max_w, void* stream);
 
 /* generic draw list on top of the overlay rasteriser: each command becomes one group of leaves (like one VisBox),
  * so vis_overlay_tiles / vis_overlay_draw(_cn) take the result unchanged.                */

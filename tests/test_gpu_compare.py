@@ -67,3 +67,28 @@ def test_file_level_functions(engine, tmp_path):
         IU.create_side_by_side_comparison(tmp_path / "missing.png", tmp_path / "b.png", tmp_path / "x.png")
     out = IU.create_status_stamp("UNSAFE", tmp_path / "stamps" / "s.png")
     assert np.array_equal(cv2.imread(str(out), cv2.IMREAD_UNCHANGED), OC.status_stamp("UNSAFE"))
+
+
+def test_side_by_side_batch_equals_single_calls(engine):
+    """A batch of pairs in two launches (vis_compose_panels_batch + one label draw over every canvas): mixed geometries
+    (bilinear, the exact-half area path, a copy-sized panel, strided inputs), custom labels; every canvas equals the
+    single-pair call and the oracle."""
+    rng = np.random.default_rng(23)
+    shapes = [((480, 640), (480, 640)), ((1600, 400), (800, 300)), ((97, 211), (333, 517)), ((480, 640), (480, 640)),
+              ((1080, 1920), (1080, 1920)), ((800, 120), (799, 1203))]
+    pairs = []
+    for (h1, w1), (h2, w2) in shapes:
+        pairs.append((rng.integers(0, 256, (h1, w1, 3), dtype=np.uint8), rng.integers(0, 256, (h2, w2, 3), dtype=np.uint8)))
+    wide = torch.from_numpy(rng.integers(0, 256, (480, 700, 3), dtype=np.uint8)).cuda()
+    dev = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in pairs] + [(wide[:, :640], wide[:, 60:])]
+    for labels in (None, ("Before", "After rework #2")):
+        outs = engine.side_by_side_batch([a for a, _ in dev], [b for _, b in dev], labels)
+        assert engine.last_launches == 2 and len(outs) == len(dev)
+        for i, (a, b) in enumerate(dev):
+            single = engine.side_by_side(a, b, labels)
+            assert torch.equal(outs[i], single), (i, labels)
+        for i in (0, 1, 4):
+            want = OC.side_by_side(*pairs[i]) if labels is None else OC.side_by_side(*pairs[i], labels)
+            assert np.array_equal(outs[i].cpu().numpy(), want), i
+    with pytest.raises(ValueError):
+        engine.side_by_side_batch([], [])

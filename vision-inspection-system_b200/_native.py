@@ -77,7 +77,9 @@ DRAW_LINE, DRAW_RECTANGLE, DRAW_CIRCLE, DRAW_TEXT = 1, 2, 3, 4
 DRAW_CMD_DTYPE = np.dtype([("kind", np.int32), ("x1", np.int32), ("y1", np.int32), ("x2", np.int32), ("y2", np.int32),
                            ("thickness", np.int32), ("line_type", np.int32), ("color", np.uint8, (4,)),
                            ("font_scale", np.float64), ("text", np.uint64)], align=True)
-assert PANEL_DTYPE.itemsize == 80 and DRAW_CMD_DTYPE.itemsize == 48
+PANEL_CANVAS_DTYPE = np.dtype([("canvas", np.uint64), ("pitch", np.int64), ("h", np.int32), ("w", np.int32),
+                               ("fill", np.int32), ("n_panels", np.int32), ("panels", PANEL_DTYPE, (4,))], align=True)
+assert PANEL_DTYPE.itemsize == 80 and DRAW_CMD_DTYPE.itemsize == 48 and PANEL_CANVAS_DTYPE.itemsize == 352
 
 EXPORTS = [
     "vis_abi_version", "vis_last_error", "vis_source_hash", "vis_coeff_ksize", "vis_build_coeffs", "vis_build_lut",
@@ -87,7 +89,7 @@ EXPORTS = [
     "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_sched_record_stride_dp", "vis_sched_pack_records_dp", "vis_preprocess_fused_sched", "vis_preprocess_fused_sched_dup",
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_batch",
-    "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn", "vis_overlay_sprite_expand", "vis_overlay_stamp_expand", "vis_overlay_plan_batch_sprites",
+    "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_compose_panels_batch", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn", "vis_overlay_sprite_expand", "vis_overlay_stamp_expand", "vis_overlay_plan_batch_sprites",
     "vis_coeff_ksize_box", "vis_build_coeffs_box", "vis_reduce_u8", "vis_nearest_table", "vis_gather_u8", "vis_alpha_premultiply_u8", "vis_repitch_u8", "vis_build_coeffs_f64", "vis_resample_hp",
     "vis_jpeg_create", "vis_jpeg_destroy", "vis_jpeg_info", "vis_jpeg_decode", "vis_jpeg_decode_batch",
     "vis_jpeg_encode_bound", "vis_jpeg_encode",
@@ -169,7 +171,7 @@ def lib() -> C.CDLL:
                 "This engine has no CPU fallback.")
         L = C.CDLL(os.fspath(LIB_PATH))
         _declare(L)
-        if L.vis_abi_version() != 18:
+        if L.vis_abi_version() != 19:
             raise RuntimeError("libvis_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
@@ -214,6 +216,7 @@ def _declare(L: C.CDLL) -> None:
     L.vis_resize_linear_mode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.vis_linear_table.argtypes = [C.c_int, C.c_int, C.c_int, i32p, vp]
     L.vis_compose_panels.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.vis_compose_panels_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.vis_text_size.argtypes = [C.c_char_p, C.c_double, C.c_int, ip, ip]
     L.vis_draw_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
     L.vis_overlay_draw_cn.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]

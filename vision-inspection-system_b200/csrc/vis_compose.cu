@@ -55,10 +55,9 @@ __device__ __forceinline__ void panel_pixel(const VisPanel& p, int x, int y, int
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_compose_panels(uint8_t* __restrict__ canvas, int64_t pitch, int h, int w, int fill, const PanelSet ps) {
-    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * kPx;
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+// one thread = four consecutive canvas pixels of a row
+__device__ __forceinline__ void compose_row4(uint8_t* __restrict__ canvas, int64_t pitch, int h, int w, int fill, const PanelSet& ps,
+                                             int x0, int y) {
     if (y >= h || x0 >= w) return;
     int v[kPx][3];
 #pragma unroll
@@ -82,6 +81,30 @@ k_compose_panels(uint8_t* __restrict__ canvas, int64_t pitch, int h, int w, int 
 #pragma unroll
             for (int c = 0; c < 3; ++c) d[j * 3 + c] = (uint8_t)v[j][c];
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_compose_panels(uint8_t* __restrict__ canvas, int64_t pitch, int h, int w, int fill, const PanelSet ps) {
+    compose_row4(canvas, pitch, h, w, fill, ps, (blockIdx.x * 32 + (threadIdx.x & 31)) * kPx, blockIdx.y * 8 + (threadIdx.x >> 5));
+}
+
+// a batch of canvases, one per blockIdx.z: the canvas record is read into shared memory once per block
+__global__ void __launch_bounds__(256)
+k_compose_panels_batch(const VisPanelCanvas* __restrict__ canvases) {
+    __shared__ VisPanelCanvas cv;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(canvases + blockIdx.z);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&cv);
+        for (int i = threadIdx.x; i < (int)(sizeof(VisPanelCanvas) / 4); i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if ((int)blockIdx.y * 8 >= cv.h || (int)blockIdx.x * 32 * kPx >= cv.w) return;
+    PanelSet ps;
+    ps.n = min(max(cv.n_panels, 0), kMaxPanels);
+#pragma unroll
+    for (int k = 0; k < kMaxPanels; ++k) ps.p[k] = cv.panels[k];
+    compose_row4(cv.canvas, cv.pitch, cv.h, cv.w, cv.fill, ps, (blockIdx.x * 32 + (threadIdx.x & 31)) * kPx,
+                 blockIdx.y * 8 + (threadIdx.x >> 5));
 }
 
 inline int16_t sat_short(float v) {
@@ -146,4 +169,18 @@ extern "C" int vis_compose_panels(uint8_t* canvas, int64_t canvas_pitch, int h, 
     const dim3 grid((w + 32 * kPx - 1) / (32 * kPx), (h + 7) / 8);
     k_compose_panels<<<grid, 256, 0, (cudaStream_t)stream>>>(canvas, canvas_pitch, h, w, fill, ps);
     return vis::check_launch("vis_compose_panels");
+}
+
+extern "C" int vis_compose_panels_batch(const VisPanelCanvas* canvases, int n_canvases, int max_h, int max_w, void* stream) {
+    if (!canvases || n_canvases <= 0 || n_canvases > 65535 || max_h <= 0 || max_w <= 0) {
+        vis::set_error("vis_compose_panels_batch: bad arguments (canvases=%d max %dx%d)", n_canvases, max_w, max_h);
+        return VIS_E_INVALID;
+    }
+    const dim3 grid((max_w + 32 * kPx - 1) / (32 * kPx), (max_h + 7) / 8, n_canvases);
+    if (grid.y > 65535) {
+        vis::set_error("vis_compose_panels_batch: canvases of %d rows are beyond the grid", max_h);
+        return VIS_E_UNSUPPORTED;
+    }
+    k_compose_panels_batch<<<grid, 256, 0, (cudaStream_t)stream>>>(canvases);
+    return vis::check_launch("vis_compose_panels_batch");
 }

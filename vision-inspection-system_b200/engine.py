@@ -1211,12 +1211,11 @@ class Engine:
         return outs
 
     # ------------------------------------------------------------------ comparison panel / status stamp
-    def _draw_list(self, canvas: torch.Tensor, cmds: np.ndarray) -> int:
-        """Apply a draw list (``compare.*_commands``) in place on a [H, W, 3|4] uint8 CUDA canvas; returns launches.
-        The expanded plan (device leaves, tiles, refs) is cached per (canvas size, draw list)."""
+    def _draw_plan(self, h: int, w: int, cmds: np.ndarray) -> dict:
+        """The expanded plan of a draw list (``compare.*_commands``) on an [h, w] canvas — leaves, touched tiles, refs, as
+        host arrays and device copies — cached per (canvas size, draw list content)."""
         from . import compare as CP
         from . import overlay as O
-        h, w, cn = int(canvas.shape[0]), int(canvas.shape[1]), int(canvas.shape[2])
         up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
         cache = self.__dict__.setdefault("_draw_plans", {})
         key = (h, w, CP.commands_key(cmds))
@@ -1227,22 +1226,29 @@ class Engine:
             tl = np.zeros(len(tiles), N.OVERLAY_TILE_DTYPE)
             if len(tiles):
                 tl["txy"], tl["ref_begin"], tl["ref_end"] = tiles[:, 0], tiles[:, 1], tiles[:, 2]
+            refs = np.ascontiguousarray(refs)
             if len(cache) >= 64:
                 cache.clear()
-            plan = cache[key] = (len(tl), up(tl) if len(tl) else None, up(np.ascontiguousarray(refs)) if len(tl) else None,
-                                 up(leaves) if len(tl) else None)
-        n_tiles, d_tiles, d_refs, d_leaves = plan
-        if n_tiles == 0:
+            plan = cache[key] = {"n_tiles": len(tl), "n_cmds": len(cmds), "tiles": tl, "refs": refs, "leaves": leaves,
+                                 "d_tiles": up(tl) if len(tl) else None, "d_refs": up(refs) if len(tl) else None,
+                                 "d_leaves": up(leaves) if len(tl) else None}
+        return plan
+
+    def _draw_list(self, canvas: torch.Tensor, cmds: np.ndarray) -> int:
+        """Apply a draw list in place on a [H, W, 3|4] uint8 CUDA canvas; returns launches."""
+        h, w, cn = int(canvas.shape[0]), int(canvas.shape[1]), int(canvas.shape[2])
+        plan = self._draw_plan(h, w, cmds)
+        if plan["n_tiles"] == 0:
             return 0
         desc = np.zeros(1, N.OVERLAY_FRAME_DTYPE)
         desc["src"] = desc["dst"] = canvas.data_ptr()
         desc["src_pitch"] = desc["dst_pitch"] = canvas.stride(0)
         desc["h"], desc["w"] = h, w
-        desc["group_begin"], desc["group_end"] = 0, len(cmds)
-        d_desc = up(desc)
-        N.check(self.L.vis_overlay_draw_cn(d_desc.data_ptr(), 1, cn, 0, d_tiles.data_ptr(), n_tiles, d_refs.data_ptr(),
-                                           d_leaves.data_ptr(), _stream_ptr()), "vis_overlay_draw_cn")
-        self._keepalive_d = (d_desc, d_tiles, d_refs, d_leaves)
+        desc["group_begin"], desc["group_end"] = 0, plan["n_cmds"]
+        d_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1).copy()).to(self.device)
+        N.check(self.L.vis_overlay_draw_cn(d_desc.data_ptr(), 1, cn, 0, plan["d_tiles"].data_ptr(), plan["n_tiles"],
+                                           plan["d_refs"].data_ptr(), plan["d_leaves"].data_ptr(), _stream_ptr()), "vis_overlay_draw_cn")
+        self._keepalive_d = (d_desc, plan)
         return 1
 
     def _linear_tables(self, src_size: int, dst_size: int, is_x: bool) -> list:
@@ -1256,13 +1262,10 @@ class Engine:
             cache[key] = [torch.from_numpy(a).to(self.device) for a in CP.linear_tables(src_size, dst_size, is_x)]
         return cache[key]
 
-    def side_by_side(self, original: torch.Tensor, annotated: torch.Tensor, labels=None) -> torch.Tensor:
-        """``create_side_by_side_comparison`` for two BGR uint8 HWC CUDA frames: both resized to a height of 800 as
-        ``cv2.resize`` does, a 40-row header and a 10-column divider of gray 45, two centred white labels.  Returns the
-        [840, W1 + 10 + W2, 3] canvas the reference hands to ``cv2.imwrite``; bit-exact.  Two launches."""
+    def _pair_panels(self, original: torch.Tensor, annotated: torch.Tensor, panels: np.ndarray, keep: list):
+        """Fill the two ``VisPanel`` records of a comparison canvas; returns (left_w, right_w)."""
         from . import compare as CP
-        labels = CP.DEFAULT_LABELS if labels is None else labels
-        keep, panels, org_x = [], np.zeros(2, N.PANEL_DTYPE), 0
+        org_x = 0
         for i, f in enumerate((original, annotated)):
             self._check_u8(f)
             if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
@@ -1280,7 +1283,16 @@ class Engine:
                 keep += dev
                 p["xofs"], p["alpha"], p["yofs"], p["beta"] = (t.data_ptr() for t in dev)
             org_x += dw + CP.DIVIDER_WIDTH
-        left_w, right_w = int(panels[0]["dst_w"]), int(panels[1]["dst_w"])
+        return int(panels[0]["dst_w"]), int(panels[1]["dst_w"])
+
+    def side_by_side(self, original: torch.Tensor, annotated: torch.Tensor, labels=None) -> torch.Tensor:
+        """``create_side_by_side_comparison`` for two BGR uint8 HWC CUDA frames: both resized to a height of 800 as
+        ``cv2.resize`` does, a 40-row header and a 10-column divider of gray 45, two centred white labels.  Returns the
+        [840, W1 + 10 + W2, 3] canvas the reference hands to ``cv2.imwrite``; bit-exact.  Two launches."""
+        from . import compare as CP
+        labels = CP.DEFAULT_LABELS if labels is None else labels
+        keep, panels = [], np.zeros(2, N.PANEL_DTYPE)
+        left_w, right_w = self._pair_panels(original, annotated, panels, keep)
         total_w = left_w + CP.DIVIDER_WIDTH + right_w
         canvas = torch.empty((CP.HEADER_HEIGHT + CP.TARGET_HEIGHT, total_w, 3), dtype=torch.uint8, device=self.device)
         N.check(self.L.vis_compose_panels(canvas.data_ptr(), canvas.stride(0), int(canvas.shape[0]), total_w, CP.BAR_GRAY,
@@ -1288,6 +1300,128 @@ class Engine:
         self._keepalive_c = keep
         self.last_launches = 1 + self._draw_list(canvas, CP.header_commands(left_w, right_w, labels))
         return canvas
+
+    def _pair_geometry(self, h1: int, w1: int, h2: int, w2: int):
+        """Everything of a comparison canvas that depends on the two frame sizes only: a ``VisPanelCanvas`` record with
+        the panel geometry, modes and device tables filled in (sources and canvas left open), and (left_w, right_w)."""
+        from . import compare as CP
+        cache = self.__dict__.setdefault("_pair_geo", {})
+        key = (h1, w1, h2, w2)
+        if key not in cache:
+            rec = np.zeros(1, N.PANEL_CANVAS_DTYPE)
+            keep, org_x = [], 0
+            for i, (h, w) in enumerate(((h1, w1), (h2, w2))):
+                dw = CP.panel_width(h, w)
+                if dw < 1:
+                    raise ValueError(f"frame {w}x{h} is too narrow for an {CP.TARGET_HEIGHT}-row panel")
+                mode = N.check(self.L.vis_resize_linear_mode(h, w, CP.TARGET_HEIGHT, dw), "vis_resize_linear_mode")
+                p = rec[0]["panels"][i]
+                p["src_h"], p["src_w"] = h, w
+                p["dst_h"], p["dst_w"], p["org_x"], p["org_y"], p["mode"] = CP.TARGET_HEIGHT, dw, org_x, CP.HEADER_HEIGHT, mode
+                if mode == N.RESIZE_BILINEAR:
+                    dev = self._linear_tables(w, dw, True) + self._linear_tables(h, CP.TARGET_HEIGHT, False)
+                    keep += dev
+                    p["xofs"], p["alpha"], p["yofs"], p["beta"] = (t.data_ptr() for t in dev)
+                org_x += dw + CP.DIVIDER_WIDTH
+            lw, rw = int(rec[0]["panels"][0]["dst_w"]), int(rec[0]["panels"][1]["dst_w"])
+            rec["h"], rec["w"] = CP.HEADER_HEIGHT + CP.TARGET_HEIGHT, lw + CP.DIVIDER_WIDTH + rw
+            rec["fill"], rec["n_panels"] = CP.BAR_GRAY, 2
+            if len(cache) >= 256:
+                cache.clear()
+            cache[key] = (rec, lw, rw, keep)
+        return cache[key]
+
+    def _frame_table(self, frames):
+        """(ptr uint64[n], pitch int64[n], h int32[n], w int32[n]) of BGR uint8 HWC CUDA frames: a [B, H, W, 3] tensor by
+        arithmetic, a list frame by frame."""
+        if isinstance(frames, torch.Tensor) and frames.dim() == 4:
+            self._check_u8(frames)
+            if frames.shape[3] != 3 or frames.stride(3) != 1 or frames.stride(2) != 3:
+                raise ValueError("frames must be [B, H, W, 3] uint8 with contiguous pixels")
+            n = int(frames.shape[0])
+            ptr = np.uint64(frames.data_ptr()) + np.arange(n, dtype=np.uint64) * np.uint64(frames.stride(0))
+            return (ptr, np.full(n, frames.stride(1), np.int64), np.full(n, int(frames.shape[1]), np.int32),
+                    np.full(n, int(frames.shape[2]), np.int32))
+        flist = list(frames)
+        for f in flist:
+            self._check_u8(f)
+            if f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                raise ValueError("frames must be [H, W, 3] uint8 with contiguous pixels")
+        return (np.array([f.data_ptr() for f in flist], np.uint64), np.array([f.stride(0) for f in flist], np.int64),
+                np.array([f.shape[0] for f in flist], np.int32), np.array([f.shape[1] for f in flist], np.int32))
+
+    def side_by_side_batch(self, originals, annotateds, labels=None) -> list:
+        """``side_by_side`` for many (original, annotated) pairs — a report run composes one panel per inspected image:
+        ONE compose launch and ONE label launch for the whole batch (``vis_compose_panels_batch`` + the overlay draw
+        kernel over every canvas's header tiles).  ``originals`` / ``annotateds``: lists of [H, W, 3] frames or
+        [B, H, W, 3] tensors.  Returns one [840, W, 3] canvas per pair (views of one allocation per distinct width);
+        every canvas equals what ``side_by_side`` returns for its pair."""
+        from . import compare as CP
+        labels = CP.DEFAULT_LABELS if labels is None else labels
+        pa, pitch_a, ha, wa = self._frame_table(originals)
+        pb, pitch_b, hb, wb = self._frame_table(annotateds)
+        n = len(pa)
+        if n == 0 or n != len(pb):
+            raise ValueError("one annotated frame per original expected (at least one pair)")
+        if n > 65535:
+            raise ValueError("at most 65535 pairs per call")
+        H = CP.HEADER_HEIGHT + CP.TARGET_HEIGHT
+        shapes = np.stack([ha, wa, hb, wb], axis=1)
+        uniq, inverse = np.unique(shapes, axis=0, return_inverse=True)
+        inverse = inverse.reshape(-1)
+        recs, keep, geo = np.zeros(n, N.PANEL_CANVAS_DTYPE), [], []
+        for g, (h1, w1, h2, w2) in enumerate(uniq):
+            rec, lw, rw, tabs = self._pair_geometry(int(h1), int(w1), int(h2), int(w2))
+            recs[inverse == g] = rec[0]
+            geo.append((lw, rw))
+            keep.append(tabs)
+        recs["panels"]["src"][:, 0], recs["panels"]["src"][:, 1] = pa, pb
+        recs["panels"]["src_pitch"][:, 0], recs["panels"]["src_pitch"][:, 1] = pitch_a, pitch_b
+        totals = recs["w"].astype(np.int64)
+        canvases, ptrs, pitches = [None] * n, np.zeros(n, np.uint64), np.zeros(n, np.int64)
+        for tw in np.unique(totals):                      # one allocation per distinct canvas width
+            idx = np.flatnonzero(totals == tw)
+            block = torch.empty((len(idx), H, int(tw), 3), dtype=torch.uint8, device=self.device)
+            ptrs[idx] = np.uint64(block.data_ptr()) + np.arange(len(idx), dtype=np.uint64) * np.uint64(block.stride(0))
+            pitches[idx] = block.stride(1)
+            for k, view in zip(idx, block.unbind(0)):
+                canvases[k] = view
+        recs["canvas"], recs["pitch"] = ptrs, pitches
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(self.device)  # noqa: E731
+        d_recs = up(recs)
+        sp = _stream_ptr()
+        N.check(self.L.vis_compose_panels_batch(d_recs.data_ptr(), n, H, int(totals.max()), sp), "vis_compose_panels_batch")
+        # the header labels: canvases of one geometry share one expanded draw list; its tiles are instantiated per canvas
+        plans = [self._draw_plan(H, lw + CP.DIVIDER_WIDTH + rw, CP.header_commands(lw, rw, labels)) for lw, rw in geo]
+        leaf_base = np.concatenate(([0], np.cumsum([len(p["leaves"]) for p in plans])))
+        ref_base = np.concatenate(([0], np.cumsum([len(p["refs"]) for p in plans])))
+        desc = np.zeros(n, N.OVERLAY_FRAME_DTYPE)
+        desc["src"] = desc["dst"] = ptrs
+        desc["src_pitch"] = desc["dst_pitch"] = pitches
+        desc["h"], desc["w"] = H, totals
+        desc["group_begin"] = leaf_base[inverse]
+        desc["group_end"] = leaf_base[inverse] + np.array([p["n_cmds"] for p in plans])[inverse]
+        tiles = []
+        for g, p in enumerate(plans):
+            idx = np.flatnonzero(inverse == g)
+            if p["n_tiles"] == 0 or len(idx) == 0:
+                continue
+            t = np.tile(p["tiles"], len(idx))
+            t["frame"] = np.repeat(idx, p["n_tiles"])
+            t["ref_begin"] += ref_base[g]
+            t["ref_end"] += ref_base[g]
+            tiles.append(t)
+        self.last_launches = 1
+        d_draw = None
+        if tiles:
+            tiles = np.concatenate(tiles)
+            d_draw = (up(desc), up(tiles), up(np.concatenate([p["refs"] for p in plans])),
+                      up(np.concatenate([p["leaves"] for p in plans])))
+            N.check(self.L.vis_overlay_draw_cn(d_draw[0].data_ptr(), n, 3, 0, d_draw[1].data_ptr(), len(tiles),
+                                               d_draw[2].data_ptr(), d_draw[3].data_ptr(), sp), "vis_overlay_draw_cn")
+            self.last_launches = 2
+        self._keepalive_c = (keep, d_recs, d_draw)
+        return canvases
 
     def status_stamp(self, verdict: str, size=(300, 100)) -> torch.Tensor:
         """``create_status_stamp``: the [height, width, 4] BGRA stamp (transparent background, 4-px border, verdict
@@ -1383,7 +1517,7 @@ def _locked(fn):
 # one script thread per session): every public entry point holds the engine's lock while it plans and enqueues.
 for _name in ("resize_batch_u8", "resize_u8", "resize_hp", "reduce_u8", "resize_box_u8", "alpha_premultiply_", "resize_nearest_u8",
               "resize_reducing_u8", "agent_inputs", "plan_batch", "preprocess", "preprocess_dual", "preprocess_host", "preprocess_jpeg", "plan_overlay", "annotate",
-              "heatmap", "plan_heatmap", "heatmap_batch", "side_by_side", "status_stamp", "quality_stats"):
+              "heatmap", "plan_heatmap", "heatmap_batch", "side_by_side", "side_by_side_batch", "status_stamp", "quality_stats"):
     setattr(Engine, _name, _locked(getattr(Engine, _name)))
 del _name
 
