@@ -64,3 +64,24 @@ def test_assess_image_quality_file_semantics(engine, tmp_path):
     same_result(res, Q.assess(frame), 1e-9)
     bad = IQ.assess_image_quality(tmp_path / "missing.png")          # never raises: failed-result dict
     assert bad["quality_passed"] is False and bad["quality_score"] == 0.0 and "Failed to load image" in bad["error"]
+
+
+def test_ring_strips_next_to_partial_strips(engine):
+    """Rows that ARE 16-byte aligned (the bulk-copy ring) with a partial last strip: >= 6 pixels left (the last ring strip
+    takes its right halo from the row), < 6 left (that strip falls back to per-lane loads), and row-padded views whose
+    pitch, not width, carries the alignment."""
+    rng = np.random.default_rng(5)
+    cases = [(90, 1168, 1168), (75, 1028, 1040), (300, 640, 704), (41, 134, 144), (200, 2560, 2560), (33, 1024 + 6, 1040)]
+    frames, views = [], []
+    for h, w, wp in cases:
+        assert (wp * 3) % 16 == 0
+        buf = rng.integers(0, 256, (h, wp, 3), dtype=np.uint8)
+        frames.append(np.ascontiguousarray(buf[:, :w]))
+        views.append(torch.from_numpy(buf).cuda()[:, :w])
+    for v, f, c in zip(views, frames, cases):                      # one by one (tall bands) ...
+        sums, _ = engine.quality_stats([v])
+        assert tuple(int(x) for x in sums[0].cpu().numpy()) == Q.stats(f), c
+    sums, _ = engine.quality_stats(views)                           # ... and as one mixed batch (short bands)
+    host = sums.cpu().numpy()
+    for i, f in enumerate(frames):
+        assert tuple(int(x) for x in host[i]) == Q.stats(f), cases[i]
