@@ -672,7 +672,15 @@ def main():
         configs["quality_stats_1080p"] = leg(lambda: eng.quality_stats(qfr), n_q, n_q * 1080 * 1920 * 3,
                                              note=f"{n_q} 1080p BGR frames per GPU -> sum(gray), sum(lap), sum(lap^2) per frame, exact int64; "
                                              "frame descriptors cached for the repeated batch tensor (like the batch plans); bytes = H*W*3 per frame (read only)")
-        del qfr
+        # the report's comparison panels, one per inspected image, as one batch (two launches)
+        n_p = 256
+        pa = qfr
+        pb = qfr.roll(5, 0).contiguous()
+        panel_bytes = 2 * 1080 * 1920 * 3 + 840 * (1422 + 10 + 1422) * 3
+        configs["comparison_panels_1080p"] = leg(lambda: eng.side_by_side_batch(pa, pb), n_p, n_p * panel_bytes,
+                                                 note=f"{n_p} pairs of 1080p BGR frames -> [840, 2854, 3] side-by-side canvases with header labels "
+                                                 "(cv2.resize arithmetic, bit-exact); host record assembly inside the call; bytes = both frames + canvas")
+        del qfr, pa, pb
         n_h = 64
         hfr, hdef = [], []
         for i in range(n_h):
