@@ -9,8 +9,8 @@
 //         (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.
 // All of it is evaluated with OpenCV's own integer operations, so the result equals cv2's bit for bit.
 //
-// A block owns a 128 x 16 tile of the canvas.  A tile that lies inside ONE bilinear panel takes the two-pass route
-// OpenCV itself takes: the horizontal pass of every source row the tile needs (<= 40), `(r0 >> 4)` as 16-bit values in
+// A block owns a 128 x 32 tile of the canvas.  A tile that lies inside ONE bilinear panel takes the two-pass route
+// OpenCV itself takes: the horizontal pass of every source row the tile needs (<= 56), `(r0 >> 4)` as 16-bit values in
 // shared memory (planar, so both passes are conflict free), then the vertical pass — each source row is interpolated
 // once however many output rows use it, and the per-pixel work is six IMAD.HI instead of twenty-four byte loads.  Every
 // other tile (header, divider, panel borders, copies, the area path) is evaluated pixel by pixel: a thread owns 4
@@ -88,7 +88,14 @@ __device__ __forceinline__ void compose_row4(uint8_t* __restrict__ canvas, int64
     }
 }
 
-constexpr int kTileW = 128, kTileH = 16, kMaxSrcRows = 40;
+#ifndef VIS_PANEL_TILE_H
+#define VIS_PANEL_TILE_H 32
+#endif
+#ifndef VIS_PANEL_SRC_ROWS
+#define VIS_PANEL_SRC_ROWS 56
+#endif
+constexpr int kTileW = 128, kTileH = VIS_PANEL_TILE_H, kMaxSrcRows = VIS_PANEL_SRC_ROWS;
+static_assert(kMaxSrcRows * 3 * kTileW * 2 <= 46 * 1024, "static shared memory");
 
 // the tile at (x0, y0) of a canvas; `hs` = kMaxSrcRows x 3 x kTileW uint16 of shared memory
 __device__ __forceinline__ void compose_tile(uint8_t* __restrict__ canvas, int64_t pitch, int h, int w, int fill,
@@ -122,13 +129,14 @@ __device__ __forceinline__ void compose_tile(uint8_t* __restrict__ canvas, int64
         const int cx = tid & (kTileW - 1);
         const int sx = __ldg(p.xofs + px0 + cx), sx1 = min(sx + 1, p.src_w - 1);      // the weight of sx1 is 0 at the border
         const int a0 = __ldg(p.alpha + 2 * (px0 + cx)), a1 = __ldg(p.alpha + 2 * (px0 + cx) + 1);
-        const uint8_t* c0 = p.src + (int64_t)sx * 3;
-        const uint8_t* c1 = p.src + (int64_t)sx1 * 3;
-        for (int r = tid >> 7; r < n_src; r += 2) {
-            const int64_t row = (int64_t)(sy_first + r) * p.src_pitch;
+        const uint8_t* c0 = p.src + (int64_t)sx * 3 + (int64_t)(sy_first + (tid >> 7)) * p.src_pitch;
+        const uint8_t* c1 = p.src + (int64_t)sx1 * 3 + (int64_t)(sy_first + (tid >> 7)) * p.src_pitch;
+        const int64_t step = 2 * p.src_pitch;
+        uint16_t* o = hs + (tid >> 7) * 3 * kTileW + cx;
+#pragma unroll 2
+        for (int r = tid >> 7; r < n_src; r += 2, c0 += step, c1 += step, o += 6 * kTileW) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                hs[(r * 3 + c) * kTileW + cx] = (uint16_t)(((int)__ldg(c0 + row + c) * a0 + (int)__ldg(c1 + row + c) * a1) >> 4);
+            for (int c = 0; c < 3; ++c) o[c * kTileW] = (uint16_t)(((int)__ldg(c0 + c) * a0 + (int)__ldg(c1 + c) * a1) >> 4);
         }
     }
     __syncthreads();
