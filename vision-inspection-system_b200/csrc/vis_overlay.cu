@@ -233,17 +233,14 @@ k_overlay_copy(const VisOverlayFrame* __restrict__ frames, int channels) {
 #ifndef VIS_OVERLAY_MIN_BLOCKS
 #define VIS_OVERLAY_MIN_BLOCKS 6          // 40 registers: the kernel is latency bound (dependent loads), occupancy pays for a few spills
 #endif
+#ifndef VIS_OVERLAY_WAVES
+#define VIS_OVERLAY_WAVES 16              // > 0: a persistent grid of (resident CTAs x this) walks the tile list; 0: one CTA per tile
+#endif
+// one listed tile; the eight warps of the CTA are autonomous (a warp owns a 32 x 4 sub-tile and never waits for another)
 template <int CN>
-__global__ void __launch_bounds__(kThreads, VIS_OVERLAY_MIN_BLOCKS)
-k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile* __restrict__ tiles,
-                const VisOverlayRef* __restrict__ refs, const VisLeaf* __restrict__ leaves) {
-    __shared__ int s_leaf[kThreads / 32][32][VIS_LEAF_WORDS];
-    __shared__ int s_filter[64];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 64) s_filter[tid] = c_filter[tid];
-    __syncthreads();
-
-    const VisOverlayTile tl = tiles[blockIdx.x];
+__device__ __forceinline__ void draw_tile(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile tl,
+                                          const VisOverlayRef* __restrict__ refs, const VisLeaf* __restrict__ leaves,
+                                          int (*my_leaf)[VIS_LEAF_WORDS], const int* s_filter, int lane, int warp) {
     const VisOverlayFrame f = frames[tl.frame];
     Tile t;
     t.x0 = (tl.txy & 0xffff) * kTileW + (warp & 1) * 32;
@@ -259,7 +256,6 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
     bool loaded = false, dirty = false;
     uint8_t* const px = f.dst + (size_t)y * f.dst_pitch + (size_t)x * CN;
     const bool vec = ((f.dst_pitch | (int64_t)(uintptr_t)f.dst) & 3) == 0;
-    int (*my_leaf)[VIS_LEAF_WORDS] = s_leaf[warp];
 
     auto fetch = [&]() {
         if (CN == 4 && nv == kPx && vec) {
@@ -357,6 +353,21 @@ k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile
     }
 }
 
+template <int CN>
+__global__ void __launch_bounds__(kThreads, VIS_OVERLAY_MIN_BLOCKS)
+k_overlay_tiles(const VisOverlayFrame* __restrict__ frames, const VisOverlayTile* __restrict__ tiles, int n_tiles,
+                const VisOverlayRef* __restrict__ refs, const VisLeaf* __restrict__ leaves) {
+    __shared__ int s_leaf[kThreads / 32][32][VIS_LEAF_WORDS];
+    __shared__ int s_filter[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) s_filter[tid] = c_filter[tid];
+    __syncthreads();
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+        draw_tile<CN>(frames, tiles[ti], refs, leaves, s_leaf[warp], s_filter, lane, warp);
+        __syncwarp();                             // the warp's leaf staging area is reused by its next tile
+    }
+}
+
 }  // namespace
 
 extern "C" int vis_overlay_draw_cn(const VisOverlayFrame* frames, int n_frames, int channels, int copy_frames,
@@ -374,9 +385,19 @@ extern "C" int vis_overlay_draw_cn(const VisOverlayFrame* frames, int n_frames, 
         if (rc != VIS_OK) return rc;
     }
     if (n_tiles > 0) {
-        if (channels == 3)      k_overlay_tiles<3><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
-        else if (channels == 4) k_overlay_tiles<4><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);
-        else                    k_overlay_tiles<kRecord><<<n_tiles, kThreads, 0, st>>>(frames, tiles, refs, leaves);   // stamp recording
+        int grid = n_tiles;
+#if VIS_OVERLAY_WAVES > 0
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        }
+        grid = n_tiles < sms * VIS_OVERLAY_MIN_BLOCKS * VIS_OVERLAY_WAVES ? n_tiles : sms * VIS_OVERLAY_MIN_BLOCKS * VIS_OVERLAY_WAVES;
+#endif
+        if (channels == 3)      k_overlay_tiles<3><<<grid, kThreads, 0, st>>>(frames, tiles, n_tiles, refs, leaves);
+        else if (channels == 4) k_overlay_tiles<4><<<grid, kThreads, 0, st>>>(frames, tiles, n_tiles, refs, leaves);
+        else                    k_overlay_tiles<kRecord><<<grid, kThreads, 0, st>>>(frames, tiles, n_tiles, refs, leaves);   // stamp recording
         return vis::check_launch("vis_overlay_draw");
     }
     return VIS_OK;
