@@ -215,7 +215,9 @@ typedef struct VisSched {            /* opaque to callers: filled by vis_sched_b
     int32_t out_mode;                /* VIS_SCHED_OUT_PIXEL_VALUES or VIS_SCHED_OUT_U8                              */
     int32_t h_pull;                  /* 1: 17..32 taps, the horizontal role pulls its window (no step masks)        */
     int32_t n_vwarps;                /* 16-slot kernel: vertical-pass warps of the launch (6 / 4 / 3: fewer for strong downscales) */
-    int32_t dp_words;                /* > 0: packed-byte kernel (vis_fused_dp.cu), W words of 4 taps per window (4..9)  */
+    int32_t dp_words;                /* > 0: packed-byte kernels (vis_fused_dp.cu / vis_fused_mma.cu), W words of 4 taps per window (4..9) */
+    int32_t mma_ks;                  /* > 0: integer tensor-path kernel (vis_fused_mma.cu); 32-pixel k-steps per tile of 8 output columns */
+    int32_t reserved0;               /* keeps the arrays below 8-byte aligned                                            */
     VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
     VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_MAX_SUBS];
     VisSchedSeg   seg[VIS_SCHED_MAX_SEGS];
@@ -231,6 +233,10 @@ typedef struct VisFrameRef {         /* per frame of a scheduled launch (device 
 #define VIS_SCHED_OUT_U8           1   /* resized RGB uint8 HWC (dst_w multiple of 4): Image.resize / thumbnails      */
 #define VIS_SCHED_FLAG_DP4A    0x100   /* OR-ed into out_mode: serve 9+ tap geometries with the packed-byte (IDP.4A) kernel
                                           instead of the 16-slot IMAD kernel (same results; the faster one where measured) */
+
+#define VIS_SCHED_FLAG_MMA     0x200   /* OR-ed into out_mode: serve 9+ tap geometries with the integer tensor-path kernel
+                                          (mma.sync u8 x 8-bit limbs -> s32, same limb arithmetic and results as the packed-byte
+                                          kernel; falls back to it when a tile's window exceeds three k-steps)            */
 
 /* sizeof(VisSched), for bindings that treat it as an opaque byte buffer                  [host] */
 int vis_sched_sizeof(void);
@@ -250,6 +256,12 @@ int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds
 int vis_sched_record_stride_dp(int words);
 int vis_sched_pack_records_dp(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int words,
                               int32_t* rec, int64_t rec_capacity);
+/* records for the integer tensor-path kernel (sched.mma_ks > 0): the limb rows of vis_sched_pack_records_dp followed by
+ * two int32: the absolute 4-sample word index of record byte 0 ((end >> 2) - (words - 1)) and of the window's first tap
+ * (first >> 2).  rec: (out_size + 1) * vis_sched_record_stride_mma(words) int32.             [host] */
+int vis_sched_record_stride_mma(int words);
+int vis_sched_pack_records_mma(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int words,
+                               int32_t* rec, int64_t rec_capacity);
 /* frames: DEVICE array; hrec / vrec: DEVICE records from vis_sched_pack_records.        [device] */
 int vis_preprocess_fused_sched(const VisSched* sched, const VisFrameRef* frames, int n_frames,
                                const int32_t* hrec, const int32_t* vrec,

@@ -91,9 +91,9 @@ def test_overlay_random_frames_and_boxes(engine):
         assert np.array_equal(d.cpu().numpy(), OV.draw_bounding_boxes(f, b)), (k, f.shape, "in place")
 
 
-def test_both_kernel_families_for_long_windows(engine):
-    """9+ tap geometries are served by the packed-byte (IDP.4A) kernel by default and by the 16-slot IMAD kernel on
-    request: both bit-exact against the oracle — 4K at the default max_pixels (13 taps), bicubic 2x downscales, the
+def test_all_kernel_families_for_long_windows(engine):
+    """9+ tap geometries are served by the integer tensor-path (IMMA) kernel by default, by the packed-byte (IDP.4A) kernel
+    and by the 16-slot IMAD kernel on request: all bit-exact against the oracle — 4K at the default max_pixels (13 taps), bicubic 2x downscales, the
     agents' LANCZOS thumbnails (13 and 25 taps), odd segment counts."""
     frames4k = [synth.noise_frame(4000 + i, 2160, 3840) for i in range(3)]
     want4k, wgrid = Q.preprocess(frames4k)
@@ -102,8 +102,8 @@ def test_both_kernel_families_for_long_windows(engine):
     thumbs = [(2160, 3840, 2048), (2160, 3840, 1024), (1080, 1920, 1024), (1600, 2560, 1024), (1234, 3008, 1024)]
     tframes = [synth.noise_frame(4200 + i, h, w) for i, (h, w, _) in enumerate(thumbs)]
     try:
-        for dp in (True, False):
-            engine.use_dp4a(dp)
+        for dp in ((True, True), (True, False), (False, False)):
+            engine.use_dp4a(*dp)
             pv, grid = engine.preprocess(torch.from_numpy(np.stack(frames4k)).cuda())
             assert np.array_equal(grid.numpy(), wgrid) and np.array_equal(pv.cpu().numpy(), want4k), ("4k", dp)
             plan = engine.plan_batch(torch.from_numpy(np.stack(frames4k)).cuda())
@@ -115,4 +115,4 @@ def test_both_kernel_families_for_long_windows(engine):
                 assert engine.last_launches == 1, (h, w, limit, dp)
                 assert np.array_equal(got.cpu().numpy(), Q.agent_thumbnail(f, limit)), (h, w, limit, dp)
     finally:
-        engine.use_dp4a(True)
+        engine.use_dp4a(True, True)

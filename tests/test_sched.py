@@ -227,3 +227,109 @@ def test_packed_byte_records(shape, out, filt, mode, want_words):
             acc = (1 << 21) + int((px * k0[o]).sum()) + (int((px * k1[o]).sum()) << 8) + (int((px * k2[o]).sum()) << 16)
             want = (1 << 21) + int((line[first:first + taps] * t.k[o, :taps]).sum())
             assert acc == want
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Integer tensor-path kernel (vis_fused_mma.cu): replay of its fragment indexing on the CPU.  The device gathers the B
+# operand of the horizontal pass and the A operand of the vertical pass from compact per-sample records
+# (vis_sched_pack_records_mma) by word arithmetic; this replays exactly that arithmetic in numpy and compares the banded
+# products with Pillow's definition  clip8((sum k * p + 2^21) >> 22).
+def _mma_records(table, words):
+    L = N.lib()
+    stride = L.vis_sched_record_stride_mma(words)
+    assert stride >= 3 * words + 2 and stride % 4 == 0
+    rec = np.zeros((table.out_size + 1, stride), np.int32)
+    assert L.vis_sched_pack_records_mma(table.out_size, N.i32ptr(table.k), N.i32ptr(table.bounds), table.ksize, words,
+                                        N.i32ptr(rec), rec.size) == N.VIS_OK
+    return rec
+
+
+def _limb_rows(rec_row, words):
+    """(3, 4 * words) int64: the limb bytes of one record; limb 2 is signed."""
+    b = rec_row[:3 * words].view(np.uint8).reshape(3, 4 * words).astype(np.int64)
+    b[2] = b[2].astype(np.uint8).astype(np.int8)
+    return b
+
+
+def _direct_pass(table, line):
+    """Pillow's 8bpc pass along the last axis of `line` ([..., in_size] uint8) by definition."""
+    out = np.zeros(line.shape[:-1] + (table.out_size,), np.uint8)
+    for o in range(table.out_size):
+        f, n = table.bounds[o]
+        acc = (line[..., f:f + n].astype(np.int64) * table.k[o, :n].astype(np.int64)).sum(-1) + (1 << 21)
+        out[..., o] = np.clip(acc >> 22, 0, 255)
+    return out
+
+
+@pytest.mark.parametrize("src_h,src_w,dst_h,dst_w,filt,mode", [
+    (2160, 3840, 756, 1316, N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES),      # 4K at the default max_pixels
+    (2160, 3840, 576, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),                # Auditor thumbnail, 25 taps
+    (1080, 1920, 576, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),
+    (700, 1000, 252, 364, N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES),
+])
+def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
+    pitch = (src_w * 3 + 15) // 16 * 16
+    rc, sc, ht, vt = build(src_h, src_w, dst_h, dst_w, pitch, 3, filt, mode | N.SCHED_FLAG_MMA)
+    assert rc == N.VIS_OK
+    head = sc["head"]
+    W, KS = int(head["dp_words"]), int(head["mma_ks"])
+    assert 4 <= W <= 9 and 1 <= KS <= 3 and head["ring"] == 16
+    hrec, vrec = _mma_records(ht, W), _mma_records(vt, W)
+    rng = np.random.default_rng(5)
+
+    # ---- horizontal pass: tiles of 8 outputs per strip, B gathered from the records, K = 32 * KS pixels from word kw ----
+    row = rng.integers(0, 256, src_w + 4 * 8 * KS + 64, dtype=np.uint8)       # reads past the row meet zero coefficients
+    row[src_w:] = 255
+    want = _direct_pass(ht, row[:src_w])
+    got = np.zeros(dst_w, np.uint8)
+    for S in sc["strip"][:head["n_strips"]]:
+        x0, x1, px0 = int(S["x0"]), int(S["x1"]), int(S["px0"])
+        sw = x1 - x0
+        for jt in range((sw + 7) // 8):
+            kw = int(hrec[x0 + 8 * jt, 3 * W + 1])
+            assert 4 * kw >= px0
+            for g in range(8):
+                xr = x0 + min(8 * jt + g, sw - 1)
+                bw = int(hrec[xr, 3 * W])
+                limbs = _limb_rows(hrec[xr], W)
+                col = np.zeros((3, 32 * KS), np.int64)
+                for wd in range(8 * KS):                                        # word of the k window: kw + 8s + 4h + t
+                    q = kw + wd - bw
+                    if 0 <= q < W:
+                        col[:, 4 * wd:4 * wd + 4] = limbs[:, 4 * q:4 * q + 4]
+                px = row[4 * kw:4 * kw + 32 * KS].astype(np.int64)
+                acc = (px * col[0]).sum() + ((px * col[1]).sum() << 8) + ((px * col[2]).sum() << 16) + (1 << 21)
+                if 8 * jt + g < sw:
+                    got[xr] = np.clip(acc >> 22, 0, 255)
+    assert np.array_equal(got, want)
+
+    # ---- vertical pass: chunks of 32 ring rows + carry, A gathered from the chunk's records relative to ring byte 0 ----
+    carry = 4 * (W - 1)
+    col_px = rng.integers(0, 256, (5, src_h), dtype=np.uint8)
+    want_v = _direct_pass(vt, col_px)
+    got_v = np.zeros((5, dst_h), np.uint8)
+    for G_ in sc["seg"][:head["n_segs"]]:
+        y0, y1, r_first, r_end, moff = (int(G_[k]) for k in ("y0", "y1", "r_first", "r_end", "mask_off"))
+        yo = y0
+        for c in range((r_end - r_first + 31) // 32):
+            r0 = r_first + 32 * c
+            n = sum(bin(read_mask(sc["mask"], moff, 2 * c + i, 16)[0]).count("1") for i in range(2))
+            assert n <= 32
+            cbw = (r0 - carry) >> 2
+            ring = np.zeros((5, 64), np.int64)                                   # ring bytes of a column: rows r0 - carry ...
+            for b in range(64):
+                rr = r0 - carry + b
+                ring[:, b] = col_px[:, rr] if 0 <= rr < src_h else 255           # garbage wherever no real row sits
+            for i in range(n):
+                rel = int(vrec[yo + i, 3 * W]) - cbw
+                limbs = _limb_rows(vrec[yo + i], W)
+                a = np.zeros((3, 64), np.int64)
+                for wd in range(16):                                             # ring word 8s + 4h + t
+                    q = wd - rel
+                    if 0 <= q < W:
+                        a[:, 4 * wd:4 * wd + 4] = limbs[:, 4 * q:4 * q + 4]
+                acc = (ring * a[0]).sum(1) + ((ring * a[1]).sum(1) << 8) + ((ring * a[2]).sum(1) << 16) + (1 << 21)
+                got_v[:, yo + i] = np.clip(acc >> 22, 0, 255)
+            yo += n
+        assert yo == y1
+    assert np.array_equal(got_v, want_v)

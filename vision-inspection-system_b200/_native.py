@@ -44,9 +44,10 @@ FRAME_REF_DTYPE = np.dtype([("src", np.uint64), ("row0", np.int64)], align=True)
 SCHED_HEAD_DTYPE = np.dtype([("src_h", np.int32), ("src_w", np.int32), ("dst_h", np.int32), ("dst_w", np.int32),
                              ("src_pitch", np.int64), ("kt", np.int32), ("n_strips", np.int32), ("n_segs", np.int32),
                              ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("per_index", np.int32), ("ring", np.int32),
-                             ("n_subs", np.int32), ("out_mode", np.int32), ("h_pull", np.int32), ("n_vwarps", np.int32), ("dp_words", np.int32)], align=True)
+                             ("n_subs", np.int32), ("out_mode", np.int32), ("h_pull", np.int32), ("n_vwarps", np.int32), ("dp_words", np.int32), ("mma_ks", np.int32), ("reserved0", np.int32)], align=True)
 SCHED_OUT_PIXEL_VALUES, SCHED_OUT_U8 = 0, 1
 SCHED_FLAG_DP4A = 0x100
+SCHED_FLAG_MMA = 0x200
 RESIZE_REF_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64)], align=True)
 
 assert FRAME_DTYPE.itemsize == 56 and STRIP_DTYPE.itemsize == 20 and BOX_DTYPE.itemsize == 32
@@ -86,7 +87,7 @@ EXPORTS = [
     "vis_resample_h_u8", "vis_resample_v_u8", "vis_normalize_patchify",
     "vis_max_taps", "vis_fused_kt_class", "vis_record_stride", "vis_pack_records", "vis_fused_supported",
     "vis_plan_strips_max", "vis_plan_strips", "vis_preprocess_fused",
-    "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_sched_record_stride_dp", "vis_sched_pack_records_dp", "vis_preprocess_fused_sched", "vis_preprocess_fused_sched_dup",
+    "vis_sched_sizeof", "vis_sched_build", "vis_sched_pack_records", "vis_sched_record_stride_dp", "vis_sched_pack_records_dp", "vis_sched_record_stride_mma", "vis_sched_pack_records_mma", "vis_preprocess_fused_sched", "vis_preprocess_fused_sched_dup",
     "vis_resize_fused_sched",
     "vis_overlay_expand", "vis_overlay_tiles", "vis_overlay_plan_batch", "vis_overlay_draw", "vis_quality_stats", "vis_heatmap_batch",
     "vis_resize_linear_mode", "vis_linear_table", "vis_compose_panels", "vis_compose_panels_batch", "vis_text_size", "vis_draw_expand", "vis_overlay_draw_cn", "vis_overlay_sprite_expand", "vis_overlay_stamp_expand", "vis_overlay_plan_batch_sprites",
@@ -204,6 +205,8 @@ def _declare(L: C.CDLL) -> None:
     L.vis_sched_pack_records.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_int, i32p, C.c_int64]
     L.vis_sched_record_stride_dp.argtypes = [C.c_int]
     L.vis_sched_pack_records_dp.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, C.c_int64]
+    L.vis_sched_record_stride_mma.argtypes = [C.c_int]
+    L.vis_sched_pack_records_mma.argtypes = [C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, C.c_int64]
     L.vis_preprocess_fused_sched.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.vis_preprocess_fused_sched_dup.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.vis_overlay_expand.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]

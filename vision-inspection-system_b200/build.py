@@ -26,7 +26,7 @@ LIB_PATH = PKG_DIR / "libvis_b200.so"
 OBJ_DIR = PKG_DIR.parent / "build" / "obj"
 
 SOURCES = ["vis_host.cpp", "vis_generic.cu", "vis_fused_ws.cu", "vis_fused_sched.cu", "vis_fused_sched16.cu",
-           "vis_fused_dp.cu", "vis_overlay_host.cpp", "vis_overlay.cu", "vis_quality.cu", "vis_heatmap.cu", "vis_compose.cu",
+           "vis_fused_dp.cu", "vis_fused_mma.cu", "vis_overlay_host.cpp", "vis_overlay.cu", "vis_quality.cu", "vis_heatmap.cu", "vis_compose.cu",
            "vis_jpeg.cpp"]
 
 NVCC_FLAGS = [

@@ -1,0 +1,537 @@
+// vis_fused_mma.cu — statically scheduled, warp-specialised kernel for 9..33-tap windows: both Pillow passes as banded
+// u8 x 8-bit-limb matrix products on the integer tensor path (mma.sync.m16n8k32 .s32.u8.{u8,s8}, SASS IMMA.16832).
+//
+// Same path and arithmetic as vis_fused_dp.cu (Pillow 8bpc horizontal pass -> uint8 -> vertical pass -> uint8, then either
+// LUT + Qwen2-VL patch layout or RGB uint8 rows), same loader / store roles, mbarrier rings, VisSched and coefficient
+// limbs k = k0 + 2^8 k1 + 2^16 k2 (k0, k1 unsigned, k2 signed), so that
+//     sum p*k = sum p*k0 + 2^8 sum p*k1 + 2^16 sum p*k2      (mod 2^32 = Pillow's int32 accumulator, exactly).
+// Why it exists (tools/ubench_imma.cu -> profiles/r02_ubench_imma.jsonl): strong downscales are not HBM bound on CUDA
+// cores — IDP.4A issues at 62 lanes / clk / SM = 248 byte MACs, the packed-byte kernel sits at 0.52 of that and at 0.2-0.5
+// of the HBM roofline — while IMMA.16832 issues every 2 clocks per SM = 2037 byte MACs / clk / SM, 8.2x, with LDS free next
+// to it.  A resampling pass IS a (banded) matrix product, out = C x in; per 8 outputs the band is 2-3 k-steps of 32 wide.
+//   H  (8 warps)  warp = every 8th tile of 8 output pixels, all 32 rows of the chunk (two M-tiles of 16 rows).
+//                 A = staged pixels [row][32 input pixels of one channel]: 3 x LDS.32 + 6 PRMT de-interleave 4 pixels of the
+//                 three channels; the stage rows are skewed by 16 bytes per 4 rows so that lanes (row 4g+j, word 3t+w) never
+//                 share a bank.  B = coefficient limbs [32 input pixels][8 outputs], gathered by predicated LDS.32 from
+//                 the same compact per-output records the packed-byte kernel uses (W words per limb + the window's first
+//                 word index), shared by both M-tiles and the three channels.  M index m <-> chunk row 4g + {0,1} (tile 0)
+//                 / 4g + {2,3} (tile 1): a thread ends up with rows 4g..4g+3 of two output columns per channel = one
+//                 STS.32 each into the TRANSPOSED H ring [channel][column][row].
+//   V  (4 warps)  warp = every 4th tile of 8 ring columns.  A = coefficient limbs [16 output rows][64 ring rows] from the
+//                 chunk's vertical records (once per chunk and M-tile), B = ring words (4 consecutive rows of a column:
+//                 exactly the fragment layout, LDS.32, column pitch = 4 mod 8 words: conflict free), 6 IMMA per tile.
+//   epilogue      acc0 (preloaded with 2^21) + (acc1 << 8) + (acc2 << 16), >> 22, I2IP.U8.S32.SAT packs two samples.
+#include "vis_fused_common.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace visf;
+
+namespace {
+
+#ifndef VIS_MMA_HWARPS
+#define VIS_MMA_HWARPS 8
+#endif
+#ifndef VIS_MMA_VWARPS
+#define VIS_MMA_VWARPS 4
+#endif
+#ifndef VIS_MMA_SWARPS
+#define VIS_MMA_SWARPS 2
+#endif
+constexpr int kHWarps = VIS_MMA_HWARPS, kVWarps = VIS_MMA_VWARPS, kSWarps = VIS_MMA_SWARPS;
+// warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
+constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
+constexpr int kThreads = (kHWarps + kVWarps + kSWarps + 1) * 32;
+constexpr int kChunk = 32;
+constexpr int kVRecs = kChunk + 1;                // vertical records a chunk can touch (scale >= 1): 32 emits + 1 look-ahead
+constexpr int kSmemMax = 227 * 1024;
+constexpr int kStageSkew = 128;                   // 16 bytes x (row >> 2): 112 bytes of slack per slot
+
+enum Bar { SF = 0, SE = 2, HF = 4, HE = 6, VF = 8, OF = 10, OE = 12, kBars = 14 };   // full/empty pairs, two slots each
+
+// words per record: 3 limb rows of W words, then the absolute word index of record byte 0 and of the window's first tap
+__host__ __device__ constexpr int rec_stride_mma(int W) { return (3 * W + 2 + 3) & ~3; }
+
+struct LayoutM {
+    int stage_pitch, stage_slot, hrec_slot, vrec_slot;
+    int cpitch, hplane;          // H ring: bytes per (channel, column) = carry rows + 32 fresh rows, padded to 4 mod 8 words
+    int opitch, oplane;          // band tile: bytes per row (strip width), bytes per channel plane (14 rows)
+    int off_stage, off_hring, off_otile, off_hrec, off_vrec, off_lut, off_bar, total;
+};
+
+inline LayoutM make_layout_m(int stage_pitch, int strip_w, int W) {
+    const int stride = rec_stride_mma(W);
+    LayoutM L;
+    L.stage_pitch = stage_pitch;
+    L.stage_slot = kChunk * stage_pitch + kStageSkew;
+    L.hrec_slot = align_up((strip_w + 1) * stride * 4, 16);
+    L.vrec_slot = align_up(kVRecs * stride * 4, 16);
+    int cw = W - 1 + kChunk / 4;                   // carry words + fresh words
+    while (cw % 8 != 4) ++cw;
+    L.cpitch = 4 * cw;
+    L.hplane = strip_w * L.cpitch;
+    L.opitch = strip_w;
+    L.oplane = VIS_PATCH * L.opitch;
+    int off = 0;
+    L.off_stage = off; off += 2 * L.stage_slot;
+    L.off_hring = off; off += 2 * 3 * L.hplane + 64;      // a k-step reads 64 bytes of a column whatever its pitch
+    L.off_otile = off; off += 2 * 3 * L.oplane;
+    off = align_up(off, 16);
+    L.off_hrec = off;  off += 2 * L.hrec_slot;
+    L.off_vrec = off;  off += 2 * L.vrec_slot;
+    L.off_lut = off;   off += 768 * 4;
+    L.off_bar = off;   off += kBars * 8;
+    L.total = off;
+    return L;
+}
+
+__device__ __forceinline__ void imma_uu(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void imma_us(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// coefficient limbs as the A operand (vertical pass): unsigned / signed limb rows x u8 ring bytes
+__device__ __forceinline__ void imma_uu_a(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { imma_uu(d, a, b0, b1); }
+__device__ __forceinline__ void imma_su_a(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (c << 16) | (sat_u8(hi) << 8) | sat_u8(lo)      (I2IP.U8.S32.SAT)
+__device__ __forceinline__ uint32_t pack_sat(int hi, int lo, uint32_t c) {
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(c));
+    return d;
+}
+// Pillow's (acc + 2^21) >> 22 with the rounding constant already inside limb 0's accumulator
+__device__ __forceinline__ int recombine(int a0, int a1, int a2) { return (a0 + (a1 << 8) + (a2 << 16)) >> VIS_PRECISION_BITS; }
+
+struct FramePtrs { const unsigned char* src; long long second; };      // VisFrameRef / VisResizeRef: same layout
+
+template <int KS, bool U8>
+__global__ void __launch_bounds__(kThreads, 1)
+k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ frames, int n_items,
+            const __grid_constant__ LayoutM L, long long dst_pitch, const int* __restrict__ hrec_g,
+            const int* __restrict__ vrec_g, const float* __restrict__ lut768, float* __restrict__ pixel_values) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = sc.dp_words;
+    const int STRIDE = rec_stride_mma(W);
+    const int CARRY = 4 * (W - 1);                     // rows of the previous chunk a window may reach back to
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;             // fragment coordinates of mma.m16n8k32
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);               // warp-uniform for the compiler
+    float* lut = reinterpret_cast<float*>(smem + L.off_lut);              // transposed: lut[c * 256 + v]
+    const uint32_t bar0 = smem_u32(smem + L.off_bar);
+    auto bar = [&](int which, int slot) { return bar0 + (uint32_t)(which + slot) * 8; };
+    const int per_frame = sc.n_strips * sc.n_segs;
+
+    if (!U8)
+        for (int i = tid; i < 768; i += (int)blockDim.x) lut[(i % 3) * 256 + i / 3] = __ldg(lut768 + i);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(SF, s), 1);
+            mbar_init(bar(SE, s), kHWarps);
+            mbar_init(bar(HF, s), kHWarps);
+            mbar_init(bar(HE, s), kVWarps);
+            mbar_init(bar(VF, s), 1);
+            mbar_init(bar(OF, s), kVWarps);
+            mbar_init(bar(OE, s), kSWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();                                   // the only CTA-wide barrier
+
+    if (warp == kLBase) {
+        // ============================== loader ==============================
+        int k = 0, sl = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++sl) {
+            const int f = w / per_frame, r = w - f * per_frame;
+            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+            const VisSchedStrip S = sc.strip[st];
+            const VisSchedSeg G = sc.seg[sg];
+            const unsigned char* src = frames[f].src + (size_t)S.px0 * 3;
+            const uint32_t rec_bytes = (uint32_t)(S.x1 - S.x0 + 1) * STRIDE * 4;
+            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            int yo = G.y0;
+            for (int c = 0; c < n_chunks; ++c, ++k) {
+                const int slot = k & 1;
+                const uint32_t prev = ((k >> 1) - 1) & 1;
+                if (k >= 2) mbar_wait(bar(SE, slot), prev);                 // H is done with the stage slot
+                const int r0 = G.r_first + c * kChunk;
+                const int rows = max(0, min(kChunk, sc.src_h - r0));        // r_end may include virtual rows past the image
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(bar(SF, slot), (uint32_t)rows * (uint32_t)S.row_bytes + (c == 0 ? rec_bytes : 0u));
+                }
+                __syncwarp();
+                unsigned char* stage = smem + L.off_stage + slot * L.stage_slot;
+                if (lane < rows)                                            // row r sits 16 * (r >> 2) bytes to the right
+                    bulk_g2s(smem_u32(stage + lane * L.stage_pitch + 16 * (lane >> 2)), src + (size_t)(r0 + lane) * sc.src_pitch,
+                             (uint32_t)S.row_bytes, bar(SF, slot));
+                if (c == 0 && lane == 0)
+                    bulk_g2s(smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot), hrec_g + (size_t)S.x0 * STRIDE,
+                             rec_bytes, bar(SF, slot));
+                if (k >= 2) mbar_wait(bar(HE, slot), prev);                 // V is done with the record slot
+                if (lane == 0) {
+                    const uint32_t vbytes = (uint32_t)min(kVRecs, sc.dst_h + 1 - yo) * STRIDE * 4;
+                    fence_proxy_async();
+                    mbar_expect_tx(bar(VF, slot), vbytes);
+                    bulk_g2s(smem_u32(smem + L.off_vrec + slot * L.vrec_slot), vrec_g + (size_t)yo * STRIDE, vbytes,
+                             bar(VF, slot));
+                }
+                // 2 groups x (16-bit first-sample mask, 16-bit second-sample mask: never set here) per chunk
+                const uint32_t* m8 = reinterpret_cast<const uint32_t*>(sc.mask + G.mask_off + c * 8);
+                yo += __popc(m8[0]) + __popc(m8[1]);
+            }
+        }
+    } else if (warp < kHBase + kHWarps) {
+        // ============================== horizontal pass ==============================
+        const int hw = warp - kHBase;
+        int k = 0, sl = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++sl) {
+            const int f = w / per_frame, r = w - f * per_frame;
+            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+            const VisSchedStrip S = sc.strip[st];
+            const VisSchedSeg G = sc.seg[sg];
+            const int sw = S.x1 - S.x0;
+            const int n_tiles = (sw + 7) >> 3;
+            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            const uint32_t hrec0 = smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot);
+            for (int c = 0; c < n_chunks; ++c, ++k) {
+                const int slot = k & 1, j = k >> 1;
+                mbar_wait(bar(SF, slot), j & 1);
+                if (k >= 2) mbar_wait(bar(HE, slot), (j - 1) & 1);
+                // this lane's rows 4g..4g+3 of the stage slot (skewed) and of the ring columns it stores
+                const uint32_t srow = smem_u32(smem + L.off_stage + slot * L.stage_slot) + (uint32_t)(4 * g * L.stage_pitch + 16 * g);
+                const uint32_t hring = smem_u32(smem + L.off_hring + slot * 3 * L.hplane) + (uint32_t)(CARRY + 4 * g);
+#pragma unroll 1
+                for (int jt = hw; jt < n_tiles; jt += kHWarps) {
+                    // ---- B: coefficient limbs of the tile's 8 outputs, 32 input pixels per k-step ----
+                    const int xr = min(8 * jt + g, sw - 1);                              // output column of this lane's B column
+                    const uint32_t rec = hrec0 + (uint32_t)(xr * STRIDE * 4);
+                    const int bw = (int)lds32(rec + (uint32_t)(3 * W * 4));
+                    const int kw = __shfl_sync(0xffffffffu, (int)lds32(rec + (uint32_t)((3 * W + 1) * 4)), 0);   // first word of the tile's window
+                    uint32_t b[KS][3][2];
+#pragma unroll
+                    for (int s = 0; s < KS; ++s)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int q = kw + 8 * s + 4 * h + t - bw;
+                            const bool ok = (unsigned)q < (unsigned)W;
+#pragma unroll
+                            for (int l = 0; l < 3; ++l) b[s][l][h] = ok ? lds32(rec + (uint32_t)((l * W + q) * 4)) : 0u;
+                        }
+                    // raw bytes of pixel (4 * (kw + t)) of the stage row, relative to the row start
+                    const uint32_t px_off = (uint32_t)((4 * (kw + t) - S.px0) * 3);
+                    uint32_t pk[3][2];                                                   // rows 4g+2, 4g+3 of columns 2t, 2t+1 per channel
+#pragma unroll
+                    for (int mt = 1; mt >= 0; --mt) {
+                        int acc[3][3][4];
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { acc[ch][0][e] = 1 << (VIS_PRECISION_BITS - 1); acc[ch][1][e] = 0; acc[ch][2][e] = 0; }
+                        const uint32_t r0a = srow + (uint32_t)(2 * mt * L.stage_pitch) + px_off;     // row 4g + 2mt
+                        const uint32_t r1a = r0a + (uint32_t)L.stage_pitch;                          // row 4g + 2mt + 1
+#pragma unroll
+                        for (int s = 0; s < KS; ++s) {
+                            uint32_t a[3][4];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t o = (uint32_t)((32 * s + 16 * h) * 3);
+                                const uint32_t x0 = lds32(r0a + o), x1 = lds32(r0a + o + 4), x2 = lds32(r0a + o + 8);
+                                const uint32_t y0 = lds32(r1a + o), y1 = lds32(r1a + o + 4), y2 = lds32(r1a + o + 8);
+                                a[0][2 * h] = __byte_perm(__byte_perm(x0, x1, 0x0630), x2, 0x5210);
+                                a[1][2 * h] = __byte_perm(__byte_perm(x0, x1, 0x0741), x2, 0x6210);
+                                a[2][2 * h] = __byte_perm(__byte_perm(x0, x1, 0x0052), x2, 0x7410);
+                                a[0][2 * h + 1] = __byte_perm(__byte_perm(y0, y1, 0x0630), y2, 0x5210);
+                                a[1][2 * h + 1] = __byte_perm(__byte_perm(y0, y1, 0x0741), y2, 0x6210);
+                                a[2][2 * h + 1] = __byte_perm(__byte_perm(y0, y1, 0x0052), y2, 0x7410);
+                            }
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) {
+                                imma_uu(acc[ch][0], a[ch], b[s][0][0], b[s][0][1]);
+                                imma_uu(acc[ch][1], a[ch], b[s][1][0], b[s][1][1]);
+                                imma_us(acc[ch][2], a[ch], b[s][2][0], b[s][2][1]);
+                            }
+                        }
+                        // D: e = 0/1 -> (row 4g+2mt, columns 2t / 2t+1), e = 2/3 -> (row 4g+2mt+1, columns 2t / 2t+1)
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            int v[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = recombine(acc[ch][0][e], acc[ch][1][e], acc[ch][2][e]);
+                            if (mt == 1) {
+                                pk[ch][0] = pack_sat(v[2], v[0], 0u);
+                                pk[ch][1] = pack_sat(v[3], v[1], 0u);
+                            } else {
+                                pk[ch][0] = pack_sat(v[2], v[0], pk[ch][0]);             // bytes: rows 4g, 4g+1, 4g+2, 4g+3
+                                pk[ch][1] = pack_sat(v[3], v[1], pk[ch][1]);
+                            }
+                        }
+                    }
+                    const int xc = 8 * jt + 2 * t;                                       // strip widths are multiples of 4
+                    if (xc < sw) {
+                        const uint32_t at = hring + (uint32_t)(xc * L.cpitch);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            sts32(at + (uint32_t)(ch * L.hplane), pk[ch][0]);
+                            sts32(at + (uint32_t)(ch * L.hplane + L.cpitch), pk[ch][1]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(SE, slot));          // stage slot may be refilled
+                    mbar_arrive(bar(HF, slot));          // H-ring slot is complete
+                }
+            }
+        }
+    } else if (warp >= kVBase) {
+        // ============================== vertical pass ==============================
+        const int wv = warp - kVBase;
+        int k = 0, nb = 0, ready = 1;                      // bands 0 and 1 find their slots empty
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int f = w / per_frame, r = w - f * per_frame;
+            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+            const VisSchedStrip S = sc.strip[st];
+            const VisSchedSeg G = sc.seg[sg];
+            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            const int sw = S.x1 - S.x0, NC = 3 * sw;
+            const int n_tiles = (NC + 7) >> 3;
+            const int seg_rows = G.y1 - G.y0;
+            const uint8_t* const gm = sc.mask + G.mask_off;
+            const uint32_t otile0 = smem_u32(smem + L.off_otile);
+            int ycount = 0;                                // output rows of the segment emitted so far
+            for (int c = 0; c < n_chunks; ++c, ++k) {
+                const int slot = k & 1, j = k >> 1;
+                mbar_wait(bar(VF, slot), j & 1);
+                mbar_wait(bar(HF, slot), j & 1);
+                const uint32_t vrec0 = smem_u32(smem + L.off_vrec + slot * L.vrec_slot);
+                const uint32_t ring0 = smem_u32(smem + L.off_hring + slot * 3 * L.hplane);
+                const uint32_t* m8 = reinterpret_cast<const uint32_t*>(gm + c * 8);
+                const int n = __popc(m8[0]) + __popc(m8[1]);           // output rows whose window ends in this chunk
+                const int cbw = (G.r_first + c * kChunk - CARRY) >> 2;  // absolute word index of ring byte 0
+#pragma unroll 1
+                for (int mt = 0; 16 * mt < n; ++mt) {
+                    const int ihi = min(n, 16 * mt + 16);
+                    // ---- A: coefficient limbs [16 output rows][64 ring rows] of this M-tile ----
+                    uint32_t a[2][3][4];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {                     // rows 16 mt + g and 16 mt + g + 8
+                        const int i = 16 * mt + g + 8 * hh;
+                        const uint32_t rec = vrec0 + (uint32_t)(min(i, kVRecs - 1) * STRIDE * 4);
+                        const int rel = (int)lds32(rec + (uint32_t)(3 * W * 4)) - cbw;
+#pragma unroll
+                        for (int s = 0; s < 2; ++s)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int q = 8 * s + 4 * h + t - rel;
+                                const bool ok = i < ihi && (unsigned)q < (unsigned)W;
+#pragma unroll
+                                for (int l = 0; l < 3; ++l) a[s][l][2 * h + hh] = ok ? lds32(rec + (uint32_t)((l * W + q) * 4)) : 0u;
+                            }
+                    }
+                    const int bfirst = (ycount + 16 * mt) / VIS_PATCH, blast = (ycount + ihi - 1) / VIS_PATCH;
+#pragma unroll 1
+                    for (int bs = bfirst; bs <= blast; bs += 2) {        // at most two bands per pass: both slots, never a third
+                        const int be = min(bs + 1, blast);
+                        while (ready < nb + be) {
+                            ++ready;
+                            mbar_wait(bar(OE, ready & 1), ((ready >> 1) - 1) & 1);
+                        }
+                        // where this thread's two rows go (byte offset into the band tile of column 0, channel 0)
+                        bool ok_r[2];
+                        uint32_t off_r[2];
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int i = 16 * mt + g + 8 * hh, yr = ycount + i, bl = yr / VIS_PATCH;
+                            ok_r[hh] = i < ihi && bl >= bs && bl <= be;
+                            off_r[hh] = (uint32_t)(((nb + bl) & 1) * 3 * L.oplane + (yr - bl * VIS_PATCH) * L.opitch);
+                        }
+#pragma unroll 1
+                        for (int jt = wv; jt < n_tiles; jt += kVWarps) {
+                            const int cb = min(8 * jt + g, NC - 1);                      // ring column of this lane's B column
+                            const int chb = (cb >= sw) + (cb >= 2 * sw);
+                            const uint32_t ba = ring0 + (uint32_t)(chb * L.hplane + (cb - chb * sw) * L.cpitch + 4 * t);
+                            const uint32_t b00 = lds32(ba), b01 = lds32(ba + 16), b10 = lds32(ba + 32), b11 = lds32(ba + 48);
+                            int a0[4], a1[4], a2[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { a0[e] = 1 << (VIS_PRECISION_BITS - 1); a1[e] = 0; a2[e] = 0; }
+                            imma_uu_a(a0, a[0][0], b00, b01);
+                            imma_uu_a(a1, a[0][1], b00, b01);
+                            imma_su_a(a2, a[0][2], b00, b01);
+                            imma_uu_a(a0, a[1][0], b10, b11);
+                            imma_uu_a(a1, a[1][1], b10, b11);
+                            imma_su_a(a2, a[1][2], b10, b11);
+                            // D: e = 0/1 -> (row g, columns 2t / 2t+1), e = 2/3 -> (row g+8, columns 2t / 2t+1)
+                            const int cs = 8 * jt + 2 * t;
+                            if (cs < NC) {
+                                const int chs = (cs >= sw) + (cs >= 2 * sw);
+                                const uint32_t oa = otile0 + (uint32_t)(chs * L.oplane + (cs - chs * sw));
+                                if (ok_r[0]) {
+                                    const uint32_t p = pack_sat(recombine(a0[1], a1[1], a2[1]), recombine(a0[0], a1[0], a2[0]), 0u);
+                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa + off_r[0]), "h"((unsigned short)p) : "memory");
+                                }
+                                if (ok_r[1]) {
+                                    const uint32_t p = pack_sat(recombine(a0[3], a1[3], a2[3]), recombine(a0[2], a1[2], a2[2]), 0u);
+                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa + off_r[1]), "h"((unsigned short)p) : "memory");
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        for (int bb = bs; bb <= be; ++bb)                                // bands completed by the rows stored so far
+                            if (min(VIS_PATCH * (bb + 1), seg_rows) <= ycount + ihi && lane == 0)
+                                mbar_arrive(bar(OF, (nb + bb) & 1));
+                    }
+                }
+                ycount += n;
+                if (c + 1 < n_chunks) {                   // carry: the last W-1 words of every column -> front of the other slot
+                    const uint32_t dst0 = smem_u32(smem + L.off_hring + (slot ^ 1) * 3 * L.hplane);
+                    const int per = 8 * (W - 1);
+                    for (int jt = wv; jt < n_tiles; jt += kVWarps)
+                        for (int i = lane; i < per; i += 32) {
+                            const int cc = 8 * jt + i / (W - 1), q = i % (W - 1);
+                            if (cc < NC) {
+                                const int ch = (cc >= sw) + (cc >= 2 * sw);
+                                const uint32_t o = (uint32_t)(ch * L.hplane + (cc - ch * sw) * L.cpitch + 4 * q);
+                                sts32(dst0 + o, lds32(ring0 + o + kChunk));
+                            }
+                        }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(HE, slot));       // H-ring slot and record slot consumed
+            }
+            nb += (seg_rows + VIS_PATCH - 1) / VIS_PATCH;
+        }
+    } else {
+        // ============================== band store ==============================
+        const int sw_i = warp - kSBase;
+        int nb = 0;
+        if (U8) {
+            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const int f = w / per_frame, r = w - f * per_frame;
+                const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+                const VisSchedStrip S = sc.strip[st];
+                const VisSchedSeg G = sc.seg[sg];
+                const int wpr = (S.x1 - S.x0) / 4;                 // 4-pixel groups per row of the strip
+                unsigned char* const dst0 = reinterpret_cast<unsigned char*>(frames[f].second) + (size_t)S.x0 * 3;
+                for (int y = G.y0; y < G.y1; y += VIS_PATCH, ++nb) {
+                    const int os = nb & 1, rows = min(VIS_PATCH, G.y1 - y);
+                    mbar_wait(bar(OF, os), (nb >> 1) & 1);
+                    const uint32_t otile = smem_u32(smem + L.off_otile + os * 3 * L.oplane);
+                    for (int i = sw_i * 32 + lane; i < rows * wpr; i += kSWarps * 32) {
+                        const int rr = i / wpr, q = i - rr * wpr;
+                        const uint32_t at = otile + (uint32_t)(rr * L.opitch + q * 4);
+                        const uint32_t A = lds32(at), B = lds32(at + L.oplane), C = lds32(at + 2 * L.oplane);
+                        const uint32_t ab = __byte_perm(A, B, 0x5140), ab2 = __byte_perm(A, B, 0x7362);   // a0 b0 a1 b1 / a2 b2 a3 b3
+                        uint32_t* o = reinterpret_cast<uint32_t*>(dst0 + (size_t)(y + rr) * dst_pitch + (size_t)q * 12);
+                        o[0] = __byte_perm(ab, C, 0x2410);                                      // a0 b0 c0 a1
+                        o[1] = __byte_perm(__byte_perm(ab, C, 0x0053), ab2, 0x5410);             // b1 c1 a2 b2
+                        o[2] = __byte_perm(ab2, C, 0x7326);                                     // c2 a3 b3 c3
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(OE, os));
+                }
+            }
+        } else {
+            // lane-constant description of up to five 16-byte chunks (c, q) of a patch row: item = lane + 32 * i < 147
+            int sa[5], sb[5], go[5], lo[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int item = min(lane + 32 * i, 146);
+                const int c = item / 49, q = item - c * 49;
+                const int f0 = 4 * q, f2 = f0 + 2;
+                const int pya = f0 / VIS_PATCH, pyb = f2 / VIS_PATCH;
+                sa[i] = c * L.oplane + pya * L.opitch + (f0 - pya * VIS_PATCH);
+                sb[i] = c * L.oplane + pyb * L.opitch + (f2 - pyb * VIS_PATCH);
+                go[i] = c * 392 + f0;
+                lo[i] = c * 256;
+            }
+            const int half_gw = sc.dst_w / (2 * VIS_PATCH);
+            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const int f = w / per_frame, r = w - f * per_frame;
+                const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+                const VisSchedStrip S = sc.strip[st];
+                const VisSchedSeg G = sc.seg[sg];
+                const int n_patches = (S.x1 - S.x0) / VIS_PATCH, gx0 = S.x0 / VIS_PATCH;
+                float* const frame_out = pixel_values + (size_t)frames[f].second * VIS_ROW_FLOATS;
+                for (int gy = G.y0 / VIS_PATCH; gy < G.y1 / VIS_PATCH; ++gy, ++nb) {
+                    const int os = nb & 1;
+                    mbar_wait(bar(OF, os), (nb >> 1) & 1);
+                    const unsigned char* otile = smem + L.off_otile + os * 3 * L.oplane;
+                    float* band = frame_out + (size_t)((gy >> 1) * half_gw * 4 + (gy & 1) * 2) * VIS_ROW_FLOATS;
+                    for (int gp = sw_i; gp < n_patches; gp += kSWarps) {
+                        const int gx = gx0 + gp;
+                        float* prow = band + (size_t)((gx >> 1) * 4 + (gx & 1)) * VIS_ROW_FLOATS;
+                        const unsigned char* pt = otile + gp * VIS_PATCH;
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            if (lane + 32 * i < 147) {
+                                const unsigned a = *reinterpret_cast<const unsigned short*>(pt + sa[i]);
+                                const unsigned b = *reinterpret_cast<const unsigned short*>(pt + sb[i]);
+                                const float* l = lut + lo[i];
+                                const float v0 = l[a & 0xff], v1 = l[a >> 8], v2 = l[b & 0xff], v3 = l[b >> 8];
+                                stg128(prow + go[i], v0, v1, v2, v3);
+                                stg128(prow + go[i] + 196, v0, v1, v2, v3);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(OE, os));
+                }
+            }
+        }
+    }
+}
+
+template <int KS, bool U8>
+int launch_mma(const VisSched& sc, const void* frames, int n_frames, const LayoutM& L, int64_t dst_pitch, const int* hrec,
+               const int* vrec, const float* lut768, float* pixel_values, cudaStream_t st) {
+    auto kern = k_fused_mma<KS, U8>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return vis::cuda_fail(e, "vis_fused_mma: cudaFuncSetAttribute");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_items = n_frames * sc.n_strips * sc.n_segs;
+    const int grid = n_items < sms ? n_items : sms;
+    kern<<<grid, kThreads, L.total, st>>>(sc, reinterpret_cast<const FramePtrs*>(frames), n_items, L, (long long)dst_pitch,
+                                          hrec, vrec, lut768, pixel_values);
+    return vis::check_launch("vis_fused_mma");
+}
+
+}  // namespace
+
+namespace visf {
+
+int mma_max_strip_w() { return 256; }
+int mma_max_ksteps() { return 3; }
+int mma_layout_bytes(int stage_pitch, int strip_w, int words) { return make_layout_m(stage_pitch, strip_w, words).total; }
+int mma_record_stride(int words) { return rec_stride_mma(words); }
+
+int mma_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
+               const float* lut768, float* pixel_values, cudaStream_t st) {
+    const int W = sc.dp_words;
+    if (W < 4 || W > 9 || sc.ring != 16 || sc.per_index != 1 || sc.mma_ks < 1 || sc.mma_ks > 3) {
+        vis::set_error("vis_fused_mma: schedule of another kernel class (ring %d, %d words, %d k-steps)", sc.ring, W, sc.mma_ks);
+        return VIS_E_INVALID;
+    }
+    const LayoutM L = make_layout_m(sc.stage_pitch, sc.max_strip_w, W);
+    if (L.total > kSmemMax) {
+        vis::set_error("vis_fused_mma: %d bytes of shared memory needed", L.total);
+        return VIS_E_UNSUPPORTED;
+    }
+    const bool u8 = sc.out_mode == VIS_SCHED_OUT_U8;
+#define VIS_LM(KK) (u8 ? launch_mma<KK, true>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st) \
+                       : launch_mma<KK, false>(sc, frames, n_frames, L, dst_pitch, hrec, vrec, lut768, pixel_values, st))
+    return sc.mma_ks <= 2 ? VIS_LM(2) : VIS_LM(3);
+#undef VIS_LM
+}
+
+}  // namespace visf

@@ -44,6 +44,15 @@ int dp_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_
               const float* lut768, float* pixel_values, cudaStream_t st);
 }
 
+namespace visf {   // integer tensor-path (IMMA) kernel, vis_fused_mma.cu
+int mma_max_strip_w();
+int mma_max_ksteps();
+int mma_layout_bytes(int stage_pitch, int strip_w, int words);
+int mma_record_stride(int words);
+int mma_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
+               const float* lut768, float* pixel_values, cudaStream_t st);
+}
+
 #ifndef VIS_DP_NV_SPLIT
 #define VIS_DP_NV_SPLIT 2.4       // packed-byte kernel: 4 vertical-pass warps from this vertical scale on, 6 below
 #endif
@@ -450,7 +459,9 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
         return VIS_E_INVALID;
     }
     auto unsupported = [](const char* why) { vis::set_error("vis_sched_build: %s", why); return VIS_E_UNSUPPORTED; };
-    const bool want_dp = (out_mode & VIS_SCHED_FLAG_DP4A) != 0;
+    const bool want_mma = (out_mode & VIS_SCHED_FLAG_MMA) != 0;
+    const bool want_dp = want_mma || (out_mode & VIS_SCHED_FLAG_DP4A) != 0;
+    const int mode_in = out_mode;
     out_mode &= 0xff;
     const bool u8 = out_mode == VIS_SCHED_OUT_U8;
     if (!u8 && (dst_h % 28 || dst_w % 28)) return unsupported("output size is not a multiple of 28");
@@ -476,11 +487,25 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
         if (dp_words) cls = 4 * dp_words - 3;
     }
     const bool h_pull = !dp_words && cls > 16;
+    const bool mma = want_mma && dp_words > 0;      // same limb records, both passes on the integer tensor path
+    int mma_ks = 0;
+    if (mma) {
+        // k-steps of 32 input pixels that the window of a tile of 8 outputs spans, counted from the 4-pixel word of the
+        // tile's first tap.  Tiles start at multiples of 4 columns wherever the strips fall, so this is a property of the
+        // geometry (the records are cached per geometry); beyond the kernel's register budget: the packed-byte kernel.
+        for (int x = 0; x < dst_w; x += 4) {
+            int lastpx = 0;
+            for (int o = x; o < x + 8 && o < dst_w; ++o) lastpx = std::max(lastpx, hb[2 * o] + hb[2 * o + 1] - 1);
+            mma_ks = std::max(mma_ks, (lastpx + 1 - (hb[2 * x] & ~3) + 31) / 32);
+        }
+        if (mma_ks > visf::mma_max_ksteps())
+            return vis_sched_build(src_h, src_w, dst_h, dst_w, src_pitch, hb, vb, vsplit, (mode_in & ~VIS_SCHED_FLAG_MMA) | VIS_SCHED_FLAG_DP4A, out);
+    }
     const int n_subs = ring == 8 ? 12 : dp_words ? visf::dp_subs() : visf::sched16_subs();
     // 16-slot kernels: fewer vertical-pass warps the stronger the vertical downscale (the V role gets lighter)
     const double vscale = (double)src_h / dst_h;
     const int n_vwarps = ring == 8 ? 0 : dp_words ? (vscale >= VIS_DP_NV_SPLIT ? 4 : 6) : cls > 16 ? (vscale >= 3.4 ? 3 : 4) : (vscale >= 2.4 ? 4 : 6);
-    const int max_w = ring == 8 ? kMaxStripW : dp_words ? visf::dp_max_strip_w(n_vwarps) : visf::sched16_max_strip_w(n_vwarps);
+    const int max_w = ring == 8 ? kMaxStripW : mma ? visf::mma_max_strip_w() : dp_words ? visf::dp_max_strip_w(n_vwarps) : visf::sched16_max_strip_w(n_vwarps);
     int per_index = 1;
     // an exact class (13, 14) may be too tight for the virtual ends of the far-border samples: widen it
     while ((cls == 13 || cls == 14) && (!schedule_ends(hb, dst_w, cls, 1, hl) || !schedule_ends(vb, dst_h, cls, 1, vl)))
@@ -496,7 +521,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     std::memset(&s, 0, sizeof(s));
     s.src_h = src_h; s.src_w = src_w; s.dst_h = dst_h; s.dst_w = dst_w; s.src_pitch = src_pitch; s.kt = cls;
     s.per_index = per_index; s.ring = ring; s.n_subs = n_subs; s.out_mode = out_mode; s.h_pull = h_pull ? 1 : 0;
-    s.n_vwarps = n_vwarps; s.dp_words = dp_words;
+    s.n_vwarps = n_vwarps; s.dp_words = dp_words; s.mma_ks = mma_ks;
     const int stride = dp_words ? visf::dp_record_stride(dp_words) : vis_record_stride(cls);
     auto last = [](const int32_t* b, int i) { return b[2 * i] + b[2 * i + 1] - 1; };
     auto span_of = [&](int x0, int x1, int* px0) {
@@ -507,6 +532,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     };
     auto layout_bytes = [&](int pitch, int strip_w) {
         return ring == 8 ? make_layout_s(pitch, strip_w, stride).total
+                         : mma ? visf::mma_layout_bytes(pitch, strip_w, dp_words)
                          : dp_words ? visf::dp_layout_bytes(pitch, strip_w, dp_words) : visf::sched16_layout_bytes(pitch, strip_w, cls);
     };
     // column strips: the fewest (widest, <= 336 columns) whose shared-memory layout fits; strip edges are multiples
@@ -549,7 +575,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
             VisSchedSub& U = s.sub[i][u];
             const int xa = S.x0 + (int)((int64_t)sw * u / n_subs), xb = S.x0 + (int)((int64_t)sw * (u + 1) / n_subs);
             U.xa = (uint16_t)xa; U.xb = (uint16_t)xb;
-            if (xa >= xb || h_pull) continue;                          // nsteps = 0: nothing to walk (pull order needs no masks)
+            if (xa >= xb || h_pull || mma) continue;                   // nsteps = 0: nothing to walk (pull order / tiles need no masks)
             const int p0 = hb[2 * xa] & ~(step - 1);
             const int nsteps = (hl[xb - 1] - p0) / step + 1;
             if (!mask_room(2 * mbytes * nsteps) || nsteps > 65535) return unsupported("schedule too large");
@@ -655,6 +681,55 @@ int vis_sched_pack_records_dp(int out_size, const int32_t* k, const int32_t* bou
     return VIS_OK;
 }
 
+int vis_sched_record_stride_mma(int words) {
+    if (words < 4 || words > 9) return VIS_E_INVALID;
+    return visf::mma_record_stride(words);
+}
+
+int vis_sched_pack_records_mma(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int words,
+                               int32_t* rec, int64_t rec_capacity) {
+    if (out_size <= 0 || !k || !bounds || !rec || ksize <= 0 || words < 4 || words > 9) {
+        vis::set_error("vis_sched_pack_records_mma: bad arguments");
+        return VIS_E_INVALID;
+    }
+    const int stride = visf::mma_record_stride(words);
+    if (rec_capacity < (int64_t)(out_size + 1) * stride) {
+        vis::set_error("vis_sched_pack_records_mma: capacity too small");
+        return VIS_E_CAPACITY;
+    }
+    std::vector<int> ends;
+    if (!schedule_ends(bounds, out_size, 4 * words - 3, 1, ends)) {
+        vis::set_error("vis_sched_pack_records_mma: table is not schedulable with %d words (upscale or too many taps)", words);
+        return VIS_E_UNSUPPORTED;
+    }
+    std::memset(rec, 0, sizeof(int32_t) * (size_t)(out_size + 1) * stride);
+    for (int o = 0; o < out_size; ++o) {
+        const int first = bounds[2 * o], taps = bounds[2 * o + 1], end = ends[o];
+        const int bw = (end >> 2) - (words - 1);                    // absolute word index of record byte 0 (may be negative)
+        if (end < first + taps - 1 || first < 4 * bw) {
+            vis::set_error("vis_sched_pack_records_mma: window of sample %d ([%d, %d), end %d) does not fit %d words", o, first,
+                           first + taps, end, words);
+            return VIS_E_UNSUPPORTED;
+        }
+        int32_t* r32 = rec + (size_t)o * stride;
+        unsigned char* r = reinterpret_cast<unsigned char*>(r32);
+        for (int t = 0; t < taps; ++t) {
+            const int32_t c = k[(size_t)o * ksize + t];
+            if (c < -(1 << 23) || c >= (1 << 23)) {
+                vis::set_error("vis_sched_pack_records_mma: coefficient %d outside three byte limbs", c);
+                return VIS_E_UNSUPPORTED;
+            }
+            const int at = first + t - 4 * bw;                       // byte position inside the W-word window
+            r[at] = (unsigned char)(c & 0xff);
+            r[4 * words + at] = (unsigned char)((c >> 8) & 0xff);
+            r[8 * words + at] = (unsigned char)((c >> 16) & 0xff);   // signed limb (arithmetic shift), two's complement byte
+        }
+        r32[3 * words] = bw;
+        r32[3 * words + 1] = first >> 2;
+    }
+    return VIS_OK;
+}
+
 int vis_preprocess_fused_sched_dup(const VisSched* sched, const VisFrameRef* frames, int n_frames,
                                    const int32_t* hrec, const int32_t* vrec,
                                    const float* lut768, float* pixel_values, const int64_t* dup_rows, void* stream) {
@@ -670,6 +745,7 @@ int vis_preprocess_fused_sched_dup(const VisSched* sched, const VisFrameRef* fra
             vis::set_error("vis_preprocess_fused_sched_dup: duplicate rows are served by the 8-slot kernel only (<= 8 taps)");
             return VIS_E_UNSUPPORTED;
         }
+        if (sched->mma_ks) return mma_launch(*sched, frames, n_frames, 0, hrec, vrec, lut768, pixel_values, st);
         if (sched->dp_words) return dp_launch(*sched, frames, n_frames, 0, hrec, vrec, lut768, pixel_values, st);
         return sched16_launch(*sched, frames, n_frames, 0, hrec, vrec, lut768, pixel_values, st);
     }
@@ -702,6 +778,7 @@ int vis_resize_fused_sched(const VisSched* sched, const VisResizeRef* frames, in
         vis::set_error("vis_resize_fused_sched: bad arguments");
         return VIS_E_INVALID;
     }
+    if (sched->mma_ks) return mma_launch(*sched, frames, n_frames, dst_pitch, hrec, vrec, nullptr, nullptr, (cudaStream_t)stream);
     if (sched->dp_words) return dp_launch(*sched, frames, n_frames, dst_pitch, hrec, vrec, nullptr, nullptr, (cudaStream_t)stream);
     return sched16_launch(*sched, frames, n_frames, dst_pitch, hrec, vrec, nullptr, nullptr, (cudaStream_t)stream);
 }

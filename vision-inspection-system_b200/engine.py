@@ -89,14 +89,23 @@ class Engine:
         # 9+ tap geometries: the packed-byte (IDP.4A) kernel unless VIS_B200_DP4A=0 selects the 16-slot IMAD kernel
         # (developer A/B switch; both are bit-exact)
         self.dp4a = os.environ.get("VIS_B200_DP4A", "1") != "0"
+        # ... and, on top of it, both passes as banded u8 x limb matrix products on the integer tensor path (IMMA.16832,
+        # vis_fused_mma.cu) unless VIS_B200_MMA=0 keeps the IDP.4A kernel; the three families are bit-exact
+        self.mma = os.environ.get("VIS_B200_MMA", "1") != "0"
         self._lock = threading.RLock()   # public entry points are serialised: caches and staging buffers are shared
         self._tls = threading.local()    # per-thread state (nvJPEG handles are not thread-safe)
 
-    def use_dp4a(self, on: bool) -> None:
-        """Select the kernel family of 9+ tap geometries — packed bytes / IDP.4A (default) or the 16-slot IMAD kernel —
-        and drop every cached schedule and plan (A/B runs and the tests that keep both families green)."""
+    def _sched_flags(self) -> int:
+        return (N.SCHED_FLAG_MMA if self.mma and self.dp4a else 0) | (N.SCHED_FLAG_DP4A if self.dp4a else 0)
+
+    def use_dp4a(self, on: bool, mma: bool | None = None) -> None:
+        """Select the kernel family of 9+ tap geometries — byte limbs (default: on the integer tensor path, ``mma=False``:
+        IDP.4A) or the 16-slot IMAD kernel — and drop every cached schedule and plan (A/B runs and the tests that keep
+        all families green)."""
         with self._lock:
             self.dp4a = bool(on)
+            if mma is not None:
+                self.mma = bool(mma)
             self._geoms.clear()
             self._dev_tables.clear()
             self._batch_plans.clear()
@@ -154,7 +163,12 @@ class Engine:
         kt, per_index, words = int(head["kt"]), int(head["per_index"]), int(head["dp_words"])
         out = []
         for t in tables:
-            if words:
+            if words and int(head["mma_ks"]):
+                stride = N.check(self.L.vis_sched_record_stride_mma(words), "vis_sched_record_stride_mma")
+                rec = np.zeros((t.out_size + 1, stride), np.int32)
+                N.check(self.L.vis_sched_pack_records_mma(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, words,
+                                                          N.i32ptr(rec), rec.size), "vis_sched_pack_records_mma")
+            elif words:
                 stride = N.check(self.L.vis_sched_record_stride_dp(words), "vis_sched_record_stride_dp")
                 rec = np.zeros((t.out_size + 1, stride), np.int32)
                 N.check(self.L.vis_sched_pack_records_dp(t.out_size, N.i32ptr(t.k), N.i32ptr(t.bounds), t.ksize, words,
@@ -173,7 +187,7 @@ class Engine:
         key = (pitch, n_segs)
         if key not in g.scheds:
             buf = np.zeros(self.L.vis_sched_sizeof(), np.uint8)
-            mode = N.SCHED_OUT_PIXEL_VALUES | (N.SCHED_FLAG_DP4A if self.dp4a else 0)
+            mode = N.SCHED_OUT_PIXEL_VALUES | self._sched_flags()
             rc = self.L.vis_sched_build(g.src_h, g.src_w, g.dst_h, g.dst_w, pitch, N.i32ptr(g.htable.bounds),
                                         N.i32ptr(g.vtable.bounds), n_segs, mode, buf.ctypes.data_as(C.c_void_p))
             if rc == N.VIS_E_UNSUPPORTED:
@@ -198,7 +212,7 @@ class Engine:
         if G.pil_pass_order(src_h, src_w, out_h, out_w) == "hv":
             ht, vt = T.coeff_table(src_w, out_w, filt), T.coeff_table(src_h, out_h, filt)
             buf = np.zeros(self.L.vis_sched_sizeof(), np.uint8)
-            mode = N.SCHED_OUT_U8 | (N.SCHED_FLAG_DP4A if self.dp4a else 0)
+            mode = N.SCHED_OUT_U8 | self._sched_flags()
             rc = self.L.vis_sched_build(src_h, src_w, out_h, out_w, pitch, N.i32ptr(ht.bounds), N.i32ptr(vt.bounds), n_segs,
                                         mode, buf.ctypes.data_as(C.c_void_p))
             if rc != N.VIS_E_UNSUPPORTED:
