@@ -256,8 +256,8 @@ int vis_sched_pack_records(int out_size, const int32_t* k, const int32_t* bounds
 int vis_sched_record_stride_dp(int words);
 int vis_sched_pack_records_dp(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int words,
                               int32_t* rec, int64_t rec_capacity);
-/* records for the integer tensor-path kernel (sched.mma_ks > 0): the limb rows of vis_sched_pack_records_dp followed by
- * two int32: the absolute 4-sample word index of record byte 0 ((end >> 2) - (words - 1)) and of the window's first tap
+/* records for the integer tensor-path kernel (sched.mma_ks > 0): the limb bytes of vis_sched_pack_records_dp, limb-minor
+ * (32-bit word 3 q + l = limb l of the four samples of window word q), followed by two int32: the absolute 4-sample word index of record byte 0 ((end >> 2) - (words - 1)) and of the window's first tap
  * (first >> 2).  rec: (out_size + 1) * vis_sched_record_stride_mma(words) int32.             [host] */
 int vis_sched_record_stride_mma(int words);
 int vis_sched_pack_records_mma(int out_size, const int32_t* k, const int32_t* bounds, int ksize, int words,

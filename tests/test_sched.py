@@ -246,7 +246,7 @@ def _mma_records(table, words):
 
 def _limb_rows(rec_row, words):
     """(3, 4 * words) int64: the limb bytes of one record; limb 2 is signed."""
-    b = rec_row[:3 * words].view(np.uint8).reshape(3, 4 * words).astype(np.int64)
+    b = rec_row[:3 * words].view(np.uint8).reshape(words, 3, 4).transpose(1, 0, 2).reshape(3, 4 * words).astype(np.int64)
     b[2] = b[2].astype(np.uint8).astype(np.int8)
     return b
 

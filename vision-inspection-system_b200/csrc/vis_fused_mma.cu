@@ -31,27 +31,40 @@ using namespace visf;
 namespace {
 
 #ifndef VIS_MMA_HWARPS
-#define VIS_MMA_HWARPS 8
+#define VIS_MMA_HWARPS 10
 #endif
 #ifndef VIS_MMA_VWARPS
-#define VIS_MMA_VWARPS 4
+#define VIS_MMA_VWARPS 8
 #endif
 #ifndef VIS_MMA_SWARPS
 #define VIS_MMA_SWARPS 2
 #endif
-constexpr int kHWarps = VIS_MMA_HWARPS, kVWarps = VIS_MMA_VWARPS, kSWarps = VIS_MMA_SWARPS;
-// warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
-constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kHWarps + 1 + kSWarps;
-constexpr int kThreads = (kHWarps + kVWarps + kSWarps + 1) * 32;
+#ifndef VIS_MMA_DWARPS
+#define VIS_MMA_DWARPS 3
+#endif
+constexpr int kHWarps = VIS_MMA_HWARPS, kVWarps = VIS_MMA_VWARPS, kSWarps = VIS_MMA_SWARPS, kDWarps = VIS_MMA_DWARPS;
+// warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < D < S < V
+constexpr int kHBase = 0, kLBase = kHWarps, kDBase = kHWarps + 1, kSBase = kDBase + kDWarps, kVBase = kSBase + kSWarps;
+constexpr int kThreads = (kHWarps + kVWarps + kSWarps + kDWarps + 1) * 32;
+#ifndef VIS_MMA_VUNROLL
+#define VIS_MMA_VUNROLL 1
+#endif
+constexpr int kVUnroll = VIS_MMA_VUNROLL;         // independent column tiles a V warp keeps in flight
 constexpr int kChunk = 32;
 constexpr int kVRecs = kChunk + 1;                // vertical records a chunk can touch (scale >= 1): 32 emits + 1 look-ahead
 constexpr int kSmemMax = 227 * 1024;
 constexpr int kStageSkew = 128;                   // 16 bytes x (row >> 2): 112 bytes of slack per slot
 
-enum Bar { SF = 0, SE = 2, HF = 4, HE = 6, VF = 8, OF = 10, OE = 12, kBars = 14 };   // full/empty pairs, two slots each
+#ifndef VIS_MMA_OSLOTS
+#define VIS_MMA_OSLOTS 3
+#endif
+constexpr int kOSlots = VIS_MMA_OSLOTS;           // band tiles in flight between the vertical pass and the store warps
+// full/empty pairs, two slots each; band tiles: kOSlots each
+enum Bar { SF = 0, SE = 2, HF = 4, HE = 6, VF = 8, DF = 10, OF = 12, OE = 12 + kOSlots, kBars = 12 + 2 * kOSlots };
 
-// words per record: 3 limb rows of W words, then the absolute word index of record byte 0 and of the window's first tap
-__host__ __device__ constexpr int rec_stride_mma(int W) { return (3 * W + 2 + 3) & ~3; }
+// words per record: W words x 3 limbs (limb-minor), then the absolute word index of record byte 0 and of the window's first tap
+// (4 mod 8 words: the eight records a fragment gather touches start in eight different bank groups)
+__host__ __device__ constexpr int rec_stride_mma(int W) { return ((3 * W + 2 + 3) & ~7) + 4 >= 3 * W + 2 ? ((3 * W + 2 + 3) & ~7) + 4 : ((3 * W + 2 + 3) & ~7) + 12; }
 
 struct LayoutM {
     int stage_pitch, stage_slot, hrec_slot, vrec_slot;
@@ -75,8 +88,8 @@ inline LayoutM make_layout_m(int stage_pitch, int strip_w, int W) {
     L.oplane = VIS_PATCH * L.opitch;
     int off = 0;
     L.off_stage = off; off += 2 * L.stage_slot;
-    L.off_hring = off; off += 2 * 3 * L.hplane + 64;      // a k-step reads 64 bytes of a column whatever its pitch
-    L.off_otile = off; off += 2 * 3 * L.oplane;
+    L.off_hring = off; off += 2 * 3 * L.hplane;           // tiles past the strip read (and discard) whatever follows: the ring is never the last region
+    L.off_otile = off; off += kOSlots * 3 * L.oplane;
     off = align_up(off, 16);
     L.off_hrec = off;  off += 2 * L.hrec_slot;
     L.off_vrec = off;  off += 2 * L.vrec_slot;
@@ -112,6 +125,10 @@ __device__ __forceinline__ uint32_t pack_sat(int hi, int lo, uint32_t c) {
 // Pillow's (acc + 2^21) >> 22 with the rounding constant already inside limb 0's accumulator
 __device__ __forceinline__ int recombine(int a0, int a1, int a2) { return (a0 + (a1 << 8) + (a2 << 16)) >> VIS_PRECISION_BITS; }
 
+__device__ __forceinline__ void sts16_if(bool p, uint32_t addr, uint32_t v) {     // predicated, no branch
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.shared.u16 [%1], %2;\n}\n" ::"r"((uint32_t)p), "r"(addr), "h"((unsigned short)v) : "memory");
+}
+
 struct FramePtrs { const unsigned char* src; long long second; };      // VisFrameRef / VisResizeRef: same layout
 
 template <int KS, bool U8>
@@ -140,6 +157,9 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             mbar_init(bar(HF, s), kHWarps);
             mbar_init(bar(HE, s), kVWarps);
             mbar_init(bar(VF, s), 1);
+            mbar_init(bar(DF, s), kDWarps);
+        }
+        for (int s = 0; s < kOSlots; ++s) {
             mbar_init(bar(OF, s), kVWarps);
             mbar_init(bar(OE, s), kSWarps);
         }
@@ -205,10 +225,12 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             const uint32_t hrec0 = smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot);
             for (int c = 0; c < n_chunks; ++c, ++k) {
                 const int slot = k & 1, j = k >> 1;
-                mbar_wait(bar(SF, slot), j & 1);
+                mbar_wait(bar(DF, slot), j & 1);                // the D warps have de-interleaved the chunk in place
+                mbar_wait(bar(SF, slot), j & 1);                // (complete long ago: the strip's records ride on it)
+                const uint32_t stage0 = smem_u32(smem + L.off_stage + slot * L.stage_slot);
                 if (k >= 2) mbar_wait(bar(HE, slot), (j - 1) & 1);
                 // this lane's rows 4g..4g+3 of the stage slot (skewed) and of the ring columns it stores
-                const uint32_t srow = smem_u32(smem + L.off_stage + slot * L.stage_slot) + (uint32_t)(4 * g * L.stage_pitch + 16 * g);
+                const uint32_t srow = stage0 + (uint32_t)(4 * g * L.stage_pitch + 16 * g);
                 const uint32_t hring = smem_u32(smem + L.off_hring + slot * 3 * L.hplane) + (uint32_t)(CARRY + 4 * g);
 #pragma unroll 1
                 for (int jt = hw; jt < n_tiles; jt += kHWarps) {
@@ -224,49 +246,37 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                         for (int h = 0; h < 2; ++h) {
                             const int q = kw + 8 * s + 4 * h + t - bw;
                             const bool ok = (unsigned)q < (unsigned)W;
+                            const uint32_t qa = rec + (uint32_t)(12 * q);              // limbs of a word sit side by side
 #pragma unroll
-                            for (int l = 0; l < 3; ++l) b[s][l][h] = ok ? lds32(rec + (uint32_t)((l * W + q) * 4)) : 0u;
+                            for (int l = 0; l < 3; ++l) b[s][l][h] = ok ? lds32(qa + 4 * l) : 0u;
                         }
-                    // raw bytes of pixel (4 * (kw + t)) of the stage row, relative to the row start
-                    const uint32_t px_off = (uint32_t)((4 * (kw + t) - S.px0) * 3);
+                    // group (kw + t) of the stage row: 12 bytes = 4 pixels, channel planes of 4 bytes
+                    const uint32_t g_off = (uint32_t)(12 * (kw + t - (S.px0 >> 2)));
                     uint32_t pk[3][2];                                                   // rows 4g+2, 4g+3 of columns 2t, 2t+1 per channel
 #pragma unroll
                     for (int mt = 1; mt >= 0; --mt) {
-                        int acc[3][3][4];
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { acc[ch][0][e] = 1 << (VIS_PRECISION_BITS - 1); acc[ch][1][e] = 0; acc[ch][2][e] = 0; }
-                        const uint32_t r0a = srow + (uint32_t)(2 * mt * L.stage_pitch) + px_off;     // row 4g + 2mt
+                        const uint32_t r0a = srow + (uint32_t)(2 * mt * L.stage_pitch) + g_off;      // row 4g + 2mt
                         const uint32_t r1a = r0a + (uint32_t)L.stage_pitch;                          // row 4g + 2mt + 1
 #pragma unroll
-                        for (int s = 0; s < KS; ++s) {
-                            uint32_t a[3][4];
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const uint32_t o = (uint32_t)((32 * s + 16 * h) * 3);
-                                const uint32_t x0 = lds32(r0a + o), x1 = lds32(r0a + o + 4), x2 = lds32(r0a + o + 8);
-                                const uint32_t y0 = lds32(r1a + o), y1 = lds32(r1a + o + 4), y2 = lds32(r1a + o + 8);
-                                a[0][2 * h] = __byte_perm(__byte_perm(x0, x1, 0x0630), x2, 0x5210);
-                                a[1][2 * h] = __byte_perm(__byte_perm(x0, x1, 0x0741), x2, 0x6210);
-                                a[2][2 * h] = __byte_perm(__byte_perm(x0, x1, 0x0052), x2, 0x7410);
-                                a[0][2 * h + 1] = __byte_perm(__byte_perm(y0, y1, 0x0630), y2, 0x5210);
-                                a[1][2 * h + 1] = __byte_perm(__byte_perm(y0, y1, 0x0741), y2, 0x6210);
-                                a[2][2 * h + 1] = __byte_perm(__byte_perm(y0, y1, 0x0052), y2, 0x7410);
-                            }
-#pragma unroll
-                            for (int ch = 0; ch < 3; ++ch) {
-                                imma_uu(acc[ch][0], a[ch], b[s][0][0], b[s][0][1]);
-                                imma_uu(acc[ch][1], a[ch], b[s][1][0], b[s][1][1]);
-                                imma_us(acc[ch][2], a[ch], b[s][2][0], b[s][2][1]);
-                            }
-                        }
-                        // D: e = 0/1 -> (row 4g+2mt, columns 2t / 2t+1), e = 2/3 -> (row 4g+2mt+1, columns 2t / 2t+1)
-#pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
+                            int acc[3][4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { acc[0][e] = 1 << (VIS_PRECISION_BITS - 1); acc[1][e] = 0; acc[2][e] = 0; }
+#pragma unroll
+                            for (int s = 0; s < KS; ++s) {
+                                uint32_t a[4];
+                                a[0] = lds32(r0a + (uint32_t)(96 * s + 4 * ch));
+                                a[1] = lds32(r1a + (uint32_t)(96 * s + 4 * ch));
+                                a[2] = lds32(r0a + (uint32_t)(96 * s + 48 + 4 * ch));
+                                a[3] = lds32(r1a + (uint32_t)(96 * s + 48 + 4 * ch));
+                                imma_uu(acc[0], a, b[s][0][0], b[s][0][1]);
+                                imma_uu(acc[1], a, b[s][1][0], b[s][1][1]);
+                                imma_us(acc[2], a, b[s][2][0], b[s][2][1]);
+                            }
+                            // D: e = 0/1 -> (row 4g+2mt, columns 2t / 2t+1), e = 2/3 -> (row 4g+2mt+1, columns 2t / 2t+1)
                             int v[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = recombine(acc[ch][0][e], acc[ch][1][e], acc[ch][2][e]);
+                            for (int e = 0; e < 4; ++e) v[e] = recombine(acc[0][e], acc[1][e], acc[2][e]);
                             if (mt == 1) {
                                 pk[ch][0] = pack_sat(v[2], v[0], 0u);
                                 pk[ch][1] = pack_sat(v[3], v[1], 0u);
@@ -277,12 +287,12 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                         }
                     }
                     const int xc = 8 * jt + 2 * t;                                       // strip widths are multiples of 4
-                    if (xc < sw) {
+                    if (xc < sw) {                                                       // ring column = channel * sw + x
                         const uint32_t at = hring + (uint32_t)(xc * L.cpitch);
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
-                            sts32(at + (uint32_t)(ch * L.hplane), pk[ch][0]);
-                            sts32(at + (uint32_t)(ch * L.hplane + L.cpitch), pk[ch][1]);
+                            sts32(at + (uint32_t)(ch * sw * L.cpitch), pk[ch][0]);
+                            sts32(at + (uint32_t)(ch * sw * L.cpitch + L.cpitch), pk[ch][1]);
                         }
                     }
                 }
@@ -293,10 +303,49 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                 }
             }
         }
+    } else if (warp >= kDBase && warp < kDBase + kDWarps) {
+        // ============================== de-interleave (in place) ==============================
+        // RGBRGBRGBRGB -> RRRR GGGG BBBB inside the same 12 bytes, 16 pixels (48 bytes) per step: every staged byte is
+        // permuted once per chunk instead of once per tile window that covers it, and an A fragment of the horizontal
+        // pass becomes ONE LDS.32 per channel.
+        const int dthread = tid - kDBase * 32;
+        int k = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int f = w / per_frame, r = w - f * per_frame;
+            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
+            const VisSchedStrip S = sc.strip[st];
+            const VisSchedSeg G = sc.seg[sg];
+            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            const uint32_t upr = (uint32_t)(S.row_bytes + 47) / 48u;     // 16-pixel units per staged row (the pitch covers them)
+            const uint32_t inv = (1u << 20) / upr + 1u;                  // id / upr == (id * inv) >> 20 for id < 32 * upr <= 2560
+            for (int c = 0; c < n_chunks; ++c, ++k) {
+                const int slot = k & 1, j = k >> 1;
+                mbar_wait(bar(SF, slot), j & 1);
+                const uint32_t stage0 = smem_u32(smem + L.off_stage + slot * L.stage_slot);
+                for (uint32_t id = (uint32_t)dthread; id < kChunk * upr; id += kDWarps * 32) {
+                    const uint32_t row = (id * inv) >> 20, u = id - row * upr;
+                    const uint32_t at = stage0 + row * (uint32_t)L.stage_pitch + 16u * (row >> 2) + 48u * u;
+                    const uint4 q0 = lds128(at), q1 = lds128(at + 16), q2 = lds128(at + 32);
+                    uint32_t x[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t r0 = x[3 * q], r1 = x[3 * q + 1], r2 = x[3 * q + 2];
+                        x[3 * q] = __byte_perm(__byte_perm(r0, r1, 0x0630), r2, 0x5210);
+                        x[3 * q + 1] = __byte_perm(__byte_perm(r0, r1, 0x0741), r2, 0x6210);
+                        x[3 * q + 2] = __byte_perm(__byte_perm(r0, r1, 0x0052), r2, 0x7410);
+                    }
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(at), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(at + 16), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(at + 32), "r"(x[8]), "r"(x[9]), "r"(x[10]), "r"(x[11]) : "memory");
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(DF, slot));
+            }
+        }
     } else if (warp >= kVBase) {
         // ============================== vertical pass ==============================
         const int wv = warp - kVBase;
-        int k = 0, nb = 0, ready = 1;                      // bands 0 and 1 find their slots empty
+        int k = 0, nb = 0, ready = kOSlots - 1;            // the first kOSlots bands find their slots empty
         for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
             const int f = w / per_frame, r = w - f * per_frame;
             const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
@@ -334,17 +383,18 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                             for (int h = 0; h < 2; ++h) {
                                 const int q = 8 * s + 4 * h + t - rel;
                                 const bool ok = i < ihi && (unsigned)q < (unsigned)W;
+                                const uint32_t qa = rec + (uint32_t)(12 * q);
 #pragma unroll
-                                for (int l = 0; l < 3; ++l) a[s][l][2 * h + hh] = ok ? lds32(rec + (uint32_t)((l * W + q) * 4)) : 0u;
+                                for (int l = 0; l < 3; ++l) a[s][l][2 * h + hh] = ok ? lds32(qa + 4 * l) : 0u;
                             }
                     }
                     const int bfirst = (ycount + 16 * mt) / VIS_PATCH, blast = (ycount + ihi - 1) / VIS_PATCH;
 #pragma unroll 1
-                    for (int bs = bfirst; bs <= blast; bs += 2) {        // at most two bands per pass: both slots, never a third
+                    for (int bs = bfirst; bs <= blast; bs += 2) {        // at most two bands per pass: never more slots than there are
                         const int be = min(bs + 1, blast);
                         while (ready < nb + be) {
                             ++ready;
-                            mbar_wait(bar(OE, ready & 1), ((ready >> 1) - 1) & 1);
+                            mbar_wait(bar(OE, ready % kOSlots), (ready / kOSlots - 1) & 1);
                         }
                         // where this thread's two rows go (byte offset into the band tile of column 0, channel 0)
                         bool ok_r[2];
@@ -353,57 +403,63 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                         for (int hh = 0; hh < 2; ++hh) {
                             const int i = 16 * mt + g + 8 * hh, yr = ycount + i, bl = yr / VIS_PATCH;
                             ok_r[hh] = i < ihi && bl >= bs && bl <= be;
-                            off_r[hh] = (uint32_t)(((nb + bl) & 1) * 3 * L.oplane + (yr - bl * VIS_PATCH) * L.opitch);
+                            off_r[hh] = (uint32_t)(((nb + bl) % kOSlots) * 3 * L.oplane + (yr - bl * VIS_PATCH) * NC + 2 * t);
                         }
+                        // ring column 8 jt + g: linear in the tile index (columns past the strip read slack, results unused)
+                        uint32_t ba = ring0 + (uint32_t)((8 * wv + g) * L.cpitch + 4 * t);
+                        uint32_t oa = otile0 + (uint32_t)(8 * wv);
 #pragma unroll 1
-                        for (int jt = wv; jt < n_tiles; jt += kVWarps) {
-                            const int cb = min(8 * jt + g, NC - 1);                      // ring column of this lane's B column
-                            const int chb = (cb >= sw) + (cb >= 2 * sw);
-                            const uint32_t ba = ring0 + (uint32_t)(chb * L.hplane + (cb - chb * sw) * L.cpitch + 4 * t);
-                            const uint32_t b00 = lds32(ba), b01 = lds32(ba + 16), b10 = lds32(ba + 32), b11 = lds32(ba + 48);
-                            int a0[4], a1[4], a2[4];
+                        for (int jt = wv; jt < n_tiles; jt += kVUnroll * kVWarps, ba += (uint32_t)(kVUnroll * 8 * kVWarps * L.cpitch),
+                                 oa += kVUnroll * 8 * kVWarps) {
+                            // kVUnroll independent tiles in flight (tiles past the strip read slack and store nothing)
+                            uint32_t bq[kVUnroll][4];
+                            int acc[kVUnroll][3][4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) { a0[e] = 1 << (VIS_PRECISION_BITS - 1); a1[e] = 0; a2[e] = 0; }
-                            imma_uu_a(a0, a[0][0], b00, b01);
-                            imma_uu_a(a1, a[0][1], b00, b01);
-                            imma_su_a(a2, a[0][2], b00, b01);
-                            imma_uu_a(a0, a[1][0], b10, b11);
-                            imma_uu_a(a1, a[1][1], b10, b11);
-                            imma_su_a(a2, a[1][2], b10, b11);
+                            for (int u = 0; u < kVUnroll; ++u) {
+                                const uint32_t bu = ba + (uint32_t)(u * 8 * kVWarps * L.cpitch);
+                                bq[u][0] = lds32(bu); bq[u][1] = lds32(bu + 16); bq[u][2] = lds32(bu + 32); bq[u][3] = lds32(bu + 48);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { acc[u][0][e] = 1 << (VIS_PRECISION_BITS - 1); acc[u][1][e] = 0; acc[u][2][e] = 0; }
+                            }
+#pragma unroll
+                            for (int u = 0; u < kVUnroll; ++u) {
+                                imma_uu_a(acc[u][0], a[0][0], bq[u][0], bq[u][1]);
+                                imma_uu_a(acc[u][1], a[0][1], bq[u][0], bq[u][1]);
+                                imma_su_a(acc[u][2], a[0][2], bq[u][0], bq[u][1]);
+                            }
+#pragma unroll
+                            for (int u = 0; u < kVUnroll; ++u) {
+                                imma_uu_a(acc[u][0], a[1][0], bq[u][2], bq[u][3]);
+                                imma_uu_a(acc[u][1], a[1][1], bq[u][2], bq[u][3]);
+                                imma_su_a(acc[u][2], a[1][2], bq[u][2], bq[u][3]);
+                            }
                             // D: e = 0/1 -> (row g, columns 2t / 2t+1), e = 2/3 -> (row g+8, columns 2t / 2t+1)
-                            const int cs = 8 * jt + 2 * t;
-                            if (cs < NC) {
-                                const int chs = (cs >= sw) + (cs >= 2 * sw);
-                                const uint32_t oa = otile0 + (uint32_t)(chs * L.oplane + (cs - chs * sw));
-                                if (ok_r[0]) {
-                                    const uint32_t p = pack_sat(recombine(a0[1], a1[1], a2[1]), recombine(a0[0], a1[0], a2[0]), 0u);
-                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa + off_r[0]), "h"((unsigned short)p) : "memory");
-                                }
-                                if (ok_r[1]) {
-                                    const uint32_t p = pack_sat(recombine(a0[3], a1[3], a2[3]), recombine(a0[2], a1[2], a2[2]), 0u);
-                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa + off_r[1]), "h"((unsigned short)p) : "memory");
-                                }
+#pragma unroll
+                            for (int u = 0; u < kVUnroll; ++u) {
+                                const bool in = 8 * (jt + u * kVWarps) + 2 * t < NC;
+                                const uint32_t p0 = pack_sat(recombine(acc[u][0][1], acc[u][1][1], acc[u][2][1]),
+                                                             recombine(acc[u][0][0], acc[u][1][0], acc[u][2][0]), 0u);
+                                const uint32_t p1 = pack_sat(recombine(acc[u][0][3], acc[u][1][3], acc[u][2][3]),
+                                                             recombine(acc[u][0][2], acc[u][1][2], acc[u][2][2]), 0u);
+                                sts16_if(in && ok_r[0], oa + (uint32_t)(u * 8 * kVWarps) + off_r[0], p0);
+                                sts16_if(in && ok_r[1], oa + (uint32_t)(u * 8 * kVWarps) + off_r[1], p1);
                             }
                         }
                         __syncwarp();
                         for (int bb = bs; bb <= be; ++bb)                                // bands completed by the rows stored so far
                             if (min(VIS_PATCH * (bb + 1), seg_rows) <= ycount + ihi && lane == 0)
-                                mbar_arrive(bar(OF, (nb + bb) & 1));
+                                mbar_arrive(bar(OF, (nb + bb) % kOSlots));
                     }
                 }
                 ycount += n;
                 if (c + 1 < n_chunks) {                   // carry: the last W-1 words of every column -> front of the other slot
                     const uint32_t dst0 = smem_u32(smem + L.off_hring + (slot ^ 1) * 3 * L.hplane);
-                    const int per = 8 * (W - 1);
-                    for (int jt = wv; jt < n_tiles; jt += kVWarps)
-                        for (int i = lane; i < per; i += 32) {
-                            const int cc = 8 * jt + i / (W - 1), q = i % (W - 1);
-                            if (cc < NC) {
-                                const int ch = (cc >= sw) + (cc >= 2 * sw);
-                                const uint32_t o = (uint32_t)(ch * L.hplane + (cc - ch * sw) * L.cpitch + 4 * q);
-                                sts32(dst0 + o, lds32(ring0 + o + kChunk));
-                            }
-                        }
+                    for (int jt = wv; jt < n_tiles; jt += kVWarps) {                     // lane (g, t): words t and t + 4 of column 8 jt + g
+                        const int cc = 8 * jt + g;
+                        const uint32_t o = (uint32_t)(cc * L.cpitch + 4 * t);
+                        if (cc < NC && t < W - 1) sts32(dst0 + o, lds32(ring0 + o + kChunk));
+                        if (cc < NC && t + 4 < W - 1) sts32(dst0 + o + 16, lds32(ring0 + o + kChunk + 16));
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(HE, slot));       // H-ring slot and record slot consumed
@@ -421,15 +477,16 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                 const VisSchedStrip S = sc.strip[st];
                 const VisSchedSeg G = sc.seg[sg];
                 const int wpr = (S.x1 - S.x0) / 4;                 // 4-pixel groups per row of the strip
+                const uint32_t oplane = (uint32_t)(S.x1 - S.x0), opitch = 3 * oplane;     // band tile: [row][channel * sw + x]
                 unsigned char* const dst0 = reinterpret_cast<unsigned char*>(frames[f].second) + (size_t)S.x0 * 3;
                 for (int y = G.y0; y < G.y1; y += VIS_PATCH, ++nb) {
-                    const int os = nb & 1, rows = min(VIS_PATCH, G.y1 - y);
-                    mbar_wait(bar(OF, os), (nb >> 1) & 1);
+                    const int os = nb % kOSlots, rows = min(VIS_PATCH, G.y1 - y);
+                    mbar_wait(bar(OF, os), (nb / kOSlots) & 1);
                     const uint32_t otile = smem_u32(smem + L.off_otile + os * 3 * L.oplane);
                     for (int i = sw_i * 32 + lane; i < rows * wpr; i += kSWarps * 32) {
                         const int rr = i / wpr, q = i - rr * wpr;
-                        const uint32_t at = otile + (uint32_t)(rr * L.opitch + q * 4);
-                        const uint32_t A = lds32(at), B = lds32(at + L.oplane), C = lds32(at + 2 * L.oplane);
+                        const uint32_t at = otile + (uint32_t)rr * opitch + (uint32_t)(q * 4);
+                        const uint32_t A = lds32(at), B = lds32(at + oplane), C = lds32(at + 2 * oplane);
                         const uint32_t ab = __byte_perm(A, B, 0x5140), ab2 = __byte_perm(A, B, 0x7362);   // a0 b0 a1 b1 / a2 b2 a3 b3
                         uint32_t* o = reinterpret_cast<uint32_t*>(dst0 + (size_t)(y + rr) * dst_pitch + (size_t)q * 12);
                         o[0] = __byte_perm(ab, C, 0x2410);                                      // a0 b0 c0 a1
@@ -442,15 +499,14 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             }
         } else {
             // lane-constant description of up to five 16-byte chunks (c, q) of a patch row: item = lane + 32 * i < 147
-            int sa[5], sb[5], go[5], lo[5];
+            int ca[5], ra[5], rb[5], xa[5], xb[5], go[5], lo[5];
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
                 const int item = min(lane + 32 * i, 146);
                 const int c = item / 49, q = item - c * 49;
                 const int f0 = 4 * q, f2 = f0 + 2;
-                const int pya = f0 / VIS_PATCH, pyb = f2 / VIS_PATCH;
-                sa[i] = c * L.oplane + pya * L.opitch + (f0 - pya * VIS_PATCH);
-                sb[i] = c * L.oplane + pyb * L.opitch + (f2 - pyb * VIS_PATCH);
+                ca[i] = c; ra[i] = f0 / VIS_PATCH; rb[i] = f2 / VIS_PATCH;
+                xa[i] = f0 - ra[i] * VIS_PATCH; xb[i] = f2 - rb[i] * VIS_PATCH;
                 go[i] = c * 392 + f0;
                 lo[i] = c * 256;
             }
@@ -461,10 +517,17 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                 const VisSchedStrip S = sc.strip[st];
                 const VisSchedSeg G = sc.seg[sg];
                 const int n_patches = (S.x1 - S.x0) / VIS_PATCH, gx0 = S.x0 / VIS_PATCH;
+                const int oplane = S.x1 - S.x0, opitch = 3 * oplane;                    // band tile: [row][channel * sw + x]
+                int sa[5], sb[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    sa[i] = ca[i] * oplane + ra[i] * opitch + xa[i];
+                    sb[i] = ca[i] * oplane + rb[i] * opitch + xb[i];
+                }
                 float* const frame_out = pixel_values + (size_t)frames[f].second * VIS_ROW_FLOATS;
                 for (int gy = G.y0 / VIS_PATCH; gy < G.y1 / VIS_PATCH; ++gy, ++nb) {
-                    const int os = nb & 1;
-                    mbar_wait(bar(OF, os), (nb >> 1) & 1);
+                    const int os = nb % kOSlots;
+                    mbar_wait(bar(OF, os), (nb / kOSlots) & 1);
                     const unsigned char* otile = smem + L.off_otile + os * 3 * L.oplane;
                     float* band = frame_out + (size_t)((gy >> 1) * half_gw * 4 + (gy & 1) * 2) * VIS_ROW_FLOATS;
                     for (int gp = sw_i; gp < n_patches; gp += kSWarps) {

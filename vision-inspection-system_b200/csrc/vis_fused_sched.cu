@@ -445,6 +445,13 @@ inline int stage_pitch_for(int span_bytes) {
     return p;
 }
 
+// integer tensor-path kernel: rows are de-interleaved in place in 48-byte units, so the pitch covers whole units
+inline int stage_pitch_for_mma(int span_bytes) {
+    int p = align_up(span_bytes, 48);
+    if ((p / 16) % 2 == 0) p += 48;
+    return p;
+}
+
 }  // namespace
 
 extern "C" {
@@ -549,9 +556,10 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
             worst_span = span > worst_span ? span : worst_span;
             worst_w = (b1 - b0) * unit > worst_w ? (b1 - b0) * unit : worst_w;
         }
-        if (worst_w <= max_w && layout_bytes(stage_pitch_for(worst_span), worst_w) <= kSmemMax) {
+        const int pitch_n = mma ? stage_pitch_for_mma(worst_span) : stage_pitch_for(worst_span);
+        if (worst_w <= max_w && layout_bytes(pitch_n, worst_w) <= kSmemMax) {
             n_strips = n;
-            s.stage_pitch = stage_pitch_for(worst_span);
+            s.stage_pitch = pitch_n;
             s.max_strip_w = worst_w;
         }
     }
@@ -720,9 +728,10 @@ int vis_sched_pack_records_mma(int out_size, const int32_t* k, const int32_t* bo
                 return VIS_E_UNSUPPORTED;
             }
             const int at = first + t - 4 * bw;                       // byte position inside the W-word window
-            r[at] = (unsigned char)(c & 0xff);
-            r[4 * words + at] = (unsigned char)((c >> 8) & 0xff);
-            r[8 * words + at] = (unsigned char)((c >> 16) & 0xff);   // signed limb (arithmetic shift), two's complement byte
+            unsigned char* q = r + 12 * (at >> 2) + (at & 3);          // word at >> 2: limbs 0, 1, 2 in consecutive 32-bit words
+            q[0] = (unsigned char)(c & 0xff);
+            q[4] = (unsigned char)((c >> 8) & 0xff);
+            q[8] = (unsigned char)((c >> 16) & 0xff);                // signed limb (arithmetic shift), two's complement byte
         }
         r32[3 * words] = bw;
         r32[3 * words + 1] = first >> 2;
