@@ -277,7 +277,7 @@ def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
     hrec, vrec = _mma_records(ht, W), _mma_records(vt, W)
     rng = np.random.default_rng(5)
 
-    # ---- horizontal pass: tiles of 8 outputs per strip, B gathered from the records, K = 32 * KS pixels from word kw ----
+    # ---- horizontal pass: tiles of 16 outputs per strip, A gathered from the records, K = 32 * KS pixels from word kw ----
     row = rng.integers(0, 256, src_w + 4 * 8 * KS + 64, dtype=np.uint8)       # reads past the row meet zero coefficients
     row[src_w:] = 255
     want = _direct_pass(ht, row[:src_w])
@@ -285,11 +285,11 @@ def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
     for S in sc["strip"][:head["n_strips"]]:
         x0, x1, px0 = int(S["x0"]), int(S["x1"]), int(S["px0"])
         sw = x1 - x0
-        for jt in range((sw + 7) // 8):
-            kw = int(hrec[x0 + 8 * jt, 3 * W + 1])
+        for jt in range((sw + 15) // 16):
+            kw = int(hrec[x0 + 16 * jt, 3 * W + 1])
             assert 4 * kw >= px0
-            for g in range(8):
-                xr = x0 + min(8 * jt + g, sw - 1)
+            for m in range(16):
+                xr = x0 + min(16 * jt + m, sw - 1)
                 bw = int(hrec[xr, 3 * W])
                 limbs = _limb_rows(hrec[xr], W)
                 col = np.zeros((3, 32 * KS), np.int64)
@@ -299,7 +299,7 @@ def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
                         col[:, 4 * wd:4 * wd + 4] = limbs[:, 4 * q:4 * q + 4]
                 px = row[4 * kw:4 * kw + 32 * KS].astype(np.int64)
                 acc = (px * col[0]).sum() + ((px * col[1]).sum() << 8) + ((px * col[2]).sum() << 16) + (1 << 21)
-                if 8 * jt + g < sw:
+                if 16 * jt + m < sw:
                     got[xr] = np.clip(acc >> 22, 0, 255)
     assert np.array_equal(got, want)
 

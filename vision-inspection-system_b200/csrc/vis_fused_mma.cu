@@ -31,21 +31,18 @@ using namespace visf;
 namespace {
 
 #ifndef VIS_MMA_HWARPS
-#define VIS_MMA_HWARPS 10
+#define VIS_MMA_HWARPS 12
 #endif
 #ifndef VIS_MMA_VWARPS
 #define VIS_MMA_VWARPS 8
 #endif
 #ifndef VIS_MMA_SWARPS
-#define VIS_MMA_SWARPS 2
+#define VIS_MMA_SWARPS 3
 #endif
-#ifndef VIS_MMA_DWARPS
-#define VIS_MMA_DWARPS 3
-#endif
-constexpr int kHWarps = VIS_MMA_HWARPS, kVWarps = VIS_MMA_VWARPS, kSWarps = VIS_MMA_SWARPS, kDWarps = VIS_MMA_DWARPS;
-// warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < D < S < V
-constexpr int kHBase = 0, kLBase = kHWarps, kDBase = kHWarps + 1, kSBase = kDBase + kDWarps, kVBase = kSBase + kSWarps;
-constexpr int kThreads = (kHWarps + kVWarps + kSWarps + kDWarps + 1) * 32;
+constexpr int kHWarps = VIS_MMA_HWARPS, kVWarps = VIS_MMA_VWARPS, kSWarps = VIS_MMA_SWARPS;
+// warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
+constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kSBase + kSWarps;
+constexpr int kThreads = (kHWarps + kVWarps + kSWarps + 1) * 32;
 #ifndef VIS_MMA_VUNROLL
 #define VIS_MMA_VUNROLL 1
 #endif
@@ -60,7 +57,7 @@ constexpr int kStageSkew = 128;                   // 16 bytes x (row >> 2): 112 
 #endif
 constexpr int kOSlots = VIS_MMA_OSLOTS;           // band tiles in flight between the vertical pass and the store warps
 // full/empty pairs, two slots each; band tiles: kOSlots each
-enum Bar { SF = 0, SE = 2, HF = 4, HE = 6, VF = 8, DF = 10, OF = 12, OE = 12 + kOSlots, kBars = 12 + 2 * kOSlots };
+enum Bar { SF = 0, SE = 2, HF = 4, HE = 6, VF = 8, OF = 10, OE = 10 + kOSlots, kBars = 10 + 2 * kOSlots };
 
 // words per record: W words x 3 limbs (limb-minor), then the absolute word index of record byte 0 and of the window's first tap
 // (4 mod 8 words: the eight records a fragment gather touches start in eight different bank groups)
@@ -157,7 +154,6 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             mbar_init(bar(HF, s), kHWarps);
             mbar_init(bar(HE, s), kVWarps);
             mbar_init(bar(VF, s), 1);
-            mbar_init(bar(DF, s), kDWarps);
         }
         for (int s = 0; s < kOSlots; ++s) {
             mbar_init(bar(OF, s), kVWarps);
@@ -212,6 +208,13 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
         }
     } else if (warp < kHBase + kHWarps) {
         // ============================== horizontal pass ==============================
+        // D[16 output columns][8 rows] = A[16 outputs][32 k] (coefficient limbs) x B[32 k][8 rows] (pixels of one channel).
+        // A 16-output window is hardly wider than an 8-output one (60 vs 36 of the 64 pixels two k-steps hold at 4K), so
+        // the pixels are fetched half as often as with the rows on the M side, and they are de-interleaved in registers
+        // (3 LDS.32 + 6 PRMT give the B words of all three channels): no separate pass over the staged chunk.
+        // N-tile c holds rows 4g + c (n = g): with the 16-byte skew per 4 rows the eight rows of a fragment load sit in
+        // eight different bank groups; the four N-tiles of a chunk give a thread rows 8t..8t+3 and 8t+4..8t+7 of columns
+        // g and g + 8: four STS.32 per channel into the TRANSPOSED H ring [channel * sw + column][row].
         const int hw = warp - kHBase;
         int k = 0, sl = 0;
         for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++sl) {
@@ -220,43 +223,54 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             const VisSchedStrip S = sc.strip[st];
             const VisSchedSeg G = sc.seg[sg];
             const int sw = S.x1 - S.x0;
-            const int n_tiles = (sw + 7) >> 3;
+            const int n_tiles = (sw + 15) >> 4;
             const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
             const uint32_t hrec0 = smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot);
             for (int c = 0; c < n_chunks; ++c, ++k) {
                 const int slot = k & 1, j = k >> 1;
-                mbar_wait(bar(DF, slot), j & 1);                // the D warps have de-interleaved the chunk in place
-                mbar_wait(bar(SF, slot), j & 1);                // (complete long ago: the strip's records ride on it)
-                const uint32_t stage0 = smem_u32(smem + L.off_stage + slot * L.stage_slot);
+                mbar_wait(bar(SF, slot), j & 1);
                 if (k >= 2) mbar_wait(bar(HE, slot), (j - 1) & 1);
-                // this lane's rows 4g..4g+3 of the stage slot (skewed) and of the ring columns it stores
-                const uint32_t srow = stage0 + (uint32_t)(4 * g * L.stage_pitch + 16 * g);
-                const uint32_t hring = smem_u32(smem + L.off_hring + slot * 3 * L.hplane) + (uint32_t)(CARRY + 4 * g);
+                // row 4g of the stage slot (skewed by 16 bytes per 4 rows); rows 8t.. of the ring columns this lane stores
+                const uint32_t srow = smem_u32(smem + L.off_stage + slot * L.stage_slot) + (uint32_t)(4 * g * L.stage_pitch + 16 * g);
+                const uint32_t hring = smem_u32(smem + L.off_hring + slot * 3 * L.hplane) + (uint32_t)(CARRY + 8 * t);
 #pragma unroll 1
                 for (int jt = hw; jt < n_tiles; jt += kHWarps) {
-                    // ---- B: coefficient limbs of the tile's 8 outputs, 32 input pixels per k-step ----
-                    const int xr = min(8 * jt + g, sw - 1);                              // output column of this lane's B column
-                    const uint32_t rec = hrec0 + (uint32_t)(xr * STRIDE * 4);
-                    const int bw = (int)lds32(rec + (uint32_t)(3 * W * 4));
-                    const int kw = __shfl_sync(0xffffffffu, (int)lds32(rec + (uint32_t)((3 * W + 1) * 4)), 0);   // first word of the tile's window
-                    uint32_t b[KS][3][2];
+                    // ---- A: coefficient limbs of outputs 16 jt + g and 16 jt + g + 8, 32 input pixels per k-step ----
+                    const int xa = min(16 * jt + g, sw - 1), xb = min(16 * jt + g + 8, sw - 1);
+                    const uint32_t reca = hrec0 + (uint32_t)(xa * STRIDE * 4), recb = hrec0 + (uint32_t)(xb * STRIDE * 4);
+                    const int bwa = (int)lds32(reca + (uint32_t)(3 * W * 4)), bwb = (int)lds32(recb + (uint32_t)(3 * W * 4));
+                    const int kw = __shfl_sync(0xffffffffu, (int)lds32(reca + (uint32_t)((3 * W + 1) * 4)), 0);  // first word of the tile's window
+                    uint32_t a[KS][3][4];
 #pragma unroll
                     for (int s = 0; s < KS; ++s)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const int q = kw + 8 * s + 4 * h + t - bw;
-                            const bool ok = (unsigned)q < (unsigned)W;
-                            const uint32_t qa = rec + (uint32_t)(12 * q);              // limbs of a word sit side by side
+                            const int qa = kw + 8 * s + 4 * h + t - bwa, qb = kw + 8 * s + 4 * h + t - bwb;
+                            const bool oka = (unsigned)qa < (unsigned)W, okb = (unsigned)qb < (unsigned)W;
+                            const uint32_t pa = reca + (uint32_t)(12 * qa), pb = recb + (uint32_t)(12 * qb);   // limbs side by side
 #pragma unroll
-                            for (int l = 0; l < 3; ++l) b[s][l][h] = ok ? lds32(qa + 4 * l) : 0u;
+                            for (int l = 0; l < 3; ++l) {
+                                a[s][l][2 * h] = oka ? lds32(pa + 4 * l) : 0u;
+                                a[s][l][2 * h + 1] = okb ? lds32(pb + 4 * l) : 0u;
+                            }
                         }
-                    // group (kw + t) of the stage row: 12 bytes = 4 pixels, channel planes of 4 bytes
+                    // pixel group (kw + t) of a stage row: 12 bytes = 4 RGB pixels
                     const uint32_t g_off = (uint32_t)(12 * (kw + t - (S.px0 >> 2)));
-                    uint32_t pk[3][2];                                                   // rows 4g+2, 4g+3 of columns 2t, 2t+1 per channel
+                    uint32_t P[3][4];                                   // per channel and N-tile: the four samples of D, saturated
 #pragma unroll
-                    for (int mt = 1; mt >= 0; --mt) {
-                        const uint32_t r0a = srow + (uint32_t)(2 * mt * L.stage_pitch) + g_off;      // row 4g + 2mt
-                        const uint32_t r1a = r0a + (uint32_t)L.stage_pitch;                          // row 4g + 2mt + 1
+                    for (int cn = 0; cn < 4; ++cn) {                    // N-tile cn: rows 4g + cn
+                        const uint32_t ra = srow + (uint32_t)(cn * L.stage_pitch) + g_off;
+                        uint32_t b[3][KS][2];
+#pragma unroll
+                        for (int s = 0; s < KS; ++s)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t o = (uint32_t)(96 * s + 48 * h);
+                                const uint32_t x0 = lds32(ra + o), x1 = lds32(ra + o + 4), x2 = lds32(ra + o + 8);
+                                b[0][s][h] = __byte_perm(__byte_perm(x0, x1, 0x0630), x2, 0x5210);
+                                b[1][s][h] = __byte_perm(__byte_perm(x0, x1, 0x0741), x2, 0x6210);
+                                b[2][s][h] = __byte_perm(__byte_perm(x0, x1, 0x0052), x2, 0x7410);
+                            }
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
                             int acc[3][4];
@@ -264,35 +278,31 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                             for (int e = 0; e < 4; ++e) { acc[0][e] = 1 << (VIS_PRECISION_BITS - 1); acc[1][e] = 0; acc[2][e] = 0; }
 #pragma unroll
                             for (int s = 0; s < KS; ++s) {
-                                uint32_t a[4];
-                                a[0] = lds32(r0a + (uint32_t)(96 * s + 4 * ch));
-                                a[1] = lds32(r1a + (uint32_t)(96 * s + 4 * ch));
-                                a[2] = lds32(r0a + (uint32_t)(96 * s + 48 + 4 * ch));
-                                a[3] = lds32(r1a + (uint32_t)(96 * s + 48 + 4 * ch));
-                                imma_uu(acc[0], a, b[s][0][0], b[s][0][1]);
-                                imma_uu(acc[1], a, b[s][1][0], b[s][1][1]);
-                                imma_us(acc[2], a, b[s][2][0], b[s][2][1]);
+                                imma_uu_a(acc[0], a[s][0], b[ch][s][0], b[ch][s][1]);
+                                imma_uu_a(acc[1], a[s][1], b[ch][s][0], b[ch][s][1]);
+                                imma_su_a(acc[2], a[s][2], b[ch][s][0], b[ch][s][1]);
                             }
-                            // D: e = 0/1 -> (row 4g+2mt, columns 2t / 2t+1), e = 2/3 -> (row 4g+2mt+1, columns 2t / 2t+1)
+                            // D: e = 0/1 -> (column g, rows 8t+cn / 8t+4+cn), e = 2/3 -> (column g+8, same rows)
                             int v[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) v[e] = recombine(acc[0][e], acc[1][e], acc[2][e]);
-                            if (mt == 1) {
-                                pk[ch][0] = pack_sat(v[2], v[0], 0u);
-                                pk[ch][1] = pack_sat(v[3], v[1], 0u);
-                            } else {
-                                pk[ch][0] = pack_sat(v[2], v[0], pk[ch][0]);             // bytes: rows 4g, 4g+1, 4g+2, 4g+3
-                                pk[ch][1] = pack_sat(v[3], v[1], pk[ch][1]);
-                            }
+                            P[ch][cn] = pack_sat(v[1], v[0], pack_sat(v[3], v[2], 0u));              // byte e = sample e
                         }
                     }
-                    const int xc = 8 * jt + 2 * t;                                       // strip widths are multiples of 4
-                    if (xc < sw) {                                                       // ring column = channel * sw + x
-                        const uint32_t at = hring + (uint32_t)(xc * L.cpitch);
+                    // 4 x 4 byte transpose per channel: word e = samples e of N-tiles 0..3 = four consecutive rows
+                    const bool oka = 16 * jt + g < sw, okb = 16 * jt + g + 8 < sw;
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            sts32(at + (uint32_t)(ch * sw * L.cpitch), pk[ch][0]);
-                            sts32(at + (uint32_t)(ch * sw * L.cpitch + L.cpitch), pk[ch][1]);
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const uint32_t t0 = __byte_perm(P[ch][0], P[ch][1], 0x5140), t1 = __byte_perm(P[ch][2], P[ch][3], 0x5140);
+                        const uint32_t t2 = __byte_perm(P[ch][0], P[ch][1], 0x7362), t3 = __byte_perm(P[ch][2], P[ch][3], 0x7362);
+                        const uint32_t at = hring + (uint32_t)((ch * sw + 16 * jt + g) * L.cpitch);       // ring column = channel * sw + x
+                        if (oka) {
+                            sts32(at, __byte_perm(t0, t1, 0x5410));
+                            sts32(at + 4, __byte_perm(t0, t1, 0x7632));
+                        }
+                        if (okb) {
+                            sts32(at + (uint32_t)(8 * L.cpitch), __byte_perm(t2, t3, 0x5410));
+                            sts32(at + (uint32_t)(8 * L.cpitch) + 4, __byte_perm(t2, t3, 0x7632));
                         }
                     }
                 }
@@ -301,45 +311,6 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                     mbar_arrive(bar(SE, slot));          // stage slot may be refilled
                     mbar_arrive(bar(HF, slot));          // H-ring slot is complete
                 }
-            }
-        }
-    } else if (warp >= kDBase && warp < kDBase + kDWarps) {
-        // ============================== de-interleave (in place) ==============================
-        // RGBRGBRGBRGB -> RRRR GGGG BBBB inside the same 12 bytes, 16 pixels (48 bytes) per step: every staged byte is
-        // permuted once per chunk instead of once per tile window that covers it, and an A fragment of the horizontal
-        // pass becomes ONE LDS.32 per channel.
-        const int dthread = tid - kDBase * 32;
-        int k = 0;
-        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-            const int f = w / per_frame, r = w - f * per_frame;
-            const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
-            const VisSchedStrip S = sc.strip[st];
-            const VisSchedSeg G = sc.seg[sg];
-            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
-            const uint32_t upr = (uint32_t)(S.row_bytes + 47) / 48u;     // 16-pixel units per staged row (the pitch covers them)
-            const uint32_t inv = (1u << 20) / upr + 1u;                  // id / upr == (id * inv) >> 20 for id < 32 * upr <= 2560
-            for (int c = 0; c < n_chunks; ++c, ++k) {
-                const int slot = k & 1, j = k >> 1;
-                mbar_wait(bar(SF, slot), j & 1);
-                const uint32_t stage0 = smem_u32(smem + L.off_stage + slot * L.stage_slot);
-                for (uint32_t id = (uint32_t)dthread; id < kChunk * upr; id += kDWarps * 32) {
-                    const uint32_t row = (id * inv) >> 20, u = id - row * upr;
-                    const uint32_t at = stage0 + row * (uint32_t)L.stage_pitch + 16u * (row >> 2) + 48u * u;
-                    const uint4 q0 = lds128(at), q1 = lds128(at + 16), q2 = lds128(at + 32);
-                    uint32_t x[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t r0 = x[3 * q], r1 = x[3 * q + 1], r2 = x[3 * q + 2];
-                        x[3 * q] = __byte_perm(__byte_perm(r0, r1, 0x0630), r2, 0x5210);
-                        x[3 * q + 1] = __byte_perm(__byte_perm(r0, r1, 0x0741), r2, 0x6210);
-                        x[3 * q + 2] = __byte_perm(__byte_perm(r0, r1, 0x0052), r2, 0x7410);
-                    }
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(at), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(at + 16), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]) : "memory");
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(at + 32), "r"(x[8]), "r"(x[9]), "r"(x[10]), "r"(x[11]) : "memory");
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(DF, slot));
             }
         }
     } else if (warp >= kVBase) {

@@ -445,13 +445,6 @@ inline int stage_pitch_for(int span_bytes) {
     return p;
 }
 
-// integer tensor-path kernel: rows are de-interleaved in place in 48-byte units, so the pitch covers whole units
-inline int stage_pitch_for_mma(int span_bytes) {
-    int p = align_up(span_bytes, 48);
-    if ((p / 16) % 2 == 0) p += 48;
-    return p;
-}
-
 }  // namespace
 
 extern "C" {
@@ -497,12 +490,12 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     const bool mma = want_mma && dp_words > 0;      // same limb records, both passes on the integer tensor path
     int mma_ks = 0;
     if (mma) {
-        // k-steps of 32 input pixels that the window of a tile of 8 outputs spans, counted from the 4-pixel word of the
+        // k-steps of 32 input pixels that the window of a tile of 16 outputs spans, counted from the 4-pixel word of the
         // tile's first tap.  Tiles start at multiples of 4 columns wherever the strips fall, so this is a property of the
         // geometry (the records are cached per geometry); beyond the kernel's register budget: the packed-byte kernel.
         for (int x = 0; x < dst_w; x += 4) {
             int lastpx = 0;
-            for (int o = x; o < x + 8 && o < dst_w; ++o) lastpx = std::max(lastpx, hb[2 * o] + hb[2 * o + 1] - 1);
+            for (int o = x; o < x + 16 && o < dst_w; ++o) lastpx = std::max(lastpx, hb[2 * o] + hb[2 * o + 1] - 1);
             mma_ks = std::max(mma_ks, (lastpx + 1 - (hb[2 * x] & ~3) + 31) / 32);
         }
         if (mma_ks > visf::mma_max_ksteps())
@@ -556,7 +549,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
             worst_span = span > worst_span ? span : worst_span;
             worst_w = (b1 - b0) * unit > worst_w ? (b1 - b0) * unit : worst_w;
         }
-        const int pitch_n = mma ? stage_pitch_for_mma(worst_span) : stage_pitch_for(worst_span);
+        const int pitch_n = stage_pitch_for(worst_span);
         if (worst_w <= max_w && layout_bytes(pitch_n, worst_w) <= kSmemMax) {
             n_strips = n;
             s.stage_pitch = pitch_n;
