@@ -264,7 +264,7 @@ def _direct_pass(table, line):
 @pytest.mark.parametrize("src_h,src_w,dst_h,dst_w,filt,mode", [
     (2160, 3840, 756, 1316, N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES),      # 4K at the default max_pixels
     (2160, 3840, 576, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),                # Auditor thumbnail, 25 taps
-    (1080, 1920, 576, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),
+    (1600, 2560, 640, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),
     (700, 1000, 252, 364, N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES),
 ])
 def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
@@ -333,3 +333,12 @@ def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
             yo += n
         assert yo == y1
     assert np.array_equal(got_v, want_v)
+
+
+def test_mma_only_where_one_m_tile_covers_a_chunk():
+    """Vertical scale < 2 (more than 16 output rows per 32-row chunk) keeps the packed-byte kernel: same records family
+    (dp_words > 0) but mma_ks == 0, so the engine packs IDP.4A records."""
+    rc, sc, _, _ = build(1080, 1920, 576, 1024, 1920 * 3, 1, N.FILTER_LANCZOS, N.SCHED_OUT_U8 | N.SCHED_FLAG_MMA)
+    assert rc == N.VIS_OK and sc["head"]["dp_words"] >= 4 and sc["head"]["mma_ks"] == 0
+    rc, sc, _, _ = build(2160, 3840, 576, 1024, 3840 * 3, 1, N.FILTER_LANCZOS, N.SCHED_OUT_U8 | N.SCHED_FLAG_MMA)
+    assert rc == N.VIS_OK and sc["head"]["mma_ks"] in (2, 3)

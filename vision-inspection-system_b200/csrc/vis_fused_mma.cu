@@ -34,10 +34,10 @@ namespace {
 #define VIS_MMA_HWARPS 12
 #endif
 #ifndef VIS_MMA_VWARPS
-#define VIS_MMA_VWARPS 8
+#define VIS_MMA_VWARPS 9
 #endif
 #ifndef VIS_MMA_SWARPS
-#define VIS_MMA_SWARPS 3
+#define VIS_MMA_SWARPS 2
 #endif
 constexpr int kHWarps = VIS_MMA_HWARPS, kVWarps = VIS_MMA_VWARPS, kSWarps = VIS_MMA_SWARPS;
 // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V

@@ -487,7 +487,9 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
         if (dp_words) cls = 4 * dp_words - 3;
     }
     const bool h_pull = !dp_words && cls > 16;
-    const bool mma = want_mma && dp_words > 0;      // same limb records, both passes on the integer tensor path
+    // same limb records, both passes on the integer tensor path — where one M-tile of 16 output rows covers what a 32-row
+    // chunk emits (vertical scale >= 2); below that the second M-tile would run nearly empty and IDP.4A is as fast
+    const bool mma = want_mma && dp_words > 0 && (int64_t)src_h >= 2 * (int64_t)dst_h;
     int mma_ks = 0;
     if (mma) {
         // k-steps of 32 input pixels that the window of a tile of 16 outputs spans, counted from the 4-pixel word of the
