@@ -217,7 +217,7 @@ typedef struct VisSched {            /* opaque to callers: filled by vis_sched_b
     int32_t n_vwarps;                /* 16-slot kernel: vertical-pass warps of the launch (6 / 4 / 3: fewer for strong downscales) */
     int32_t dp_words;                /* > 0: packed-byte kernels (vis_fused_dp.cu / vis_fused_mma.cu), W words of 4 taps per window (4..9) */
     int32_t mma_ks;                  /* > 0: integer tensor-path kernel (vis_fused_mma.cu); 32-pixel k-steps per tile of 16 output columns */
-    int32_t reserved0;               /* keeps the arrays below 8-byte aligned                                            */
+    int32_t chunk_rows;              /* input rows a chunk advances by (32; 28 / 24 for the tensor-path kernel at vertical scales < 2) */
     VisSchedStrip strip[VIS_SCHED_MAX_STRIPS];
     VisSchedSub   sub[VIS_SCHED_MAX_STRIPS][VIS_SCHED_MAX_SUBS];
     VisSchedSeg   seg[VIS_SCHED_MAX_SEGS];

@@ -265,6 +265,8 @@ def _direct_pass(table, line):
     (2160, 3840, 756, 1316, N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES),      # 4K at the default max_pixels
     (2160, 3840, 576, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),                # Auditor thumbnail, 25 taps
     (1600, 2560, 640, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),
+    (1080, 1920, 576, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),                # 17 rows per 32-row chunk: 28-row chunks
+    (2160, 3840, 1152, 2048, N.FILTER_LANCZOS, N.SCHED_OUT_U8),
     (700, 1000, 252, 364, N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES),
 ])
 def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
@@ -305,14 +307,16 @@ def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
 
     # ---- vertical pass: chunks of 32 ring rows + carry, A gathered from the chunk's records relative to ring byte 0 ----
     carry = 4 * (W - 1)
+    CR = int(head["chunk_rows"])
+    assert CR in (24, 28, 32)
     col_px = rng.integers(0, 256, (5, src_h), dtype=np.uint8)
     want_v = _direct_pass(vt, col_px)
     got_v = np.zeros((5, dst_h), np.uint8)
     for G_ in sc["seg"][:head["n_segs"]]:
         y0, y1, r_first, r_end, moff = (int(G_[k]) for k in ("y0", "y1", "r_first", "r_end", "mask_off"))
         yo = y0
-        for c in range((r_end - r_first + 31) // 32):
-            r0 = r_first + 32 * c
+        for c in range((r_end - r_first + CR - 1) // CR):
+            r0 = r_first + CR * c
             n = sum(bin(read_mask(sc["mask"], moff, 2 * c + i, 16)[0]).count("1") for i in range(2))
             assert n <= 32
             cbw = (r0 - carry) >> 2
@@ -335,10 +339,30 @@ def test_mma_fragment_indexing_replay(src_h, src_w, dst_h, dst_w, filt, mode):
     assert np.array_equal(got_v, want_v)
 
 
-def test_mma_only_where_one_m_tile_covers_a_chunk():
-    """Vertical scale < 2 (more than 16 output rows per 32-row chunk) keeps the packed-byte kernel: same records family
-    (dp_words > 0) but mma_ks == 0, so the engine packs IDP.4A records."""
-    rc, sc, _, _ = build(1080, 1920, 576, 1024, 1920 * 3, 1, N.FILTER_LANCZOS, N.SCHED_OUT_U8 | N.SCHED_FLAG_MMA)
-    assert rc == N.VIS_OK and sc["head"]["dp_words"] >= 4 and sc["head"]["mma_ks"] == 0
-    rc, sc, _, _ = build(2160, 3840, 576, 1024, 3840 * 3, 1, N.FILTER_LANCZOS, N.SCHED_OUT_U8 | N.SCHED_FLAG_MMA)
-    assert rc == N.VIS_OK and sc["head"]["mma_ks"] in (2, 3)
+def test_mma_chunk_rows_follow_the_vertical_scale():
+    """One M-tile of 16 output rows per chunk: 32-row chunks from vertical scale 2 on, 28 / 24 below; under 24 the
+    packed-byte kernel keeps the geometry (dp_words > 0, mma_ks == 0, IDP.4A records)."""
+    for (sh, swd, dh, dw, want) in ((2160, 3840, 576, 1024, 32), (1080, 1920, 576, 1024, 28), (900, 1600, 576, 1024, 24),
+                                    (800, 1400, 576, 1008, 0)):
+        rc, sc, _, _ = build(sh, swd, dh, dw, (swd * 3 + 15) // 16 * 16, 1, N.FILTER_LANCZOS, N.SCHED_OUT_U8 | N.SCHED_FLAG_MMA)
+        assert rc == N.VIS_OK and sc["head"]["dp_words"] >= 4
+        if want:
+            assert sc["head"]["mma_ks"] in (1, 2, 3) and sc["head"]["chunk_rows"] == want, (sh, sc["head"])
+        else:
+            assert sc["head"]["mma_ks"] == 0 and sc["head"]["chunk_rows"] == 32, (sh, sc["head"])
+
+
+def test_kernel_family_is_a_property_of_the_geometry():
+    """The engine packs the records once per geometry: the kernel family and chunk advance that vis_sched_build picks may
+    depend neither on the segment count nor on the row pitch."""
+    for (sh, swd, dh, dw, filt, mode) in ((64, 96, 56, 84, N.FILTER_BICUBIC, N.SCHED_OUT_U8),
+                                          (1080, 1920, 576, 1024, N.FILTER_LANCZOS, N.SCHED_OUT_U8),
+                                          (2160, 3840, 756, 1316, N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES),
+                                          (1536, 2048, 840, 1148, N.FILTER_BICUBIC, N.SCHED_OUT_PIXEL_VALUES)):
+        seen = set()
+        for pitch in ((swd * 3 + 15) // 16 * 16, (swd * 3 + 15) // 16 * 16 + 64):
+            for vs in (1, 2, 3, 4, 7):
+                rc, sc, _, _ = build(sh, swd, dh, dw, pitch, vs, filt, mode | N.SCHED_FLAG_MMA)
+                assert rc == N.VIS_OK
+                seen.add((int(sc["head"]["dp_words"]), int(sc["head"]["mma_ks"]), int(sc["head"]["chunk_rows"])))
+        assert len(seen) == 1, (sh, swd, seen)

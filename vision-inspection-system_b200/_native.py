@@ -44,7 +44,7 @@ FRAME_REF_DTYPE = np.dtype([("src", np.uint64), ("row0", np.int64)], align=True)
 SCHED_HEAD_DTYPE = np.dtype([("src_h", np.int32), ("src_w", np.int32), ("dst_h", np.int32), ("dst_w", np.int32),
                              ("src_pitch", np.int64), ("kt", np.int32), ("n_strips", np.int32), ("n_segs", np.int32),
                              ("stage_pitch", np.int32), ("max_strip_w", np.int32), ("per_index", np.int32), ("ring", np.int32),
-                             ("n_subs", np.int32), ("out_mode", np.int32), ("h_pull", np.int32), ("n_vwarps", np.int32), ("dp_words", np.int32), ("mma_ks", np.int32), ("reserved0", np.int32)], align=True)
+                             ("n_subs", np.int32), ("out_mode", np.int32), ("h_pull", np.int32), ("n_vwarps", np.int32), ("dp_words", np.int32), ("mma_ks", np.int32), ("chunk_rows", np.int32)], align=True)
 SCHED_OUT_PIXEL_VALUES, SCHED_OUT_U8 = 0, 1
 SCHED_FLAG_DP4A = 0x100
 SCHED_FLAG_MMA = 0x200

@@ -137,6 +137,7 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
     const int W = sc.dp_words;
     const int STRIDE = rec_stride_mma(W);
     const int CARRY = 4 * (W - 1);                     // rows of the previous chunk a window may reach back to
+    const int CR = sc.chunk_rows;                      // input rows a chunk advances by (<= kChunk: the stage / ring slots hold kChunk)
     const int tid = threadIdx.x, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;             // fragment coordinates of mma.m16n8k32
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);               // warp-uniform for the compiler
@@ -173,14 +174,14 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             const VisSchedSeg G = sc.seg[sg];
             const unsigned char* src = frames[f].src + (size_t)S.px0 * 3;
             const uint32_t rec_bytes = (uint32_t)(S.x1 - S.x0 + 1) * STRIDE * 4;
-            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            const int n_chunks = (G.r_end - G.r_first + CR - 1) / CR;
             int yo = G.y0;
             for (int c = 0; c < n_chunks; ++c, ++k) {
                 const int slot = k & 1;
                 const uint32_t prev = ((k >> 1) - 1) & 1;
                 if (k >= 2) mbar_wait(bar(SE, slot), prev);                 // H is done with the stage slot
-                const int r0 = G.r_first + c * kChunk;
-                const int rows = max(0, min(kChunk, sc.src_h - r0));        // r_end may include virtual rows past the image
+                const int r0 = G.r_first + c * CR;
+                const int rows = max(0, min(CR, sc.src_h - r0));        // r_end may include virtual rows past the image
                 if (lane == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(bar(SF, slot), (uint32_t)rows * (uint32_t)S.row_bytes + (c == 0 ? rec_bytes : 0u));
@@ -224,7 +225,7 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             const VisSchedSeg G = sc.seg[sg];
             const int sw = S.x1 - S.x0;
             const int n_tiles = (sw + 15) >> 4;
-            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            const int n_chunks = (G.r_end - G.r_first + CR - 1) / CR;
             const uint32_t hrec0 = smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot);
             for (int c = 0; c < n_chunks; ++c, ++k) {
                 const int slot = k & 1, j = k >> 1;
@@ -322,7 +323,7 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             const int sg = r / sc.n_strips, st = r - sg * sc.n_strips;
             const VisSchedStrip S = sc.strip[st];
             const VisSchedSeg G = sc.seg[sg];
-            const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+            const int n_chunks = (G.r_end - G.r_first + CR - 1) / CR;
             const int sw = S.x1 - S.x0, NC = 3 * sw;
             const int n_tiles = (NC + 7) >> 3;
             const int seg_rows = G.y1 - G.y0;
@@ -337,7 +338,7 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                 const uint32_t ring0 = smem_u32(smem + L.off_hring + slot * 3 * L.hplane);
                 const uint32_t* m8 = reinterpret_cast<const uint32_t*>(gm + c * 8);
                 const int n = __popc(m8[0]) + __popc(m8[1]);           // output rows whose window ends in this chunk
-                const int cbw = (G.r_first + c * kChunk - CARRY) >> 2;  // absolute word index of ring byte 0
+                const int cbw = (G.r_first + c * CR - CARRY) >> 2;  // absolute word index of ring byte 0
 #pragma unroll 1
                 for (int mt = 0; 16 * mt < n; ++mt) {
                     const int ihi = min(n, 16 * mt + 16);
@@ -428,8 +429,8 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                     for (int jt = wv; jt < n_tiles; jt += kVWarps) {                     // lane (g, t): words t and t + 4 of column 8 jt + g
                         const int cc = 8 * jt + g;
                         const uint32_t o = (uint32_t)(cc * L.cpitch + 4 * t);
-                        if (cc < NC && t < W - 1) sts32(dst0 + o, lds32(ring0 + o + kChunk));
-                        if (cc < NC && t + 4 < W - 1) sts32(dst0 + o + 16, lds32(ring0 + o + kChunk + 16));
+                        if (cc < NC && t < W - 1) sts32(dst0 + o, lds32(ring0 + o + (uint32_t)CR));
+                        if (cc < NC && t + 4 < W - 1) sts32(dst0 + o + 16, lds32(ring0 + o + (uint32_t)CR + 16));
                     }
                 }
                 __syncwarp();
@@ -552,7 +553,8 @@ int mma_record_stride(int words) { return rec_stride_mma(words); }
 int mma_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_pitch, const int* hrec, const int* vrec,
                const float* lut768, float* pixel_values, cudaStream_t st) {
     const int W = sc.dp_words;
-    if (W < 4 || W > 9 || sc.ring != 16 || sc.per_index != 1 || sc.mma_ks < 1 || sc.mma_ks > 3) {
+    if (W < 4 || W > 9 || sc.ring != 16 || sc.per_index != 1 || sc.mma_ks < 1 || sc.mma_ks > 3 || sc.chunk_rows < 4 ||
+        sc.chunk_rows > kChunk || sc.chunk_rows % 4) {
         vis::set_error("vis_fused_mma: schedule of another kernel class (ring %d, %d words, %d k-steps)", sc.ring, W, sc.mma_ks);
         return VIS_E_INVALID;
     }

@@ -487,9 +487,36 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
         if (dp_words) cls = 4 * dp_words - 3;
     }
     const bool h_pull = !dp_words && cls > 16;
-    // same limb records, both passes on the integer tensor path — where one M-tile of 16 output rows covers what a 32-row
-    // chunk emits (vertical scale >= 2); below that the second M-tile would run nearly empty and IDP.4A is as fast
-    const bool mma = want_mma && dp_words > 0 && (int64_t)src_h >= 2 * (int64_t)dst_h;
+    // same limb records, both passes on the integer tensor path.  Its vertical pass takes ONE M-tile of 16 output rows per
+    // chunk at full efficiency, so a chunk advances by as many input rows (32, 28 or 24: whole 4-row words) as never emit
+    // more than 16; the horizontal pass still computes 32 rows per chunk (the rest is unused), so below 24 rows per chunk
+    // the packed-byte kernel is the better one.
+    bool mma = want_mma && dp_words > 0;
+    int chunk_rows = kChunk;
+    const int prow = (dst_h + 13) / 14;
+    const int n_segs_eff = std::max(1, std::min(std::min(vsplit, prow), (int)VIS_SCHED_MAX_SEGS));
+    auto seg_rows = [&](int g, int* y0, int* y1) {
+        *y0 = (int)((int64_t)prow * g / n_segs_eff) * 14;
+        *y1 = std::min((int)((int64_t)prow * (g + 1) / n_segs_eff) * 14, dst_h);
+    };
+    if (mma) {
+        // window ends inside ANY cr consecutive input rows, wherever the segments put their chunk bases: the choice is a
+        // property of the geometry (the records are cached per geometry, whatever the segment count).  More than 16
+        // (a second, nearly empty M-tile) is allowed for a few windows: the samples Pillow clamps at the far border
+        // crowd into its last rows.
+        auto crowded = [&](int cr) {
+            int over = 0;
+            for (int y = 0, z = 0; y < dst_h; ++y) {
+                while (z < dst_h && vl[z] < vl[y] + cr) ++z;
+                over += z - y > 16;
+            }
+            return over * 20 > dst_h;                      // more than 5 % of the windows
+        };
+        chunk_rows = 0;
+        for (int cr = kChunk; cr >= 24 && !chunk_rows; cr -= 4)
+            if (!crowded(cr)) chunk_rows = cr;
+        if (!chunk_rows) { mma = false; chunk_rows = kChunk; }
+    }
     int mma_ks = 0;
     if (mma) {
         // k-steps of 32 input pixels that the window of a tile of 16 outputs spans, counted from the 4-pixel word of the
@@ -523,7 +550,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     std::memset(&s, 0, sizeof(s));
     s.src_h = src_h; s.src_w = src_w; s.dst_h = dst_h; s.dst_w = dst_w; s.src_pitch = src_pitch; s.kt = cls;
     s.per_index = per_index; s.ring = ring; s.n_subs = n_subs; s.out_mode = out_mode; s.h_pull = h_pull ? 1 : 0;
-    s.n_vwarps = n_vwarps; s.dp_words = dp_words; s.mma_ks = mma_ks;
+    s.n_vwarps = n_vwarps; s.dp_words = dp_words; s.mma_ks = mma_ks; s.chunk_rows = chunk_rows;
     const int stride = dp_words ? visf::dp_record_stride(dp_words) : vis_record_stride(cls);
     auto last = [](const int32_t* b, int i) { return b[2 * i] + b[2 * i + 1] - 1; };
     auto span_of = [&](int x0, int x1, int* px0) {
@@ -588,22 +615,22 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
         }
     }
     // row segments: edges at multiples of 14 output rows (the last one ends at dst_h); chunk bases are multiples of 16
-    const int prow = (dst_h + 13) / 14;
-    if (vsplit > prow) vsplit = prow;
-    if (vsplit > VIS_SCHED_MAX_SEGS) vsplit = VIS_SCHED_MAX_SEGS;
+    vsplit = n_segs_eff;
     s.n_segs = vsplit;
     mask_at = align_up(mask_at, 8);
     for (int g = 0; g < vsplit; ++g) {
         VisSchedSeg& G = s.seg[g];
-        G.y0 = (int)((int64_t)prow * g / vsplit) * 14;
-        G.y1 = std::min((int)((int64_t)prow * (g + 1) / vsplit) * 14, dst_h);
+        seg_rows(g, &G.y0, &G.y1);
         G.r_first = vb[2 * G.y0] & ~15;
         G.r_end = vl[G.y1 - 1] + 1;                                  // may exceed src_h by the virtual rows
-        const int n_chunks = (G.r_end - G.r_first + kChunk - 1) / kChunk;
+        const int n_chunks = (G.r_end - G.r_first + chunk_rows - 1) / chunk_rows;
         const int bytes = 2 * mbytes * n_chunks * (kChunk / step);
         if (!mask_room(bytes)) return unsupported("schedule too large");
         G.mask_off = mask_at;
-        for (int y = G.y0; y < G.y1; ++y) set_bit(mask_at, vl[y] - G.r_first);
+        for (int y = G.y0; y < G.y1; ++y) {                          // chunk = rel / chunk_rows; bit = row inside the chunk
+            const int rel = vl[y] - G.r_first;
+            set_bit(mask_at, rel / chunk_rows * kChunk + rel % chunk_rows);
+        }
         mask_at += bytes;
     }
     return VIS_OK;
