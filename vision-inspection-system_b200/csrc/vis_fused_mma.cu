@@ -113,6 +113,18 @@ __device__ __forceinline__ void imma_su_a(int (&d)[4], const uint32_t (&a)[4], u
                  : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// first k-step of a tile: D = A x B + C with C a loop-invariant register quad (the rounding constant) or zero, so no
+// accumulator is initialised by moves
+#define VIS_IMMA_C(NAME, TA, TB)                                                                                              \
+    __device__ __forceinline__ void NAME(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const int (&c)[4]) {  \
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32." TA "." TB ".s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "          \
+                     "{%10,%11,%12,%13};"                                                                                     \
+                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])                                                         \
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3])); \
+    }
+VIS_IMMA_C(imma_uu_c, "u8", "u8")
+VIS_IMMA_C(imma_su_c, "s8", "u8")
+#undef VIS_IMMA_C
 // (c << 16) | (sat_u8(hi) << 8) | sat_u8(lo)      (I2IP.U8.S32.SAT)
 __device__ __forceinline__ uint32_t pack_sat(int hi, int lo, uint32_t c) {
     uint32_t d;
@@ -145,6 +157,9 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
     const uint32_t bar0 = smem_u32(smem + L.off_bar);
     auto bar = [&](int which, int slot) { return bar0 + (uint32_t)(which + slot) * 8; };
     const int per_frame = sc.n_strips * sc.n_segs;
+    const int kRound[4] = {1 << (VIS_PRECISION_BITS - 1), 1 << (VIS_PRECISION_BITS - 1), 1 << (VIS_PRECISION_BITS - 1),
+                           1 << (VIS_PRECISION_BITS - 1)};
+    const int kZero[4] = {0, 0, 0, 0};
 
     if (!U8)
         for (int i = tid; i < 768; i += (int)blockDim.x) lut[(i % 3) * 256 + i / 3] = __ldg(lut768 + i);
@@ -227,6 +242,13 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             const int n_tiles = (sw + 15) >> 4;
             const int n_chunks = (G.r_end - G.r_first + CR - 1) / CR;
             const uint32_t hrec0 = smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot);
+            const bool one_tile = KS <= 2 && n_tiles <= kHWarps;      // (three k-steps of limbs are too many registers to keep)
+            uint32_t a[KS][3][4];
+            int kw = 0;
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) a[s][l][0] = a[s][l][1] = a[s][l][2] = a[s][l][3] = 0u;
             for (int c = 0; c < n_chunks; ++c, ++k) {
                 const int slot = k & 1, j = k >> 1;
                 mbar_wait(bar(SF, slot), j & 1);
@@ -237,24 +259,26 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
 #pragma unroll 1
                 for (int jt = hw; jt < n_tiles; jt += kHWarps) {
                     // ---- A: coefficient limbs of outputs 16 jt + g and 16 jt + g + 8, 32 input pixels per k-step ----
-                    const int xa = min(16 * jt + g, sw - 1), xb = min(16 * jt + g + 8, sw - 1);
-                    const uint32_t reca = hrec0 + (uint32_t)(xa * STRIDE * 4), recb = hrec0 + (uint32_t)(xb * STRIDE * 4);
-                    const int bwa = (int)lds32(reca + (uint32_t)(3 * W * 4)), bwb = (int)lds32(recb + (uint32_t)(3 * W * 4));
-                    const int kw = __shfl_sync(0xffffffffu, (int)lds32(reca + (uint32_t)((3 * W + 1) * 4)), 0);  // first word of the tile's window
-                    uint32_t a[KS][3][4];
+                    // (they do not depend on the chunk: a warp that owns ONE tile of the strip gathers them once per item)
+                    if (!one_tile || c == 0) {
+                        const int xa = min(16 * jt + g, sw - 1), xb = min(16 * jt + g + 8, sw - 1);
+                        const uint32_t reca = hrec0 + (uint32_t)(xa * STRIDE * 4), recb = hrec0 + (uint32_t)(xb * STRIDE * 4);
+                        const int bwa = (int)lds32(reca + (uint32_t)(3 * W * 4)), bwb = (int)lds32(recb + (uint32_t)(3 * W * 4));
+                        kw = __shfl_sync(0xffffffffu, (int)lds32(reca + (uint32_t)((3 * W + 1) * 4)), 0);     // first word of the tile's window
 #pragma unroll
-                    for (int s = 0; s < KS; ++s)
+                        for (int s = 0; s < KS; ++s)
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int qa = kw + 8 * s + 4 * h + t - bwa, qb = kw + 8 * s + 4 * h + t - bwb;
-                            const bool oka = (unsigned)qa < (unsigned)W, okb = (unsigned)qb < (unsigned)W;
-                            const uint32_t pa = reca + (uint32_t)(12 * qa), pb = recb + (uint32_t)(12 * qb);   // limbs side by side
+                            for (int h = 0; h < 2; ++h) {
+                                const int qa = kw + 8 * s + 4 * h + t - bwa, qb = kw + 8 * s + 4 * h + t - bwb;
+                                const bool oka = (unsigned)qa < (unsigned)W, okb = (unsigned)qb < (unsigned)W;
+                                const uint32_t pa = reca + (uint32_t)(12 * qa), pb = recb + (uint32_t)(12 * qb);   // limbs side by side
 #pragma unroll
-                            for (int l = 0; l < 3; ++l) {
-                                a[s][l][2 * h] = oka ? lds32(pa + 4 * l) : 0u;
-                                a[s][l][2 * h + 1] = okb ? lds32(pb + 4 * l) : 0u;
+                                for (int l = 0; l < 3; ++l) {
+                                    a[s][l][2 * h] = oka ? lds32(pa + 4 * l) : 0u;
+                                    a[s][l][2 * h + 1] = okb ? lds32(pb + 4 * l) : 0u;
+                                }
                             }
-                        }
+                    }
                     // pixel group (kw + t) of a stage row: 12 bytes = 4 RGB pixels
                     const uint32_t g_off = (uint32_t)(12 * (kw + t - (S.px0 >> 2)));
                     uint32_t P[3][4];                                   // per channel and N-tile: the four samples of D, saturated
@@ -275,10 +299,11 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
                             int acc[3][4];
+                            imma_uu_c(acc[0], a[0][0], b[ch][0][0], b[ch][0][1], kRound);
+                            imma_uu_c(acc[1], a[0][1], b[ch][0][0], b[ch][0][1], kZero);
+                            imma_su_c(acc[2], a[0][2], b[ch][0][0], b[ch][0][1], kZero);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) { acc[0][e] = 1 << (VIS_PRECISION_BITS - 1); acc[1][e] = 0; acc[2][e] = 0; }
-#pragma unroll
-                            for (int s = 0; s < KS; ++s) {
+                            for (int s = 1; s < KS; ++s) {
                                 imma_uu_a(acc[0], a[s][0], b[ch][s][0], b[ch][s][1]);
                                 imma_uu_a(acc[1], a[s][1], b[ch][s][0], b[ch][s][1]);
                                 imma_su_a(acc[2], a[s][2], b[ch][s][0], b[ch][s][1]);
@@ -390,14 +415,12 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                             for (int u = 0; u < kVUnroll; ++u) {
                                 const uint32_t bu = ba + (uint32_t)(u * 8 * kVWarps * L.cpitch);
                                 bq[u][0] = lds32(bu); bq[u][1] = lds32(bu + 16); bq[u][2] = lds32(bu + 32); bq[u][3] = lds32(bu + 48);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) { acc[u][0][e] = 1 << (VIS_PRECISION_BITS - 1); acc[u][1][e] = 0; acc[u][2][e] = 0; }
                             }
 #pragma unroll
                             for (int u = 0; u < kVUnroll; ++u) {
-                                imma_uu_a(acc[u][0], a[0][0], bq[u][0], bq[u][1]);
-                                imma_uu_a(acc[u][1], a[0][1], bq[u][0], bq[u][1]);
-                                imma_su_a(acc[u][2], a[0][2], bq[u][0], bq[u][1]);
+                                imma_uu_c(acc[u][0], a[0][0], bq[u][0], bq[u][1], kRound);
+                                imma_uu_c(acc[u][1], a[0][1], bq[u][0], bq[u][1], kZero);
+                                imma_su_c(acc[u][2], a[0][2], bq[u][0], bq[u][1], kZero);
                             }
 #pragma unroll
                             for (int u = 0; u < kVUnroll; ++u) {
@@ -545,7 +568,8 @@ int launch_mma(const VisSched& sc, const void* frames, int n_frames, const Layou
 
 namespace visf {
 
-int mma_max_strip_w() { return 256; }
+// up to two k-steps: one tile of 16 columns per horizontal-pass warp, whose coefficient fragments then stay in registers
+int mma_max_strip_w(int ksteps) { return ksteps <= 2 ? 16 * kHWarps : 256; }
 int mma_max_ksteps() { return 3; }
 int mma_layout_bytes(int stage_pitch, int strip_w, int words) { return make_layout_m(stage_pitch, strip_w, words).total; }
 int mma_record_stride(int words) { return rec_stride_mma(words); }

@@ -45,7 +45,7 @@ int dp_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst_
 }
 
 namespace visf {   // integer tensor-path (IMMA) kernel, vis_fused_mma.cu
-int mma_max_strip_w();
+int mma_max_strip_w(int ksteps);
 int mma_max_ksteps();
 int mma_layout_bytes(int stage_pitch, int strip_w, int words);
 int mma_record_stride(int words);
@@ -534,7 +534,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
     // 16-slot kernels: fewer vertical-pass warps the stronger the vertical downscale (the V role gets lighter)
     const double vscale = (double)src_h / dst_h;
     const int n_vwarps = ring == 8 ? 0 : dp_words ? (vscale >= VIS_DP_NV_SPLIT ? 4 : 6) : cls > 16 ? (vscale >= 3.4 ? 3 : 4) : (vscale >= 2.4 ? 4 : 6);
-    const int max_w = ring == 8 ? kMaxStripW : mma ? visf::mma_max_strip_w() : dp_words ? visf::dp_max_strip_w(n_vwarps) : visf::sched16_max_strip_w(n_vwarps);
+    const int max_w = ring == 8 ? kMaxStripW : mma ? visf::mma_max_strip_w(mma_ks) : dp_words ? visf::dp_max_strip_w(n_vwarps) : visf::sched16_max_strip_w(n_vwarps);
     int per_index = 1;
     // an exact class (13, 14) may be too tight for the virtual ends of the far-border samples: widen it
     while ((cls == 13 || cls == 14) && (!schedule_ends(hb, dst_w, cls, 1, hl) || !schedule_ends(vb, dst_h, cls, 1, vl)))
