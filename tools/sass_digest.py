@@ -6,8 +6,9 @@
 For every kernel in the cubin: registers, shared memory, instruction count, and the counts of the mnemonics that matter
 for this path — UBLKCP (cp.async.bulk: the 1-D bulk-copy engine that stages row segments), SYNCS (mbarrier), STG.E.128 /
 LDG.E.128 (128-bit global accesses), IMAD / IDP (the integer MACs), PRMT (byte unpack), LDS / STS, NANOSLEEP (mbarrier
-poll back-off) — and, as negative evidence, tensor-core / tensor-map mnemonics (HMMA, IMMA, UTC*MMA, UTMALDG): this path
-is integer resampling and rasterisation, not a contraction, so none may appear.
+poll back-off), IMMA / I2IP (the integer tensor path and the saturating pack of the 9..33-tap kernel k_fused_mma: the ONLY
+kernel that may hold IMMA — its passes are banded u8 x byte-limb products) — and, as negative evidence,
+the other tensor-core / tensor-map mnemonics (HMMA, UTC*MMA, UTMALDG): nothing else on this path is a contraction.
 """
 import collections
 import re
@@ -17,8 +18,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 WANT = ["UBLKCP", "SYNCS", "STG.E.128", "LDG.E.128", "STG", "LDG", "IMAD", "IDP", "PRMT", "LDS", "STS", "NANOSLEEP", "BAR",
-        "SHFL", "VIMNMX", "ATOM", "RED"]
-FORBIDDEN = ["HMMA", "IMMA", "DMMA", "UTCHMMA", "UTCIMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "HGMMA", "LDTM", "STTM"]
+        "SHFL", "VIMNMX", "ATOM", "RED", "IMMA", "I2IP"]
+FORBIDDEN = ["HMMA", "DMMA", "UTCHMMA", "UTCIMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "HGMMA", "LDTM", "STTM"]
 
 
 def demangle(names):
@@ -77,11 +78,13 @@ def main():
         for f in FORBIDDEN:
             if c[f]:
                 bad_total[f] += c[f]
+        if c["IMMA"] and "k_fused_mma" not in short:
+            bad_total["IMMA outside k_fused_mma"] += c["IMMA"]
     tot = collections.Counter()
     for c in kernels.values():
         tot.update(c)
     print("# library totals: " + ", ".join(f"{w} {tot[w]}" for w in WANT))
-    print("# tensor-core / tensor-map mnemonics (must be absent on this path): " +
+    print("# floating-point tensor-core / tensor-map mnemonics, and IMMA outside k_fused_mma (must be absent): " +
           (", ".join(f"{k} {v}" for k, v in bad_total.items()) if bad_total else "none"))
 
 
