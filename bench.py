@@ -436,7 +436,11 @@ def main():
         if macs_per_call:
             mhz = (ck or {}).get("sm_mhz") or 1965.0
             rec["int_macs"] = int(macs_per_call)
+            # Pillow taps per second against ONE tap per CUDA-core integer-MAC lane and clock: the yardstick of the IMAD /
+            # IDP.4A kernels.  Since the 9+ tap geometries run on the integer tensor path (k_fused_mma, IMMA.16832:
+            # 2037 byte MACs / clk / SM measured, three limb MACs per tap) it is a comparison figure, not a utilisation.
             rec["int_mac_issue_frac"] = macs_per_call / (per * 1e-3) / (sm_count * INT_MAC_LANES_PER_CLK_PER_SM * mhz * 1e6)
+            rec["int_mac_yardstick"] = "taps/s per CUDA-core integer-MAC lane (62 / clk / SM); 9+ tap legs use IMMA"
         if note:
             rec["note"] = note
         return rec
