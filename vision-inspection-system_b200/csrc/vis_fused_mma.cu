@@ -30,19 +30,29 @@ using namespace visf;
 
 namespace {
 
+// Warp split of the roles, per k-step class.  Up to 24 warps keep 80 registers per thread, up to 20 keep 96: the two
+// k-step kernels (12-13 taps at 4K, the 2048 / 1024 thumbnails of 16:9 frames) run 12 H + 9 V + 2 store + loader; the three
+// k-step kernels hold 36 registers of coefficient fragments and are faster unspilled with 9 + 8 + 2 + 1
+// (profiles/r02_mma_ab_log.txt, steps 11-13).
 #ifndef VIS_MMA_HWARPS
 #define VIS_MMA_HWARPS 12
 #endif
 #ifndef VIS_MMA_VWARPS
 #define VIS_MMA_VWARPS 9
 #endif
+#ifndef VIS_MMA_HWARPS3
+#define VIS_MMA_HWARPS3 9
+#endif
+#ifndef VIS_MMA_VWARPS3
+#define VIS_MMA_VWARPS3 8
+#endif
 #ifndef VIS_MMA_SWARPS
 #define VIS_MMA_SWARPS 2
 #endif
-constexpr int kHWarps = VIS_MMA_HWARPS, kVWarps = VIS_MMA_VWARPS, kSWarps = VIS_MMA_SWARPS;
-// warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
-constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kSBase + kSWarps;
-constexpr int kThreads = (kHWarps + kVWarps + kSWarps + 1) * 32;
+constexpr int kSWarps = VIS_MMA_SWARPS;
+__host__ __device__ constexpr int h_warps(int ks) { return ks <= 2 ? VIS_MMA_HWARPS : VIS_MMA_HWARPS3; }
+__host__ __device__ constexpr int v_warps(int ks) { return ks <= 2 ? VIS_MMA_VWARPS : VIS_MMA_VWARPS3; }
+__host__ __device__ constexpr int n_threads(int ks) { return (h_warps(ks) + v_warps(ks) + kSWarps + 1) * 32; }
 #ifndef VIS_MMA_VUNROLL
 #define VIS_MMA_VUNROLL 1
 #endif
@@ -141,11 +151,14 @@ __device__ __forceinline__ void sts16_if(bool p, uint32_t addr, uint32_t v) {   
 struct FramePtrs { const unsigned char* src; long long second; };      // VisFrameRef / VisResizeRef: same layout
 
 template <int KS, bool U8>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(n_threads(KS), 1)
 k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ frames, int n_items,
             const __grid_constant__ LayoutM L, long long dst_pitch, const int* __restrict__ hrec_g,
             const int* __restrict__ vrec_g, const float* __restrict__ lut768, float* __restrict__ pixel_values) {
     extern __shared__ __align__(128) unsigned char smem[];
+    // warp ranges in priority order (the scheduler prefers the highest ready warp id): H < loader < S < V
+    constexpr int kHWarps = h_warps(KS), kVWarps = v_warps(KS);
+    constexpr int kHBase = 0, kLBase = kHWarps, kSBase = kHWarps + 1, kVBase = kSBase + kSWarps;
     const int W = sc.dp_words;
     const int STRIDE = rec_stride_mma(W);
     const int CARRY = 4 * (W - 1);                     // rows of the previous chunk a window may reach back to
@@ -404,16 +417,19 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                         }
                         // ring column 8 jt + g: linear in the tile index (columns past the strip read slack, results unused)
                         uint32_t ba = ring0 + (uint32_t)((8 * wv + g) * L.cpitch + 4 * t);
-                        uint32_t oa = otile0 + (uint32_t)(8 * wv);
+                        uint32_t oa0 = otile0 + (uint32_t)(8 * wv) + off_r[0], oa1 = otile0 + (uint32_t)(8 * wv) + off_r[1];
+                        const uint32_t ba_step = (uint32_t)(8 * kVWarps * L.cpitch);
+                        const int lim = (NC - 2 * t + 7) >> 3;                            // tiles whose columns 2t, 2t+1 lie inside the strip
+                        const int lim0 = ok_r[0] ? lim : 0, lim1 = ok_r[1] ? lim : 0;
 #pragma unroll 1
-                        for (int jt = wv; jt < n_tiles; jt += kVUnroll * kVWarps, ba += (uint32_t)(kVUnroll * 8 * kVWarps * L.cpitch),
-                                 oa += kVUnroll * 8 * kVWarps) {
+                        for (int jt = wv; jt < n_tiles; jt += kVUnroll * kVWarps, ba += kVUnroll * ba_step,
+                                 oa0 += kVUnroll * 8 * kVWarps, oa1 += kVUnroll * 8 * kVWarps) {
                             // kVUnroll independent tiles in flight (tiles past the strip read slack and store nothing)
                             uint32_t bq[kVUnroll][4];
                             int acc[kVUnroll][3][4];
 #pragma unroll
                             for (int u = 0; u < kVUnroll; ++u) {
-                                const uint32_t bu = ba + (uint32_t)(u * 8 * kVWarps * L.cpitch);
+                                const uint32_t bu = ba + u * ba_step;
                                 bq[u][0] = lds32(bu); bq[u][1] = lds32(bu + 16); bq[u][2] = lds32(bu + 32); bq[u][3] = lds32(bu + 48);
                             }
 #pragma unroll
@@ -431,13 +447,14 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                             // D: e = 0/1 -> (row g, columns 2t / 2t+1), e = 2/3 -> (row g+8, columns 2t / 2t+1)
 #pragma unroll
                             for (int u = 0; u < kVUnroll; ++u) {
-                                const bool in = 8 * (jt + u * kVWarps) + 2 * t < NC;
                                 const uint32_t p0 = pack_sat(recombine(acc[u][0][1], acc[u][1][1], acc[u][2][1]),
                                                              recombine(acc[u][0][0], acc[u][1][0], acc[u][2][0]), 0u);
                                 const uint32_t p1 = pack_sat(recombine(acc[u][0][3], acc[u][1][3], acc[u][2][3]),
                                                              recombine(acc[u][0][2], acc[u][1][2], acc[u][2][2]), 0u);
-                                sts16_if(in && ok_r[0], oa + (uint32_t)(u * 8 * kVWarps) + off_r[0], p0);
-                                sts16_if(in && ok_r[1], oa + (uint32_t)(u * 8 * kVWarps) + off_r[1], p1);
+                                if (jt + u * kVWarps < lim0)
+                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa0 + (uint32_t)(u * 8 * kVWarps)), "h"((unsigned short)p0) : "memory");
+                                if (jt + u * kVWarps < lim1)
+                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa1 + (uint32_t)(u * 8 * kVWarps)), "h"((unsigned short)p1) : "memory");
                             }
                         }
                         __syncwarp();
@@ -559,7 +576,7 @@ int launch_mma(const VisSched& sc, const void* frames, int n_frames, const Layou
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_items = n_frames * sc.n_strips * sc.n_segs;
     const int grid = n_items < sms ? n_items : sms;
-    kern<<<grid, kThreads, L.total, st>>>(sc, reinterpret_cast<const FramePtrs*>(frames), n_items, L, (long long)dst_pitch,
+    kern<<<grid, n_threads(KS), L.total, st>>>(sc, reinterpret_cast<const FramePtrs*>(frames), n_items, L, (long long)dst_pitch,
                                           hrec, vrec, lut768, pixel_values);
     return vis::check_launch("vis_fused_mma");
 }
@@ -569,7 +586,7 @@ int launch_mma(const VisSched& sc, const void* frames, int n_frames, const Layou
 namespace visf {
 
 // up to two k-steps: one tile of 16 columns per horizontal-pass warp, whose coefficient fragments then stay in registers
-int mma_max_strip_w(int ksteps) { return ksteps <= 2 ? 16 * kHWarps : 256; }
+int mma_max_strip_w(int ksteps) { return ksteps <= 2 ? 16 * h_warps(2) : 256; }
 int mma_max_ksteps() { return 3; }
 int mma_layout_bytes(int stage_pitch, int strip_w, int words) { return make_layout_m(stage_pitch, strip_w, words).total; }
 int mma_record_stride(int words) { return rec_stride_mma(words); }
