@@ -53,6 +53,10 @@ constexpr int kSWarps = VIS_MMA_SWARPS;
 __host__ __device__ constexpr int h_warps(int ks) { return ks <= 2 ? VIS_MMA_HWARPS : VIS_MMA_HWARPS3; }
 __host__ __device__ constexpr int v_warps(int ks) { return ks <= 2 ? VIS_MMA_VWARPS : VIS_MMA_VWARPS3; }
 __host__ __device__ constexpr int n_threads(int ks) { return (h_warps(ks) + v_warps(ks) + kSWarps + 1) * 32; }
+#ifndef VIS_MMA_VPIPE
+#define VIS_MMA_VPIPE 0            // A/B: 1 = software-pipelined vertical tile loop (tile i's IMMA between the pieces of tile
+                                   // i-1's epilogue): 85.8 k -> 77.1 k images/s on 4K, rejected (profiles/r02_mma_ab_log.txt, step 15)
+#endif
 #ifndef VIS_MMA_VUNROLL
 #define VIS_MMA_VUNROLL 1
 #endif
@@ -421,6 +425,46 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                         const uint32_t ba_step = (uint32_t)(8 * kVWarps * L.cpitch);
                         const int lim = (NC - 2 * t + 7) >> 3;                            // tiles whose columns 2t, 2t+1 lie inside the strip
                         const int lim0 = ok_r[0] ? lim : 0, lim1 = ok_r[1] ? lim : 0;
+#if VIS_MMA_VPIPE
+                        // software pipeline: the six IMMA of tile i (one per 8 clocks and sub-core at best) are issued
+                        // between the pieces of tile i-1's epilogue, and tile i+1's ring words are requested behind them
+                        {
+                            int accp[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+                            int jtp = 0x40000000;                                         // "no previous tile": stores nothing
+                            uint32_t b0 = lds32(ba), b1 = lds32(ba + 16), b2 = lds32(ba + 32), b3 = lds32(ba + 48);
+#pragma unroll 1
+                            for (int jt = wv; jt < n_tiles; jt += kVWarps) {
+                                int acc[3][4];
+                                imma_uu_c(acc[0], a[0][0], b0, b1, kRound);
+                                const int v0 = recombine(accp[0][0], accp[1][0], accp[2][0]);
+                                const int v1 = recombine(accp[0][1], accp[1][1], accp[2][1]);
+                                imma_uu_c(acc[1], a[0][1], b0, b1, kZero);
+                                const uint32_t p0 = pack_sat(v1, v0, 0u);
+                                imma_su_c(acc[2], a[0][2], b0, b1, kZero);
+                                const int v2 = recombine(accp[0][2], accp[1][2], accp[2][2]);
+                                const int v3 = recombine(accp[0][3], accp[1][3], accp[2][3]);
+                                imma_uu_a(acc[0], a[1][0], b2, b3);
+                                const uint32_t p1 = pack_sat(v3, v2, 0u);
+                                imma_uu_a(acc[1], a[1][1], b2, b3);
+                                if (jtp < lim0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa0 - 8 * kVWarps), "h"((unsigned short)p0) : "memory");
+                                if (jtp < lim1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa1 - 8 * kVWarps), "h"((unsigned short)p1) : "memory");
+                                imma_su_a(acc[2], a[1][2], b2, b3);
+                                ba += ba_step;
+                                b0 = lds32(ba); b1 = lds32(ba + 16); b2 = lds32(ba + 32); b3 = lds32(ba + 48);   // next tile (or slack)
+                                oa0 += 8 * kVWarps; oa1 += 8 * kVWarps;
+                                jtp = jt;
+#pragma unroll
+                                for (int l = 0; l < 3; ++l)
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) accp[l][e] = acc[l][e];
+                            }
+                            // epilogue of the last tile
+                            const uint32_t p0 = pack_sat(recombine(accp[0][1], accp[1][1], accp[2][1]), recombine(accp[0][0], accp[1][0], accp[2][0]), 0u);
+                            const uint32_t p1 = pack_sat(recombine(accp[0][3], accp[1][3], accp[2][3]), recombine(accp[0][2], accp[1][2], accp[2][2]), 0u);
+                            if (jtp < lim0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa0 - 8 * kVWarps), "h"((unsigned short)p0) : "memory");
+                            if (jtp < lim1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa1 - 8 * kVWarps), "h"((unsigned short)p1) : "memory");
+                        }
+#else
 #pragma unroll 1
                         for (int jt = wv; jt < n_tiles; jt += kVUnroll * kVWarps, ba += kVUnroll * ba_step,
                                  oa0 += kVUnroll * 8 * kVWarps, oa1 += kVUnroll * 8 * kVWarps) {
@@ -457,6 +501,7 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
                                     asm volatile("st.shared.u16 [%0], %1;" ::"r"(oa1 + (uint32_t)(u * 8 * kVWarps)), "h"((unsigned short)p1) : "memory");
                             }
                         }
+#endif
                         __syncwarp();
                         for (int bb = bs; bb <= be; ++bb)                                // bands completed by the rows stored so far
                             if (min(VIS_PATCH * (bb + 1), seg_rows) <= ycount + ihi && lane == 0)
