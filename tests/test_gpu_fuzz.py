@@ -116,3 +116,34 @@ def test_all_kernel_families_for_long_windows(engine):
                 assert np.array_equal(got.cpu().numpy(), Q.agent_thumbnail(f, limit)), (h, w, limit, dp)
     finally:
         engine.use_dp4a(True, True)
+
+
+def test_tensor_path_kernel_random_scales(engine):
+    """The integer tensor-path kernel (k_fused_mma) over its whole envelope: vertical scales 1.5 .. 5.5 (chunk advance 24 /
+    28 / 32 rows), 9 .. 33 taps (4 .. 9 window words, 1 .. 3 k-steps), strip widths that are no multiple of 16, batches that
+    take several row segments — LANCZOS and BICUBIC uint8 resizes against the oracle (the pixel_values form of such
+    geometries is in test_preprocess_random_geometries and tests/test_gpu_preprocess.py)."""
+    from vision_inspection_system_b200 import _native as N
+    rng = np.random.default_rng(777)
+    taken = 0
+    for k in range(64):
+        filt = Q.LANCZOS if k % 2 else Q.BICUBIC
+        sx = float(rng.uniform(1.5, 5.4 if filt == Q.LANCZOS else 7.5))
+        sy = float(rng.uniform(1.5, 5.4 if filt == Q.LANCZOS else 7.5))
+        out_w = int(rng.integers(16, 160)) * 4
+        out_h = int(rng.integers(30, 400))
+        w = (int(out_w * sx) + 15) // 16 * 16
+        h = int(out_h * sy)
+        if h * w > 3000 * 6000:
+            continue
+        n = int(rng.integers(1, 4))
+        frames = [synth.noise_frame(8000 + 10 * k + i, h, w) for i in range(n)]
+        dev = [torch.from_numpy(f).cuda() for f in frames]
+        outs = engine.resize_batch_u8(dev, out_h, out_w, filt)
+        hit = engine._resize_sched(h, w, out_h, out_w, filt, w * 3, 1)
+        if hit is not None:
+            head = np.frombuffer(hit[0][:N.SCHED_HEAD_DTYPE.itemsize], N.SCHED_HEAD_DTYPE)[0]
+            taken += int(head["mma_ks"]) > 0
+        for f, o in zip(frames, outs):
+            assert np.array_equal(o.cpu().numpy(), Q.resize(f, out_h, out_w, filt)), (h, w, out_h, out_w, filt)
+    assert taken >= 36, taken        # most of these geometries are the tensor-path kernel's
