@@ -244,6 +244,20 @@ def test_preprocess_dual_equals_two_role_passes(engine):
     assert launches <= 14, launches
     again = engine.preprocess_dual(dev, out=torch.empty_like(torch.cat([res["inspector"][0], res["auditor"][0]])))
     assert torch.equal(again["auditor"][0], res["auditor"][0]) and torch.equal(again["inspector"][0], res["inspector"][0])
+    # the cached pass spreads its independent launches over several CUDA streams (event dependencies between a thumbnail
+    # and the processor launch that reads it): one stream after the other and any stream count give the same tensors,
+    # also when the result buffer was just overwritten on the caller's stream
+    assert engine.dual_streams > 1
+    keep = engine.dual_streams
+    try:
+        for n_streams in (1, 2, 5):
+            engine.dual_streams = n_streams
+            scratch = torch.full_like(torch.cat([res["inspector"][0], res["auditor"][0]]), float("nan"))
+            got = engine.preprocess_dual(dev, out=scratch)
+            torch.cuda.synchronize()
+            assert torch.equal(got["auditor"][0], res["auditor"][0]) and torch.equal(got["inspector"][0], res["inspector"][0]), n_streams
+    finally:
+        engine.dual_streams = keep
     # a frame >= 4x the Auditor's limit takes Pillow's reduce pre-pass (not cacheable as one fused launch): still exact,
     # next to an unaligned 502-pixel frame in the same call; twice, because the second call reuses the cached plan
     big = [synth.noise_frame(9200, 2200, 4400), synth.noise_frame(9201, 100, 502), synth.noise_frame(9202, 1080, 1920)]

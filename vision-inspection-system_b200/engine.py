@@ -92,6 +92,8 @@ class Engine:
         # ... and, on top of it, both passes as banded u8 x limb matrix products on the integer tensor path (IMMA.16832,
         # vis_fused_mma.cu) unless VIS_B200_MMA=0 keeps the IDP.4A kernel; the three families are bit-exact
         self.mma = os.environ.get("VIS_B200_MMA", "1") != "0"
+        # preprocess_dual: CUDA streams its independent launches are spread over (1 = one after the other on the caller's)
+        self.dual_streams = max(1, int(os.environ.get("VIS_B200_DUAL_STREAMS", "4")))
         self._lock = threading.RLock()   # public entry points are serialised: caches and staging buffers are shared
         self._tls = threading.local()    # per-thread state (nvJPEG handles are not thread-safe)
 
@@ -726,15 +728,80 @@ class Engine:
             plan = self.plan_batch(work, min_pixels, max_pixels, rows=dp["rows"], dup_rows=dp["dup"], total_rows=dp["total"])
         else:
             plan = dp["plan"]
-        for rp in dp["thumbs"]:
-            self._run_resize(rp)
-            launches += 1
-        if dp["align"] is not None:
-            self._run_align(dp["align"])
-            launches += 1
-        pv = self._run_plan(plan, work, out, launches)
+        if self.dual_streams > 1 and not dp["slow"] and dp.get("early") is not None:
+            pv = self._run_dual_streams(dp, plan, out)
+        else:
+            for rp in dp["thumbs"]:
+                self._run_resize(rp)
+                launches += 1
+            if dp["align"] is not None:
+                self._run_align(dp["align"])
+                launches += 1
+            pv = self._run_plan(plan, work, out, launches)
         ti = dp["total_i"]
         return {"inspector": (pv[:ti], dp["grid_i"]), "auditor": (pv[ti:], dp["grid_a"])}
+
+    def _run_dual_streams(self, dp: dict, plan: "BatchPlan", out):
+        """The launches of a cached dual pass on ``dual_streams`` CUDA streams.  They are persistent grids of at most one
+        CTA per SM whose last round leaves SMs idle (4.2 rounds = 84 % of the machine for 624 items) and several cover
+        fewer items than there are SMs; launches that do not depend on each other fill those gaps when they sit on
+        different streams (tools/dual_breakdown.py: 3.25 -> 3.00 ms for the 192-frame slice of bench.py).  The thumbnails, the
+        re-pitch launch and the processor launches that read caller frames only go first; a processor launch that reads
+        thumbnails (or re-pitched frames) waits for the events of exactly those launches.  Forked from and joined back into
+        the caller's stream."""
+        if out is None:
+            out = torch.empty((plan.total_rows, G.ROW_FLOATS), dtype=torch.float32, device=self.device)
+        elif (tuple(out.shape) != (plan.total_rows, G.ROW_FLOATS) or out.dtype != torch.float32
+              or not out.is_contiguous() or out.device != self.device):
+            raise ValueError(f"out must be a contiguous float32 [{plan.total_rows}, {G.ROW_FLOATS}] tensor on {self.device}")
+        cur = torch.cuda.current_stream()
+        side = self.__dict__.get("_side_streams")
+        if side is None or len(side) != self.dual_streams - 1:
+            side = self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.dual_streams - 1)]
+        streams = [cur] + side
+        fork = cur.record_event()
+        for st in side:
+            st.wait_event(fork)
+        turn = [0]
+
+        def on_next(fn):
+            st = streams[turn[0] % len(streams)]
+            turn[0] += 1
+            with torch.cuda.stream(st):
+                fn()
+            return st
+
+        def launch(fl):
+            N.check(self.L.vis_preprocess_fused_sched_dup(fl.sched.ctypes.data_as(C.c_void_p), fl.frames.data_ptr(), fl.n_frames,
+                                                          fl.hrec.data_ptr(), fl.vrec.data_ptr(), self.lut.data_ptr(),
+                                                          out.data_ptr(), fl.dup.data_ptr() if fl.dup is not None else None,
+                                                          _stream_ptr()), "vis_preprocess_fused_sched")
+        n = 0
+        t_ev = []                                        # (stream, event) per thumbnail launch
+        for rp in dp["thumbs"]:
+            st = on_next(lambda rp=rp: self._run_resize(rp))
+            t_ev.append((st, st.record_event()))
+            n += 1
+        a_ev = None
+        if dp["align"] is not None:
+            st = on_next(lambda: self._run_align(dp["align"]))
+            a_ev = (st, st.record_event())
+            n += 1
+        order = sorted(range(len(plan.fused)), key=lambda j: (len(dp["deps"][j][0]) > 0 or dp["deps"][j][1], j))
+        for j in order:                                  # launches that read caller frames only go first
+            thumbs_read, repitched = dp["deps"][j]
+            st = streams[turn[0] % len(streams)]
+            for k in thumbs_read:
+                if t_ev[k][0] is not st:
+                    st.wait_event(t_ev[k][1])
+            if repitched and a_ev is not None and a_ev[0] is not st:
+                st.wait_event(a_ev[1])
+            on_next(lambda fl=plan.fused[j]: launch(fl))
+            n += 1
+        for st in side:
+            cur.wait_event(st.record_event())
+        self.last_launches = n
+        return out
 
     def _plan_dual(self, batch: list, min_pixels: int, max_pixels: int) -> dict:
         n = len(batch)
@@ -795,6 +862,20 @@ class Engine:
             work, dp["align"] = self._align_frames(work, plan_only=True)
             dp["plan"] = self.plan_batch(work, min_pixels, max_pixels, rows=rows, dup_rows=dup, total_rows=dp["total"])
         dp["work"] = work
+        dp["early"] = None
+        plan = dp["plan"]
+        if plan is not None and not plan.generic and all(isinstance(fl, _SchedLaunch) for fl in plan.fused):
+            # what each processor launch reads besides caller frames: which thumbnail launches, and re-pitched frames
+            base = {int(f.data_ptr()) for f in batch}
+            spans = [(int(rp[6].data_ptr()), int(rp[6].data_ptr()) + rp[6].numel()) for rp in thumbs]
+            deps = []
+            for fl in plan.fused:
+                srcs = [int(p) for p in np.frombuffer(fl.frames.cpu().numpy().tobytes(), N.FRAME_REF_DTYPE)["src"]]
+                reads = sorted({k for p in srcs for k, (lo, hi) in enumerate(spans) if lo <= p < hi})
+                other = any(p not in base and not any(lo <= p < hi for lo, hi in spans) for p in srcs)
+                deps.append((reads, other))
+            dp["deps"] = deps
+            dp["early"] = [not r and not o for r, o in deps]
         return dp
 
     def _align_frames(self, frames: list, plan_only: bool = False):
