@@ -8,19 +8,26 @@
 // Why it exists (tools/ubench_imma.cu -> profiles/r02_ubench_imma.jsonl): strong downscales are not HBM bound on CUDA
 // cores — IDP.4A issues at 62 lanes / clk / SM = 248 byte MACs, the packed-byte kernel sits at 0.52 of that and at 0.2-0.5
 // of the HBM roofline — while IMMA.16832 issues every 2 clocks per SM = 2037 byte MACs / clk / SM, 8.2x, with LDS free next
-// to it.  A resampling pass IS a (banded) matrix product, out = C x in; per 8 outputs the band is 2-3 k-steps of 32 wide.
-//   H  (8 warps)  warp = every 8th tile of 8 output pixels, all 32 rows of the chunk (two M-tiles of 16 rows).
-//                 A = staged pixels [row][32 input pixels of one channel]: 3 x LDS.32 + 6 PRMT de-interleave 4 pixels of the
-//                 three channels; the stage rows are skewed by 16 bytes per 4 rows so that lanes (row 4g+j, word 3t+w) never
-//                 share a bank.  B = coefficient limbs [32 input pixels][8 outputs], gathered by predicated LDS.32 from
-//                 the same compact per-output records the packed-byte kernel uses (W words per limb + the window's first
-//                 word index), shared by both M-tiles and the three channels.  M index m <-> chunk row 4g + {0,1} (tile 0)
-//                 / 4g + {2,3} (tile 1): a thread ends up with rows 4g..4g+3 of two output columns per channel = one
-//                 STS.32 each into the TRANSPOSED H ring [channel][column][row].
-//   V  (4 warps)  warp = every 4th tile of 8 ring columns.  A = coefficient limbs [16 output rows][64 ring rows] from the
-//                 chunk's vertical records (once per chunk and M-tile), B = ring words (4 consecutive rows of a column:
-//                 exactly the fragment layout, LDS.32, column pitch = 4 mod 8 words: conflict free), 6 IMMA per tile.
-//   epilogue      acc0 (preloaded with 2^21) + (acc1 << 8) + (acc2 << 16), >> 22, I2IP.U8.S32.SAT packs two samples.
+// to it.  A resampling pass IS a (banded) matrix product, out = C x in; per 16 outputs the band is 2-3 k-steps of 32 wide.
+//   H  (12 / 9 warps)  warp = a tile of 16 output columns x the 32 rows of the chunk, per channel
+//                 D[16 outputs][8 rows] = A[16 outputs][32 k] x B[32 k][8 rows].  A = coefficient limbs, gathered by predicated
+//                 LDS.32 from compact per-output records (W words x 3 limbs, limb-minor, + the word index of the record and
+//                 of its first tap; record stride = 4 mod 8 words: the eight records of a gather start in eight bank groups),
+//                 once per item when the warp owns one tile of the strip.  B = pixels: 3 x LDS.32 + 6 PRMT give the words of
+//                 all three channels (de-interleave in registers); N-tile c holds chunk rows 4g + c, and the stage rows are
+//                 skewed by 16 bytes per 4 rows so that the eight rows of a fragment load never share a bank.  A 16-output
+//                 window is hardly wider than an 8-output one, so with the outputs on the M side the pixels are fetched half
+//                 as often as with the rows there.  The four N-tiles leave a thread with rows 8t..8t+3 / 8t+4..8t+7 of columns
+//                 g and g+8: a 4x4 byte transpose and four STS.32 per channel into the TRANSPOSED H ring
+//                 [channel * sw + column][row].
+//   V  (9 / 8 warps)  warp = every n-th tile of 8 ring columns, D[16 output rows][8 columns].  A = coefficient limbs of the
+//                 rows the chunk emits (gathered per chunk from the vertical records relative to ring byte 0), B = ring
+//                 words (4 consecutive rows of a column: exactly the fragment layout, LDS.32, column pitch = 4 mod 8 words:
+//                 conflict free), 6 IMMA per tile, STS.U16 into a three-slot band tile [row][channel * sw + x].  One M-tile
+//                 per chunk is the efficient case: a chunk advances by 32, 28 or 24 input rows (VisSched.chunk_rows).
+//   epilogue      acc0 (2^21 as the C operand of its first IMMA) + (acc1 << 8) + (acc2 << 16), >> 22, I2IP.U8.S32.SAT packs
+//                 and clips two samples per instruction.
+// DESIGN.md 4.1d has the measurements, the build history and what bounds the kernel now.
 #include "vis_fused_common.cuh"
 
 #include <cstring>
