@@ -53,6 +53,9 @@ int mma_launch(const VisSched& sc, const void* frames, int n_frames, int64_t dst
                const float* lut768, float* pixel_values, cudaStream_t st);
 }
 
+#ifndef VIS_MMA_MIN_CHUNK_ROWS
+#define VIS_MMA_MIN_CHUNK_ROWS 24     // tensor-path kernel: smallest chunk advance (the horizontal pass computes 32 rows per chunk anyway)
+#endif
 #ifndef VIS_DP_NV_SPLIT
 #define VIS_DP_NV_SPLIT 2.4       // packed-byte kernel: 4 vertical-pass warps from this vertical scale on, 6 below
 #endif
@@ -513,7 +516,7 @@ int vis_sched_build(int src_h, int src_w, int dst_h, int dst_w, int64_t src_pitc
             return over * 20 > dst_h;                      // more than 5 % of the windows
         };
         chunk_rows = 0;
-        for (int cr = kChunk; cr >= 24 && !chunk_rows; cr -= 4)
+        for (int cr = kChunk; cr >= VIS_MMA_MIN_CHUNK_ROWS && !chunk_rows; cr -= 4)
             if (!crowded(cr)) chunk_rows = cr;
         if (!chunk_rows) { mma = false; chunk_rows = kChunk; }
     }
