@@ -366,3 +366,24 @@ def test_kernel_family_is_a_property_of_the_geometry():
                 assert rc == N.VIS_OK
                 seen.add((int(sc["head"]["dp_words"]), int(sc["head"]["mma_ks"]), int(sc["head"]["chunk_rows"])))
         assert len(seen) == 1, (sh, swd, seen)
+
+
+def test_mma_declines_windows_wider_than_three_k_steps():
+    """A tile of 16 output columns whose window spans more than 96 input pixels (scale ~5 and up with LANCZOS / ~6 with
+    BICUBIC) stays with the packed-byte kernel: vis_sched_build answers the tensor-path request with an IDP.4A schedule."""
+    seen = {}
+    for scale_w, filt in ((4.6, N.FILTER_LANCZOS), (5.3, N.FILTER_LANCZOS), (5.0, N.FILTER_BICUBIC), (7.4, N.FILTER_BICUBIC)):
+        dw, dh = 256, 128
+        sw_, sh_ = int(dw * scale_w) // 16 * 16, int(dh * 3.0)
+        rc, sc, ht, _ = build(sh_, sw_, dh, dw, sw_ * 3, 2, filt, N.SCHED_OUT_U8 | N.SCHED_FLAG_MMA)
+        if rc != N.VIS_OK:
+            continue                                   # more than 33 taps: generic passes
+        h = sc["head"]
+        span = max(int(ht.bounds[min(x + 15, dw - 1), 0] + ht.bounds[min(x + 15, dw - 1), 1] - (ht.bounds[x, 0] & ~3))
+                   for x in range(0, dw, 4))
+        seen[(scale_w, filt)] = (int(h["mma_ks"]), span)
+        assert h["dp_words"] >= 4
+        assert (h["mma_ks"] > 0) == (span <= 96), (scale_w, filt, h, span)
+        if h["mma_ks"]:
+            assert h["mma_ks"] == (span + 31) // 32
+    assert any(v[0] == 0 for v in seen.values()) and any(v[0] > 0 for v in seen.values()), seen
