@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VIS_B200_ABI_VERSION 19
+#define VIS_B200_ABI_VERSION 20
 
 /* status codes */
 #define VIS_OK            0

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_header():
     for name in names:
         assert hasattr(L, name), f"{name} declared in include/vis_b200.h but not exported"
     assert set(names) == set(N.EXPORTS), "binding list and header disagree"
-    assert N.lib().vis_abi_version() == 19
+    assert N.lib().vis_abi_version() == 20
 
 
 def test_struct_layouts_match_header():
