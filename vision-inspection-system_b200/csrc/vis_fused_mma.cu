@@ -60,6 +60,9 @@ constexpr int kSWarps = VIS_MMA_SWARPS;
 __host__ __device__ constexpr int h_warps(int ks) { return ks <= 2 ? VIS_MMA_HWARPS : VIS_MMA_HWARPS3; }
 __host__ __device__ constexpr int v_warps(int ks) { return ks <= 2 ? VIS_MMA_VWARPS : VIS_MMA_VWARPS3; }
 __host__ __device__ constexpr int n_threads(int ks) { return (h_warps(ks) + v_warps(ks) + kSWarps + 1) * 32; }
+#ifndef VIS_MMA_HOIST3
+#define VIS_MMA_HOIST3 1           // three k-step kernels too: strips of one tile per H warp, coefficient fragments gathered once per item (0: 256-column strips; 80.3 k vs 84.0 k images/s on the 4K -> 1024 thumbnail)
+#endif
 #ifndef VIS_MMA_VPIPE
 #define VIS_MMA_VPIPE 0            // A/B: 1 = software-pipelined vertical tile loop (tile i's IMMA between the pieces of tile
                                    // i-1's epilogue): 85.8 k -> 77.1 k images/s on 4K, rejected (profiles/r02_mma_ab_log.txt, step 15)
@@ -266,7 +269,7 @@ k_fused_mma(const __grid_constant__ VisSched sc, const FramePtrs* __restrict__ f
             const int n_tiles = (sw + 15) >> 4;
             const int n_chunks = (G.r_end - G.r_first + CR - 1) / CR;
             const uint32_t hrec0 = smem_u32(smem + L.off_hrec + (sl & 1) * L.hrec_slot);
-            const bool one_tile = KS <= 2 && n_tiles <= kHWarps;      // (three k-steps of limbs are too many registers to keep)
+            const bool one_tile = (KS <= 2 || VIS_MMA_HOIST3) && n_tiles <= kHWarps;   // (three k-steps: 36 registers of limbs to keep)
             uint32_t a[KS][3][4];
             int kw = 0;
 #pragma unroll
@@ -638,7 +641,7 @@ int launch_mma(const VisSched& sc, const void* frames, int n_frames, const Layou
 namespace visf {
 
 // up to two k-steps: one tile of 16 columns per horizontal-pass warp, whose coefficient fragments then stay in registers
-int mma_max_strip_w(int ksteps) { return ksteps <= 2 ? 16 * h_warps(2) : 256; }
+int mma_max_strip_w(int ksteps) { return ksteps <= 2 ? 16 * h_warps(2) : VIS_MMA_HOIST3 ? 16 * h_warps(3) : 256; }
 int mma_max_ksteps() { return 3; }
 int mma_layout_bytes(int stage_pitch, int strip_w, int words) { return make_layout_m(stage_pitch, strip_w, words).total; }
 int mma_record_stride(int words) { return rec_stride_mma(words); }
